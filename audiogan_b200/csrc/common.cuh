@@ -1,0 +1,64 @@
+// Shared helpers for the audiogan_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/audiogan_b200.h"
+
+namespace ag {
+
+void set_error(const char* fmt, ...);
+
+#define AG_CHECK_ARG(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      ag::set_error(__VA_ARGS__);               \
+      return AG_EINVAL;                         \
+    }                                           \
+  } while (0)
+
+#define AG_CUDA(call)                                                                 \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      ag::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return AG_ECUDA;                                                                \
+    }                                                                                 \
+  } while (0)
+
+#define AG_LAUNCH_CHECK() AG_CUDA(cudaGetLastError())
+
+int sm_count();
+int smem_optin();
+
+__device__ __forceinline__ float ld_any(const void* p, int64_t i, int dtype) {
+  return dtype ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
+               : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void st_any(void* p, int64_t i, float v, int dtype) {
+  if (dtype) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
+  else reinterpret_cast<float*>(p)[i] = v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Block-wide sum; `red` is >= 32 floats of shared memory.  All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) v = warp_sum(v);
+  if (threadIdx.x == 0) red[0] = v;
+  __syncthreads();
+  return red[0];
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+}  // namespace ag

@@ -1,0 +1,255 @@
+// HBM-bound kernels: weight-norm (multi-tensor), gather/pack, framing+noise, BCE, small reductions.
+#include "common.cuh"
+
+namespace ag {
+
+// ---------------------------------------------------------------- weight norm (audiogan.py:77-80)
+// One block per (tensor,row).  Finds its tensor by binary search over row_start.
+__device__ __forceinline__ int find_tensor(const int32_t* row_start, int nt, int row) {
+  int lo = 0, hi = nt - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (row_start[mid] <= row) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(128) wn_fwd_kernel(const ag_wn_entry* __restrict__ table,
+                                                     const int32_t* __restrict__ row_start, int nt) {
+  __shared__ float red[32];
+  const int row_g = blockIdx.x;
+  const int ti = find_tensor(row_start, nt, row_g);
+  const ag_wn_entry e = table[ti];
+  const int row = row_g - row_start[ti];
+  const int64_t base = (int64_t)row * e.cols;
+  if (e.kind == 1) {
+    for (int c = threadIdx.x; c < e.cols; c += blockDim.x) e.w[base + c] = e.v[base + c];
+    return;
+  }
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < e.cols; c += blockDim.x) { float x = e.v[base + c]; ss += x * x; }
+  ss = block_sum(ss, red);
+  const float nrm = sqrtf(ss);
+  const float sc = e.g[row] / nrm;
+  if (threadIdx.x == 0) e.norm[row] = nrm;
+  for (int c = threadIdx.x; c < e.cols; c += blockDim.x) e.w[base + c] = e.v[base + c] * sc;
+}
+
+// dg = <dw,v>/||v|| ; dv = g/||v|| * (dw - v*<dw,v>/||v||^2)
+__global__ void __launch_bounds__(128) wn_bwd_kernel(const ag_wn_entry* __restrict__ table,
+                                                     const int32_t* __restrict__ row_start, int nt) {
+  __shared__ float red[32];
+  const int row_g = blockIdx.x;
+  const int ti = find_tensor(row_start, nt, row_g);
+  const ag_wn_entry e = table[ti];
+  const int row = row_g - row_start[ti];
+  const int64_t base = (int64_t)row * e.cols;
+  if (e.kind == 1) {
+    for (int c = threadIdx.x; c < e.cols; c += blockDim.x) e.dv[base + c] = e.dw[base + c];
+    return;
+  }
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < e.cols; c += blockDim.x) dot += e.dw[base + c] * e.v[base + c];
+  dot = block_sum(dot, red);
+  const float nrm = e.norm[row], g = e.g[row];
+  const float inv = 1.f / nrm;
+  if (threadIdx.x == 0) e.dg[row] = dot * inv;
+  const float sc = g * inv, k = dot * inv * inv;
+  for (int c = threadIdx.x; c < e.cols; c += blockDim.x)
+    e.dv[base + c] = sc * (e.dw[base + c] - e.v[base + c] * k);
+}
+
+__global__ void gather_kernel(void* __restrict__ dst, const float* __restrict__ src,
+                              const int32_t* __restrict__ idx, int64_t n, int dtype) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t j = idx[i];
+    st_any(dst, i, j >= 0 ? src[j] : 0.f, dtype);
+  }
+}
+
+// ---------------------------------------------------------------- framing + noise
+__global__ void frame_noise_kernel(void* __restrict__ dst, int64_t dst_ld, int64_t pad_l,
+                                   const float* __restrict__ src, int64_t src_ld,
+                                   const float* __restrict__ noise, float nscale, int64_t B, int64_t L, int dtype) {
+  const int64_t total = B * dst_ld;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / dst_ld, j = i - b * dst_ld - pad_l;
+    float v = 0.f;
+    if (j >= 0 && j < L) {
+      v = src[b * src_ld + j];
+      if (noise) v += nscale * noise[b * L + j];
+    }
+    st_any(dst, i, v, dtype);
+  }
+}
+
+// ---------------------------------------------------------------- BCE (audiogan.py:187-197)
+__device__ __forceinline__ float bce_elem(float x, float t) {
+  const float mx = fmaxf(-x, 0.f);
+  return x - x * t + mx + logf(expf(-mx) + expf(-x - mx));
+}
+__global__ void __launch_bounds__(256) bce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ tgt,
+                                                      const float* __restrict__ w, float* __restrict__ loss, int64_t T) {
+  __shared__ float red[32];
+  const int64_t b = blockIdx.x;
+  float acc = 0.f;
+  for (int64_t t = threadIdx.x; t < T; t += blockDim.x) {
+    const int64_t i = b * T + t;
+    float l = bce_elem(x[i], tgt[i]);
+    if (w) l *= w[i];
+    acc += l;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) loss[b] = acc;
+}
+__global__ void bce_bwd_kernel(const float* __restrict__ x, const float* __restrict__ tgt, const float* __restrict__ w,
+                               const float* __restrict__ gout, float* __restrict__ dx, int64_t B, int64_t T) {
+  const int64_t n = B * T;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = gout[i / T] * (sigmoidf_(x[i]) - tgt[i]);
+    if (w) g *= w[i];
+    dx[i] = g;
+  }
+}
+__global__ void __launch_bounds__(256) bce_const_kernel(const float* __restrict__ x, int64_t ld, const int32_t* __restrict__ len,
+                                                        float target, float sign, float* __restrict__ loss_mean,
+                                                        float* __restrict__ loss_ps, float* __restrict__ dlogits,
+                                                        float* __restrict__ stats, int64_t B, int64_t T) {
+  __shared__ float red[32];
+  const int64_t b = blockIdx.x;
+  const int n = len[b];
+  const float invn = 1.f / (float)n, invnb = invn / (float)B;
+  float acc = 0.f, corr = 0.f;
+  for (int64_t t = threadIdx.x; t < T; t += blockDim.x) {
+    const float xv = x[b * ld + t];
+    const bool in = t < n;
+    if (in) { acc += bce_elem(xv, target); corr += (sign * xv > 0.f) ? 1.f : 0.f; }
+    if (dlogits) dlogits[b * ld + t] = in ? (sigmoidf_(xv) - target) * invnb : 0.f;
+  }
+  acc = block_sum(acc, red);
+  corr = block_sum(corr, red);
+  if (threadIdx.x == 0) {
+    if (loss_ps) loss_ps[b] = acc * invn;
+    if (loss_mean) atomicAdd(loss_mean, acc * invnb);
+    if (stats) { atomicAdd(stats, corr); atomicAdd(stats + 1, (float)(n < T ? n : (int)T)); }
+  }
+}
+
+// ---------------------------------------------------------------- small reductions / layout
+__global__ void rowgroup_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t T, int64_t N) {
+  const int64_t b = blockIdx.y;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* p = in + b * T * N + n;
+  float acc = 0.f;
+  for (int64_t t = 0; t < T; ++t) acc += p[t * N];
+  out[b * N + n] = acc;
+}
+
+// src [B,C,T] <-> dst channel-last with strides; 32x32 smem tile transpose.
+__global__ void transpose_bct_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t C, int64_t T,
+                                     int64_t dst_bs, int64_t dst_rs, int to_cl) {
+  __shared__ float tile[32][33];
+  const int64_t b = blockIdx.z;
+  const int64_t c0 = (int64_t)blockIdx.y * 32, t0 = (int64_t)blockIdx.x * 32;
+  const float* s = src + b * C * T;
+  float* d = dst + b * dst_bs;
+  if (to_cl) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int64_t c = c0 + i, t = t0 + threadIdx.x;
+      tile[i][threadIdx.x] = (c < C && t < T) ? s[c * T + t] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int64_t t = t0 + i, c = c0 + threadIdx.x;
+      if (c < C && t < T) d[t * dst_rs + c] = tile[threadIdx.x][i];
+    }
+  } else {  // channel-last (dst arg is the strided one) -> [B,C,T] written to src arg
+    float* so = const_cast<float*>(s);
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int64_t t = t0 + i, c = c0 + threadIdx.x;
+      tile[i][threadIdx.x] = (c < C && t < T) ? d[t * dst_rs + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int64_t c = c0 + i, t = t0 + threadIdx.x;
+      if (c < C && t < T) so[c * T + t] = tile[threadIdx.x][i];
+    }
+  }
+}
+
+static inline int grid_for(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace ag
+
+using namespace ag;
+extern "C" {
+
+int ag_wn_fwd_multi(const ag_wn_entry* table, const int32_t* row_start, int32_t nt, int32_t total_rows, void* stream) {
+  AG_CHECK_ARG(table && row_start && nt > 0 && total_rows > 0, "ag_wn_fwd_multi: bad args");
+  wn_fwd_kernel<<<total_rows, 128, 0, (cudaStream_t)stream>>>(table, row_start, nt);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_wn_bwd_multi(const ag_wn_entry* table, const int32_t* row_start, int32_t nt, int32_t total_rows, void* stream) {
+  AG_CHECK_ARG(table && row_start && nt > 0 && total_rows > 0, "ag_wn_bwd_multi: bad args");
+  wn_bwd_kernel<<<total_rows, 128, 0, (cudaStream_t)stream>>>(table, row_start, nt);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_gather(void* dst, const float* src, const int32_t* idx, int64_t n, int32_t dtype, void* stream) {
+  AG_CHECK_ARG(dst && src && idx && n >= 0, "ag_gather: bad args");
+  if (n == 0) return AG_OK;
+  gather_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dst, src, idx, n, dtype);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_frame_noise(void* dst, int64_t dst_ld, int64_t pad_l, const float* src, int64_t src_ld, const float* noise,
+                   float nscale, int64_t B, int64_t L, int32_t dtype, void* stream) {
+  AG_CHECK_ARG(dst && src && B > 0 && L > 0 && dst_ld >= pad_l + L, "ag_frame_noise: bad args");
+  frame_noise_kernel<<<grid_for(B * dst_ld, 256), 256, 0, (cudaStream_t)stream>>>(dst, dst_ld, pad_l, src, src_ld, noise,
+                                                                                 nscale, B, L, dtype);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_bce_fwd(const float* x, const float* tgt, const float* w, float* loss, int64_t B, int64_t T, void* stream) {
+  AG_CHECK_ARG(x && tgt && loss && B > 0 && T > 0, "ag_bce_fwd: bad args");
+  bce_fwd_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(x, tgt, w, loss, T);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_bce_bwd(const float* x, const float* tgt, const float* w, const float* gout, float* dx, int64_t B, int64_t T,
+               void* stream) {
+  AG_CHECK_ARG(x && tgt && gout && dx && B > 0 && T > 0, "ag_bce_bwd: bad args");
+  bce_bwd_kernel<<<grid_for(B * T, 256), 256, 0, (cudaStream_t)stream>>>(x, tgt, w, gout, dx, B, T);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_bce_const_fused(const float* x, int64_t ld, const int32_t* len, float target, float sign, float* loss_mean,
+                       float* loss_ps, float* dlogits, float* stats, int64_t B, int64_t T, void* stream) {
+  AG_CHECK_ARG(x && len && B > 0 && T > 0 && ld >= T, "ag_bce_const_fused: bad args");
+  bce_const_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(x, ld, len, target, sign, loss_mean, loss_ps, dlogits,
+                                                                  stats, B, T);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_rowgroup_sum(const float* in, float* out, int64_t B, int64_t T, int64_t N, void* stream) {
+  AG_CHECK_ARG(in && out && B > 0 && T > 0 && N > 0, "ag_rowgroup_sum: bad args");
+  dim3 grid((unsigned)((N + 127) / 128), (unsigned)B);
+  rowgroup_sum_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(in, out, T, N);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_transpose_bct(const float* src, float* dst, int64_t B, int64_t C, int64_t T, int64_t dst_bs, int64_t dst_rs,
+                     int32_t to_cl, void* stream) {
+  AG_CHECK_ARG(src && dst && B > 0 && C > 0 && T > 0 && B < 65536, "ag_transpose_bct: bad args");
+  dim3 grid((unsigned)((T + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)B);
+  transpose_bct_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, dst, C, T, dst_bs, dst_rs, to_cl);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+}

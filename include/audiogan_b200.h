@@ -1,0 +1,199 @@
+/*
+ * audiogan_b200 -- C ABI of the B200 (sm_100a) kernels behind the audiogan GAN training step.
+ *
+ * The reference (BarclayII/audiogan) has no FFI of its own: its hot path is Python calling
+ * torch.nn modules (audiogan.py).  Each entry point below replaces the PyTorch call site(s)
+ * cited next to it (file:line in /root/reference); INTEGRATION.md shows the ctypes stubs a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named h_*;
+ *   - the library never allocates, frees or retains caller memory (workspaces are passed in);
+ *   - every call launches on the cudaStream_t passed as `stream` (void* here) and returns
+ *     0 on success or a negative AG_E* code; nothing throws or exits across the ABI;
+ *     ag_last_error_string() describes the last failure on the calling thread;
+ *   - fp32 unless a parameter says otherwise; sizes are int64_t.
+ */
+#ifndef AUDIOGAN_B200_H
+#define AUDIOGAN_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AG_OK 0
+#define AG_EINVAL (-1)   /* bad argument / unsupported shape */
+#define AG_ECUDA (-2)    /* CUDA runtime error (see ag_last_error_string) */
+#define AG_ENOTSUP (-3)  /* device is not sm_100 / feature not available */
+
+int ag_version(void);
+const char* ag_last_error_string(void);
+/* cudaStreamSynchronize + cudaGetLastError: surfaces asynchronous faults. */
+int ag_sync_check(void* stream);
+/* SM count, max opt-in shared memory per block, compute capability major*10+minor. */
+int ag_device_info(int* sm_count, int* smem_optin, int* cc);
+
+/* ------------------------------------------------------------------------------------------
+ * View-GEMM: one engine for Linear / Conv1d / ConvTranspose1d forward, data-gradient and
+ * weight-gradient.  Replaces F.linear (audiogan.py:260, :409-410, :509-511), NN.Conv1d
+ * (:272, :406, :490) and NN.ConvTranspose1d (:275) plus their autograd backward, with the bias,
+ * LeakyReLU (:261, :277, :532), skip (:264, :282) and length mask (:534) fused in the epilogue.
+ *
+ * Operands are *views*: a row index m splits into (batch = m / rpb, t = m % rpb) and a column
+ * index into (outer = k / kin, inner = k % kin) so that an im2col matrix of a channel-last
+ * activation is addressed in place (no im2col copy):
+ *   A(m,k)  at  A + batch*a_bs + t*a_rs + outer*a_k1s + inner
+ *   B(n,k)  at  B + n*ldb + k                                  (packed weights, K contiguous)
+ *   C(m,n)  at  C + batch*c_bs + t*c_rs + (n / c_nin)*c_n1s + n % c_nin
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ag_gemm_desc {
+  int64_t M, N, K;
+  const void* A; int64_t a_rpb, a_bs, a_rs, a_kin, a_k1s;
+  const void* B; int64_t ldb;
+  void* C;       int64_t c_rpb, c_bs, c_rs, c_nin, c_n1s;
+  /* epilogue, applied in this order (null pointer / zero flag = skipped) */
+  float alpha;                  /* acc *= alpha (0 means 1) */
+  const float* bias;  int64_t bias_mod;     /* += bias[n % bias_mod] */
+  const float* rowbias; int64_t rowbias_ld; /* += rowbias[batch*rowbias_ld + n] */
+  const void* skip;             /* += skip[C-addressing]   (skip == C gives C += ...) */
+  int32_t act;                  /* 1: LeakyReLU(slope) */
+  const void* dact;             /* *= (dact[C-addressing] > 0 ? 1 : slope)  (LeakyReLU') */
+  float slope;
+  const int32_t* mask_len;      /* zero where t*mask_tmul + (n/c_nin)*mask_n1mul + mask_toff >= mask_len[batch] */
+  int64_t mask_tmul, mask_n1mul, mask_toff;
+  int32_t a_dtype, b_dtype, c_dtype, aux_dtype;   /* 0 = fp32, 1 = bf16 (skip/dact use aux_dtype) */
+  int32_t reserved;
+} ag_gemm_desc;
+
+/* C = epilogue(A . B^T).  fp32 FFMA path ("fp32 mode", <=1e-5 parity). */
+int ag_gemm_nt_f32(const ag_gemm_desc* d, void* stream);
+/* Weight gradient: C[n, k] += sum_m Y(m,n) * A(m,k), C plain [N, ldc] fp32, accumulated with
+ * atomics (zero it first).  Y uses the C-addressing fields of the descriptor (d->C = Y, read
+ * only), the result goes to `dw`.  If `ones_col` != 0, column K of dw receives sum_m Y(m,n)
+ * (the bias gradient). */
+int ag_gemm_tn_f32(const ag_gemm_desc* d, float* dw, int64_t ldw, int32_t ones_col, void* stream);
+
+/* bf16 tcgen05 / TMA path ("bf16 mode", <=2e-2 parity): same descriptor, a_dtype = b_dtype = 1,
+ * fp32 accumulation in TMEM.  Requires 16-byte aligned row strides. */
+int ag_gemm_nt_tc(const ag_gemm_desc* d, void* stream);
+int ag_gemm_tn_tc(const ag_gemm_desc* d, float* dw, int64_t ldw, int32_t ones_col, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Persistent recurrent kernels (cooperative launch, weights resident in shared memory).
+ * Replaces NN.LSTMCell + proj + stopper + stop sampling per frame (audiogan.py:437-460) and
+ * NN.LSTM(bidirectional) under dynamic_rnn (:214-229, :498-503, :543), and their backward.
+ * Gate order i,f,g,o.  Layouts (fp32):
+ *   pre    [B, T, ndir*4H]   input projections + both biases (hoisted GEMM)
+ *   whh    [ndir, 4H, H]
+ *   hbuf   [B, T+2, ndir*H]  row t+1 holds h_t; rows 0 and T+1 stay zero (the caller zeroes them)
+ *   gates  [B, T, ndir*4H]   post-activation i,f,g,o (saved for backward)
+ *   cbuf   [B, T, ndir*H]    cell state c_t (saved for backward)
+ *   len    [B] int32 or NULL (all T): steps t >= len[b] leave the state untouched and emit 0;
+ *          direction 1 runs t = T-1 .. 0, i.e. starts at each sample's own last frame.
+ * Feedback variant (generator, ndir == 1): gates also get wx[4H,F] . x_{t-1} where
+ *   x_t = tanh(wp[F,H] . h_t + bp), logit_t = ws[H] . h_t + bs, written to
+ *   xbuf [B, T+1, F] (row t+1 holds x_t, row 0 zero) and sbuf [B, T].
+ *   Stop sampling: stop[b,t] = u[b,t] < sigmoid(logit) (u NULL: never), glen[b] = frames until
+ *   the first stop inclusive, *t_end = first step count at which every sample has stopped (or T).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ag_lstm_desc {
+  int32_t B, T, H, ndir, F;        /* F = 0: no feedback */
+  int32_t reserved;
+  const float* pre; const float* whh;
+  float* hbuf; float* gates; float* cbuf;
+  const int32_t* len;
+  /* feedback (F > 0) */
+  const float* wx; const float* wp; const float* bp; const float* ws; const float* bs;
+  float* xbuf; float* sbuf;
+  const float* u; int32_t* stop; int32_t* glen; int32_t* t_end;
+  /* backward only */
+  const float* dh_ext;   /* [B, T, ndir*H] grad wrt emitted h (NULL = 0) */
+  const float* dx_ext;   /* [B, T, F] grad wrt emitted frames (feedback) */
+  const float* ds_ext;   /* [B, T] grad wrt stop logits (NULL = 0) */
+  float* dgates;         /* [B, T, ndir*4H] out: grad wrt pre-activation gates (= d pre) */
+  float* dpx;            /* [B, T, F+1] out: grad wrt proj pre-activation, col F = ds */
+  const float* whh_t;    /* [ndir, H, 4H]  transposed copies for the backward pass */
+  const float* wx_t;     /* [F, 4H] */
+  const float* wp_t;     /* [H, F+1]  (col F = ws) */
+  unsigned int* barrier; /* >= 8 zeroed uint32 in device memory (grid barrier state) */
+} ag_lstm_desc;
+
+int ag_lstm_fwd(const ag_lstm_desc* d, void* stream);
+int ag_lstm_bwd(const ag_lstm_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight-norm (audiogan.py:77-80 -> torch.nn.utils.weight_norm dim 0), multi-tensor.
+ * One table entry per parameter tensor; kind 0: w = g*v/||v||_row, kind 1: w = v (plain
+ * parameter, e.g. Discriminator.rnn).  The table and row_start live in DEVICE memory.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ag_wn_entry {
+  const float* v; const float* g;   /* g unused for kind 1 */
+  float* w;                         /* forward out [rows*cols] */
+  float* norm;                      /* [rows] forward out / backward in */
+  const float* dw; float* dv; float* dg;   /* backward */
+  int32_t rows, cols, kind, reserved;
+} ag_wn_entry;
+int ag_wn_fwd_multi(const ag_wn_entry* table, const int32_t* row_start, int32_t ntensors,
+                    int32_t total_rows, void* stream);
+int ag_wn_bwd_multi(const ag_wn_entry* table, const int32_t* row_start, int32_t ntensors,
+                    int32_t total_rows, void* stream);
+
+/* dst[i] = idx[i] >= 0 ? src[idx[i]] : 0 ; dst_dtype 0 fp32 / 1 bf16.  Packs canonical weights
+ * into GEMM operand layouts and un-packs weight gradients (index maps built once on the host). */
+int ag_gather(void* dst, const float* src, const int32_t* idx, int64_t n, int32_t dst_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Waveform framing + noise (audiogan.py:462-464, :724-725, :750-751, :842-843):
+ * dst[b, pad_l + i] = src[b*src_ld + i] + noise_scale*noise[b*L + i] (noise may be NULL) for i < L,
+ * pads [0,pad_l) and [pad_l+L, dst_ld) zeroed.  dst_dtype 0/1.
+ * ------------------------------------------------------------------------------------------ */
+int ag_frame_noise(void* dst, int64_t dst_ld, int64_t pad_l, const float* src, int64_t src_ld,
+                   const float* noise, float noise_scale, int64_t B, int64_t L, int32_t dst_dtype, void* stream);
+
+/* Masked BCE-with-logits per sample (audiogan.py:187-197): loss[b] = sum_t w*(x - x*tgt + max(-x,0)
+ * + log(exp(-max) + exp(-x-max))).  weight may be NULL (=1).  Backward: dx = gout[b]*w*(sigmoid(x)-tgt). */
+int ag_bce_fwd(const float* x, const float* tgt, const float* w, float* loss, int64_t B, int64_t T, void* stream);
+int ag_bce_bwd(const float* x, const float* tgt, const float* w, const float* gout, float* dx,
+               int64_t B, int64_t T, void* stream);
+/* Fused training-loop form (audiogan.py:739-740, :766, :780, :864, :897): per-sample masked BCE
+ * against a constant target, / len[b], mean over B accumulated into *loss_mean (zero it first);
+ * dlogits = (sigmoid(x)-target)/(len[b]*B) inside the mask, 0 outside.  Also counts
+ * correct = sum(mask * (sign*x > 0)) and num = sum(mask) into stats[0..1] (:741-742, :781-782). */
+int ag_bce_const_fused(const float* x, int64_t ld, const int32_t* len, float target, float sign,
+                       float* loss_mean, float* loss_ps, float* dlogits, float* stats,
+                       int64_t B, int64_t T, void* stream);
+
+/* out[b, n] = sum_t in[b, t, n] */
+int ag_rowgroup_sum(const float* in, float* out, int64_t B, int64_t T, int64_t N, void* stream);
+/* dst[b, t, c] (channel-last, row stride dst_rs, batch stride dst_bs) <-> src[b, c, t] */
+int ag_transpose_bct(const float* src, float* dst, int64_t B, int64_t C, int64_t T,
+                     int64_t dst_bs, int64_t dst_rs, int32_t to_channel_last, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-tensor optimizer with the reference's per-tensor clip (audiogan.py:232-253,
+ * :693-694, :786-788, :909-921).  Table entries in DEVICE memory.
+ *   pass 1 (ag_mt_sqnorm): sqnorm[i] = sum g^2, flags[0] |= any NaN, flags[1] |= any |g| > 1e5
+ *   pass 2 (ag_mt_rmsprop / ag_mt_adam): g' = g * min(1, clip/||g||) (clip <= 0: none), then
+ *     RMSprop: sq = alpha*sq + (1-alpha)*g'^2 ; p -= lr * g' / (sqrt(sq) + eps)
+ *     Adam   : m,v moments with bias correction from `step`.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ag_mt_entry {
+  float* p; const float* g; float* s1; float* s2;   /* s1 = sq (RMSprop) / m (Adam); s2 = v (Adam) */
+  int64_t n;
+} ag_mt_entry;
+int ag_mt_sqnorm(const ag_mt_entry* table, const int32_t* chunk_tensor, const int64_t* chunk_off,
+                 int32_t nchunks, int32_t chunk, float* sqnorm, int32_t* flags, void* stream);
+int ag_mt_rmsprop(const ag_mt_entry* table, const int32_t* chunk_tensor, const int64_t* chunk_off,
+                  int32_t nchunks, int32_t chunk, const float* sqnorm, float clip, float gscale,
+                  float lr, float alpha, float eps, void* stream);
+int ag_mt_adam(const ag_mt_entry* table, const int32_t* chunk_tensor, const int64_t* chunk_off,
+               int32_t nchunks, int32_t chunk, const float* sqnorm, float clip, float gscale,
+               float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIOGAN_B200_H */
