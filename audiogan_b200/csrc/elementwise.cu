@@ -135,6 +135,62 @@ __global__ void __launch_bounds__(256) bce_const_kernel(const float* __restrict_
   }
 }
 
+
+// ---------------------------------------------------------------- activation-gradient assembly
+__global__ void ew_grad_kernel(const ag_ew_desc d) {
+  const int64_t Tp = d.pad_l + d.T + d.pad_r;
+  const int64_t total = d.B * Tp * d.C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % d.C, r = (i / d.C) % Tp, b = i / (d.C * Tp);
+    const int64_t t = r - d.pad_l;
+    float v = 0.f;
+    if (t >= 0 && t < d.T && (!d.len || t < d.len[b])) {
+      if (d.g1) v += d.g1[b * d.g1_bs + t * d.g1_rs + c * d.g1_cs];
+      if (d.g2) v += d.g2[b * d.g2_bs + t * d.g2_rs + c * d.g2_cs];
+      if (d.act) v *= (d.act[b * d.a_bs + t * d.a_rs + c] > 0.f) ? 1.f : d.slope;
+      if (d.acc) d.acc[b * d.acc_bs + t * d.acc_rs + c] += v;
+    }
+    if (d.out) d.out[i] = v;
+  }
+}
+
+// out[c] += sum over rows; block = 32 columns x 8 row lanes, grid.y splits the rows.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ in, int64_t bs, int64_t rs, int64_t T,
+                                                     int64_t M, int64_t C, float* __restrict__ out, int64_t rows_per) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + cx;
+  const int64_t m0 = (int64_t)blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
+  float acc = 0.f;
+  if (c < C)
+    for (int64_t m = m0 + ry; m < m1; m += 8) {
+      const int64_t b = m / T;
+      acc += in[b * bs + (m - b * T) * rs + c];
+    }
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += red[i][cx];
+    atomicAdd(&out[c], v);
+  }
+}
+
+
+// generic strided 3-D copy / accumulate: dst[b,t,c] (+)= src[b,t,c]
+__global__ void copy3d_kernel(float* __restrict__ dst, int64_t d_bs, int64_t d_rs, int64_t d_cs,
+                              const float* __restrict__ src, int64_t s_bs, int64_t s_rs, int64_t s_cs,
+                              int64_t B, int64_t T, int64_t Cn, int accumulate) {
+  const int64_t total = B * T * Cn;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % Cn, t = (i / Cn) % T, b = i / (Cn * T);
+    const float v = src[b * s_bs + t * s_rs + c * s_cs];
+    float* q = dst + b * d_bs + t * d_rs + c * d_cs;
+    *q = accumulate ? (*q + v) : v;
+  }
+}
+
 // ---------------------------------------------------------------- small reductions / layout
 __global__ void rowgroup_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t T, int64_t N) {
   const int64_t b = blockIdx.y;
@@ -234,6 +290,34 @@ int ag_bce_const_fused(const float* x, int64_t ld, const int32_t* len, float tar
   AG_CHECK_ARG(x && len && B > 0 && T > 0 && ld >= T, "ag_bce_const_fused: bad args");
   bce_const_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(x, ld, len, target, sign, loss_mean, loss_ps, dlogits,
                                                                   stats, B, T);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_ew_grad(const ag_ew_desc* d, void* stream) {
+  AG_CHECK_ARG(d && d->B > 0 && d->T > 0 && d->C > 0 && (d->out || d->acc), "ag_ew_grad: bad args");
+  const int64_t total = d->B * (d->pad_l + d->T + d->pad_r) * d->C;
+  ew_grad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*d);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_colsum(const float* in, int64_t bs, int64_t rs, int64_t B, int64_t T, int64_t C, float* out, void* stream) {
+  AG_CHECK_ARG(in && out && B > 0 && T > 0 && C > 0, "ag_colsum: bad args");
+  const int64_t M = B * T;
+  const int64_t gx = (C + 31) / 32;
+  int64_t gy = (int64_t)sm_count() * 8 / gx;
+  if (gy < 1) gy = 1;
+  int64_t rows_per = (M + gy - 1) / gy;
+  if (rows_per < 64) rows_per = 64;
+  gy = (M + rows_per - 1) / rows_per;
+  colsum_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(in, bs, rs, T, M, C, out, rows_per);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_copy3d(float* dst, int64_t d_bs, int64_t d_rs, int64_t d_cs, const float* src, int64_t s_bs, int64_t s_rs,
+              int64_t s_cs, int64_t B, int64_t T, int64_t Cn, int32_t accumulate, void* stream) {
+  AG_CHECK_ARG(dst && src && B > 0 && T > 0 && Cn > 0, "ag_copy3d: bad args");
+  copy3d_kernel<<<grid_for(B * T * Cn, 256), 256, 0, (cudaStream_t)stream>>>(dst, d_bs, d_rs, d_cs, src, s_bs, s_rs, s_cs, B, T,
+                                                                            Cn, accumulate);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

@@ -128,7 +128,10 @@ __global__ void __launch_bounds__(NT_THREADS) gemm_nt_kernel(const ag_gemm_desc 
       if (d.skip) v += ld_any(d.skip, ci, d.aux_dtype);
       if (d.act == 1) v = v > 0.f ? v : v * d.slope;
       if (d.dact) v *= (ld_any(d.dact, ci, d.aux_dtype) > 0.f) ? 1.f : d.slope;
-      if (d.mask_len && (t * d.mask_tmul + n1 * d.mask_n1mul + d.mask_toff >= mlen)) v = 0.f;
+      if (d.mask_len) {
+        const int64_t pos = t * d.mask_tmul + n1 * d.mask_n1mul + d.mask_toff;
+        if (pos < 0 || pos >= mlen) v = 0.f;
+      }
       st_any(d.C, ci, v, d.c_dtype);
     }
   }

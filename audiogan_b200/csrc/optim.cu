@@ -101,6 +101,22 @@ __global__ void __launch_bounds__(256) mt_update_kernel(const ag_mt_entry* __res
   }
 }
 
+// In-place per-tensor clip (audiogan.py:243-253): g *= clip/||g|| where ||g|| > clip.
+__global__ void __launch_bounds__(256) mt_clip_kernel(const ag_mt_entry* __restrict__ table,
+                                                      const int32_t* __restrict__ chunk_tensor,
+                                                      const int64_t* __restrict__ chunk_off, int chunk,
+                                                      const float* __restrict__ sqnorm, float clip) {
+  const int ti = chunk_tensor[blockIdx.x];
+  const float nrm = sqrtf(sqnorm[ti]);
+  if (!(nrm > clip)) return;
+  const float sc = 1.f / (nrm / clip);
+  const int64_t off = chunk_off[blockIdx.x];
+  const ag_mt_entry e = table[ti];
+  const int64_t n = min((int64_t)chunk, e.n - off);
+  float* g = const_cast<float*>(e.g) + off;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) g[i] *= sc;
+}
+
 }  // namespace ag
 
 using namespace ag;
@@ -109,6 +125,13 @@ int ag_mt_sqnorm(const ag_mt_entry* table, const int32_t* ct, const int64_t* co,
                  float* sqnorm, int32_t* flags, void* stream) {
   AG_CHECK_ARG(table && ct && co && nchunks > 0 && chunk > 0 && sqnorm && flags, "ag_mt_sqnorm: bad args");
   mt_sqnorm_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(table, ct, co, chunk, sqnorm, flags);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_mt_clip(const ag_mt_entry* table, const int32_t* ct, const int64_t* co, int32_t nchunks, int32_t chunk,
+               const float* sqnorm, float clip, void* stream) {
+  AG_CHECK_ARG(table && ct && co && nchunks > 0 && chunk > 0 && sqnorm && clip > 0.f, "ag_mt_clip: bad args");
+  mt_clip_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(table, ct, co, chunk, sqnorm, clip);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

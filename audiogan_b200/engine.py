@@ -1,0 +1,379 @@
+"""autograd Functions that drive the sm_100a kernels for the generator and the discriminator.
+
+Three coarse Functions cover the whole hot path (plus plan._PackFn for the weights):
+  _GenFn       Generator.forward body  audiogan.py:428-468 (recurrence + frame assembly + conv stack)
+  _DiscCNNFn   Discriminator conv loop audiogan.py:527-536
+  _DiscTailFn  BiLSTM + residual + classifier audiogan.py:537-549
+Every arithmetic step is a call into libaudiogan_b200.so (kernels.py); torch is used for device
+memory, views and autograd bookkeeping only.
+"""
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import kernels as K
+from .plan import pack  # noqa: F401  (re-exported)
+
+GPAD = 8        # zero rows either side of the generator's dense channel-last buffer
+DPAD = 3        # zero rows either side of the discriminator's channel-last activations
+
+
+def _zeros(*shape, device):
+    return torch.zeros(*shape, device=device, dtype=torch.float32)
+
+
+def _empty(*shape, device):
+    return torch.empty(*shape, device=device, dtype=torch.float32)
+
+
+# =========================================================================================
+# Generator
+# =========================================================================================
+class _GenFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, struct, token, zc1, u_stop, early_exit_sync):
+        """zc1: (B, T, NZ+2) = [noise | conditioning | 1 | 1].  Returns (x (B, t*F), s (B, t), stop (B, t) int32,
+        glen (B,) int32)."""
+        dev = plan.device
+        B, Tcap, _ = zc1.shape
+        H, F, NZ, CT, FP = plan.H, plan.F, plan.NZ, plan.CT, plan.FP
+        zc1 = zc1.contiguous()
+        save = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        # hoisted input projection: pre = [z|c|1|1] . [W_z | b_ih | b_hh]^T      (audiogan.py:425-426, :439-440)
+        pre = _empty(B, Tcap, 4 * H, device=dev)
+        K.gemm_nt(B * Tcap, 4 * H, NZ + 2, zc1, (Tcap, Tcap * (NZ + 2), NZ + 2), plan.Poff("wz"), NZ + 2,
+                  pre, (Tcap, Tcap * 4 * H, 4 * H))
+        hbuf = _zeros(B, Tcap + 2, H, device=dev)
+        xbuf = _zeros(B, Tcap + 1, F, device=dev)
+        gates = _empty(B, Tcap, 4 * H, device=dev) if save else None
+        cbuf = _empty(B, Tcap, H, device=dev) if save else None
+        sbuf = _zeros(B, Tcap, device=dev)
+        stop = torch.zeros(B, Tcap, device=dev, dtype=torch.int32)
+        glen = torch.zeros(B, device=dev, dtype=torch.int32)
+        misc = torch.zeros(16, device=dev, dtype=torch.int32)          # [0:8] barrier, [8] t_end
+        u = u_stop.contiguous() if u_stop is not None else None
+        K.lstm_fwd(B=B, T=Tcap, Tcap=Tcap, H=H, ndir=1, F=F, pre=pre, w1=plan.Poff("w1"), w2=plan.Poff("w2"),
+                   b2=plan.Poff("b2"), hbuf=hbuf, gates=gates, cbuf=cbuf, xbuf=xbuf, sbuf=sbuf, u=u, stop=stop,
+                   glen=glen, t_end=(misc, 8), barrier=misc)
+        if u is not None and early_exit_sync:
+            T = int(misc[8].item())          # the one host sync per generator pass (audiogan.py:459-460)
+        else:
+            T = Tcap
+        L = T * F
+        Lp = L + 2 * GPAD
+        # frame assembly into channel 0 of the dense buffer (audiogan.py:462-464)
+        Xd = _empty(B, Lp, CT, device=dev)
+        Xd[:, :GPAD].zero_()
+        Xd[:, GPAD + L:].zero_()
+        K.copy3d((Xd, GPAD * CT), (Lp * CT, CT, 0), (xbuf, F), ((Tcap + 1) * F, 1, 0), B, L, 1)
+        hh = []
+        cin = 1
+        lenL = plan.const_len(B, L)
+        for li, (k, s, hid, out) in enumerate(struct):                       # audiogan.py:278-283, :465-467
+            p, pd, Lh = (k - 1) // 2, s // 2, L // s
+            Hh = _empty(B, Lh + 2, hid, device=dev)
+            Hh[:, 0].zero_()
+            Hh[:, Lh + 1].zero_()
+            K.gemm_nt(B * Lh, hid, k * cin, (Xd, (GPAD - p) * CT), (Lh, Lp * CT, s * CT, cin, CT),
+                      plan.Poff("c%d.w" % li), k * cin, (Hh, hid), (Lh, (Lh + 2) * hid, hid),
+                      bias=plan.Poff("c%d.b" % li), act=1)
+            skip = (Xd, (GPAD - pd) * CT + cin - out) if cin >= out else None
+            K.gemm_nt(B * (Lh + 1), s * out, 2 * hid, Hh, (Lh + 1, (Lh + 2) * hid, hid),
+                      plan.Poff("d%d.w" % li), 2 * hid, (Xd, (GPAD - pd) * CT + cin), (Lh + 1, Lp * CT, s * CT, out, CT),
+                      bias=plan.Poff("d%d.b" % li), bias_mod=out, skip=skip, act=1,
+                      mask_len=lenL, mask=(s, 1, -pd))
+            hh.append(Hh)
+            cin += out
+        xout = _empty(B, L, device=dev)
+        K.gemm_nt(B * L, 1, 3 * CT, (Xd, (GPAD - 1) * CT), (L, Lp * CT, CT), plan.Poff("f.w"), 3 * CT,
+                  xout, (L, L, 1), bias=plan.Poff("f.b"))
+        s_out = sbuf[:, :T]
+        if save:
+            ctx.plan, ctx.struct, ctx.dims = plan, struct, (B, T, Tcap, L)
+            ctx.bufs = (zc1, hbuf, xbuf, gates, cbuf, Xd, hh)
+        ctx.mark_non_differentiable(stop, glen)
+        ctx.set_materialize_grads(False)
+        return xout, s_out, stop[:, :T], glen
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gx, gs, _gstop, _glen):
+        plan, struct = ctx.plan, ctx.struct
+        B, T, Tcap, L = ctx.dims
+        zc1, hbuf, xbuf, gates, cbuf, Xd, hh = ctx.bufs
+        dev = plan.device
+        H, F, NZ, CT, FP = plan.H, plan.F, plan.NZ, plan.CT, plan.FP
+        Lp = L + 2 * GPAD
+        wgrad = ctx.needs_input_grad[2]
+        dx_ext = None
+        if gx is not None:
+            gx = gx.contiguous()
+            # ---- final conv (audiogan.py:403-407): data gradient into all CT channels, weight gradient
+            gyp = _empty(B, L + 2, device=dev)
+            K.frame_noise(gyp, L + 2, 1, gx, L, None, 0.0, B, L)
+            dXd = _empty(B, Lp, CT, device=dev)
+            K.gemm_nt(B * L, CT, 3, gyp, (L, L + 2, 1), plan.Poff("f.wg"), 3, (dXd, GPAD * CT), (L, Lp * CT, CT))
+            if wgrad:
+                K.gemm_tn(B * L, 1, 3 * CT, gx, (L, L, 1), (Xd, (GPAD - 1) * CT), (L, Lp * CT, CT),
+                          plan.GPoff("f.w"), 3 * CT + 1, ones_col=True)
+            cins = [1]
+            for (_, _, _, out) in struct:
+                cins.append(cins[-1] + out)
+            for li in range(len(struct) - 1, -1, -1):
+                k, s, hid, out = struct[li]
+                cin = cins[li]
+                p, pd, Lh, kd = (k - 1) // 2, s // 2, L // s, k - 1
+                Hh = hh[li]
+                # dyl = d(block output) * lrelu'(output); also feeds the dense skip (audiogan.py:281-283)
+                dyl = _empty(B, L + 2 * pd, out, device=dev)
+                slice_off = GPAD * CT + cin
+                K.ew_grad(B, L, out, out=dyl, pad=(pd, pd), g1=(dXd, slice_off), g1_str=(Lp * CT, CT, 1),
+                          act=(Xd, slice_off), act_str=(Lp * CT, CT),
+                          acc=((dXd, GPAD * CT + cin - out) if cin >= out else None), acc_str=(Lp * CT, CT))
+                if wgrad:
+                    K.colsum((dyl, pd * out), (L + 2 * pd) * out, out, B, L, out, plan.GPoff("d%d.b" % li))
+                # transposed-conv data gradient = strided conv over dyl, times lrelu'(hidden)
+                dH = _empty(B, Lh + 2, hid, device=dev)
+                dH[:, 0].zero_()
+                dH[:, Lh + 1].zero_()
+                K.gemm_nt(B * Lh, hid, kd * out, dyl, (Lh, (L + 2 * pd) * out, s * out), plan.Poff("d%d.wg" % li), kd * out,
+                          (dH, hid), (Lh, (Lh + 2) * hid, hid), dact=(Hh, hid))
+                if wgrad:
+                    K.gemm_tn(B * Lh, hid, kd * out, (Hh, hid), (Lh, (Lh + 2) * hid, hid), dyl,
+                              (Lh, (L + 2 * pd) * out, s * out), plan.GPoff("d%d.w" % li), kd * out)
+                    K.gemm_tn(B * Lh, hid, k * cin, (dH, hid), (Lh, (Lh + 2) * hid, hid), (Xd, (GPAD - p) * CT),
+                              (Lh, Lp * CT, s * CT, cin, CT), plan.GPoff("c%d.w" % li), k * cin + 1, ones_col=True)
+                # conv data gradient (3 taps over dH), accumulated into channels [0, cin) of dXd
+                cdst = (dXd, (GPAD + s - p) * CT)
+                K.gemm_nt(B * Lh, s * cin, 3 * hid, dH, (Lh, (Lh + 2) * hid, hid), plan.Poff("c%d.wg" % li), 3 * hid,
+                          cdst, (Lh, Lp * CT, s * CT, cin, CT), skip=cdst)
+            dx_ext = _zeros(B, Tcap, F, device=dev)
+            K.copy3d(dx_ext, (Tcap * F, 1, 0), (dXd, GPAD * CT), (Lp * CT, CT, 0), B, L, 1)
+        ds_ext = None
+        if gs is not None:
+            ds_ext = _zeros(B, Tcap, device=dev)
+            ds_ext[:, :T] = gs
+        # ---- BPTT through the recurrence (audiogan.py:437-444)
+        dgates = _empty(B, Tcap, 4 * H, device=dev)
+        dpx = _empty(B, Tcap, FP, device=dev)
+        if T < Tcap:
+            dgates[:, T:].zero_()
+            dpx[:, T:].zero_()
+        misc = torch.zeros(16, device=dev, dtype=torch.int32)
+        K.lstm_bwd(B=B, T=T, Tcap=Tcap, H=H, ndir=1, F=F, gates=gates, cbuf=cbuf, xbuf=xbuf, dx_ext=dx_ext,
+                   ds_ext=ds_ext, dgates=dgates, dpx=dpx, w1t=plan.Poff("w1t"), wxt=plan.Poff("wxt"), barrier=misc)
+        if wgrad:
+            yv = (T, Tcap * 4 * H, 4 * H)
+            K.gemm_tn(B * T, 4 * H, H, dgates, yv, hbuf, (T, (Tcap + 2) * H, H), plan.GPoff("w1"), H + F)
+            K.gemm_tn(B * T, 4 * H, F, dgates, yv, xbuf, (T, (Tcap + 1) * F, F), plan.GPoff("w1", H), H + F)
+            K.gemm_tn(B * T, 4 * H, NZ + 2, dgates, yv, zc1, (T, Tcap * (NZ + 2), NZ + 2), plan.GPoff("wz"), NZ + 2)
+            K.gemm_tn(B * T, FP, H, dpx, (T, Tcap * FP, FP), (hbuf, H), (T, (Tcap + 2) * H, H), plan.GPoff("w2"), H + 1,
+                      ones_col=True)
+        dzc1 = None
+        if ctx.needs_input_grad[3]:
+            dzc1 = _zeros(B, Tcap, NZ + 2, device=dev)
+            K.gemm_nt(B * T, NZ, 4 * H, dgates, (T, Tcap * 4 * H, 4 * H), plan.Poff("wzt"), 4 * H,
+                      dzc1, (T, Tcap * (NZ + 2), NZ + 2))
+        gtok = torch.zeros(1, device=dev) if wgrad else None
+        return None, None, gtok, dzc1, None, None
+
+
+# =========================================================================================
+# Discriminator: conv stack
+# =========================================================================================
+class _DiscCNNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, struct, token, x, lens):
+        """x (B, L) waveform; lens: list of per-layer int32 [B] frame counts (device).  Returns the 6
+        activations as (B, C_i, T_i) views of zero-padded channel-last buffers."""
+        dev = plan.device
+        B, L = x.shape
+        x = x.contiguous()
+        a0 = _empty(B, L + 2 * DPAD, device=dev)
+        K.frame_noise(a0, L + 2 * DPAD, DPAD, x, L, None, 0.0, B, L)
+        acts, Ts = [a0], [L]
+        cin, Tin = 1, L
+        for i, (k, s, cout) in enumerate(struct):
+            Tout = (Tin + s - 1) // s
+            a = _empty(B, Tout + 2 * DPAD, cout, device=dev)
+            a[:, :DPAD].zero_()
+            a[:, DPAD + Tout:].zero_()
+            K.gemm_nt(B * Tout, cout, k * cin, acts[-1], (Tout, (Tin + 2 * DPAD) * cin, s * cin),
+                      plan.Poff("c%d.w" % i), k * cin, (a, DPAD * cout), (Tout, (Tout + 2 * DPAD) * cout, cout),
+                      bias=plan.Poff("c%d.b" % i), act=1, mask_len=lens[i], mask=(1, 0, 0))
+            acts.append(a)
+            Ts.append(Tout)
+            cin, Tin = cout, Tout
+        ctx.plan, ctx.struct, ctx.acts, ctx.Ts, ctx.lens = plan, struct, acts, Ts, lens
+        ctx.set_materialize_grads(False)
+        return tuple(a[:, DPAD:DPAD + t].permute(0, 2, 1) for a, t in zip(acts[1:], Ts[1:]))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *gouts):
+        plan, struct, acts, Ts, lens = ctx.plan, ctx.struct, ctx.acts, ctx.Ts, ctx.lens
+        dev = plan.device
+        B = acts[0].shape[0]
+        wgrad = ctx.needs_input_grad[2]
+        need_dx = ctx.needs_input_grad[3]
+        chans = [1] + [c for (_, _, c) in struct]
+        dX = None                   # internal gradient wrt acts[i+1], padded geometry
+        for i in range(len(struct) - 1, -1, -1):
+            k, s, cout = struct[i]
+            cin, Tin, Tout = chans[i], Ts[i], Ts[i + 1]
+            g = gouts[i]
+            if g is None and dX is None:
+                continue
+            a_out = acts[i + 1]
+            geo = ((Tout + 2 * DPAD) * cout, cout)
+            dy = _empty(B, Tout + 2 * DPAD, cout, device=dev)
+            kw = {}
+            if g is not None:                  # (B, C, T) tensor with arbitrary strides
+                kw.update(g1=g, g1_str=(g.stride(0), g.stride(2), g.stride(1)))
+            if dX is not None:
+                kw.update(g2=(dX, DPAD * cout), g2_str=(geo[0], geo[1], 1))
+            K.ew_grad(B, Tout, cout, out=dy, pad=(DPAD, DPAD), act=(a_out, DPAD * cout), act_str=geo, length=lens[i], **kw)
+            a_view = (Tout, (Tin + 2 * DPAD) * cin, s * cin)
+            if wgrad:
+                K.gemm_tn(B * Tout, cout, k * cin, (dy, DPAD * cout), (Tout, geo[0], cout), acts[i], a_view,
+                          plan.GPoff("c%d.w" % i), k * cin + 1, ones_col=True)
+            if i > 0 or need_dx:
+                Mp = (Tin + DPAD + 1) // 2
+                dXn = _empty(B, Tin + 2 * DPAD, cin, device=dev)
+                if 2 * Mp < Tin + 2 * DPAD:
+                    dXn[:, 2 * Mp:].zero_()
+                K.gemm_nt(B * Mp, 2 * cin, 4 * cout, dy, (Mp, geo[0], cout), plan.Poff("c%d.wg" % i), 4 * cout,
+                          dXn, (Mp, (Tin + 2 * DPAD) * cin, 2 * cin, cin, cin),
+                          mask_len=plan.const_len(B, Tin), mask=(2, 1, -DPAD))
+                dX = dXn
+            else:
+                dX = None
+        gx = dX[:, DPAD:DPAD + Ts[0], 0] if (need_dx and dX is not None) else None
+        gtok = torch.zeros(1, device=dev) if wgrad else None
+        return None, None, gtok, gx, None
+
+
+# =========================================================================================
+# Discriminator: BiLSTM + residual net + classifier
+# =========================================================================================
+class _DiscTailFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, token, feat, c, nfr, Tm):
+        """feat: (B, Cf, T6) channel-last view; c (B, E); nfr int32 [B] frames per sample; Tm = max(nfr)."""
+        dev = plan.device
+        B, Cf, T6 = feat.shape
+        if feat.stride(1) != 1:
+            feat = feat.permute(0, 2, 1).contiguous().permute(0, 2, 1)
+        S, H, E = plan.S, plan.H, plan.E
+        ldi = Cf + E + 2
+        c1 = torch.cat([c, torch.ones(B, 2, device=dev)], 1).contiguous()
+        rb = _empty(B, 8 * H, device=dev)
+        K.gemm_nt(B, 8 * H, E + 2, c1, (B, 0, E + 2), plan.Poff("wih", Cf), ldi,
+                  rb, (B, 0, 8 * H))
+        pre = _empty(B, Tm, 8 * H, device=dev)
+        K.gemm_nt(B * Tm, 8 * H, Cf, feat, (Tm, feat.stride(0), feat.stride(2)), plan.Poff("wih"), ldi,
+                  pre, (Tm, Tm * 8 * H, 8 * H), rowbias=rb, rowbias_ld=8 * H)
+        hbuf = _zeros(B, Tm + 2, 2 * H, device=dev)
+        gates = _empty(B, Tm, 8 * H, device=dev)
+        cbuf = _empty(B, Tm, 2 * H, device=dev)
+        misc = torch.zeros(16, device=dev, dtype=torch.int32)
+        K.lstm_fwd(B=B, T=Tm, Tcap=Tm, H=H, ndir=2, F=0, pre=pre, w1=plan.Poff("w1"), hbuf=hbuf, gates=gates, cbuf=cbuf,
+                   len=nfr, barrier=misc)
+        # residual_net + classifier on the (B*Tm) rows (audiogan.py:547-549); same row geometry as hbuf
+        geo = (Tm, (Tm + 2) * S, S)
+        r1 = _empty(B, Tm + 2, S, device=dev)
+        r2 = _empty(B, Tm + 2, S, device=dev)
+        K.gemm_nt(B * Tm, S, S, (hbuf, S), geo, plan.Poff("r0.w"), S, (r1, S), geo, bias=plan.Poff("r0.b"),
+                  skip=(hbuf, S), act=1)
+        K.gemm_nt(B * Tm, S, S, (r1, S), geo, plan.Poff("r1.w"), S, (r2, S), geo, bias=plan.Poff("r1.b"),
+                  skip=(r1, S), act=1)
+        h3 = _empty(B * Tm, S // 2, device=dev)
+        K.gemm_nt(B * Tm, S // 2, S, (r2, S), geo, plan.Poff("k0.w"), S, h3, (B * Tm, 0, S // 2), bias=plan.Poff("k0.b"), act=1)
+        logits = _empty(B, Tm, device=dev)
+        K.gemm_nt(B * Tm, 1, S // 2, h3, (B * Tm, 0, S // 2), plan.Poff("k2.w"), S // 2, logits, (B * Tm, 0, 1),
+                  bias=plan.Poff("k2.b"))
+        ctx.plan, ctx.dims = plan, (B, Cf, T6, Tm)
+        ctx.bufs = (feat, c1, nfr, hbuf, gates, cbuf, r1, r2, h3)
+        return logits
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        plan = ctx.plan
+        B, Cf, T6, Tm = ctx.dims
+        feat, c1, nfr, hbuf, gates, cbuf, r1, r2, h3 = ctx.bufs
+        dev = plan.device
+        S, H, E = plan.S, plan.H, plan.E
+        ldi = Cf + E + 2
+        wgrad = ctx.needs_input_grad[1]
+        M = B * Tm
+        g = g.contiguous()
+        geo = (Tm, (Tm + 2) * S, S)
+        flat = lambda n: (M, 0, n)
+        if wgrad:
+            K.gemm_tn(M, 1, S // 2, g, flat(1), h3, flat(S // 2), plan.GPoff("k2.w"), S // 2 + 1, ones_col=True)
+        dh3 = _empty(M, S // 2, device=dev)
+        K.gemm_nt(M, S // 2, 1, g, flat(1), plan.Poff("k2.w"), 1, dh3, flat(S // 2), dact=h3)
+        if wgrad:
+            K.gemm_tn(M, S // 2, S, dh3, flat(S // 2), (r2, S), geo, plan.GPoff("k0.w"), S + 1, ones_col=True)
+        dz2 = _empty(B, Tm + 2, S, device=dev)           # grads below keep the padded-row geometry of r1 / r2 / hbuf
+        K.gemm_nt(M, S, S // 2, dh3, flat(S // 2), plan.Poff("k0.wt"), S // 2, (dz2, S), geo, dact=(r2, S))
+        if wgrad:
+            K.gemm_tn(M, S, S, (dz2, S), geo, (r1, S), geo, plan.GPoff("r1.w"), S + 1, ones_col=True)
+        dz1 = _empty(B, Tm + 2, S, device=dev)
+        K.gemm_nt(M, S, S, (dz2, S), geo, plan.Poff("r1.wt"), S, (dz1, S), geo, skip=(dz2, S), dact=(r1, S))
+        if wgrad:
+            K.gemm_tn(M, S, S, (dz1, S), geo, (hbuf, S), geo, plan.GPoff("r0.w"), S + 1, ones_col=True)
+        dh_ext = _empty(B, Tm + 2, S, device=dev)
+        K.gemm_nt(M, S, S, (dz1, S), geo, plan.Poff("r0.wt"), S, (dh_ext, S), geo, skip=(dz1, S))
+        # BPTT through both directions
+        dgates = _empty(B, Tm, 8 * H, device=dev)
+        misc = torch.zeros(16, device=dev, dtype=torch.int32)
+        K.lstm_bwd(B=B, T=Tm, Tcap=Tm, H=H, ndir=2, F=0, gates=gates, cbuf=cbuf, len=nfr, dh_ext=(dh_ext, S),
+                   dh_ext_bs=(Tm + 2) * S, dgates=dgates, w1t=plan.Poff("w1t"), barrier=misc)
+        dgsum = None
+        if wgrad or ctx.needs_input_grad[3]:
+            dgsum = _empty(B, 8 * H, device=dev)
+            K.rowgroup_sum(dgates, dgsum, B, Tm, 8 * H)
+        if wgrad:
+            for d in range(2):
+                K.gemm_tn(M, 4 * H, H, (dgates, d * 4 * H), (Tm, Tm * 8 * H, 8 * H),
+                          (hbuf, (2 * d) * 2 * H + d * H), (Tm, (Tm + 2) * 2 * H, 2 * H),
+                          plan.GPoff("whh", d * 4 * H * H), H)
+            K.gemm_tn(M, 8 * H, Cf, dgates, flat(8 * H), feat, (Tm, feat.stride(0), feat.stride(2)), plan.GPoff("wih"), ldi)
+            K.gemm_tn(B, 8 * H, E + 2, dgsum, (B, 0, 8 * H), c1, (B, 0, E + 2), plan.GPoff("wih", Cf), ldi)
+        dfeat = None
+        if ctx.needs_input_grad[2]:
+            dfeat = _zeros(B, T6, Cf, device=dev) if Tm < T6 else _empty(B, T6, Cf, device=dev)
+            K.gemm_nt(M, Cf, 8 * H, dgates, flat(8 * H), plan.Poff("wiht"), 8 * H, dfeat, (Tm, T6 * Cf, Cf))
+            dfeat = dfeat.permute(0, 2, 1)
+        dc = None
+        if ctx.needs_input_grad[3]:
+            dc = _empty(B, E, device=dev)
+            K.gemm_nt(B, E, 8 * H, dgsum, (B, 0, 8 * H), plan.Poff("wiht", Cf * 8 * H), 8 * H,
+                      dc, (B, 0, E))
+        gtok = torch.zeros(1, device=dev) if wgrad else None
+        return None, gtok, dfeat, dc, None, None
+
+
+# =========================================================================================
+# BCE with logits per sample (audiogan.py:187-197)
+# =========================================================================================
+class _BCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target, weight):
+        B, T = x.shape
+        x, target = x.contiguous(), target.contiguous()
+        w = weight.contiguous() if weight is not None else None
+        loss = torch.empty(B, device=x.device, dtype=torch.float32)
+        K.bce_fwd(x, target, w, loss, B, T)
+        ctx.save_for_backward(x, target, w)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        x, target, w = ctx.saved_tensors
+        B, T = x.shape
+        dx = torch.empty_like(x)
+        K.bce_bwd(x, target, w, gout.contiguous(), dx, B, T)
+        return dx, None, None

@@ -1,0 +1,182 @@
+"""Thin tensor-level wrappers over the C ABI (one Python function per exported kernel).
+
+Operands are torch CUDA tensors used purely as device memory; an operand may be given as
+``(tensor, element_offset)``.  No arithmetic happens here: every function fills a descriptor
+and launches on torch's current stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _abi as A
+
+LRELU_SLOPE = 0.01      # NN.LeakyReLU() / F.leaky_relu defaults (audiogan.py:261, :277, :532)
+_ESIZE = {torch.float32: 4, torch.bfloat16: 2, torch.int32: 4}
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def addr(x):
+    """x: None | tensor | (tensor, element offset) -> integer device address (None -> 0)."""
+    if x is None:
+        return None
+    if isinstance(x, tuple):
+        t, off = x
+        return t.data_ptr() + off * t.element_size()
+    return x.data_ptr()
+
+
+def _dtype_of(x):
+    if x is None:
+        return 0
+    t = x[0] if isinstance(x, tuple) else x
+    return _DT[t.dtype]
+
+
+def gemm_desc(M, N, K, A_, a_view, B_, ldb, C_, c_view, alpha=0.0, bias=None, bias_mod=0, rowbias=None,
+              rowbias_ld=0, skip=None, act=0, dact=None, slope=LRELU_SLOPE, mask_len=None, mask=(0, 0, 0)):
+    """a_view = (rows_per_batch, batch_stride, row_stride[, k_inner, k_outer_stride]);
+    c_view = (rows_per_batch, batch_stride, row_stride[, n_inner, n_outer_stride])."""
+    d = A.GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A = addr(A_)
+    a = tuple(a_view) + ((K, 0) if len(a_view) == 3 else ())
+    d.a_rpb, d.a_bs, d.a_rs, d.a_kin, d.a_k1s = a
+    d.B = addr(B_)
+    d.ldb = ldb
+    d.C = addr(C_)
+    c = tuple(c_view) + ((N, 0) if len(c_view) == 3 else ())
+    d.c_rpb, d.c_bs, d.c_rs, d.c_nin, d.c_n1s = c
+    d.alpha = alpha
+    d.bias = addr(bias)
+    d.bias_mod = bias_mod
+    d.rowbias = addr(rowbias)
+    d.rowbias_ld = rowbias_ld
+    d.skip = addr(skip)
+    d.act = act
+    d.dact = addr(dact)
+    d.slope = slope
+    d.mask_len = addr(mask_len)
+    d.mask_tmul, d.mask_n1mul, d.mask_toff = mask
+    d.a_dtype, d.b_dtype, d.c_dtype = _dtype_of(A_), _dtype_of(B_), _dtype_of(C_)
+    d.aux_dtype = _dtype_of(skip if skip is not None else dact)
+    return d
+
+
+def gemm_nt(*args, **kw):
+    d = gemm_desc(*args, **kw)
+    A.call("ag_gemm_nt_f32", C.byref(d), A.stream())
+
+
+def gemm_tn(M, N, K, Y, y_view, A_, a_view, dw, ldw, ones_col=False):
+    """dw[n, k] += sum_m Y(m, n) * A(m, k); optional bias column K."""
+    d = gemm_desc(M, N, K, A_, a_view, None, 0, Y, y_view)
+    A.call("ag_gemm_tn_f32", C.byref(d), addr(dw), ldw, 1 if ones_col else 0, A.stream())
+
+
+def lstm_desc(**kw):
+    d = A.LstmDesc()
+    for k, v in kw.items():
+        if isinstance(v, (torch.Tensor, tuple)):
+            v = addr(v)
+        setattr(d, k, v)
+    return d
+
+
+def lstm_fwd(**kw):
+    d = lstm_desc(**kw)
+    A.call("ag_lstm_fwd", C.byref(d), A.stream())
+
+
+def lstm_bwd(**kw):
+    d = lstm_desc(**kw)
+    A.call("ag_lstm_bwd", C.byref(d), A.stream())
+
+
+def gather(dst, src, idx):
+    A.call("ag_gather", addr(dst), addr(src), addr(idx), idx.numel(), _DT[dst.dtype], A.stream())
+
+
+def frame_noise(dst, dst_ld, pad_l, src, src_ld, noise, noise_scale, B, L):
+    A.call("ag_frame_noise", addr(dst), dst_ld, pad_l, addr(src), src_ld, addr(noise), float(noise_scale), B, L,
+           _dtype_of(dst), A.stream())
+
+
+def ew_grad(B, T, Cn, out=None, pad=(0, 0), g1=None, g1_str=(0, 0, 0), g2=None, g2_str=(0, 0, 0), act=None,
+            act_str=(0, 0), length=None, acc=None, acc_str=(0, 0), slope=LRELU_SLOPE):
+    d = A.EwDesc()
+    d.B, d.T, d.C = B, T, Cn
+    d.g1 = addr(g1)
+    d.g1_bs, d.g1_rs, d.g1_cs = g1_str
+    d.g2 = addr(g2)
+    d.g2_bs, d.g2_rs, d.g2_cs = g2_str
+    d.act = addr(act)
+    d.a_bs, d.a_rs = act_str
+    d.slope = slope
+    d.len = addr(length)
+    d.out = addr(out)
+    d.pad_l, d.pad_r = pad
+    d.acc = addr(acc)
+    d.acc_bs, d.acc_rs = acc_str
+    A.call("ag_ew_grad", C.byref(d), A.stream())
+
+
+def colsum(src, bs, rs, B, T, Cn, out):
+    A.call("ag_colsum", addr(src), bs, rs, B, T, Cn, addr(out), A.stream())
+
+
+def copy3d(dst, d_str, src, s_str, B, T, Cn, accumulate=False):
+    A.call("ag_copy3d", addr(dst), d_str[0], d_str[1], d_str[2], addr(src), s_str[0], s_str[1], s_str[2], B, T, Cn,
+           1 if accumulate else 0, A.stream())
+
+
+def rowgroup_sum(src, out, B, T, N):
+    A.call("ag_rowgroup_sum", addr(src), addr(out), B, T, N, A.stream())
+
+
+def bce_fwd(x, tgt, w, loss, B, T):
+    A.call("ag_bce_fwd", addr(x), addr(tgt), addr(w), addr(loss), B, T, A.stream())
+
+
+def bce_bwd(x, tgt, w, gout, dx, B, T):
+    A.call("ag_bce_bwd", addr(x), addr(tgt), addr(w), addr(gout), addr(dx), B, T, A.stream())
+
+
+def bce_const_fused(x, ld, length, target, sign, loss_mean, loss_ps, dlogits, stats, B, T):
+    A.call("ag_bce_const_fused", addr(x), ld, addr(length), float(target), float(sign), addr(loss_mean), addr(loss_ps),
+           addr(dlogits), addr(stats), B, T, A.stream())
+
+
+def wn_table(entries, device):
+    """entries: list of dicts(v,g,w,norm,dw,dv,dg,rows,cols,kind) with tensors/None -> device table + row_start."""
+    arr = (A.WnEntry * len(entries))()
+    starts, total = [], 0
+    for i, e in enumerate(entries):
+        for f in ("v", "g", "w", "norm", "dw", "dv", "dg"):
+            setattr(arr[i], f, addr(e.get(f)))
+        arr[i].rows, arr[i].cols, arr[i].kind = e["rows"], e["cols"], e["kind"]
+        starts.append(total)
+        total += e["rows"]
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+    rs = torch.tensor(starts, dtype=torch.int32).to(device)
+    return raw, rs, total
+
+
+def wn_fwd(table, row_start, nt, total_rows):
+    A.call("ag_wn_fwd_multi", addr(table), addr(row_start), nt, total_rows, A.stream())
+
+
+def wn_bwd(table, row_start, nt, total_rows):
+    A.call("ag_wn_bwd_multi", addr(table), addr(row_start), nt, total_rows, A.stream())
+
+
+def mt_table(entries, device=None, out=None):
+    """entries: list of (p, g, s1, s2) tensors -> uint8 tensor holding ag_mt_entry[]."""
+    arr = (A.MtEntry * len(entries))()
+    for i, (p, g, s1, s2) in enumerate(entries):
+        arr[i].p, arr[i].g, arr[i].s1, arr[i].s2 = addr(p), addr(g), addr(s1), addr(s2)
+        arr[i].n = p.numel()
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    if out is not None:
+        out.copy_(raw, non_blocking=True)
+        return out
+    return raw.to(device)

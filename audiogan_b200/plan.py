@@ -1,0 +1,337 @@
+"""Flat parameter plans: weight-norm table, packed GEMM operand layouts and gradient un-packing.
+
+The reference re-computes ``w = g * v / ||v||`` inside every module call through forward
+pre-hooks (audiogan.py:77-80 -- 736 ``_weight_norm_interface`` calls per step).  Here
+one multi-tensor kernel writes every effective weight of a network into one flat fp32 buffer
+(``wflat``) and one gather kernel re-lays them out into every operand layout the GEMM / recurrent
+kernels consume (``pflat``): im2col-ordered conv filters, phase-decomposed transposed-conv and
+data-gradient filters, concatenated / transposed recurrent matrices.  Weight gradients are
+accumulated by the kernels into ``gpflat`` (one region per weight, bias gradient in an extra
+column) and come back through the inverse index map and the weight-norm backward kernel.
+
+All layouts are described with ordinary torch indexing on *index tensors* (``-1`` = structural
+zero), so a layout is declared exactly the way one would write the corresponding reshape.
+"""
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import kernels as K
+
+_ALIGN = 64     # elements: every region starts 256-byte aligned
+
+
+def _round(n, a=_ALIGN):
+    return (n + a - 1) // a * a
+
+
+class Regions:
+    """Named regions in one flat buffer."""
+
+    def __init__(self):
+        self.off = {}
+        self.shape = {}
+        self.size = 0
+
+    def add(self, name, shape):
+        shape = tuple(int(s) for s in shape)
+        n = 1
+        for s in shape:
+            n *= s
+        self.off[name] = self.size
+        self.shape[name] = shape
+        self.size = _round(self.size + n)
+        return self.index(name)
+
+    def index(self, name):
+        n = 1
+        for s in self.shape[name]:
+            n *= s
+        return torch.arange(self.off[name], self.off[name] + n, dtype=torch.int64).view(self.shape[name])
+
+    def view(self, flat, name):
+        n = 1
+        for s in self.shape[name]:
+            n *= s
+        return flat[self.off[name]:self.off[name] + n].view(self.shape[name])
+
+
+class NetPlan:
+    """Everything that depends only on a network's parameter shapes, built once per (module, device)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.canon = Regions()          # effective weights (after weight-norm), canonical torch layouts
+        self.pack = Regions()           # GEMM / recurrent operand layouts
+        self.gpack = Regions()          # packed weight gradients
+        self._wn = []                   # (canon name, kind, v param, g param)
+        self._pack_idx = {}
+        self._unpack_idx = {}
+        self.params = []                # parameters in module.parameters() order
+        self.mode = "fp32"
+
+    # -- declaration ----------------------------------------------------------------------
+    def weight(self, name, v, g=None):
+        """Declare an effective weight: weight-normed (v, g) pair or plain parameter."""
+        idx = self.canon.add(name, v.shape)
+        self._wn.append((name, 0 if g is not None else 1, v, g))
+        return idx
+
+    def layout(self, name, idx):
+        """Declare a packed operand layout from an index tensor into the canonical buffer."""
+        self.pack.add(name, idx.shape)
+        self._pack_idx[name] = idx.contiguous()
+
+    def grad_region(self, name, shape):
+        return self.gpack.add(name, shape)
+
+    def grad_of(self, canon_name, idx):
+        """Canonical gradient of `canon_name` = gpflat[idx] (idx has the canonical shape)."""
+        assert tuple(idx.shape) == self.canon.shape[canon_name], (canon_name, idx.shape, self.canon.shape[canon_name])
+        self._unpack_idx[canon_name] = idx.contiguous()
+
+    # -- materialisation ------------------------------------------------------------------
+    def finalize(self, params):
+        dev = self.device
+        self.params = list(params)
+        self.wflat = torch.zeros(self.canon.size, device=dev)
+        self.dwflat = torch.zeros(self.canon.size, device=dev)
+        self.pflat = torch.zeros(self.pack.size, device=dev)
+        self.gpflat = torch.zeros(self.gpack.size, device=dev)
+        pidx = torch.full((self.pack.size,), -1, dtype=torch.int64)
+        for name, idx in self._pack_idx.items():
+            o = self.pack.off[name]
+            pidx[o:o + idx.numel()] = idx.reshape(-1)
+        self.idx_pack = pidx.to(torch.int32).to(dev)
+        uidx = torch.full((self.canon.size,), -1, dtype=torch.int64)
+        for name, _, _, _ in self._wn:
+            idx = self._unpack_idx[name]
+            o = self.canon.off[name]
+            uidx[o:o + idx.numel()] = idx.reshape(-1)
+        self.idx_unpack = uidx.to(torch.int32).to(dev)
+        # flat gradient work buffer in parameter order
+        self.poff, n = {}, 0
+        for p in self.params:
+            self.poff[id(p)] = n
+            n = _round(n + p.numel(), 4)
+        self.ngrad = n
+        self.gwork = torch.zeros(n, device=dev)
+        rows = sum(v.shape[0] for _, _, v, _ in self._wn)
+        self.norms = torch.zeros(rows, device=dev)
+        entries, r0 = [], 0
+        for name, kind, v, g in self._wn:
+            nrow = v.shape[0]
+            ncol = v.numel() // nrow
+            o = self.canon.off[name]
+            e = dict(v=v.data, g=(g.data if g is not None else None), w=(self.wflat, o), norm=(self.norms, r0),
+                     dw=(self.dwflat, o), dv=(self.gwork, self.poff[id(v)]),
+                     dg=((self.gwork, self.poff[id(g)]) if g is not None else None),
+                     rows=nrow, cols=ncol, kind=kind)
+            entries.append(e)
+            r0 += nrow
+        self.wn_tab, self.wn_rows, self.wn_total = K.wn_table(entries, dev)
+        self.wn_n = len(entries)
+        self.signature = tuple(p.data_ptr() for p in self.params)
+        self._const_len = {}
+        return self
+
+    def P(self, name):
+        return self.pack.view(self.pflat, name)
+
+    def Poff(self, name, extra=0):
+        return (self.pflat, self.pack.off[name] + extra)
+
+    def GP(self, name):
+        return self.gpack.view(self.gpflat, name)
+
+    def GPoff(self, name, extra=0):
+        return (self.gpflat, self.gpack.off[name] + extra)
+
+    def W(self, name):
+        return self.canon.view(self.wflat, name)
+
+    def const_len(self, B, value):
+        """int32 [B] filled with `value` (bounds-only masks for the view-GEMM epilogue)."""
+        key = (int(B), int(value))
+        t = self._const_len.get(key)
+        if t is None:
+            t = torch.full((int(B),), int(value), dtype=torch.int32, device=self.device)
+            self._const_len[key] = t
+        return t
+
+    # -- per-step work --------------------------------------------------------------------
+    def pack_forward(self):
+        K.wn_fwd(self.wn_tab, self.wn_rows, self.wn_n, self.wn_total)
+        K.gather(self.pflat, self.wflat, self.idx_pack)
+
+    def pack_backward(self):
+        """Consume gpflat -> fresh flat gradient buffer in parameter order (views per parameter)."""
+        K.gather(self.dwflat, self.gpflat, self.idx_unpack)
+        self.gpflat.zero_()
+        K.wn_bwd(self.wn_tab, self.wn_rows, self.wn_n, self.wn_total)
+        out = self.gwork.clone()
+        return [out[self.poff[id(p)]:self.poff[id(p)] + p.numel()].view(p.shape) for p in self.params]
+
+
+class _PackFn(torch.autograd.Function):
+    """wflat/pflat <- params.  Returns a 1-element token every consumer takes as an input, so that
+    autograd runs this node's backward after all of them (they accumulate into plan.gpflat)."""
+
+    @staticmethod
+    def forward(ctx, plan, *params):
+        ctx.plan = plan
+        plan.pack_forward()
+        return torch.zeros(1, device=plan.device)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gtoken):
+        plan = ctx.plan
+        grads = plan.pack_backward()
+        out = [g if ctx.needs_input_grad[i + 1] else None for i, g in enumerate(grads)]
+        return (None, *out)
+
+
+def pack(plan):
+    return _PackFn.apply(plan, *plan.params)
+
+
+# =========================================================================================
+# Generator plan (audiogan.py:362-410)
+# =========================================================================================
+def build_generator_plan(mod, device):
+    H, F, NZ = mod._state_size, mod._frame_size, mod._noise_size + mod._embed_size
+    FP = (F + 1 + 3) // 4 * 4
+    pl = NetPlan(device)
+    cell = mod.rnn[0].module
+    wih = pl.weight("rnn.wih", cell.weight_ih_v, cell.weight_ih_g)
+    whh = pl.weight("rnn.whh", cell.weight_hh_v, cell.weight_hh_g)
+    bhh = pl.weight("rnn.bhh", cell.bias_hh_v, cell.bias_hh_g)
+    bih = pl.weight("rnn.bih", cell.bias_ih_v, cell.bias_ih_g)
+    convs = []
+    for li, (k, s, hid, out) in enumerate(mod._struct):
+        blk = mod.dense_res_gen[li].module
+        cw = pl.weight("c%d.w" % li, blk.conv.weight_v, blk.conv.weight_g)
+        cb = pl.weight("c%d.b" % li, blk.conv.bias_v, blk.conv.bias_g)
+        dw = pl.weight("d%d.w" % li, blk.deconv.weight_v, blk.deconv.weight_g)
+        db = pl.weight("d%d.b" % li, blk.deconv.bias_v, blk.deconv.bias_g)
+        convs.append((cw, cb, dw, db))
+    fin = mod.dense_res_gen[len(mod._struct)].module
+    fw = pl.weight("f.w", fin.weight_v, fin.weight_g)
+    fb = pl.weight("f.b", fin.bias_v, fin.bias_g)
+    pw = pl.weight("proj.w", mod.proj.module.weight_v, mod.proj.module.weight_g)
+    pb = pl.weight("proj.b", mod.proj.module.bias_v, mod.proj.module.bias_g)
+    sw = pl.weight("stop.w", mod.stopper.module.weight_v, mod.stopper.module.weight_g)
+    sb = pl.weight("stop.b", mod.stopper.module.bias_v, mod.stopper.module.bias_g)
+
+    neg = lambda *shape: torch.full(shape, -1, dtype=torch.int64)
+    # recurrent operands
+    pl.layout("w1", torch.cat([whh, wih[:, :F]], 1))                                   # [4H, H+F]
+    pl.layout("wz", torch.cat([wih[:, F:], bih[:, None], bhh[:, None]], 1))            # [4H, NZ+2]
+    pl.layout("w2", torch.cat([pw, sw], 0))                                            # [F+1, H]
+    pl.layout("b2", torch.cat([pb, sb], 0))
+    pl.layout("w1t", torch.cat([whh.t(), pw.t(), sw.t(), neg(H, FP - F - 1)], 1))       # [H, 4H+FP]
+    pl.layout("wxt", wih[:, :F].t())                                                   # [F, 4H]
+    pl.layout("wzt", wih[:, F:].t())                                                   # [NZ, 4H]
+    g1 = pl.grad_region("w1", (4 * H, H + F))
+    gz = pl.grad_region("wz", (4 * H, NZ + 2))
+    g2 = pl.grad_region("w2", (FP, H + 1))
+    pl.grad_of("rnn.wih", torch.cat([g1[:, H:], gz[:, :NZ]], 1))
+    pl.grad_of("rnn.whh", g1[:, :H])
+    pl.grad_of("rnn.bih", gz[:, NZ])
+    pl.grad_of("rnn.bhh", gz[:, NZ + 1])
+    pl.grad_of("proj.w", g2[:F, :H])
+    pl.grad_of("proj.b", g2[:F, H])
+    pl.grad_of("stop.w", g2[F:F + 1, :H])
+    pl.grad_of("stop.b", g2[F:F + 1, H])
+    # conv stack
+    cin = 1
+    for li, (k, s, hid, out) in enumerate(mod._struct):
+        cw, cb, dw, db = convs[li]
+        kd = k - 1
+        assert kd == 2 * s and (k - 1) // 2 == s, "dense_res_bottleneck layer must have kernel = 2*stride + 1"
+        pl.layout("c%d.w" % li, cw.permute(0, 2, 1).reshape(hid, k * cin))              # (j, ci)
+        pl.layout("c%d.b" % li, cb)
+        # transposed conv as a GEMM over 2 taps: [(r', co), (u, ci)] = Wd[ci, co, s*(1-u) + r']
+        d4 = dw.view(hid, out, 2, s).flip(2)                                            # [ci, co, u, r']
+        pl.layout("d%d.w" % li, d4.permute(3, 1, 2, 0).reshape(s * out, 2 * hid))
+        pl.layout("d%d.b" % li, db)
+        pl.layout("d%d.wg" % li, dw.permute(0, 2, 1).reshape(hid, kd * out))            # [ci, (j, co)]
+        # conv data-gradient over 3 taps: [(r', ci), (u, h)] = Wc[h, ci, s*(2-u) + r']
+        cpad = torch.cat([cw, neg(hid, cin, 3 * s - k)], 2).view(hid, cin, 3, s).flip(2)   # [h, ci, u, r']
+        pl.layout("c%d.wg" % li, cpad.permute(3, 1, 2, 0).reshape(s * cin, 3 * hid))
+        gc = pl.grad_region("c%d.w" % li, (hid, k * cin + 1))
+        gd = pl.grad_region("d%d.w" % li, (hid, kd * out))
+        gb = pl.grad_region("d%d.b" % li, (out,))
+        pl.grad_of("c%d.w" % li, gc[:, :k * cin].reshape(hid, k, cin).permute(0, 2, 1))
+        pl.grad_of("c%d.b" % li, gc[:, k * cin])
+        pl.grad_of("d%d.w" % li, gd.view(hid, kd, out).permute(0, 2, 1))
+        pl.grad_of("d%d.b" % li, gb)
+        cin += out
+    CT = cin
+    pl.layout("f.w", fw.permute(0, 2, 1).reshape(1, 3 * CT))
+    pl.layout("f.b", fb)
+    pl.layout("f.wg", fw[0].flip(1))                                                   # [CT, 3]: W[0, ci, 2-kk]
+    gf = pl.grad_region("f.w", (1, 3 * CT + 1))
+    pl.grad_of("f.w", gf[:, :3 * CT].reshape(1, 3, CT).permute(0, 2, 1))
+    pl.grad_of("f.b", gf[:, 3 * CT])
+    pl.CT, pl.H, pl.F, pl.NZ, pl.FP = CT, H, F, NZ, FP
+    return pl.finalize(mod.parameters())
+
+
+# =========================================================================================
+# Discriminator plan (audiogan.py:472-512)
+# =========================================================================================
+def build_discriminator_plan(mod, device):
+    S, E = mod._state_size, mod._embed_size
+    H = S // 2
+    pl = NetPlan(device)
+    neg = lambda *shape: torch.full(shape, -1, dtype=torch.int64)
+    cin = 1
+    for i, (k, s, cout) in enumerate(mod._cnn_struct):
+        assert k == 7 and s == 2, "discriminator conv layers are kernel 7 / stride 2 (audiogan.py:476)"
+        cm = mod.cnn[i].module
+        w = pl.weight("c%d.w" % i, cm.weight_v, cm.weight_g)
+        b = pl.weight("c%d.b" % i, cm.bias_v, cm.bias_g)
+        pl.layout("c%d.w" % i, w.permute(0, 2, 1).reshape(cout, k * cin))
+        pl.layout("c%d.b" % i, b)
+        # data gradient over 4 taps: [(r', ci), (u, co)] = W[co, ci, 2*(3-u) + r']
+        wp = torch.cat([w, neg(cout, cin, 1)], 2).view(cout, cin, 4, 2).flip(2)          # [co, ci, u, r']
+        pl.layout("c%d.wg" % i, wp.permute(3, 1, 2, 0).reshape(2 * cin, 4 * cout))
+        g = pl.grad_region("c%d.w" % i, (cout, k * cin + 1))
+        pl.grad_of("c%d.w" % i, g[:, :k * cin].reshape(cout, k, cin).permute(0, 2, 1))
+        pl.grad_of("c%d.b" % i, g[:, k * cin])
+        cin = cout
+    Cf = cin
+    r = mod.rnn
+    wih, whh, bih, bhh = [], [], [], []
+    for d, sfx in enumerate(("", "_reverse")):
+        wih.append(pl.weight("rnn.wih%d" % d, getattr(r, "weight_ih_l0" + sfx)))
+        whh.append(pl.weight("rnn.whh%d" % d, getattr(r, "weight_hh_l0" + sfx)))
+        bih.append(pl.weight("rnn.bih%d" % d, getattr(r, "bias_ih_l0" + sfx)))
+        bhh.append(pl.weight("rnn.bhh%d" % d, getattr(r, "bias_hh_l0" + sfx)))
+    pl.layout("wih", torch.cat([torch.cat([wih[d], bih[d][:, None], bhh[d][:, None]], 1) for d in range(2)], 0))
+    pl.layout("w1", torch.stack(whh, 0))                                               # [2, 4H, H]
+    pl.layout("w1t", torch.stack([w.t() for w in whh], 0))                             # [2, H, 4H]
+    pl.layout("wiht", torch.cat([w.t() for w in wih], 1))                              # [Cf+E, 8H]
+    gi = pl.grad_region("wih", (8 * H, Cf + E + 2))
+    gh = pl.grad_region("whh", (2, 4 * H, H))
+    for d in range(2):
+        rows = slice(d * 4 * H, (d + 1) * 4 * H)
+        pl.grad_of("rnn.wih%d" % d, gi[rows, :Cf + E])
+        pl.grad_of("rnn.bih%d" % d, gi[rows, Cf + E])
+        pl.grad_of("rnn.bhh%d" % d, gi[rows, Cf + E + 1])
+        pl.grad_of("rnn.whh%d" % d, gh[d])
+    lin = [("r0", mod.residual_net.module[0].linear), ("r1", mod.residual_net.module[1].linear),
+           ("k0", mod.classifier.module[0]), ("k2", mod.classifier.module[2])]
+    for name, m in lin:
+        w = pl.weight(name + ".w", m.weight_v, m.weight_g)
+        b = pl.weight(name + ".b", m.bias_v, m.bias_g)
+        pl.layout(name + ".w", w)
+        pl.layout(name + ".wt", w.t())
+        pl.layout(name + ".b", b)
+        n, kk = w.shape
+        g = pl.grad_region(name + ".w", (n, kk + 1))
+        pl.grad_of(name + ".w", g[:, :kk])
+        pl.grad_of(name + ".b", g[:, kk])
+    pl.S, pl.H, pl.E, pl.Cf = S, H, E, Cf
+    return pl.finalize(mod.parameters())

@@ -1,0 +1,276 @@
+"""The two updates of the GAN training step (audiogan.py:706-788 and :816-921), the fused
+multi-tensor optimizer with the reference's per-tensor clip, and the loop helpers
+``check_grad`` / ``clip_grad`` (audiogan.py:232-253).
+
+``d_update`` / ``g_update`` take the same batch dictionaries as ``oracle.restated`` so the parity
+tests read side by side; they run the reference's call pattern on the drop-in modules
+(``Generator`` / ``Discriminator`` forward, ``loss.backward()``, clip, optimizer step).
+"""
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import kernels as K
+from . import _abi as A
+from .modules import (binary_cross_entropy_with_logits_per_sample, calc_dists, length_mask)  # noqa: F401
+
+_CHUNK = 65536
+
+
+class _MT:
+    """Chunk tables for the multi-tensor kernels over a fixed parameter list."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        dev = self.params[0].device
+        ct, co = [], []
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            for off in range(0, n, _CHUNK):
+                ct.append(i)
+                co.append(off)
+        self.nchunks = len(ct)
+        self.chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=dev)
+        self.chunk_off = torch.tensor(co, dtype=torch.int64, device=dev)
+        self.sqnorm = torch.zeros(len(self.params), device=dev)
+        self.flags = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.device = dev
+        self._dummy = torch.zeros(1, device=dev)
+
+    def table(self, state1=None, state2=None):
+        ents = []
+        for i, p in enumerate(self.params):
+            g = p.grad if p.grad is not None else None
+            if g is not None and not g.is_contiguous():
+                p.grad = g = g.contiguous()
+            ents.append((p.data, g, state1[i] if state1 else None, state2[i] if state2 else None))
+        # parameters without a gradient are skipped by giving them n = 0
+        import ctypes as C
+        arr = (A.MtEntry * len(ents))()
+        for i, (p, g, s1, s2) in enumerate(ents):
+            arr[i].p, arr[i].g, arr[i].s1, arr[i].s2 = K.addr(p), K.addr(g), K.addr(s1), K.addr(s2)
+            arr[i].n = p.numel() if g is not None else 0
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+        return raw.to(self.device, non_blocking=True)
+
+    def sqnorms(self, table):
+        self.sqnorm.zero_()
+        self.flags.zero_()
+        A.call("ag_mt_sqnorm", K.addr(table), K.addr(self.chunk_tensor), K.addr(self.chunk_off), self.nchunks, _CHUNK,
+               K.addr(self.sqnorm), K.addr(self.flags), A.stream())
+
+
+_mt_cache = {}
+
+
+def _mt_for(params):
+    params = list(params)
+    key = tuple(id(p) for p in params)
+    mt = _mt_cache.get(key)
+    if mt is None or mt.device != params[0].device:
+        mt = _mt_cache[key] = _MT(params)
+    return mt
+
+
+def check_grad(params):                                          # audiogan.py:232-240
+    """assert no NaN and no |g| > 1e5 in any gradient (one fused pass + one flag read)."""
+    mt = _mt_for(params)
+    mt.sqnorms(mt.table())
+    nan, big = mt.flags.tolist()
+    assert nan == 0
+    assert big == 0
+
+
+def clip_grad(params, clip_norm):                                # audiogan.py:243-253
+    """Per-tensor clip in place; returns the SUM of the per-tensor norms (as the reference does)."""
+    if clip_norm == 0:
+        return
+    mt = _mt_for(params)
+    tab = mt.table()
+    mt.sqnorms(tab)
+    A.call("ag_mt_clip", K.addr(tab), K.addr(mt.chunk_tensor), K.addr(mt.chunk_off), mt.nchunks, _CHUNK,
+           K.addr(mt.sqnorm), float(clip_norm), A.stream())
+    return mt.sqnorm.sqrt().sum()
+
+
+class FusedRMSprop:
+    """torch.optim.RMSprop(lr, alpha=0.99, eps=1e-8) (audiogan.py:693-694) as two multi-tensor launches.
+
+    ``step(clip=c)`` fuses the reference's ``clip_grad(params, c)`` (per-tensor) into the update;
+    ``step()`` after a separate ``clip_grad`` call is the literal reference sequence.  ``grad_scale``
+    multiplies every gradient first (1/world_size after a summed all-reduce)."""
+
+    def __init__(self, params, lr=1e-4, alpha=0.99, eps=1e-8, adam=False, betas=(0.9, 0.999)):
+        self.params = list(params)
+        self.lr, self.alpha, self.eps = lr, alpha, eps
+        self.adam, self.betas, self.nstep = adam, betas, 0
+        self.mt = _MT(self.params)
+        self.s1 = [torch.zeros_like(p.data) for p in self.params]
+        self.s2 = [torch.zeros_like(p.data) for p in self.params] if adam else None
+        self.param_groups = [{"params": self.params, "lr": lr}]
+        self.last_norm = None
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def step(self, clip=0.0, grad_scale=1.0, check=False):
+        mt = self.mt
+        tab = mt.table(self.s1, self.s2)
+        sq = None
+        if clip > 0 or check:
+            mt.sqnorms(tab)
+            sq = mt.sqnorm
+            self.last_norm = sq.sqrt().sum() * grad_scale
+        if check:
+            nan, big = mt.flags.tolist()
+            assert nan == 0 and big == 0, "check_grad: NaN or |g| > 1e5 (audiogan.py:239-240)"
+        self.nstep += 1
+        if self.adam:
+            A.call("ag_mt_adam", K.addr(tab), K.addr(mt.chunk_tensor), K.addr(mt.chunk_off), mt.nchunks, _CHUNK,
+                   K.addr(sq), float(clip), float(grad_scale), float(self.lr), float(self.betas[0]),
+                   float(self.betas[1]), float(self.eps), self.nstep, A.stream())
+        else:
+            A.call("ag_mt_rmsprop", K.addr(tab), K.addr(mt.chunk_tensor), K.addr(mt.chunk_off), mt.nchunks, _CHUNK,
+                   K.addr(sq), float(clip), float(grad_scale), float(self.lr), float(self.alpha), float(self.eps),
+                   A.stream())
+        return self.last_norm
+
+
+# ------------------------------------------------------------------------------- fused loss
+class _BCEConstFn(torch.autograd.Function):
+    """mean_b( sum_t mask * BCE(x, target) / nframes[b] ) with a constant target (audiogan.py:739-740, :766, :780,
+    :864, :897) plus the accuracy counters (:741-742, :781-782), one launch; backward is a scale."""
+
+    @staticmethod
+    def forward(ctx, x, nframes_i32, target, sign):
+        B, T = x.shape
+        x = x.contiguous()
+        loss = torch.zeros((), device=x.device)
+        stats = torch.zeros(2, device=x.device)                # correct, num
+        loss_ps = torch.empty(B, device=x.device)
+        dlog = torch.empty_like(x)
+        K.bce_const_fused(x, T, nframes_i32, target, sign, loss, loss_ps, dlog, stats, B, T)
+        ctx.save_for_backward(dlog)
+        ctx.mark_non_differentiable(loss_ps, stats)
+        return loss, loss_ps, stats
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gloss, _gps, _gstats):
+        (dlog,) = ctx.saved_tensors
+        return dlog * gloss, None, None, None
+
+
+def masked_bce_mean(logits, nframes, target, sign=1.0):
+    """-> (loss scalar, per-sample loss (B,), stats = [sum(mask * (sign*x > 0)), sum(mask)])."""
+    nf = nframes.to(logits.device, torch.int32)
+    return _BCEConstFn.apply(logits, nf, float(target), float(sign))
+
+
+# ------------------------------------------------------------------------------- FGSM helpers
+def adversarial_movement_d(d, data, data_len, embed_d, target, weight, scale=1e-3):     # audiogan.py:139-150
+    cls, _, _, nframes = d(data, data_len, embed_d)
+    loss = binary_cross_entropy_with_logits_per_sample(cls, target, weight) / nframes.to(cls.device).float()
+    grad = torch.autograd.grad(loss, data, grad_outputs=torch.ones_like(loss))[0]
+    return ((grad > 0).float() - (grad < 0).float()) * scale
+
+
+def adversarially_sample_z(g, d, z, embed_g, embed_d, noise, g_optim="boundary_seeking", scale=1e-2, u_stop=None):
+    """audiogan.py:99-137 with z / noise supplied by the caller (the reference draws them at :101, :104)."""
+    z = z.detach().clone().requires_grad_(True)
+    fake, _, _, fake_len = g(z=z, c=embed_g, u_stop=u_stop)
+    fake = fake + noise[:, :fake.shape[1]]
+    cls_g, _, _, nframes_g = d(fake, fake_len, embed_d)
+    tgt = torch.full_like(cls_g, 0.5 if g_optim == "boundary_seeking" else 0.0)
+    weight = length_mask(cls_g.shape, nframes_g)
+    loss = binary_cross_entropy_with_logits_per_sample(cls_g, tgt, weight) / nframes_g.to(cls_g.device).float()
+    grad = torch.autograd.grad(loss, z, grad_outputs=torch.ones_like(loss))[0]
+    advers = ((grad > 1e-9).float() - (grad < -1e-9).float()) * scale
+    return (z + advers).detach()
+
+
+# ------------------------------------------------------------------------------- the two updates
+def _set_requires_grad(module, flag):
+    for p in module.parameters():
+        p.requires_grad = flag
+
+
+def d_update(g, d, opt_d, batch, clip=1.0, fgsm=False, with_x_grad_norm=False, check=False, grad_sync=None):
+    """One discriminator update, audiogan.py:706-788.  batch keys as oracle.restated.d_update.
+    ``grad_sync(params)`` (optional) is called between backward and the optimizer step (data-parallel
+    all-reduce); it returns the gradient scale to apply."""
+    _set_requires_grad(g, False)                                                # :706-709
+    _set_requires_grad(d, True)
+    real_len = batch["real_len"]
+    u_stop = batch.get("u_stop")
+    if not fgsm:
+        real = batch["real"] + batch["noise_real"]                              # :724-725
+        cls_d, _, _, nframes_d = d(real, real_len, batch["c_real"])
+    else:
+        real = batch["real"].clone().requires_grad_(True)                       # :730-731
+        cls_d, _, _, nframes_d = d(real, real_len, batch["c_real"])
+        target = torch.full_like(cls_d, 0.9)
+        weight = length_mask(cls_d.shape, nframes_d)
+        adversarial_movement_d(d, real, real_len, batch["c_real"], target, weight)      # :735 (unused by the loss)
+    loss_d, _, st_d = masked_bce_mean(cls_d, nframes_d, 0.9, 1.0)               # :739-742
+    with torch.no_grad():
+        fake, _, _, fake_len = g(z=batch["z"], c=batch["c_g"], u_stop=u_stop)   # :748
+    if not fgsm:
+        fake = (fake + batch["noise_fake"][:, :fake.shape[1]]).detach()         # :750-751
+    else:
+        fake = fake.detach().clone().requires_grad_(True)                       # :753-754
+        cls_g, _, _, nframes_g = d(fake, fake_len, batch["c_d2"])
+        adv = adversarial_movement_d(d, fake, fake_len, batch["c_d2"], torch.zeros_like(cls_g),
+                                     length_mask(cls_g.shape, nframes_g))       # :758
+        fake = (fake + adv).detach()
+    out = {}
+    if with_x_grad_norm:
+        fake.requires_grad_(True)                                               # :760
+    cls_g, _, _, nframes_g = d(fake, fake_len, batch["c_d2"])                    # :761
+    loss_g, loss_g_ps, st_g = masked_bce_mean(cls_g, nframes_g, 0.0, -1.0)       # :762-766, :780-782
+    if with_x_grad_norm:                                                        # :769-775
+        gx = torch.autograd.grad(loss_g, fake, retain_graph=True)[0] * fake.shape[0]
+        out["x_grad_norm"] = ((gx.norm(2, 1) ** 2) / nframes_g.to(gx.device).float()).mean()
+    loss = loss_d + loss_g                                                      # :783
+    opt_d.zero_grad()
+    loss.backward()                                                             # :784-785
+    scale = grad_sync(opt_d.params) if grad_sync is not None else 1.0
+    gn = opt_d.step(clip=clip, grad_scale=scale, check=check)                   # :786-788 fused
+    out.update(loss_d=loss_d.detach(), loss_g=loss_g.detach(), loss=loss.detach(), d_grad_norm=gn,
+               stats_d=st_d, stats_g=st_g, cls_d=cls_d.detach(), cls_g=cls_g.detach(), fake=fake.detach())
+    return out
+
+
+def g_update(g, d, opt_g, batch, clip=0.1, g_optim="boundary_seeking", feature_matching=False, adv_z=False,
+             check=False, lambda_fp=1.0, grad_sync=None):
+    """One generator update, audiogan.py:816-921 (core step: feature_matching = adv_z = False).
+    batch keys as oracle.restated.g_update."""
+    _set_requires_grad(g, True)                                                 # :816-819
+    _set_requires_grad(d, False)
+    z = batch["z"]
+    u_stop = batch.get("u_stop")
+    if adv_z:                                                                   # :836
+        z = adversarially_sample_z(g, d, z, batch["c_g"], batch["c_d"], batch["noise_adv"], g_optim, u_stop=u_stop)
+    fake, fake_s, fake_stop, fake_len = g(z=z, c=batch["c_g"], u_stop=u_stop)   # :841
+    fake = fake + batch["noise_fake"][:, :fake.shape[1]]                        # :842-843
+    cls_g, hs_g, hl_g, nframes_g = d(fake, fake_len, batch["c_d"])               # :845
+    fp = None
+    if feature_matching:                                                        # :847-855
+        real = batch["real"] + batch["noise_real"]
+        _, hs_d, hl_d, _ = d(real, batch["real_len"], batch["c_d"])
+        fp = 0
+        for r, f in zip(calc_dists(hs_d, hl_d), calc_dists(hs_g, hl_g)):
+            fp = fp + torch.pow(r[0] - f[0], 2).mean() / fake.shape[0]
+    tgt = 0.5 if g_optim == "boundary_seeking" else 0.0                          # :857-860
+    _loss, loss_ps, _ = masked_bce_mean(cls_g, nframes_g, tgt, -1.0)             # :864, :897
+    loss = _loss if fp is None else _loss + fp * lambda_fp                      # :898
+    opt_g.zero_grad()
+    loss.backward()                                                             # :902-903
+    scale = grad_sync(opt_g.params) if grad_sync is not None else 1.0
+    gn = opt_g.step(clip=clip, grad_scale=scale, check=check)                   # :909-921 fused
+    _set_requires_grad(d, True)
+    return dict(loss=_loss.detach(), feature_penalty=fp, g_grad_norm=gn, cls_g=cls_g.detach(), fake=fake.detach(),
+                loss_ps=loss_ps)

@@ -62,7 +62,7 @@ typedef struct ag_gemm_desc {
   int32_t act;                  /* 1: LeakyReLU(slope) */
   const void* dact;             /* *= (dact[C-addressing] > 0 ? 1 : slope)  (LeakyReLU') */
   float slope;
-  const int32_t* mask_len;      /* zero where t*mask_tmul + (n/c_nin)*mask_n1mul + mask_toff >= mask_len[batch] */
+  const int32_t* mask_len;      /* pos = t*mask_tmul + (n/c_nin)*mask_n1mul + mask_toff; zero unless 0 <= pos < mask_len[batch] */
   int64_t mask_tmul, mask_n1mul, mask_toff;
   int32_t a_dtype, b_dtype, c_dtype, aux_dtype;   /* 0 = fp32, 1 = bf16 (skip/dact use aux_dtype) */
   int32_t reserved;
@@ -82,43 +82,47 @@ int ag_gemm_nt_tc(const ag_gemm_desc* d, void* stream);
 int ag_gemm_tn_tc(const ag_gemm_desc* d, float* dw, int64_t ldw, int32_t ones_col, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Persistent recurrent kernels (cooperative launch, weights resident in shared memory).
- * Replaces NN.LSTMCell + proj + stopper + stop sampling per frame (audiogan.py:437-460) and
- * NN.LSTM(bidirectional) under dynamic_rnn (:214-229, :498-503, :543), and their backward.
- * Gate order i,f,g,o.  Layouts (fp32):
- *   pre    [B, T, ndir*4H]   input projections + both biases (hoisted GEMM)
- *   whh    [ndir, 4H, H]
- *   hbuf   [B, T+2, ndir*H]  row t+1 holds h_t; rows 0 and T+1 stay zero (the caller zeroes them)
- *   gates  [B, T, ndir*4H]   post-activation i,f,g,o (saved for backward)
- *   cbuf   [B, T, ndir*H]    cell state c_t (saved for backward)
- *   len    [B] int32 or NULL (all T): steps t >= len[b] leave the state untouched and emit 0;
- *          direction 1 runs t = T-1 .. 0, i.e. starts at each sample's own last frame.
- * Feedback variant (generator, ndir == 1): gates also get wx[4H,F] . x_{t-1} where
- *   x_t = tanh(wp[F,H] . h_t + bp), logit_t = ws[H] . h_t + bs, written to
- *   xbuf [B, T+1, F] (row t+1 holds x_t, row 0 zero) and sbuf [B, T].
+ * Persistent recurrent kernels (cooperative launch, one CTA per slice of hidden units, its
+ * weight slice resident in shared memory for the whole sequence when it fits, one grid barrier
+ * per dependent phase).  Replaces NN.LSTMCell + proj + stopper + stop sampling per frame
+ * (audiogan.py:437-460) and NN.LSTM(bidirectional) under dynamic_rnn (:214-229, :498-503, :543),
+ * and their backward (BPTT).  Gate order i,f,g,o (torch).  Layouts (fp32); Tcap is the allocated
+ * number of steps, T <= Tcap the number to run:
+ *   pre    [B, Tcap, ndir*4H]   input projections + both biases (hoisted GEMM)
+ *   w1     [ndir, 4H, H+F]      rows in torch gate order; columns [whh | wx]
+ *   hbuf   [B, Tcap+2, ndir*H]  row t+1 holds h_t; rows 0 and T+1 must be zero on entry
+ *   gates  [B, Tcap, ndir*4H]   post-activation i,f,g,o (saved for backward; may be NULL)
+ *   cbuf   [B, Tcap, ndir*H]    cell state c_t (saved for backward; may be NULL)
+ *   len    [B] int32 or NULL (all T): steps t >= len[b] emit h = 0; direction 1 runs
+ *          t = T-1 .. 0 and therefore starts at each sample's own last frame.
+ * Feedback variant (generator, ndir == 1, F > 0): the gates also get wx . x_{t-1} where
+ *   x_t = tanh(wp . h_t + bp), logit_t = ws . h_t + bs;  w2 = [wp ; ws] is [F+1, H], b2 [F+1].
+ *   xbuf [B, Tcap+1, F] (row t+1 holds x_t, row 0 must be zero) and sbuf [B, Tcap] (logits).
  *   Stop sampling: stop[b,t] = u[b,t] < sigmoid(logit) (u NULL: never), glen[b] = frames until
- *   the first stop inclusive, *t_end = first step count at which every sample has stopped (or T).
+ *   the first stop inclusive, *t_end = number of steps run (the loop ends early once every
+ *   sample has stopped, audiogan.py:458-460).
+ * Backward: dgates [B, Tcap, ndir*4H] = grad wrt the pre-activation gates (= grad wrt `pre`),
+ *   dpx [B, Tcap, FP] = grad wrt the proj pre-activation, column F = grad wrt the stop logit,
+ *   FP = F+1 rounded up to a multiple of 4 (pad columns zero).  Weight gradients are batched
+ *   GEMMs over these two buffers (ag_gemm_tn_*), outside the recurrence.
+ *   w1t [ndir, H, 4H+FP] rows j: [whh[:, j] | wp[:, j], ws[j], 0-pad];  wxt [F, 4H] = wx^T.
+ * H % 4 == 0, F % 4 == 0.  `barrier`: >= 8 uint32 of device memory (zeroed by the call).
  * ------------------------------------------------------------------------------------------ */
 typedef struct ag_lstm_desc {
-  int32_t B, T, H, ndir, F;        /* F = 0: no feedback */
-  int32_t reserved;
-  const float* pre; const float* whh;
+  int32_t B, T, Tcap, H, ndir, F;
+  const float* pre; const float* w1; const float* w2; const float* b2;
   float* hbuf; float* gates; float* cbuf;
   const int32_t* len;
-  /* feedback (F > 0) */
-  const float* wx; const float* wp; const float* bp; const float* ws; const float* bs;
   float* xbuf; float* sbuf;
   const float* u; int32_t* stop; int32_t* glen; int32_t* t_end;
   /* backward only */
-  const float* dh_ext;   /* [B, T, ndir*H] grad wrt emitted h (NULL = 0) */
-  const float* dx_ext;   /* [B, T, F] grad wrt emitted frames (feedback) */
-  const float* ds_ext;   /* [B, T] grad wrt stop logits (NULL = 0) */
-  float* dgates;         /* [B, T, ndir*4H] out: grad wrt pre-activation gates (= d pre) */
-  float* dpx;            /* [B, T, F+1] out: grad wrt proj pre-activation, col F = ds */
-  const float* whh_t;    /* [ndir, H, 4H]  transposed copies for the backward pass */
-  const float* wx_t;     /* [F, 4H] */
-  const float* wp_t;     /* [H, F+1]  (col F = ws) */
-  unsigned int* barrier; /* >= 8 zeroed uint32 in device memory (grid barrier state) */
+  const float* dh_ext;   /* [B, Tcap, ndir*H] grad wrt emitted h (NULL = 0); batch stride dh_ext_bs if != 0 */
+  const float* dx_ext;   /* [B, Tcap, F] grad wrt emitted frames (NULL = 0) */
+  const float* ds_ext;   /* [B, Tcap] grad wrt stop logits (NULL = 0) */
+  float* dgates; float* dpx;
+  const float* w1t; const float* wxt;
+  unsigned int* barrier;
+  int64_t dh_ext_bs;
 } ag_lstm_desc;
 
 int ag_lstm_fwd(const ag_lstm_desc* d, void* stream);
@@ -166,6 +170,33 @@ int ag_bce_const_fused(const float* x, int64_t ld, const int32_t* len, float tar
                        float* loss_mean, float* loss_ps, float* dlogits, float* stats,
                        int64_t B, int64_t T, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Activation-gradient assembly (backward of LeakyReLU + length mask + dense skip,
+ * audiogan.py:261-264, :277-283, :532-534), strided element-wise:
+ *   v[b,t,c] = (g1[b,t,c] + g2[b,t,c]) * (act[b,t,c] > 0 ? 1 : slope) * (t < len[b])
+ *   out[b, pad_l + t, c] = v, the pad_l rows before and pad_r rows after each sequence zeroed
+ *   (out is a packed channel-last buffer [B, pad_l + T + pad_r, C] ready to be a GEMM operand);
+ *   acc[b,t,c] += v when acc != NULL (the dense-net skip path).
+ * g1/g2/act/len may be NULL (0 / 1 / all).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ag_ew_desc {
+  int64_t B, T, C;
+  const float* g1; int64_t g1_bs, g1_rs, g1_cs;
+  const float* g2; int64_t g2_bs, g2_rs, g2_cs;
+  const float* act; int64_t a_bs, a_rs;
+  float slope; int32_t reserved;
+  const int32_t* len;
+  float* out; int64_t pad_l, pad_r;
+  float* acc; int64_t acc_bs, acc_rs;
+} ag_ew_desc;
+int ag_ew_grad(const ag_ew_desc* d, void* stream);
+/* out[c] += sum_{b,t} in[b*bs + t*rs + c]  (bias gradients); out must be initialised. */
+int ag_colsum(const float* in, int64_t bs, int64_t rs, int64_t B, int64_t T, int64_t C, float* out, void* stream);
+
+/* dst[b*d_bs + t*d_rs + c*d_cs] (+)= src[b*s_bs + t*s_rs + c*s_cs]: frame assembly into the dense
+ * generator buffer (audiogan.py:462-464) and its gradient read-back. */
+int ag_copy3d(float* dst, int64_t d_bs, int64_t d_rs, int64_t d_cs, const float* src, int64_t s_bs, int64_t s_rs,
+              int64_t s_cs, int64_t B, int64_t T, int64_t C, int32_t accumulate, void* stream);
 /* out[b, n] = sum_t in[b, t, n] */
 int ag_rowgroup_sum(const float* in, float* out, int64_t B, int64_t T, int64_t N, void* stream);
 /* dst[b, t, c] (channel-last, row stride dst_rs, batch stride dst_bs) <-> src[b, c, t] */
@@ -186,6 +217,9 @@ typedef struct ag_mt_entry {
 } ag_mt_entry;
 int ag_mt_sqnorm(const ag_mt_entry* table, const int32_t* chunk_tensor, const int64_t* chunk_off,
                  int32_t nchunks, int32_t chunk, float* sqnorm, int32_t* flags, void* stream);
+/* clip_grad alone (audiogan.py:243-253): g *= clip/||g|| in place where ||g|| > clip. */
+int ag_mt_clip(const ag_mt_entry* table, const int32_t* chunk_tensor, const int64_t* chunk_off,
+               int32_t nchunks, int32_t chunk, const float* sqnorm, float clip, void* stream);
 int ag_mt_rmsprop(const ag_mt_entry* table, const int32_t* chunk_tensor, const int64_t* chunk_off,
                   int32_t nchunks, int32_t chunk, const float* sqnorm, float clip, float gscale,
                   float lr, float alpha, float eps, void* stream);

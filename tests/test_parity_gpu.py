@@ -1,0 +1,213 @@
+"""GPU parity: the drop-in modules (CUDA kernels through the C ABI) against the CPU oracle
+(oracle/restated.py, itself pinned to the reference classes by tests/test_oracle.py) and against the
+committed golden vectors generated from the reference's own classes.  fp32 mode: <= 1e-5 relative
+(BASELINE.json north_star); relative = max|a-b| / max|b| per tensor."""
+import glob
+import os
+import warnings
+
+import pytest
+import torch as T
+
+from oracle import restated as O
+from audiogan_b200.synthetic import step_inputs
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+RTOL = 1e-5
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max()) / (float(b.abs().max()) + 1e-30)
+
+
+class Report:
+    def __init__(self):
+        self.bad, self.rows = [], []
+
+    def check(self, name, a, b, tol=RTOL):
+        if tuple(a.shape) != tuple(b.shape):
+            self.bad.append("%s: shape %s vs %s" % (name, tuple(a.shape), tuple(b.shape)))
+            return
+        r = rel(a, b)
+        self.rows.append((name, r))
+        if not (r <= tol):
+            self.bad.append("%s: rel err %.3e > %.1e" % (name, r, tol))
+
+    def done(self):
+        assert not self.bad, "\n".join(self.bad)
+
+
+def build(case, dev="cuda"):
+    import audiogan_b200 as ag
+    gk, dk = case.get("gk", {}), case.get("dk", {})
+    Pg = O.pin_stopper(O.init_generator(case.get("g_seed", 11), **gk))
+    Pd = O.init_discriminator(case.get("d_seed", 12), **dk)
+    g = ag.Generator(embed_size=100, **gk)
+    d = ag.Discriminator(embed_size=100, **dk)
+    g.load_state_dict(Pg)
+    d.load_state_dict(Pd)
+    return Pg, Pd, g.to(dev), d.to(dev)
+
+
+def to_dev(inp, dev="cuda"):
+    return {k: (v.to(dev) if isinstance(v, T.Tensor) else v) for k, v in inp.items()}
+
+
+CASES = {
+    "small_h64_b4_l1000_mixed": dict(B=4, L=1000, full=False, gk={"state_size": 64}, dk={"state_size": 64}),
+    "default_b3_l1200_mixed": dict(B=3, L=1200, full=False),
+    "default_b2_l1600_full": dict(B=2, L=1600, full=True),
+}
+
+
+def bce_mean(cls, nf, tgt):
+    w = O.length_mask(cls.shape, nf)
+    return (O.bce_with_logits_per_sample(cls, T.full_like(cls, tgt), w) / nf.float()).mean()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_and_grads_match_oracle(name):
+    import audiogan_b200 as ag
+    cs = CASES[name]
+    Pg, Pd, g, d = build(cs)
+    inp = step_inputs(cs["B"], cs["L"], seed=1234, full_length=cs["full"])
+    di = to_dev(inp)
+    R = Report()
+    # ---------------- oracle (CPU fp32)
+    Pg_r = {k: v.clone().requires_grad_(True) for k, v in Pg.items()}
+    Pd_r = {k: v.clone().requires_grad_(True) for k, v in Pd.items()}
+    z_r = inp["g_z"].clone().requires_grad_(True)
+    x_r, s_r, stop_r, glen_r = O.generator_forward(Pg_r, inp["g_c_g"], z=z_r)
+    ln = glen_r if cs["full"] else inp["real_len"]
+    cls_r, hs_r, hl_r, nf_r = O.discriminator_forward(Pd_r, x_r + inp["g_noise_fake"], ln, inp["g_c_d"])
+    loss_r = bce_mean(cls_r, nf_r, 0.5)
+    gk, dk = list(Pg_r), list(Pd_r)
+    grads_r = T.autograd.grad(loss_r, [Pg_r[k] for k in gk] + [Pd_r[k] for k in dk] + [z_r], allow_unused=True)
+    # ---------------- CUDA path
+    z = di["g_z"].clone().requires_grad_(True)
+    x, s, stop_list, glen = g(z=z, c=di["g_c_g"], u_stop=None)
+    R.check("G.s (stop logits)", s, s_r)
+    R.check("G.x", x, x_r)
+    assert T.equal(glen.cpu(), glen_r), (glen, glen_r)
+    assert len(stop_list) == s_r.shape[1] and tuple(stop_list[0].shape) == (cs["B"], 1)
+    ln_d = glen if cs["full"] else di["real_len"]
+    cls, hs, hl, nf = d(x + di["g_noise_fake"], ln_d, di["g_c_d"])
+    assert T.equal(nf.cpu(), nf_r)
+    for i, (a, b) in enumerate(zip(hs, hs_r)):
+        R.check("D.cnn[%d]" % i, a, b)
+        assert T.equal(hl[i].cpu(), hl_r[i])
+    R.check("D.logits", cls, cls_r)
+    loss, _, _ = ag.masked_bce_mean(cls, nf, 0.5, -1.0)
+    R.check("loss", loss.reshape(1), loss_r.reshape(1))
+    loss.backward()
+    sg, sd = dict(g.named_parameters()), dict(d.named_parameters())
+    for k, gr in zip(gk, grads_r[:len(gk)]):
+        got = sg[k].grad
+        if k.endswith("bias_v"):      # d/dv of g*sign(v) = 0 on both sides up to rounding noise
+            continue
+        if gr is None:
+            assert got is None or float(got.abs().max()) == 0.0, k
+            continue
+        R.check("dG/" + k, got, gr, tol=5e-5)
+    for k, gr in zip(dk, grads_r[len(gk):len(gk) + len(dk)]):
+        if k.endswith("bias_v"):
+            continue
+        R.check("dD/" + k, sd[k].grad, gr, tol=5e-5)
+    R.check("dz", z.grad, grads_r[-1], tol=5e-5)
+    print("\n".join("%-50s %.3e" % r for r in R.rows))
+    R.done()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])
+def test_against_reference_golden(path):
+    """Outputs of the REFERENCE's own classes (tests/golden, made by oracle/make_golden.py)."""
+    import audiogan_b200 as ag
+    gold = T.load(path)
+    cs = gold["case"]
+    Pg, Pd, g, d = build(cs)
+    di = to_dev(step_inputs(cs["B"], cs["L"], seed=cs["input_seed"], full_length=cs["full"]))
+    R = Report()
+    G = gold["G"]
+    z = di["g_z"].clone().requires_grad_(True)
+    x, s, _, glen = g(z=z, c=di["g_c_g"], u_stop=None)
+    R.check("x", x, G["x"])
+    R.check("s", s, G["s"])
+    assert T.equal(glen.cpu(), G["len"])
+    ln = glen if cs["full"] else di["real_len"]
+    cls_g, hs, hl, nf = d(x + di["g_noise_fake"], ln, di["g_c_d"])
+    R.check("cls_g", cls_g, G["cls_g"])
+    for h, n in zip(hs, G["cnn_norms"]):
+        assert abs(float(h.norm()) - n) <= 2e-5 * n
+    loss, _, _ = ag.masked_bce_mean(cls_g, nf, 0.5, -1.0)
+    assert abs(float(loss) - G["loss"]) < 2e-6
+    loss.backward()
+    for k, p in g.named_parameters():
+        gs = G["grads"][k]
+        if gs is None or k.endswith("bias_v"):
+            continue
+        assert abs(float(p.grad.norm()) - gs["norm"]) <= 5e-5 * gs["norm"] + 1e-12, k
+        assert float((p.grad.flatten()[:32].cpu() - gs["head"]).abs().max()) <= 5e-5 * gs["absmax"] + 1e-12, k
+    assert abs(float(z.grad.norm()) - G["dz"]["norm"]) <= 5e-5 * G["dz"]["norm"]
+    # D-update style losses on real + detached fake
+    D = gold["D"]
+    g.zero_grad(); d.zero_grad()
+    real = (di["real"] + di["noise_real"]).requires_grad_(True)
+    cls_d, _, _, nfd = d(real, di["real_len"], di["c_real"])
+    with T.no_grad():
+        xf, _, _, flen = g(z=di["z"], c=di["c_g"], u_stop=None)
+    fk = (xf + di["noise_fake"]).detach().requires_grad_(True)
+    cls_f, _, _, nff = d(fk, flen, di["c_d2"])
+    R.check("cls_d", cls_d, D["cls_d"])
+    R.check("cls_f", cls_f, D["cls_f"])
+    loss_d, _, _ = ag.masked_bce_mean(cls_d, nfd, 0.9, 1.0)
+    loss_f, _, _ = ag.masked_bce_mean(cls_f, nff, 0.0, -1.0)
+    assert abs(float(loss_d) - D["loss_d"]) < 2e-6 and abs(float(loss_f) - D["loss_f"]) < 2e-6
+    (loss_d + loss_f).backward()
+    for k, p in d.named_parameters():
+        gs = D["grads"][k]
+        if k.endswith("bias_v"):
+            continue
+        assert abs(float(p.grad.norm()) - gs["norm"]) <= 5e-5 * gs["norm"] + 1e-12, k
+        assert float((p.grad.flatten()[:32].cpu() - gs["head"]).abs().max()) <= 5e-5 * gs["absmax"] + 1e-12, k
+    assert abs(float(real.grad.norm()) - D["dreal"]["norm"]) <= 5e-5 * D["dreal"]["norm"]
+    assert abs(float(fk.grad.norm()) - D["dfake"]["norm"]) <= 5e-5 * D["dfake"]["norm"]
+    R.done()
+
+
+def test_core_step_matches_oracle_updates():
+    """1 D-update + 1 G-update (SURVEY 8(d) core step): losses and post-step parameters."""
+    import audiogan_b200 as ag
+    cs = dict(B=3, L=1200, full=True, gk={"state_size": 64}, dk={"state_size": 64})
+    Pg, Pd, g, d = build(cs)
+    inp = step_inputs(cs["B"], cs["L"], seed=77, full_length=True)
+    di = to_dev(inp)
+    Pg_r = {k: v.clone() for k, v in Pg.items()}
+    Pd_r = {k: v.clone() for k, v in Pd.items()}
+    st_d, st_g = {}, {}
+    gb = lambda dd: {"c_g": dd["g_c_g"], "c_d": dd["g_c_d"], "z": dd["g_z"], "noise_fake": dd["g_noise_fake"]}
+    o1 = O.d_update(Pg_r, Pd_r, st_d, inp)
+    o2 = O.g_update(Pg_r, Pd_r, st_g, gb(inp))
+    opt_d = ag.FusedRMSprop(d.parameters(), lr=1e-4)
+    opt_g = ag.FusedRMSprop(g.parameters(), lr=1e-4)
+    di["u_stop"] = None
+    m1 = ag.d_update(g, d, opt_d, di, clip=1.0, check=True)
+    gbd = gb(di); gbd["u_stop"] = None
+    m2 = ag.g_update(g, d, opt_g, gbd, clip=0.1, check=True)
+    R = Report()
+    R.check("loss_d", m1["loss_d"].reshape(1), T.tensor([o1["loss_d"]]))
+    R.check("loss_g(D)", m1["loss_g"].reshape(1), T.tensor([o1["loss_g"]]))
+    R.check("d_grad_norm", m1["d_grad_norm"].reshape(1), T.tensor([o1["d_grad_norm"]]), tol=5e-5)
+    R.check("loss(G)", m2["loss"].reshape(1), T.tensor([o2["loss"]]))
+    R.check("g_grad_norm", m2["g_grad_norm"].reshape(1), T.tensor([o2["g_grad_norm"]]), tol=5e-5)
+    for k, p in d.named_parameters():
+        delta_r = Pd_r[k].detach() - Pd[k]
+        R.check("D step " + k, p.detach().cpu() - Pd[k], delta_r, tol=2e-3)   # RMSprop's first step is +-lr*sign-like
+    for k, p in g.named_parameters():
+        if k.endswith("bias_v"):
+            continue
+        R.check("G step " + k, p.detach().cpu() - Pg[k], Pg_r[k].detach() - Pg[k], tol=2e-3)
+    print("\n".join("%-50s %.3e" % r for r in R.rows))
+    R.done()
