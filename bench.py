@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- the audiogan GAN training step on B200 (BASELINE.json metric / config).
+
+A "step" is one core training step: 1 discriminator update (G forward detached,
+D forward on real and on fake, D backward, per-tensor clip, RMSprop) + 1 generator update (G forward,
+D forward, D data-gradient, G backward incl. BPTT, clip, RMSprop) on one synthetic minibatch.
+Workload (configs[1]): default generator / discriminator, per-GPU batch 64, 2 s synthetic 8 kHz
+waveforms (L = 16000); N GPUs = batch-sharded data parallel (global batch 64 N, weak scaling) with a
+bucketed NCCL all-reduce of each net's gradients.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the CPU oracle port of the reference step on the host cores
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+RATE = 8000
+FRAME = 200
+
+
+def flops_per_sample(L):
+    """Algorithmic FLOPs of one core step per sample: 4 F_G + 8 F_D MACs, 2 FLOP/MAC."""
+    F_G = 60475.64 * L
+    F_D = 140736.0 * L
+    return 2.0 * (4 * F_G + 8 * F_D)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="MEASURED_PEAKS.json")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        get_r = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = get_r(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def stop(self):
+        self._halt.set()
+        if self.ok:
+            self.join(timeout=2)
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------- our arm
+class KernelTimer:
+    """CUDA-event pairs around every C-ABI launch (on the launching stream), grouped per kernel family."""
+
+    def __init__(self, torch):
+        self.torch, self.recs = torch, []
+
+    def hook(self, name, args):
+        tc = self.torch.cuda
+        flops = 0.0
+        if name.startswith("ag_gemm"):
+            d = args[0]._obj
+            flops = 2.0 * d.M * d.N * d.K
+        elif name.startswith("ag_lstm"):
+            d = args[0]._obj
+            if name.endswith("fwd"):
+                per = d.ndir * 4 * d.H * (d.H + d.F) + (d.F + 1) * d.H * (1 if d.F else 0)
+            else:
+                per = d.ndir * d.H * (4 * d.H + (d.F + 1 if d.F else 0)) + d.F * 4 * d.H
+            flops = 2.0 * d.B * d.T * per
+        e0, e1 = tc.Event(enable_timing=True), tc.Event(enable_timing=True)
+        e0.record()
+        rec = [name, flops, e0, e1]
+        self.recs.append(rec)
+        return e1.record
+
+    def summary(self):
+        fam = {}
+        for name, flops, e0, e1 in self.recs:
+            ms = e0.elapsed_time(e1)
+            f = fam.setdefault(name, [0.0, 0.0, 0])
+            f[0] += ms
+            f[1] += flops
+            f[2] += 1
+        return fam
+
+
+def make_batches(torch, B, L, rank, nb, pinned):
+    from audiogan_b200.synthetic import step_inputs
+    out = []
+    for i in range(nb):
+        inp = step_inputs(B, L, seed=1234 + 1000 * rank + i, full_length=True)
+        if pinned:
+            inp = {k: v.pin_memory() for k, v in inp.items()}
+        out.append(inp)
+    return out
+
+
+def run_ours(args):
+    import torch
+    import audiogan_b200 as ag
+    from audiogan_b200 import dist as agd
+    from audiogan_b200 import _abi
+
+    rank, world, local = agd.init()
+    if world != args.gpus:
+        if args.gpus != 1:
+            raise SystemExit("--gpus %d needs torchrun with %d ranks (WORLD_SIZE=%d)" % (args.gpus, args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.manual_seed(1234)
+    B, L = args.batch, args.samples
+    g = ag.pin_stopper(ag.Generator(embed_size=100)).to(dev)
+    d = ag.Discriminator(embed_size=100).to(dev)
+    agd.broadcast_parameters([g, d])
+    opt_d = ag.FusedRMSprop(d.parameters(), lr=1e-4)
+    opt_g = ag.FusedRMSprop(g.parameters(), lr=1e-4)
+    sync = agd.GradSync(nbuckets=4) if world > 1 else None
+
+    host = make_batches(torch, B, L, rank, 2, pinned=True)
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def step(di):
+        di = dict(di)
+        di["u_stop"] = None
+        m1 = ag.d_update(g, d, opt_d, di, clip=1.0, grad_sync=sync)
+        gb = {"c_g": di["g_c_g"], "c_d": di["g_c_d"], "z": di["g_z"], "noise_fake": di["g_noise_fake"], "u_stop": None}
+        m2 = ag.g_update(g, d, opt_g, gb, clip=0.1, grad_sync=sync)
+        return m1, m2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, K):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for i in range(args.warmup):
+        step(resident[i % 2])
+    # ---- headline: inputs resident in HBM
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _abi.launches
+    ms = timed(lambda i: step(resident[i % 2]), args.steps)
+    launches = (_abi.launches - l0) / args.steps
+    clocks = sampler.stop()
+    ms_step = ms / args.steps
+    audio_s = world * B * L / RATE
+    value = audio_s / (ms_step * 1e-3)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": round(ms_step, 4), "value": round(value, 2), "gpu_launches": launches}))
+        return
+    # ---- e2e: host buffers, H2D of the step's inputs and D2H of the losses inside the timed region
+    d2h = [0]
+
+    def e2e_step(i):
+        di = {k: v.to(dev, non_blocking=True) for k, v in host[i % 2].items()}
+        m1, m2 = step(di)
+        res = torch.stack([m1["loss_d"], m1["loss_g"], m2["loss"]]).cpu()
+        d2h[0] = res.numel() * res.element_size()
+
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+
+    # ---- per-kernel attribution with CUDA events around every launch (same steps, instrumented)
+    kt = KernelTimer(torch)
+    _abi.set_hook(kt.hook)
+    ms_inst = timed(lambda i: step(resident[i % 2]), args.steps) / args.steps
+    _abi.set_hook(None)
+    fam = kt.summary()
+    pk = peaks()
+    tot_kernel_ms = sum(v[0] for v in fam.values())
+    top = max(fam.items(), key=lambda kv: kv[1][0])
+    tname, (tms, tflops, tcount) = top
+    achieved = (tflops / (tms * 1e-3)) / 1e12 if tms > 0 else 0.0
+    roofline = {"kernel": tname, "bound": "tensor", "achieved": round(achieved, 3), "peak": pk["tc"], "unit": "TFLOP/s",
+                "frac": round(achieved / pk["tc"], 5), "traffic": None, "avg_launch_ms": round(tms / tcount, 5),
+                "launches_per_step": tcount / args.steps, "share_of_kernel_time": round(tms / tot_kernel_ms, 4),
+                "peak_source": pk["src"] + " (bf16_tflops_sustained, of measured)"}
+    families = {k: {"ms_per_step": round(v[0] / args.steps, 4), "tflops": round((v[1] / (v[0] * 1e-3)) / 1e12, 3) if v[0] > 0 else 0,
+                    "launches_per_step": v[2] / args.steps} for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])}
+
+    out = {
+        "metric": "audio_seconds_per_s", "value": round(value, 2), "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mode == "fp32" else "bf16", "data": "synthetic",
+        "steps_per_s": round(1e3 / ms_step, 4),
+        "step_tflops": round(world * B * flops_per_sample(L) / (ms_step * 1e-3) / 1e12, 3),
+        "frac_tc_peak_whole_step": round(B * flops_per_sample(L) / (ms_step * 1e-3) / 1e12 / pk["tc"], 5),
+        "config": {"workload": "audiogan core GAN step (1 D-update + 1 G-update), default nets, per-GPU batch %d, "
+                               "%.1f s synthetic 8 kHz waveforms (L=%d)" % (B, L / RATE, L),
+                   "global_batch": world * B, "samples": L, "mode": args.mode, "parallelism": "dp%d" % world,
+                   "l2_policy": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; two input batches alternate"},
+        "e2e": {"value": round(audio_s / (ms_e2e * 1e-3), 2), "unit": "audio-s/s", "ms_per_step": round(ms_e2e, 4),
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h[0]},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "ms_per_step_instrumented": round(ms_inst, 4),
+        "kernel_families": families,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_step_throughput(args, steps=2, warmup=1)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------- CPU arm
+def cpu_step_throughput(args, steps, warmup):
+    """The oracle port (oracle/restated.py: the reference's step restated for py3 / torch 2.x, pinned to the
+    reference classes by tests/test_oracle.py) on the host cores, on a bounded sample of the workload."""
+    import torch
+    from oracle import restated as O
+    from audiogan_b200.synthetic import step_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs, L = args.cpu_batch, args.samples
+    Pg = O.pin_stopper(O.init_generator(11))
+    Pd = O.init_discriminator(12)
+    inp = step_inputs(Bs, L, seed=1234, full_length=True)
+    gb = {"c_g": inp["g_c_g"], "c_d": inp["g_c_d"], "z": inp["g_z"], "noise_fake": inp["g_noise_fake"]}
+    sd, sg = {}, {}
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.d_update(Pg, Pd, sd, inp)
+        O.g_update(Pg, Pd, sg, gb)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return {"value": round(Bs * L / RATE / t, 3), "unit": "audio-s/s", "cores": cores, "kind": "port",
+            "s_per_step": round(t, 4), "steps_per_s_at_sample_batch": round(1.0 / t, 4),
+            "sample": "oracle port of the reference step (torch fp32 CPU, %d threads) on %d of the %d samples of a "
+                      "minibatch, L=%d, %d timed steps after %d warm-up" % (cores, Bs, args.batch, L, steps, warmup)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    cb = cpu_step_throughput(args, steps=steps, warmup=warm)
+    L = args.samples
+    out = {
+        "impl": "reference", "metric": "audio_seconds_per_s", "value": cb["value"], "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": round(cb["s_per_step"] * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "audiogan core GAN step (1 D-update + 1 G-update), default nets, per-GPU batch %d, "
+                               "%.1f s synthetic 8 kHz waveforms (L=%d)" % (args.batch, L / RATE, L),
+                   "global_batch": args.batch, "samples": L, "mode": "fp32", "parallelism": "cpu"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("AUDIOGAN_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (configs[1]: 64)")
+    ap.add_argument("--samples", type=int, default=16000, help="waveform length L (2 s at 8 kHz)")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="samples per step of the bounded CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline timing only (for ncu runs): no e2e / attribution / CPU legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
