@@ -62,9 +62,9 @@ def gemm_desc(M, N, K, A_, a_view, B_, ldb, C_, c_view, alpha=0.0, bias=None, bi
     return d
 
 
-def gemm_nt(*args, **kw):
+def gemm_nt(*args, tc=False, **kw):
     d = gemm_desc(*args, **kw)
-    A.call("ag_gemm_nt_f32", C.byref(d), A.stream())
+    A.call("ag_gemm_nt_tc" if tc else "ag_gemm_nt_f32", C.byref(d), A.stream())
 
 
 def gemm_tn(M, N, K, Y, y_view, A_, a_view, dw, ldw, ones_col=False):

@@ -202,3 +202,45 @@ def test_weight_norm_bce_optimizer():
     for q, b in zip(qs, before):
         n = float(b.norm())
         assert rel(q.grad, b / (n / 0.25) if n > 0.25 else b) < 1e-6
+
+
+@pytest.mark.parametrize("M,N,K,vec", [(300, 70, 64, True), (1000, 256, 448, True), (517, 512, 1024, True),
+                                       (260, 16, 7, False), (129, 40, 153, False), (64, 1, 512, True)])
+def test_gemm_nt_tc_matches_bf16_reference(M, N, K, vec):
+    """tcgen05 path: operands rounded to bf16, fp32 accumulation in TMEM -> equals an fp32 matmul of the
+    bf16-rounded operands up to summation order."""
+    from audiogan_b200 import kernels as Kn
+    T.manual_seed(7)
+    Kp = (K + 7) // 8 * 8
+    A, B, bias, skip = T.randn(M, K), T.randn(N, K), T.randn(N), T.randn(M, N)
+    Ab, Bb = A.bfloat16().float(), B.bfloat16().float()
+    ref = F.leaky_relu(Ab @ Bb.t() + bias + skip, 0.01)
+    Bd = T.zeros(N, Kp, dtype=T.bfloat16, device="cuda")
+    Bd[:, :K] = B.cuda().bfloat16()
+    C = T.empty(M, N, device="cuda")
+    Kn.gemm_nt(M, N, K, A.cuda(), (M, 0, K), Bd, Kp, C, (M, 0, N), bias=bias.cuda(), skip=skip.cuda(), act=1, tc=True)
+    assert rel(C, ref) < 2e-5
+    # bf16 A operand and bf16 output
+    Cb = T.empty(M, N, device="cuda", dtype=T.bfloat16)
+    A16 = T.zeros(M, Kp, dtype=T.bfloat16, device="cuda")
+    A16[:, :K] = A.cuda().bfloat16()
+    Kn.gemm_nt(M, N, K, A16, (M, 0, Kp), Bd, Kp, Cb, (M, 0, N), tc=True)
+    assert rel(Cb, (Ab @ Bb.t())) < 1e-2
+
+
+def test_gemm_nt_tc_conv_view():
+    from audiogan_b200 import kernels as Kn
+    T.manual_seed(8)
+    Bn, Cin, Cout, Tin, k, s, p = 3, 16, 40, 301, 7, 2, 3
+    x, w, b = T.randn(Bn, Cin, Tin), T.randn(Cout, Cin, k), T.randn(Cout)
+    lens = T.tensor([151, 70, 12], dtype=T.int32)
+    Tout = (Tin + s - 1) // s
+    ref = F.leaky_relu(F.conv1d(x.bfloat16().float(), w.bfloat16().float(), b, stride=s, padding=p), 0.01)
+    ref = ref * (T.arange(Tout)[None, None, :] < lens[:, None, None]).float()
+    xp = T.zeros(Bn, Tin + 2 * p, Cin)
+    xp[:, p:p + Tin] = x.permute(0, 2, 1)
+    wp = w.permute(0, 2, 1).reshape(Cout, k * Cin).contiguous().cuda().bfloat16()
+    out = T.zeros(Bn, Tout, Cout, device="cuda")
+    Kn.gemm_nt(Bn * Tout, Cout, k * Cin, xp.cuda(), (Tout, (Tin + 2 * p) * Cin, s * Cin), wp, k * Cin,
+               out, (Tout, Tout * Cout, Cout), bias=b.cuda(), act=1, mask_len=lens.cuda(), mask=(1, 0, 0), tc=True)
+    assert rel(out.permute(0, 2, 1), ref) < 2e-5
