@@ -101,11 +101,11 @@ _PROTOS = {
     "ag_mt_rmsprop": [vp, vp, vp, i32, i32, vp, f32, f32, f32, f32, f32, vp],
     "ag_mt_adam": [vp, vp, vp, i32, i32, vp, f32, f32, f32, f32, f32, f32, i32, vp],
 }
-# optional entry points (tensor-core path); bound when the library exports them
-_OPTIONAL = {
+_PROTOS.update({
     "ag_gemm_nt_tc": [C.POINTER(GemmDesc), vp],
     "ag_gemm_tn_tc": [C.POINTER(GemmDesc), vp, i64, i32, vp],
-}
+})
+_OPTIONAL = {}
 
 _lib = None
 
