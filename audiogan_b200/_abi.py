@@ -50,6 +50,9 @@ class LstmDesc(C.Structure):
         ("w1t", vp), ("wxt", vp),
         ("barrier", vp),
         ("dh_ext_bs", i64),
+        ("prec", i32), ("reserved2", i32),
+        ("hbuf16", vp), ("xbuf16", vp), ("dgates16", vp), ("dpx16", vp),
+        ("dbg", vp),
     ]
 
 

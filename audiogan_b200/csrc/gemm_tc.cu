@@ -17,7 +17,7 @@
 namespace ag {
 namespace tc {
 
-constexpr int BM = 128, BK = 64, STAGES = 4, NTHREADS = 160, NPROD = 128;
+constexpr int BM = 128, BK = 64, NTHREADS = 160, NPROD = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -449,10 +449,11 @@ static int launch_nt(const ag_gemm_desc* d, cudaStream_t s) {
 // MMA operands are MN-major: a stage holds 64 m-rows; operand "A" = Y^T as two 64-wide n blocks, operand "B" =
 // the activation window as BNK/64 k blocks, each block [64 m-rows][128 B] with the 128B swizzle.
 template <int BNK, int MODEY, int MODEA>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const ag_gemm_desc d, float* __restrict__ dw, int64_t ldw,
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_desc d, float* __restrict__ dw, int64_t ldw,
                                                                 int ones_col, int64_t rows_per_split) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int STAGES = nt_stages(BNK);                   // 2-4 stages, <= 96 KB: two CTAs per SM
   constexpr int RM = 64;                                   // reduction rows per stage
   constexpr int A_BYTES = 2 * RM * 128, B_BYTES = (BNK / 64) * RM * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -609,10 +610,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const ag_gemm_d
 template <int BNK>
 static int launch_tn(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones_col, bool vy, bool va, cudaStream_t s) {
   constexpr int RM = 64;
+  constexpr int STAGES = nt_stages(BNK);
   constexpr int smem = STAGES * (2 * RM * 128 + (BNK / 64) * RM * 128) + 1024 + (2 * STAGES + 1) * 8 + 16 + 2 * STAGES * RM * 8;
   const int64_t ktot = d->K + (ones_col ? 1 : 0);
   const int64_t gx = (ktot + BNK - 1) / BNK, gy = (d->N + BM - 1) / BM;
-  int64_t want = (int64_t)sm_count() * 2 / (gx * gy);
+  int64_t want = (int64_t)sm_count() * 4 / (gx * gy);
   if (want < 1) want = 1;
   int64_t rows = (d->M + want - 1) / want;
   if (rows < 512) rows = 512;

@@ -14,6 +14,7 @@
 // the Bernoulli stop draw from supplied uniforms and the device-side early-exit flag -- no
 // host synchronisation per frame.
 #include "common.cuh"
+#include <algorithm>
 
 namespace ag {
 
@@ -41,7 +42,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(ctr, 1u);
-    while (ld_acquire_u32(ctr) < target) { __nanosleep(20); }
+    while (ld_acquire_u32(ctr) < target) { }
     __threadfence();
   }
   __syncthreads();
@@ -51,6 +52,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
 struct Seg {
   const float* p0; int64_t s0; int n0;
   const float* p1; int64_t s1; int n1;
+  const __nv_bfloat16* q0; const __nv_bfloat16* q1;   // bf16 shadow copies (same strides), bf16 mode only
 };
 
 __device__ __forceinline__ void stage_chunk(float* stage, int buf, const Seg& sg, int k0, int K, int b0, int B) {
@@ -77,11 +79,15 @@ __device__ __forceinline__ void slice_gemm(float (&acc)[RPT][8], const float* co
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int ks = (KS > 1) ? lane / (32 / KS) : 0;
   const int nch = (K + KC - 1) / KC;
-  stage_chunk(stage, 0, sg, 0, K, b0, B);
+  // every CTA walks the K chunks in a different rotation: right after a grid barrier all CTAs want the same [B, K]
+  // vector, and identical request streams serialise on the same L2 lines
+  const int rot = (int)((blockIdx.x * 5u) % (unsigned)nch);
+  auto kof = [&](int c) { int cc = c + rot; if (cc >= nch) cc -= nch; return cc * KC; };
+  stage_chunk(stage, 0, sg, kof(0), K, b0, B);
   cp_async_commit();
   for (int c = 0; c < nch; ++c) {
     if (c + 1 < nch) {
-      stage_chunk(stage, (c + 1) & 1, sg, (c + 1) * KC, K, b0, B);
+      stage_chunk(stage, (c + 1) & 1, sg, kof(c + 1), K, b0, B);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -91,7 +97,7 @@ __device__ __forceinline__ void slice_gemm(float (&acc)[RPT][8], const float* co
     const float* sb = stage + ((c & 1) * BTILE + w * 8) * SLD;
 #pragma unroll 4
     for (int i = ks; i < KC / 4; i += KS) {
-      const int k = c * KC + 4 * i;
+      const int k = kof(c) + 4 * i;
       if (k < K) {
         float4 wv[RPT];
 #pragma unroll
@@ -121,6 +127,216 @@ __device__ __forceinline__ void slice_gemm(float (&acc)[RPT][8], const float* co
   }
 }
 
+
+// Batched twin of warp_rows_dot: NB vectors at once (all their loads in flight together), nr <= 4 weight rows.
+// out[i][r] = <Wrows[r], vec[i]>.  fp32 weights/vectors; vec[i] == nullptr gives zeros.
+template <int NB>
+__device__ __forceinline__ void warp_rows_dot_nb(float (&out)[NB][4], const float* Wrows, int ldw, int nr,
+                                                 const float* const (&vec)[NB], int K4) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) { out[i][0] = 0.f; out[i][1] = 0.f; out[i][2] = 0.f; out[i][3] = 0.f; }
+  for (int k4 = lane; k4 < K4; k4 += 32) {
+    float4 v[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      v[i] = vec[i] ? __ldcg(reinterpret_cast<const float4*>(vec[i]) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (r < nr) {
+        const float4 q = *reinterpret_cast<const float4*>(Wrows + r * ldw + 4 * k4);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) out[i][r] += q.x * v[i].x + q.y * v[i].y + q.z * v[i].z + q.w * v[i].w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) out[i][r] = warp_sum(out[i][r]);
+}
+// bf16 weights (smem) and bf16 vectors (global, L2)
+template <int NB>
+__device__ __forceinline__ void warp_rows_dot16_nb(float (&out)[NB][4], const __nv_bfloat16* Wrows, int ldw, int nr,
+                                                   const __nv_bfloat16* const (&vec)[NB], int K8) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) { out[i][0] = 0.f; out[i][1] = 0.f; out[i][2] = 0.f; out[i][3] = 0.f; }
+  for (int k8 = lane; k8 < K8; k8 += 32) {
+    uint4 v[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      v[i] = vec[i] ? __ldcg(reinterpret_cast<const uint4*>(vec[i]) + k8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (r < nr) {
+        const uint4 q = *reinterpret_cast<const uint4*>(Wrows + r * ldw + 8 * k8);
+        const __nv_bfloat162* qp = reinterpret_cast<const __nv_bfloat162*>(&q);
+        float2 y[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) y[e] = __bfloat1622float2(qp[e]);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          const __nv_bfloat162* vp = reinterpret_cast<const __nv_bfloat162*>(&v[i]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 x = __bfloat1622float2(vp[e]);
+            out[i][r] = fmaf(x.x, y[e].x, out[i][r]);
+            out[i][r] = fmaf(x.y, y[e].y, out[i][r]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) out[i][r] = warp_sum(out[i][r]);
+}
+
+struct PhaseClock {
+  long long t0, acc[8];
+  __device__ __forceinline__ void start() { t0 = clock64(); }
+  __device__ __forceinline__ void lap(int i) { const long long t = clock64(); acc[i] += t - t0; t0 = t; }
+};
+
+// ------------------------------------------------------------------------------------ bf16 tensor-core variant
+// bf16 mode: the per-step [B, K] operand is read from bf16 shadow buffers through a 4-deep cp.async ring (the
+// fp32 variant's 2-deep ring exposes the L2 latency of every 64-column chunk), the resident weight slice is bf16,
+// and the products run on mma.sync.m16n8k16 (bf16 x bf16 -> fp32).  The recurrent state stays fp32.
+constexpr int NST_MIN = 4;        // cp.async ring depth: 4, 8 or 12 stages, the deepest that fits (runtime `nst`)
+constexpr int SLD16 = KC + 8;     // staged bf16 row stride (elements): 144 B rows, conflict-free fragment reads
+
+__host__ __device__ inline int pad_ld16(int K) {          // >= K rounded to a whole chunk, == 8 (mod 64): conflict-free
+  return (K + KC - 1) / KC * KC + 8;
+}
+
+// Per-thread view of the [B, K] bf16 operand for one (step, batch tile): each thread always copies the same two
+// (row, 16-byte column) cells of every chunk, so the row pointers are resolved once per step, not once per chunk.
+struct Stager16 {
+  const __nv_bfloat16* r0[2];   // row base inside segment 0 (nullptr = zeros)
+  const __nv_bfloat16* r1[2];   // row base inside segment 1, already shifted by -n0
+  int dst[2];                   // element offset inside a ring slot
+  int kk, n0, K;
+  __device__ __forceinline__ void init(const Seg& sg, int b0, int B, int K_) {
+    kk = (threadIdx.x & 7) << 3;
+    n0 = sg.n0;
+    K = K_;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int bl = (threadIdx.x + LT * i) >> 3, b = b0 + bl;
+      dst[i] = bl * SLD16 + kk;
+      const bool ok = b < B;
+      r0[i] = (ok && sg.q0) ? sg.q0 + b * sg.s0 : nullptr;
+      r1[i] = (ok && sg.q1) ? sg.q1 + b * sg.s1 - sg.n0 : nullptr;
+    }
+  }
+  __device__ __forceinline__ void issue(__nv_bfloat16* slot, int k0) const {
+    const int k = k0 + kk;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const __nv_bfloat16* base = (k < n0) ? r0[i] : r1[i];
+      if (base != nullptr && k < K) cp_async16(slot + dst[i], base + k);
+      else *reinterpret_cast<uint4*>(slot + dst[i]) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+};
+
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void cp_async_wait_dyn(int pending) {
+  if (pending >= 10) cp_async_wait<10>();
+  else if (pending >= 6) cp_async_wait<6>();
+  else cp_async_wait<2>();
+}
+
+// MT 16-row tiles of the weight slice x up to 8 batch tiles of 8.  Warp w owns row tile w % MT and the batch tiles
+// w / MT + (8 / MT) * i, i < MT, skipping those past the last valid batch.  acc[i] is an m16n8 fragment:
+// [0],[1] -> row g, batches 2t, 2t+1; [2],[3] -> row g+8.  All fragment loads of a chunk are issued before its MMAs.
+template <int MT>
+__device__ __forceinline__ void slice_gemm_mma(float (&acc)[MT][4], const __nv_bfloat16* Ws, int ldw, const Seg& sg, int K,
+                                               int b0, int B, __nv_bfloat16* stage, const int NST, PhaseClock* pc = nullptr) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int mt = w % MT, nt0 = w / MT;
+  constexpr int NSTEP = 8 / MT;                         // batch-tile stride between a warp's tiles
+  const int ntv = (min(B - b0, BTILE) + 7) >> 3;        // valid batch tiles in this batch tile
+  const int nch = (K + KC - 1) / KC;
+  const int rot = (int)((blockIdx.x * 5u) % (unsigned)nch);     // per-CTA chunk rotation (see slice_gemm)
+  auto kof = [&](int c) { int cc = c + rot; if (cc >= nch) cc -= nch; return cc * KC; };
+  Stager16 st;
+  st.init(sg, b0, B, K);
+  for (int s = 0; s < NST - 1; ++s) {
+    if (s < nch) st.issue(stage + s * BTILE * SLD16, kof(s));
+    cp_async_commit();
+  }
+  const __nv_bfloat16* wa = Ws + (mt * 16 + g) * ldw + 2 * t;
+  // independent mma.sync dependency chains per warp: MT tiles x NCH accumulator sets (k16 steps interleaved)
+  constexpr int NCH = MT >= 4 ? 1 : (MT == 2 ? 2 : 4);
+  float part[NCH][MT][4];
+#pragma unroll
+  for (int q = 0; q < NCH; ++q)
+#pragma unroll
+    for (int i = 0; i < MT; ++i) { part[q][i][0] = 0.f; part[q][i][1] = 0.f; part[q][i][2] = 0.f; part[q][i][3] = 0.f; }
+  for (int c = 0; c < nch; ++c) {
+    long long q0 = 0;
+    if (pc) q0 = clock64();
+    cp_async_wait_dyn(NST - 2);
+    __syncthreads();
+    if (pc) { const long long q1 = clock64(); pc->acc[5] += q1 - q0; q0 = q1; }
+    if (c + NST - 1 < nch) st.issue(stage + ((c + NST - 1) % NST) * BTILE * SLD16, kof(c + NST - 1));
+    cp_async_commit();
+    if (pc) { const long long q1 = clock64(); pc->acc[6] += q1 - q0; q0 = q1; }
+    const __nv_bfloat16* sb = stage + ((c % NST) * BTILE) * SLD16 + g * SLD16 + 2 * t;
+    const __nv_bfloat16* wk = wa + kof(c);
+    uint32_t af[KC / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < KC / 16; ++kk) {
+      af[kk][0] = *reinterpret_cast<const uint32_t*>(wk + kk * 16);
+      af[kk][1] = *reinterpret_cast<const uint32_t*>(wk + 8 * ldw + kk * 16);
+      af[kk][2] = *reinterpret_cast<const uint32_t*>(wk + kk * 16 + 8);
+      af[kk][3] = *reinterpret_cast<const uint32_t*>(wk + 8 * ldw + kk * 16 + 8);
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      const int nt = nt0 + NSTEP * i;
+      if (nt < ntv) {
+        uint32_t bf[KC / 16][2];
+#pragma unroll
+        for (int kk = 0; kk < KC / 16; ++kk) {
+          bf[kk][0] = *reinterpret_cast<const uint32_t*>(sb + nt * 8 * SLD16 + kk * 16);
+          bf[kk][1] = *reinterpret_cast<const uint32_t*>(sb + nt * 8 * SLD16 + kk * 16 + 8);
+        }
+#pragma unroll
+        for (int kk = 0; kk < KC / 16; ++kk)
+          mma_bf16(part[kk % NCH][i], af[kk][0], af[kk][1], af[kk][2], af[kk][3], bf[kk][0], bf[kk][1]);
+      }
+    }
+    if (pc) { const long long q1 = clock64(); pc->acc[7] += q1 - q0; }
+  }
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v = part[0][i][e];
+#pragma unroll
+      for (int q = 1; q < NCH; ++q) v += part[q][i][e];
+      acc[i][e] += v;
+    }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+// fp32 rows of a weight matrix -> bf16 resident slice (tail columns up to ldw zeroed)
+__device__ __forceinline__ void fill_slice16(__nv_bfloat16* Ws, int ldw, int lr, const float* src, int K) {
+  // called by all threads with the same (lr, src): columns strided over the block
+  for (int k = threadIdx.x; k < ldw; k += LT) Ws[lr * ldw + k] = __float2bfloat16(k < K ? src[k] : 0.f);
+}
+
 __host__ __device__ inline int pad_ld(int K) { return (K % 8 == 0) ? K + 4 : K; }   // K % 4 == 0 -> ld % 8 == 4
 
 // out[r] (r < nr <= 4) = <W2s[r], vec> with the K range split over the warp's lanes; every lane gets the sums.
@@ -138,10 +354,36 @@ __device__ __forceinline__ void warp_rows_dot(float (&out)[4], const float* Wrow
   out[0] = warp_sum(a0); out[1] = warp_sum(a1); out[2] = warp_sum(a2); out[3] = warp_sum(a3);
 }
 
+// bf16 twin of warp_rows_dot: weights rows (smem) and the vector (global, L2) are bf16, 8 elements per lane per step
+__device__ __forceinline__ void warp_rows_dot16(float (&out)[4], const __nv_bfloat16* Wrows, int ldw, int nr,
+                                                const __nv_bfloat16* vec, int K8) {
+  const int lane = threadIdx.x & 31;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k8 = lane; k8 < K8; k8 += 32) {
+    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(vec) + k8);
+    const __nv_bfloat162* vp = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (r < nr) {
+        const uint4 q = *reinterpret_cast<const uint4*>(Wrows + r * ldw + 8 * k8);
+        const __nv_bfloat162* qp = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 x = __bfloat1622float2(vp[e]), y = __bfloat1622float2(qp[e]);
+          a[r] = fmaf(x.x, y.x, a[r]);
+          a[r] = fmaf(x.y, y.y, a[r]);
+        }
+      }
+    }
+  }
+  out[0] = warp_sum(a[0]); out[1] = warp_sum(a[1]); out[2] = warp_sum(a[2]); out[3] = warp_sum(a[3]);
+}
+
 // =====================================================================================  forward
-template <int HS, bool FB, bool RES>
-__global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, const int ncta_dir, const int PR) {
+template <int HS, bool FB, bool RES, bool BF>
+__global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, const int ncta_dir, const int PR, const int NST, const int bsplit) {
   constexpr int ROWS = 4 * HS;
+  constexpr int MT = ROWS / 16 > 0 ? ROWS / 16 : 1;
   constexpr int RL = ROWS < 32 ? ROWS : 32;
   constexpr int KS = 32 / RL;
   constexpr int RPT = ROWS / RL;
@@ -149,20 +391,31 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int H = d.H, F = FB ? d.F : 0, K1 = H + F, ndir = d.ndir, B = d.B, T = d.T, Tcap = d.Tcap;
-  const int dir = blockIdx.x / ncta_dir, cta = blockIdx.x % ncta_dir, j0 = cta * HS;
+  // CTA = (direction, slice of HS hidden units, batch range): blockIdx.x = (dir * ncta_dir + slice) * bsplit + bs
+  const int grp = blockIdx.x / bsplit, bsi = blockIdx.x - grp * bsplit;
+  const int dir = grp / ncta_dir, cta = grp % ncta_dir, j0 = cta * HS;
+  const int Bper = (((B + bsplit - 1) / bsplit) + 7) & ~7;
+  const int blo = min(B, bsi * Bper), bhi = min(B, blo + Bper);
   const int ldw = pad_ld(K1), ld2 = pad_ld(H);
 
+  const int ldw16 = pad_ld16(K1);
+  // fp32: [Ws fp32][stage 2 x 64 x 68 fp32];  bf16: [Ws16 bf16][stage16 4 x 64 x 72 bf16]  (both multiples of 16 B)
   float* Ws = smem;
+  __nv_bfloat16* Ws16 = reinterpret_cast<__nv_bfloat16*>(smem);
   float* stage = Ws + (RES ? ROWS * ldw : 0);
-  float* gs = stage + 2 * BTILE * SLD;
-  float* cs = gs + BTILE * ROWS;
-  float* W2s = cs + B * HS;
+  __nv_bfloat16* stage16 = Ws16 + ROWS * ldw16;
+  // bf16: the gate exchange tile aliases the (idle) cp.async ring
+  float* gs = BF ? reinterpret_cast<float*>(stage16) : stage + 2 * BTILE * SLD;
+  float* cs = BF ? reinterpret_cast<float*>(stage16 + NST * BTILE * SLD16) : gs + BTILE * ROWS;
+  float* W2s = cs + Bper * HS;
   int* gen = reinterpret_cast<int*>(W2s + (FB ? PR * ld2 : 0));
   int* cnt = gen + B;
 
   // local row lr = jj*4 + q  <->  global gate row q*H + j0 + jj
   const float* w1d = d.w1 + (int64_t)dir * 4 * H * K1;
-  if (RES) {
+  if (BF) {
+    for (int lr = 0; lr < ROWS; ++lr) fill_slice16(Ws16, ldw16, lr, w1d + (int64_t)((lr & 3) * H + j0 + (lr >> 2)) * K1, K1);
+  } else if (RES) {
     const int K4 = K1 / 4;
     for (int idx = tid; idx < ROWS * K4; idx += LT) {
       const int lr = idx / K4, k4 = idx - lr * K4;
@@ -177,7 +430,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
     const int grow = (lr & 3) * H + j0 + (lr >> 2);
     wrow[rr] = RES ? (Ws + lr * ldw) : (w1d + (int64_t)grow * K1);
   }
-  for (int i = tid; i < B * HS; i += LT) cs[i] = 0.f;
+  for (int i = tid; i < Bper * HS; i += LT) cs[i] = 0.f;
   // phase-2 rows owned by this CTA (feedback only; ndir == 1)
   int p0 = 0, np = 0;
   bool owns_logit = false;
@@ -200,15 +453,21 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
   const int64_t gstr = (int64_t)Tcap * ndir * 4 * H;     // pre / gates batch stride
   const int64_t cstr = (int64_t)Tcap * ndir * H;         // cbuf batch stride
   int steps_run = T;
+  PhaseClock pc;
+  for (int i = 0; i < 8; ++i) pc.acc[i] = 0;
+  const long long tstart = clock64();
 
   for (int s = 0; s < T; ++s) {
+    pc.start();
     const int t = dir ? (T - 1 - s) : s;
     const int prow = dir ? (t + 2) : t;                  // hbuf row holding the previous h
     Seg sg;
     sg.p0 = d.hbuf + (int64_t)prow * ndir * H + dir * H; sg.s0 = hstr; sg.n0 = H;
     sg.p1 = FB ? (d.xbuf + (int64_t)t * F) : nullptr; sg.s1 = (int64_t)(Tcap + 1) * F; sg.n1 = F;
+    sg.q0 = BF ? reinterpret_cast<const __nv_bfloat16*>(d.hbuf16) + (int64_t)prow * ndir * H + dir * H : nullptr;
+    sg.q1 = (BF && FB) ? reinterpret_cast<const __nv_bfloat16*>(d.xbuf16) + (int64_t)t * F : nullptr;
 
-    for (int b0 = 0; b0 < B; b0 += BTILE) {
+    for (int b0 = blo; b0 < bhi; b0 += BTILE) {
       // prefetch this tile's input projections (independent of the recurrence)
       float pre[IPT > 0 ? IPT : 1][4];
 #pragma unroll
@@ -216,25 +475,42 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
         const int it = tid + LT * ii, bl = it / HS, jj = it - bl * HS, b = b0 + bl;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          pre[ii][q] = (b < B) ? d.pre[b * gstr + (int64_t)t * ndir * 4 * H + dir * 4 * H + q * H + j0 + jj] : 0.f;
+          pre[ii][q] = (b < bhi) ? d.pre[b * gstr + (int64_t)t * ndir * 4 * H + dir * 4 * H + q * H + j0 + jj] : 0.f;
       }
-      float acc[RPT][8];
+      if (BF) {
+        float accm[MT][4];
 #pragma unroll
-      for (int rr = 0; rr < RPT; ++rr)
+        for (int i = 0; i < MT; ++i) { accm[i][0] = 0.f; accm[i][1] = 0.f; accm[i][2] = 0.f; accm[i][3] = 0.f; }
+        slice_gemm_mma<MT>(accm, Ws16, ldw16, sg, K1, b0, bhi, stage16, NST, d.dbg ? &pc : nullptr);
+        pc.lap(0);
+        const int g = lane >> 2, tq = lane & 3, mt = w % MT, nt0 = w / MT;
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) acc[rr][nb] = 0.f;
-      slice_gemm<RPT, KS>(acc, wrow, sg, K1, b0, B, stage);
-      if (lane < RL) {
+        for (int i = 0; i < MT; ++i) {
+          const int bl = (nt0 + (8 / MT) * i) * 8 + 2 * tq, lr = mt * 16 + g;
+          gs[bl * ROWS + lr] = accm[i][0];
+          gs[(bl + 1) * ROWS + lr] = accm[i][1];
+          gs[bl * ROWS + lr + 8] = accm[i][2];
+          gs[(bl + 1) * ROWS + lr + 8] = accm[i][3];
+        }
+      } else {
+        float acc[RPT][8];
 #pragma unroll
         for (int rr = 0; rr < RPT; ++rr)
 #pragma unroll
-          for (int nb = 0; nb < 8; ++nb) gs[(w * 8 + nb) * ROWS + lane + RL * rr] = acc[rr][nb];
+          for (int nb = 0; nb < 8; ++nb) acc[rr][nb] = 0.f;
+        slice_gemm<RPT, KS>(acc, wrow, sg, K1, b0, bhi, stage);
+        if (lane < RL) {
+#pragma unroll
+          for (int rr = 0; rr < RPT; ++rr)
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) gs[(w * 8 + nb) * ROWS + lane + RL * rr] = acc[rr][nb];
+        }
       }
       __syncthreads();
 #pragma unroll
       for (int ii = 0; ii < IPT; ++ii) {
         const int it = tid + LT * ii, bl = it / HS, jj = it - bl * HS, b = b0 + bl;
-        if (b >= B) continue;
+        if (b >= bhi) continue;
         const int j = j0 + jj;
         const float4 a = *reinterpret_cast<const float4*>(gs + bl * ROWS + jj * 4);
         const bool valid = !d.len || t < d.len[b];
@@ -244,11 +520,12 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
           gf = sigmoidf_(a.y + pre[ii][1]);
           gg = tanhf(a.z + pre[ii][2]);
           go = sigmoidf_(a.w + pre[ii][3]);
-          c = gf * cs[b * HS + jj] + gi * gg;
+          c = gf * cs[(b - blo) * HS + jj] + gi * gg;
           h = go * tanhf(c);
-          cs[b * HS + jj] = c;
+          cs[(b - blo) * HS + jj] = c;
         }
         d.hbuf[b * hstr + (int64_t)(t + 1) * ndir * H + dir * H + j] = h;
+        if (d.hbuf16) reinterpret_cast<__nv_bfloat16*>(d.hbuf16)[b * hstr + (int64_t)(t + 1) * ndir * H + dir * H + j] = __float2bfloat16(h);
         if (d.cbuf) d.cbuf[b * cstr + (int64_t)t * ndir * H + dir * H + j] = c;
         if (d.gates) {
           float* gp = d.gates + b * gstr + (int64_t)t * ndir * 4 * H + dir * 4 * H + j;
@@ -257,29 +534,46 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
       }
       __syncthreads();
     }
-    grid_barrier(bar, (++nbar) * ncta_dir);
+    pc.lap(1);
+    grid_barrier(bar, (++nbar) * ncta_dir * bsplit);
+    pc.lap(2);
 
     if (FB) {
       // phase 2: x_t = tanh(wp h_t + bp), logit = ws h_t + bs, stop draw, early-exit flag
       if (np > 0) {
-        for (int b = w; b < B; b += LT / 32) {
-          const float* hrow = d.hbuf + b * hstr + (int64_t)(t + 1) * H;
+        constexpr int NB = 8;                                      // batches in flight per warp
+        for (int bi0 = w; bi0 < B; bi0 += NB * (LT / 32)) {
+          const float* hrow[NB];
+          int bb[NB];
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
+            const int bi = bi0 + i * (LT / 32);
+            bb[i] = bi < B ? (bi + (int)blockIdx.x) % B : -1;      // per-CTA rotation of the batch order
+            hrow[i] = bb[i] >= 0 ? d.hbuf + bb[i] * hstr + (int64_t)(t + 1) * H : nullptr;
+          }
           for (int pp = 0; pp < np; pp += 4) {
-            float o[4];
+            float o[NB][4];
             const int nr = min(4, np - pp);
-            warp_rows_dot(o, W2s + pp * ld2, ld2, nr, hrow, H / 4);
+            warp_rows_dot_nb<NB>(o, W2s + pp * ld2, ld2, nr, hrow, H / 4);
             if (lane == 0) {
-              for (int r = 0; r < nr; ++r) {
-                const int p = p0 + pp + r;
-                const float v = o[r] + d.b2[p];
-                if (p < F) {
-                  d.xbuf[(b * (int64_t)(Tcap + 1) + t + 1) * F + p] = tanhf(v);
-                } else {
-                  if (d.sbuf) d.sbuf[b * (int64_t)Tcap + t] = v;
-                  const int stop = (d.u && d.u[b * (int64_t)Tcap + t] < sigmoidf_(v)) ? 1 : 0;
-                  if (d.stop) d.stop[b * (int64_t)Tcap + t] = stop;
-                  if (gen[b]) cnt[b] += 1;
-                  if (stop) gen[b] = 0;
+#pragma unroll
+              for (int i = 0; i < NB; ++i) {
+                const int b = bb[i];
+                if (b < 0) continue;
+                for (int r = 0; r < nr; ++r) {
+                  const int p = p0 + pp + r;
+                  const float v = o[i][r] + d.b2[p];
+                  if (p < F) {
+                    const float xv = tanhf(v);
+                    d.xbuf[(b * (int64_t)(Tcap + 1) + t + 1) * F + p] = xv;
+                    if (d.xbuf16) reinterpret_cast<__nv_bfloat16*>(d.xbuf16)[(b * (int64_t)(Tcap + 1) + t + 1) * F + p] = __float2bfloat16(xv);
+                  } else {
+                    if (d.sbuf) d.sbuf[b * (int64_t)Tcap + t] = v;
+                    const int stop = (d.u && d.u[b * (int64_t)Tcap + t] < sigmoidf_(v)) ? 1 : 0;
+                    if (d.stop) d.stop[b * (int64_t)Tcap + t] = stop;
+                    if (gen[b]) cnt[b] += 1;
+                    if (stop) gen[b] = 0;
+                  }
                 }
               }
             }
@@ -293,10 +587,17 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
         const int any = __syncthreads_or(g);
         if (!any && tid == 0) *reinterpret_cast<volatile int*>(d.t_end) = t + 1;
       }
-      grid_barrier(bar, (++nbar) * ncta_dir);
+      pc.lap(3);
+      grid_barrier(bar, (++nbar) * ncta_dir * bsplit);
+      pc.lap(2);
       const int te = *reinterpret_cast<volatile int*>(d.t_end);
       if (te != 0) { steps_run = te; break; }
     }
+  }
+  if (d.dbg && tid == 0) {
+    long long* q = d.dbg + (int64_t)blockIdx.x * 8;
+    for (int i = 0; i < 8; ++i) q[i] = pc.acc[i];
+    q[4] = clock64() - tstart;
   }
   if (FB && owns_logit) {
     __syncthreads();
@@ -306,26 +607,35 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
 }
 
 // ====================================================================================  backward
-template <int HS, bool FB, bool RES>
-__global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, const int ncta_dir, const int PR) {
+template <int HS, bool FB, bool RES, bool BF>
+__global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, const int ncta_dir, const int PR, const int NST, const int bsplit) {
   constexpr int RL = HS;            // 4, 8 or 16 rows -> k split over the rest of the warp
   constexpr int KS = 32 / RL;
   constexpr int IPT = (BTILE * HS) / LT;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int H = d.H, F = FB ? d.F : 0, FP = FB ? ((F + 1 + 3) / 4) * 4 : 0, K = 4 * H + FP;
+  const int H = d.H, F = FB ? d.F : 0, FP = FB ? ((F + 1 + 7) / 8) * 8 : 0, K = 4 * H + FP;
   const int ndir = d.ndir, B = d.B, T = d.T, Tcap = d.Tcap;
-  const int dir = blockIdx.x / ncta_dir, cta = blockIdx.x % ncta_dir, j0 = cta * HS;
+  const int grp = blockIdx.x / bsplit, bsi = blockIdx.x - grp * bsplit;
+  const int dir = grp / ncta_dir, cta = grp % ncta_dir, j0 = cta * HS;
+  const int Bper = (((B + bsplit - 1) / bsplit) + 7) & ~7;
+  const int blo = min(B, bsi * Bper), bhi = min(B, blo + Bper);
+  constexpr int MT = HS / 16 > 0 ? HS / 16 : 1;
   const int ldw = pad_ld(K), ldx = pad_ld(4 * H);
 
+  const int ldw16 = pad_ld16(K);
   float* Ws = smem;
+  __nv_bfloat16* Ws16 = reinterpret_cast<__nv_bfloat16*>(smem);
   float* stage = Ws + (RES ? HS * ldw : 0);
-  float* dhs = stage + 2 * BTILE * SLD;
-  float* dcs = dhs + BTILE * HS;
-  float* Wxs = dcs + B * HS;
+  __nv_bfloat16* stage16 = Ws16 + HS * ldw16;
+  float* dhs = BF ? reinterpret_cast<float*>(stage16) : stage + 2 * BTILE * SLD;      // bf16: aliases the idle ring
+  float* dcs = BF ? reinterpret_cast<float*>(stage16 + NST * BTILE * SLD16) : dhs + BTILE * HS;
+  float* Wxs = dcs + Bper * HS;
 
   const float* w1d = d.w1t + ((int64_t)dir * H + j0) * K;
-  if (RES) {
+  if (BF) {
+    for (int lr = 0; lr < HS; ++lr) fill_slice16(Ws16, ldw16, lr, w1d + (int64_t)lr * K, K);
+  } else if (RES) {
     const int K4 = K / 4;
     for (int idx = tid; idx < HS * K4; idx += LT) {
       const int lr = idx / K4, k4 = idx - lr * K4;
@@ -334,15 +644,23 @@ __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, c
   }
   const float* wrow[1];
   wrow[0] = RES ? (Ws + (lane % RL) * ldw) : (w1d + (int64_t)(lane % RL) * K);
-  for (int i = tid; i < B * HS; i += LT) dcs[i] = 0.f;
+  for (int i = tid; i < Bper * HS; i += LT) dcs[i] = 0.f;
   int p0 = 0, np = 0;
   if (FB) {
     p0 = blockIdx.x * PR;
     np = min(PR, F - p0);
     if (np < 0) np = 0;
-    for (int idx = tid; idx < np * H; idx += LT) {       // H float4 per row of wxt (4H floats)
-      const int r = idx / H, k4 = idx - r * H;
-      *reinterpret_cast<float4*>(Wxs + r * ldx + 4 * k4) = *reinterpret_cast<const float4*>(d.wxt + (int64_t)(p0 + r) * 4 * H + 4 * k4);
+    if (BF) {                                            // bf16 rows of wx^T, stride 4H + 8
+      __nv_bfloat16* Wxs16 = reinterpret_cast<__nv_bfloat16*>(Wxs);
+      for (int idx = tid; idx < np * 4 * H; idx += LT) {
+        const int r = idx / (4 * H), k = idx - r * 4 * H;
+        Wxs16[r * (4 * H + 8) + k] = __float2bfloat16(d.wxt[(int64_t)(p0 + r) * 4 * H + k]);
+      }
+    } else {
+      for (int idx = tid; idx < np * H; idx += LT) {     // H float4 per row of wxt (4H floats)
+        const int r = idx / H, k4 = idx - r * H;
+        *reinterpret_cast<float4*>(Wxs + r * ldx + 4 * k4) = *reinterpret_cast<const float4*>(d.wxt + (int64_t)(p0 + r) * 4 * H + 4 * k4);
+      }
     }
   }
   __syncthreads();
@@ -352,7 +670,11 @@ __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, c
   const int64_t gstr = (int64_t)Tcap * ndir * 4 * H;
   const int64_t cstr = (int64_t)Tcap * ndir * H;
 
+  PhaseClock pc;
+  for (int i = 0; i < 8; ++i) pc.acc[i] = 0;
+  const long long tstart = clock64();
   for (int s = 0; s < T; ++s) {
+    pc.start();
     const int t = dir ? s : (T - 1 - s);                 // reverse of the forward order
     const int tn = dir ? (t - 1) : (t + 1);              // the step processed just before this one
     const bool has_next = s > 0;
@@ -360,19 +682,38 @@ __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, c
     if (FB) {
       // phase A: dpx[b,t,p] = (dx_ext + wx^T dgates_{t+1})[p] * (1 - x_t[p]^2); column F = ds_ext
       if (np > 0) {
-        for (int b = w; b < B; b += LT / 32) {
-          const float* dgrow = d.dgates + b * gstr + (int64_t)tn * 4 * H;
+        constexpr int NB = 8;
+        for (int bi0 = w; bi0 < B; bi0 += NB * (LT / 32)) {
+          const float* dgrow[NB];
+          const __nv_bfloat16* dgrow16[NB];
+          int bb[NB];
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
+            const int bi = bi0 + i * (LT / 32);
+            bb[i] = bi < B ? (bi + (int)blockIdx.x) % B : -1;
+            dgrow[i] = (bb[i] >= 0 && has_next) ? d.dgates + bb[i] * gstr + (int64_t)tn * 4 * H : nullptr;
+            dgrow16[i] = (BF && bb[i] >= 0 && has_next)
+                             ? reinterpret_cast<const __nv_bfloat16*>(d.dgates16) + bb[i] * gstr + (int64_t)tn * 4 * H : nullptr;
+          }
           for (int pp = 0; pp < np; pp += 4) {
-            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            float o[NB][4];
             const int nr = min(4, np - pp);
-            if (has_next) warp_rows_dot(o, Wxs + pp * ldx, ldx, nr, dgrow, H);
+            if (BF) warp_rows_dot16_nb<NB>(o, reinterpret_cast<const __nv_bfloat16*>(Wxs) + pp * (4 * H + 8), 4 * H + 8, nr, dgrow16, H / 2);
+            else warp_rows_dot_nb<NB>(o, Wxs + pp * ldx, ldx, nr, dgrow, H);
             if (lane == 0) {
-              for (int r = 0; r < nr; ++r) {
-                const int p = p0 + pp + r;
-                float dx = o[r];
-                if (d.dx_ext) dx += d.dx_ext[(b * (int64_t)Tcap + t) * F + p];
-                const float x = d.xbuf[(b * (int64_t)(Tcap + 1) + t + 1) * F + p];
-                d.dpx[(b * (int64_t)Tcap + t) * FP + p] = dx * (1.f - x * x);
+#pragma unroll
+              for (int i = 0; i < NB; ++i) {
+                const int b = bb[i];
+                if (b < 0) continue;
+                for (int r = 0; r < nr; ++r) {
+                  const int p = p0 + pp + r;
+                  float dx = o[i][r];
+                  if (d.dx_ext) dx += d.dx_ext[(b * (int64_t)Tcap + t) * F + p];
+                  const float x = d.xbuf[(b * (int64_t)(Tcap + 1) + t + 1) * F + p];
+                  const float dpv = dx * (1.f - x * x);
+                  d.dpx[(b * (int64_t)Tcap + t) * FP + p] = dpv;
+                  if (d.dpx16) reinterpret_cast<__nv_bfloat16*>(d.dpx16)[(b * (int64_t)Tcap + t) * FP + p] = __float2bfloat16(dpv);
+                }
               }
             }
           }
@@ -383,60 +724,115 @@ __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, c
           float* q = d.dpx + (b * (int64_t)Tcap + t) * FP;
           q[F] = d.ds_ext ? d.ds_ext[b * (int64_t)Tcap + t] : 0.f;
           for (int p = F + 1; p < FP; ++p) q[p] = 0.f;
+          if (d.dpx16) {
+            __nv_bfloat16* q16 = reinterpret_cast<__nv_bfloat16*>(d.dpx16) + (b * (int64_t)Tcap + t) * FP;
+            for (int p = F; p < FP; ++p) q16[p] = __float2bfloat16(q[p]);
+          }
         }
       }
-      grid_barrier(bar, (++nbar) * ncta_dir);
+      pc.lap(3);
+      grid_barrier(bar, (++nbar) * ncta_dir * bsplit);
+      pc.lap(2);
     }
 
     // phase B: dh = dh_ext + whh^T dgates_next (+ wp^T dpx_t + ws ds_t), then the cell backward
     Seg sg;
     sg.p0 = has_next ? (d.dgates + (int64_t)tn * ndir * 4 * H + dir * 4 * H) : nullptr; sg.s0 = gstr; sg.n0 = 4 * H;
     sg.p1 = FB ? (d.dpx + (int64_t)t * FP) : nullptr; sg.s1 = (int64_t)Tcap * FP; sg.n1 = FP;
-    for (int b0 = 0; b0 < B; b0 += BTILE) {
-      float acc[1][8];
+    sg.q0 = (BF && has_next) ? reinterpret_cast<const __nv_bfloat16*>(d.dgates16) + (int64_t)tn * ndir * 4 * H + dir * 4 * H : nullptr;
+    sg.q1 = (BF && FB) ? reinterpret_cast<const __nv_bfloat16*>(d.dpx16) + (int64_t)t * FP : nullptr;
+    for (int b0 = blo; b0 < bhi; b0 += BTILE) {
+      // prefetch what the cell backward needs (saved gates, c_t, c_prev, external dh): independent of this step's GEMM
+      float pg[IPT > 0 ? IPT : 1][7];
+      bool pv[IPT > 0 ? IPT : 1];
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb) acc[0][nb] = 0.f;
-      if (has_next || FB) slice_gemm<1, KS>(acc, wrow, sg, K, b0, B, stage);
-      if (lane < RL) {
+      for (int ii = 0; ii < IPT; ++ii) {
+        const int it = tid + LT * ii, bl = it / HS, jj = it - bl * HS, b = b0 + bl, j = j0 + jj;
+        pv[ii] = false;
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) dhs[(w * 8 + nb) * HS + lane] = acc[0][nb];
+        for (int e = 0; e < 7; ++e) pg[ii][e] = 0.f;
+        if (b < bhi) {
+          const int Lb = d.len ? min(d.len[b], T) : T;
+          if (t < Lb) {
+            pv[ii] = true;
+            const float* gp = d.gates + b * gstr + (int64_t)t * ndir * 4 * H + dir * 4 * H + j;
+            pg[ii][0] = gp[0]; pg[ii][1] = gp[H]; pg[ii][2] = gp[2 * H]; pg[ii][3] = gp[3 * H];
+            pg[ii][4] = d.cbuf[b * cstr + (int64_t)t * ndir * H + dir * H + j];
+            const int tp = dir ? (t + 1) : (t - 1);
+            const bool has_prev = dir ? (tp < Lb) : (tp >= 0);
+            pg[ii][5] = has_prev ? d.cbuf[b * cstr + (int64_t)tp * ndir * H + dir * H + j] : 0.f;
+            pg[ii][6] = d.dh_ext ? d.dh_ext[b * (d.dh_ext_bs ? d.dh_ext_bs : cstr) + (int64_t)t * ndir * H + dir * H + j] : 0.f;
+          }
+        }
+      }
+      if (BF) {
+        float accm[MT][4];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) { accm[i][0] = 0.f; accm[i][1] = 0.f; accm[i][2] = 0.f; accm[i][3] = 0.f; }
+        if (has_next || FB) slice_gemm_mma<MT>(accm, Ws16, ldw16, sg, K, b0, bhi, stage16, NST, d.dbg ? &pc : nullptr);
+        pc.lap(0);
+        if (HS >= 16) {
+          const int g = lane >> 2, tq = lane & 3, mt = w % MT, nt0 = w / MT;
+#pragma unroll
+          for (int i = 0; i < MT; ++i) {
+            const int bl = (nt0 + (8 / MT) * i) * 8 + 2 * tq, lr = mt * 16 + g;
+            dhs[bl * HS + lr] = accm[i][0];
+            dhs[(bl + 1) * HS + lr] = accm[i][1];
+            dhs[bl * HS + lr + 8] = accm[i][2];
+            dhs[(bl + 1) * HS + lr + 8] = accm[i][3];
+          }
+        }
+      } else {
+        float acc[1][8];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) acc[0][nb] = 0.f;
+        if (has_next || FB) slice_gemm<1, KS>(acc, wrow, sg, K, b0, bhi, stage);
+        if (lane < RL) {
+#pragma unroll
+          for (int nb = 0; nb < 8; ++nb) dhs[(w * 8 + nb) * HS + lane] = acc[0][nb];
+        }
       }
       __syncthreads();
 #pragma unroll
       for (int ii = 0; ii < IPT; ++ii) {
         const int it = tid + LT * ii, bl = it / HS, jj = it - bl * HS, b = b0 + bl;
-        if (b >= B) continue;
+        if (b >= bhi) continue;
         const int j = j0 + jj;
-        const int Lb = d.len ? min(d.len[b], T) : T;
         float* dg = d.dgates + b * gstr + (int64_t)t * ndir * 4 * H + dir * 4 * H + j;
-        if (t >= Lb) {
+        __nv_bfloat16* dg16 = d.dgates16 ? reinterpret_cast<__nv_bfloat16*>(d.dgates16) + b * gstr + (int64_t)t * ndir * 4 * H + dir * 4 * H + j : nullptr;
+        if (!pv[ii]) {
           dg[0] = 0.f; dg[H] = 0.f; dg[2 * H] = 0.f; dg[3 * H] = 0.f;
+          if (dg16) { const __nv_bfloat16 z = __float2bfloat16(0.f); dg16[0] = z; dg16[H] = z; dg16[2 * H] = z; dg16[3 * H] = z; }
           continue;
         }
-        const float* gp = d.gates + b * gstr + (int64_t)t * ndir * 4 * H + dir * 4 * H + j;
-        const float gi = gp[0], gf = gp[H], gg = gp[2 * H], go = gp[3 * H];
-        const float c = d.cbuf[b * cstr + (int64_t)t * ndir * H + dir * H + j];
-        const int tp = dir ? (t + 1) : (t - 1);
-        const bool has_prev = dir ? (tp < Lb) : (tp >= 0);
-        const float cprev = has_prev ? d.cbuf[b * cstr + (int64_t)tp * ndir * H + dir * H + j] : 0.f;
-        float dh = dhs[bl * HS + jj];
-        if (d.dh_ext) dh += d.dh_ext[b * (d.dh_ext_bs ? d.dh_ext_bs : cstr) + (int64_t)t * ndir * H + dir * H + j];
+        const float gi = pg[ii][0], gf = pg[ii][1], gg = pg[ii][2], go = pg[ii][3], c = pg[ii][4], cprev = pg[ii][5];
+        const float dh = dhs[bl * HS + jj] + pg[ii][6];
         const float tc = tanhf(c);
-        const float dc = dcs[b * HS + jj] + dh * go * (1.f - tc * tc);
-        dcs[b * HS + jj] = dc * gf;
-        dg[0] = dc * gg * gi * (1.f - gi);
-        dg[H] = dc * cprev * gf * (1.f - gf);
-        dg[2 * H] = dc * gi * (1.f - gg * gg);
-        dg[3 * H] = dh * tc * go * (1.f - go);
+        const float dc = dcs[(b - blo) * HS + jj] + dh * go * (1.f - tc * tc);
+        dcs[(b - blo) * HS + jj] = dc * gf;
+        const float di = dc * gg * gi * (1.f - gi), df = dc * cprev * gf * (1.f - gf);
+        const float dgg = dc * gi * (1.f - gg * gg), dgo = dh * tc * go * (1.f - go);
+        dg[0] = di; dg[H] = df; dg[2 * H] = dgg; dg[3 * H] = dgo;
+        if (dg16) {
+          dg16[0] = __float2bfloat16(di); dg16[H] = __float2bfloat16(df);
+          dg16[2 * H] = __float2bfloat16(dgg); dg16[3 * H] = __float2bfloat16(dgo);
+        }
       }
       __syncthreads();
     }
-    grid_barrier(bar, (++nbar) * ncta_dir);
+    pc.lap(1);
+    grid_barrier(bar, (++nbar) * ncta_dir * bsplit);
+    pc.lap(2);
+  }
+  if (d.dbg && tid == 0) {
+    long long* q = d.dbg + (int64_t)blockIdx.x * 8;
+    for (int i = 0; i < 8; ++i) q[i] = pc.acc[i];
+    q[4] = clock64() - tstart;
   }
 }
 
 // ---------------------------------------------------------------------------------- host side
-struct Plan { int HS, ncta_dir, PR; bool res; size_t smem; };
+struct Plan { int HS, ncta_dir, PR, nst, bsplit; bool res, bf; size_t smem; };
 
 static int pick_hs(int H, int ndir) {
   const int hs_opts[3] = {4, 8, 16};
@@ -447,17 +843,19 @@ static int pick_hs(int H, int ndir) {
   return 0;
 }
 
-static size_t fwd_smem(const ag_lstm_desc* d, int HS, int PR, bool res) {
+static size_t fwd_smem(const ag_lstm_desc* d, int HS, int PR, bool res, bool bf = false, int NST = NST_MIN) {
   const int F = d->F, K1 = d->H + F;
-  size_t fl = (res ? (size_t)4 * HS * pad_ld(K1) : 0) + 2 * BTILE * SLD + (size_t)BTILE * 4 * HS + (size_t)d->B * HS +
-              (F > 0 ? (size_t)PR * pad_ld(d->H) : 0);
-  return fl * 4 + (size_t)2 * d->B * 4 + 16;
+  size_t fl = (bf ? 0 : (size_t)BTILE * 4 * HS) + (size_t)(d->B + 8) * HS + (F > 0 ? (size_t)PR * pad_ld(d->H) : 0);
+  size_t head = bf ? ((size_t)4 * HS * pad_ld16(K1) + (size_t)NST * BTILE * SLD16) * 2
+                   : ((res ? (size_t)4 * HS * pad_ld(K1) : 0) + 2 * BTILE * SLD) * 4;
+  return head + fl * 4 + (size_t)2 * d->B * 4 + 16;
 }
-static size_t bwd_smem(const ag_lstm_desc* d, int HS, int PR, bool res) {
-  const int F = d->F, FP = F > 0 ? ((F + 1 + 3) / 4) * 4 : 0, K = 4 * d->H + FP;
-  size_t fl = (res ? (size_t)HS * pad_ld(K) : 0) + 2 * BTILE * SLD + (size_t)BTILE * HS + (size_t)d->B * HS +
-              (F > 0 ? (size_t)PR * pad_ld(4 * d->H) : 0);
-  return fl * 4 + 16;
+static size_t bwd_smem(const ag_lstm_desc* d, int HS, int PR, bool res, bool bf = false, int NST = NST_MIN) {
+  const int F = d->F, FP = F > 0 ? ((F + 1 + 7) / 8) * 8 : 0, K = 4 * d->H + FP;
+  size_t fl = (bf ? 0 : (size_t)BTILE * HS) + (size_t)(d->B + 8) * HS + (F > 0 ? (bf ? (size_t)PR * (2 * d->H + 4) : (size_t)PR * pad_ld(4 * d->H)) : 0);
+  size_t head = bf ? ((size_t)HS * pad_ld16(K) + (size_t)NST * BTILE * SLD16) * 2
+                   : ((res ? (size_t)HS * pad_ld(K) : 0) + 2 * BTILE * SLD) * 4;
+  return head + fl * 4 + 16;
 }
 
 static int check_lstm(const ag_lstm_desc* d, const char* who, bool bwd) {
@@ -480,25 +878,25 @@ template <typename KernT>
 static int launch_coop(KernT kern, const ag_lstm_desc* d, const Plan& p, cudaStream_t s) {
   AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   ag_lstm_desc dd = *d;
-  int ncta_dir = p.ncta_dir, PR = p.PR;
-  void* args[3] = {&dd, &ncta_dir, &PR};
-  AG_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)(p.ncta_dir * d->ndir)), dim3(LT), args, p.smem, s));
+  int ncta_dir = p.ncta_dir, PR = p.PR, nst = p.nst, bsplit = p.bsplit;
+  void* args[5] = {&dd, &ncta_dir, &PR, &nst, &bsplit};
+  AG_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)(p.ncta_dir * d->ndir * p.bsplit)), dim3(LT), args, p.smem, s));
   return AG_OK;
 }
 
-#define AG_LSTM_DISPATCH(KERN)                                                                      \
-  do {                                                                                              \
-    const bool fb = d->F > 0;                                                                       \
-    if (p.HS == 4) {                                                                                \
-      if (fb) return p.res ? launch_coop(KERN<4, true, true>, d, p, s) : launch_coop(KERN<4, true, false>, d, p, s);     \
-      return p.res ? launch_coop(KERN<4, false, true>, d, p, s) : launch_coop(KERN<4, false, false>, d, p, s);           \
-    } else if (p.HS == 8) {                                                                         \
-      if (fb) return p.res ? launch_coop(KERN<8, true, true>, d, p, s) : launch_coop(KERN<8, true, false>, d, p, s);     \
-      return p.res ? launch_coop(KERN<8, false, true>, d, p, s) : launch_coop(KERN<8, false, false>, d, p, s);           \
-    } else {                                                                                        \
-      if (fb) return p.res ? launch_coop(KERN<16, true, true>, d, p, s) : launch_coop(KERN<16, true, false>, d, p, s);   \
-      return p.res ? launch_coop(KERN<16, false, true>, d, p, s) : launch_coop(KERN<16, false, false>, d, p, s);         \
-    }                                                                                               \
+#define AG_LSTM_DISPATCH_HS(KERN, HS_)                                                                               \
+  do {                                                                                                              \
+    if (p.bf) return fb ? launch_coop(KERN<HS_, true, true, true>, d, p, s) : launch_coop(KERN<HS_, false, true, true>, d, p, s); \
+    if (fb) return p.res ? launch_coop(KERN<HS_, true, true, false>, d, p, s) : launch_coop(KERN<HS_, true, false, false>, d, p, s); \
+    return p.res ? launch_coop(KERN<HS_, false, true, false>, d, p, s) : launch_coop(KERN<HS_, false, false, false>, d, p, s);     \
+  } while (0)
+#define AG_LSTM_DISPATCH(KERN)          \
+  do {                                  \
+    const bool fb = d->F > 0;           \
+    if (p.HS == 4) AG_LSTM_DISPATCH_HS(KERN, 4);  \
+    if (p.HS == 8) AG_LSTM_DISPATCH_HS(KERN, 8);  \
+    if (p.HS == 16) AG_LSTM_DISPATCH_HS(KERN, 16);  \
+    AG_LSTM_DISPATCH_HS(KERN, 32);      \
   } while (0)
 
 static int run_fwd(const ag_lstm_desc* d, const Plan& p, cudaStream_t s) { AG_LSTM_DISPATCH(lstm_fwd_kernel); }
@@ -513,14 +911,34 @@ int ag_lstm_fwd(const ag_lstm_desc* d, void* stream) {
   int rc = check_lstm(d, "ag_lstm_fwd", false);
   if (rc) return rc;
   Plan p;
-  p.HS = pick_hs(d->H, d->ndir);
-  AG_CHECK_ARG(p.HS > 0, "ag_lstm_fwd: H=%d (ndir %d) does not map onto %d SMs", d->H, d->ndir, sm_count());
-  p.ncta_dir = d->H / p.HS;
-  const int ncta = p.ncta_dir * d->ndir;
-  p.PR = d->F > 0 ? (d->F + 1 + ncta - 1) / ncta : 0;
-  p.res = true;
-  p.smem = fwd_smem(d, p.HS, p.PR, true);
-  if (p.smem > (size_t)smem_optin()) { p.res = false; p.smem = fwd_smem(d, p.HS, p.PR, false); }
+  p.res = true; p.bf = false; p.nst = NST_MIN; p.bsplit = 1; p.HS = 0;
+  const int nsm = sm_count();
+  auto pr_for = [&](int ncta) { return d->F > 0 ? (d->F + 1 + ncta - 1) / ncta : 0; };
+  if (d->prec == 1 && d->H % 8 == 0 && d->F % 8 == 0) {
+    // tensor-core variant: the largest slice whose bf16 weights stay resident (fewest re-reads of the [B, K] operand
+    // per step), then split the batch over the remaining SMs (>= 8 samples per CTA)
+    const int opts[4] = {32, 16, 8, 4};
+    for (int i = 0; i < 4 && !p.bf; ++i) {
+      const int hs = opts[i];
+      if (d->H % hs || (int64_t)d->ndir * (d->H / hs) > nsm) continue;
+      const int groups = d->ndir * (d->H / hs);
+      int bs = nsm / groups;
+      bs = std::max(1, std::min(bs, (d->B + 7) / 8));
+      const int pr = pr_for(groups * bs);
+      const size_t sm16 = fwd_smem(d, hs, pr, true, true);
+      if (sm16 > (size_t)smem_optin()) continue;
+      AG_CHECK_ARG(d->hbuf16 && (d->F == 0 || d->xbuf16), "ag_lstm_fwd: bf16 mode needs hbuf16 / xbuf16");
+      p.bf = true; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm16;
+    }
+  }
+  if (!p.bf) {
+    p.HS = pick_hs(d->H, d->ndir);
+    AG_CHECK_ARG(p.HS > 0, "ag_lstm_fwd: H=%d (ndir %d) does not map onto %d SMs", d->H, d->ndir, nsm);
+    p.ncta_dir = d->H / p.HS;
+    p.PR = pr_for(p.ncta_dir * d->ndir);
+    p.smem = fwd_smem(d, p.HS, p.PR, true);
+    if (p.smem > (size_t)smem_optin()) { p.res = false; p.smem = fwd_smem(d, p.HS, p.PR, false); }
+  }
   AG_CHECK_ARG(p.smem <= (size_t)smem_optin(), "ag_lstm_fwd: needs %zu B of shared memory", p.smem);
   cudaStream_t s = (cudaStream_t)stream;
   AG_CUDA(cudaMemsetAsync(d->barrier, 0, 8 * sizeof(unsigned), s));
@@ -532,14 +950,32 @@ int ag_lstm_bwd(const ag_lstm_desc* d, void* stream) {
   int rc = check_lstm(d, "ag_lstm_bwd", true);
   if (rc) return rc;
   Plan p;
-  p.HS = pick_hs(d->H, d->ndir);
-  AG_CHECK_ARG(p.HS > 0, "ag_lstm_bwd: H=%d (ndir %d) does not map onto %d SMs", d->H, d->ndir, sm_count());
-  p.ncta_dir = d->H / p.HS;
-  const int ncta = p.ncta_dir * d->ndir;
-  p.PR = d->F > 0 ? (d->F + ncta - 1) / ncta : 0;
-  p.res = true;
-  p.smem = bwd_smem(d, p.HS, p.PR, true);
-  if (p.smem > (size_t)smem_optin()) { p.res = false; p.smem = bwd_smem(d, p.HS, p.PR, false); }
+  p.res = true; p.bf = false; p.nst = NST_MIN; p.bsplit = 1; p.HS = 0;
+  const int nsm = sm_count();
+  auto pr_for = [&](int ncta) { return d->F > 0 ? (d->F + ncta - 1) / ncta : 0; };
+  if (d->prec == 1) {
+    const int opts[2] = {32, 16};
+    for (int i = 0; i < 2 && !p.bf; ++i) {
+      const int hs = opts[i];
+      if (d->H % hs || (int64_t)d->ndir * (d->H / hs) > nsm) continue;
+      const int groups = d->ndir * (d->H / hs);
+      int bs = nsm / groups;
+      bs = std::max(1, std::min(bs, (d->B + 7) / 8));
+      const int pr = pr_for(groups * bs);
+      const size_t sm16 = bwd_smem(d, hs, pr, true, true);
+      if (sm16 > (size_t)smem_optin()) continue;
+      AG_CHECK_ARG(d->dgates16 && (d->F == 0 || d->dpx16), "ag_lstm_bwd: bf16 mode needs dgates16 / dpx16");
+      p.bf = true; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm16;
+    }
+  }
+  if (!p.bf) {
+    p.HS = pick_hs(d->H, d->ndir);
+    AG_CHECK_ARG(p.HS > 0, "ag_lstm_bwd: H=%d (ndir %d) does not map onto %d SMs", d->H, d->ndir, nsm);
+    p.ncta_dir = d->H / p.HS;
+    p.PR = pr_for(p.ncta_dir * d->ndir);
+    p.smem = bwd_smem(d, p.HS, p.PR, true);
+    if (p.smem > (size_t)smem_optin()) { p.res = false; p.smem = bwd_smem(d, p.HS, p.PR, false); }
+  }
   AG_CHECK_ARG(p.smem <= (size_t)smem_optin(), "ag_lstm_bwd: needs %zu B of shared memory", p.smem);
   cudaStream_t s = (cudaStream_t)stream;
   AG_CUDA(cudaMemsetAsync(d->barrier, 0, 8 * sizeof(unsigned), s));

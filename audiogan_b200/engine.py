@@ -44,6 +44,9 @@ class _GenFn(torch.autograd.Function):
                   pre, (Tcap, Tcap * 4 * H, 4 * H))
         hbuf = _zeros(B, Tcap + 2, H, device=dev)
         xbuf = _zeros(B, Tcap + 1, F, device=dev)
+        bf = plan.mode == "bf16"
+        hbuf16 = torch.zeros(B, Tcap + 2, H, device=dev, dtype=torch.bfloat16) if bf else None
+        xbuf16 = torch.zeros(B, Tcap + 1, F, device=dev, dtype=torch.bfloat16) if bf else None
         gates = _empty(B, Tcap, 4 * H, device=dev) if save else None
         cbuf = _empty(B, Tcap, H, device=dev) if save else None
         sbuf = _zeros(B, Tcap, device=dev)
@@ -53,7 +56,7 @@ class _GenFn(torch.autograd.Function):
         u = u_stop.contiguous() if u_stop is not None else None
         K.lstm_fwd(B=B, T=Tcap, Tcap=Tcap, H=H, ndir=1, F=F, pre=pre, w1=plan.Poff("w1"), w2=plan.Poff("w2"),
                    b2=plan.Poff("b2"), hbuf=hbuf, gates=gates, cbuf=cbuf, xbuf=xbuf, sbuf=sbuf, u=u, stop=stop,
-                   glen=glen, t_end=(misc, 8), barrier=misc)
+                   glen=glen, t_end=(misc, 8), barrier=misc, prec=1 if bf else 0, hbuf16=hbuf16, xbuf16=xbuf16)
         if u is not None and early_exit_sync:
             T = int(misc[8].item())          # the one host sync per generator pass (audiogan.py:459-460)
         else:
@@ -89,7 +92,7 @@ class _GenFn(torch.autograd.Function):
         s_out = sbuf[:, :T]
         if save:
             ctx.plan, ctx.struct, ctx.dims = plan, struct, (B, T, Tcap, L)
-            ctx.bufs = (zc1, hbuf, xbuf, gates, cbuf, Xd, hh)
+            ctx.bufs = (zc1, hbuf, xbuf, gates, cbuf, Xd, hh, hbuf16, xbuf16)
         ctx.mark_non_differentiable(stop, glen)
         ctx.set_materialize_grads(False)
         return xout, s_out, stop[:, :T], glen
@@ -99,7 +102,8 @@ class _GenFn(torch.autograd.Function):
     def backward(ctx, gx, gs, _gstop, _glen):
         plan, struct = ctx.plan, ctx.struct
         B, T, Tcap, L = ctx.dims
-        zc1, hbuf, xbuf, gates, cbuf, Xd, hh = ctx.bufs
+        zc1, hbuf, xbuf, gates, cbuf, Xd, hh, hbuf16, xbuf16 = ctx.bufs
+        bf = hbuf16 is not None
         dev = plan.device
         H, F, NZ, CT, FP = plan.H, plan.F, plan.NZ, plan.CT, plan.FP
         Lp = L + 2 * GPAD
@@ -159,19 +163,24 @@ class _GenFn(torch.autograd.Function):
             dgates[:, T:].zero_()
             dpx[:, T:].zero_()
         misc = torch.zeros(16, device=dev, dtype=torch.int32)
+        dgates16 = torch.empty(B, Tcap, 4 * H, device=dev, dtype=torch.bfloat16) if bf else None
+        dpx16 = torch.empty(B, Tcap, FP, device=dev, dtype=torch.bfloat16) if bf else None
         K.lstm_bwd(B=B, T=T, Tcap=Tcap, H=H, ndir=1, F=F, gates=gates, cbuf=cbuf, xbuf=xbuf, dx_ext=dx_ext,
-                   ds_ext=ds_ext, dgates=dgates, dpx=dpx, w1t=plan.Poff("w1t"), wxt=plan.Poff("wxt"), barrier=misc)
+                   ds_ext=ds_ext, dgates=dgates, dpx=dpx, w1t=plan.Poff("w1t"), wxt=plan.Poff("wxt"), barrier=misc,
+                   prec=1 if bf else 0, dgates16=dgates16, dpx16=dpx16)
+        # in bf16 mode the batched GEMMs read the kernels' bf16 shadow copies (half the operand traffic)
+        dgo, hbo, xbo, dpo = (dgates16, hbuf16, xbuf16, dpx16) if bf else (dgates, hbuf, xbuf, dpx)
         if wgrad:
             yv = (T, Tcap * 4 * H, 4 * H)
-            K.gemm_tn(B * T, 4 * H, H, dgates, yv, hbuf, (T, (Tcap + 2) * H, H), plan.GPoff("w1"), H + F)
-            K.gemm_tn(B * T, 4 * H, F, dgates, yv, xbuf, (T, (Tcap + 1) * F, F), plan.GPoff("w1", H), H + F)
-            K.gemm_tn(B * T, 4 * H, NZ + 2, dgates, yv, zc1, (T, Tcap * (NZ + 2), NZ + 2), plan.GPoff("wz"), NZ + 2)
-            K.gemm_tn(B * T, FP, H, dpx, (T, Tcap * FP, FP), (hbuf, H), (T, (Tcap + 2) * H, H), plan.GPoff("w2"), H + 1,
+            K.gemm_tn(B * T, 4 * H, H, dgo, yv, hbo, (T, (Tcap + 2) * H, H), plan.GPoff("w1"), H + F)
+            K.gemm_tn(B * T, 4 * H, F, dgo, yv, xbo, (T, (Tcap + 1) * F, F), plan.GPoff("w1", H), H + F)
+            K.gemm_tn(B * T, 4 * H, NZ + 2, dgo, yv, zc1, (T, Tcap * (NZ + 2), NZ + 2), plan.GPoff("wz"), NZ + 2)
+            K.gemm_tn(B * T, FP, H, dpo, (T, Tcap * FP, FP), (hbo, H), (T, (Tcap + 2) * H, H), plan.GPoff("w2"), H + 1,
                       ones_col=True)
         dzc1 = None
         if ctx.needs_input_grad[3]:
             dzc1 = _zeros(B, Tcap, NZ + 2, device=dev)
-            K.gemm_nt(B * T, NZ, 4 * H, dgates, (T, Tcap * 4 * H, 4 * H), plan.Poff("wzt"), 4 * H,
+            K.gemm_nt(B * T, NZ, 4 * H, dgo, (T, Tcap * 4 * H, 4 * H), plan.Poff("wzt"), 4 * H,
                       dzc1, (T, Tcap * (NZ + 2), NZ + 2))
         gtok = torch.zeros(1, device=dev) if wgrad else None
         return None, None, gtok, dzc1, None, None
@@ -273,11 +282,13 @@ class _DiscTailFn(torch.autograd.Function):
         K.gemm_nt(B * Tm, 8 * H, Cf, feat, (Tm, feat.stride(0), feat.stride(2)), plan.Poff("wih"), ldi,
                   pre, (Tm, Tm * 8 * H, 8 * H), rowbias=rb, rowbias_ld=8 * H)
         hbuf = _zeros(B, Tm + 2, 2 * H, device=dev)
+        bf = plan.mode == "bf16"
+        hbuf16 = torch.zeros(B, Tm + 2, 2 * H, device=dev, dtype=torch.bfloat16) if bf else None
         gates = _empty(B, Tm, 8 * H, device=dev)
         cbuf = _empty(B, Tm, 2 * H, device=dev)
         misc = torch.zeros(16, device=dev, dtype=torch.int32)
         K.lstm_fwd(B=B, T=Tm, Tcap=Tm, H=H, ndir=2, F=0, pre=pre, w1=plan.Poff("w1"), hbuf=hbuf, gates=gates, cbuf=cbuf,
-                   len=nfr, barrier=misc)
+                   len=nfr, barrier=misc, prec=1 if bf else 0, hbuf16=hbuf16)
         # residual_net + classifier on the (B*Tm) rows (audiogan.py:547-549); same row geometry as hbuf
         geo = (Tm, (Tm + 2) * S, S)
         r1 = _empty(B, Tm + 2, S, device=dev)
@@ -292,7 +303,7 @@ class _DiscTailFn(torch.autograd.Function):
         K.gemm_nt(B * Tm, 1, S // 2, h3, (B * Tm, 0, S // 2), plan.Poff("k2.w"), S // 2, logits, (B * Tm, 0, 1),
                   bias=plan.Poff("k2.b"))
         ctx.plan, ctx.dims = plan, (B, Cf, T6, Tm)
-        ctx.bufs = (feat, c1, nfr, hbuf, gates, cbuf, r1, r2, h3)
+        ctx.bufs = (feat, c1, nfr, hbuf, gates, cbuf, r1, r2, h3, hbuf16)
         return logits
 
     @staticmethod
@@ -300,7 +311,8 @@ class _DiscTailFn(torch.autograd.Function):
     def backward(ctx, g):
         plan = ctx.plan
         B, Cf, T6, Tm = ctx.dims
-        feat, c1, nfr, hbuf, gates, cbuf, r1, r2, h3 = ctx.bufs
+        feat, c1, nfr, hbuf, gates, cbuf, r1, r2, h3, hbuf16 = ctx.bufs
+        bf = hbuf16 is not None
         dev = plan.device
         S, H, E = plan.S, plan.H, plan.E
         ldi = Cf + E + 2
@@ -328,23 +340,26 @@ class _DiscTailFn(torch.autograd.Function):
         # BPTT through both directions
         dgates = _empty(B, Tm, 8 * H, device=dev)
         misc = torch.zeros(16, device=dev, dtype=torch.int32)
+        dgates16 = torch.empty(B, Tm, 8 * H, device=dev, dtype=torch.bfloat16) if bf else None
         K.lstm_bwd(B=B, T=Tm, Tcap=Tm, H=H, ndir=2, F=0, gates=gates, cbuf=cbuf, len=nfr, dh_ext=(dh_ext, S),
-                   dh_ext_bs=(Tm + 2) * S, dgates=dgates, w1t=plan.Poff("w1t"), barrier=misc)
+                   dh_ext_bs=(Tm + 2) * S, dgates=dgates, w1t=plan.Poff("w1t"), barrier=misc,
+                   prec=1 if bf else 0, dgates16=dgates16)
+        dgo, hbo = (dgates16, hbuf16) if bf else (dgates, hbuf)
         dgsum = None
         if wgrad or ctx.needs_input_grad[3]:
             dgsum = _empty(B, 8 * H, device=dev)
             K.rowgroup_sum(dgates, dgsum, B, Tm, 8 * H)
         if wgrad:
             for d in range(2):
-                K.gemm_tn(M, 4 * H, H, (dgates, d * 4 * H), (Tm, Tm * 8 * H, 8 * H),
-                          (hbuf, (2 * d) * 2 * H + d * H), (Tm, (Tm + 2) * 2 * H, 2 * H),
+                K.gemm_tn(M, 4 * H, H, (dgo, d * 4 * H), (Tm, Tm * 8 * H, 8 * H),
+                          (hbo, (2 * d) * 2 * H + d * H), (Tm, (Tm + 2) * 2 * H, 2 * H),
                           plan.GPoff("whh", d * 4 * H * H), H)
-            K.gemm_tn(M, 8 * H, Cf, dgates, flat(8 * H), feat, (Tm, feat.stride(0), feat.stride(2)), plan.GPoff("wih"), ldi)
+            K.gemm_tn(M, 8 * H, Cf, dgo, flat(8 * H), feat, (Tm, feat.stride(0), feat.stride(2)), plan.GPoff("wih"), ldi)
             K.gemm_tn(B, 8 * H, E + 2, dgsum, (B, 0, 8 * H), c1, (B, 0, E + 2), plan.GPoff("wih", Cf), ldi)
         dfeat = None
         if ctx.needs_input_grad[2]:
             dfeat = _zeros(B, T6, Cf, device=dev) if Tm < T6 else _empty(B, T6, Cf, device=dev)
-            K.gemm_nt(M, Cf, 8 * H, dgates, flat(8 * H), plan.Poff("wiht"), 8 * H, dfeat, (Tm, T6 * Cf, Cf))
+            K.gemm_nt(M, Cf, 8 * H, dgo, flat(8 * H), plan.Poff("wiht"), 8 * H, dfeat, (Tm, T6 * Cf, Cf))
             dfeat = dfeat.permute(0, 2, 1)
         dc = None
         if ctx.needs_input_grad[3]:

@@ -238,7 +238,7 @@ def pack(plan):
 # =========================================================================================
 def build_generator_plan(mod, device):
     H, F, NZ = mod._state_size, mod._frame_size, mod._noise_size + mod._embed_size
-    FP = (F + 1 + 3) // 4 * 4
+    FP = (F + 1 + 7) // 8 * 8
     pl = NetPlan(device)
     cell = mod.rnn[0].module
     wih = pl.weight("rnn.wih", cell.weight_ih_v, cell.weight_ih_g)

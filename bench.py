@@ -114,6 +114,8 @@ class KernelTimer:
             else:
                 per = d.ndir * d.H * (4 * d.H + (d.F + 1 if d.F else 0)) + d.F * 4 * d.H
             flops = 2.0 * d.B * d.T * per
+            if self.shapes:
+                name = name + " H%d ndir%d F%d T%d" % (d.H, d.ndir, d.F, d.T)
         e0, e1 = tc.Event(enable_timing=True), tc.Event(enable_timing=True)
         e0.record()
         if name.startswith("ag_gemm"):

@@ -103,7 +103,7 @@ int ag_gemm_tn_tc(const ag_gemm_desc* d, float* dw, int64_t ldw, int32_t ones_co
  *   sample has stopped, audiogan.py:458-460).
  * Backward: dgates [B, Tcap, ndir*4H] = grad wrt the pre-activation gates (= grad wrt `pre`),
  *   dpx [B, Tcap, FP] = grad wrt the proj pre-activation, column F = grad wrt the stop logit,
- *   FP = F+1 rounded up to a multiple of 4 (pad columns zero).  Weight gradients are batched
+ *   FP = F+1 rounded up to a multiple of 8 (pad columns zero).  Weight gradients are batched
  *   GEMMs over these two buffers (ag_gemm_tn_*), outside the recurrence.
  *   w1t [ndir, H, 4H+FP] rows j: [whh[:, j] | wp[:, j], ws[j], 0-pad];  wxt [F, 4H] = wx^T.
  * H % 4 == 0, F % 4 == 0.  `barrier`: >= 8 uint32 of device memory (zeroed by the call).
@@ -123,6 +123,12 @@ typedef struct ag_lstm_desc {
   const float* w1t; const float* wxt;
   unsigned int* barrier;
   int64_t dh_ext_bs;
+  /* bf16 mode (prec = 1): the recurrent products run on tensor cores (bf16 operands, fp32 accumulate, fp32 state).
+   * The kernels keep bf16 shadow copies of the per-step operands, same shapes as their fp32 twins:
+   * hbuf16 / xbuf16 (forward writes, rows 0 / T+1 zero on entry), dgates16 / dpx16 (backward writes). */
+  int32_t prec, reserved2;
+  void* hbuf16; void* xbuf16; void* dgates16; void* dpx16;
+  long long* dbg;        /* optional [gridDim][8] cycle counters per CTA: gemm, cell, barrier, phase2/A, total (profiling aid) */
 } ag_lstm_desc;
 
 int ag_lstm_fwd(const ag_lstm_desc* d, void* stream);

@@ -126,7 +126,7 @@ def test_lstm_feedback_fwd_bwd(H, B, Tn, Fr):
     gX, gS = T.randn_like(X), T.randn_like(S)
     (X * gX).sum().add((S * gS).sum()).backward()
     dev = "cuda"
-    FP = (Fr + 1 + 3) // 4 * 4
+    FP = (Fr + 1 + 7) // 8 * 8
     w1 = T.cat([whh, wx], 1).detach().contiguous().to(dev)
     w2 = T.cat([wp, ws], 0).detach().contiguous().to(dev)
     b2 = T.cat([bp, bs], 0).detach().contiguous().to(dev)
@@ -277,3 +277,53 @@ def test_gemm_tn_tc_conv_wgrad_view():
                dw, k * Cin + 1, ones_col=True, tc=True)
     assert rel(dw[:, :k * Cin].reshape(Cout, k, Cin).permute(0, 2, 1), w.grad) < 2e-5
     assert rel(dw[:, k * Cin], bb.grad) < 2e-5
+
+
+@pytest.mark.parametrize("H,B,Tn,ndir,Fr", [(64, 5, 12, 2, 0), (512, 40, 9, 2, 0), (64, 9, 7, 1, 200), (1024, 64, 6, 1, 200)])
+def test_lstm_bf16_mode_tracks_fp32_kernels(H, B, Tn, ndir, Fr):
+    """prec=1 (mma.sync bf16 products, fp32 state) against the fp32 kernels on the same inputs: <= 2e-2."""
+    from audiogan_b200 import kernels as Kn
+    T.manual_seed(11)
+    dev = "cuda"
+    sc = 1.0 / H ** 0.5
+    FP = (Fr + 1 + 7) // 8 * 8 if Fr else 0
+    pre = T.randn(B, Tn, ndir * 4 * H, device=dev)
+    w1 = (T.randn(ndir, 4 * H, H + Fr, device=dev) * sc).contiguous()
+    w2 = (T.randn(Fr + 1, H, device=dev) * sc) if Fr else None
+    b2 = (T.randn(Fr + 1, device=dev) * sc) if Fr else None
+    lens = None if Fr else T.randint(1, Tn + 1, (B,), device=dev, dtype=T.int32)
+    if lens is not None:
+        lens[0] = Tn
+    if Fr:
+        w1t = T.cat([w1[0, :, :H].t(), w2[:Fr].t(), w2[Fr:].t(), T.zeros(H, FP - Fr - 1, device=dev)], 1).contiguous()
+        wxt = w1[0, :, H:].t().contiguous()
+    else:
+        w1t, wxt = w1.permute(0, 2, 1).contiguous(), None
+    dh_ext = None if Fr else T.randn(B, Tn, ndir * H, device=dev)
+    dx_ext = T.randn(B, Tn, Fr, device=dev) if Fr else None
+    res = {}
+    for prec in (0, 1):
+        hbuf, gates, cbuf = T.zeros(B, Tn + 2, ndir * H, device=dev), T.empty(B, Tn, ndir * 4 * H, device=dev), T.empty(B, Tn, ndir * H, device=dev)
+        xbuf = T.zeros(B, Tn + 1, Fr, device=dev) if Fr else None
+        sbuf = T.zeros(B, Tn, device=dev) if Fr else None
+        misc = T.zeros(16, dtype=T.int32, device=dev)
+        kw = {}
+        if prec:
+            kw = dict(prec=1, hbuf16=T.zeros(B, Tn + 2, ndir * H, device=dev, dtype=T.bfloat16),
+                      xbuf16=T.zeros(B, Tn + 1, Fr, device=dev, dtype=T.bfloat16) if Fr else None)
+        Kn.lstm_fwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=ndir, F=Fr, pre=pre, w1=w1, w2=w2, b2=b2, hbuf=hbuf, gates=gates, cbuf=cbuf,
+                    len=lens, xbuf=xbuf, sbuf=sbuf, t_end=(misc, 8) if Fr else None, barrier=misc, **kw)
+        dgates = T.empty(B, Tn, ndir * 4 * H, device=dev)
+        dpx = T.empty(B, Tn, FP, device=dev) if Fr else None
+        kw = {}
+        if prec:
+            kw = dict(prec=1, dgates16=T.empty(B, Tn, ndir * 4 * H, device=dev, dtype=T.bfloat16),
+                      dpx16=T.empty(B, Tn, FP, device=dev, dtype=T.bfloat16) if Fr else None)
+        Kn.lstm_bwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=ndir, F=Fr, gates=gates, cbuf=cbuf, len=lens, xbuf=xbuf, dh_ext=dh_ext,
+                    dx_ext=dx_ext, dgates=dgates, dpx=dpx, w1t=w1t, wxt=wxt, barrier=misc, **kw)
+        res[prec] = (hbuf.clone(), dgates.clone(), xbuf.clone() if Fr else None, kw.get("dgates16"))
+    assert rel(res[1][0], res[0][0]) < 2e-2, "h"
+    assert rel(res[1][1], res[0][1]) < 3e-2, "dgates"
+    if Fr:
+        assert rel(res[1][2], res[0][2]) < 2e-2, "x"
+    assert rel(res[1][3].float(), res[1][1]) < 1e-2, "bf16 shadow"
