@@ -205,36 +205,44 @@ struct PhaseClock {
 // fp32 variant's 2-deep ring exposes the L2 latency of every 64-column chunk), the resident weight slice is bf16,
 // and the products run on mma.sync.m16n8k16 (bf16 x bf16 -> fp32).  The recurrent state stays fp32.
 constexpr int NST_MIN = 4;        // cp.async ring depth: 4, 8 or 12 stages, the deepest that fits (runtime `nst`)
-constexpr int SLD16 = KC + 8;     // staged bf16 row stride (elements): 144 B rows, conflict-free fragment reads
+constexpr int SLD16 = KC + 8;     // staged bf16 row stride at kc = 64 (elements): 144 B rows, conflict-free reads
+constexpr int SLOT16 = BTILE * SLD16;   // ring slot size in elements (>= rb * (kc + 8) for every (rb, kc) pair)
 
-__host__ __device__ inline int pad_ld16(int K) {          // >= K rounded to a whole chunk, == 8 (mod 64): conflict-free
+__host__ __device__ inline int pad_ld16(int K) {          // >= K rounded to a whole sub-chunk, == 8 (mod 64): conflict-free
   return (K + KC - 1) / KC * KC + 8;
 }
+__host__ __device__ inline int ring_kc(int bper) {         // columns per ring slot for a CTA owning `bper` batches
+  return bper <= 16 ? 256 : (bper <= 32 ? 128 : 64);
+}
 
-// Per-thread view of the [B, K] bf16 operand for one (step, batch tile): each thread always copies the same two
-// (row, 16-byte column) cells of every chunk, so the row pointers are resolved once per step, not once per chunk.
+// Per-thread view of the [B, K] bf16 operand for one (step, batch tile).  A ring slot holds `rb` batch rows x `kc`
+// columns with rb * kc == 4096 (rb = 64/32/16 -> kc = 64/128/256): CTAs that own a narrow batch range stage wide
+// chunks, so the number of block-wide syncs per step shrinks with the batch split.  Each thread always copies the
+// same two (row, 16-byte column) cells of every chunk: row pointers are resolved once per step.
 struct Stager16 {
   const __nv_bfloat16* r0[2];   // row base inside segment 0 (nullptr = zeros)
   const __nv_bfloat16* r1[2];   // row base inside segment 1, already shifted by -n0
   int dst[2];                   // element offset inside a ring slot
-  int kk, n0, K;
-  __device__ __forceinline__ void init(const Seg& sg, int b0, int B, int K_) {
-    kk = (threadIdx.x & 7) << 3;
+  int kk[2], n0, K;
+  __device__ __forceinline__ void init(const Seg& sg, int b0, int B, int K_, int kc) {
     n0 = sg.n0;
     K = K_;
+    const int cpr = kc >> 3, sld = kc + 8;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int bl = (threadIdx.x + LT * i) >> 3, b = b0 + bl;
-      dst[i] = bl * SLD16 + kk;
+      const int idx = threadIdx.x + LT * i;
+      const int bl = idx / cpr, b = b0 + bl;
+      kk[i] = (idx - bl * cpr) << 3;
+      dst[i] = bl * sld + kk[i];
       const bool ok = b < B;
       r0[i] = (ok && sg.q0) ? sg.q0 + b * sg.s0 : nullptr;
       r1[i] = (ok && sg.q1) ? sg.q1 + b * sg.s1 - sg.n0 : nullptr;
     }
   }
   __device__ __forceinline__ void issue(__nv_bfloat16* slot, int k0) const {
-    const int k = k0 + kk;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
+      const int k = k0 + kk[i];
       const __nv_bfloat16* base = (k < n0) ? r0[i] : r1[i];
       if (base != nullptr && k < K) cp_async16(slot + dst[i], base + k);
       else *reinterpret_cast<uint4*>(slot + dst[i]) = make_uint4(0u, 0u, 0u, 0u);
@@ -256,22 +264,25 @@ __device__ __forceinline__ void cp_async_wait_dyn(int pending) {
 
 // MT 16-row tiles of the weight slice x up to 8 batch tiles of 8.  Warp w owns row tile w % MT and the batch tiles
 // w / MT + (8 / MT) * i, i < MT, skipping those past the last valid batch.  acc[i] is an m16n8 fragment:
-// [0],[1] -> row g, batches 2t, 2t+1; [2],[3] -> row g+8.  All fragment loads of a chunk are issued before its MMAs.
+// [0],[1] -> row g, batches 2t, 2t+1; [2],[3] -> row g+8.  All fragment loads of a 64-column sub-chunk are issued
+// before its MMAs; `kc` columns (rb = 4096 / kc rows) per ring slot, one block-wide sync per slot.
 template <int MT>
 __device__ __forceinline__ void slice_gemm_mma(float (&acc)[MT][4], const __nv_bfloat16* Ws, int ldw, const Seg& sg, int K,
-                                               int b0, int B, __nv_bfloat16* stage, const int NST, PhaseClock* pc = nullptr) {
+                                               int b0, int B, __nv_bfloat16* stage, const int NST, const int kc,
+                                               PhaseClock* pc = nullptr) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int mt = w % MT, nt0 = w / MT;
   constexpr int NSTEP = 8 / MT;                         // batch-tile stride between a warp's tiles
-  const int ntv = (min(B - b0, BTILE) + 7) >> 3;        // valid batch tiles in this batch tile
-  const int nch = (K + KC - 1) / KC;
+  const int rb = 4096 / kc, sld = kc + 8, slot = rb * sld;
+  const int ntv = (min(min(B - b0, BTILE), rb) + 7) >> 3;   // valid batch tiles held by a slot
+  const int nch = (K + kc - 1) / kc;
   const int rot = (int)((blockIdx.x * 5u) % (unsigned)nch);     // per-CTA chunk rotation (see slice_gemm)
-  auto kof = [&](int c) { int cc = c + rot; if (cc >= nch) cc -= nch; return cc * KC; };
+  auto kof = [&](int c) { int cc = c + rot; if (cc >= nch) cc -= nch; return cc * kc; };
   Stager16 st;
-  st.init(sg, b0, B, K);
+  st.init(sg, b0, B, K, kc);
   for (int s = 0; s < NST - 1; ++s) {
-    if (s < nch) st.issue(stage + s * BTILE * SLD16, kof(s));
+    if (s < nch) st.issue(stage + s * slot, kof(s));
     cp_async_commit();
   }
   const __nv_bfloat16* wa = Ws + (mt * 16 + g) * ldw + 2 * t;
@@ -288,32 +299,36 @@ __device__ __forceinline__ void slice_gemm_mma(float (&acc)[MT][4], const __nv_b
     cp_async_wait_dyn(NST - 2);
     __syncthreads();
     if (pc) { const long long q1 = clock64(); pc->acc[5] += q1 - q0; q0 = q1; }
-    if (c + NST - 1 < nch) st.issue(stage + ((c + NST - 1) % NST) * BTILE * SLD16, kof(c + NST - 1));
+    if (c + NST - 1 < nch) st.issue(stage + ((c + NST - 1) % NST) * slot, kof(c + NST - 1));
     cp_async_commit();
     if (pc) { const long long q1 = clock64(); pc->acc[6] += q1 - q0; q0 = q1; }
-    const __nv_bfloat16* sb = stage + ((c % NST) * BTILE) * SLD16 + g * SLD16 + 2 * t;
-    const __nv_bfloat16* wk = wa + kof(c);
-    uint32_t af[KC / 16][4];
+    const int kbase = kof(c);
+    const __nv_bfloat16* sb0 = stage + (c % NST) * slot + g * sld + 2 * t;
+    for (int sub = 0; sub < kc && kbase + sub < K; sub += KC) {
+      const __nv_bfloat16* wk = wa + kbase + sub;
+      const __nv_bfloat16* sb = sb0 + sub;
+      uint32_t af[KC / 16][4];
 #pragma unroll
-    for (int kk = 0; kk < KC / 16; ++kk) {
-      af[kk][0] = *reinterpret_cast<const uint32_t*>(wk + kk * 16);
-      af[kk][1] = *reinterpret_cast<const uint32_t*>(wk + 8 * ldw + kk * 16);
-      af[kk][2] = *reinterpret_cast<const uint32_t*>(wk + kk * 16 + 8);
-      af[kk][3] = *reinterpret_cast<const uint32_t*>(wk + 8 * ldw + kk * 16 + 8);
-    }
+      for (int kk = 0; kk < KC / 16; ++kk) {
+        af[kk][0] = *reinterpret_cast<const uint32_t*>(wk + kk * 16);
+        af[kk][1] = *reinterpret_cast<const uint32_t*>(wk + 8 * ldw + kk * 16);
+        af[kk][2] = *reinterpret_cast<const uint32_t*>(wk + kk * 16 + 8);
+        af[kk][3] = *reinterpret_cast<const uint32_t*>(wk + 8 * ldw + kk * 16 + 8);
+      }
 #pragma unroll
-    for (int i = 0; i < MT; ++i) {
-      const int nt = nt0 + NSTEP * i;
-      if (nt < ntv) {
-        uint32_t bf[KC / 16][2];
+      for (int i = 0; i < MT; ++i) {
+        const int nt = nt0 + NSTEP * i;
+        if (nt < ntv) {
+          uint32_t bf[KC / 16][2];
 #pragma unroll
-        for (int kk = 0; kk < KC / 16; ++kk) {
-          bf[kk][0] = *reinterpret_cast<const uint32_t*>(sb + nt * 8 * SLD16 + kk * 16);
-          bf[kk][1] = *reinterpret_cast<const uint32_t*>(sb + nt * 8 * SLD16 + kk * 16 + 8);
+          for (int kk = 0; kk < KC / 16; ++kk) {
+            bf[kk][0] = *reinterpret_cast<const uint32_t*>(sb + nt * 8 * sld + kk * 16);
+            bf[kk][1] = *reinterpret_cast<const uint32_t*>(sb + nt * 8 * sld + kk * 16 + 8);
+          }
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk)
+            mma_bf16(part[kk % NCH][i], af[kk][0], af[kk][1], af[kk][2], af[kk][3], bf[kk][0], bf[kk][1]);
         }
-#pragma unroll
-        for (int kk = 0; kk < KC / 16; ++kk)
-          mma_bf16(part[kk % NCH][i], af[kk][0], af[kk][1], af[kk][2], af[kk][3], bf[kk][0], bf[kk][1]);
       }
     }
     if (pc) { const long long q1 = clock64(); pc->acc[7] += q1 - q0; }
@@ -406,7 +421,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
   __nv_bfloat16* stage16 = Ws16 + ROWS * ldw16;
   // bf16: the gate exchange tile aliases the (idle) cp.async ring
   float* gs = BF ? reinterpret_cast<float*>(stage16) : stage + 2 * BTILE * SLD;
-  float* cs = BF ? reinterpret_cast<float*>(stage16 + NST * BTILE * SLD16) : gs + BTILE * ROWS;
+  float* cs = BF ? reinterpret_cast<float*>(stage16 + NST * SLOT16) : gs + BTILE * ROWS;
   float* W2s = cs + Bper * HS;
   int* gen = reinterpret_cast<int*>(W2s + (FB ? PR * ld2 : 0));
   int* cnt = gen + B;
@@ -481,7 +496,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
         float accm[MT][4];
 #pragma unroll
         for (int i = 0; i < MT; ++i) { accm[i][0] = 0.f; accm[i][1] = 0.f; accm[i][2] = 0.f; accm[i][3] = 0.f; }
-        slice_gemm_mma<MT>(accm, Ws16, ldw16, sg, K1, b0, bhi, stage16, NST, d.dbg ? &pc : nullptr);
+        slice_gemm_mma<MT>(accm, Ws16, ldw16, sg, K1, b0, bhi, stage16, NST, ring_kc(Bper), d.dbg ? &pc : nullptr);
         pc.lap(0);
         const int g = lane >> 2, tq = lane & 3, mt = w % MT, nt0 = w / MT;
 #pragma unroll
@@ -629,7 +644,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, c
   float* stage = Ws + (RES ? HS * ldw : 0);
   __nv_bfloat16* stage16 = Ws16 + HS * ldw16;
   float* dhs = BF ? reinterpret_cast<float*>(stage16) : stage + 2 * BTILE * SLD;      // bf16: aliases the idle ring
-  float* dcs = BF ? reinterpret_cast<float*>(stage16 + NST * BTILE * SLD16) : dhs + BTILE * HS;
+  float* dcs = BF ? reinterpret_cast<float*>(stage16 + NST * SLOT16) : dhs + BTILE * HS;
   float* Wxs = dcs + Bper * HS;
 
   const float* w1d = d.w1t + ((int64_t)dir * H + j0) * K;
@@ -769,7 +784,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, c
         float accm[MT][4];
 #pragma unroll
         for (int i = 0; i < MT; ++i) { accm[i][0] = 0.f; accm[i][1] = 0.f; accm[i][2] = 0.f; accm[i][3] = 0.f; }
-        if (has_next || FB) slice_gemm_mma<MT>(accm, Ws16, ldw16, sg, K, b0, bhi, stage16, NST, d.dbg ? &pc : nullptr);
+        if (has_next || FB) slice_gemm_mma<MT>(accm, Ws16, ldw16, sg, K, b0, bhi, stage16, NST, ring_kc(Bper), d.dbg ? &pc : nullptr);
         pc.lap(0);
         if (HS >= 16) {
           const int g = lane >> 2, tq = lane & 3, mt = w % MT, nt0 = w / MT;
@@ -846,14 +861,14 @@ static int pick_hs(int H, int ndir) {
 static size_t fwd_smem(const ag_lstm_desc* d, int HS, int PR, bool res, bool bf = false, int NST = NST_MIN) {
   const int F = d->F, K1 = d->H + F;
   size_t fl = (bf ? 0 : (size_t)BTILE * 4 * HS) + (size_t)(d->B + 8) * HS + (F > 0 ? (size_t)PR * pad_ld(d->H) : 0);
-  size_t head = bf ? ((size_t)4 * HS * pad_ld16(K1) + (size_t)NST * BTILE * SLD16) * 2
+  size_t head = bf ? ((size_t)4 * HS * pad_ld16(K1) + (size_t)NST * SLOT16) * 2
                    : ((res ? (size_t)4 * HS * pad_ld(K1) : 0) + 2 * BTILE * SLD) * 4;
   return head + fl * 4 + (size_t)2 * d->B * 4 + 16;
 }
 static size_t bwd_smem(const ag_lstm_desc* d, int HS, int PR, bool res, bool bf = false, int NST = NST_MIN) {
   const int F = d->F, FP = F > 0 ? ((F + 1 + 7) / 8) * 8 : 0, K = 4 * d->H + FP;
   size_t fl = (bf ? 0 : (size_t)BTILE * HS) + (size_t)(d->B + 8) * HS + (F > 0 ? (bf ? (size_t)PR * (2 * d->H + 4) : (size_t)PR * pad_ld(4 * d->H)) : 0);
-  size_t head = bf ? ((size_t)HS * pad_ld16(K) + (size_t)NST * BTILE * SLD16) * 2
+  size_t head = bf ? ((size_t)HS * pad_ld16(K) + (size_t)NST * SLOT16) * 2
                    : ((res ? (size_t)HS * pad_ld(K) : 0) + 2 * BTILE * SLD) * 4;
   return head + fl * 4 + 16;
 }
