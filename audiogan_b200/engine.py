@@ -64,28 +64,28 @@ class _GenFn(torch.autograd.Function):
         L = T * F
         Lp = L + 2 * GPAD
         # frame assembly into channel 0 of the dense buffer (audiogan.py:462-464)
-        Xd = _empty(B, Lp, CT, device=dev)
+        Xd = _empty(B, Lp, CT, device=dev)                  # CT = padded channel count (slots of 8, plan.py)
         Xd[:, :GPAD].zero_()
         Xd[:, GPAD + L:].zero_()
+        Xd[:, GPAD:GPAD + L, 1:plan.coff[0]].zero_()        # pad channels of the waveform slot
         K.copy3d((Xd, GPAD * CT), (Lp * CT, CT, 0), (xbuf, F), ((Tcap + 1) * F, 1, 0), B, L, 1)
         hh = []
-        cin = 1
         lenL = plan.const_len(B, L)
         for li, (k, s, hid, out) in enumerate(struct):                       # audiogan.py:278-283, :465-467
             p, pd, Lh = (k - 1) // 2, s // 2, L // s
+            cin = plan.cinp[li]                             # padded channel prefix this block reads == slot it writes
             Hh = _empty(B, Lh + 2, hid, device=dev)
             Hh[:, 0].zero_()
             Hh[:, Lh + 1].zero_()
             K.gemm_nt(B * Lh, hid, k * cin, (Xd, (GPAD - p) * CT), (Lh, Lp * CT, s * CT, cin, CT),
                       plan.Poff("c%d.w" % li), k * cin, (Hh, hid), (Lh, (Lh + 2) * hid, hid),
                       bias=plan.Poff("c%d.b" % li), act=1)
-            skip = (Xd, (GPAD - pd) * CT + cin - out) if cin >= out else None
+            skip = (Xd, (GPAD - pd) * CT + plan.skip_off[li]) if plan.skip_off[li] >= 0 else None
             K.gemm_nt(B * (Lh + 1), s * out, 2 * hid, Hh, (Lh + 1, (Lh + 2) * hid, hid),
                       plan.Poff("d%d.w" % li), 2 * hid, (Xd, (GPAD - pd) * CT + cin), (Lh + 1, Lp * CT, s * CT, out, CT),
                       bias=plan.Poff("d%d.b" % li), bias_mod=out, skip=skip, act=1,
                       mask_len=lenL, mask=(s, 1, -pd))
             hh.append(Hh)
-            cin += out
         xout = _empty(B, L, device=dev)
         K.gemm_nt(B * L, 1, 3 * CT, (Xd, (GPAD - 1) * CT), (L, Lp * CT, CT), plan.Poff("f.w"), 3 * CT,
                   xout, (L, L, 1), bias=plan.Poff("f.b"))
@@ -119,12 +119,9 @@ class _GenFn(torch.autograd.Function):
             if wgrad:
                 K.gemm_tn(B * L, 1, 3 * CT, gx, (L, L, 1), (Xd, (GPAD - 1) * CT), (L, Lp * CT, CT),
                           plan.GPoff("f.w"), 3 * CT + 1, ones_col=True)
-            cins = [1]
-            for (_, _, _, out) in struct:
-                cins.append(cins[-1] + out)
             for li in range(len(struct) - 1, -1, -1):
                 k, s, hid, out = struct[li]
-                cin = cins[li]
+                cin = plan.cinp[li]
                 p, pd, Lh, kd = (k - 1) // 2, s // 2, L // s, k - 1
                 Hh = hh[li]
                 # dyl = d(block output) * lrelu'(output); also feeds the dense skip (audiogan.py:281-283)
@@ -132,7 +129,8 @@ class _GenFn(torch.autograd.Function):
                 slice_off = GPAD * CT + cin
                 K.ew_grad(B, L, out, out=dyl, pad=(pd, pd), g1=(dXd, slice_off), g1_str=(Lp * CT, CT, 1),
                           act=(Xd, slice_off), act_str=(Lp * CT, CT),
-                          acc=((dXd, GPAD * CT + cin - out) if cin >= out else None), acc_str=(Lp * CT, CT))
+                          acc=((dXd, GPAD * CT + plan.skip_off[li]) if plan.skip_off[li] >= 0 else None),
+                          acc_str=(Lp * CT, CT))
                 if wgrad:
                     K.colsum((dyl, pd * out), (L + 2 * pd) * out, out, B, L, out, plan.GPoff("d%d.b" % li))
                 # transposed-conv data gradient = strided conv over dyl, times lrelu'(hidden)

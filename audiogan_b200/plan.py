@@ -281,36 +281,70 @@ def build_generator_plan(mod, device):
     pl.grad_of("proj.b", g2[:F, H])
     pl.grad_of("stop.w", g2[F:F + 1, :H])
     pl.grad_of("stop.b", g2[F:F + 1, H])
-    # conv stack
+    # conv stack.  The dense channel-last buffer keeps every channel group in a slot padded to a multiple of 8
+    # channels (x: 1 -> 8, then each block's `out`), so channel prefixes, slot offsets and the row pitch are all
+    # 16/32-byte aligned: vector loads / stores in the GEMM kernels.  pos[c] = padded position of canonical channel c.
+    r8 = lambda n: (n + 7) // 8 * 8
+    pos, slot_off, nxt = [0], [], r8(1)
+    for (_, _, _, out) in mod._struct:
+        slot_off.append(nxt)
+        pos += list(range(nxt, nxt + out))
+        nxt += r8(out)
+    CTp = nxt
+    pos_t = torch.tensor(pos, dtype=torch.int64)
+
+    def pad_ch(idx, dim, cin, cp):
+        """scatter the `cin` canonical channels of `idx` along `dim` into their `cp` padded positions (-1 elsewhere)"""
+        shape = list(idx.shape)
+        shape[dim] = cp
+        out_ = torch.full(shape, -1, dtype=torch.int64)
+        out_.index_copy_(dim, pos_t[:cin], idx)
+        return out_
+
+    def unpad_ch(idx, dim, cin):
+        return idx.index_select(dim, pos_t[:cin])
+
     cin = 1
+    pl.cinp, pl.coff, pl.skip_off = [], [], []
     for li, (k, s, hid, out) in enumerate(mod._struct):
         cw, cb, dw, db = convs[li]
         kd = k - 1
         assert kd == 2 * s and (k - 1) // 2 == s, "dense_res_bottleneck layer must have kernel = 2*stride + 1"
-        pl.layout("c%d.w" % li, cw.permute(0, 2, 1).reshape(hid, k * cin))              # (j, ci)
+        cp = slot_off[li]                                   # padded prefix read by this block == slot it writes to
+        pl.cinp.append(cp)
+        pl.coff.append(slot_off[li])
+        if cin >= out:                                      # skip = last `out` canonical channels: must be one slot run
+            sk = pos[cin - out:cin]
+            assert sk == list(range(sk[0], sk[0] + out)), "dense skip must cover one contiguous padded slot"
+            pl.skip_off.append(sk[0])
+        else:
+            pl.skip_off.append(-1)
+        cwp = pad_ch(cw, 1, cin, cp)                                                     # [hid, cp, k]
+        pl.layout("c%d.w" % li, cwp.permute(0, 2, 1).reshape(hid, k * cp))              # (j, ci_p)
         pl.layout("c%d.b" % li, cb)
         # transposed conv as a GEMM over 2 taps: [(r', co), (u, ci)] = Wd[ci, co, s*(1-u) + r']
         d4 = dw.view(hid, out, 2, s).flip(2)                                            # [ci, co, u, r']
         pl.layout("d%d.w" % li, d4.permute(3, 1, 2, 0).reshape(s * out, 2 * hid))
         pl.layout("d%d.b" % li, db)
         pl.layout("d%d.wg" % li, dw.permute(0, 2, 1).reshape(hid, kd * out))            # [ci, (j, co)]
-        # conv data-gradient over 3 taps: [(r', ci), (u, h)] = Wc[h, ci, s*(2-u) + r']
-        cpad = torch.cat([cw, neg(hid, cin, 3 * s - k)], 2).view(hid, cin, 3, s).flip(2)   # [h, ci, u, r']
-        pl.layout("c%d.wg" % li, cpad.permute(3, 1, 2, 0).reshape(s * cin, 3 * hid))
-        gc = pl.grad_region("c%d.w" % li, (hid, k * cin + 1))
+        # conv data-gradient over 3 taps: [(r', ci_p), (u, h)] = Wc[h, ci, s*(2-u) + r']
+        cpad = torch.cat([cwp, neg(hid, cp, 3 * s - k)], 2).view(hid, cp, 3, s).flip(2)   # [h, ci_p, u, r']
+        pl.layout("c%d.wg" % li, cpad.permute(3, 1, 2, 0).reshape(s * cp, 3 * hid))
+        gc = pl.grad_region("c%d.w" % li, (hid, k * cp + 1))
         gd = pl.grad_region("d%d.w" % li, (hid, kd * out))
         gb = pl.grad_region("d%d.b" % li, (out,))
-        pl.grad_of("c%d.w" % li, gc[:, :k * cin].reshape(hid, k, cin).permute(0, 2, 1))
-        pl.grad_of("c%d.b" % li, gc[:, k * cin])
+        pl.grad_of("c%d.w" % li, unpad_ch(gc[:, :k * cp].reshape(hid, k, cp).permute(0, 2, 1), 1, cin))
+        pl.grad_of("c%d.b" % li, gc[:, k * cp])
         pl.grad_of("d%d.w" % li, gd.view(hid, kd, out).permute(0, 2, 1))
         pl.grad_of("d%d.b" % li, gb)
         cin += out
-    CT = cin
-    pl.layout("f.w", fw.permute(0, 2, 1).reshape(1, 3 * CT))
+    CT = CTp
+    fwp = pad_ch(fw, 1, cin, CTp)                                                      # [1, CTp, 3]
+    pl.layout("f.w", fwp.permute(0, 2, 1).reshape(1, 3 * CT))
     pl.layout("f.b", fb)
-    pl.layout("f.wg", fw[0].flip(1))                                                   # [CT, 3]: W[0, ci, 2-kk]
+    pl.layout("f.wg", fwp[0].flip(1))                                                  # [CTp, 3]: W[0, ci, 2-kk]
     gf = pl.grad_region("f.w", (1, 3 * CT + 1))
-    pl.grad_of("f.w", gf[:, :3 * CT].reshape(1, 3, CT).permute(0, 2, 1))
+    pl.grad_of("f.w", unpad_ch(gf[:, :3 * CT].reshape(1, 3, CT).permute(0, 2, 1), 1, cin))
     pl.grad_of("f.b", gf[:, 3 * CT])
     pl.CT, pl.H, pl.F, pl.NZ, pl.FP = CT, H, F, NZ, FP
     return pl.finalize(mod.parameters())
