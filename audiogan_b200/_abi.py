@@ -96,6 +96,9 @@ _PROTOS = {
     "ag_bce_const_fused": [vp, i64, vp, f32, f32, vp, vp, vp, vp, i64, i64, vp],
     "ag_ew_grad": [C.POINTER(EwDesc), vp],
     "ag_colsum": [vp, i64, i64, i64, i64, i64, vp, vp],
+    "ag_conv1out_fwd": [vp, i64, i64, i32, vp, vp, vp, i64, i64, vp],
+    "ag_conv1out_dgrad": [vp, vp, vp, i64, i64, i32, i64, i64, vp],
+    "ag_conv1out_wgrad": [vp, vp, i64, i64, i32, vp, i64, i64, vp],
     "ag_copy3d": [vp, i64, i64, i64, vp, i64, i64, i64, i64, i64, i64, i32, vp],
     "ag_rowgroup_sum": [vp, vp, i64, i64, i64, vp],
     "ag_transpose_bct": [vp, vp, i64, i64, i64, i64, i64, i32, vp],

@@ -1,0 +1,135 @@
+// The generator's last layer, Conv1d(C -> 1, k = 3) over the dense channel-last buffer (audiogan.py:403-407, :467),
+// and its two gradients.  With one output channel there is nothing for tensor cores to do: each kernel streams the
+// [B, T + k - 1, C] buffer once -- HBM-bound (4 B per buffer element), coalesced 16-byte accesses.
+#include "common.cuh"
+
+namespace ag {
+
+// out[b,t] = bias + sum_{j<k,c<C} X[b, t+j, c] * w[j*C + c].  One warp per output row; the k*C window is contiguous.
+__global__ void __launch_bounds__(256) conv1out_fwd_kernel(const float* __restrict__ X, int64_t x_bs, int C, int k,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           float* __restrict__ out, int64_t B, int64_t T) {
+  extern __shared__ float ws[];                      // k*C weights
+  const int K = k * C;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float bv = bias ? bias[0] : 0.f;
+  const int64_t rows = B * T;
+  for (int64_t m = (int64_t)blockIdx.x * nw + wid; m < rows; m += (int64_t)gridDim.x * nw) {
+    const int64_t b = m / T, t = m - b * T;
+    const float4* p = reinterpret_cast<const float4*>(X + b * x_bs + t * C);
+    float acc = 0.f;
+    for (int k4 = lane; k4 < K / 4; k4 += 32) {
+      const float4 v = __ldg(p + k4);
+      const float4 q = *reinterpret_cast<const float4*>(ws + 4 * k4);
+      acc += v.x * q.x + v.y * q.y + v.z * q.z + v.w * q.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[m] = acc + bv;
+  }
+}
+
+// dX[b, t', c] = sum_j g[b, t'-j] * w[j*C + c], t' in [0, T+k-1).  Thread = 4 channels, block walks rows.
+template <int KMAX>
+__global__ void __launch_bounds__(128) conv1out_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ w,
+                                                             float* __restrict__ dX, int64_t dx_bs, int C, int k, int64_t T,
+                                                             int rows_per_block) {
+  const int c4 = threadIdx.x;                        // channel group
+  if (c4 * 4 >= C) return;
+  const int64_t b = blockIdx.y;
+  const int64_t t0 = (int64_t)blockIdx.x * rows_per_block, t1 = min(T + k - 1, t0 + rows_per_block);
+  float4 wv[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) wv[j] = j < k ? *reinterpret_cast<const float4*>(w + j * C + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* gb = g + b * T;
+  for (int64_t t = t0; t < t1; ++t) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      const int64_t tg = t - j;
+      const float gv = (j < k && tg >= 0 && tg < T) ? __ldg(gb + tg) : 0.f;
+      acc.x += gv * wv[j].x; acc.y += gv * wv[j].y; acc.z += gv * wv[j].z; acc.w += gv * wv[j].w;
+    }
+    *reinterpret_cast<float4*>(dX + b * dx_bs + t * C + 4 * c4) = acc;
+  }
+}
+
+// dw[j*C + c] += sum_{b,t} g[b,t] * X[b, t+j, c];  dw[k*C] += sum g.   Thread = 4 channels; every X element is read once.
+template <int KMAX>
+__global__ void __launch_bounds__(128) conv1out_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ X,
+                                                             int64_t x_bs, int C, int k, float* __restrict__ dw, int64_t T,
+                                                             int rows_per_block) {
+  const int c4 = threadIdx.x;
+  const int64_t b = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(T + k - 1, r0 + rows_per_block);   // X rows
+  const float* gb = g + b * T;
+  if (c4 * 4 < C) {
+    float4 acc[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = r0; r < r1; ++r) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(X + b * x_bs + r * C + 4 * c4));
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        const int64_t t = r - j;                       // X row r is tap j of output t = r - j
+        const float gv = (j < k && t >= 0 && t < T) ? __ldg(gb + t) : 0.f;
+        acc[j].x += gv * x.x; acc[j].y += gv * x.y; acc[j].z += gv * x.z; acc[j].w += gv * x.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      if (j < k) {
+        float* q = dw + j * C + 4 * c4;
+        atomicAdd(q, acc[j].x); atomicAdd(q + 1, acc[j].y); atomicAdd(q + 2, acc[j].z); atomicAdd(q + 3, acc[j].w);
+      }
+    }
+  } else if (c4 * 4 == ((C + 3) / 4) * 4) {            // one spare thread: the bias gradient over this block's outputs
+    float s = 0.f;
+    for (int64_t t = r0; t < min(T, r0 + (int64_t)rows_per_block); ++t) s += gb[t];
+    atomicAdd(dw + k * C, s);
+  }
+}
+
+}  // namespace ag
+
+using namespace ag;
+extern "C" {
+
+int ag_conv1out_fwd(const float* X, int64_t x_bs, int64_t C, int32_t k, const float* w, const float* bias, float* out,
+                    int64_t B, int64_t T, void* stream) {
+  AG_CHECK_ARG(X && w && out && B > 0 && T > 0 && C > 0 && C % 4 == 0 && k > 0 && x_bs % 4 == 0, "ag_conv1out_fwd: bad args");
+  AG_CHECK_ARG(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, "ag_conv1out_fwd: unaligned");
+  const int64_t rows = B * T;
+  int64_t grid = (rows + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  conv1out_fwd_kernel<<<(unsigned)grid, 256, (size_t)k * C * 4, (cudaStream_t)stream>>>(X, x_bs, (int)C, k, w, bias, out, B, T);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+
+int ag_conv1out_dgrad(const float* g, const float* w, float* dX, int64_t dx_bs, int64_t C, int32_t k, int64_t B, int64_t T,
+                      void* stream) {
+  AG_CHECK_ARG(g && w && dX && B > 0 && B < 65536 && T > 0 && C > 0 && C % 4 == 0 && C <= 512 && k > 0 && k <= 4 && dx_bs % 4 == 0,
+               "ag_conv1out_dgrad: bad args");
+  AG_CHECK_ARG(((reinterpret_cast<uintptr_t>(dX) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, "ag_conv1out_dgrad: unaligned");
+  const int rpb = 64;
+  dim3 grid((unsigned)((T + k - 1 + rpb - 1) / rpb), (unsigned)B);
+  conv1out_dgrad_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(g, w, dX, dx_bs, (int)C, k, T, rpb);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+
+int ag_conv1out_wgrad(const float* g, const float* X, int64_t x_bs, int64_t C, int32_t k, float* dw, int64_t B, int64_t T,
+                      void* stream) {
+  AG_CHECK_ARG(g && X && dw && B > 0 && B < 65536 && T > 0 && C > 0 && C % 4 == 0 && C <= 508 && k > 0 && k <= 4 && x_bs % 4 == 0,
+               "ag_conv1out_wgrad: bad args");
+  AG_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0, "ag_conv1out_wgrad: unaligned");
+  const int rpb = 256;
+  dim3 grid((unsigned)((T + k - 1 + rpb - 1) / rpb), (unsigned)B);
+  conv1out_wgrad_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(g, X, x_bs, (int)C, k, dw, T, rpb);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+}

@@ -87,8 +87,7 @@ class _GenFn(torch.autograd.Function):
                       mask_len=lenL, mask=(s, 1, -pd))
             hh.append(Hh)
         xout = _empty(B, L, device=dev)
-        K.gemm_nt(B * L, 1, 3 * CT, (Xd, (GPAD - 1) * CT), (L, Lp * CT, CT), plan.Poff("f.w"), 3 * CT,
-                  xout, (L, L, 1), bias=plan.Poff("f.b"))
+        K.conv1out_fwd((Xd, (GPAD - 1) * CT), Lp * CT, CT, 3, plan.Poff("f.w"), plan.Poff("f.b"), xout, B, L)
         s_out = sbuf[:, :T]
         if save:
             ctx.plan, ctx.struct, ctx.dims = plan, struct, (B, T, Tcap, L)
@@ -112,13 +111,10 @@ class _GenFn(torch.autograd.Function):
         if gx is not None:
             gx = gx.contiguous()
             # ---- final conv (audiogan.py:403-407): data gradient into all CT channels, weight gradient
-            gyp = _empty(B, L + 2, device=dev)
-            K.frame_noise(gyp, L + 2, 1, gx, L, None, 0.0, B, L)
             dXd = _empty(B, Lp, CT, device=dev)
-            K.gemm_nt(B * L, CT, 3, gyp, (L, L + 2, 1), plan.Poff("f.wg"), 3, (dXd, GPAD * CT), (L, Lp * CT, CT))
+            K.conv1out_dgrad(gx, plan.Poff("f.w"), (dXd, (GPAD - 1) * CT), Lp * CT, CT, 3, B, L)
             if wgrad:
-                K.gemm_tn(B * L, 1, 3 * CT, gx, (L, L, 1), (Xd, (GPAD - 1) * CT), (L, Lp * CT, CT),
-                          plan.GPoff("f.w"), 3 * CT + 1, ones_col=True)
+                K.conv1out_wgrad(gx, (Xd, (GPAD - 1) * CT), Lp * CT, CT, 3, plan.GPoff("f.w"), B, L)
             for li in range(len(struct) - 1, -1, -1):
                 k, s, hid, out = struct[li]
                 cin = plan.cinp[li]

@@ -146,6 +146,18 @@ def copy3d(dst, d_str, src, s_str, B, T, Cn, accumulate=False):
            1 if accumulate else 0, A.stream())
 
 
+def conv1out_fwd(X, x_bs, Cn, k, w, bias, out, B, T):
+    A.call("ag_conv1out_fwd", addr(X), x_bs, Cn, k, addr(w), addr(bias), addr(out), B, T, A.stream())
+
+
+def conv1out_dgrad(g, w, dX, dx_bs, Cn, k, B, T):
+    A.call("ag_conv1out_dgrad", addr(g), addr(w), addr(dX), dx_bs, Cn, k, B, T, A.stream())
+
+
+def conv1out_wgrad(g, X, x_bs, Cn, k, dw, B, T):
+    A.call("ag_conv1out_wgrad", addr(g), addr(X), x_bs, Cn, k, addr(dw), B, T, A.stream())
+
+
 def rowgroup_sum(src, out, B, T, N):
     A.call("ag_rowgroup_sum", addr(src), addr(out), B, T, N, A.stream())
 

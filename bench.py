@@ -332,7 +332,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("AUDIOGAN_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--mode", default=os.environ.get("AUDIOGAN_MODE", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (configs[1]: 64)")
     ap.add_argument("--samples", type=int, default=16000, help="waveform length L (2 s at 8 kHz)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="samples per step of the bounded CPU baseline")

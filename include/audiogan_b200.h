@@ -199,6 +199,21 @@ int ag_ew_grad(const ag_ew_desc* d, void* stream);
 /* out[c] += sum_{b,t} in[b*bs + t*rs + c]  (bias gradients); out must be initialised. */
 int ag_colsum(const float* in, int64_t bs, int64_t rs, int64_t B, int64_t T, int64_t C, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Last generator layer, Conv1d(C -> 1, k) over the dense channel-last buffer (audiogan.py:403-407, :467): HBM-bound
+ * streaming kernels (no tensor-core work with one output channel).  X points at the first tap row of output 0,
+ * batch stride x_bs floats, C % 4 == 0, weights w[j*C + c]:
+ *   fwd:   out[b,t] = bias + sum_{j<k,c<C} X[b, t+j, c] * w[j*C+c]
+ *   dgrad: dX[b, t', c] = sum_j g[b, t'-j] * w[j*C+c]        for t' in [0, T+k-1)   (plain store)
+ *   wgrad: dw[j*C+c] += sum_{b,t} g[b,t] * X[b, t+j, c];  dw[k*C] += sum_{b,t} g[b,t]
+ * ------------------------------------------------------------------------------------------ */
+int ag_conv1out_fwd(const float* X, int64_t x_bs, int64_t C, int32_t k, const float* w, const float* bias, float* out,
+                    int64_t B, int64_t T, void* stream);
+int ag_conv1out_dgrad(const float* g, const float* w, float* dX, int64_t dx_bs, int64_t C, int32_t k, int64_t B, int64_t T,
+                      void* stream);
+int ag_conv1out_wgrad(const float* g, const float* X, int64_t x_bs, int64_t C, int32_t k, float* dw, int64_t B, int64_t T,
+                      void* stream);
+
 /* dst[b*d_bs + t*d_rs + c*d_cs] (+)= src[b*s_bs + t*s_rs + c*s_cs]: frame assembly into the dense
  * generator buffer (audiogan.py:462-464) and its gradient read-back. */
 int ag_copy3d(float* dst, int64_t d_bs, int64_t d_rs, int64_t d_cs, const float* src, int64_t s_bs, int64_t s_rs,
