@@ -216,7 +216,7 @@ def run_ours(args):
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "ms_per_step": round(ms_step, 4), "value": round(value, 2), "gpu_launches": launches}))
+            emit({"quick": True, "ms_per_step": round(ms_step, 4), "value": round(value, 2), "gpu_launches": launches})
         return
     # ---- e2e: host buffers, H2D of the step's inputs and D2H of the losses inside the timed region
     d2h = [0]
@@ -270,7 +270,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_step_throughput(args, steps=2, warmup=1)
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -323,10 +323,28 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line on the real stdout (libraries such as NCCL print banners to stdout: fd 1 is pointed at stderr
+    for the duration of the run)."""
+    line = json.dumps(obj) + "\n"
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line.encode())
+    else:
+        sys.stdout.write(line)
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
