@@ -288,3 +288,48 @@ def test_bf16_mode_within_2e2(name):
         check_dir("dD/" + k, sd[k].grad, gr)
     check_dir("dz", z.grad, grads_r[-1])
     R.done("bf16_" + name)
+
+
+def test_reference_faithful_extras_match_oracle():
+    """The extra passes of the reference loop: FGSM moves + x_grad_norm in the D-update
+    (audiogan.py:729-736, :752-759, :769-775), adversarially sampled z and the feature-matching penalty over
+    calc_dists in the G-update (:836, :847-855).  Sign steps make the inputs of later passes discontinuous in the
+    gradient, so the comparison is on losses / norms / penalties (1e-4) rather than on every parameter."""
+    import audiogan_b200 as ag
+    cs = dict(B=3, L=1200, full=True, gk={"state_size": 64}, dk={"state_size": 64})
+    Pg, Pd, g, d = build(cs)
+    inp = step_inputs(cs["B"], cs["L"], seed=99, full_length=True)
+    di = to_dev(inp)
+    di["u_stop"] = None
+    Pg_r = {k: v.clone() for k, v in Pg.items()}
+    Pd_r = {k: v.clone() for k, v in Pd.items()}
+    o1 = O.d_update(Pg_r, Pd_r, {}, inp, with_x_grad_norm=True)
+    opt_d = ag.FusedRMSprop(d.parameters(), lr=1e-4)
+    m1 = ag.d_update(g, d, opt_d, di, clip=1.0, with_x_grad_norm=True, check=True)
+    R = Report()
+    R.check("loss_d", m1["loss_d"].reshape(1), T.tensor([o1["loss_d"]]), 1e-5)
+    R.check("loss_g", m1["loss_g"].reshape(1), T.tensor([o1["loss_g"]]), 1e-5)
+    R.check("x_grad_norm", m1["x_grad_norm"].reshape(1), T.tensor([o1["x_grad_norm"]]), 1e-4)
+    # FGSM branch: runs the two extra D passes + sign steps; the real-branch loss is taken before the move
+    Pg2, Pd2, g2, d2 = build(cs)
+    o3 = O.d_update({k: v.clone() for k, v in Pg2.items()}, {k: v.clone() for k, v in Pd2.items()}, {}, inp, fgsm=True)
+    m3 = ag.d_update(g2, d2, ag.FusedRMSprop(d2.parameters(), lr=1e-4), di, clip=1.0, fgsm=True, check=True)
+    R.check("fgsm loss_d", m3["loss_d"].reshape(1), T.tensor([o3["loss_d"]]), 1e-5)
+    R.check("fgsm loss_g", m3["loss_g"].reshape(1), T.tensor([o3["loss_g"]]), 2e-3)     # sign(grad) flips move x by 1e-3
+    # G-update with feature matching (no sign steps: exact parity) and with adversarial z (sign steps: loose)
+    gb_r = {"c_g": inp["g_c_g"], "c_d": inp["g_c_d"], "z": inp["g_z"], "noise_fake": inp["g_noise_fake"], "real": inp["real"],
+            "real_len": inp["real_len"], "noise_real": inp["noise_real"], "noise_adv": inp["noise_fake"]}
+    gb_d = to_dev(gb_r)
+    gb_d["u_stop"] = None
+    Pg3, Pd3, g3, d3 = build(cs)
+    o2 = O.g_update({k: v.clone() for k, v in Pg3.items()}, {k: v.clone() for k, v in Pd3.items()}, {}, gb_r,
+                    feature_matching=True)
+    m2 = ag.g_update(g3, d3, ag.FusedRMSprop(g3.parameters(), lr=1e-4), gb_d, clip=0.1, feature_matching=True, check=True)
+    R.check("G loss", m2["loss"].reshape(1), T.tensor([o2["loss"]]), 1e-5)
+    R.check("feature_penalty", m2["feature_penalty"].detach().reshape(1), T.tensor([o2["feature_penalty"]]), 1e-4)
+    R.check("g_grad_norm (fm)", m2["g_grad_norm"].reshape(1), T.tensor([o2["g_grad_norm"]]), 1e-4)
+    Pg4, Pd4, g4, d4 = build(cs)
+    o4 = O.g_update({k: v.clone() for k, v in Pg4.items()}, {k: v.clone() for k, v in Pd4.items()}, {}, gb_r, adv_z=True)
+    m4 = ag.g_update(g4, d4, ag.FusedRMSprop(g4.parameters(), lr=1e-4), gb_d, clip=0.1, adv_z=True, check=True)
+    R.check("G loss (adv z)", m4["loss"].reshape(1), T.tensor([o4["loss"]]), 2e-3)
+    R.done("extras")
