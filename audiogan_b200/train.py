@@ -198,12 +198,46 @@ def _set_requires_grad(module, flag):
         p.requires_grad = flag
 
 
-def d_update(g, d, opt_d, batch, clip=1.0, fgsm=False, with_x_grad_norm=False, check=False, grad_sync=None):
+def _d_update_batched(g, d, opt_d, batch, clip, check, grad_sync):
+    """Even-iteration D-update (audiogan.py:723-728, :748-751, :761-788) with the real and the fake pass of the
+    discriminator run as ONE pass over the concatenated 2B minibatch.  D has no cross-sample operation, so logits,
+    losses and gradients are those of the two separate calls; the sequential recurrent kernels run once, not twice."""
+    real_len = batch["real_len"]
+    with torch.no_grad():
+        fake, _, _, fake_len = g(z=batch["z"], c=batch["c_g"], u_stop=batch.get("u_stop"))   # :748
+    fake = fake + batch["noise_fake"][:, :fake.shape[1]]                         # :750-751
+    real = batch["real"] + batch["noise_real"]                                   # :724-725
+    Bn, Lr, Lf = real.shape[0], real.shape[1], fake.shape[1]
+    if Lr != Lf:                                                                # early stop: zero-extend (== conv zero padding)
+        L = max(Lr, Lf)
+        real = torch.nn.functional.pad(real, (0, L - Lr))
+        fake = torch.nn.functional.pad(fake, (0, L - Lf))
+    x = torch.cat([real, fake], 0)
+    lens = torch.cat([real_len.to(x.device), fake_len.to(x.device)], 0)
+    c = torch.cat([batch["c_real"], batch["c_d2"]], 0)
+    cls, _, _, nf = d(x, lens, c)
+    cls_d, cls_g, nf = cls[:Bn], cls[Bn:], nf.to(cls.device)
+    loss_d, _, st_d = masked_bce_mean(cls_d, nf[:Bn], 0.9, 1.0)                   # :739-742
+    loss_g, _, st_g = masked_bce_mean(cls_g, nf[Bn:], 0.0, -1.0)                  # :762-766, :780-782
+    loss = loss_d + loss_g                                                      # :783
+    opt_d.zero_grad()
+    loss.backward()                                                             # :784-785
+    scale = grad_sync(opt_d.params) if grad_sync is not None else 1.0
+    gn = opt_d.step(clip=clip, grad_scale=scale, check=check)                   # :786-788 fused
+    return dict(loss_d=loss_d.detach(), loss_g=loss_g.detach(), loss=loss.detach(), d_grad_norm=gn, stats_d=st_d,
+                stats_g=st_g, cls_d=cls_d.detach(), cls_g=cls_g.detach(), fake=fake.detach())
+
+
+def d_update(g, d, opt_d, batch, clip=1.0, fgsm=False, with_x_grad_norm=False, check=False, grad_sync=None,
+             batched=True):
     """One discriminator update, audiogan.py:706-788.  batch keys as oracle.restated.d_update.
     ``grad_sync(params)`` (optional) is called between backward and the optimizer step (data-parallel
-    all-reduce); it returns the gradient scale to apply."""
+    all-reduce); it returns the gradient scale to apply.  ``batched`` runs the two D passes of the even-iteration
+    branch as one 2B pass (same numbers); ``batched=False`` is the literal call-by-call sequence."""
     _set_requires_grad(g, False)                                                # :706-709
     _set_requires_grad(d, True)
+    if batched and not fgsm and not with_x_grad_norm:
+        return _d_update_batched(g, d, opt_d, batch, clip, check, grad_sync)
     real_len = batch["real_len"]
     u_stop = batch.get("u_stop")
     if not fgsm:

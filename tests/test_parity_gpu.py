@@ -212,7 +212,14 @@ def test_core_step_matches_oracle_updates():
     opt_d = ag.FusedRMSprop(d.parameters(), lr=1e-4)
     opt_g = ag.FusedRMSprop(g.parameters(), lr=1e-4)
     di["u_stop"] = None
-    m1 = ag.d_update(g, d, opt_d, di, clip=1.0, check=True)
+    m1 = ag.d_update(g, d, opt_d, di, clip=1.0, check=True)          # batched: real + fake in one 2B discriminator pass
+    # the literal two-call sequence gives the same update
+    Pg_b, Pd_b, g_b, d_b = build(cs)
+    mb = ag.d_update(g_b, d_b, ag.FusedRMSprop(d_b.parameters(), lr=1e-4), di, clip=1.0, check=True, batched=False)
+    assert abs(float(mb["loss"]) - float(m1["loss"])) < 1e-6
+    for (k, p), (_, q) in zip(d.named_parameters(), d_b.named_parameters()):
+        if not noise_only(k):
+            assert rel(p, q) < 1e-5, k
     gbd = gb(di); gbd["u_stop"] = None
     m2 = ag.g_update(g, d, opt_g, gbd, clip=0.1, check=True)
     R = Report()
