@@ -14,6 +14,7 @@
 // the Bernoulli stop draw from supplied uniforms and the device-side early-exit flag -- no
 // host synchronisation per frame.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <algorithm>
 
 namespace ag {
@@ -259,7 +260,9 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ void cp_async_wait_dyn(int pending) {
   if (pending >= 10) cp_async_wait<10>();
   else if (pending >= 6) cp_async_wait<6>();
-  else cp_async_wait<2>();
+  else if (pending >= 2) cp_async_wait<2>();
+  else if (pending == 1) cp_async_wait<1>();
+  else cp_async_wait<0>();
 }
 
 // MT 16-row tiles of the weight slice x up to 8 batch tiles of 8.  Warp w owns row tile w % MT and the batch tiles
@@ -346,6 +349,187 @@ __device__ __forceinline__ void slice_gemm_mma(float (&acc)[MT][4], const __nv_b
   __syncthreads();
 }
 
+
+// ------------------------------------------------------------------------------------ tcgen05 variant (prec = 2)
+// The per-step product on 5th-generation tensor cores: D[batch (M = 64 TMEM lanes), rows (N = NR columns)] +=
+// act[batch, K] . Wslice[rows, K]^T.  The weight slice is the B operand, resident in shared memory for the whole
+// sequence in the canonical K-major SWIZZLE_128B layout (one [NR x 128 B] tile per 64 columns); the [B, K] activation
+// chunk is the A operand, staged by cp.async straight into the same swizzled layout (64-row tiles; rows past the
+// CTA's batch range stay zero).  One elected thread issues the MMAs of a chunk; tcgen05.commit recycles the ring slot
+// and, after the last chunk, publishes the accumulator, which warps 0-3 read back with tcgen05.ld.
+struct TcState {
+  uint8_t* Wt;            // [nkb][NR][128 B]
+  uint8_t* ring;          // [NST][kcb][64][128 B]
+  uint64_t* slot_free;    // [NST]
+  uint64_t* acc_ready;
+  uint32_t tmem;
+  uint32_t gc;            // chunks issued so far (all steps): slot = gc % NST, use = gc / NST
+  uint32_t steps;         // accumulator hand-offs so far
+  int NST, kcb, rb;
+};
+
+struct StagerTc {
+  const __nv_bfloat16* r0[2];
+  const __nv_bfloat16* r1[2];
+  int dst[2], kk[2], n0, K;
+  bool on[2];
+  __device__ __forceinline__ void init(const Seg& sg, int b0, int B, int K_, int kc, int rb) {
+    n0 = sg.n0;
+    K = K_;
+    const int cpr = kc >> 3;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = threadIdx.x + LT * i;
+      on[i] = idx < rb * cpr;
+      const int bl = idx / cpr, b = b0 + bl, c = idx - bl * cpr;        // c: 16-byte column inside the chunk
+      kk[i] = c << 3;
+      dst[i] = (c >> 3) * 8192 + bl * 128 + (((c & 7) ^ (bl & 7)) << 4);   // bytes: k-block tile, row, swizzled 16-byte cell
+      const bool ok = on[i] && b < B;
+      r0[i] = (ok && sg.q0) ? sg.q0 + b * sg.s0 : nullptr;
+      r1[i] = (ok && sg.q1) ? sg.q1 + b * sg.s1 - sg.n0 : nullptr;
+    }
+  }
+  __device__ __forceinline__ void issue(uint8_t* slot, int k0) const {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (!on[i]) continue;
+      const int k = k0 + kk[i];
+      const __nv_bfloat16* base = (k < n0) ? r0[i] : r1[i];
+      if (base != nullptr && k < K) cp_async16(slot + dst[i], base + k);
+      else *reinterpret_cast<uint4*>(slot + dst[i]) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+};
+
+// out[bl * ldo + n] = sum_k act[b0 + bl, k] * Wslice[n, k] for bl < rb, n < NR
+template <int NR>
+__device__ __forceinline__ void slice_gemm_tc(TcState& st, const Seg& sg, int K, int b0, int B, float* out, int ldo,
+                                              PhaseClock* pc = nullptr) {
+  using namespace tc;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int kc = st.kcb * 64, slot_bytes = st.kcb * 8192;
+  const int nch = (K + kc - 1) / kc;
+  StagerTc sgr;
+  sgr.init(sg, b0, B, K, kc, st.rb);
+  auto acquire_and_issue = [&](int c) {             // chunk c of this step goes to ring slot (gc + c) % NST
+    const uint32_t g = st.gc + (uint32_t)c, slot = g % (uint32_t)st.NST, use = g / (uint32_t)st.NST;
+    if (use > 0) mbar_wait(&st.slot_free[slot], (use - 1) & 1);        // the MMAs that last read this slot are done
+    sgr.issue(st.ring + slot * slot_bytes, c * kc);
+  };
+  for (int s = 0; s < st.NST - 1; ++s) {
+    if (s < nch) acquire_and_issue(s);
+    cp_async_commit();
+  }
+  const uint32_t idesc = umma_idesc(64, NR, 0, 0);
+  const uint64_t da0 = umma_desc(smem_u32(st.ring), 16, 1024), db0 = umma_desc(smem_u32(st.Wt), 16, 1024);
+  for (int c = 0; c < nch; ++c) {
+    long long q0 = 0;
+    if (pc) q0 = clock64();
+    cp_async_wait_dyn(st.NST - 2);
+    fence_proxy_async();                            // this thread's landed cp.async / zero stores -> visible to the MMA proxy
+    __syncthreads();
+    if (pc) { const long long q1 = clock64(); pc->acc[5] += q1 - q0; q0 = q1; }
+    if (c + st.NST - 1 < nch) acquire_and_issue(c + st.NST - 1);
+    cp_async_commit();
+    if (pc) { const long long q1 = clock64(); pc->acc[6] += q1 - q0; q0 = q1; }
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t slot = (st.gc + (uint32_t)c) % (uint32_t)st.NST;
+      // descriptors differ only in the 14-bit start-address field: advance it with plain adds
+      uint64_t da = da0 + (uint64_t)(slot * (uint32_t)(slot_bytes >> 4));
+      uint64_t db = db0 + (uint64_t)((uint32_t)(c * st.kcb) * (uint32_t)(NR * 8));
+      const int nkbv = min(st.kcb, (K - c * kc + 63) >> 6);
+      for (int kb = 0; kb < nkbv; ++kb) {
+        tc_mma(st.tmem, da, db, idesc, (c | kb) ? 1u : 0u);
+        tc_mma(st.tmem, da + 2, db + 2, idesc, 1u);
+        tc_mma(st.tmem, da + 4, db + 4, idesc, 1u);
+        tc_mma(st.tmem, da + 6, db + 6, idesc, 1u);
+        da += 512;                  // next 64-column A tile: 8192 B
+        db += NR * 8;               // next 64-column B tile: NR * 128 B
+      }
+      tc_commit(&st.slot_free[slot]);
+      if (c == nch - 1) tc_commit(st.acc_ready);
+    }
+    if (pc) { const long long q1 = clock64(); pc->acc[7] += q1 - q0; }
+  }
+  st.gc += (uint32_t)nch;
+  cp_async_wait<0>();
+  long long q2 = 0;
+  if (pc) q2 = clock64();
+  mbar_wait(st.acc_ready, st.steps & 1);
+  if (pc) pc->acc[3] += clock64() - q2;
+  st.steps += 1;
+  tc_fence_after();
+  // accumulator row m (batch) lives in TMEM lane (m % 16) + 32 * (m / 16): warp q < 4 holds batches 16q .. 16q+15
+  if (w < 4) {
+    const int bl = 16 * w + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < NR; c0 += 16) {
+      uint32_t v[16];
+      tc_ld16(st.tmem + ((uint32_t)(w * 32) << 16) + (uint32_t)c0, v);
+      if (lane < 16 && bl < st.rb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(out + bl * ldo + c0 + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+}
+
+// one-time setup: barriers, TMEM columns, zeroed ring (rows past the batch range must read as zeros), swizzled weights
+template <int NR>
+__device__ __forceinline__ void tc_setup(TcState& st, uint32_t* tmem_slot, int nkb) {
+  using namespace tc;
+  const int tid = threadIdx.x, w = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < st.NST; ++s) mbar_init(&st.slot_free[s], 1);
+    mbar_init(st.acc_ready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr uint32_t COLS = NR < 32 ? 32 : (NR <= 32 ? 32 : (NR <= 64 ? 64 : (NR <= 128 ? 128 : 256)));
+  if (w == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  const int ring_bytes = st.NST * st.kcb * 8192;
+  for (int i = tid * 16; i < ring_bytes; i += LT * 16) *reinterpret_cast<uint4*>(st.ring + i) = make_uint4(0u, 0u, 0u, 0u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  st.tmem = *tmem_slot;
+  st.gc = 0;
+  st.steps = 0;
+  (void)nkb;
+}
+template <int NR>
+__device__ __forceinline__ void tc_teardown(TcState& st) {
+  using namespace tc;
+  constexpr uint32_t COLS = NR < 32 ? 32 : (NR <= 32 ? 32 : (NR <= 64 ? 64 : (NR <= 128 ? 128 : 256)));
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(st.tmem), "r"(COLS) : "memory");
+  }
+}
+// fp32 global row `src` (K columns) -> row lr of the swizzled B-operand tiles (zero past K up to nkb * 64)
+template <int NR>
+__device__ __forceinline__ void fill_slice_tc(uint8_t* Wt, int lr, const float* src, int K, int nkb) {
+  for (int k8 = threadIdx.x; k8 < nkb * 8; k8 += LT) {          // one 16-byte cell (8 columns) per iteration
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k8 * 8 + 2 * e;
+      const float a = k < K ? src[k] : 0.f, b = k + 1 < K ? src[k + 1] : 0.f;
+      pk[e] = tc::pack_bf16(a, b);
+    }
+    const int kb = k8 >> 3, c = k8 & 7;
+    *reinterpret_cast<uint4*>(Wt + (size_t)kb * (NR * 128) + lr * 128 + ((c ^ (lr & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
 // fp32 rows of a weight matrix -> bf16 resident slice (tail columns up to ldw zeroed)
 __device__ __forceinline__ void fill_slice16(__nv_bfloat16* Ws, int ldw, int lr, const float* src, int K) {
   // called by all threads with the same (lr, src): columns strided over the block
@@ -395,9 +579,11 @@ __device__ __forceinline__ void warp_rows_dot16(float (&out)[4], const __nv_bflo
 }
 
 // =====================================================================================  forward
-template <int HS, bool FB, bool RES, bool BF>
-__global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, const int ncta_dir, const int PR, const int NST, const int bsplit) {
+template <int HS, bool FB, bool RES, int BF>
+__global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, const int ncta_dir, const int PR, const int NST, const int bsplit,
+                                                         const int kcb) {
   constexpr int ROWS = 4 * HS;
+  constexpr int GSLD = BF == 2 ? ROWS + 4 : ROWS;   // gate exchange tile row stride
   constexpr int MT = ROWS / 16 > 0 ? ROWS / 16 : 1;
   constexpr int RL = ROWS < 32 ? ROWS : 32;
   constexpr int KS = 32 / RL;
@@ -422,13 +608,34 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
   // bf16: the gate exchange tile aliases the (idle) cp.async ring
   float* gs = BF ? reinterpret_cast<float*>(stage16) : stage + 2 * BTILE * SLD;
   float* cs = BF ? reinterpret_cast<float*>(stage16 + NST * SLOT16) : gs + BTILE * ROWS;
+  TcState tcs;
+  uint32_t* tmem_slot = nullptr;
+  const int nkb = (K1 + 63) / 64;
+  if (BF == 2) {
+    // tcgen05: [Wt nkb x ROWS x 128 B | ring NST x kcb x 8 KB | barriers 64 B | gs 64 x GSLD fp32 | cs ...], 1 KB aligned
+    uint8_t* sm8 = reinterpret_cast<uint8_t*>(smem);
+    sm8 += (1024u - (tc::smem_u32(sm8) & 1023u)) & 1023u;
+    tcs.Wt = sm8;
+    tcs.ring = sm8 + (size_t)nkb * ROWS * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tcs.ring + (size_t)NST * kcb * 8192);
+    tcs.slot_free = bars;
+    tcs.acc_ready = bars + 6;
+    tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    tcs.NST = NST; tcs.kcb = kcb;
+    tcs.rb = min(64, (Bper + 15) & ~15);
+    gs = reinterpret_cast<float*>(bars + 8);
+    cs = gs + BTILE * GSLD;
+  }
   float* W2s = cs + Bper * HS;
   int* gen = reinterpret_cast<int*>(W2s + (FB ? PR * ld2 : 0));
   int* cnt = gen + B;
 
   // local row lr = jj*4 + q  <->  global gate row q*H + j0 + jj
   const float* w1d = d.w1 + (int64_t)dir * 4 * H * K1;
-  if (BF) {
+  if (BF == 2) {
+    for (int lr = 0; lr < ROWS; ++lr) fill_slice_tc<ROWS>(tcs.Wt, lr, w1d + (int64_t)((lr & 3) * H + j0 + (lr >> 2)) * K1, K1, nkb);
+    tc_setup<ROWS>(tcs, tmem_slot, nkb);
+  } else if (BF) {
     for (int lr = 0; lr < ROWS; ++lr) fill_slice16(Ws16, ldw16, lr, w1d + (int64_t)((lr & 3) * H + j0 + (lr >> 2)) * K1, K1);
   } else if (RES) {
     const int K4 = K1 / 4;
@@ -492,7 +699,10 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
         for (int q = 0; q < 4; ++q)
           pre[ii][q] = (b < bhi) ? d.pre[b * gstr + (int64_t)t * ndir * 4 * H + dir * 4 * H + q * H + j0 + jj] : 0.f;
       }
-      if (BF) {
+      if (BF == 2) {
+        slice_gemm_tc<ROWS>(tcs, sg, K1, b0, bhi, gs, GSLD, d.dbg ? &pc : nullptr);
+        pc.lap(0);
+      } else if (BF) {
         float accm[MT][4];
 #pragma unroll
         for (int i = 0; i < MT; ++i) { accm[i][0] = 0.f; accm[i][1] = 0.f; accm[i][2] = 0.f; accm[i][3] = 0.f; }
@@ -527,7 +737,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
         const int it = tid + LT * ii, bl = it / HS, jj = it - bl * HS, b = b0 + bl;
         if (b >= bhi) continue;
         const int j = j0 + jj;
-        const float4 a = *reinterpret_cast<const float4*>(gs + bl * ROWS + jj * 4);
+        const float4 a = *reinterpret_cast<const float4*>(gs + bl * GSLD + jj * 4);
         const bool valid = !d.len || t < d.len[b];
         float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, c = 0.f, h = 0.f;
         if (valid) {
@@ -614,6 +824,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
     for (int i = 0; i < 8; ++i) q[i] = pc.acc[i];
     q[4] = clock64() - tstart;
   }
+  if (BF == 2) tc_teardown<ROWS>(tcs);
   if (FB && owns_logit) {
     __syncthreads();
     for (int b = tid; b < B; b += LT) if (d.glen) d.glen[b] = cnt[b];
@@ -622,8 +833,10 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
 }
 
 // ====================================================================================  backward
-template <int HS, bool FB, bool RES, bool BF>
-__global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, const int ncta_dir, const int PR, const int NST, const int bsplit) {
+template <int HS, bool FB, bool RES, int BF>
+__global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, const int ncta_dir, const int PR, const int NST, const int bsplit,
+                                                         const int kcb) {
+  constexpr int DHLD = BF == 2 ? HS + 4 : HS;       // dh exchange tile row stride
   constexpr int RL = HS;            // 4, 8 or 16 rows -> k split over the rest of the warp
   constexpr int KS = 32 / RL;
   constexpr int IPT = (BTILE * HS) / LT;
@@ -645,10 +858,30 @@ __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, c
   __nv_bfloat16* stage16 = Ws16 + HS * ldw16;
   float* dhs = BF ? reinterpret_cast<float*>(stage16) : stage + 2 * BTILE * SLD;      // bf16: aliases the idle ring
   float* dcs = BF ? reinterpret_cast<float*>(stage16 + NST * SLOT16) : dhs + BTILE * HS;
+  TcState tcs;
+  uint32_t* tmem_slot = nullptr;
+  const int nkb = (K + 63) / 64;
+  if (BF == 2) {
+    uint8_t* sm8 = reinterpret_cast<uint8_t*>(smem);
+    sm8 += (1024u - (tc::smem_u32(sm8) & 1023u)) & 1023u;
+    tcs.Wt = sm8;
+    tcs.ring = sm8 + (size_t)nkb * HS * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tcs.ring + (size_t)NST * kcb * 8192);
+    tcs.slot_free = bars;
+    tcs.acc_ready = bars + 6;
+    tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    tcs.NST = NST; tcs.kcb = kcb;
+    tcs.rb = min(64, (Bper + 15) & ~15);
+    dhs = reinterpret_cast<float*>(bars + 8);
+    dcs = dhs + BTILE * DHLD;
+  }
   float* Wxs = dcs + Bper * HS;
 
   const float* w1d = d.w1t + ((int64_t)dir * H + j0) * K;
-  if (BF) {
+  if (BF == 2) {
+    for (int lr = 0; lr < HS; ++lr) fill_slice_tc<HS>(tcs.Wt, lr, w1d + (int64_t)lr * K, K, nkb);
+    tc_setup<HS>(tcs, tmem_slot, nkb);
+  } else if (BF) {
     for (int lr = 0; lr < HS; ++lr) fill_slice16(Ws16, ldw16, lr, w1d + (int64_t)lr * K, K);
   } else if (RES) {
     const int K4 = K / 4;
@@ -780,7 +1013,14 @@ __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, c
           }
         }
       }
-      if (BF) {
+      if (BF == 2) {
+        if (has_next || FB) {
+          slice_gemm_tc<HS>(tcs, sg, K, b0, bhi, dhs, DHLD, d.dbg ? &pc : nullptr);
+        } else {
+          for (int i = tid; i < BTILE * DHLD; i += LT) dhs[i] = 0.f;
+        }
+        pc.lap(0);
+      } else if (BF) {
         float accm[MT][4];
 #pragma unroll
         for (int i = 0; i < MT; ++i) { accm[i][0] = 0.f; accm[i][1] = 0.f; accm[i][2] = 0.f; accm[i][3] = 0.f; }
@@ -821,7 +1061,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, c
           continue;
         }
         const float gi = pg[ii][0], gf = pg[ii][1], gg = pg[ii][2], go = pg[ii][3], c = pg[ii][4], cprev = pg[ii][5];
-        const float dh = dhs[bl * HS + jj] + pg[ii][6];
+        const float dh = dhs[bl * DHLD + jj] + pg[ii][6];
         const float tc = tanhf(c);
         const float dc = dcs[(b - blo) * HS + jj] + dh * go * (1.f - tc * tc);
         dcs[(b - blo) * HS + jj] = dc * gf;
@@ -844,10 +1084,11 @@ __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, c
     for (int i = 0; i < 8; ++i) q[i] = pc.acc[i];
     q[4] = clock64() - tstart;
   }
+  if (BF == 2) tc_teardown<HS>(tcs);
 }
 
 // ---------------------------------------------------------------------------------- host side
-struct Plan { int HS, ncta_dir, PR, nst, bsplit; bool res, bf; size_t smem; };
+struct Plan { int HS, ncta_dir, PR, nst, bsplit, kcb, bf; bool res; size_t smem; };
 
 static int pick_hs(int H, int ndir) {
   const int hs_opts[3] = {4, 8, 16};
@@ -889,25 +1130,39 @@ static int check_lstm(const ag_lstm_desc* d, const char* who, bool bwd) {
   return AG_OK;
 }
 
+static int bper_of(int B, int bsplit) { return (((B + bsplit - 1) / bsplit) + 7) & ~7; }
+static size_t fwd_smem_tc(const ag_lstm_desc* d, int HS, int PR, int NST, int kcb, int bsplit) {
+  const int F = d->F, K1 = d->H + F, nkb = (K1 + 63) / 64, rows = 4 * HS;
+  return 1024 + (size_t)nkb * rows * 128 + (size_t)NST * kcb * 8192 + 64 + (size_t)BTILE * (rows + 4) * 4 +
+         (size_t)bper_of(d->B, bsplit) * HS * 4 + (F > 0 ? (size_t)PR * pad_ld(d->H) * 4 : 0) + (size_t)2 * d->B * 4 + 16;
+}
+static size_t bwd_smem_tc(const ag_lstm_desc* d, int HS, int PR, int NST, int kcb, int bsplit) {
+  const int F = d->F, FP = F > 0 ? ((F + 1 + 7) / 8) * 8 : 0, K = 4 * d->H + FP, nkb = (K + 63) / 64;
+  return 1024 + (size_t)nkb * HS * 128 + (size_t)NST * kcb * 8192 + 64 + (size_t)BTILE * (HS + 4) * 4 +
+         (size_t)bper_of(d->B, bsplit) * HS * 4 + (F > 0 ? (size_t)PR * (2 * d->H + 4) * 4 : 0) + 16;
+}
+
 template <typename KernT>
 static int launch_coop(KernT kern, const ag_lstm_desc* d, const Plan& p, cudaStream_t s) {
   AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   ag_lstm_desc dd = *d;
-  int ncta_dir = p.ncta_dir, PR = p.PR, nst = p.nst, bsplit = p.bsplit;
-  void* args[5] = {&dd, &ncta_dir, &PR, &nst, &bsplit};
+  int ncta_dir = p.ncta_dir, PR = p.PR, nst = p.nst, bsplit = p.bsplit, kcb = p.kcb;
+  void* args[6] = {&dd, &ncta_dir, &PR, &nst, &bsplit, &kcb};
   AG_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)(p.ncta_dir * d->ndir * p.bsplit)), dim3(LT), args, p.smem, s));
   return AG_OK;
 }
 
 #define AG_LSTM_DISPATCH_HS(KERN, HS_)                                                                               \
   do {                                                                                                              \
-    if (p.bf) return fb ? launch_coop(KERN<HS_, true, true, true>, d, p, s) : launch_coop(KERN<HS_, false, true, true>, d, p, s); \
-    if (fb) return p.res ? launch_coop(KERN<HS_, true, true, false>, d, p, s) : launch_coop(KERN<HS_, true, false, false>, d, p, s); \
-    return p.res ? launch_coop(KERN<HS_, false, true, false>, d, p, s) : launch_coop(KERN<HS_, false, false, false>, d, p, s);     \
+    if (p.bf == 1) return fb ? launch_coop(KERN<HS_, true, true, 1>, d, p, s) : launch_coop(KERN<HS_, false, true, 1>, d, p, s); \
+    if (fb) return p.res ? launch_coop(KERN<HS_, true, true, 0>, d, p, s) : launch_coop(KERN<HS_, true, false, 0>, d, p, s); \
+    return p.res ? launch_coop(KERN<HS_, false, true, 0>, d, p, s) : launch_coop(KERN<HS_, false, false, 0>, d, p, s);     \
   } while (0)
 #define AG_LSTM_DISPATCH(KERN)          \
   do {                                  \
     const bool fb = d->F > 0;           \
+    if (p.bf == 2 && p.HS == 16) return fb ? launch_coop(KERN<16, true, true, 2>, d, p, s) : launch_coop(KERN<16, false, true, 2>, d, p, s); \
+    if (p.bf == 2 && p.HS == 32) return fb ? launch_coop(KERN<32, true, true, 2>, d, p, s) : launch_coop(KERN<32, false, true, 2>, d, p, s); \
     if (p.HS == 4) AG_LSTM_DISPATCH_HS(KERN, 4);  \
     if (p.HS == 8) AG_LSTM_DISPATCH_HS(KERN, 8);  \
     if (p.HS == 16) AG_LSTM_DISPATCH_HS(KERN, 16);  \
@@ -926,10 +1181,28 @@ int ag_lstm_fwd(const ag_lstm_desc* d, void* stream) {
   int rc = check_lstm(d, "ag_lstm_fwd", false);
   if (rc) return rc;
   Plan p;
-  p.res = true; p.bf = false; p.nst = NST_MIN; p.bsplit = 1; p.HS = 0;
+  p.res = true; p.bf = 0; p.nst = NST_MIN; p.bsplit = 1; p.HS = 0; p.kcb = 1;
   const int nsm = sm_count();
   auto pr_for = [&](int ncta) { return d->F > 0 ? (d->F + 1 + ncta - 1) / ncta : 0; };
-  if (d->prec == 1 && d->H % 8 == 0 && d->F % 8 == 0) {
+  if (d->prec == 2 && d->H % 8 == 0 && d->F % 8 == 0) {
+    // tcgen05 variant: 64 or 128 gate rows per CTA (the MMA's N), batch on the 64 TMEM lanes, 3-deep ring
+    const int opts[2] = {32, 16};
+    for (int i = 0; i < 2 && !p.bf; ++i) {
+      const int hs = opts[i];
+      if (d->H % hs || (int64_t)d->ndir * (d->H / hs) > nsm) continue;
+      const int groups = d->ndir * (d->H / hs);
+      int bs = std::max(1, std::min(nsm / groups, (d->B + 15) / 16));
+      const int pr = pr_for(groups * bs);
+      const int rb = std::min(64, (bper_of(d->B, bs) + 15) & ~15);
+      for (int kcb = 64 / rb; kcb >= 1 && !p.bf; kcb >>= 1) {
+        const size_t sm = fwd_smem_tc(d, hs, pr, 3, kcb, bs);
+        if (sm > (size_t)smem_optin()) continue;
+        AG_CHECK_ARG(d->hbuf16 && (d->F == 0 || d->xbuf16), "ag_lstm_fwd: bf16 mode needs hbuf16 / xbuf16");
+        p.bf = 2; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm; p.nst = 3; p.kcb = kcb;
+      }
+    }
+  }
+  if (!p.bf && d->prec >= 1 && d->H % 8 == 0 && d->F % 8 == 0) {
     // tensor-core variant: the largest slice whose bf16 weights stay resident (fewest re-reads of the [B, K] operand
     // per step), then split the batch over the remaining SMs (>= 8 samples per CTA)
     const int opts[4] = {32, 16, 8, 4};
@@ -943,7 +1216,7 @@ int ag_lstm_fwd(const ag_lstm_desc* d, void* stream) {
       const size_t sm16 = fwd_smem(d, hs, pr, true, true);
       if (sm16 > (size_t)smem_optin()) continue;
       AG_CHECK_ARG(d->hbuf16 && (d->F == 0 || d->xbuf16), "ag_lstm_fwd: bf16 mode needs hbuf16 / xbuf16");
-      p.bf = true; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm16;
+      p.bf = 1; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm16;
     }
   }
   if (!p.bf) {
@@ -965,10 +1238,27 @@ int ag_lstm_bwd(const ag_lstm_desc* d, void* stream) {
   int rc = check_lstm(d, "ag_lstm_bwd", true);
   if (rc) return rc;
   Plan p;
-  p.res = true; p.bf = false; p.nst = NST_MIN; p.bsplit = 1; p.HS = 0;
+  p.res = true; p.bf = 0; p.nst = NST_MIN; p.bsplit = 1; p.HS = 0; p.kcb = 1;
   const int nsm = sm_count();
   auto pr_for = [&](int ncta) { return d->F > 0 ? (d->F + ncta - 1) / ncta : 0; };
-  if (d->prec == 1) {
+  if (d->prec == 2) {
+    const int opts[2] = {32, 16};
+    for (int i = 0; i < 2 && !p.bf; ++i) {
+      const int hs = opts[i];
+      if (d->H % hs || (int64_t)d->ndir * (d->H / hs) > nsm) continue;
+      const int groups = d->ndir * (d->H / hs);
+      int bs = std::max(1, std::min(nsm / groups, (d->B + 15) / 16));
+      const int pr = pr_for(groups * bs);
+      const int rb = std::min(64, (bper_of(d->B, bs) + 15) & ~15);
+      for (int kcb = 64 / rb; kcb >= 1 && !p.bf; kcb >>= 1) {
+        const size_t sm = bwd_smem_tc(d, hs, pr, 3, kcb, bs);
+        if (sm > (size_t)smem_optin()) continue;
+        AG_CHECK_ARG(d->dgates16 && (d->F == 0 || d->dpx16), "ag_lstm_bwd: bf16 mode needs dgates16 / dpx16");
+        p.bf = 2; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm; p.nst = 3; p.kcb = kcb;
+      }
+    }
+  }
+  if (!p.bf && d->prec >= 1) {
     const int opts[2] = {32, 16};
     for (int i = 0; i < 2 && !p.bf; ++i) {
       const int hs = opts[i];
@@ -980,7 +1270,7 @@ int ag_lstm_bwd(const ag_lstm_desc* d, void* stream) {
       const size_t sm16 = bwd_smem(d, hs, pr, true, true);
       if (sm16 > (size_t)smem_optin()) continue;
       AG_CHECK_ARG(d->dgates16 && (d->F == 0 || d->dpx16), "ag_lstm_bwd: bf16 mode needs dgates16 / dpx16");
-      p.bf = true; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm16;
+      p.bf = 1; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm16;
     }
   }
   if (!p.bf) {

@@ -12,6 +12,8 @@ column) and come back through the inverse index map and the weight-norm backward
 All layouts are described with ordinary torch indexing on *index tensors* (``-1`` = structural
 zero), so a layout is declared exactly the way one would write the corresponding reshape.
 """
+import os
+
 import torch
 from torch.autograd.function import once_differentiable
 
@@ -86,6 +88,9 @@ class NetPlan:
         self._unpack_idx = {}
         self.params = []                # parameters in module.parameters() order
         self.mode = "fp32"
+        # recurrent products in bf16 mode: 1 = mma.sync path (default: measured faster end to end, see
+        # profiles/r1_lstm_phase_cycles.txt), 2 = tcgen05 / TMEM path (AUDIOGAN_LSTM=tcgen05)
+        self.lstm_prec = 2 if os.environ.get("AUDIOGAN_LSTM", "") == "tcgen05" else 1
 
     # -- declaration ----------------------------------------------------------------------
     def weight(self, name, v, g=None):

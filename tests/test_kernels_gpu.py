@@ -280,8 +280,10 @@ def test_gemm_tn_tc_conv_wgrad_view():
 
 
 @pytest.mark.parametrize("H,B,Tn,ndir,Fr", [(64, 5, 12, 2, 0), (512, 40, 9, 2, 0), (64, 9, 7, 1, 200), (1024, 64, 6, 1, 200)])
-def test_lstm_bf16_mode_tracks_fp32_kernels(H, B, Tn, ndir, Fr):
-    """prec=1 (mma.sync bf16 products, fp32 state) against the fp32 kernels on the same inputs: <= 2e-2."""
+@pytest.mark.parametrize("prec_tc", [1, 2])
+def test_lstm_bf16_mode_tracks_fp32_kernels(H, B, Tn, ndir, Fr, prec_tc):
+    """prec=1 (mma.sync) / prec=2 (tcgen05, TMEM accumulator) bf16 products with fp32 state against the fp32 kernels
+    on the same inputs: <= 2e-2."""
     from audiogan_b200 import kernels as Kn
     T.manual_seed(11)
     dev = "cuda"
@@ -302,14 +304,14 @@ def test_lstm_bf16_mode_tracks_fp32_kernels(H, B, Tn, ndir, Fr):
     dh_ext = None if Fr else T.randn(B, Tn, ndir * H, device=dev)
     dx_ext = T.randn(B, Tn, Fr, device=dev) if Fr else None
     res = {}
-    for prec in (0, 1):
+    for prec in (0, prec_tc):
         hbuf, gates, cbuf = T.zeros(B, Tn + 2, ndir * H, device=dev), T.empty(B, Tn, ndir * 4 * H, device=dev), T.empty(B, Tn, ndir * H, device=dev)
         xbuf = T.zeros(B, Tn + 1, Fr, device=dev) if Fr else None
         sbuf = T.zeros(B, Tn, device=dev) if Fr else None
         misc = T.zeros(16, dtype=T.int32, device=dev)
         kw = {}
         if prec:
-            kw = dict(prec=1, hbuf16=T.zeros(B, Tn + 2, ndir * H, device=dev, dtype=T.bfloat16),
+            kw = dict(prec=prec, hbuf16=T.zeros(B, Tn + 2, ndir * H, device=dev, dtype=T.bfloat16),
                       xbuf16=T.zeros(B, Tn + 1, Fr, device=dev, dtype=T.bfloat16) if Fr else None)
         Kn.lstm_fwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=ndir, F=Fr, pre=pre, w1=w1, w2=w2, b2=b2, hbuf=hbuf, gates=gates, cbuf=cbuf,
                     len=lens, xbuf=xbuf, sbuf=sbuf, t_end=(misc, 8) if Fr else None, barrier=misc, **kw)
@@ -317,13 +319,14 @@ def test_lstm_bf16_mode_tracks_fp32_kernels(H, B, Tn, ndir, Fr):
         dpx = T.empty(B, Tn, FP, device=dev) if Fr else None
         kw = {}
         if prec:
-            kw = dict(prec=1, dgates16=T.empty(B, Tn, ndir * 4 * H, device=dev, dtype=T.bfloat16),
+            kw = dict(prec=prec, dgates16=T.empty(B, Tn, ndir * 4 * H, device=dev, dtype=T.bfloat16),
                       dpx16=T.empty(B, Tn, FP, device=dev, dtype=T.bfloat16) if Fr else None)
         Kn.lstm_bwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=ndir, F=Fr, gates=gates, cbuf=cbuf, len=lens, xbuf=xbuf, dh_ext=dh_ext,
                     dx_ext=dx_ext, dgates=dgates, dpx=dpx, w1t=w1t, wxt=wxt, barrier=misc, **kw)
         res[prec] = (hbuf.clone(), dgates.clone(), xbuf.clone() if Fr else None, kw.get("dgates16"))
-    assert rel(res[1][0], res[0][0]) < 2e-2, "h"
-    assert rel(res[1][1], res[0][1]) < 3e-2, "dgates"
+    r1 = res[prec_tc]
+    assert rel(r1[0], res[0][0]) < 2e-2, "h"
+    assert rel(r1[1], res[0][1]) < 3e-2, "dgates"
     if Fr:
-        assert rel(res[1][2], res[0][2]) < 2e-2, "x"
-    assert rel(res[1][3].float(), res[1][1]) < 1e-2, "bf16 shadow"
+        assert rel(r1[2], res[0][2]) < 2e-2, "x"
+    assert rel(r1[3].float(), r1[1]) < 1e-2, "bf16 shadow"
