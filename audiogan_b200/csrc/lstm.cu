@@ -581,7 +581,7 @@ __device__ __forceinline__ void warp_rows_dot16(float (&out)[4], const __nv_bflo
 // =====================================================================================  forward
 template <int HS, bool FB, bool RES, int BF>
 __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, const int ncta_dir, const int PR, const int NST, const int bsplit,
-                                                         const int kcb) {
+                                                         const int kcb, const int nbg2) {
   constexpr int ROWS = 4 * HS;
   constexpr int GSLD = BF == 2 ? ROWS + 4 : ROWS;   // gate exchange tile row stride
   constexpr int MT = ROWS / 16 > 0 ? ROWS / 16 : 1;
@@ -627,7 +627,8 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
     cs = gs + BTILE * GSLD;
   }
   float* W2s = cs + Bper * HS;
-  int* gen = reinterpret_cast<int*>(W2s + (FB ? PR * ld2 : 0));
+  // phase-2 weights: fp32 rows (stride ld2) or, in the bf16 modes, bf16 rows (stride H + 8)
+  int* gen = reinterpret_cast<int*>(W2s + (FB ? (BF ? (PR * (H + 8) + 1) / 2 : PR * ld2) : 0));
   int* cnt = gen + B;
 
   // local row lr = jj*4 + q  <->  global gate row q*H + j0 + jj
@@ -654,16 +655,30 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
   }
   for (int i = tid; i < Bper * HS; i += LT) cs[i] = 0.f;
   // phase-2 rows owned by this CTA (feedback only; ndir == 1)
-  int p0 = 0, np = 0;
+  // phase 2 is tiled 2-D: CTA = (row group of PR proj/stop rows, batch group) -> each CTA reads only its batch
+  // group's h rows instead of all of h
+  int p0 = 0, np = 0, b2lo = 0, b2hi = 0;
   bool owns_logit = false;
   if (FB) {
-    p0 = blockIdx.x * PR;
+    const int rg = blockIdx.x / nbg2, bg = blockIdx.x - rg * nbg2;
+    const int B2per = (B + nbg2 - 1) / nbg2;
+    b2lo = min(B, bg * B2per);
+    b2hi = min(B, b2lo + B2per);
+    p0 = rg * PR;
     np = min(PR, F + 1 - p0);
-    if (np < 0) np = 0;
+    if (np < 0 || b2hi <= b2lo) np = 0;
     owns_logit = (np > 0) && (p0 + np == F + 1);
-    for (int idx = tid; idx < np * (H / 4); idx += LT) {
-      const int r = idx / (H / 4), k4 = idx - r * (H / 4);
-      *reinterpret_cast<float4*>(W2s + r * ld2 + 4 * k4) = *reinterpret_cast<const float4*>(d.w2 + (int64_t)(p0 + r) * H + 4 * k4);
+    if (BF) {
+      __nv_bfloat16* W2s16 = reinterpret_cast<__nv_bfloat16*>(W2s);
+      for (int idx = tid; idx < np * H; idx += LT) {
+        const int r = idx / H, k = idx - r * H;
+        W2s16[r * (H + 8) + k] = __float2bfloat16(d.w2[(int64_t)(p0 + r) * H + k]);
+      }
+    } else {
+      for (int idx = tid; idx < np * (H / 4); idx += LT) {
+        const int r = idx / (H / 4), k4 = idx - r * (H / 4);
+        *reinterpret_cast<float4*>(W2s + r * ld2 + 4 * k4) = *reinterpret_cast<const float4*>(d.w2 + (int64_t)(p0 + r) * H + 4 * k4);
+      }
     }
     for (int b = tid; b < B; b += LT) { gen[b] = 1; cnt[b] = 0; }
   }
@@ -765,21 +780,26 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
 
     if (FB) {
       // phase 2: x_t = tanh(wp h_t + bp), logit = ws h_t + bs, stop draw, early-exit flag
+      if (s > 0 && blockIdx.x == 0 && tid == 0) reinterpret_cast<volatile unsigned*>(d.barrier)[4 + ((s + 1) & 1)] = 0u;
       if (np > 0) {
         constexpr int NB = 8;                                      // batches in flight per warp
-        for (int bi0 = w; bi0 < B; bi0 += NB * (LT / 32)) {
+        const int nb2 = b2hi - b2lo, rotb = (int)(blockIdx.x / nbg2) % nb2;
+        for (int bi0 = w; bi0 < nb2; bi0 += NB * (LT / 32)) {
           const float* hrow[NB];
+          const __nv_bfloat16* hrow16[NB];
           int bb[NB];
 #pragma unroll
           for (int i = 0; i < NB; ++i) {
             const int bi = bi0 + i * (LT / 32);
-            bb[i] = bi < B ? (bi + (int)blockIdx.x) % B : -1;      // per-CTA rotation of the batch order
+            bb[i] = bi < nb2 ? b2lo + (bi + rotb) % nb2 : -1;     // per-CTA rotation of the batch order
             hrow[i] = bb[i] >= 0 ? d.hbuf + bb[i] * hstr + (int64_t)(t + 1) * H : nullptr;
+            hrow16[i] = (BF && bb[i] >= 0) ? reinterpret_cast<const __nv_bfloat16*>(d.hbuf16) + bb[i] * hstr + (int64_t)(t + 1) * H : nullptr;
           }
           for (int pp = 0; pp < np; pp += 4) {
             float o[NB][4];
             const int nr = min(4, np - pp);
-            warp_rows_dot_nb<NB>(o, W2s + pp * ld2, ld2, nr, hrow, H / 4);
+            if (BF) warp_rows_dot16_nb<NB>(o, reinterpret_cast<const __nv_bfloat16*>(W2s) + pp * (H + 8), H + 8, nr, hrow16, H / 8);
+            else warp_rows_dot_nb<NB>(o, W2s + pp * ld2, ld2, nr, hrow, H / 4);
             if (lane == 0) {
 #pragma unroll
               for (int i = 0; i < NB; ++i) {
@@ -805,18 +825,17 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
           }
         }
       }
-      if (owns_logit) {
+      if (owns_logit) {                 // one owner per batch group: count its samples that are still generating
         __syncthreads();
         int g = 0;
-        for (int b = tid; b < B; b += LT) g |= gen[b];
-        const int any = __syncthreads_or(g);
-        if (!any && tid == 0) *reinterpret_cast<volatile int*>(d.t_end) = t + 1;
+        for (int b = b2lo + tid; b < b2hi; b += LT) g += gen[b] ? 1 : 0;
+        g = (int)block_sum((float)g, reinterpret_cast<float*>(cnt + B));
+        if (tid == 0 && g > 0) atomicAdd(d.barrier + 4 + (s & 1), (unsigned)g);
       }
       pc.lap(3);
       grid_barrier(bar, (++nbar) * ncta_dir * bsplit);
       pc.lap(2);
-      const int te = *reinterpret_cast<volatile int*>(d.t_end);
-      if (te != 0) { steps_run = te; break; }
+      if (d.u && *reinterpret_cast<volatile unsigned*>(d.barrier + 4 + (s & 1)) == 0u) { steps_run = t + 1; break; }
     }
   }
   if (d.dbg && tid == 0) {
@@ -825,17 +844,18 @@ __global__ void __launch_bounds__(LT, 1) lstm_fwd_kernel(const ag_lstm_desc d, c
     q[4] = clock64() - tstart;
   }
   if (BF == 2) tc_teardown<ROWS>(tcs);
-  if (FB && owns_logit) {
+  if (FB) {
     __syncthreads();
-    for (int b = tid; b < B; b += LT) if (d.glen) d.glen[b] = cnt[b];
-    if (tid == 0 && steps_run == T) *reinterpret_cast<volatile int*>(d.t_end) = T;
+    if (owns_logit)
+      for (int b = b2lo + tid; b < b2hi; b += LT) if (d.glen) d.glen[b] = cnt[b];
+    if (blockIdx.x == 0 && tid == 0) *reinterpret_cast<volatile int*>(d.t_end) = steps_run;
   }
 }
 
 // ====================================================================================  backward
 template <int HS, bool FB, bool RES, int BF>
 __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, const int ncta_dir, const int PR, const int NST, const int bsplit,
-                                                         const int kcb) {
+                                                         const int kcb, const int nbg2) {
   constexpr int DHLD = BF == 2 ? HS + 4 : HS;       // dh exchange tile row stride
   constexpr int RL = HS;            // 4, 8 or 16 rows -> k split over the rest of the warp
   constexpr int KS = 32 / RL;
@@ -893,11 +913,15 @@ __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, c
   const float* wrow[1];
   wrow[0] = RES ? (Ws + (lane % RL) * ldw) : (w1d + (int64_t)(lane % RL) * K);
   for (int i = tid; i < Bper * HS; i += LT) dcs[i] = 0.f;
-  int p0 = 0, np = 0;
-  if (FB) {
-    p0 = blockIdx.x * PR;
+  int p0 = 0, np = 0, b2lo = 0, b2hi = 0;
+  if (FB) {                                              // phase A tiled 2-D: (row group of wx^T rows, batch group)
+    const int rg = blockIdx.x / nbg2, bg = blockIdx.x - rg * nbg2;
+    const int B2per = (B + nbg2 - 1) / nbg2;
+    b2lo = min(B, bg * B2per);
+    b2hi = min(B, b2lo + B2per);
+    p0 = rg * PR;
     np = min(PR, F - p0);
-    if (np < 0) np = 0;
+    if (np < 0 || b2hi <= b2lo) np = 0;
     if (BF) {                                            // bf16 rows of wx^T, stride 4H + 8
       __nv_bfloat16* Wxs16 = reinterpret_cast<__nv_bfloat16*>(Wxs);
       for (int idx = tid; idx < np * 4 * H; idx += LT) {
@@ -931,14 +955,15 @@ __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, c
       // phase A: dpx[b,t,p] = (dx_ext + wx^T dgates_{t+1})[p] * (1 - x_t[p]^2); column F = ds_ext
       if (np > 0) {
         constexpr int NB = 8;
-        for (int bi0 = w; bi0 < B; bi0 += NB * (LT / 32)) {
+        const int nb2 = b2hi - b2lo, rotb = (int)(blockIdx.x / nbg2) % nb2;
+        for (int bi0 = w; bi0 < nb2; bi0 += NB * (LT / 32)) {
           const float* dgrow[NB];
           const __nv_bfloat16* dgrow16[NB];
           int bb[NB];
 #pragma unroll
           for (int i = 0; i < NB; ++i) {
             const int bi = bi0 + i * (LT / 32);
-            bb[i] = bi < B ? (bi + (int)blockIdx.x) % B : -1;
+            bb[i] = bi < nb2 ? b2lo + (bi + rotb) % nb2 : -1;
             dgrow[i] = (bb[i] >= 0 && has_next) ? d.dgates + bb[i] * gstr + (int64_t)tn * 4 * H : nullptr;
             dgrow16[i] = (BF && bb[i] >= 0 && has_next)
                              ? reinterpret_cast<const __nv_bfloat16*>(d.dgates16) + bb[i] * gstr + (int64_t)tn * 4 * H : nullptr;
@@ -1088,7 +1113,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_bwd_kernel(const ag_lstm_desc d, c
 }
 
 // ---------------------------------------------------------------------------------- host side
-struct Plan { int HS, ncta_dir, PR, nst, bsplit, kcb, bf; bool res; size_t smem; };
+struct Plan { int HS, ncta_dir, PR, nst, bsplit, kcb, bf, nbg2; bool res; size_t smem; };
 
 static int pick_hs(int H, int ndir) {
   const int hs_opts[3] = {4, 8, 16};
@@ -1101,10 +1126,11 @@ static int pick_hs(int H, int ndir) {
 
 static size_t fwd_smem(const ag_lstm_desc* d, int HS, int PR, bool res, bool bf = false, int NST = NST_MIN) {
   const int F = d->F, K1 = d->H + F;
-  size_t fl = (bf ? 0 : (size_t)BTILE * 4 * HS) + (size_t)(d->B + 8) * HS + (F > 0 ? (size_t)PR * pad_ld(d->H) : 0);
+  size_t fl = (bf ? 0 : (size_t)BTILE * 4 * HS) + (size_t)(d->B + 8) * HS +
+              (F > 0 ? (bf ? ((size_t)PR * (d->H + 8) + 1) / 2 : (size_t)PR * pad_ld(d->H)) : 0);
   size_t head = bf ? ((size_t)4 * HS * pad_ld16(K1) + (size_t)NST * SLOT16) * 2
                    : ((res ? (size_t)4 * HS * pad_ld(K1) : 0) + 2 * BTILE * SLD) * 4;
-  return head + fl * 4 + (size_t)2 * d->B * 4 + 16;
+  return head + fl * 4 + (size_t)2 * d->B * 4 + 64 * 4 + 16;
 }
 static size_t bwd_smem(const ag_lstm_desc* d, int HS, int PR, bool res, bool bf = false, int NST = NST_MIN) {
   const int F = d->F, FP = F > 0 ? ((F + 1 + 7) / 8) * 8 : 0, K = 4 * d->H + FP;
@@ -1130,11 +1156,18 @@ static int check_lstm(const ag_lstm_desc* d, const char* who, bool bwd) {
   return AG_OK;
 }
 
+// batch groups of the 2-D phase-2 / phase-A tiling.  Measured (profiles/r1_lstm_phase_cycles.txt): these phases are
+// bound by the per-warp dot-product / reduction latency, not by the bytes of h they read -- more rows per CTA (what a
+// batch split costs) made phase 2 slower (13.4 k -> 22.6 k cycles per step), so the 1-D row split stays the default.
+static int pick_nbg2(int B, int ncta) {
+  (void)B; (void)ncta;
+  return 1;
+}
 static int bper_of(int B, int bsplit) { return (((B + bsplit - 1) / bsplit) + 7) & ~7; }
 static size_t fwd_smem_tc(const ag_lstm_desc* d, int HS, int PR, int NST, int kcb, int bsplit) {
   const int F = d->F, K1 = d->H + F, nkb = (K1 + 63) / 64, rows = 4 * HS;
   return 1024 + (size_t)nkb * rows * 128 + (size_t)NST * kcb * 8192 + 64 + (size_t)BTILE * (rows + 4) * 4 +
-         (size_t)bper_of(d->B, bsplit) * HS * 4 + (F > 0 ? (size_t)PR * pad_ld(d->H) * 4 : 0) + (size_t)2 * d->B * 4 + 16;
+         (size_t)bper_of(d->B, bsplit) * HS * 4 + (F > 0 ? (size_t)PR * (d->H + 8) * 2 + 4 : 0) + (size_t)2 * d->B * 4 + 64 * 4 + 16;
 }
 static size_t bwd_smem_tc(const ag_lstm_desc* d, int HS, int PR, int NST, int kcb, int bsplit) {
   const int F = d->F, FP = F > 0 ? ((F + 1 + 7) / 8) * 8 : 0, K = 4 * d->H + FP, nkb = (K + 63) / 64;
@@ -1146,8 +1179,8 @@ template <typename KernT>
 static int launch_coop(KernT kern, const ag_lstm_desc* d, const Plan& p, cudaStream_t s) {
   AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   ag_lstm_desc dd = *d;
-  int ncta_dir = p.ncta_dir, PR = p.PR, nst = p.nst, bsplit = p.bsplit, kcb = p.kcb;
-  void* args[6] = {&dd, &ncta_dir, &PR, &nst, &bsplit, &kcb};
+  int ncta_dir = p.ncta_dir, PR = p.PR, nst = p.nst, bsplit = p.bsplit, kcb = p.kcb, nbg2 = p.nbg2;
+  void* args[7] = {&dd, &ncta_dir, &PR, &nst, &bsplit, &kcb, &nbg2};
   AG_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)(p.ncta_dir * d->ndir * p.bsplit)), dim3(LT), args, p.smem, s));
   return AG_OK;
 }
@@ -1181,7 +1214,7 @@ int ag_lstm_fwd(const ag_lstm_desc* d, void* stream) {
   int rc = check_lstm(d, "ag_lstm_fwd", false);
   if (rc) return rc;
   Plan p;
-  p.res = true; p.bf = 0; p.nst = NST_MIN; p.bsplit = 1; p.HS = 0; p.kcb = 1;
+  p.res = true; p.bf = 0; p.nst = NST_MIN; p.bsplit = 1; p.HS = 0; p.kcb = 1; p.nbg2 = 1;
   const int nsm = sm_count();
   auto pr_for = [&](int ncta) { return d->F > 0 ? (d->F + 1 + ncta - 1) / ncta : 0; };
   if (d->prec == 2 && d->H % 8 == 0 && d->F % 8 == 0) {
@@ -1192,13 +1225,14 @@ int ag_lstm_fwd(const ag_lstm_desc* d, void* stream) {
       if (d->H % hs || (int64_t)d->ndir * (d->H / hs) > nsm) continue;
       const int groups = d->ndir * (d->H / hs);
       int bs = std::max(1, std::min(nsm / groups, (d->B + 15) / 16));
-      const int pr = pr_for(groups * bs);
+      const int nbg2 = pick_nbg2(d->B, groups * bs);
+      const int pr = pr_for((groups * bs) / nbg2);
       const int rb = std::min(64, (bper_of(d->B, bs) + 15) & ~15);
       for (int kcb = 64 / rb; kcb >= 1 && !p.bf; kcb >>= 1) {
         const size_t sm = fwd_smem_tc(d, hs, pr, 3, kcb, bs);
         if (sm > (size_t)smem_optin()) continue;
         AG_CHECK_ARG(d->hbuf16 && (d->F == 0 || d->xbuf16), "ag_lstm_fwd: bf16 mode needs hbuf16 / xbuf16");
-        p.bf = 2; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm; p.nst = 3; p.kcb = kcb;
+        p.bf = 2; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm; p.nst = 3; p.kcb = kcb; p.nbg2 = nbg2;
       }
     }
   }
@@ -1212,11 +1246,12 @@ int ag_lstm_fwd(const ag_lstm_desc* d, void* stream) {
       const int groups = d->ndir * (d->H / hs);
       int bs = nsm / groups;
       bs = std::max(1, std::min(bs, (d->B + 7) / 8));
-      const int pr = pr_for(groups * bs);
+      const int nbg2 = pick_nbg2(d->B, groups * bs);
+      const int pr = pr_for((groups * bs) / nbg2);
       const size_t sm16 = fwd_smem(d, hs, pr, true, true);
       if (sm16 > (size_t)smem_optin()) continue;
       AG_CHECK_ARG(d->hbuf16 && (d->F == 0 || d->xbuf16), "ag_lstm_fwd: bf16 mode needs hbuf16 / xbuf16");
-      p.bf = 1; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm16;
+      p.bf = 1; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm16; p.nbg2 = nbg2;
     }
   }
   if (!p.bf) {
@@ -1238,7 +1273,7 @@ int ag_lstm_bwd(const ag_lstm_desc* d, void* stream) {
   int rc = check_lstm(d, "ag_lstm_bwd", true);
   if (rc) return rc;
   Plan p;
-  p.res = true; p.bf = 0; p.nst = NST_MIN; p.bsplit = 1; p.HS = 0; p.kcb = 1;
+  p.res = true; p.bf = 0; p.nst = NST_MIN; p.bsplit = 1; p.HS = 0; p.kcb = 1; p.nbg2 = 1;
   const int nsm = sm_count();
   auto pr_for = [&](int ncta) { return d->F > 0 ? (d->F + ncta - 1) / ncta : 0; };
   if (d->prec == 2) {
@@ -1248,13 +1283,14 @@ int ag_lstm_bwd(const ag_lstm_desc* d, void* stream) {
       if (d->H % hs || (int64_t)d->ndir * (d->H / hs) > nsm) continue;
       const int groups = d->ndir * (d->H / hs);
       int bs = std::max(1, std::min(nsm / groups, (d->B + 15) / 16));
-      const int pr = pr_for(groups * bs);
+      const int nbg2 = pick_nbg2(d->B, groups * bs);
+      const int pr = pr_for((groups * bs) / nbg2);
       const int rb = std::min(64, (bper_of(d->B, bs) + 15) & ~15);
       for (int kcb = 64 / rb; kcb >= 1 && !p.bf; kcb >>= 1) {
         const size_t sm = bwd_smem_tc(d, hs, pr, 3, kcb, bs);
         if (sm > (size_t)smem_optin()) continue;
         AG_CHECK_ARG(d->dgates16 && (d->F == 0 || d->dpx16), "ag_lstm_bwd: bf16 mode needs dgates16 / dpx16");
-        p.bf = 2; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm; p.nst = 3; p.kcb = kcb;
+        p.bf = 2; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm; p.nst = 3; p.kcb = kcb; p.nbg2 = nbg2;
       }
     }
   }
@@ -1266,11 +1302,12 @@ int ag_lstm_bwd(const ag_lstm_desc* d, void* stream) {
       const int groups = d->ndir * (d->H / hs);
       int bs = nsm / groups;
       bs = std::max(1, std::min(bs, (d->B + 7) / 8));
-      const int pr = pr_for(groups * bs);
+      const int nbg2 = pick_nbg2(d->B, groups * bs);
+      const int pr = pr_for((groups * bs) / nbg2);
       const size_t sm16 = bwd_smem(d, hs, pr, true, true);
       if (sm16 > (size_t)smem_optin()) continue;
       AG_CHECK_ARG(d->dgates16 && (d->F == 0 || d->dpx16), "ag_lstm_bwd: bf16 mode needs dgates16 / dpx16");
-      p.bf = 1; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm16;
+      p.bf = 1; p.HS = hs; p.ncta_dir = d->H / hs; p.bsplit = bs; p.PR = pr; p.smem = sm16; p.nbg2 = nbg2;
     }
   }
   if (!p.bf) {

@@ -48,5 +48,6 @@ def run(H, B, Tn, ndir, Fr, prec=1):
         mx = dd[used].max(0)[0] / Tn
         print("%s H%d ndir%d F%d T%d B%d prec%d: %.3f ms (%.1f us/step), %d CTAs; cycles/step mean gemm %.0f cell %.0f barrier %.0f phase2/A %.0f total %.0f | gemm split: wait+sync %.0f stage-issue %.0f mma %.0f" % (
             name, H, ndir, Fr, Tn, B, prec, ms, ms * 1e3 / Tn, int(used.sum()), m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]))
-for prec in (2, 1):
+for prec in (1,):
     run(512, 64, 250, 2, 0, prec)
+    run(1024, 64, 80, 1, 200, prec)
