@@ -111,6 +111,13 @@ class _PlanOwner(NN.Module):
             self._plan.mode = mode
         return self
 
+    def __getstate__(self):
+        # T.save(module) / copy.deepcopy (audiogan.py:936-939 pickles whole modules): the plan holds device pointers
+        # and is rebuilt lazily, so it never travels with the module
+        st = dict(self.__dict__)
+        st.pop("_plan", None)
+        return st
+
     def _get_plan(self):
         params = list(self.parameters())
         dev = params[0].device
@@ -259,6 +266,28 @@ def calc_dists(hidden_states, hidden_state_lengths):             # audiogan.py:3
             stds_d.append((q.std(0), q.std(0)))
             fourth_d.append((fourth_moment(q), q.std(0)))
     return means_d + stds_d + fourth_d
+
+
+class Embedder(NN.Module):
+    """Character embedder producing the conditioning vector `c` (audiogan.py:302-334): Embedding(256, 50) ->
+    BiLSTM(50 -> 2 x output/2) over the packed character sequence -> last hidden states (B, output).  A "next" row of
+    SURVEY 8(f): 53.6 k parameters and <= ~20 character steps, far off the hot path -- it runs on stock torch modules
+    (cuDNN); same constructor, forward signature, state_dict keys (`embed.module.weight`, `rnn.*`) as the reference."""
+
+    def __init__(self, output_size=100, char_embed_size=50, num_layers=1, num_chars=256):
+        NN.Module.__init__(self)
+        self._output_size, self._char_embed_size, self._num_layers = output_size, char_embed_size, num_layers
+        self.embed = _DP(NN.Embedding(num_chars, char_embed_size))
+        self.rnn = NN.LSTM(char_embed_size, output_size // 2, num_layers, bidirectional=True)
+
+    def forward(self, chars, length):
+        from torch.nn.utils.rnn import pack_padded_sequence
+        batch_size = chars.size(0)
+        seq = self.embed.module(chars).permute(1, 0, 2)                          # :322-324
+        packed = pack_padded_sequence(seq, length.detach().cpu(), enforce_sorted=False)   # dynamic_rnn :214-229
+        _, (h, _) = self.rnn(packed)
+        h = h.permute(1, 0, 2)                                                   # :333
+        return h[:, -2:].reshape(batch_size, self._output_size)                   # :334
 
 
 def pin_stopper(g, value=30.0):

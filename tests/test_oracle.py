@@ -146,3 +146,29 @@ def test_core_step_runs_and_losses_finite():
     for o in (o1, o2, o3):
         assert all(v == v for v in [o["loss"]])
     assert o1["x_grad_norm"] >= 0
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference not present (GPU box)")
+def test_embedder_and_pickling_match_reference_api():
+    """The drop-in Embedder (stock torch) has the reference's state_dict keys and output; the
+    Generator / Discriminator modules pickle without their device plans (audiogan.py:936-939 saves whole modules)."""
+    import io
+    import audiogan_b200 as ag
+    ns = R.load()
+    T.manual_seed(0)
+    ref = ns["Embedder"](output_size=100)
+    mine = ag.Embedder(output_size=100)
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    mine.load_state_dict(ref.state_dict())
+    chars = T.randint(0, 256, (5, 9))
+    lens = T.tensor([9, 3, 7, 1, 5])
+    with R.py2_tensor_semantics():
+        want = ref(chars, lens)
+    got = mine(chars, lens)
+    assert T.allclose(got, want, atol=1e-6)
+    g = ag.Generator(embed_size=100, state_size=32)
+    buf = io.BytesIO()
+    T.save(g, buf)
+    buf.seek(0)
+    g2 = T.load(buf, weights_only=False)
+    assert list(g2.state_dict().keys()) == list(g.state_dict().keys()) and g2._plan is None
