@@ -13,11 +13,6 @@ namespace ag {
 
 constexpr int BM = 128, BK = 16, NT_THREADS = 256;
 
-struct RowCol {
-  int64_t off;
-  int32_t batch, t;
-};
-
 __device__ __forceinline__ int64_t c_col_off(const ag_gemm_desc& d, int64_t n, int64_t* n1_out) {
   const int64_t n1 = n / d.c_nin;
   if (n1_out) *n1_out = n1;

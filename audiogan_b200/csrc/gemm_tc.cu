@@ -13,18 +13,11 @@
 #include "tc_common.cuh"
 #include <cuda.h>
 #include <mutex>
-#include <unordered_map>
 
 namespace ag {
 namespace tc {
 
 constexpr int BM = 128, BK = 64, NTHREADS = 160, NPROD = 128;
-
-struct SmemLayout {
-  // [STAGES][A 16 KB][B BN*128 B] then barriers
-  static __host__ __device__ constexpr int a_bytes() { return BM * BK * 2; }
-  static __host__ __device__ constexpr int b_bytes(int BN) { return BN * BK * 2; }
-};
 
 // Column c of a row: element offset (c / inner) * outer_stride + c % inner (32-bit division: columns < 2^31).
 __device__ __forceinline__ int64_t col_off(int64_t c, int64_t inner, int64_t outer_stride) {

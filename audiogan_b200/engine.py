@@ -227,26 +227,29 @@ class _DiscCNNFn(torch.autograd.Function):
             if g is None and dX is None:
                 continue
             a_out = acts[i + 1]
-            geo = ((Tout + 2 * DPAD) * cout, cout)
-            dy = _empty(B, Tout + 2 * DPAD, cout, device=dev)
+            ntap = plan.d_ntap[i]
+            PL = ntap - 1                                  # left pad of dy: the data-gradient window reaches ntap-1 rows back
+            geo = ((Tout + 2 * DPAD) * cout, cout)         # geometry of the forward activation buffers
+            gdy = ((PL + Tout + DPAD) * cout, cout)        # geometry of dy
+            dy = _empty(B, PL + Tout + DPAD, cout, device=dev)
             kw = {}
             if g is not None:                  # (B, C, T) tensor with arbitrary strides
                 kw.update(g1=g, g1_str=(g.stride(0), g.stride(2), g.stride(1)))
             if dX is not None:
                 kw.update(g2=(dX, DPAD * cout), g2_str=(geo[0], geo[1], 1))
-            K.ew_grad(B, Tout, cout, out=dy, pad=(DPAD, DPAD), act=(a_out, DPAD * cout), act_str=geo, length=lens[i], **kw)
+            K.ew_grad(B, Tout, cout, out=dy, pad=(PL, DPAD), act=(a_out, DPAD * cout), act_str=geo, length=lens[i], **kw)
             a_view = (Tout, (Tin + 2 * DPAD) * cin, s * cin)
             if wgrad:
-                K.gemm_tn(B * Tout, cout, k * cin, (dy, DPAD * cout), (Tout, geo[0], cout), acts[i], a_view,
+                K.gemm_tn(B * Tout, cout, k * cin, (dy, PL * cout), (Tout, gdy[0], cout), acts[i], a_view,
                           plan.GPoff("c%d.w" % i), k * cin + 1, ones_col=True)
             if i > 0 or need_dx:
-                Mp = (Tin + DPAD + 1) // 2
+                Mp = (Tin + DPAD + s - 1) // s
                 dXn = _empty(B, Tin + 2 * DPAD, cin, device=dev)
-                if 2 * Mp < Tin + 2 * DPAD:
-                    dXn[:, 2 * Mp:].zero_()
-                K.gemm_nt(B * Mp, 2 * cin, 4 * cout, dy, (Mp, geo[0], cout), plan.Poff("c%d.wg" % i), 4 * cout,
-                          dXn, (Mp, (Tin + 2 * DPAD) * cin, 2 * cin, cin, cin),
-                          mask_len=plan.const_len(B, Tin), mask=(2, 1, -DPAD))
+                if s * Mp < Tin + 2 * DPAD:
+                    dXn[:, s * Mp:].zero_()
+                K.gemm_nt(B * Mp, s * cin, ntap * cout, dy, (Mp, gdy[0], cout), plan.Poff("c%d.wg" % i), ntap * cout,
+                          dXn, (Mp, (Tin + 2 * DPAD) * cin, s * cin, cin, cin),
+                          mask_len=plan.const_len(B, Tin), mask=(s, 1, -DPAD))
                 dX = dXn
             else:
                 dX = None

@@ -11,7 +11,6 @@ import torch
 from . import _abi as A
 
 LRELU_SLOPE = 0.01      # NN.LeakyReLU() / F.leaky_relu defaults (audiogan.py:261, :277, :532)
-_ESIZE = {torch.float32: 4, torch.bfloat16: 2, torch.int32: 4}
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
 
@@ -196,16 +195,3 @@ def wn_fwd(table, row_start, nt, total_rows):
 
 def wn_bwd(table, row_start, nt, total_rows):
     A.call("ag_wn_bwd_multi", addr(table), addr(row_start), nt, total_rows, A.stream())
-
-
-def mt_table(entries, device=None, out=None):
-    """entries: list of (p, g, s1, s2) tensors -> uint8 tensor holding ag_mt_entry[]."""
-    arr = (A.MtEntry * len(entries))()
-    for i, (p, g, s1, s2) in enumerate(entries):
-        arr[i].p, arr[i].g, arr[i].s1, arr[i].s2 = addr(p), addr(g), addr(s1), addr(s2)
-        arr[i].n = p.numel()
-    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-    if out is not None:
-        out.copy_(raw, non_blocking=True)
-        return out
-    return raw.to(device)

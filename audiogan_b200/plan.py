@@ -364,16 +364,19 @@ def build_discriminator_plan(mod, device):
     pl = NetPlan(device)
     neg = lambda *shape: torch.full(shape, -1, dtype=torch.int64)
     cin = 1
+    pl.d_ntap = []
     for i, (k, s, cout) in enumerate(mod._cnn_struct):
-        assert k == 7 and s == 2, "discriminator conv layers are kernel 7 / stride 2 (audiogan.py:476)"
+        assert k == 7 and s in (1, 2), "discriminator conv layers: kernel 7, stride 1 or 2 (audiogan.py:476; cfg 5 adds stride-1 layers)"
+        ntap = (k + s - 1) // s                             # taps per output phase of the data gradient
+        pl.d_ntap.append(ntap)
         cm = mod.cnn[i].module
         w = pl.weight("c%d.w" % i, cm.weight_v, cm.weight_g)
         b = pl.weight("c%d.b" % i, cm.bias_v, cm.bias_g)
         pl.layout("c%d.w" % i, w.permute(0, 2, 1).reshape(cout, k * cin))
         pl.layout("c%d.b" % i, b)
-        # data gradient over 4 taps: [(r', ci), (u, co)] = W[co, ci, 2*(3-u) + r']
-        wp = torch.cat([w, neg(cout, cin, 1)], 2).view(cout, cin, 4, 2).flip(2)          # [co, ci, u, r']
-        pl.layout("c%d.wg" % i, wp.permute(3, 1, 2, 0).reshape(2 * cin, 4 * cout))
+        # data gradient over ntap taps per phase: [(r', ci), (u, co)] = W[co, ci, s*(ntap-1-u) + r']
+        wp = torch.cat([w, neg(cout, cin, ntap * s - k)], 2).view(cout, cin, ntap, s).flip(2)   # [co, ci, u, r']
+        pl.layout("c%d.wg" % i, wp.permute(3, 1, 2, 0).reshape(s * cin, ntap * cout))
         g = pl.grad_region("c%d.w" % i, (cout, k * cin + 1))
         pl.grad_of("c%d.w" % i, g[:, :k * cin].reshape(cout, k, cin).permute(0, 2, 1))
         pl.grad_of("c%d.b" % i, g[:, k * cin])

@@ -34,7 +34,6 @@ class _MT:
         self.sqnorm = torch.zeros(len(self.params), device=dev)
         self.flags = torch.zeros(2, dtype=torch.int32, device=dev)
         self.device = dev
-        self._dummy = torch.zeros(1, device=dev)
 
     def table(self, state1=None, state2=None):
         ents = []
@@ -44,7 +43,6 @@ class _MT:
                 p.grad = g = g.contiguous()
             ents.append((p.data, g, state1[i] if state1 else None, state2[i] if state2 else None))
         # parameters without a gradient are skipped by giving them n = 0
-        import ctypes as C
         arr = (A.MtEntry * len(ents))()
         for i, (p, g, s1, s2) in enumerate(ents):
             arr[i].p, arr[i].g, arr[i].s1, arr[i].s2 = K.addr(p), K.addr(g), K.addr(s1), K.addr(s2)

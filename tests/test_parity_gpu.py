@@ -389,3 +389,35 @@ def test_loss_trajectory_tracks_oracle():
         assert float(dev_rel.max()) <= 0.15, (mode, "whole curve", float(dev_rel.max()))
         assert float(got[-1, 0]) < float(got[0, 0])
     assert float(ref[-1, 0]) < float(ref[0, 0])            # the discriminator is actually learning on this batch
+
+
+def test_scaled_discriminator_with_stride1_layers():
+    """BASELINE configs[4] shape family ("2x conv channels and depth"): extra kernel-7 stride-1 layers between the
+    stride-2 ones (SURVEY 8(d) cfg 5).  Forward activations, logits and every gradient against the oracle."""
+    import audiogan_b200 as ag
+    struct = [[7, 2, 8], [7, 1, 8], [7, 2, 16], [7, 1, 16], [7, 2, 32], [7, 1, 32]]
+    cs = dict(B=3, L=1000, full=False, gk={"state_size": 32}, dk={"state_size": 32, "cnn_struct": struct})
+    Pg, Pd, g, d = build(cs)
+    inp = step_inputs(cs["B"], cs["L"], seed=21, full_length=False)
+    di = to_dev(inp)
+    R = Report()
+    Pd_r = {k: v.clone().requires_grad_(True) for k, v in Pd.items()}
+    x_r = (inp["real"] + inp["noise_real"]).requires_grad_(True)
+    cls_r, hs_r, hl_r, nf_r = O.discriminator_forward(Pd_r, x_r, inp["real_len"], inp["c_real"], cnn_struct=struct)
+    loss_r = bce_mean(cls_r, nf_r, 0.9)
+    dk = list(Pd_r)
+    grads_r = T.autograd.grad(loss_r, [Pd_r[k] for k in dk] + [x_r])
+    x = (di["real"] + di["noise_real"]).requires_grad_(True)
+    cls, hs, hl, nf = d(x, di["real_len"], di["c_real"])
+    assert T.equal(nf.cpu(), nf_r) and len(hs) == len(struct)
+    for i, (a, b) in enumerate(zip(hs, hs_r)):
+        R.check("D.cnn[%d]" % i, a, b)
+    R.check("D.logits", cls, cls_r)
+    loss, _, _ = ag.masked_bce_mean(cls, nf, 0.9, 1.0)
+    loss.backward()
+    sd = dict(d.named_parameters())
+    for k, gr in zip(dk, grads_r[:-1]):
+        if not noise_only(k):
+            R.check("dD/" + k, sd[k].grad, gr, tol=5e-5)
+    R.check("dx", x.grad, grads_r[-1], tol=5e-5)
+    R.done("scaled_d")
