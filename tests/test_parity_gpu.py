@@ -421,3 +421,32 @@ def test_scaled_discriminator_with_stride1_layers():
             R.check("dD/" + k, sd[k].grad, gr, tol=5e-5)
     R.check("dx", x.grad, grads_r[-1], tol=5e-5)
     R.done("scaled_d")
+
+
+def test_double_hidden_generator_streams_weights():
+    """BASELINE configs[3] shape family (2x recurrent hidden size): with H = 2048 a 64-row slice of [whh | wx] no longer
+    fits in shared memory, so the recurrent kernels take the non-resident path (weights streamed from L2 each step).
+    Generator outputs and gradients against the oracle."""
+    cs = dict(B=2, L=600, full=True, gk={"state_size": 2048}, dk={"state_size": 64})
+    Pg, Pd, g, d = build(cs)
+    inp = step_inputs(cs["B"], cs["L"], seed=31, full_length=True)
+    di = to_dev(inp)
+    Pg_r = {k: v.clone().requires_grad_(True) for k, v in Pg.items()}
+    z_r = inp["g_z"].clone().requires_grad_(True)
+    x_r, s_r, _, _ = O.generator_forward(Pg_r, inp["g_c_g"], z=z_r)
+    T.manual_seed(2)
+    up = T.randn_like(x_r)
+    gk = list(Pg_r)
+    grads_r = T.autograd.grad((x_r * up).sum(), [Pg_r[k] for k in gk] + [z_r], allow_unused=True)
+    R = Report()
+    z = di["g_z"].clone().requires_grad_(True)
+    x, s, _, _ = g(z=z, c=di["g_c_g"], u_stop=None)
+    R.check("G.x", x, x_r)
+    R.check("G.s", s, s_r)
+    (x * up.cuda()).sum().backward()
+    sg = dict(g.named_parameters())
+    for k, gr in zip(gk, grads_r[:-1]):
+        if gr is not None and not noise_only(k):
+            R.check("dG/" + k, sg[k].grad, gr, tol=5e-5)
+    R.check("dz", z.grad, grads_r[-1], tol=5e-5)
+    R.done("h2048")
