@@ -82,6 +82,43 @@ __device__ __forceinline__ void load_chunks(uint4 (&out)[NCH], const void* base,
   }
 }
 
+// Two-phase variant for the vector modes: issue() puts the global loads of a stage in flight, get() converts them.
+// The NT producers issue stage k+1 before they store stage k, so a stage's load latency overlaps the slot wait, the
+// swizzled stores and the proxy fence of the previous one.
+template <int MODE, int NCH>
+struct ChunkLoader {
+  float4 lo[MODE == 0 ? NCH : 1], hi[MODE == 0 ? NCH : 1];
+  uint4 raw[MODE == 1 ? NCH : 1];
+  bool ok[NCH];
+  __device__ __forceinline__ void issue(const void* base, const int64_t (&roff)[NCH], const int64_t (&c)[NCH], int64_t ncols,
+                                        int64_t inner, int64_t outer_stride) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      ok[i] = roff[i] >= 0 && c[i] + 8 <= ncols;
+      const int64_t off = ok[i] ? roff[i] + col_off(c[i], inner, outer_stride) : 0;
+      if (MODE == 0) {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+        lo[i] = __ldg(p);
+        hi[i] = __ldg(p + 1);
+      } else {
+        raw[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off));
+      }
+    }
+  }
+  __device__ __forceinline__ void get(uint4 (&out)[NCH]) const {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      if (MODE == 0) {
+        out[i].x = pack_bf16(lo[i].x, lo[i].y); out[i].y = pack_bf16(lo[i].z, lo[i].w);
+        out[i].z = pack_bf16(hi[i].x, hi[i].y); out[i].w = pack_bf16(hi[i].z, hi[i].w);
+      } else {
+        out[i] = raw[i];
+      }
+      if (!ok[i]) out[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+};
+
 // pipeline depth per tile width: BN = 256 -> 2 stages (96 KB) so that TWO CTAs are resident per SM and one CTA's
 // epilogue overlaps the other's main loop (TMEM: 2 x 256 columns); narrower tiles get 3-4 stages, still 2 CTAs/SM.
 __host__ __device__ constexpr int nt_stages(int BN) { return BN >= 256 ? 2 : (BN >= 128 ? 3 : 4); }
@@ -139,25 +176,40 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_tc_kernel(const ag_gemm_d
 
   if (warp < 4) {
     // ------------------------------------------------------------------ producers
+    int64_t ro[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ro[i] = rowoff[(i * NPROD + tid) >> 3];
+    auto cols_of = [&](int kb, int64_t (&cc)[8]) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cc[i] = (int64_t)kb * BK + ((i * NPROD + tid) & 7) * 8;
+    };
+    ChunkLoader<MODE == 2 ? 0 : MODE, 8> ld;
+    if (MODE != 2) {
+      int64_t cc[8];
+      cols_of(0, cc);
+      ld.issue(d.A, ro, cc, d.K, d.a_kin, d.a_k1s);
+    }
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STG;
       const uint32_t ph = (kb / STG) & 1;
+      uint4 ch[8];
+      if (MODE != 2) {
+        ld.get(ch);                                   // stage kb has landed (or we wait for it here)
+        if (kb + 1 < nkb) {                           // put stage kb+1 in flight before touching shared memory
+          int64_t cc[8];
+          cols_of(kb + 1, cc);
+          ld.issue(d.A, ro, cc, d.K, d.a_kin, d.a_k1s);
+        }
+      } else {
+        int64_t cc[8];
+        cols_of(kb, cc);
+        load_chunks<2, 8>(ch, d.A, d.a_dtype, ro, cc, d.K, d.a_kin, d.a_k1s, -1);
+      }
       mbar_wait(&empty[s], ph ^ 1);
       uint8_t* sa = smem + s * STAGE_BYTES;
       if (tid == 0) {
         mbar_arrive_expect_tx(&full[s], B_BYTES);
         tma_load_2d(sa + A_BYTES, &mapB, &full[s], kb * BK, n0);
-      }
-      uint4 ch[8];
-      {
-        int64_t ro[8], cc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int cid = i * NPROD + tid;
-          ro[i] = rowoff[cid >> 3];
-          cc[i] = (int64_t)kb * BK + (cid & 7) * 8;
-        }
-        load_chunks<MODE, 8>(ch, d.A, d.a_dtype, ro, cc, d.K, d.a_kin, d.a_k1s, -1);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -219,30 +271,37 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_tc_kernel(const ag_gemm_d
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (nv && d.bias) bv = *reinterpret_cast<const float4*>(d.bias + (d.bias_mod > 0 ? n % d.bias_mod : n));
         const int64_t mpos = n1 * d.mask_n1mul + d.mask_toff;
-#pragma unroll 2
+        // all global reads of the chunk's epilogue operands first (8 rows x {row-bias, skip, dact}): one exposed latency
+        float4 rbv[8], skv[8], dav[8];
+        int64_t civ[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = warp * 32 + it * 4 + rs;
+          const int64_t crow = rowoff[row];
+          civ[it] = (crow < 0 || !nv) ? -1 : crow + coff;
+          rbv[it] = skv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          dav[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (civ[it] >= 0) {
+            if (d.rowbias) rbv[it] = *reinterpret_cast<const float4*>(d.rowbias + (int64_t)s_b[row] * d.rowbias_ld + n);
+            if (d.skip) skv[it] = ld4_any(d.skip, civ[it], d.aux_dtype);
+            if (d.dact) dav[it] = ld4_any(d.dact, civ[it], d.aux_dtype);
+          }
+        }
+#pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int r = it * 4 + rs, row = warp * 32 + r;
-          const int64_t crow = rowoff[row];
-          if (crow < 0 || !nv) continue;
-          const int64_t ci = crow + coff;
+          if (civ[it] < 0) continue;
+          const int64_t ci = civ[it];
           float4 x = *reinterpret_cast<const float4*>(tr + r * TRLD + 4 * q);
-          x.x = x.x * alpha + bv.x; x.y = x.y * alpha + bv.y; x.z = x.z * alpha + bv.z; x.w = x.w * alpha + bv.w;
-          if (d.rowbias) {
-            const float4 rb = *reinterpret_cast<const float4*>(d.rowbias + (int64_t)s_b[row] * d.rowbias_ld + n);
-            x.x += rb.x; x.y += rb.y; x.z += rb.z; x.w += rb.w;
-          }
-          if (d.skip) {
-            const float4 sk = ld4_any(d.skip, ci, d.aux_dtype);
-            x.x += sk.x; x.y += sk.y; x.z += sk.z; x.w += sk.w;
-          }
+          x.x = x.x * alpha + bv.x + rbv[it].x + skv[it].x; x.y = x.y * alpha + bv.y + rbv[it].y + skv[it].y;
+          x.z = x.z * alpha + bv.z + rbv[it].z + skv[it].z; x.w = x.w * alpha + bv.w + rbv[it].w + skv[it].w;
           if (d.act == 1) {
             x.x = x.x > 0.f ? x.x : x.x * d.slope; x.y = x.y > 0.f ? x.y : x.y * d.slope;
             x.z = x.z > 0.f ? x.z : x.z * d.slope; x.w = x.w > 0.f ? x.w : x.w * d.slope;
           }
           if (d.dact) {
-            const float4 da = ld4_any(d.dact, ci, d.aux_dtype);
-            x.x *= da.x > 0.f ? 1.f : d.slope; x.y *= da.y > 0.f ? 1.f : d.slope;
-            x.z *= da.z > 0.f ? 1.f : d.slope; x.w *= da.w > 0.f ? 1.f : d.slope;
+            x.x *= dav[it].x > 0.f ? 1.f : d.slope; x.y *= dav[it].y > 0.f ? 1.f : d.slope;
+            x.z *= dav[it].z > 0.f ? 1.f : d.slope; x.w *= dav[it].w > 0.f ? 1.f : d.slope;
           }
           if (d.mask_len) {
             const int64_t pos = (int64_t)s_t[row] * d.mask_tmul + mpos;
