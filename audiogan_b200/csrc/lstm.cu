@@ -1207,12 +1207,22 @@ static int run_bwd(const ag_lstm_desc* d, const Plan& p, cudaStream_t s) { AG_LS
 
 }  // namespace ag
 
+namespace ag { namespace lc {
+int cluster_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);   // lstm_cluster.cu
+int cluster_bwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);
+} }
+
 using namespace ag;
 extern "C" {
 
 int ag_lstm_fwd(const ag_lstm_desc* d, void* stream) {
   int rc = check_lstm(d, "ag_lstm_fwd", false);
   if (rc) return rc;
+  {
+    int launched = 0;
+    rc = lc::cluster_fwd(d, (cudaStream_t)stream, &launched);
+    if (rc || launched) return rc;
+  }
   Plan p;
   p.res = true; p.bf = 0; p.nst = NST_MIN; p.bsplit = 1; p.HS = 0; p.kcb = 1; p.nbg2 = 1;
   const int nsm = sm_count();
@@ -1272,6 +1282,11 @@ int ag_lstm_fwd(const ag_lstm_desc* d, void* stream) {
 int ag_lstm_bwd(const ag_lstm_desc* d, void* stream) {
   int rc = check_lstm(d, "ag_lstm_bwd", true);
   if (rc) return rc;
+  {
+    int launched = 0;
+    rc = lc::cluster_bwd(d, (cudaStream_t)stream, &launched);
+    if (rc || launched) return rc;
+  }
   Plan p;
   p.res = true; p.bf = 0; p.nst = NST_MIN; p.bsplit = 1; p.HS = 0; p.kcb = 1; p.nbg2 = 1;
   const int nsm = sm_count();

@@ -126,13 +126,20 @@ typedef struct ag_lstm_desc {
   /* bf16 mode (prec = 1): the recurrent products run on tensor cores (bf16 operands, fp32 accumulate, fp32 state).
    * The kernels keep bf16 shadow copies of the per-step operands, same shapes as their fp32 twins:
    * hbuf16 / xbuf16 (forward writes, rows 0 / T+1 zero on entry), dgates16 / dpx16 (backward writes). */
-  int32_t prec, reserved2;
+  int32_t prec, reserved2;   /* reserved2 bit 0: do not use the cluster-resident kernels (see below) */
   void* hbuf16; void* xbuf16; void* dgates16; void* dpx16;
   long long* dbg;        /* optional [gridDim][8] cycle counters per CTA: gemm, cell, barrier, phase2/A, total (profiling aid) */
 } ag_lstm_desc;
 
 int ag_lstm_fwd(const ag_lstm_desc* d, void* stream);
 int ag_lstm_bwd(const ag_lstm_desc* d, void* stream);
+/* Non-feedback sequences in bf16 mode (prec >= 1, F == 0, H in {128, 256, 512}: the discriminator's BiLSTM) run on
+ * cluster-resident kernels: one thread-block cluster of H/32 CTAs keeps a full copy of one direction's recurrent
+ * weights in distributed shared memory and carries a slice of <= 32 samples through all T steps with tcgen05 MMAs,
+ * exchanging h_t (forward) / partial dh sums (backward) through DSMEM -- no grid barrier.  Same buffers and layouts
+ * as above.  Returns how many such clusters can be co-resident on this device (< ndir: the calls above fall back to
+ * the grid-barrier kernels), or -1 on error. */
+int ag_lstm_cluster_max_active(int H, int bwd);
 
 /* ------------------------------------------------------------------------------------------
  * Weight-norm (audiogan.py:77-80 -> torch.nn.utils.weight_norm dim 0), multi-tensor.
