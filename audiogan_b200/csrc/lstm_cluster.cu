@@ -352,179 +352,227 @@ __global__ void __launch_bounds__(GT * MAXG, 1) lstm_cl_fwd_kernel(const ag_lstm
 }
 
 // ====================================================================================== backward
-// Shared memory: At [H/128 M-tiles][2][128 rows][128 B] (rows = hidden units, K = this CTA's 128 gate rows) |
-// Bop [2][NB rows][128 B] (own dgates of the step just processed, bf16) | red[2] [CS][NB/4][32][4] fp32 | mbarrier | tmem slot.
-template <int NB>
-__global__ void __launch_bounds__(LT, 1) lstm_cl_bwd_kernel(const ag_lstm_desc d, const int nchunks, const int cpd) {
-  constexpr int IPT = NB * UPC / LT;         // (unit, sample) items per thread in the cell backward (2 for NB = 16)
-  static_assert(NB == 16 && IPT == 2, "backward slice is 16 samples");
+// Same decomposition (CTA = 32 hidden units of one direction, G warp groups x 16 samples).  Per step and group:
+//   partial dh[H units, 16] = Whh_slice^T [H, 128] . dgates_{prev step, slice}[16, 128]^T  -- A = the transposed weight slice,
+//   H/128 M-tiles x 64 TMEM columns, resident; B = the CTA's OWN gate gradients of the step it just finished (no
+//   all-gather).  The M-tiles are independent accumulator chains, issued by one thread per warp.
+//   Reduce-scatter: warp q holds units 128 m + 32 q .. of every M-tile m = exactly owner CTA 4m + q's units; the partial
+//   sums go (bf16, sample pairs packed) into a staging block per owner and leave as ONE 1 KB bulk DSMEM copy per owner,
+//   completing on the owner's mbarrier.  Each owner adds its CS incoming blocks, runs the cell backward (dc in
+//   registers) and refills its B operand.
+//   smem per group: Bop [16 k-chunks][16 rows][16 B] | stage[2] [CS owners][8 sample pairs][32 units] bf16x2 |
+//                   red[2] [CS sources][8][32] bf16x2 | full[2], mma_done.
+constexpr int MAXG_BWD = 3;
+__host__ __device__ inline uint32_t bwd_group_bytes(int H) {
+  const uint32_t CS = (uint32_t)H / UPC;
+  return 16u * NBG * 16 + 4u * CS * (NBG / 2) * UPC * 4 + 64;
+}
+
+__global__ void __launch_bounds__(GT * MAXG_BWD, 1) lstm_cl_bwd_kernel(const ag_lstm_desc d, const int nss, const int cpd, const int G) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, qd = w & 3, hf = w >> 2;
+  const int tid = threadIdx.x, g = tid >> 7, gt = tid & (GT - 1), lane = tid & 31, q = (tid >> 5) & 3;
   const int H = d.H, ndir = d.ndir, B = d.B, T = d.T, Tcap = d.Tcap;
   const int CS = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
-  const int cid = blockIdx.x / CS, dir = cid % ndir, j0 = rank * UPC;
+  const int cid = blockIdx.x / CS, dir = cid % ndir, cl = cid / ndir, j0 = rank * UPC;
   const int MT = H / 128;
 
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* At = sm;
-  uint8_t* Bop = At + (size_t)MT * 2 * 128 * 128;
-  uint8_t* red = Bop + 2 * NB * 128;
-  const uint32_t red_bytes = (uint32_t)CS * NB * UPC * 4;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 2 * (size_t)red_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm);
+  uint8_t* gbase = sm + 64 + (size_t)g * bwd_group_bytes(H);
+  const uint32_t blk_bytes = (NBG / 2) * UPC * 4;            // one (owner | source) block: 8 sample pairs x 32 units x bf16x2 = 1 KB
+  const uint32_t red_bytes = (uint32_t)CS * blk_bytes;
+  uint8_t* Bop = gbase;
+  uint8_t* stage = Bop + 16 * NBG * 16;
+  uint8_t* red = stage + 2 * (size_t)red_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * (size_t)red_bytes);
+  uint64_t* mma_done = full + 2;
 
-  // A[unit j][k = lr] = whh[gate row q*H + j0 + jj][j] = w1t[dir][j][q*H + j0 + jj],  lr = q*32 + jj
-  {
-    const int K = 4 * H;
-    const float* wt = d.w1t + (int64_t)dir * H * K;
-    for (int cell = tid; cell < H * 16; cell += LT) {
-      const int j = cell >> 4, c = cell & 15;
-      const float* src = wt + (int64_t)j * K + (c >> 2) * H + j0 + (c & 3) * 8;
-      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-      const int m = j >> 7, r = j & 127, ka = c >> 3, cc = c & 7;
-      *reinterpret_cast<uint4*>(At + (size_t)(m * 2 + ka) * (128 * 128) + r * 128 + ((cc ^ (r & 7)) << 4)) =
-          make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
-    }
-  }
-  if (tid == 0) {
-    mbar_init(mbar, 1);
+  if (gt == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(mma_done, (uint32_t)MT);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const uint32_t tmem = tmem_alloc<64>(tmem_slot);
-  uint32_t ph = 0;
+  const uint32_t tmem = tmem_alloc<512>(tmem_slot);
+  // A[unit j][k = lr] = whh[gate row (lr/32)*H + j0 + lr%32][j] = w1t[dir][j][...]; this thread's rows: 128 m + 32 q + lane
+  {
+    const float* wt = d.w1t + (int64_t)dir * H * 4 * H;
+    for (int idx = g; idx < MT * 8; idx += G) {
+      const int m = idx >> 3, kk = idx & 7, lr0 = kk * 16;
+      const float* src = wt + (int64_t)(m * 128 + q * 32 + lane) * 4 * H + (lr0 >> 5) * H + j0 + (lr0 & 31);
+      uint32_t v[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src) + e);
+        v[2 * e] = pack_bf16(a.x, a.y);
+        v[2 * e + 1] = pack_bf16(a.z, a.w);
+      }
+      tc_st8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * 64 + kk * 8), v);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_arrive();
+  cluster_wait();
+  tc_fence_after();
 
-  const uint32_t idesc = umma_idesc(128, NB, 0, 0);
-  const uint64_t da0 = umma_desc(smem_u32(At), 16, 1024), db0 = umma_desc(smem_u32(Bop), 16, 1024);
-  const int64_t gstr = (int64_t)Tcap * ndir * 4 * H;
-  const int64_t cstr = (int64_t)Tcap * ndir * H;
+  const uint32_t tmem_d = tmem + (uint32_t)(MT * 64 + MT * NBG * g);
+  const uint32_t idesc = umma_idesc(128, NBG, 0, 0);
+  const int64_t gstr = (int64_t)Tcap * ndir * 4 * H, cstr = (int64_t)Tcap * ndir * H;
   const int64_t dhbs = d.dh_ext_bs ? d.dh_ext_bs : cstr;
   __nv_bfloat16* dg16 = reinterpret_cast<__nv_bfloat16*>(d.dgates16);
-  const uint32_t red_local = smem_u32(red);
-  // cell-backward items of this thread: unit jj = lane, samples bl = 2*w, 2*w + 1
+  const uint32_t bop_local = smem_u32(Bop), stage_local = smem_u32(stage), red_local = smem_u32(red), full_local = smem_u32(full);
+  uint32_t nuse0 = 0, nuse1 = 0, nmma = 0;
   Clk ck;
   ck.init(d.dbg != nullptr);
   const long long tstart = clock64();
 
-  for (int chunk = cid / ndir; chunk < nchunks; chunk += cpd) {
-    const int b0 = chunk * NB;
-    float dcs[IPT];
-    int len_i[IPT];
-#pragma unroll
-    for (int ii = 0; ii < IPT; ++ii) {
-      dcs[ii] = 0.f;
-      const int b = b0 + 2 * w + ii;
-      len_i[ii] = b < B ? (d.len ? min(d.len[b], T) : T) : 0;
-    }
-    cluster_arrive();          // the previous slice's last reduce (any peer) is over before anyone pushes again
-    cluster_wait();
-
-    for (int s = 0; s < T; ++s) {
-      ck.start();
-      const int t = dir ? s : (T - 1 - s);               // reverse of the forward order
-      const uint32_t buf = (uint32_t)s & 1u;
-      // prefetch what the cell backward needs: saved gates, c_t, c_prev, external dh (independent of the recurrence)
-      float pg[IPT][7];
-      bool pv[IPT];
-#pragma unroll
-      for (int ii = 0; ii < IPT; ++ii) {
-        const int b = b0 + 2 * w + ii;
-        pv[ii] = t < len_i[ii];
-#pragma unroll
-        for (int e = 0; e < 7; ++e) pg[ii][e] = 0.f;
-        if (pv[ii]) {
-          const float* gp = d.gates + b * gstr + (int64_t)t * ndir * 4 * H + dir * 4 * H + j0 + lane;
-          pg[ii][0] = __ldg(gp); pg[ii][1] = __ldg(gp + H); pg[ii][2] = __ldg(gp + 2 * H); pg[ii][3] = __ldg(gp + 3 * H);
-          pg[ii][4] = __ldg(d.cbuf + b * cstr + (int64_t)t * ndir * H + dir * H + j0 + lane);
-          const int tp = dir ? (t + 1) : (t - 1);
-          const bool has_prev = dir ? (tp < len_i[ii]) : (tp >= 0);
-          pg[ii][5] = has_prev ? __ldg(d.cbuf + b * cstr + (int64_t)tp * ndir * H + dir * H + j0 + lane) : 0.f;
-          pg[ii][6] = d.dh_ext ? __ldg(d.dh_ext + b * dhbs + (int64_t)t * ndir * H + dir * H + j0 + lane) : 0.f;
-        }
+  for (int ss0 = 0; ss0 < nss; ss0 += cpd * G) {
+    const int ss = ss0 + g * cpd + cl;
+    if (ss < nss) {
+      const int b0 = ss * NBG;
+      const int bl = gt >> 3, j4 = (gt & 7) * 4, bme = b0 + bl;      // cell-backward items: sample bl, units j4 .. j4 + 3
+      const int len_me = bme < B ? (d.len ? min(d.len[bme], T) : T) : 0;
+      float dcs[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gt == 0) {
+        if (T > 1) mbar_arrive_expect_tx(&full[1], red_bytes);
+        if (T > 2) mbar_arrive_expect_tx(&full[0], red_bytes);
       }
-      float dh[IPT] = {0.f, 0.f};
-      if (s > 0) {
-        if (tid == 0) {
-          tc_fence_after();
-          for (int m = 0; m < MT; ++m) {
-            const uint64_t da = da0 + (uint64_t)(m * 2048);    // M-tile: 2 k-tiles x 16 KB
+
+      for (int s = 0; s < T; ++s) {
+        ck.start();
+        const int t = dir ? s : (T - 1 - s);               // reverse of the forward order
+        const uint32_t buf = (uint32_t)s & 1u;
+        // what the cell backward needs (saved gates, c_t, c_prev, external dh): independent of the recurrence
+        const bool valid = t < len_me;
+        float4 pg[4], pc = make_float4(0.f, 0.f, 0.f, 0.f), pcp = pc, pdh = pc;
 #pragma unroll
-            for (int ka = 0; ka < 2; ++ka) {
-              const uint64_t a = da + ka * 1024, b = db0 + ka * (NB * 8);
-              tc_mma(tmem + m * NB, a, b, idesc, ka ? 1u : 0u);
-              tc_mma(tmem + m * NB, a + 2, b + 2, idesc, 1u);
-              tc_mma(tmem + m * NB, a + 4, b + 4, idesc, 1u);
-              tc_mma(tmem + m * NB, a + 6, b + 6, idesc, 1u);
+        for (int qq = 0; qq < 4; ++qq) pg[qq] = pc;
+        if (valid) {
+          const float* gp = d.gates + bme * gstr + (int64_t)t * ndir * 4 * H + dir * 4 * H + j0 + j4;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) pg[qq] = __ldg(reinterpret_cast<const float4*>(gp + qq * H));
+          const float* cp = d.cbuf + bme * cstr + dir * H + j0 + j4;
+          pc = __ldg(reinterpret_cast<const float4*>(cp + (int64_t)t * ndir * H));
+          const int tp = dir ? (t + 1) : (t - 1);
+          if (dir ? (tp < len_me) : (tp >= 0)) pcp = __ldg(reinterpret_cast<const float4*>(cp + (int64_t)tp * ndir * H));
+          if (d.dh_ext) pdh = __ldg(reinterpret_cast<const float4*>(d.dh_ext + bme * dhbs + (int64_t)t * ndir * H + dir * H + j0 + j4));
+        }
+        float dh[4] = {0.f, 0.f, 0.f, 0.f};
+        if (s > 0) {
+          if (lane == 0 && q < MT) {
+            tc_fence_after();
+            uint64_t db = umma_desc_nosw(bop_local, NBG * 16, 128);
+            uint32_t ta = tmem + (uint32_t)(q * 64);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              tc_mma_ts(tmem_d + NBG * q, ta, db, idesc, kk ? 1u : 0u);
+              ta += 8;
+              db += 2 * NBG;
+            }
+            tc_commit(mma_done);
+          }
+          mbar_wait(mma_done, nmma & 1u);
+          ++nmma;
+          tc_fence_after();
+          ck.lap(0);
+          // reduce-scatter, outgoing side: M-tile m, lanes 32 q .. = owner CTA 4 m + q's units
+          uint8_t* stb = stage + buf * red_bytes;
+          for (int m = 0; m < MT; ++m) {
+            uint32_t v[NBG];
+            tc_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * NBG), v);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(stb + (uint32_t)(4 * m + q) * blk_bytes) + lane;
+#pragma unroll
+            for (int p = 0; p < NBG / 2; ++p) dst[p * UPC] = pack_bf16(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]));
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          group_sync(g);
+          ck.lap(1);
+          if (lane < 4) {
+            const int owner = lane * 4 + q;
+            if (owner < CS) {
+              const uint32_t dst = mapa(red_local + buf * red_bytes + (uint32_t)rank * blk_bytes, (uint32_t)owner);
+              const uint32_t bar = mapa(full_local + buf * 8, (uint32_t)owner);
+              bulk_copy_to_peer(dst, stage_local + buf * red_bytes + (uint32_t)owner * blk_bytes, blk_bytes, bar);
             }
           }
-          tc_commit(mbar);
-        }
-        mbar_wait(mbar, ph);
-        ph ^= 1u;
-        tc_fence_after();
-        ck.lap(0);
-        // reduce-scatter: TMEM lane = unit m*128 + qd*32 + lane -> owner CTA 4m + qd, its unit `lane`
-        for (int m = hf; m < MT; m += 2) {
-          uint32_t v[16];
-          tc_ld16(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(m * NB), v);
-          const uint32_t dst = mapa(red_local, (uint32_t)(4 * m + qd)) + buf * red_bytes + (uint32_t)(rank * (NB / 4) * UPC + lane) * 16;
+          ck.lap(2);
+          if (buf) { mbar_wait(&full[1], nuse1 & 1u); ++nuse1; }
+          else { mbar_wait(&full[0], nuse0 & 1u); ++nuse0; }
+          ck.lap(3);
+          // incoming side: sum the CS blocks; pair bl/2 holds samples (bl & ~1, bl | 1) as (lo, hi) bf16
+          const uint8_t* rb = red + buf * red_bytes + ((bl >> 1) * UPC + j4) * 4;
+          for (int k = 0; k < CS; ++k) {
+            const uint4 x = *reinterpret_cast<const uint4*>(rb + (uint32_t)k * blk_bytes);
+            const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-          for (int c4 = 0; c4 < NB / 4; ++c4)
-            st_cluster_v4(dst + c4 * (UPC * 16), v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+            for (int e = 0; e < 4; ++e) dh[e] += __uint_as_float((bl & 1) ? (xs[e] & 0xffff0000u) : (xs[e] << 16));
+          }
         }
-        tc_fence_before();
-        cluster_arrive();
-        ck.lap(1);
-        cluster_wait();
-        ck.lap(2);
-        // my units' dh: sum of the CS incoming blocks; samples 2w, 2w+1 = float2 at [k][c4 = w/2][lane][(w&1)*2]
-        const float* rp = reinterpret_cast<const float*>(red + buf * red_bytes) + ((w >> 1) * UPC + lane) * 4 + (w & 1) * 2;
-        for (int k = 0; k < CS; ++k) {
-          const float2 x = *reinterpret_cast<const float2*>(rp + k * (NB / 4) * UPC * 4);
-          dh[0] += x.x;
-          dh[1] += x.y;
+        float4 dq[4];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) dq[qq] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          const float gi[4] = {pg[0].x, pg[0].y, pg[0].z, pg[0].w}, gf[4] = {pg[1].x, pg[1].y, pg[1].z, pg[1].w};
+          const float gg[4] = {pg[2].x, pg[2].y, pg[2].z, pg[2].w}, go[4] = {pg[3].x, pg[3].y, pg[3].z, pg[3].w};
+          const float cc[4] = {pc.x, pc.y, pc.z, pc.w}, cp[4] = {pcp.x, pcp.y, pcp.z, pcp.w}, de[4] = {pdh.x, pdh.y, pdh.z, pdh.w};
+          float o[4][4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float dht = dh[e] + de[e];
+            const float tch = tanh_approx(cc[e]);      // the same function the forward applied
+            const float dc = dcs[e] + dht * go[e] * (1.f - tch * tch);
+            dcs[e] = dc * gf[e];
+            o[0][e] = dc * gg[e] * gi[e] * (1.f - gi[e]);
+            o[1][e] = dc * cp[e] * gf[e] * (1.f - gf[e]);
+            o[2][e] = dc * gi[e] * (1.f - gg[e] * gg[e]);
+            o[3][e] = dht * tch * go[e] * (1.f - go[e]);
+          }
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) dq[qq] = make_float4(o[qq][0], o[qq][1], o[qq][2], o[qq][3]);
         }
+        // next step's B operand (own gate gradients, bf16): element (row bl, k = 32 qq + j4 + e), no-swizzle core matrices
+        uint2 d16[4];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          d16[qq] = make_uint2(pack_bf16(dq[qq].x, dq[qq].y), pack_bf16(dq[qq].z, dq[qq].w));
+          const int lr = qq * 32 + j4;
+          *reinterpret_cast<uint2*>(Bop + (lr >> 3) * (NBG * 16) + bl * 16 + (lr & 7) * 2) = d16[qq];
+        }
+        fence_proxy_async();
+        group_sync(g);
+        ck.lap(4);
+        if (bme < B) {
+          const int64_t o = bme * gstr + (int64_t)t * ndir * 4 * H + dir * 4 * H + j0 + j4;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            *reinterpret_cast<float4*>(d.dgates + o + qq * H) = dq[qq];
+            if (dg16) *reinterpret_cast<uint2*>(dg16 + o + qq * H) = d16[qq];
+          }
+        }
+        // re-arm the barrier this step used: partial sums of step s + 2 land there (peers cannot send them before they
+        // have this CTA's step s + 1 block, which leaves after this point)
+        if (gt == 0 && s > 0 && s + 2 < T) mbar_arrive_expect_tx(&full[buf], red_bytes);
+        ck.lap(5);
       }
-#pragma unroll
-      for (int ii = 0; ii < IPT; ++ii) {
-        const int bl = 2 * w + ii, b = b0 + bl;
-        float di = 0.f, df = 0.f, dgg = 0.f, dgo = 0.f;
-        if (pv[ii]) {
-          const float gi = pg[ii][0], gf = pg[ii][1], gg = pg[ii][2], go = pg[ii][3], c = pg[ii][4], cprev = pg[ii][5];
-          const float dht = dh[ii] + pg[ii][6];
-          const float tch = ftanh(c);
-          const float dc = dcs[ii] + dht * go * (1.f - tch * tch);
-          dcs[ii] = dc * gf;
-          di = dc * gg * gi * (1.f - gi);
-          df = dc * cprev * gf * (1.f - gf);
-          dgg = dc * gi * (1.f - gg * gg);
-          dgo = dht * tch * go * (1.f - go);
-        }
-        const __nv_bfloat16 v16[4] = {__float2bfloat16(di), __float2bfloat16(df), __float2bfloat16(dgg), __float2bfloat16(dgo)};
-        if (b < B) {
-          const int64_t o = b * gstr + (int64_t)t * ndir * 4 * H + dir * 4 * H + j0 + lane;
-          d.dgates[o] = di; d.dgates[o + H] = df; d.dgates[o + 2 * H] = dgg; d.dgates[o + 3 * H] = dgo;
-          if (dg16) { dg16[o] = v16[0]; dg16[o + H] = v16[1]; dg16[o + 2 * H] = v16[2]; dg16[o + 3 * H] = v16[3]; }
-        }
-        // next step's B operand: element (row bl, k = q*32 + lane)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int lr = q * 32 + lane, cc = (lr & 63) >> 3;
-          *reinterpret_cast<__nv_bfloat16*>(Bop + (lr >> 6) * (NB * 128) + bl * 128 + ((cc ^ (bl & 7)) << 4) + (lr & 7) * 2) = v16[q];
-        }
-      }
-      fence_proxy_async();
+    }
+    if (ss0 + cpd * G < nss) {
       __syncthreads();
-      ck.lap(3);
+      cluster_arrive();
+      cluster_wait();
     }
   }
+  tc_fence_before();
+  __syncthreads();
   cluster_arrive();
   cluster_wait();
-  if (d.dbg && tid == 0) {
-    long long* q = d.dbg + (int64_t)blockIdx.x * 8;
-    for (int i = 0; i < 7; ++i) q[i] = ck.acc[i];
-    q[7] = clock64() - tstart;
+  if (d.dbg && gt == 0) {
+    long long* qd = d.dbg + ((int64_t)blockIdx.x * MAXG + g) * 8;
+    for (int i = 0; i < 7; ++i) qd[i] = ck.acc[i];
+    qd[7] = clock64() - tstart;
   }
-  tmem_free<64>(tmem);
+  tmem_free<512>(tmem);
 }
 
 // ---------------------------------------------------------------------------------- host side
@@ -532,34 +580,8 @@ static size_t fwd_smem_bytes(int H, int G) {
   // >= 120 KB keeps the clusters at one CTA per SM (every CTA allocates all 512 TMEM columns)
   return std::max((size_t)120 * 1024, 1024 + 64 + (size_t)G * fwd_group_bytes(H));
 }
-static size_t bwd_smem_bytes(int H, int NB) {
-  const int CS = H / UPC;
-  return 1024 + (size_t)(H / 128) * 2 * 128 * 128 + (size_t)2 * NB * 128 + 2 * (size_t)CS * NB * UPC * 4 + 16;
-}
-
-template <typename KernT>
-static int launch_cluster(KernT kern, const ag_lstm_desc* d, int CS, int NB, size_t smem, cudaStream_t s, int* launched) {
-  *launched = 0;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return AG_OK; }
-  if (CS > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return AG_OK; }
-  const int nchunks = (d->B + NB - 1) / NB;
-  cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = (unsigned)CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  cfg.blockDim = dim3(LT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cfg.gridDim = dim3((unsigned)(CS * d->ndir * nchunks));
-  int nmax = 0;
-  if (cudaOccupancyMaxActiveClusters(&nmax, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return AG_OK; }
-  if (nmax < d->ndir) return AG_OK;                         // cannot host one cluster per direction: caller falls back
-  // clusters are independent, so any count works; co-resident ones avoid a tail of late clusters
-  int cpd = std::min(nchunks, std::max(1, nmax / d->ndir));
-  cfg.gridDim = dim3((unsigned)(CS * d->ndir * cpd));
-  ag_lstm_desc dd = *d;
-  AG_CUDA(cudaLaunchKernelEx(&cfg, kern, dd, nchunks, cpd));
-  *launched = 1;
-  return AG_OK;
+static size_t bwd_smem_bytes(int H, int G) {
+  return std::max((size_t)120 * 1024, 1024 + 64 + (size_t)G * bwd_group_bytes(H));
 }
 
 static bool eligible(const ag_lstm_desc* d) {
@@ -577,26 +599,25 @@ static void cluster_cfg(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int CS
 }
 
 // Returns AG_OK with *launched = 1 when the cluster kernel took the call; *launched = 0 -> the caller uses lstm.cu.
-int cluster_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
+template <typename KernT>
+static int launch_groups(KernT kern, const ag_lstm_desc* d, int maxg, size_t (*smem_of)(int, int), cudaStream_t s, int* launched) {
   *launched = 0;
-  if (!eligible(d) || !d->hbuf16) return AG_OK;
   const int CS = d->H / UPC;
-  auto kern = lstm_cl_fwd_kernel;
-  size_t smem = fwd_smem_bytes(d->H, MAXG);
+  size_t smem = smem_of(d->H, maxg);
   if (smem > (size_t)smem_optin()) return AG_OK;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return AG_OK; }
   if (CS > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return AG_OK; }
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute at[1];
-  cluster_cfg(&cfg, at, CS, GT * MAXG, smem, s);
+  cluster_cfg(&cfg, at, CS, GT * maxg, smem, s);
   int nmax = 0;
   if (cudaOccupancyMaxActiveClusters(&nmax, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return AG_OK; }
   if (nmax < d->ndir) return AG_OK;                         // cannot host one cluster per direction: caller falls back
   // sub-slices of 16 samples per direction -> G warp groups on each of cpd clusters (fewest rounds, then fewest groups)
   const int nss = (d->B + NBG - 1) / NBG, cpd_max = nmax / d->ndir;
-  const int G = std::min(MAXG, (nss + cpd_max - 1) / cpd_max);
+  const int G = std::min(maxg, (nss + cpd_max - 1) / cpd_max);
   const int cpd = std::min(cpd_max, (nss + G - 1) / G);
-  smem = fwd_smem_bytes(d->H, G);
+  smem = smem_of(d->H, G);
   cluster_cfg(&cfg, at, CS, GT * G, smem, s);
   cfg.gridDim = dim3((unsigned)(CS * d->ndir * cpd));
   ag_lstm_desc dd = *d;
@@ -604,13 +625,15 @@ int cluster_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
   *launched = 1;
   return AG_OK;
 }
+int cluster_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
+  *launched = 0;
+  if (!eligible(d) || !d->hbuf16) return AG_OK;
+  return launch_groups(lstm_cl_fwd_kernel, d, MAXG, fwd_smem_bytes, s, launched);
+}
 int cluster_bwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
   *launched = 0;
   if (!eligible(d)) return AG_OK;
-  const int CS = d->H / UPC;
-  const size_t smem = bwd_smem_bytes(d->H, 16);
-  if (smem > (size_t)smem_optin()) return AG_OK;
-  return launch_cluster(lstm_cl_bwd_kernel<16>, d, CS, 16, smem, s, launched);
+  return launch_groups(lstm_cl_bwd_kernel, d, MAXG_BWD, bwd_smem_bytes, s, launched);
 }
 
 }  // namespace lc
@@ -628,10 +651,11 @@ extern "C" int ag_lstm_cluster_max_active(int H, int bwd) {
   int nmax = 0;
   cudaError_t e;
   if (bwd) {
-    cfg.dynamicSmemBytes = bwd_smem_bytes(H, 16);
-    cudaFuncSetAttribute(lstm_cl_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
-    if (CS > 8) cudaFuncSetAttribute(lstm_cl_bwd_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    e = cudaOccupancyMaxActiveClusters(&nmax, lstm_cl_bwd_kernel<16>, &cfg);
+    cfg.dynamicSmemBytes = bwd_smem_bytes(H, MAXG_BWD);
+    cfg.blockDim = dim3(GT * MAXG_BWD);
+    cudaFuncSetAttribute(lstm_cl_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+    if (CS > 8) cudaFuncSetAttribute(lstm_cl_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    e = cudaOccupancyMaxActiveClusters(&nmax, lstm_cl_bwd_kernel, &cfg);
   } else {
     cfg.dynamicSmemBytes = fwd_smem_bytes(H, MAXG);
     cfg.blockDim = dim3(GT * MAXG);

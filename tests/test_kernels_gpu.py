@@ -330,3 +330,47 @@ def test_lstm_bf16_mode_tracks_fp32_kernels(H, B, Tn, ndir, Fr, prec_tc):
     if Fr:
         assert rel(r1[2], res[0][2]) < 2e-2, "x"
     assert rel(r1[3].float(), r1[1]) < 1e-2, "bf16 shadow"
+
+
+@pytest.mark.parametrize("H,B,Tn", [(512, 40, 9), (128, 5, 12), (256, 70, 17), (512, 200, 5), (512, 128, 33)])
+def test_lstm_cluster_kernels_track_fp32_kernels(H, B, Tn):
+    """Cluster-resident BiLSTM (csrc/lstm_cluster.cu: TMEM-resident weights, DSMEM exchange; what the discriminator's
+    NN.LSTM, audiogan.py:498-503, runs on in bf16 mode) against the fp32 grid-barrier kernels and against the bf16
+    grid-barrier kernels (reserved2 bit 0) on the same inputs, mixed lengths, ragged last slice, several rounds (B = 200)."""
+    from audiogan_b200 import kernels as Kn, _abi as A
+    assert A.lib().ag_lstm_cluster_max_active(H, 0) >= 2 and A.lib().ag_lstm_cluster_max_active(H, 1) >= 2, "cluster launch unavailable"
+    T.manual_seed(5)
+    dev, ndir = "cuda", 2
+    pre = T.randn(B, Tn, ndir * 4 * H, device=dev)
+    w1 = (T.randn(ndir, 4 * H, H, device=dev) / H ** 0.5).contiguous()
+    w1t = w1.permute(0, 2, 1).contiguous()
+    lens = T.randint(1, Tn + 1, (B,), device=dev, dtype=T.int32)
+    lens[0] = Tn
+    dh_ext = T.randn(B, Tn, ndir * H, device=dev)
+    out = {}
+    for name, prec, flags in (("fp32", 0, 0), ("grid", 1, 1), ("cluster", 1, 0)):
+        hbuf, gates, cbuf = T.zeros(B, Tn + 2, ndir * H, device=dev), T.zeros(B, Tn, ndir * 4 * H, device=dev), T.zeros(B, Tn, ndir * H, device=dev)
+        misc = T.zeros(16, dtype=T.int32, device=dev)
+        dbg = T.zeros(148 * 4, 8, dtype=T.int64, device=dev) if name == "cluster" else None
+        hbuf16 = T.zeros(B, Tn + 2, ndir * H, device=dev, dtype=T.bfloat16) if prec else None
+        dgates = T.full((B, Tn, ndir * 4 * H), float("nan"), device=dev)
+        dgates16 = T.zeros(B, Tn, ndir * 4 * H, device=dev, dtype=T.bfloat16) if prec else None
+        Kn.lstm_fwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=ndir, F=0, pre=pre, w1=w1, hbuf=hbuf, gates=gates, cbuf=cbuf, len=lens,
+                    barrier=misc, prec=prec, reserved2=flags, hbuf16=hbuf16, dbg=dbg)
+        if dbg is not None:
+            assert int((dbg[:, 7] > 0).sum()) > 0, "the cluster forward kernel did not run"
+            dbg.zero_()
+        Kn.lstm_bwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=ndir, F=0, gates=gates, cbuf=cbuf, len=lens, dh_ext=dh_ext, dgates=dgates,
+                    w1t=w1t, barrier=misc, prec=prec, reserved2=flags, dgates16=dgates16, dbg=dbg)
+        if dbg is not None:
+            assert int((dbg[:, 7] > 0).sum()) > 0, "the cluster backward kernel did not run"
+        out[name] = (hbuf, gates, cbuf, dgates, hbuf16, dgates16)
+    f, gr, c = out["fp32"], out["grid"], out["cluster"]
+    for i, nm in enumerate(("h", "gates", "c", "dgates")):
+        assert bool(T.isfinite(c[i]).all()), nm
+        assert rel(c[i], f[i]) < 2e-2, (nm, rel(c[i], f[i]))
+        assert rel(c[i], gr[i]) < 2e-2, (nm, "vs grid bf16", rel(c[i], gr[i]))
+    # steps past a sample's length emit exactly zero (packed-sequence semantics, audiogan.py:214-229)
+    tt = T.arange(Tn, device=dev)[None, :, None] >= lens[:, None, None]
+    assert float((c[0][:, 1:Tn + 1] * tt).abs().max()) == 0.0 and float((c[3] * tt).abs().max()) == 0.0
+    assert rel(c[4].float(), c[0]) < 1e-2 and rel(c[5].float(), c[3]) < 1e-2, "bf16 shadows"

@@ -51,7 +51,7 @@ def run(H, B, Tn, ndir=2, mixed=True, time_it=True):
         out[name] = (hbuf.clone(), gates.clone(), cbuf.clone(), dgates.clone(), hbuf16, dgates16)
         print("  %-8s H%d B%d T%d: fwd %.3f ms (%.2f us/step)  bwd %.3f ms (%.2f us/step)" % (name, H, B, Tn, tf, tf * 1e3 / Tn, tb, tb * 1e3 / Tn), flush=True)
         if name == "cluster":
-            for nm, dd, labels in (("fwd", dfw, "wait-h, mma, tmem-ld, act+sync, cell+fence+sync, push, prefetch+stores"), ("bwd", dbw, "mma+wait, ld+push, barrier-wait, reduce+cell, -")):
+            for nm, dd, labels in (("fwd", dfw, "wait-h, mma, tmem-ld, act+sync, cell+fence+sync, push, prefetch+stores"), ("bwd", dbw, "mma, tmem-ld+stage+sync, push, wait-partials, reduce+cell+Bop+sync, stores+rearm, -")):
                 used = dd[:, 7] > 0
                 if used.sum() == 0:
                     print("    %s: cluster kernel did not run (fallback)" % nm)
