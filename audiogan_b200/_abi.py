@@ -53,6 +53,7 @@ class LstmDesc(C.Structure):
         ("prec", i32), ("reserved2", i32),
         ("hbuf16", vp), ("xbuf16", vp), ("dgates16", vp), ("dpx16", vp),
         ("dbg", vp),
+        ("ll_ws", vp), ("ll_ws_bytes", i64),
     ]
 
 

@@ -1210,6 +1210,8 @@ static int run_bwd(const ag_lstm_desc* d, const Plan& p, cudaStream_t s) { AG_LS
 namespace ag { namespace lc {
 int cluster_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);   // lstm_cluster.cu
 int cluster_bwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);
+} namespace lg {
+int gen_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);       // lstm_gen.cu
 } }
 
 using namespace ag;
@@ -1221,6 +1223,8 @@ int ag_lstm_fwd(const ag_lstm_desc* d, void* stream) {
   {
     int launched = 0;
     rc = lc::cluster_fwd(d, (cudaStream_t)stream, &launched);
+    if (rc || launched) return rc;
+    rc = lg::gen_fwd(d, (cudaStream_t)stream, &launched);
     if (rc || launched) return rc;
   }
   Plan p;

@@ -183,15 +183,26 @@ __global__ void __launch_bounds__(GT * MAXG, 1) lstm_cl_fwd_kernel(const ag_lstm
   // resident weights -> TMEM: this thread's row lr = 32 q + lane (gate q, unit j0 + lane), column range split over the groups
   {
     const float* src = d.w1 + ((int64_t)dir * 4 * H + (int64_t)q * H + j0 + lane) * H;
-    for (int k0 = g * 16; k0 < H; k0 += 16 * G) {
-      uint32_t v[8];
+    // 4 column blocks per pass: all 16 loads in flight before the first tcgen05.st (latency-bound otherwise)
+    for (int k0 = g * 16; k0 < H; k0 += 64 * G) {
+      float4 a[4][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src + k0) + e);
-        v[2 * e] = pack_bf16(a.x, a.y);
-        v[2 * e + 1] = pack_bf16(a.z, a.w);
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          a[u][e] = (k0 + 16 * G * u < H) ? __ldg(reinterpret_cast<const float4*>(src + k0 + 16 * G * u) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k0 + 16 * G * u < H) {
+          uint32_t v[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[2 * e] = pack_bf16(a[u][e].x, a[u][e].y);
+            v[2 * e + 1] = pack_bf16(a[u][e].z, a[u][e].w);
+          }
+          tc_st8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((k0 + 16 * G * u) >> 1), v);
+        }
       }
-      tc_st8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(k0 >> 1), v);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
@@ -397,17 +408,29 @@ __global__ void __launch_bounds__(GT * MAXG_BWD, 1) lstm_cl_bwd_kernel(const ag_
   // A[unit j][k = lr] = whh[gate row (lr/32)*H + j0 + lr%32][j] = w1t[dir][j][...]; this thread's rows: 128 m + 32 q + lane
   {
     const float* wt = d.w1t + (int64_t)dir * H * 4 * H;
-    for (int idx = g; idx < MT * 8; idx += G) {
-      const int m = idx >> 3, kk = idx & 7, lr0 = kk * 16;
-      const float* src = wt + (int64_t)(m * 128 + q * 32 + lane) * 4 * H + (lr0 >> 5) * H + j0 + (lr0 & 31);
-      uint32_t v[8];
+    for (int idx0 = g; idx0 < MT * 8; idx0 += 4 * G) {
+      float4 a[4][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src) + e);
-        v[2 * e] = pack_bf16(a.x, a.y);
-        v[2 * e + 1] = pack_bf16(a.z, a.w);
+      for (int u = 0; u < 4; ++u) {
+        const int idx = idx0 + u * G, m = idx >> 3, lr0 = (idx & 7) * 16;
+        const float* src = wt + (int64_t)(m * 128 + q * 32 + lane) * 4 * H + (lr0 >> 5) * H + j0 + (lr0 & 31);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          a[u][e] = idx < MT * 8 ? __ldg(reinterpret_cast<const float4*>(src) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      tc_st8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * 64 + kk * 8), v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = idx0 + u * G, m = idx >> 3, kk = idx & 7;
+        if (idx < MT * 8) {
+          uint32_t v[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[2 * e] = pack_bf16(a[u][e].x, a[u][e].y);
+            v[2 * e + 1] = pack_bf16(a[u][e].z, a[u][e].w);
+          }
+          tc_st8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * 64 + kk * 8), v);
+        }
+      }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }

@@ -52,11 +52,14 @@ class _GenFn(torch.autograd.Function):
         sbuf = _zeros(B, Tcap, device=dev)
         stop = torch.zeros(B, Tcap, device=dev, dtype=torch.int32)
         glen = torch.zeros(B, device=dev, dtype=torch.int32)
-        misc = torch.zeros(16, device=dev, dtype=torch.int32)          # [0:8] barrier, [8] t_end
+        misc = torch.zeros(1024, device=dev, dtype=torch.int32)        # [0:8] barrier, [8] t_end, [16:] per-CTA flags
         u = u_stop.contiguous() if u_stop is not None else None
+        # exchange workspace of the TMEM-resident recurrence (include/audiogan_b200.h: ag_lstm_desc.ll_ws)
+        ll_ws = torch.empty(16 * ((B + 31) // 32 * 32) * (H // 2 + F) + 256, device=dev, dtype=torch.uint8)
         K.lstm_fwd(B=B, T=Tcap, Tcap=Tcap, H=H, ndir=1, F=F, pre=pre, w1=plan.Poff("w1"), w2=plan.Poff("w2"),
                    b2=plan.Poff("b2"), hbuf=hbuf, gates=gates, cbuf=cbuf, xbuf=xbuf, sbuf=sbuf, u=u, stop=stop,
-                   glen=glen, t_end=(misc, 8), barrier=misc, prec=plan.lstm_prec if bf else 0, hbuf16=hbuf16, xbuf16=xbuf16)
+                   glen=glen, t_end=(misc, 8), barrier=misc, prec=plan.lstm_prec if bf else 0, hbuf16=hbuf16, xbuf16=xbuf16,
+                   reserved2=plan.lstm_flags | 2, ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel())
         if u is not None and early_exit_sync:
             T = int(misc[8].item())          # the one host sync per generator pass (audiogan.py:459-460)
         else:
@@ -285,7 +288,7 @@ class _DiscTailFn(torch.autograd.Function):
         cbuf = _empty(B, Tm, 2 * H, device=dev)
         misc = torch.zeros(16, device=dev, dtype=torch.int32)
         K.lstm_fwd(B=B, T=Tm, Tcap=Tm, H=H, ndir=2, F=0, pre=pre, w1=plan.Poff("w1"), hbuf=hbuf, gates=gates, cbuf=cbuf,
-                   len=nfr, barrier=misc, prec=plan.lstm_prec if bf else 0, hbuf16=hbuf16)
+                   len=nfr, barrier=misc, prec=plan.lstm_prec if bf else 0, hbuf16=hbuf16, reserved2=plan.lstm_flags)
         # residual_net + classifier on the (B*Tm) rows (audiogan.py:547-549); same row geometry as hbuf
         geo = (Tm, (Tm + 2) * S, S)
         r1 = _empty(B, Tm + 2, S, device=dev)
@@ -340,7 +343,7 @@ class _DiscTailFn(torch.autograd.Function):
         dgates16 = torch.empty(B, Tm, 8 * H, device=dev, dtype=torch.bfloat16) if bf else None
         K.lstm_bwd(B=B, T=Tm, Tcap=Tm, H=H, ndir=2, F=0, gates=gates, cbuf=cbuf, len=nfr, dh_ext=(dh_ext, S),
                    dh_ext_bs=(Tm + 2) * S, dgates=dgates, w1t=plan.Poff("w1t"), barrier=misc,
-                   prec=plan.lstm_prec if bf else 0, dgates16=dgates16)
+                   prec=plan.lstm_prec if bf else 0, dgates16=dgates16, reserved2=plan.lstm_flags)
         dgo, hbo = (dgates16, hbuf16) if bf else (dgates, hbuf)
         dgsum = None
         if wgrad or ctx.needs_input_grad[3]:

@@ -91,6 +91,8 @@ class NetPlan:
         # recurrent products in bf16 mode: 1 = mma.sync path (default: measured faster end to end, see
         # profiles/r1_lstm_phase_cycles.txt), 2 = tcgen05 / TMEM path (AUDIOGAN_LSTM=tcgen05)
         self.lstm_prec = 2 if os.environ.get("AUDIOGAN_LSTM", "") == "tcgen05" else 1
+        # AUDIOGAN_LSTM=grid keeps the grid-barrier kernels (no cluster / TMEM-resident variants): A/B timing aid
+        self.lstm_flags = 1 if os.environ.get("AUDIOGAN_LSTM", "") == "grid" else 0
 
     # -- declaration ----------------------------------------------------------------------
     def weight(self, name, v, g=None):

@@ -126,9 +126,14 @@ typedef struct ag_lstm_desc {
   /* bf16 mode (prec = 1): the recurrent products run on tensor cores (bf16 operands, fp32 accumulate, fp32 state).
    * The kernels keep bf16 shadow copies of the per-step operands, same shapes as their fp32 twins:
    * hbuf16 / xbuf16 (forward writes, rows 0 / T+1 zero on entry), dgates16 / dpx16 (backward writes). */
-  int32_t prec, reserved2;   /* reserved2 bit 0: do not use the cluster-resident kernels (see below) */
+  int32_t prec, reserved2;   /* reserved2 bit 0: use the grid-barrier kernels only (no cluster / TMEM-resident kernels);
+                              * bit 1: allow the TMEM-resident generator kernel (needs ll_ws) */
   void* hbuf16; void* xbuf16; void* dgates16; void* dpx16;
   long long* dbg;        /* optional [gridDim][8] cycle counters per CTA: gemm, cell, barrier, phase2/A, total (profiling aid) */
+  /* Workspace of the TMEM-resident generator kernel (bf16 mode, F > 0): the per-step h_t / x_t exchange between the CTAs
+   * of a batch group runs over it ("LL" words: payload + step tag).  >= 16 * B_pad * (H/2 + F) + 256 bytes with
+   * B_pad = B rounded up to 32; NULL -> the grid-barrier kernels are used.  The call zeroes what it needs. */
+  void* ll_ws; int64_t ll_ws_bytes;
 } ag_lstm_desc;
 
 int ag_lstm_fwd(const ag_lstm_desc* d, void* stream);

@@ -374,3 +374,46 @@ def test_lstm_cluster_kernels_track_fp32_kernels(H, B, Tn):
     tt = T.arange(Tn, device=dev)[None, :, None] >= lens[:, None, None]
     assert float((c[0][:, 1:Tn + 1] * tt).abs().max()) == 0.0 and float((c[3] * tt).abs().max()) == 0.0
     assert rel(c[4].float(), c[0]) < 1e-2 and rel(c[5].float(), c[3]) < 1e-2, "bf16 shadows"
+
+
+@pytest.mark.parametrize("B,Tn,stops", [(16, 3, False), (37, 12, True), (64, 9, False), (70, 7, True)])
+def test_lstm_generator_tmem_kernel_tracks_fp32_kernel(B, Tn, stops):
+    """TMEM-resident generator recurrence (csrc/lstm_gen.cu: weights in tensor memory + shared memory, LL exchange of
+    h_t / x_t through L2) against the fp32 grid-barrier kernel on the same inputs: frames, stop logits, saved state
+    <= 2e-2; with stop sampling the Bernoulli draws, lengths and the early-exit step are IDENTICAL (audiogan.py:445-460)."""
+    from audiogan_b200 import kernels as Kn
+    T.manual_seed(7)
+    dev, H, Fr = "cuda", 1024, 200
+    pre = T.randn(B, Tn, 4 * H, device=dev)
+    w1 = (T.randn(1, 4 * H, H + Fr, device=dev) / H ** 0.5).contiguous()
+    w2 = (T.randn(Fr + 1, H, device=dev) / H ** 0.5).contiguous()
+    b2 = (T.randn(Fr + 1, device=dev) / H ** 0.5).contiguous()
+    if stops:
+        b2[Fr] = 0.5                                   # stop probability ~60 % per frame: every sample stops early
+    u = T.rand(B, Tn, device=dev) if stops else None
+    out = {}
+    for name, prec, flags in (("fp32", 0, 0), ("tmem", 1, 2)):
+        hbuf, gates, cbuf = T.zeros(B, Tn + 2, H, device=dev), T.zeros(B, Tn, 4 * H, device=dev), T.zeros(B, Tn, H, device=dev)
+        xbuf, sbuf = T.zeros(B, Tn + 1, Fr, device=dev), T.zeros(B, Tn, device=dev)
+        stop, glen = T.zeros(B, Tn, dtype=T.int32, device=dev), T.zeros(B, dtype=T.int32, device=dev)
+        misc = T.zeros(1024, dtype=T.int32, device=dev)
+        dbg = T.zeros(148, 8, dtype=T.int64, device=dev) if prec else None
+        ll_ws = T.empty(16 * ((B + 31) // 32 * 32) * (H // 2 + Fr) + 256, device=dev, dtype=T.uint8)
+        hbuf16 = T.zeros(B, Tn + 2, H, device=dev, dtype=T.bfloat16) if prec else None
+        xbuf16 = T.zeros(B, Tn + 1, Fr, device=dev, dtype=T.bfloat16) if prec else None
+        Kn.lstm_fwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=1, F=Fr, pre=pre, w1=w1, w2=w2, b2=b2, hbuf=hbuf, gates=gates, cbuf=cbuf,
+                    xbuf=xbuf, sbuf=sbuf, u=u, stop=stop, glen=glen, t_end=(misc, 8), barrier=misc, prec=prec,
+                    reserved2=flags, hbuf16=hbuf16, xbuf16=xbuf16, dbg=dbg, ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel())
+        T.cuda.synchronize()
+        if dbg is not None:
+            assert int((dbg[:, 7] > 0).sum()) > 0, "the TMEM-resident kernel did not run"
+        out[name] = dict(h=hbuf, x=xbuf, s=sbuf, gates=gates, c=cbuf, stop=stop, glen=glen, t_end=int(misc[8].item()), x16=xbuf16)
+    f, c = out["fp32"], out["tmem"]
+    te = f["t_end"]
+    assert c["t_end"] == te and (not stops or te < Tn or B < 20)
+    assert T.equal(c["glen"], f["glen"]) and T.equal(c["stop"][:, :te], f["stop"][:, :te])
+    for nm in ("h", "x"):
+        assert rel(c[nm][:, :te + 1], f[nm][:, :te + 1]) < 2e-2, nm
+    for nm in ("s", "gates", "c"):
+        assert rel(c[nm][:, :te], f[nm][:, :te]) < 2e-2, nm
+    assert rel(c["x16"][:, :te + 1].float(), c["x"][:, :te + 1]) < 1e-2
