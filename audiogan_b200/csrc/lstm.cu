@@ -1212,6 +1212,7 @@ int cluster_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);   // lstm
 int cluster_bwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);
 } namespace lg {
 int gen_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);       // lstm_gen.cu
+int gen_bwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);
 } }
 
 using namespace ag;
@@ -1289,6 +1290,8 @@ int ag_lstm_bwd(const ag_lstm_desc* d, void* stream) {
   {
     int launched = 0;
     rc = lc::cluster_bwd(d, (cudaStream_t)stream, &launched);
+    if (rc || launched) return rc;
+    rc = lg::gen_bwd(d, (cudaStream_t)stream, &launched);
     if (rc || launched) return rc;
   }
   Plan p;

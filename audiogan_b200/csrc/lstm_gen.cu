@@ -25,7 +25,6 @@ using namespace tc;
 
 constexpr int LT = 256;
 constexpr int UPC = 32;                 // hidden units per CTA
-constexpr int WS_FLAGA = 16, WS_FLAGB = 176, WS_ALIVE = 336;      // uint32 offsets into desc.barrier (>= 1024 words)
 
 __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -116,6 +115,8 @@ struct FwdGeom {
 // costs ~7 k cycles per exchange, measured; two exchanges per step).  Two slots per buffer: a CTA can only be one
 // exchange ahead of its slowest peer.
 //   LLh [2][B_pad][H/2]  (bf16x2 of h_t, tag)      LLx [2][B_pad][F] (fp32 x_t, tag)     LLa [2][16] (alive count, tag)
+// Strong (relaxed, gpu scope) accesses on purpose: weak .cg stores of a lone word can sit in the SM's store-combining
+// path indefinitely and weak polling loads then never see them (observed: a hang with stop sampling on).
 __device__ __forceinline__ void ll_store2(void* p, uint32_t d0, uint32_t tag) {
   asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(d0), "r"(tag) : "memory");
 }
@@ -556,6 +557,399 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
   }
 }
 
+// ====================================================================================== backward (BPTT)
+// Per step t (descending):  [dh_pre ; dx_pre] = [whh | wx]^T dgates_{t+1}          (M = H + F rows, K = 4H)
+//                           dpx_t = (dx_ext_t + dx_pre) (1 - x_t^2),  dpx_t[F] = ds_ext_t
+//                           dh_t  = dh_pre + [wp ; ws]^T dpx_t   ->  cell backward  ->  dgates_t
+// The CTA that owns 32 hidden units owns their 128 gate rows, i.e. a K-SLICE of the big product: its A operand is
+// [whh | wx]^T restricted to those 128 columns ((H + F) x 128, ten 128-row M-tiles: five resident in tensor memory,
+// five in shared memory) and its B operand is its OWN dgates_{t+1} slice -- no all-gather of the gate gradients.  The
+// (H + F) x NB partial sums are reduce-scattered through the L2 (bf16 pairs + step tag, "LL" words): every CTA adds the
+// 32 incoming blocks of its 32 units, the owners of the x rows add theirs, form dpx_t and publish it (second, small LL
+// exchange); [wp ; ws]^T dpx_t for the CTA's own units runs on mma.sync from shared memory.
+//   LLp [2][ngroups][nsl sources][MR rows][8]  (bf16x2 of two samples, tag)      LLd [2][B_pad][F] (fp32 dpx, tag)
+struct BwdGeom {
+  int MR;        // H + F rows of the transposed product
+  int PR;        // x rows per owning CTA
+  int nsl, ngroups;
+  int FP;        // F + 1 rounded up to 8
+};
+constexpr int BT_TMEM = 5;                      // M-tiles of A in tensor memory (64 columns each); the rest in shared memory
+constexpr int BNB = 16;                         // samples per CTA
+
+__device__ __forceinline__ uint2 ll_load2(const void* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(LT, 1) lstm_gen_bwd_kernel(const ag_lstm_desc d, const BwdGeom gm) {
+  constexpr int NB = BNB;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, q = w & 3, hf = w >> 2;
+  const int H = d.H, F = d.F, FP = gm.FP, KW = 4 * H + FP, B = d.B, T = d.T, Tcap = d.Tcap;
+  const int MR = gm.MR, PR = gm.PR, nsl = gm.nsl;
+  const int slice = blockIdx.x % nsl, grp = blockIdx.x / nsl, j0 = slice * UPC, b0 = grp * NB;
+  const int NMT = (MR + 127) / 128, nst = NMT - BT_TMEM;     // M-tiles, of which in shared memory
+  const int Bpad = gm.ngroups * NB;
+  const int WLD = FP + 8;                                    // row stride (bf16) of WpT_s / dpxs
+
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* As = sm;                                                         // [nst][16 chunks][128 rows][16 B]
+  uint8_t* Bop = As + (size_t)nst * 32768;                                  // [16 chunks][NB rows][16 B]
+  __nv_bfloat16* WpT = reinterpret_cast<__nv_bfloat16*>(Bop + 16 * NB * 16);   // [32 units][WLD]: [wp[:, j] | ws[j] | 0]
+  __nv_bfloat16* dpxs = WpT + (size_t)UPC * WLD;                            // [NB][WLD]: dpx_t (col F = ds_t)
+  float* dhs = reinterpret_cast<float*>(dpxs + (size_t)NB * WLD);           // [NB][33]
+  uint64_t* mma_done = reinterpret_cast<uint64_t*>(dhs + NB * 33);     // NB * 33 floats: 8-byte aligned
+  uint64_t* mma_x = mma_done + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_x + 1);
+
+  uint2* LLp = reinterpret_cast<uint2*>(d.ll_ws);
+  uint2* LLd = LLp + (size_t)2 * gm.ngroups * nsl * MR * 8;
+
+  if (tid == 0) {
+    mbar_init(mma_done, 4);
+    mbar_init(mma_x, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (w == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_d = tmem + BT_TMEM * 64;               // accumulator of M-tile mt: columns mt * NB
+  // A[m][k = lr]: m < H -> whh[grow(lr)][m] = w1t[m][grow(lr)];  m >= H -> wx[grow(lr)][m - H] = wxt[m - H][grow(lr)],
+  // grow(lr) = (lr / 32) * H + j0 + lr % 32: 16 consecutive lr are 16 consecutive floats
+  auto arow = [&](int m, int lr0) -> const float* {
+    const int go = (lr0 >> 5) * H + j0 + (lr0 & 31);
+    return m < H ? d.w1t + (int64_t)m * KW + go : d.wxt + (int64_t)(m - H) * 4 * H + go;
+  };
+  for (int it = hf; it < BT_TMEM * 8; it += 8) {             // (tile, k-step) pairs, 4 per pass: 16 loads in flight
+    float4 a[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int id = it + 2 * u, mt = id >> 3, kk = id & 7, m = mt * 128 + q * 32 + lane;
+      const float* src = arow(min(m, MR - 1), kk * 16);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[u][e] = (id < BT_TMEM * 8 && m < MR) ? __ldg(reinterpret_cast<const float4*>(src) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int id = it + 2 * u, mt = id >> 3, kk = id & 7;
+      if (id < BT_TMEM * 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { v[2 * e] = pack_bf16(a[u][e].x, a[u][e].y); v[2 * e + 1] = pack_bf16(a[u][e].z, a[u][e].w); }
+        tc_st8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 64 + kk * 8), v);
+      }
+    }
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#pragma unroll 4
+  for (int cell = tid; cell < nst * 16 * 128; cell += LT) {
+    const int r = cell & 127, cc = (cell >> 7) & 15, ts = cell >> 11, m = (BT_TMEM + ts) * 128 + r;
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    if (m < MR) {
+      const float* src = arow(m, cc * 8);
+      lo = __ldg(reinterpret_cast<const float4*>(src));
+      hi = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    }
+    *reinterpret_cast<uint4*>(As + (size_t)ts * 32768 + cc * 2048 + r * 16) =
+        make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+  }
+  for (int idx = tid; idx < UPC * WLD; idx += LT) {
+    const int j = idx / WLD, k = idx - j * WLD;
+    WpT[idx] = __float2bfloat16(k < FP ? d.w1t[(int64_t)(j0 + j) * KW + 4 * H + k] : 0.f);
+  }
+  for (int idx = tid; idx < NB * WLD; idx += LT) dpxs[idx] = __float2bfloat16(0.f);
+  for (int idx = tid; idx < 16 * NB * 16 / 4; idx += LT) reinterpret_cast<uint32_t*>(Bop)[idx] = 0u;
+  // x rows owned by this CTA
+  const int p0 = slice * PR;
+  int np = min(PR, F - p0);
+  if (np < 0) np = 0;
+  const bool owns_last = np > 0 && p0 + np == F;             // also writes column F (ds) and the pad columns of dpx
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const uint32_t idesc = umma_idesc(128, NB, 0, 0);
+  const uint32_t as_local = smem_u32(As), bop_local = smem_u32(Bop);
+  const int64_t gstr = (int64_t)Tcap * 4 * H, cstr = (int64_t)Tcap * H, xstr = (int64_t)(Tcap + 1) * F;
+  __nv_bfloat16* dg16 = reinterpret_cast<__nv_bfloat16*>(d.dgates16);
+  __nv_bfloat16* dp16 = reinterpret_cast<__nv_bfloat16*>(d.dpx16);
+  // cell-backward items: sample bl, units jv, jv + 1;   reduce items: row rr, sample pair sp
+  const int bl = tid >> 4, jv = (tid & 15) * 2, bme = b0 + bl;
+  const int rr = tid >> 3, sp = tid & 7;
+  float dcs[2] = {0.f, 0.f};
+  uint32_t nmma = 0;
+  Clk ck;
+  ck.init(d.dbg != nullptr);
+  const long long tstart = clock64();
+
+  for (int s = 0; s < T; ++s) {
+    ck.start();
+    const int t = T - 1 - s;
+    const uint32_t tag = (uint32_t)(s + 1), slot = (uint32_t)s & 1u;
+    // inputs of the cell backward and of dpx: independent of the recurrence, in flight under the MMAs
+    float2 pg[4], pc = make_float2(0.f, 0.f), pcp = pc;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) pg[qq] = pc;
+    if (bme < B) {
+      const float* gp = d.gates + bme * gstr + (int64_t)t * 4 * H + j0 + jv;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) pg[qq] = __ldg(reinterpret_cast<const float2*>(gp + qq * H));
+      pc = __ldg(reinterpret_cast<const float2*>(d.cbuf + bme * cstr + (int64_t)t * H + j0 + jv));
+      if (t > 0) pcp = __ldg(reinterpret_cast<const float2*>(d.cbuf + bme * cstr + (int64_t)(t - 1) * H + j0 + jv));
+    }
+    float xo[2] = {0.f, 0.f}, dxe[2] = {0.f, 0.f};
+    if (tid < np * 8) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int b = b0 + 2 * sp + e;
+        if (b < B) {
+          xo[e] = __ldg(d.xbuf + b * xstr + (int64_t)(t + 1) * F + p0 + rr);
+          if (d.dx_ext) dxe[e] = __ldg(d.dx_ext + (b * (int64_t)Tcap + t) * F + p0 + rr);
+        }
+      }
+    }
+    float dsv = 0.f;
+    if (tid < NB && b0 + tid < B && d.ds_ext) dsv = __ldg(d.ds_ext + (b0 + tid) * (int64_t)Tcap + t);
+
+    uint2* outp = LLp + (((size_t)slot * gm.ngroups + grp) * nsl + slice) * MR * 8;
+    // partial sums of one M-tile -> LL blocks: row m, 8 words of (two samples as bf16x2, tag)
+    auto emit_tile = [&](int mt) {
+      uint32_t v[8], v2[8];
+      tc_ld8_nowait(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB), v);
+      tc_ld8_nowait(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB + 8), v2);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int m = mt * 128 + q * 32 + lane;
+      if (m < MR) {
+        uint2* o = outp + (size_t)m * 8;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          ll_store4(o + 2 * e, pack_bf16(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1])),
+                    pack_bf16(__uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3])), tag);
+          ll_store4(o + 4 + 2 * e, pack_bf16(__uint_as_float(v2[4 * e]), __uint_as_float(v2[4 * e + 1])),
+                    pack_bf16(__uint_as_float(v2[4 * e + 2]), __uint_as_float(v2[4 * e + 3])), tag);
+        }
+      }
+    };
+    const int MTX = H / 128;                                   // first M-tile of the x rows
+    if (s > 0) {
+      if (lane == 0 && w < 4) {
+        // the x rows first (they head the longer dependency chain: dx_pre -> dpx_t -> exchange -> [wp ; ws]^T dpx_t), their
+        // own barrier; then the unit rows.  One accumulator per M-tile, each thread interleaves its tiles k-step by k-step.
+        tc_fence_after();
+        const uint64_t db0 = umma_desc_nosw(bop_local, NB * 16, 128);
+        auto issue_tile_step = [&](int mt, int kk) {
+          if (mt < BT_TMEM) tc_mma_ts(tmem_d + mt * NB, tmem + (uint32_t)(mt * 64 + kk * 8), db0 + (uint64_t)(kk * 2 * NB), idesc, kk ? 1u : 0u);
+          else tc_mma(tmem_d + mt * NB, umma_desc_nosw(as_local + (uint32_t)(mt - BT_TMEM) * 32768 + kk * 4096, 2048, 128),
+                      db0 + (uint64_t)(kk * 2 * NB), idesc, kk ? 1u : 0u);
+        };
+        for (int kk = 0; kk < 8; ++kk)
+          for (int mt = MTX + w; mt < NMT; mt += 4) issue_tile_step(mt, kk);
+        tc_commit(mma_x);
+      }
+      mbar_wait(mma_x, nmma & 1u);
+      tc_fence_after();
+      for (int mt = MTX + hf; mt < NMT; mt += 2) emit_tile(mt);
+      // the unit rows run on the tensor pipe while the x-row owners wait for their blocks (tcgen05.ld of the x tiles
+      // would otherwise queue behind these MMAs)
+      // issued by warps 4-7: the issuing thread blocks while the pipe's queue is full, and warps 0-1 hold the x-row reduce
+      if (lane == 0 && w >= 4) {
+        tc_fence_after();
+        const uint64_t db0 = umma_desc_nosw(bop_local, NB * 16, 128);
+        for (int kk = 0; kk < 8; ++kk) {
+          for (int mt = w - 4; mt < MTX; mt += 4) {
+            if (mt < BT_TMEM) tc_mma_ts(tmem_d + mt * NB, tmem + (uint32_t)(mt * 64 + kk * 8), db0 + (uint64_t)(kk * 2 * NB), idesc, kk ? 1u : 0u);
+            else tc_mma(tmem_d + mt * NB, umma_desc_nosw(as_local + (uint32_t)(mt - BT_TMEM) * 32768 + kk * 4096, 2048, 128),
+                        db0 + (uint64_t)(kk * 2 * NB), idesc, kk ? 1u : 0u);
+          }
+        }
+        tc_commit(mma_done);
+      }
+      ck.lap(0);
+    }
+    // ---- owners of the x rows: dx_pre = sum of the nsl incoming blocks, dpx_t, publish
+    const uint2* inb = LLp + ((size_t)slot * gm.ngroups + grp) * nsl * MR * 8;
+    if (tid < np * 8) {
+      float s0 = 0.f, s1 = 0.f;
+      if (s > 0) {
+        const uint2* p = inb + (size_t)(H + p0 + rr) * 8 + sp;
+        uint2 v[32];
+        unsigned pending = nsl >= 32 ? 0xffffffffu : ((1u << nsl) - 1u);
+        while (pending) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (pending & (1u << i)) v[i] = ll_load2(p + (size_t)i * MR * 8);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if ((pending & (1u << i)) && v[i].y == tag) pending &= ~(1u << i);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < nsl) { s0 += __uint_as_float(v[i].x << 16); s1 += __uint_as_float(v[i].x & 0xffff0000u); }
+      }
+      const float dv[2] = {(dxe[0] + s0) * (1.f - xo[0] * xo[0]), (dxe[1] + s1) * (1.f - xo[1] * xo[1])};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int b = b0 + 2 * sp + e;
+        ll_store2(LLd + ((size_t)slot * Bpad + b) * F + p0 + rr, __float_as_uint(dv[e]), tag);
+        if (b < B) {
+          d.dpx[(b * (int64_t)Tcap + t) * FP + p0 + rr] = dv[e];
+          if (dp16) dp16[(b * (int64_t)Tcap + t) * FP + p0 + rr] = __float2bfloat16(dv[e]);
+        }
+      }
+    }
+    if (owns_last && tid < NB && b0 + tid < B) {
+      float* qd = d.dpx + ((b0 + tid) * (int64_t)Tcap + t) * FP;
+      qd[F] = dsv;
+      for (int p = F + 1; p < FP; ++p) qd[p] = 0.f;
+      if (dp16) {
+        __nv_bfloat16* q16 = dp16 + ((b0 + tid) * (int64_t)Tcap + t) * FP;
+        q16[F] = __float2bfloat16(dsv);
+        for (int p = F + 1; p < FP; ++p) q16[p] = __float2bfloat16(0.f);
+      }
+    }
+    if (tid < NB) dpxs[tid * WLD + F] = __float2bfloat16(dsv);
+    ck.lap(1);
+    if (s > 0) {
+      mbar_wait(mma_done, nmma & 1u);
+      ++nmma;
+      tc_fence_after();
+      for (int mt = hf; mt < MTX; mt += 2) emit_tile(mt);
+      tc_fence_before();
+    }
+    ck.lap(2);
+    // ---- every CTA: dh_pre of its 32 units
+    {
+      float s0 = 0.f, s1 = 0.f;
+      if (s > 0) {
+        const uint2* p = inb + (size_t)(j0 + rr) * 8 + sp;
+        uint2 v[32];
+        unsigned pending = nsl >= 32 ? 0xffffffffu : ((1u << nsl) - 1u);
+        while (pending) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (pending & (1u << i)) v[i] = ll_load2(p + (size_t)i * MR * 8);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if ((pending & (1u << i)) && v[i].y == tag) pending &= ~(1u << i);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < nsl) { s0 += __uint_as_float(v[i].x << 16); s1 += __uint_as_float(v[i].x & 0xffff0000u); }
+      }
+      dhs[(2 * sp) * 33 + rr] = s0;
+      dhs[(2 * sp + 1) * 33 + rr] = s1;
+    }
+    ck.lap(3);
+    // ---- dpx_t [NB, F] of the batch group -> shared memory (bf16)
+    {
+      const uint2* src = LLd + ((size_t)slot * Bpad + b0) * F;
+      constexpr int XC = 2;
+      for (int base = 0; base < NB * (F / 8); base += LT * XC) {
+        uint4 v[XC][4];
+        unsigned pending = 0;
+#pragma unroll
+        for (int i = 0; i < XC; ++i)
+          if (base + i * LT + tid < NB * (F / 8)) pending |= 1u << i;
+        while (pending) {
+#pragma unroll
+          for (int i = 0; i < XC; ++i) {
+            if (pending & (1u << i)) {
+              const int idx = base + i * LT + tid, b = idx / (F / 8), c = idx - b * (F / 8);
+              const uint2* p = src + (size_t)b * F + c * 8;
+              v[i][0] = ll_load4(p); v[i][1] = ll_load4(p + 2); v[i][2] = ll_load4(p + 4); v[i][3] = ll_load4(p + 6);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < XC; ++i) {
+            if (pending & (1u << i)) {
+              bool ok = true;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) ok = ok && v[i][e].y == tag && v[i][e].w == tag;
+              if (ok) {
+                const int idx = base + i * LT + tid, b = idx / (F / 8), c = idx - b * (F / 8);
+                *reinterpret_cast<uint4*>(dpxs + (size_t)b * WLD + c * 8) = make_uint4(
+                    pack_bf16(__uint_as_float(v[i][0].x), __uint_as_float(v[i][0].z)), pack_bf16(__uint_as_float(v[i][1].x), __uint_as_float(v[i][1].z)),
+                    pack_bf16(__uint_as_float(v[i][2].x), __uint_as_float(v[i][2].z)), pack_bf16(__uint_as_float(v[i][3].x), __uint_as_float(v[i][3].z)));
+                pending &= ~(1u << i);
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- dh += [wp ; ws]^T dpx_t for the CTA's own units: mma.sync m16n8k16, warp = (m-tile, n-tile, k half)
+    {
+      const int g8 = lane >> 2, tq = lane & 3, mtile = w & 1, ntile = (w >> 1) & 1, kh = w >> 2;
+      const int nks2 = FP / 16, k_lo = kh * ((nks2 + 1) / 2), k_hi = min(nks2, k_lo + (nks2 + 1) / 2);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const __nv_bfloat16* ar = WpT + (size_t)(mtile * 16 + g8) * WLD + 2 * tq;
+      const __nv_bfloat16* br = dpxs + (size_t)(ntile * 8 + g8) * WLD + 2 * tq;
+      for (int ks = k_lo; ks < k_hi; ++ks) {
+        uint32_t a[4];
+        a[0] = *reinterpret_cast<const uint32_t*>(ar + ks * 16);
+        a[1] = *reinterpret_cast<const uint32_t*>(ar + 8 * WLD + ks * 16);
+        a[2] = *reinterpret_cast<const uint32_t*>(ar + ks * 16 + 8);
+        a[3] = *reinterpret_cast<const uint32_t*>(ar + 8 * WLD + ks * 16 + 8);
+        mma_bf16_16816(acc, a, *reinterpret_cast<const uint32_t*>(br + ks * 16), *reinterpret_cast<const uint32_t*>(br + ks * 16 + 8));
+      }
+      const int u0 = mtile * 16 + g8, c0 = ntile * 8 + 2 * tq;
+      atomicAdd(&dhs[c0 * 33 + u0], acc[0]);
+      atomicAdd(&dhs[(c0 + 1) * 33 + u0], acc[1]);
+      atomicAdd(&dhs[c0 * 33 + u0 + 8], acc[2]);
+      atomicAdd(&dhs[(c0 + 1) * 33 + u0 + 8], acc[3]);
+    }
+    __syncthreads();
+    ck.lap(4);
+    // ---- cell backward for (sample bl, units jv, jv + 1)
+    {
+      const float gi[2] = {pg[0].x, pg[0].y}, gf[2] = {pg[1].x, pg[1].y}, gg[2] = {pg[2].x, pg[2].y}, go[2] = {pg[3].x, pg[3].y};
+      const float cc[2] = {pc.x, pc.y}, cp[2] = {pcp.x, pcp.y};
+      float o[4][2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float dht = dhs[bl * 33 + jv + e];
+        const float tch = tanh_approx(cc[e]);                  // the function the forward applied
+        const float dc = dcs[e] + dht * go[e] * (1.f - tch * tch);
+        dcs[e] = dc * gf[e];
+        o[0][e] = dc * gg[e] * gi[e] * (1.f - gi[e]);
+        o[1][e] = dc * cp[e] * gf[e] * (1.f - gf[e]);
+        o[2][e] = dc * gi[e] * (1.f - gg[e] * gg[e]);
+        o[3][e] = dht * tch * go[e] * (1.f - go[e]);
+      }
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const uint32_t pk = pack_bf16(o[qq][0], o[qq][1]);
+        const int lr = qq * 32 + jv;
+        *reinterpret_cast<uint32_t*>(Bop + (lr >> 3) * (NB * 16) + bl * 16 + (lr & 7) * 2) = pk;
+        if (bme < B) {
+          const int64_t off = bme * gstr + (int64_t)t * 4 * H + qq * H + j0 + jv;
+          *reinterpret_cast<float2*>(d.dgates + off) = make_float2(o[qq][0], o[qq][1]);
+          if (dg16) *reinterpret_cast<uint32_t*>(dg16 + off) = pk;
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    ck.lap(5);
+  }
+  if (d.dbg && tid == 0) {
+    long long* qd = d.dbg + (int64_t)blockIdx.x * 8;
+    for (int i = 0; i < 7; ++i) qd[i] = ck.acc[i];
+    qd[7] = clock64() - tstart;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (w == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------- host side
 static size_t fwd_smem(const ag_lstm_desc* d, const FwdGeom& g, int NB) {
   return 1024 + (size_t)((g.KP - g.KT) / 8) * 2048 + (size_t)(g.KP / 8) * (NB * 16 + 16) + (size_t)16 * (d->H + 8) * 2 +
@@ -584,6 +978,39 @@ int gen_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
   AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   AG_CUDA(cudaMemsetAsync(d->ll_ws, 0, ll_need, s));                  // tags: step numbers start at 1
   AG_CUDA(cudaMemsetAsync(d->t_end, 0, sizeof(int), s));
+  ag_lstm_desc dd = *d;
+  void* args[2] = {&dd, &g};
+  AG_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)(g.ngroups * g.nsl)), dim3(LT), args, smem, s));
+  *launched = 1;
+  return AG_OK;
+}
+
+
+static size_t bwd_smem(const ag_lstm_desc* d, const BwdGeom& g) {
+  const int NMT = (g.MR + 127) / 128, WLD = g.FP + 8;
+  return 1024 + (size_t)(NMT - BT_TMEM) * 32768 + 16 * BNB * 16 + (size_t)(UPC + BNB) * WLD * 2 + (size_t)(BNB * 33) * 4 + 64;
+}
+
+int gen_bwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
+  *launched = 0;
+  if (d->F <= 0 || d->ndir != 1 || d->prec < 1 || !(d->reserved2 & 2) || (d->reserved2 & 1)) return AG_OK;
+  if (d->H % 128 != 0 || d->F % 8 != 0 || !d->ll_ws || d->len || d->dh_ext) return AG_OK;
+  BwdGeom g;
+  g.nsl = d->H / UPC;
+  g.ngroups = (d->B + BNB - 1) / BNB;
+  if (g.nsl > 32 || g.ngroups * g.nsl > sm_count()) return AG_OK;
+  g.MR = d->H + d->F;
+  g.FP = (d->F + 1 + 7) / 8 * 8;
+  g.PR = (d->F + g.nsl - 1) / g.nsl;
+  const int NMT = (g.MR + 127) / 128;
+  if (g.PR * 8 > LT || NMT <= BT_TMEM || BT_TMEM * 64 + NMT * BNB > 512 || g.FP % 16 != 0) return AG_OK;
+  const size_t ll_need = ((size_t)2 * g.ngroups * g.nsl * g.MR * 8 + (size_t)2 * g.ngroups * BNB * d->F + 32) * 8;
+  if ((size_t)d->ll_ws_bytes < ll_need) return AG_OK;
+  const size_t smem = bwd_smem(d, g);
+  if (smem > (size_t)smem_optin() || smem < (size_t)116 * 1024) return AG_OK;
+  const void* kern = (const void*)lstm_gen_bwd_kernel;
+  AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  AG_CUDA(cudaMemsetAsync(d->ll_ws, 0, ll_need, s));
   ag_lstm_desc dd = *d;
   void* args[2] = {&dd, &g};
   AG_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)(g.ngroups * g.nsl)), dim3(LT), args, smem, s));

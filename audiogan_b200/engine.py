@@ -162,9 +162,13 @@ class _GenFn(torch.autograd.Function):
         misc = torch.zeros(16, device=dev, dtype=torch.int32)
         dgates16 = torch.empty(B, Tcap, 4 * H, device=dev, dtype=torch.bfloat16) if bf else None
         dpx16 = torch.empty(B, Tcap, FP, device=dev, dtype=torch.bfloat16) if bf else None
+        # reduce-scatter workspace of the TMEM-resident BPTT kernel (include/audiogan_b200.h: ag_lstm_desc.ll_ws)
+        ngr = (B + 15) // 16
+        ll_ws = torch.empty((2 * ngr * (H // 32) * (H + F) * 8 + 2 * ngr * 16 * F + 32) * 8, device=dev, dtype=torch.uint8) if bf else None
         K.lstm_bwd(B=B, T=T, Tcap=Tcap, H=H, ndir=1, F=F, gates=gates, cbuf=cbuf, xbuf=xbuf, dx_ext=dx_ext,
                    ds_ext=ds_ext, dgates=dgates, dpx=dpx, w1t=plan.Poff("w1t"), wxt=plan.Poff("wxt"), barrier=misc,
-                   prec=plan.lstm_prec if bf else 0, dgates16=dgates16, dpx16=dpx16)
+                   prec=plan.lstm_prec if bf else 0, dgates16=dgates16, dpx16=dpx16, reserved2=plan.lstm_flags | 2,
+                   ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel() if bf else 0)
         # in bf16 mode the batched GEMMs read the kernels' bf16 shadow copies (half the operand traffic)
         dgo, hbo, xbo, dpo = (dgates16, hbuf16, xbuf16, dpx16) if bf else (dgates, hbuf, xbuf, dpx)
         if wgrad:

@@ -407,7 +407,27 @@ def test_lstm_generator_tmem_kernel_tracks_fp32_kernel(B, Tn, stops):
         T.cuda.synchronize()
         if dbg is not None:
             assert int((dbg[:, 7] > 0).sum()) > 0, "the TMEM-resident kernel did not run"
-        out[name] = dict(h=hbuf, x=xbuf, s=sbuf, gates=gates, c=cbuf, stop=stop, glen=glen, t_end=int(misc[8].item()), x16=xbuf16)
+            dbg.zero_()
+        te_ = int(misc[8].item())
+        # BPTT over the steps that ran (audiogan.py:437-444 through autograd in the reference)
+        FP = (Fr + 1 + 7) // 8 * 8
+        if name == "fp32":
+            w1t = T.cat([w1[0, :, :H].t(), w2[:Fr].t(), w2[Fr:].t(), T.zeros(H, FP - Fr - 1, device=dev)], 1).contiguous()
+            wxt = w1[0, :, H:].t().contiguous()
+            dx_ext, ds_ext = T.randn(B, Tn, Fr, device=dev), T.randn(B, Tn, device=dev)
+        dgates, dpx = T.zeros(B, Tn, 4 * H, device=dev), T.zeros(B, Tn, FP, device=dev)
+        dgates16 = T.zeros(B, Tn, 4 * H, device=dev, dtype=T.bfloat16) if prec else None
+        dpx16 = T.zeros(B, Tn, FP, device=dev, dtype=T.bfloat16) if prec else None
+        ngr = (B + 15) // 16
+        ll_wb = T.empty((2 * ngr * (H // 32) * (H + Fr) * 8 + 2 * ngr * 16 * Fr + 32) * 8, device=dev, dtype=T.uint8)
+        Kn.lstm_bwd(B=B, T=te_, Tcap=Tn, H=H, ndir=1, F=Fr, gates=gates, cbuf=cbuf, xbuf=xbuf, dx_ext=dx_ext, ds_ext=ds_ext,
+                    dgates=dgates, dpx=dpx, w1t=w1t, wxt=wxt, barrier=T.zeros(1024, dtype=T.int32, device=dev), prec=prec,
+                    reserved2=flags, dgates16=dgates16, dpx16=dpx16, dbg=dbg, ll_ws=ll_wb, ll_ws_bytes=ll_wb.numel())
+        T.cuda.synchronize()
+        if dbg is not None and B <= 64:
+            assert int((dbg[:, 7] > 0).sum()) > 0, "the TMEM-resident BPTT kernel did not run"
+        out[name] = dict(h=hbuf, x=xbuf, s=sbuf, gates=gates, c=cbuf, stop=stop, glen=glen, t_end=te_, x16=xbuf16,
+                         dgates=dgates, dpx=dpx, dgates16=dgates16)
     f, c = out["fp32"], out["tmem"]
     te = f["t_end"]
     assert c["t_end"] == te and (not stops or te < Tn or B < 20)
@@ -417,3 +437,6 @@ def test_lstm_generator_tmem_kernel_tracks_fp32_kernel(B, Tn, stops):
     for nm in ("s", "gates", "c"):
         assert rel(c[nm][:, :te], f[nm][:, :te]) < 2e-2, nm
     assert rel(c["x16"][:, :te + 1].float(), c["x"][:, :te + 1]) < 1e-2
+    for nm in ("dgates", "dpx"):
+        assert rel(c[nm][:, :te], f[nm][:, :te]) < 3e-2, nm
+    assert rel(c["dgates16"][:, :te].float(), c["dgates"][:, :te]) < 1e-2

@@ -55,11 +55,13 @@ def run(H, B, Tn, Fr=200, stops=False, time_it=True, bwd=True):
             dpx16 = T.zeros(B, Tn, FP, device=dev, dtype=T.bfloat16) if prec else None
             dbg.zero_()
             misc2 = T.zeros(1024, dtype=T.int32, device=dev)
+            ngr = (B + 15) // 16
+            ll_wb = T.empty((2 * ngr * (H // 32) * (H + Fr) * 8 + 2 * ngr * 16 * Fr + 32) * 8, device=dev, dtype=T.uint8)
             e[1].record()
             if bwd:
                 Kn.lstm_bwd(B=B, T=t_end, Tcap=Tn, H=H, ndir=1, F=Fr, gates=gates, cbuf=cbuf, xbuf=xbuf, dx_ext=dx_ext, ds_ext=ds_ext,
                             dgates=dgates, dpx=dpx, w1t=w1t, wxt=wxt, barrier=misc2, prec=prec, reserved2=flags, dgates16=dgates16,
-                            dpx16=dpx16, dbg=dbg if name == "tmem" else None)
+                            dpx16=dpx16, dbg=dbg if name == "tmem" else None, ll_ws=ll_wb, ll_ws_bytes=ll_wb.numel())
             e[2].record()
             T.cuda.synchronize()
             dbw = dbg.cpu().float().clone()
@@ -70,7 +72,7 @@ def run(H, B, Tn, Fr=200, stops=False, time_it=True, bwd=True):
             name, H, B, Tn, stops, tf, tf * 1e3 / max(t_end, 1), tb, tb * 1e3 / max(t_end, 1), t_end), flush=True)
         if name == "tmem":
             for nm, dd, labels in (("fwd", dfw, "x-exchange, mma-x+wait, tmem-ld+cell+LL-store, stores+prefetch, h-exchange, phase2+LL-store, -"),
-                                   ("bwd", dbw, "phases")):
+                                   ("bwd", dbw, "mma-x+emit x tiles, x-rows reduce+dpx, wait mma+emit unit tiles, unit reduce, dpx read+wp^T dpx, cell, -")):
                 used = dd[:, 7] > 0
                 if used.sum() == 0:
                     print("    %s: TMEM-resident kernel did not run (fallback)" % nm)
