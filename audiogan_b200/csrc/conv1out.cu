@@ -55,21 +55,25 @@ __global__ void __launch_bounds__(128) conv1out_dgrad_kernel(const float* __rest
   }
 }
 
-// dw[j*C + c] += sum_{b,t} g[b,t] * X[b, t+j, c];  dw[k*C] += sum g.   Thread = 4 channels; every X element is read once.
+// dw[j*C + c] += sum_{b,t} g[b,t] * X[b, t+j, c];  dw[k*C] += sum g.   Thread = (4 channels, row lane): the block's 4 warps
+// walk interleaved rows (4 independent load streams per block instead of one); every X element is read once.
 template <int KMAX>
 __global__ void __launch_bounds__(128) conv1out_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ X,
                                                              int64_t x_bs, int C, int k, float* __restrict__ dw, int64_t T,
                                                              int rows_per_block) {
-  const int c4 = threadIdx.x;
+  const int c4 = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int64_t b = blockIdx.y;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(T + k - 1, r0 + rows_per_block);   // X rows
   const float* gb = g + b * T;
-  if (c4 * 4 < C) {
+  for (int cb = 0; cb * 128 < C; ++cb) {               // 32 channel groups (128 channels) per pass
+    const int cc = min(cb * 128 + 4 * c4, C - 4);      // lanes past C redo the last group (no divergent barriers); not added
+    const bool live = cb * 128 + 4 * c4 < C;
     float4 acc[KMAX];
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t r = r0; r < r1; ++r) {
-      const float4 x = __ldg(reinterpret_cast<const float4*>(X + b * x_bs + r * C + 4 * c4));
+#pragma unroll 2
+    for (int64_t r = r0 + rl; r < r1; r += 4) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(X + b * x_bs + r * C + cc));
 #pragma unroll
       for (int j = 0; j < KMAX; ++j) {
         const int64_t t = r - j;                       // X row r is tap j of output t = r - j
@@ -77,14 +81,28 @@ __global__ void __launch_bounds__(128) conv1out_wgrad_kernel(const float* __rest
         acc[j].x += gv * x.x; acc[j].y += gv * x.y; acc[j].z += gv * x.z; acc[j].w += gv * x.w;
       }
     }
+    // the 4 row lanes meet in shared memory: same-address L2 atomics serialise, so one set per block, not per warp
+    __shared__ float4 red[3][KMAX][32];
+    if (rl > 0) {
 #pragma unroll
-    for (int j = 0; j < KMAX; ++j) {
-      if (j < k) {
-        float* q = dw + j * C + 4 * c4;
-        atomicAdd(q, acc[j].x); atomicAdd(q + 1, acc[j].y); atomicAdd(q + 2, acc[j].z); atomicAdd(q + 3, acc[j].w);
+      for (int j = 0; j < KMAX; ++j) red[rl - 1][j][c4] = acc[j];
+    }
+    __syncthreads();
+    if (rl == 0 && live) {
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        if (j < k) {
+          float4 a = acc[j];
+#pragma unroll
+          for (int o = 0; o < 3; ++o) { const float4 v = red[o][j][c4]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+          float* q = dw + j * C + cc;
+          atomicAdd(q, a.x); atomicAdd(q + 1, a.y); atomicAdd(q + 2, a.z); atomicAdd(q + 3, a.w);
+        }
       }
     }
-  } else if (c4 * 4 == ((C + 3) / 4) * 4) {            // one spare thread: the bias gradient over this block's outputs
+    __syncthreads();
+  }
+  if (threadIdx.x == 127) {                            // the bias gradient over this block's outputs
     float s = 0.f;
     for (int64_t t = r0; t < min(T, r0 + (int64_t)rows_per_block); ++t) s += gb[t];
     atomicAdd(dw + k * C, s);
@@ -126,7 +144,7 @@ int ag_conv1out_wgrad(const float* g, const float* X, int64_t x_bs, int64_t C, i
   AG_CHECK_ARG(g && X && dw && B > 0 && B < 65536 && T > 0 && C > 0 && C % 4 == 0 && C <= 508 && k > 0 && k <= 4 && x_bs % 4 == 0,
                "ag_conv1out_wgrad: bad args");
   AG_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0, "ag_conv1out_wgrad: unaligned");
-  const int rpb = 256;
+  const int rpb = 1024;
   dim3 grid((unsigned)((T + k - 1 + rpb - 1) / rpb), (unsigned)B);
   conv1out_wgrad_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(g, X, x_bs, (int)C, k, dw, T, rpb);
   AG_LAUNCH_CHECK();
