@@ -295,13 +295,17 @@ class _DiscTailFn(torch.autograd.Function):
                    len=nfr, barrier=misc, prec=plan.lstm_prec if bf else 0, hbuf16=hbuf16, reserved2=plan.lstm_flags)
         # residual_net + classifier on the (B*Tm) rows (audiogan.py:547-549); same row geometry as hbuf
         geo = (Tm, (Tm + 2) * S, S)
-        r1 = _empty(B, Tm + 2, S, device=dev)
-        r2 = _empty(B, Tm + 2, S, device=dev)
-        K.gemm_nt(B * Tm, S, S, (hbuf, S), geo, plan.Poff("r0.w"), S, (r1, S), geo, bias=plan.Poff("r0.b"),
-                  skip=(hbuf, S), act=1)
+        # bf16 mode: the tail's activations live in HBM as bf16 (they only feed tensor-core GEMMs, whose throughput is
+        # set by operand bytes per FLOP: profiles/r1_gemm_notes.txt); fp32 accumulation and fp32 logits
+        adt = torch.bfloat16 if bf else torch.float32
+        hin = hbuf16 if bf else hbuf
+        r1 = torch.empty(B, Tm + 2, S, device=dev, dtype=adt)
+        r2 = torch.empty(B, Tm + 2, S, device=dev, dtype=adt)
+        K.gemm_nt(B * Tm, S, S, (hin, S), geo, plan.Poff("r0.w"), S, (r1, S), geo, bias=plan.Poff("r0.b"),
+                  skip=(hin, S), act=1)
         K.gemm_nt(B * Tm, S, S, (r1, S), geo, plan.Poff("r1.w"), S, (r2, S), geo, bias=plan.Poff("r1.b"),
                   skip=(r1, S), act=1)
-        h3 = _empty(B * Tm, S // 2, device=dev)
+        h3 = torch.empty(B * Tm, S // 2, device=dev, dtype=adt)
         K.gemm_nt(B * Tm, S // 2, S, (r2, S), geo, plan.Poff("k0.w"), S, h3, (B * Tm, 0, S // 2), bias=plan.Poff("k0.b"), act=1)
         logits = _empty(B, Tm, device=dev)
         K.gemm_nt(B * Tm, 1, S // 2, h3, (B * Tm, 0, S // 2), plan.Poff("k2.w"), S // 2, logits, (B * Tm, 0, 1),
@@ -327,18 +331,20 @@ class _DiscTailFn(torch.autograd.Function):
         flat = lambda n: (M, 0, n)
         if wgrad:
             K.gemm_tn(M, 1, S // 2, g, flat(1), h3, flat(S // 2), plan.GPoff("k2.w"), S // 2 + 1, ones_col=True)
-        dh3 = _empty(M, S // 2, device=dev)
+        adt = torch.bfloat16 if bf else torch.float32
+        hin = hbuf16 if bf else hbuf
+        dh3 = torch.empty(M, S // 2, device=dev, dtype=adt)
         K.gemm_nt(M, S // 2, 1, g, flat(1), plan.Poff("k2.w"), 1, dh3, flat(S // 2), dact=h3)
         if wgrad:
             K.gemm_tn(M, S // 2, S, dh3, flat(S // 2), (r2, S), geo, plan.GPoff("k0.w"), S + 1, ones_col=True)
-        dz2 = _empty(B, Tm + 2, S, device=dev)           # grads below keep the padded-row geometry of r1 / r2 / hbuf
+        dz2 = torch.empty(B, Tm + 2, S, device=dev, dtype=adt)   # grads below keep the padded-row geometry of r1 / r2 / hbuf
         K.gemm_nt(M, S, S // 2, dh3, flat(S // 2), plan.Poff("k0.wt"), S // 2, (dz2, S), geo, dact=(r2, S))
         if wgrad:
             K.gemm_tn(M, S, S, (dz2, S), geo, (r1, S), geo, plan.GPoff("r1.w"), S + 1, ones_col=True)
-        dz1 = _empty(B, Tm + 2, S, device=dev)
+        dz1 = torch.empty(B, Tm + 2, S, device=dev, dtype=adt)
         K.gemm_nt(M, S, S, (dz2, S), geo, plan.Poff("r1.wt"), S, (dz1, S), geo, skip=(dz2, S), dact=(r1, S))
         if wgrad:
-            K.gemm_tn(M, S, S, (dz1, S), geo, (hbuf, S), geo, plan.GPoff("r0.w"), S + 1, ones_col=True)
+            K.gemm_tn(M, S, S, (dz1, S), geo, (hin, S), geo, plan.GPoff("r0.w"), S + 1, ones_col=True)
         dh_ext = _empty(B, Tm + 2, S, device=dev)
         K.gemm_nt(M, S, S, (dz1, S), geo, plan.Poff("r0.wt"), S, (dh_ext, S), geo, skip=(dz1, S))
         # BPTT through both directions
