@@ -112,6 +112,8 @@ _PROTOS = {
 _PROTOS.update({
     "ag_gemm_nt_tc": [C.POINTER(GemmDesc), vp],
     "ag_gemm_tn_tc": [C.POINTER(GemmDesc), vp, i64, i32, vp],
+    "ag_gemm_dbg_enable": [i32],
+    "ag_gemm_dbg_read": [vp],
 })
 _OPTIONAL = {}
 

@@ -17,7 +17,12 @@
 namespace ag {
 namespace tc {
 
+// profiling aid (ag_gemm_dbg_*): per-phase cycle totals over all CTAs of the NT kernel, off unless enabled
+__device__ unsigned long long g_nt_dbg[16];
+__device__ int g_nt_dbg_on = 0;
+
 constexpr int BM = 128, BK = 64, NTHREADS = 160, NPROD = 128;
+constexpr int NT_THREADS = 192;      // NT kernel: + warp 5 = TMA issuer for the B tiles
 
 // Column c of a row: element offset (c / inner) * outer_stride + c % inner (32-bit division: columns < 2^31).
 __device__ __forceinline__ int64_t col_off(int64_t c, int64_t inner, int64_t outer_stride) {
@@ -132,7 +137,7 @@ __device__ __forceinline__ float4 ld4_any(const void* p, int64_t i, int dtype) {
 }
 
 template <int BN, int MODE, bool VECC>
-__global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_tc_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap mapB) {
+__global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap mapB) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int STG = nt_stages(BN);
   // 1024-byte alignment for the 128B-swizzled tiles (pointer arithmetic on the __shared__ array keeps LDS/STS)
@@ -189,10 +194,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_tc_kernel(const ag_gemm_d
       cols_of(0, cc);
       ld.issue(d.A, ro, cc, d.K, d.a_kin, d.a_k1s);
     }
+    const bool dbg = g_nt_dbg_on != 0 && tid == 0;
+    long long t_get = 0, t_empty = 0, t_store = 0, t0 = 0;
+    const long long t_begin = clock64();
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STG;
       const uint32_t ph = (kb / STG) & 1;
       uint4 ch[8];
+      if (dbg) t0 = clock64();
       if (MODE != 2) {
         ld.get(ch);                                   // stage kb has landed (or we wait for it here)
         if (kb + 1 < nkb) {                           // put stage kb+1 in flight before touching shared memory
@@ -205,12 +214,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_tc_kernel(const ag_gemm_d
         cols_of(kb, cc);
         load_chunks<2, 8>(ch, d.A, d.a_dtype, ro, cc, d.K, d.a_kin, d.a_k1s, -1);
       }
+      if (dbg) { asm volatile("" :: "r"(ch[0].x), "r"(ch[7].w)); const long long t1 = clock64(); t_get += t1 - t0; t0 = t1; }
       mbar_wait(&empty[s], ph ^ 1);
+      if (dbg) { const long long t1 = clock64(); t_empty += t1 - t0; t0 = t1; }
       uint8_t* sa = smem + s * STAGE_BYTES;
-      if (tid == 0) {
-        mbar_arrive_expect_tx(&full[s], B_BYTES);
-        tma_load_2d(sa + A_BYTES, &mapB, &full[s], kb * BK, n0);
-      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int cid = i * NPROD + tid;
@@ -220,7 +227,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_tc_kernel(const ag_gemm_d
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
+      if (dbg) { const long long t1 = clock64(); t_store += t1 - t0; }
     }
+    const long long t_main = clock64();
     // ------------------------------------------------------------------ epilogue
     // TMEM lane = output row.  Each warp transposes 32x32 blocks through shared memory (the pipeline stages are idle
     // by now) so that a warp instruction covers contiguous columns of a row: coalesced (vector) stores and reads.
@@ -342,13 +351,40 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_tc_kernel(const ag_gemm_d
       __syncwarp();
     }
     tc_fence_before();
+    if (dbg) {
+      const long long t_end = clock64();
+      atomicAdd(&g_nt_dbg[0], 1ull);
+      atomicAdd(&g_nt_dbg[1], (unsigned long long)t_get);
+      atomicAdd(&g_nt_dbg[2], (unsigned long long)t_empty);
+      atomicAdd(&g_nt_dbg[3], (unsigned long long)t_store);
+      atomicAdd(&g_nt_dbg[4], (unsigned long long)(t_main - t_begin));
+      atomicAdd(&g_nt_dbg[5], (unsigned long long)(t_end - t_main));
+      atomicAdd(&g_nt_dbg[6], (unsigned long long)nkb);
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ TMA issuer for the B (weight) tiles: its own
+    // thread, so a tile's TMA latency starts the moment the slot is free instead of after the producers' global loads
+    // of the same k-block have landed (the two latencies used to add up on the per-k-block critical path)
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STG;
+        mbar_wait(&empty[s], ((kb / STG) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], B_BYTES);
+        tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &mapB, &full[s], kb * BK, n0);
+      }
+    }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(BM, BN, 0, 0);
+      const bool dbgm = g_nt_dbg_on != 0;
+      long long t_full = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STG;
+        const long long q0 = dbgm ? clock64() : 0;
         mbar_wait(&full[s], (kb / STG) & 1);
+        if (dbgm) t_full += clock64() - q0;
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
         const uint64_t da = umma_desc(sa, 16, 1024), db = umma_desc(sa + A_BYTES, 16, 1024);
@@ -358,6 +394,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_nt_tc_kernel(const ag_gemm_d
         tc_commit(&empty[s]);
       }
       tc_commit(tmem_full);
+      if (dbgm) atomicAdd(&g_nt_dbg[7], (unsigned long long)t_full);
     }
     __syncwarp();
   }
@@ -411,7 +448,7 @@ static int launch_nt2(const ag_gemm_desc* d, cudaStream_t s) {
   auto kern = gemm_nt_tc_kernel<BN, MODE, VECC>;
   AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((unsigned)((d->M + BM - 1) / BM), (unsigned)((d->N + BN - 1) / BN));
-  kern<<<grid, NTHREADS, smem, s>>>(*d, mapB);
+  kern<<<grid, NT_THREADS, smem, s>>>(*d, mapB);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
@@ -663,4 +700,17 @@ int ag_gemm_tn_tc(const ag_gemm_desc* d, float* dw, int64_t ldw, int32_t ones_co
   if (ktot > 64) return tc::launch_tn<128>(d, dw, ldw, ones_col, vy, va, s);
   return tc::launch_tn<64>(d, dw, ldw, ones_col, vy, va, s);
 }
+}
+
+// profiling aid: enable/reset (on != 0) the NT kernel's phase counters, read them back (16 values)
+extern "C" int ag_gemm_dbg_enable(int on) {
+  unsigned long long z[16] = {0};
+  AG_CUDA(cudaMemcpyToSymbol(ag::tc::g_nt_dbg, z, sizeof(z)));
+  AG_CUDA(cudaMemcpyToSymbol(ag::tc::g_nt_dbg_on, &on, sizeof(int)));
+  return AG_OK;
+}
+extern "C" int ag_gemm_dbg_read(unsigned long long* out) {
+  AG_CUDA(cudaDeviceSynchronize());
+  AG_CUDA(cudaMemcpyFromSymbol(out, ag::tc::g_nt_dbg, 16 * sizeof(unsigned long long)));
+  return AG_OK;
 }

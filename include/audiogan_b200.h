@@ -80,6 +80,11 @@ int ag_gemm_tn_f32(const ag_gemm_desc* d, float* dw, int64_t ldw, int32_t ones_c
  * fp32 accumulation in TMEM.  Requires 16-byte aligned row strides. */
 int ag_gemm_nt_tc(const ag_gemm_desc* d, void* stream);
 int ag_gemm_tn_tc(const ag_gemm_desc* d, float* dw, int64_t ldw, int32_t ones_col, void* stream);
+/* Profiling aid for ag_gemm_nt_tc (tools/gemm_phases.py): enable (on != 0, also resets) / read 16 per-phase cycle
+ * totals summed over CTAs: [0] CTAs, [1] producer wait-for-loads, [2] wait-slot-free, [3] store+fence+arrive,
+ * [4] main loop, [5] epilogue, [6] k-blocks, [7] MMA thread wait-full. */
+int ag_gemm_dbg_enable(int on);
+int ag_gemm_dbg_read(unsigned long long* out16);
 
 /* ------------------------------------------------------------------------------------------
  * Persistent recurrent kernels (cooperative launch, one CTA per slice of hidden units, its
