@@ -525,8 +525,44 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
       uint8_t* sa = smem + s * STAGE_BYTES;
       uint8_t* sb = sa + A_BYTES;
       // Y^T: 64 rows x 16 chunks (two 64-wide n blocks); activation window: 64 rows x BNK/8 chunks
+      constexpr int NY = (RM * 16) / NPROD;
+      constexpr int CPR = BNK / 8;                          // chunks per row of the activation window
+      constexpr int NTOT = (RM * CPR) / NPROD;              // chunks per thread: 4 / 8 / 16
+      const bool edge = ones_at >= 0 && k0 + BNK > d.K;     // the chunk holding the ones column goes through the generic path
+      if (MODEY == 1 && MODEA == 1 && NTOT <= 16) {
+        // bf16 operands: 4 registers per chunk, so ALL loads of the stage (Y and the whole activation window) are in
+        // flight before the first shared-memory store -- one exposed global-load latency per stage instead of three
+        uint4 chy[NY], cha[NTOT];
+        int64_t ro[NY], cc[NY], roa[NTOT], cca[NTOT];
+#pragma unroll
+        for (int i = 0; i < NY; ++i) {
+          const int cid = i * NPROD + tid;
+          ro[i] = yo[s * RM + (cid >> 4)];
+          cc[i] = n0 + (cid & 15) * 8;
+        }
+#pragma unroll
+        for (int i = 0; i < NTOT; ++i) {
+          const int cid = i * NPROD + tid;
+          roa[i] = ao[s * RM + cid / CPR];
+          cca[i] = k0 + (cid % CPR) * 8;
+        }
+        load_chunks<1, NY>(chy, d.C, d.c_dtype, ro, cc, d.N, d.c_nin, d.c_n1s, -1);
+        if (edge) load_chunks<2, NTOT>(cha, d.A, d.a_dtype, roa, cca, d.K, d.a_kin, d.a_k1s, ones_at);
+        else load_chunks<1, NTOT>(cha, d.A, d.a_dtype, roa, cca, d.K, d.a_kin, d.a_k1s, ones_at);
+#pragma unroll
+        for (int i = 0; i < NY; ++i) {
+          const int cid = i * NPROD + tid;
+          const int r = cid >> 4, c = cid & 15;
+          *reinterpret_cast<uint4*>(sa + (c >> 3) * (RM * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = chy[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NTOT; ++i) {
+          const int cid = i * NPROD + tid;
+          const int r = cid / CPR, c = cid % CPR;
+          *reinterpret_cast<uint4*>(sb + (c >> 3) * (RM * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = cha[i];
+        }
+      } else {
       {
-        constexpr int NY = (RM * 16) / NPROD;
         uint4 ch[NY];
         int64_t ro[NY], cc[NY];
 #pragma unroll
@@ -543,8 +579,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
           *reinterpret_cast<uint4*>(sa + (c >> 3) * (RM * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = ch[i];
         }
       }
-      constexpr int CPR = BNK / 8;                          // chunks per row of the activation window
-      constexpr int NTOT = (RM * CPR) / NPROD;              // chunks per thread: 4 / 8 / 16
       constexpr int NA = NTOT < 8 ? NTOT : 8;
 #pragma unroll 1
       for (int i0 = 0; i0 < NTOT; i0 += NA) {
@@ -556,8 +590,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
           ro[i] = ao[s * RM + cid / CPR];
           cc[i] = k0 + (cid % CPR) * 8;
         }
-        // the chunk holding the ones column (and any straddling the end of K) goes through the generic path
-        if (MODEA != 2 && ones_at >= 0 && k0 + BNK > d.K)
+        if (MODEA != 2 && edge)
           load_chunks<2, NA>(ch, d.A, d.a_dtype, ro, cc, d.K, d.a_kin, d.a_k1s, ones_at);
         else
           load_chunks<MODEA, NA>(ch, d.A, d.a_dtype, ro, cc, d.K, d.a_kin, d.a_k1s, ones_at);
@@ -567,6 +600,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
           const int r = cid / CPR, c = cid % CPR;
           *reinterpret_cast<uint4*>(sb + (c >> 3) * (RM * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = ch[i];
         }
+      }
       }
       fence_proxy_async();
       __syncwarp();

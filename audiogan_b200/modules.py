@@ -181,7 +181,12 @@ class Generator(_PlanOwner):
         token = P.pack(plan)
         x, s, stop, glen = E._GenFn.apply(plan, self._struct, token, zc1, u_stop, self.early_exit_sync)
         stop_list = list(stop.long().unsqueeze(2).unbind(1))
-        return x, s, stop_list, glen.long() * self._frame_size
+        out_len = glen.long() * self._frame_size
+        if u_stop is None:
+            # no stop is ever drawn: every sample runs all frames.  The host copy rides along so that a following
+            # Discriminator.forward does not have to read the lengths back (the reference's tonumpy(length), :516)
+            out_len._ag_host = torch.full((batch_size,), nframes * self._frame_size, dtype=torch.int64)
+        return x, s, stop_list, out_len
 
 
 # =========================================================================================
@@ -215,7 +220,7 @@ class Discriminator(_PlanOwner):
         plan = self._get_plan()
         dev = plan.device
         B, L = x.shape
-        length_h = length.detach().to("cpu", torch.int64)           # host copy of the lengths (reference: tonumpy)
+        length_h = host_lengths(length)                              # host copy of the lengths (reference: tonumpy)
         lens_h, lens_d = [], []
         nf = length_h
         for _, s, _ in self._cnn_struct:                              # audiogan.py:533
@@ -234,6 +239,24 @@ class Discriminator(_PlanOwner):
 # =========================================================================================
 # helper functions the training loop calls (audiogan.py:172-253, :336-359)
 # =========================================================================================
+def host_lengths(length):
+    """int64 CPU copy of a lengths tensor.  CPU tensors and tensors that carry a host copy (Generator.forward without stop
+    sampling, cat_lengths) cost nothing; a bare CUDA tensor costs the device-to-host read the reference also pays."""
+    h = getattr(length, "_ag_host", None)
+    if h is not None:
+        return h
+    return length.detach().to("cpu", torch.int64)
+
+
+def cat_lengths(parts, device):
+    """torch.cat of lengths tensors on `device`, keeping a host copy when every part has one."""
+    hosts = [p if not p.is_cuda else getattr(p, "_ag_host", None) for p in parts]
+    out = torch.cat([p.to(device, non_blocking=True) for p in parts], 0)
+    if all(h is not None for h in hosts):
+        out._ag_host = torch.cat([h.to(torch.int64) for h in hosts], 0)
+    return out
+
+
 def length_mask(size, length):                                   # audiogan.py:204-211
     """1 where t < length[b]; built on the device (the reference fills it in a host loop and uploads it)."""
     dev = length.device if length.is_cuda else torch.device("cuda")

@@ -11,7 +11,7 @@ from torch.autograd.function import once_differentiable
 
 from . import kernels as K
 from . import _abi as A
-from .modules import (binary_cross_entropy_with_logits_per_sample, calc_dists, length_mask)  # noqa: F401
+from .modules import (binary_cross_entropy_with_logits_per_sample, calc_dists, length_mask, cat_lengths)  # noqa: F401
 
 _CHUNK = 65536
 
@@ -211,7 +211,7 @@ def _d_update_batched(g, d, opt_d, batch, clip, check, grad_sync):
         real = torch.nn.functional.pad(real, (0, L - Lr))
         fake = torch.nn.functional.pad(fake, (0, L - Lf))
     x = torch.cat([real, fake], 0)
-    lens = torch.cat([real_len.to(x.device), fake_len.to(x.device)], 0)
+    lens = cat_lengths([real_len, fake_len], x.device)
     c = torch.cat([batch["c_real"], batch["c_d2"]], 0)
     cls, _, _, nf = d(x, lens, c)
     cls_d, cls_g, nf = cls[:Bn], cls[Bn:], nf.to(cls.device)

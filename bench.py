@@ -170,8 +170,11 @@ def run_ours(args):
     sync = agd.GradSync(nbuckets=4) if world > 1 else None
 
     host = make_batches(torch, B, L, rank, 2, pinned=True)
-    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    # the per-sample lengths are host metadata (the reference carries them as numpy arrays and reads them on the host inside
+    # Discriminator.forward, audiogan.py:516): they stay CPU tensors, so no device-to-host read stalls the launch queue
+    on_dev = lambda h, **kw: {k: (v if k.endswith("_len") else v.to(dev, **kw)) for k, v in h.items()}
+    resident = [on_dev(h) for h in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for k, v in host[0].items() if not k.endswith("_len"))
 
     def step(di):
         di = dict(di)
@@ -222,7 +225,7 @@ def run_ours(args):
     d2h = [0]
 
     def e2e_step(i):
-        di = {k: v.to(dev, non_blocking=True) for k, v in host[i % 2].items()}
+        di = on_dev(host[i % 2], non_blocking=True)
         m1, m2 = step(di)
         res = torch.stack([m1["loss_d"], m1["loss_g"], m2["loss"]]).cpu()
         d2h[0] = res.numel() * res.element_size()
