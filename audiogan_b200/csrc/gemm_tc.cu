@@ -13,6 +13,7 @@
 #include "tc_common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace ag {
 namespace tc {
@@ -110,6 +111,36 @@ struct ChunkLoader {
       }
     }
   }
+  // column offsets (and their validity) computed by the caller, once: the producer warps are instruction-bound (one warp
+  // per scheduler and CTA), and col_off's division per chunk and stage was most of what they executed
+  __device__ __forceinline__ void issue_pre(const void* base, const int64_t (&roff)[NCH], const int32_t (&coff)[NCH], uint32_t cmask) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      ok[i] = roff[i] >= 0 && ((cmask >> i) & 1u);
+      const int64_t off = ok[i] ? roff[i] + coff[i] : 0;
+      if (MODE == 0) {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+        lo[i] = __ldg(p);
+        hi[i] = __ldg(p + 1);
+      } else {
+        raw[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off));
+      }
+    }
+  }
+  __device__ __forceinline__ void issue_col(const void* base, const int64_t (&roff)[NCH], int64_t coff, bool cok) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      ok[i] = roff[i] >= 0 && cok;
+      const int64_t off = ok[i] ? roff[i] + coff : 0;
+      if (MODE == 0) {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+        lo[i] = __ldg(p);
+        hi[i] = __ldg(p + 1);
+      } else {
+        raw[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off));
+      }
+    }
+  }
   __device__ __forceinline__ void get(uint4 (&out)[NCH]) const {
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
@@ -189,11 +220,12 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
       for (int i = 0; i < 8; ++i) cc[i] = (int64_t)kb * BK + ((i * NPROD + tid) & 7) * 8;
     };
     ChunkLoader<MODE == 2 ? 0 : MODE, 8> ld;
-    if (MODE != 2) {
-      int64_t cc[8];
-      cols_of(0, cc);
-      ld.issue(d.A, ro, cc, d.K, d.a_kin, d.a_k1s);
-    }
+    // all 8 chunks of a thread sit in the same 8-column group ((i*128 + tid) & 7 == tid & 7): one column offset per k-block
+    auto issue_kb = [&](int kb) {
+      const int64_t c = (int64_t)kb * BK + (tid & 7) * 8;
+      ld.issue_col(d.A, ro, col_off(c, d.a_kin, d.a_k1s), c + 8 <= d.K);
+    };
+    if (MODE != 2) issue_kb(0);
     const bool dbg = g_nt_dbg_on != 0 && tid == 0;
     long long t_get = 0, t_empty = 0, t_store = 0, t0 = 0;
     const long long t_begin = clock64();
@@ -204,11 +236,7 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
       if (dbg) t0 = clock64();
       if (MODE != 2) {
         ld.get(ch);                                   // stage kb has landed (or we wait for it here)
-        if (kb + 1 < nkb) {                           // put stage kb+1 in flight before touching shared memory
-          int64_t cc[8];
-          cols_of(kb + 1, cc);
-          ld.issue(d.A, ro, cc, d.K, d.a_kin, d.a_k1s);
-        }
+        if (kb + 1 < nkb) issue_kb(kb + 1);           // put stage kb+1 in flight before touching shared memory
       } else {
         int64_t cc[8];
         cols_of(kb, cc);
@@ -467,13 +495,17 @@ static int launch_nt(const ag_gemm_desc* d, cudaStream_t s) {
 // D[n, k] (+)= sum_m Y(m, n) * A(m, k): the reduction index m is the row index of both global operands, so both
 // MMA operands are MN-major: a stage holds 64 m-rows; operand "A" = Y^T as two 64-wide n blocks, operand "B" =
 // the activation window as BNK/64 k blocks, each block [64 m-rows][128 B] with the 128B swizzle.
+__host__ __device__ constexpr int tn_rm(int my, int ma) { return (my == 1 && ma == 1) ? 64 : 32; }
+
 template <int BNK, int MODEY, int MODEA>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_desc d, float* __restrict__ dw, int64_t ldw,
                                                                 int ones_col, int64_t rows_per_split) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int STAGES = nt_stages(BNK);                   // 2-4 stages, <= 96 KB: two CTAs per SM
-  constexpr int RM = 64;                                   // reduction rows per stage
+  // reduction rows per stage: 64 with bf16 operands, 32 otherwise (fp32 chunks cost 8 registers while in flight, and all
+  // loads of a stage are issued before the first shared-memory store); same bytes in the ring either way (<= 96 KB)
+  constexpr int RM = tn_rm(MODEY, MODEA);
+  constexpr int STAGES = nt_stages(BNK) * (64 / RM);
   constexpr int A_BYTES = 2 * RM * 128, B_BYTES = (BNK / 64) * RM * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
@@ -506,9 +538,34 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
+    // per-thread constants of the vector path: column offsets / validity of this thread's chunks (the same every stage)
+    constexpr int NYc = (RM * 16) / NPROD, CPRc = BNK / 8, NTOTc = (RM * CPRc) / NPROD;
+    int32_t ycoff[NYc], acoff[NTOTc];
+    uint32_t ymask = 0, amask = 0;
+    if (MODEY != 2 && MODEA != 2) {
+#pragma unroll
+      for (int i = 0; i < NYc; ++i) {
+        const int64_t c = n0 + ((i * NPROD + tid) & 15) * 8;
+        const bool okc = c + 8 <= d.N;
+        ycoff[i] = okc ? (int32_t)col_off(c, d.c_nin, d.c_n1s) : 0;
+        ymask |= (okc ? 1u : 0u) << i;
+      }
+#pragma unroll
+      for (int i = 0; i < NTOTc; ++i) {
+        const int64_t c = k0 + ((i * NPROD + tid) % CPRc) * 8;
+        const bool okc = c + 8 <= d.K;
+        acoff[i] = okc ? (int32_t)col_off(c, d.a_kin, d.a_k1s) : 0;
+        amask |= (okc ? 1u : 0u) << i;
+      }
+    }
+    const bool dbg = g_nt_dbg_on != 0 && tid == 0;
+    long long t_empty = 0, t_off = 0, t_ld = 0, t0 = 0;
+    const long long t_begin = clock64();
     for (int it = 0; it < nst; ++it) {
       const int s = it % STAGES;
+      if (dbg) t0 = clock64();
       mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+      if (dbg) { const long long t1 = clock64(); t_empty += t1 - t0; t0 = t1; }
       const int64_t mr0 = mbeg + (int64_t)it * RM;
       if (tid < RM) {
         const int64_t m = mr0 + tid;
@@ -522,6 +579,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
         ao[s * RM + tid] = a;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (dbg) { const long long t1 = clock64(); t_off += t1 - t0; t0 = t1; }
       uint8_t* sa = smem + s * STAGE_BYTES;
       uint8_t* sb = sa + A_BYTES;
       // Y^T: 64 rows x 16 chunks (two 64-wide n blocks); activation window: 64 rows x BNK/8 chunks
@@ -529,26 +587,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
       constexpr int CPR = BNK / 8;                          // chunks per row of the activation window
       constexpr int NTOT = (RM * CPR) / NPROD;              // chunks per thread: 4 / 8 / 16
       const bool edge = ones_at >= 0 && k0 + BNK > d.K;     // the chunk holding the ones column goes through the generic path
-      if (MODEY == 1 && MODEA == 1 && NTOT <= 16) {
-        // bf16 operands: 4 registers per chunk, so ALL loads of the stage (Y and the whole activation window) are in
-        // flight before the first shared-memory store -- one exposed global-load latency per stage instead of three
+      if (MODEY != 2 && MODEA != 2 && !edge) {
+        // ALL loads of the stage (Y and the whole activation window) are in flight before the first shared-memory store:
+        // one exposed global-load latency per stage instead of three
         uint4 chy[NY], cha[NTOT];
-        int64_t ro[NY], cc[NY], roa[NTOT], cca[NTOT];
+        int64_t ro[NY], roa[NTOT];
 #pragma unroll
-        for (int i = 0; i < NY; ++i) {
-          const int cid = i * NPROD + tid;
-          ro[i] = yo[s * RM + (cid >> 4)];
-          cc[i] = n0 + (cid & 15) * 8;
-        }
+        for (int i = 0; i < NY; ++i) ro[i] = yo[s * RM + ((i * NPROD + tid) >> 4)];
 #pragma unroll
-        for (int i = 0; i < NTOT; ++i) {
-          const int cid = i * NPROD + tid;
-          roa[i] = ao[s * RM + cid / CPR];
-          cca[i] = k0 + (cid % CPR) * 8;
-        }
-        load_chunks<1, NY>(chy, d.C, d.c_dtype, ro, cc, d.N, d.c_nin, d.c_n1s, -1);
-        if (edge) load_chunks<2, NTOT>(cha, d.A, d.a_dtype, roa, cca, d.K, d.a_kin, d.a_k1s, ones_at);
-        else load_chunks<1, NTOT>(cha, d.A, d.a_dtype, roa, cca, d.K, d.a_kin, d.a_k1s, ones_at);
+        for (int i = 0; i < NTOT; ++i) roa[i] = ao[s * RM + (i * NPROD + tid) / CPR];
+        ChunkLoader<MODEY == 2 ? 0 : MODEY, NY> ly;
+        ChunkLoader<MODEA == 2 ? 0 : MODEA, NTOT> la;
+        ly.issue_pre(d.C, ro, ycoff, ymask);
+        la.issue_pre(d.A, roa, acoff, amask);
+        ly.get(chy);
+        la.get(cha);
 #pragma unroll
         for (int i = 0; i < NY; ++i) {
           const int cid = i * NPROD + tid;
@@ -605,7 +658,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
+      if (dbg) t_ld += clock64() - t0;
     }
+    const long long t_main = clock64();
     // epilogue: TMEM lane = n, column = k; 32x32 transposes through shared memory so that one warp instruction
     // accumulates 32 consecutive k of one weight row (coalesced red.global.add.f32)
     mbar_wait(tmem_full, 0);
@@ -635,6 +690,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
       __syncwarp();
     }
     tc_fence_before();
+    if (dbg) {
+      const long long t_end = clock64();
+      atomicAdd(&g_nt_dbg[8], 1ull);
+      atomicAdd(&g_nt_dbg[9], (unsigned long long)t_empty);
+      atomicAdd(&g_nt_dbg[10], (unsigned long long)t_off);
+      atomicAdd(&g_nt_dbg[11], (unsigned long long)t_ld);
+      atomicAdd(&g_nt_dbg[12], (unsigned long long)(t_main - t_begin));
+      atomicAdd(&g_nt_dbg[13], (unsigned long long)(t_end - t_main));
+      atomicAdd(&g_nt_dbg[14], (unsigned long long)nst);
+    }
   } else {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(BM, BNK, 1, 1);
@@ -660,14 +725,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
   }
 }
 
+static int tn_split_factor() {          // experiment knob: CTAs per SM worth of row splits (AUDIOGAN_TN_SPLIT, default 4)
+  static int v = 0;
+  if (!v) { const char* e = getenv("AUDIOGAN_TN_SPLIT"); v = e ? atoi(e) : 4; if (v < 1) v = 4; }
+  return v;
+}
 template <int BNK>
 static int launch_tn(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones_col, bool vy, bool va, cudaStream_t s) {
-  constexpr int RM = 64;
-  constexpr int STAGES = nt_stages(BNK);
-  constexpr int smem = STAGES * (2 * RM * 128 + (BNK / 64) * RM * 128) + 1024 + (2 * STAGES + 1) * 8 + 16 + 2 * STAGES * RM * 8;
+  constexpr int RM = 64;                                   // row granularity of the splits (both stage depths divide it)
+  // ring bytes do not depend on the stage depth (32 rows x 2S stages = 64 rows x S stages); barriers / offsets sized for 2S
+  constexpr int STAGES = 2 * nt_stages(BNK);
+  constexpr int smem = nt_stages(BNK) * (2 * 64 * 128 + (BNK / 64) * 64 * 128) + 1024 + (2 * STAGES + 1) * 8 + 16 + 2 * STAGES * RM * 8;
   const int64_t ktot = d->K + (ones_col ? 1 : 0);
   const int64_t gx = (ktot + BNK - 1) / BNK, gy = (d->N + BM - 1) / BM;
-  int64_t want = (int64_t)sm_count() * 4 / (gx * gy);
+  int64_t want = (int64_t)sm_count() * tn_split_factor() / (gx * gy);
   if (want < 1) want = 1;
   int64_t rows = (d->M + want - 1) / want;
   if (rows < 512) rows = 512;
