@@ -23,7 +23,8 @@ __device__ unsigned long long g_nt_dbg[16];
 __device__ int g_nt_dbg_on = 0;
 
 constexpr int BM = 128, BK = 64, NTHREADS = 160, NPROD = 128;
-constexpr int NT_THREADS = 192;      // NT kernel: + warp 5 = TMA issuer for the B tiles
+constexpr int NT_THREADS = 192;
+constexpr int TN_NPROD = 256, TN_THREADS = 288;   // TN kernel: 8 producer / epilogue warps + the MMA warp      // NT kernel: + warp 5 = TMA issuer for the B tiles
 
 // Column c of a row: element offset (c / inner) * outer_stride + c % inner (32-bit division: columns < 2^31).
 __device__ __forceinline__ int64_t col_off(int64_t c, int64_t inner, int64_t outer_stride) {
@@ -498,7 +499,7 @@ static int launch_nt(const ag_gemm_desc* d, cudaStream_t s) {
 __host__ __device__ constexpr int tn_rm(int my, int ma) { return (my == 1 && ma == 1) ? 64 : 32; }
 
 template <int BNK, int MODEY, int MODEA>
-__global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_desc d, float* __restrict__ dw, int64_t ldw,
+__global__ void __launch_bounds__(TN_THREADS, 2) gemm_tn_tc_kernel(const ag_gemm_desc d, float* __restrict__ dw, int64_t ldw,
                                                                 int ones_col, int64_t rows_per_split) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -522,12 +523,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
   const int64_t ones_at = ones_col ? d.K : -1;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NPROD / 32); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], TN_NPROD / 32); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr uint32_t TMEM_COLS = BNK < 32 ? 32 : BNK;
-  if (warp == 4) {
+  if (warp == TN_NPROD / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -537,22 +538,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < TN_NPROD / 32) {
     // per-thread constants of the vector path: column offsets / validity of this thread's chunks (the same every stage)
-    constexpr int NYc = (RM * 16) / NPROD, CPRc = BNK / 8, NTOTc = (RM * CPRc) / NPROD;
+    constexpr int NYc = (RM * 16) / TN_NPROD, CPRc = BNK / 8, NTOTc = (RM * CPRc) / TN_NPROD;
     int32_t ycoff[NYc], acoff[NTOTc];
     uint32_t ymask = 0, amask = 0;
     if (MODEY != 2 && MODEA != 2) {
 #pragma unroll
       for (int i = 0; i < NYc; ++i) {
-        const int64_t c = n0 + ((i * NPROD + tid) & 15) * 8;
+        const int64_t c = n0 + ((i * TN_NPROD + tid) & 15) * 8;
         const bool okc = c + 8 <= d.N;
         ycoff[i] = okc ? (int32_t)col_off(c, d.c_nin, d.c_n1s) : 0;
         ymask |= (okc ? 1u : 0u) << i;
       }
 #pragma unroll
       for (int i = 0; i < NTOTc; ++i) {
-        const int64_t c = k0 + ((i * NPROD + tid) % CPRc) * 8;
+        const int64_t c = k0 + ((i * TN_NPROD + tid) % CPRc) * 8;
         const bool okc = c + 8 <= d.K;
         acoff[i] = okc ? (int32_t)col_off(c, d.a_kin, d.a_k1s) : 0;
         amask |= (okc ? 1u : 0u) << i;
@@ -578,14 +579,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
         yo[s * RM + tid] = y;
         ao[s * RM + tid] = a;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(TN_NPROD) : "memory");
       if (dbg) { const long long t1 = clock64(); t_off += t1 - t0; t0 = t1; }
       uint8_t* sa = smem + s * STAGE_BYTES;
       uint8_t* sb = sa + A_BYTES;
       // Y^T: 64 rows x 16 chunks (two 64-wide n blocks); activation window: 64 rows x BNK/8 chunks
-      constexpr int NY = (RM * 16) / NPROD;
+      constexpr int NY = (RM * 16) / TN_NPROD;
       constexpr int CPR = BNK / 8;                          // chunks per row of the activation window
-      constexpr int NTOT = (RM * CPR) / NPROD;              // chunks per thread: 4 / 8 / 16
+      constexpr int NTOT = (RM * CPR) / TN_NPROD;              // chunks per thread: 4 / 8 / 16
       const bool edge = ones_at >= 0 && k0 + BNK > d.K;     // the chunk holding the ones column goes through the generic path
       if (MODEY != 2 && MODEA != 2 && !edge) {
         // ALL loads of the stage (Y and the whole activation window) are in flight before the first shared-memory store:
@@ -593,9 +594,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
         uint4 chy[NY], cha[NTOT];
         int64_t ro[NY], roa[NTOT];
 #pragma unroll
-        for (int i = 0; i < NY; ++i) ro[i] = yo[s * RM + ((i * NPROD + tid) >> 4)];
+        for (int i = 0; i < NY; ++i) ro[i] = yo[s * RM + ((i * TN_NPROD + tid) >> 4)];
 #pragma unroll
-        for (int i = 0; i < NTOT; ++i) roa[i] = ao[s * RM + (i * NPROD + tid) / CPR];
+        for (int i = 0; i < NTOT; ++i) roa[i] = ao[s * RM + (i * TN_NPROD + tid) / CPR];
         ChunkLoader<MODEY == 2 ? 0 : MODEY, NY> ly;
         ChunkLoader<MODEA == 2 ? 0 : MODEA, NTOT> la;
         ly.issue_pre(d.C, ro, ycoff, ymask);
@@ -604,13 +605,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
         la.get(cha);
 #pragma unroll
         for (int i = 0; i < NY; ++i) {
-          const int cid = i * NPROD + tid;
+          const int cid = i * TN_NPROD + tid;
           const int r = cid >> 4, c = cid & 15;
           *reinterpret_cast<uint4*>(sa + (c >> 3) * (RM * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = chy[i];
         }
 #pragma unroll
         for (int i = 0; i < NTOT; ++i) {
-          const int cid = i * NPROD + tid;
+          const int cid = i * TN_NPROD + tid;
           const int r = cid / CPR, c = cid % CPR;
           *reinterpret_cast<uint4*>(sb + (c >> 3) * (RM * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = cha[i];
         }
@@ -620,14 +621,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
         int64_t ro[NY], cc[NY];
 #pragma unroll
         for (int i = 0; i < NY; ++i) {
-          const int cid = i * NPROD + tid;
+          const int cid = i * TN_NPROD + tid;
           ro[i] = yo[s * RM + (cid >> 4)];
           cc[i] = n0 + (cid & 15) * 8;
         }
         load_chunks<MODEY, NY>(ch, d.C, d.c_dtype, ro, cc, d.N, d.c_nin, d.c_n1s, -1);
 #pragma unroll
         for (int i = 0; i < NY; ++i) {
-          const int cid = i * NPROD + tid;
+          const int cid = i * TN_NPROD + tid;
           const int r = cid >> 4, c = cid & 15;
           *reinterpret_cast<uint4*>(sa + (c >> 3) * (RM * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = ch[i];
         }
@@ -639,7 +640,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
         int64_t ro[NA], cc[NA];
 #pragma unroll
         for (int i = 0; i < NA; ++i) {
-          const int cid = (i0 + i) * NPROD + tid;
+          const int cid = (i0 + i) * TN_NPROD + tid;
           ro[i] = ao[s * RM + cid / CPR];
           cc[i] = k0 + (cid % CPR) * 8;
         }
@@ -649,7 +650,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
           load_chunks<MODEA, NA>(ch, d.A, d.a_dtype, ro, cc, d.K, d.a_kin, d.a_k1s, ones_at);
 #pragma unroll
         for (int i = 0; i < NA; ++i) {
-          const int cid = (i0 + i) * NPROD + tid;
+          const int cid = (i0 + i) * TN_NPROD + tid;
           const int r = cid / CPR, c = cid % CPR;
           *reinterpret_cast<uint4*>(sb + (c >> 3) * (RM * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = ch[i];
         }
@@ -668,14 +669,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
     const int64_t ktot = d.K + (ones_col ? 1 : 0);
     float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 33);
     constexpr int CH = 32;
+    const int wq = warp & 3, wh = warp >> 2;           // TMEM lane quarter; warps w and w + 4 split the columns
 #pragma unroll 1
-    for (int c0 = 0; c0 < BNK; c0 += CH) {
+    for (int c0 = wh * (BNK / 2); c0 < (wh + 1) * (BNK / 2); c0 += CH) {
       if (k0 + c0 >= ktot) break;
       uint32_t v[16];
-      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tc_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
       for (int j = 0; j < 16; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
-      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c0 + 16), v);
+      tc_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(c0 + 16), v);
 #pragma unroll
       for (int j = 0; j < 16; ++j) tr[lane * 33 + 16 + j] = __uint_as_float(v[j]);
       __syncwarp();
@@ -683,7 +685,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
       if (k < ktot) {
 #pragma unroll 4
         for (int r = 0; r < 32; ++r) {
-          const int64_t n = n0 + warp * 32 + r;
+          const int64_t n = n0 + wq * 32 + r;
           if (n < d.N) atomicAdd(&dw[n * ldw + k], tr[r * 33 + lane]);
         }
       }
@@ -719,7 +721,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tn_tc_kernel(const ag_gemm_d
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TN_NPROD / 32) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
@@ -750,7 +752,7 @@ static int launch_tn(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones_col
   do {                                                                                                     \
     auto kern = gemm_tn_tc_kernel<BNK, MY, MA>;                                                             \
     AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));               \
-    kern<<<grid, NTHREADS, smem, s>>>(*d, dw, ldw, ones_col, rows);                                        \
+    kern<<<grid, TN_THREADS, smem, s>>>(*d, dw, ldw, ones_col, rows);                                        \
   } while (0)
   const int my = vy ? (d->c_dtype == 0 ? 0 : 1) : 2, ma = va ? (d->a_dtype == 0 ? 0 : 1) : 2;
   if (my == 0 && ma == 0) AG_TN_LAUNCH(0, 0);
