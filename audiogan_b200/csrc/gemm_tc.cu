@@ -562,24 +562,31 @@ __global__ void __launch_bounds__(TN_THREADS, 2) gemm_tn_tc_kernel(const ag_gemm
     const bool dbg = g_nt_dbg_on != 0 && tid == 0;
     long long t_empty = 0, t_off = 0, t_ld = 0, t0 = 0;
     const long long t_begin = clock64();
+    auto put_offsets = [&](int it2) {
+      if (tid < RM) {
+        const int64_t m = mbeg + (int64_t)it2 * RM + tid;
+        int64_t y = -1, a = -1;
+        if (m < mend) {
+          const uint32_t mu = (uint32_t)m, by = mu / (uint32_t)d.c_rpb, ba = mu / (uint32_t)d.a_rpb;
+          y = (int64_t)by * d.c_bs + (int64_t)(mu - by * (uint32_t)d.c_rpb) * d.c_rs;
+          a = (int64_t)ba * d.a_bs + (int64_t)(mu - ba * (uint32_t)d.a_rpb) * d.a_rs;
+        }
+        yo[(it2 % STAGES) * RM + tid] = y;
+        ao[(it2 % STAGES) * RM + tid] = a;
+      }
+    };
+    put_offsets(0);
+    asm volatile("bar.sync 1, %0;" ::"n"(TN_NPROD) : "memory");
     for (int it = 0; it < nst; ++it) {
       const int s = it % STAGES;
       if (dbg) t0 = clock64();
       mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
       if (dbg) { const long long t1 = clock64(); t_empty += t1 - t0; t0 = t1; }
+      // row offsets of this stage were written during the previous one (stage 0: before the loop); the ones of the NEXT
+      // stage go out now, in the shadow of this stage's loads (32-bit divisions: M < 2^31 is checked on the host)
+      if (it + 1 < nst) put_offsets(it + 1);
       const int64_t mr0 = mbeg + (int64_t)it * RM;
-      if (tid < RM) {
-        const int64_t m = mr0 + tid;
-        int64_t y = -1, a = -1;
-        if (m < mend) {
-          const int64_t by = m / d.c_rpb, ba = m / d.a_rpb;
-          y = by * d.c_bs + (m - by * d.c_rpb) * d.c_rs;
-          a = ba * d.a_bs + (m - ba * d.a_rpb) * d.a_rs;
-        }
-        yo[s * RM + tid] = y;
-        ao[s * RM + tid] = a;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(TN_NPROD) : "memory");
+      (void)mr0;
       if (dbg) { const long long t1 = clock64(); t_off += t1 - t0; t0 = t1; }
       uint8_t* sa = smem + s * STAGE_BYTES;
       uint8_t* sb = sa + A_BYTES;
@@ -659,6 +666,7 @@ __global__ void __launch_bounds__(TN_THREADS, 2) gemm_tn_tc_kernel(const ag_gemm
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
+      asm volatile("bar.sync 1, %0;" ::"n"(TN_NPROD) : "memory");      // next stage's row offsets are visible to all producers
       if (dbg) t_ld += clock64() - t0;
     }
     const long long t_main = clock64();
@@ -794,6 +802,7 @@ int ag_gemm_nt_tc(const ag_gemm_desc* d, void* stream) {
 }
 int ag_gemm_tn_tc(const ag_gemm_desc* d, float* dw, int64_t ldw, int32_t ones_col, void* stream) {
   AG_CHECK_ARG(d && d->M > 0 && d->N > 0 && d->K > 0 && d->A && d->C && dw, "ag_gemm_tn_tc: bad descriptor");
+  AG_CHECK_ARG(d->M < (1ll << 31) && d->a_rpb < (1ll << 31) && d->c_rpb < (1ll << 31), "ag_gemm_tn_tc: M / rows_per_batch must be < 2^31");
   AG_CHECK_ARG(d->a_rpb > 0 && d->a_kin > 0 && d->c_rpb > 0 && d->c_nin > 0, "ag_gemm_tn_tc: bad view fields");
   AG_CHECK_ARG(ldw >= d->K + (ones_col ? 1 : 0), "ag_gemm_tn_tc: bad ldw");
   cudaStream_t s = (cudaStream_t)stream;
