@@ -23,8 +23,9 @@ __device__ unsigned long long g_nt_dbg[16];
 __device__ int g_nt_dbg_on = 0;
 
 constexpr int BM = 128, BK = 64, NTHREADS = 160, NPROD = 128;
-constexpr int NT_THREADS = 192;
-constexpr int TN_NPROD = 256, TN_THREADS = 288;   // TN kernel: 8 producer / epilogue warps + the MMA warp      // NT kernel: + warp 5 = TMA issuer for the B tiles
+constexpr int NT_NPROD = 256, NT_THREADS = 320;   // NT kernel: 8 producer / epilogue warps, MMA warp, TMA warp (B tiles)
+constexpr int NT_NCHT = (BM * 8) / NT_NPROD;      // NT: 16-byte A chunks per producer thread and k-block
+constexpr int TN_NPROD = 256, TN_THREADS = 288;   // TN kernel: 8 producer / epilogue warps + the MMA warp
 
 // Column c of a row: element offset (c / inner) * outer_stride + c % inner (32-bit division: columns < 2^31).
 __device__ __forceinline__ int64_t col_off(int64_t c, int64_t inner, int64_t outer_stride) {
@@ -196,12 +197,12 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
     rowoff[tid] = off;
   }
   if (tid == 0) {
-    for (int s = 0; s < STG; ++s) { mbar_init(&full[s], NPROD / 32 + 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STG; ++s) { mbar_init(&full[s], NT_NPROD / 32 + 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;     // power of two >= 32 (BN in {16,32,64,128,256})
-  if (warp == 4) {
+  if (warp == NT_NPROD / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -211,17 +212,18 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ------------------------------------------------------------------ producers
-    int64_t ro[8];
+  if (warp < NT_NPROD / 32) {
+    // ------------------------------------------------------------------ producers (8 warps: they are instruction-bound)
+    constexpr int NCHT = NT_NCHT;
+    int64_t ro[NCHT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ro[i] = rowoff[(i * NPROD + tid) >> 3];
-    auto cols_of = [&](int kb, int64_t (&cc)[8]) {
+    for (int i = 0; i < NCHT; ++i) ro[i] = rowoff[(i * NT_NPROD + tid) >> 3];
+    auto cols_of = [&](int kb, int64_t (&cc)[NT_NCHT]) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cc[i] = (int64_t)kb * BK + ((i * NPROD + tid) & 7) * 8;
+      for (int i = 0; i < NCHT; ++i) cc[i] = (int64_t)kb * BK + ((i * NT_NPROD + tid) & 7) * 8;
     };
-    ChunkLoader<MODE == 2 ? 0 : MODE, 8> ld;
-    // all 8 chunks of a thread sit in the same 8-column group ((i*128 + tid) & 7 == tid & 7): one column offset per k-block
+    ChunkLoader<MODE == 2 ? 0 : MODE, NCHT> ld;
+    // all chunks of a thread sit in the same 8-column group ((i*256 + tid) & 7 == tid & 7): one column offset per k-block
     auto issue_kb = [&](int kb) {
       const int64_t c = (int64_t)kb * BK + (tid & 7) * 8;
       ld.issue_col(d.A, ro, col_off(c, d.a_kin, d.a_k1s), c + 8 <= d.K);
@@ -233,23 +235,23 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STG;
       const uint32_t ph = (kb / STG) & 1;
-      uint4 ch[8];
+      uint4 ch[NCHT];
       if (dbg) t0 = clock64();
       if (MODE != 2) {
         ld.get(ch);                                   // stage kb has landed (or we wait for it here)
         if (kb + 1 < nkb) issue_kb(kb + 1);           // put stage kb+1 in flight before touching shared memory
       } else {
-        int64_t cc[8];
+        int64_t cc[NCHT];
         cols_of(kb, cc);
-        load_chunks<2, 8>(ch, d.A, d.a_dtype, ro, cc, d.K, d.a_kin, d.a_k1s, -1);
+        load_chunks<2, NCHT>(ch, d.A, d.a_dtype, ro, cc, d.K, d.a_kin, d.a_k1s, -1);
       }
-      if (dbg) { asm volatile("" :: "r"(ch[0].x), "r"(ch[7].w)); const long long t1 = clock64(); t_get += t1 - t0; t0 = t1; }
+      if (dbg) { asm volatile("" :: "r"(ch[0].x), "r"(ch[NCHT - 1].w)); const long long t1 = clock64(); t_get += t1 - t0; t0 = t1; }
       mbar_wait(&empty[s], ph ^ 1);
       if (dbg) { const long long t1 = clock64(); t_empty += t1 - t0; t0 = t1; }
       uint8_t* sa = smem + s * STAGE_BYTES;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int cid = i * NPROD + tid;
+      for (int i = 0; i < NCHT; ++i) {
+        const int cid = i * NT_NPROD + tid;
         const int r = cid >> 3, c = cid & 7;
         *reinterpret_cast<uint4*>(sa + r * 128 + ((c ^ (r & 7)) << 4)) = ch[i];
       }
@@ -265,8 +267,9 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
     {
       const int64_t m = m0 + tid;               // every producer thread has passed its last rowoff read: reuse it
       __syncwarp();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (m < d.M) {
+      asm volatile("bar.sync 1, %0;" ::"n"(NT_NPROD) : "memory");
+      if (tid >= BM) {
+      } else if (m < d.M) {
         const int64_t b = m / d.c_rpb, t = m - b * d.c_rpb;
         rowoff[tid] = b * d.c_bs + t * d.c_rs;
         s_b[tid] = (int)b;
@@ -276,15 +279,17 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
         rowoff[tid] = -1;
       }
     }
+    asm volatile("bar.sync 1, %0;" ::"n"(NT_NPROD) : "memory");       // C row offsets visible to all 8 epilogue warps
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     __syncwarp();
     float* tr = reinterpret_cast<float*>(smem) + warp * (32 * TRLD);
+    const int wq = warp & 3, wh = warp >> 2;        // TMEM lane quarter; warps w and w + 4 take alternate column chunks
     const float alpha = d.alpha == 0.f ? 1.f : d.alpha;
     constexpr int CH = BN < 32 ? BN : 32;
-    const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += CH) {
+    for (int c0 = wh * CH; c0 < BN; c0 += 2 * CH) {
       if (n0 + c0 >= d.N) break;
       {
         uint32_t v[16];
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
         int64_t civ[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int row = warp * 32 + it * 4 + rs;
+          const int row = wq * 32 + it * 4 + rs;
           const int64_t crow = rowoff[row];
           civ[it] = (crow < 0 || !nv) ? -1 : crow + coff;
           rbv[it] = skv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -327,7 +332,7 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
         }
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + rs, row = warp * 32 + r;
+          const int r = it * 4 + rs, row = wq * 32 + r;
           if (civ[it] < 0) continue;
           const int64_t ci = civ[it];
           float4 x = *reinterpret_cast<const float4*>(tr + r * TRLD + 4 * q);
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
         const float bv = (nv && d.bias) ? d.bias[d.bias_mod > 0 ? n % d.bias_mod : n] : 0.f;
 #pragma unroll 2
         for (int r = 0; r < 32; ++r) {
-          const int row = warp * 32 + r;
+          const int row = wq * 32 + r;
           const int64_t crow = rowoff[row];
           if (crow < 0 || !nv) continue;
           const int64_t ci = crow + coff;
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
       atomicAdd(&g_nt_dbg[5], (unsigned long long)(t_end - t_main));
       atomicAdd(&g_nt_dbg[6], (unsigned long long)nkb);
     }
-  } else if (warp == 5) {
+  } else if (warp == NT_NPROD / 32 + 1) {
     // ------------------------------------------------------------------ TMA issuer for the B (weight) tiles: its own
     // thread, so a tile's TMA latency starts the moment the slot is free instead of after the producers' global loads
     // of the same k-block have landed (the two latencies used to add up on the per-k-block critical path)
@@ -428,7 +433,7 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NT_NPROD / 32) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
@@ -473,7 +478,7 @@ static int launch_nt2(const ag_gemm_desc* d, cudaStream_t s) {
   if (rc) return rc;
   constexpr int STG = nt_stages(BN);
   constexpr int smem = STG * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + (2 * STG + 1) * 8 + 16 + BM * 8 + 3 * BM * 4;
-  static_assert(STG * (BM * BK * 2 + BN * BK * 2) >= 4 * 32 * TRLD * 4, "epilogue transpose tiles must fit in the stages");
+  static_assert(STG * (BM * BK * 2 + BN * BK * 2) >= 8 * 32 * TRLD * 4, "epilogue transpose tiles must fit in the stages");
   auto kern = gemm_nt_tc_kernel<BN, MODE, VECC>;
   AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((unsigned)((d->M + BM - 1) / BM), (unsigned)((d->N + BN - 1) / BN));
