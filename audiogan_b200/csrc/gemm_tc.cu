@@ -309,17 +309,20 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
         const int q = lane & 7, rs = lane >> 3;
         const int64_t n = n0 + c0 + 4 * q;
         const bool nv = 4 * q < CH && n < d.N;
-        const int64_t n1 = nv ? n / d.c_nin : 0;
+        const int64_t n1 = (nv && n >= d.c_nin) ? (int64_t)((uint32_t)n / (uint32_t)d.c_nin) : 0;   // plain 2-D C: no division
         const int64_t coff = n1 * d.c_n1s + (n - n1 * d.c_nin);
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nv && d.bias) bv = *reinterpret_cast<const float4*>(d.bias + (d.bias_mod > 0 ? n % d.bias_mod : n));
+        if (nv && d.bias) bv = *reinterpret_cast<const float4*>(d.bias + ((d.bias_mod > 0 && n >= d.bias_mod) ? n % d.bias_mod : n));
         const int64_t mpos = n1 * d.mask_n1mul + d.mask_toff;
-        // all global reads of the chunk's epilogue operands first (8 rows x {row-bias, skip, dact}): one exposed latency
-        float4 rbv[8], skv[8], dav[8];
-        int64_t civ[8];
+        // all global reads of a half-chunk's epilogue operands first (4 rows x {row-bias, skip, dact}): one exposed latency
+        // per half (8 rows at once cost 112 registers of staging and spilled under the 96-register budget of 640 threads/SM)
+#pragma unroll 1
+        for (int hb = 0; hb < 8; hb += 4) {
+        float4 rbv[4], skv[4], dav[4];
+        int64_t civ[4];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = wq * 32 + it * 4 + rs;
+        for (int it = 0; it < 4; ++it) {
+          const int row = wq * 32 + (hb + it) * 4 + rs;
           const int64_t crow = rowoff[row];
           civ[it] = (crow < 0 || !nv) ? -1 : crow + coff;
           rbv[it] = skv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -331,8 +334,8 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
           }
         }
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + rs, row = wq * 32 + r;
+        for (int it = 0; it < 4; ++it) {
+          const int r = (hb + it) * 4 + rs, row = wq * 32 + r;
           if (civ[it] < 0) continue;
           const int64_t ci = civ[it];
           float4 x = *reinterpret_cast<const float4*>(tr + r * TRLD + 4 * q);
@@ -357,6 +360,7 @@ __global__ void __launch_bounds__(NT_THREADS, 2) gemm_nt_tc_kernel(const ag_gemm
             o.x = pack_bf16(x.x, x.y); o.y = pack_bf16(x.z, x.w);
             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.C) + ci) = o;
           }
+        }
         }
       } else {
         const int64_t n = n0 + c0 + lane;
