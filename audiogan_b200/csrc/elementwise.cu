@@ -209,6 +209,69 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ i
 }
 
 
+// C % 4 == 0, C <= 128, aligned rows: one block per (row chunk, batch) -- no index division; thread = (4 channels, row lane),
+// float4 loads, the row lanes meet in shared memory, one set of atomics per block.
+__global__ void __launch_bounds__(256) colsum_vec4_kernel(const float* __restrict__ in, int64_t bs, int64_t rs, int64_t T, int C4,
+                                                          float* __restrict__ out, int rows_per) {
+  __shared__ float4 red[256];
+  const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4, nrl = 256 / C4;
+  const int64_t t0 = (int64_t)blockIdx.x * rows_per, t1 = min(T, t0 + rows_per);
+  const float* p = in + (int64_t)blockIdx.y * bs + 4 * c4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a;
+  if (rl < nrl) {
+    int64_t t = t0 + rl;
+    for (; t + nrl < t1; t += 2 * nrl) {                 // two independent loads in flight per thread
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p + t * rs));
+      const float4 w = __ldg(reinterpret_cast<const float4*>(p + (t + nrl) * rs));
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      a2.x += w.x; a2.y += w.y; a2.z += w.z; a2.w += w.w;
+    }
+    if (t < t1) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p + t * rs));
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w;
+  }
+  red[threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.x < C4) {
+    float4 v = red[threadIdx.x];
+    for (int r = 1; r < nrl; ++r) { const float4 w = red[r * C4 + threadIdx.x]; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+    float* q = out + 4 * threadIdx.x;
+    atomicAdd(q, v.x); atomicAdd(q + 1, v.y); atomicAdd(q + 2, v.z); atomicAdd(q + 3, v.w);
+  }
+}
+
+// Rank-1 data gradient (the classifier's last layer, audiogan.py:508-512 backward): out[m, n] = g[m] * w[n] * lrelu'(act[m, n]).
+// HBM-bound: 16-byte accesses, act / out fp32 or bf16.
+__global__ void __launch_bounds__(256) outer_dact_kernel(const float* __restrict__ g, const float* __restrict__ w, const void* act,
+                                                         int act_dtype, void* out, int out_dtype, int64_t M, int N4, float slope) {
+  const int64_t total = M * N4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / N4;
+    const int n = (int)(i - m * N4) * 4;
+    const float gv = __ldg(g + m);
+    const float4 wv = make_float4(__ldg(w + n), __ldg(w + n + 1), __ldg(w + n + 2), __ldg(w + n + 3));   // w: any alignment
+    float4 a;
+    if (act_dtype == 0) a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(act) + m * N4 * 4 + n));
+    else {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(act) + m * N4 * 4 + n));
+      const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+      a = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+    }
+    float4 o;
+    o.x = gv * wv.x * (a.x > 0.f ? 1.f : slope); o.y = gv * wv.y * (a.y > 0.f ? 1.f : slope);
+    o.z = gv * wv.z * (a.z > 0.f ? 1.f : slope); o.w = gv * wv.w * (a.w > 0.f ? 1.f : slope);
+    if (out_dtype == 0) *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + m * N4 * 4 + n) = o;
+    else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + m * N4 * 4 + n) = u;
+    }
+  }
+}
+
 // generic strided 3-D copy / accumulate: dst[b,t,c] (+)= src[b,t,c]
 __global__ void copy3d_kernel(float* __restrict__ dst, int64_t d_bs, int64_t d_rs, int64_t d_cs,
                               const float* __restrict__ src, int64_t s_bs, int64_t s_rs, int64_t s_cs,
@@ -344,6 +407,13 @@ int ag_ew_grad(const ag_ew_desc* d, void* stream) {
 }
 int ag_colsum(const float* in, int64_t bs, int64_t rs, int64_t B, int64_t T, int64_t C, float* out, void* stream) {
   AG_CHECK_ARG(in && out && B > 0 && T > 0 && C > 0, "ag_colsum: bad args");
+  if (C % 4 == 0 && C <= 128 && bs % 4 == 0 && rs % 4 == 0 && B < 65536 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    const int rows_per = 2048;
+    dim3 grid((unsigned)((T + rows_per - 1) / rows_per), (unsigned)B);
+    colsum_vec4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, bs, rs, T, (int)(C / 4), out, rows_per);
+    AG_LAUNCH_CHECK();
+    return AG_OK;
+  }
   const int64_t M = B * T;
   const int64_t gx = (C + 31) / 32;
   int64_t gy = (int64_t)sm_count() * 8 / gx;
@@ -375,6 +445,14 @@ int ag_transpose_bct(const float* src, float* dst, int64_t B, int64_t C, int64_t
   AG_CHECK_ARG(src && dst && B > 0 && C > 0 && T > 0 && B < 65536, "ag_transpose_bct: bad args");
   dim3 grid((unsigned)((T + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)B);
   transpose_bct_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, dst, C, T, dst_bs, dst_rs, to_cl);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_outer_dact(const float* g, const float* w, const void* act, int32_t act_dtype, void* out, int32_t out_dtype, int64_t M,
+                  int64_t N, float slope, void* stream) {
+  AG_CHECK_ARG(g && w && act && out && M > 0 && N > 0 && N % 4 == 0, "ag_outer_dact: bad args");
+  AG_CHECK_ARG(((reinterpret_cast<uintptr_t>(act) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "ag_outer_dact: unaligned");
+  outer_dact_kernel<<<grid_for(M * (N / 4), 256), 256, 0, (cudaStream_t)stream>>>(g, w, act, act_dtype, out, out_dtype, M, (int)(N / 4), slope);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

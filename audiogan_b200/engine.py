@@ -334,7 +334,7 @@ class _DiscTailFn(torch.autograd.Function):
         adt = torch.bfloat16 if bf else torch.float32
         hin = hbuf16 if bf else hbuf
         dh3 = torch.empty(M, S // 2, device=dev, dtype=adt)
-        K.gemm_nt(M, S // 2, 1, g, flat(1), plan.Poff("k2.w"), 1, dh3, flat(S // 2), dact=h3)
+        K.outer_dact(g, plan.Poff("k2.w"), h3, dh3, M, S // 2)          # rank-1: dh3 = g (x) k2.w * lrelu'(h3)
         if wgrad:
             K.gemm_tn(M, S // 2, S, dh3, flat(S // 2), (r2, S), geo, plan.GPoff("k0.w"), S + 1, ones_col=True)
         dz2 = torch.empty(B, Tm + 2, S, device=dev, dtype=adt)   # grads below keep the padded-row geometry of r1 / r2 / hbuf

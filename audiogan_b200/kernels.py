@@ -136,6 +136,11 @@ def ew_grad(B, T, Cn, out=None, pad=(0, 0), g1=None, g1_str=(0, 0, 0), g2=None, 
     A.call("ag_ew_grad", C.byref(d), A.stream())
 
 
+def outer_dact(g, w, act, out, M, N, slope=LRELU_SLOPE):
+    """out[m, n] = g[m] * w[n] * lrelu'(act[m, n]) (packed [M, N]; act / out fp32 or bf16)."""
+    A.call("ag_outer_dact", addr(g), addr(w), addr(act), _dtype_of(act), addr(out), _dtype_of(out), M, N, float(slope), A.stream())
+
+
 def colsum(src, bs, rs, B, T, Cn, out):
     A.call("ag_colsum", addr(src), bs, rs, B, T, Cn, addr(out), A.stream())
 

@@ -215,6 +215,10 @@ typedef struct ag_ew_desc {
 int ag_ew_grad(const ag_ew_desc* d, void* stream);
 /* out[c] += sum_{b,t} in[b*bs + t*rs + c]  (bias gradients); out must be initialised. */
 int ag_colsum(const float* in, int64_t bs, int64_t rs, int64_t B, int64_t T, int64_t C, float* out, void* stream);
+/* Rank-1 data gradient with LeakyReLU' (backward of the classifier's 512 -> 1 layer, audiogan.py:508-512):
+ * out[m, n] = g[m] * w[n] * (act[m, n] > 0 ? 1 : slope); act / out packed [M, N], dtype 0 fp32 / 1 bf16, N % 4 == 0. */
+int ag_outer_dact(const float* g, const float* w, const void* act, int32_t act_dtype, void* out, int32_t out_dtype, int64_t M,
+                  int64_t N, float slope, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Last generator layer, Conv1d(C -> 1, k) over the dense channel-last buffer (audiogan.py:403-407, :467): HBM-bound
