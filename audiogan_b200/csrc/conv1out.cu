@@ -109,10 +109,118 @@ __global__ void __launch_bounds__(128) conv1out_wgrad_kernel(const float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The discriminator's FIRST layer, Conv1d(1 -> C, k, stride s) on the raw waveform (audiogan.py:527-536 with C_in = 1).
+// As a GEMM it has K = k = 7: nothing for tensor cores to do, the layer is a stream over the [B, T, C] output (HBM-bound).
+// out[b, t, c] = t < len[b] ? lrelu(bias[c] + sum_j w[c*k + j] * x[b*x_ld + s*t + j]) : 0.   Thread = (row, 4 channels).
+template <int KMAX>
+__global__ void __launch_bounds__(256) conv1in_fwd_kernel(const float* __restrict__ x, int64_t x_ld, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ out, int64_t out_bs,
+                                                          int k, int s, int C4, int64_t T, const int32_t* __restrict__ len, float slope) {
+  const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4, nrl = 256 / C4;
+  if (rl >= nrl) return;
+  const int64_t b = blockIdx.y;
+  float wv[4][KMAX], bv[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    bv[e] = bias ? bias[4 * c4 + e] : 0.f;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) wv[e][j] = j < k ? w[(4 * c4 + e) * k + j] : 0.f;
+  }
+  const int64_t Lb = len ? len[b] : T;
+  const float* xb = x + b * x_ld;
+  float* ob = out + b * out_bs + 4 * c4;
+  const int64_t t1 = min(T, ((int64_t)blockIdx.x + 1) * 1024);
+  for (int64_t t = (int64_t)blockIdx.x * 1024 + rl; t < t1; t += nrl) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < Lb) {
+      float xv[KMAX];
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) xv[j] = j < k ? __ldg(xb + s * t + j) : 0.f;
+      float a[4] = {bv[0], bv[1], bv[2], bv[3]};
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a[e] = fmaf(wv[e][j], xv[j], a[e]);
+      o = make_float4(a[0] > 0.f ? a[0] : a[0] * slope, a[1] > 0.f ? a[1] : a[1] * slope, a[2] > 0.f ? a[2] : a[2] * slope,
+                      a[3] > 0.f ? a[3] : a[3] * slope);
+    }
+    *reinterpret_cast<float4*>(ob + t * (4 * C4)) = o;
+  }
+}
+
+// dw[c*(k+1) + j] += sum_{b,t} dy[b,t,c] * x[b*x_ld + s*t + j],  dw[c*(k+1) + k] += sum dy[b,t,c]   (weight + bias gradient).
+template <int KMAX>
+__global__ void __launch_bounds__(256) conv1in_wgrad_kernel(const float* __restrict__ dy, int64_t dy_bs, const float* __restrict__ x,
+                                                            int64_t x_ld, float* __restrict__ dw, int k, int s, int C4, int64_t T) {
+  __shared__ float red[256];
+  const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4, nrl = 256 / C4;
+  const int64_t b = blockIdx.y;
+  float acc[4][KMAX + 1];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int j = 0; j <= KMAX; ++j) acc[e][j] = 0.f;
+  if (rl < nrl) {
+    const float* xb = x + b * x_ld;
+    const float* yb = dy + b * dy_bs + 4 * c4;
+    const int64_t t1 = min(T, ((int64_t)blockIdx.x + 1) * 2048);
+    for (int64_t t = (int64_t)blockIdx.x * 2048 + rl; t < t1; t += nrl) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(yb + t * (4 * C4)));
+      const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        const float xv = j < k ? __ldg(xb + s * t + j) : 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e][j] = fmaf(gv[e], xv, acc[e][j]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e][KMAX] += gv[e];
+    }
+  }
+  // block reduction over the row lanes, one value at a time (k + 1 values x 4 channels), then one atomic per value
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+#pragma unroll
+    for (int j = 0; j <= KMAX; ++j) {
+      if (j < k || j == KMAX) {
+        __syncthreads();
+        red[threadIdx.x] = rl < nrl ? acc[e][j] : 0.f;
+        __syncthreads();
+        if (threadIdx.x < C4) {
+          float v = 0.f;
+          for (int r = 0; r < nrl; ++r) v += red[r * C4 + threadIdx.x];
+          atomicAdd(dw + (4 * threadIdx.x + e) * (k + 1) + (j == KMAX ? k : j), v);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace ag
 
 using namespace ag;
 extern "C" {
+
+int ag_conv1in_fwd(const float* x, int64_t x_ld, const float* w, const float* bias, float* out, int64_t out_bs, int32_t k,
+                   int32_t s, int64_t C, int64_t B, int64_t T, const int32_t* len, float slope, void* stream) {
+  AG_CHECK_ARG(x && w && out && B > 0 && B < 65536 && T > 0 && C > 0 && C % 4 == 0 && C <= 1024 && k > 0 && k <= 8 && s > 0 &&
+                   out_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "ag_conv1in_fwd: bad args");
+  dim3 grid((unsigned)((T + 1023) / 1024), (unsigned)B);
+  conv1in_fwd_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_ld, w, bias, out, out_bs, k, s, (int)(C / 4), T, len, slope);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+
+int ag_conv1in_wgrad(const float* dy, int64_t dy_bs, const float* x, int64_t x_ld, float* dw, int32_t k, int32_t s, int64_t C,
+                     int64_t B, int64_t T, void* stream) {
+  AG_CHECK_ARG(dy && x && dw && B > 0 && B < 65536 && T > 0 && C > 0 && C % 4 == 0 && C <= 1024 && k > 0 && k <= 8 && s > 0 &&
+                   dy_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0, "ag_conv1in_wgrad: bad args");
+  dim3 grid((unsigned)((T + 2047) / 2048), (unsigned)B);
+  conv1in_wgrad_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, dy_bs, x, x_ld, dw, k, s, (int)(C / 4), T);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
 
 int ag_conv1out_fwd(const float* X, int64_t x_bs, int64_t C, int32_t k, const float* w, const float* bias, float* out,
                     int64_t B, int64_t T, void* stream) {

@@ -207,9 +207,14 @@ class _DiscCNNFn(torch.autograd.Function):
             a = _empty(B, Tout + 2 * DPAD, cout, device=dev)
             a[:, :DPAD].zero_()
             a[:, DPAD + Tout:].zero_()
-            K.gemm_nt(B * Tout, cout, k * cin, acts[-1], (Tout, (Tin + 2 * DPAD) * cin, s * cin),
-                      plan.Poff("c%d.w" % i), k * cin, (a, DPAD * cout), (Tout, (Tout + 2 * DPAD) * cout, cout),
-                      bias=plan.Poff("c%d.b" % i), act=1, mask_len=lens[i], mask=(1, 0, 0))
+            if cin == 1 and k <= 8 and cout % 4 == 0 and (k - 1) // 2 == DPAD:
+                # first layer on the raw waveform: K = k, a stream over the output (direct HBM kernel, fp32 arithmetic)
+                K.conv1in_fwd(acts[-1], Tin + 2 * DPAD, plan.Poff("c%d.w" % i), plan.Poff("c%d.b" % i), (a, DPAD * cout),
+                              (Tout + 2 * DPAD) * cout, k, s, cout, B, Tout, lens[i])
+            else:
+                K.gemm_nt(B * Tout, cout, k * cin, acts[-1], (Tout, (Tin + 2 * DPAD) * cin, s * cin),
+                          plan.Poff("c%d.w" % i), k * cin, (a, DPAD * cout), (Tout, (Tout + 2 * DPAD) * cout, cout),
+                          bias=plan.Poff("c%d.b" % i), act=1, mask_len=lens[i], mask=(1, 0, 0))
             acts.append(a)
             Ts.append(Tout)
             cin, Tin = cout, Tout
@@ -246,7 +251,9 @@ class _DiscCNNFn(torch.autograd.Function):
                 kw.update(g2=(dX, DPAD * cout), g2_str=(geo[0], geo[1], 1))
             K.ew_grad(B, Tout, cout, out=dy, pad=(PL, DPAD), act=(a_out, DPAD * cout), act_str=geo, length=lens[i], **kw)
             a_view = (Tout, (Tin + 2 * DPAD) * cin, s * cin)
-            if wgrad:
+            if wgrad and cin == 1 and k <= 8 and cout % 4 == 0 and (k - 1) // 2 == DPAD:
+                K.conv1in_wgrad((dy, PL * cout), gdy[0], acts[i], Tin + 2 * DPAD, plan.GPoff("c%d.w" % i), k, s, cout, B, Tout)
+            elif wgrad:
                 K.gemm_tn(B * Tout, cout, k * cin, (dy, PL * cout), (Tout, gdy[0], cout), acts[i], a_view,
                           plan.GPoff("c%d.w" % i), k * cin + 1, ones_col=True)
             if i > 0 or need_dx:

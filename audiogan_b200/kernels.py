@@ -136,6 +136,15 @@ def ew_grad(B, T, Cn, out=None, pad=(0, 0), g1=None, g1_str=(0, 0, 0), g2=None, 
     A.call("ag_ew_grad", C.byref(d), A.stream())
 
 
+def conv1in_fwd(x, x_ld, w, bias, out, out_bs, k, s, Cn, B, T, length, slope=LRELU_SLOPE):
+    A.call("ag_conv1in_fwd", addr(x), x_ld, addr(w), addr(bias), addr(out), out_bs, k, s, Cn, B, T, addr(length), float(slope),
+           A.stream())
+
+
+def conv1in_wgrad(dy, dy_bs, x, x_ld, dw, k, s, Cn, B, T):
+    A.call("ag_conv1in_wgrad", addr(dy), dy_bs, addr(x), x_ld, addr(dw), k, s, Cn, B, T, A.stream())
+
+
 def outer_dact(g, w, act, out, M, N, slope=LRELU_SLOPE):
     """out[m, n] = g[m] * w[n] * lrelu'(act[m, n]) (packed [M, N]; act / out fp32 or bf16)."""
     A.call("ag_outer_dact", addr(g), addr(w), addr(act), _dtype_of(act), addr(out), _dtype_of(out), M, N, float(slope), A.stream())

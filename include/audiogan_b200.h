@@ -221,6 +221,18 @@ int ag_outer_dact(const float* g, const float* w, const void* act, int32_t act_d
                   int64_t N, float slope, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * The discriminator's first layer, Conv1d(1 -> C, k <= 8, stride s) + bias + LeakyReLU + length mask on the raw waveform
+ * (audiogan.py:527-536 with C_in = 1), and its weight / bias gradient.  HBM-bound direct kernels (K = k is too small
+ * for tensor cores).  x: zero-padded waveform rows (tap j of output t at x[b*x_ld + s*t + j]); out / dy: channel-last
+ * [B, rows, C] with batch stride out_bs / dy_bs (pointers at row t = 0); w [C, k]; dw [C, k + 1] (column k = bias
+ * gradient), accumulated with atomics (zero it first).  C % 4 == 0.
+ * ------------------------------------------------------------------------------------------ */
+int ag_conv1in_fwd(const float* x, int64_t x_ld, const float* w, const float* bias, float* out, int64_t out_bs, int32_t k,
+                   int32_t s, int64_t C, int64_t B, int64_t T, const int32_t* len, float slope, void* stream);
+int ag_conv1in_wgrad(const float* dy, int64_t dy_bs, const float* x, int64_t x_ld, float* dw, int32_t k, int32_t s, int64_t C,
+                     int64_t B, int64_t T, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Last generator layer, Conv1d(C -> 1, k) over the dense channel-last buffer (audiogan.py:403-407, :467): HBM-bound
  * streaming kernels (no tensor-core work with one output channel).  X points at the first tap row of output 0,
  * batch stride x_bs floats, C % 4 == 0, weights w[j*C + c]:
