@@ -76,6 +76,7 @@ class EwDesc(C.Structure):
         ("len", vp),
         ("out", vp), ("pad_l", i64), ("pad_r", i64),
         ("acc", vp), ("acc_bs", i64), ("acc_rs", i64),
+        ("g1_dtype", i32), ("g2_dtype", i32), ("act_dtype", i32), ("acc_dtype", i32), ("out_dtype", i32), ("reserved2", i32),
     ]
 
 
@@ -97,14 +98,14 @@ _PROTOS = {
     "ag_bce_bwd": [vp, vp, vp, vp, vp, i64, i64, vp],
     "ag_bce_const_fused": [vp, i64, vp, f32, f32, vp, vp, vp, vp, i64, i64, vp],
     "ag_ew_grad": [C.POINTER(EwDesc), vp],
-    "ag_colsum": [vp, i64, i64, i64, i64, i64, vp, vp],
+    "ag_colsum": [vp, i32, i64, i64, i64, i64, i64, vp, vp],
     "ag_outer_dact": [vp, vp, vp, i32, vp, i32, i64, i64, f32, vp],
-    "ag_conv1in_fwd": [vp, i64, vp, vp, vp, i64, i32, i32, i64, i64, i64, vp, f32, vp],
-    "ag_conv1in_wgrad": [vp, i64, vp, i64, vp, i32, i32, i64, i64, i64, vp],
-    "ag_conv1out_fwd": [vp, i64, i64, i32, vp, vp, vp, i64, i64, vp],
-    "ag_conv1out_dgrad": [vp, vp, vp, i64, i64, i32, i64, i64, vp],
-    "ag_conv1out_wgrad": [vp, vp, i64, i64, i32, vp, i64, i64, vp],
-    "ag_copy3d": [vp, i64, i64, i64, vp, i64, i64, i64, i64, i64, i64, i32, vp],
+    "ag_conv1in_fwd": [vp, i64, vp, vp, vp, i32, i64, i32, i32, i64, i64, i64, vp, f32, vp],
+    "ag_conv1in_wgrad": [vp, i32, i64, vp, i64, vp, i32, i32, i64, i64, i64, vp],
+    "ag_conv1out_fwd": [vp, i32, i64, i64, i32, vp, vp, vp, i64, i64, vp],
+    "ag_conv1out_dgrad": [vp, vp, vp, i32, i64, i64, i32, i64, i64, vp],
+    "ag_conv1out_wgrad": [vp, vp, i32, i64, i64, i32, vp, i64, i64, vp],
+    "ag_copy3d": [vp, i64, i64, i64, vp, i64, i64, i64, i64, i64, i64, i32, i32, i32, vp],
     "ag_rowgroup_sum": [vp, vp, i64, i64, i64, vp],
     "ag_transpose_bct": [vp, vp, i64, i64, i64, i64, i64, i32, vp],
     "ag_mt_sqnorm": [vp, vp, vp, i32, i32, vp, vp, vp],

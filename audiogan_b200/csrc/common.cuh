@@ -40,6 +40,26 @@ __device__ __forceinline__ void st_any(void* p, int64_t i, float v, int dtype) {
   if (dtype) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
   else reinterpret_cast<float*>(p)[i] = v;
 }
+// 4 consecutive elements at element index i (16-byte aligned for fp32, 8-byte for bf16), read-only path / plain store
+__device__ __forceinline__ float4 ldg4_any(const void* p, int64_t i, int dtype) {
+  if (dtype == 0) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i));
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + i));
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+__device__ __forceinline__ float4 ld4_plain_any(const void* p, int64_t i, int dtype) {
+  if (dtype == 0) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+  const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + i);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+__device__ __forceinline__ void st4_any(void* p, int64_t i, float4 v, int dtype) {
+  if (dtype == 0) { *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = v; return; }
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&a); u.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p) + i) = u;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -6,7 +6,9 @@
 namespace ag {
 
 // out[b,t] = bias + sum_{j<k,c<C} X[b, t+j, c] * w[j*C + c].  One warp per output row; the k*C window is contiguous.
-__global__ void __launch_bounds__(256) conv1out_fwd_kernel(const float* __restrict__ X, int64_t x_bs, int C, int k,
+// XDT: 0 = fp32 storage (4 elements per 16-byte load), 1 = bf16 storage (8 elements per 16-byte load, K % 8 == 0).
+template <int XDT>
+__global__ void __launch_bounds__(256) conv1out_fwd_kernel(const void* __restrict__ X, int64_t x_bs, int C, int k,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
                                                            float* __restrict__ out, int64_t B, int64_t T) {
   extern __shared__ float ws[];                      // k*C weights
@@ -18,12 +20,24 @@ __global__ void __launch_bounds__(256) conv1out_fwd_kernel(const float* __restri
   const int64_t rows = B * T;
   for (int64_t m = (int64_t)blockIdx.x * nw + wid; m < rows; m += (int64_t)gridDim.x * nw) {
     const int64_t b = m / T, t = m - b * T;
-    const float4* p = reinterpret_cast<const float4*>(X + b * x_bs + t * C);
     float acc = 0.f;
-    for (int k4 = lane; k4 < K / 4; k4 += 32) {
-      const float4 v = __ldg(p + k4);
-      const float4 q = *reinterpret_cast<const float4*>(ws + 4 * k4);
-      acc += v.x * q.x + v.y * q.y + v.z * q.z + v.w * q.w;
+    if (XDT == 0) {
+      const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(X) + b * x_bs + t * C);
+      for (int k4 = lane; k4 < K / 4; k4 += 32) {
+        const float4 v = __ldg(p + k4);
+        const float4 q = *reinterpret_cast<const float4*>(ws + 4 * k4);
+        acc += v.x * q.x + v.y * q.y + v.z * q.z + v.w * q.w;
+      }
+    } else {
+      const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(X) + b * x_bs + t * C);
+      for (int k8 = lane; k8 < K / 8; k8 += 32) {
+        const uint4 u = __ldg(p + k8);
+        const float4 q0 = *reinterpret_cast<const float4*>(ws + 8 * k8), q1 = *reinterpret_cast<const float4*>(ws + 8 * k8 + 4);
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b2 = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        const __nv_bfloat162 c2 = *reinterpret_cast<const __nv_bfloat162*>(&u.z), d2 = *reinterpret_cast<const __nv_bfloat162*>(&u.w);
+        acc += __low2float(a) * q0.x + __high2float(a) * q0.y + __low2float(b2) * q0.z + __high2float(b2) * q0.w +
+               __low2float(c2) * q1.x + __high2float(c2) * q1.y + __low2float(d2) * q1.z + __high2float(d2) * q1.w;
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) out[m] = acc + bv;
@@ -31,9 +45,9 @@ __global__ void __launch_bounds__(256) conv1out_fwd_kernel(const float* __restri
 }
 
 // dX[b, t', c] = sum_j g[b, t'-j] * w[j*C + c], t' in [0, T+k-1).  Thread = 4 channels, block walks rows.
-template <int KMAX>
+template <int KMAX, int dxdt>
 __global__ void __launch_bounds__(128) conv1out_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ w,
-                                                             float* __restrict__ dX, int64_t dx_bs, int C, int k, int64_t T,
+                                                             void* __restrict__ dX, int64_t dx_bs, int C, int k, int64_t T,
                                                              int rows_per_block) {
   const int c4 = threadIdx.x;                        // channel group
   if (c4 * 4 >= C) return;
@@ -51,14 +65,14 @@ __global__ void __launch_bounds__(128) conv1out_dgrad_kernel(const float* __rest
       const float gv = (j < k && tg >= 0 && tg < T) ? __ldg(gb + tg) : 0.f;
       acc.x += gv * wv[j].x; acc.y += gv * wv[j].y; acc.z += gv * wv[j].z; acc.w += gv * wv[j].w;
     }
-    *reinterpret_cast<float4*>(dX + b * dx_bs + t * C + 4 * c4) = acc;
+    st4_any(dX, b * dx_bs + t * C + 4 * c4, acc, dxdt);
   }
 }
 
 // dw[j*C + c] += sum_{b,t} g[b,t] * X[b, t+j, c];  dw[k*C] += sum g.   Thread = (4 channels, row lane): the block's 4 warps
 // walk interleaved rows (4 independent load streams per block instead of one); every X element is read once.
-template <int KMAX>
-__global__ void __launch_bounds__(128) conv1out_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ X,
+template <int KMAX, int xdt>
+__global__ void __launch_bounds__(128) conv1out_wgrad_kernel(const float* __restrict__ g, const void* __restrict__ X,
                                                              int64_t x_bs, int C, int k, float* __restrict__ dw, int64_t T,
                                                              int rows_per_block) {
   const int c4 = threadIdx.x & 31, rl = threadIdx.x >> 5;
@@ -73,7 +87,7 @@ __global__ void __launch_bounds__(128) conv1out_wgrad_kernel(const float* __rest
     for (int j = 0; j < KMAX; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
     for (int64_t r = r0 + rl; r < r1; r += 4) {
-      const float4 x = __ldg(reinterpret_cast<const float4*>(X + b * x_bs + r * C + cc));
+      const float4 x = ldg4_any(X, b * x_bs + r * C + cc, xdt);
 #pragma unroll
       for (int j = 0; j < KMAX; ++j) {
         const int64_t t = r - j;                       // X row r is tap j of output t = r - j
@@ -115,7 +129,7 @@ __global__ void __launch_bounds__(128) conv1out_wgrad_kernel(const float* __rest
 // out[b, t, c] = t < len[b] ? lrelu(bias[c] + sum_j w[c*k + j] * x[b*x_ld + s*t + j]) : 0.   Thread = (row, 4 channels).
 template <int KMAX>
 __global__ void __launch_bounds__(256) conv1in_fwd_kernel(const float* __restrict__ x, int64_t x_ld, const float* __restrict__ w,
-                                                          const float* __restrict__ bias, float* __restrict__ out, int64_t out_bs,
+                                                          const float* __restrict__ bias, void* __restrict__ out, int odt, int64_t out_bs,
                                                           int k, int s, int C4, int64_t T, const int32_t* __restrict__ len, float slope) {
   const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4, nrl = 256 / C4;
   if (rl >= nrl) return;
@@ -129,7 +143,7 @@ __global__ void __launch_bounds__(256) conv1in_fwd_kernel(const float* __restric
   }
   const int64_t Lb = len ? len[b] : T;
   const float* xb = x + b * x_ld;
-  float* ob = out + b * out_bs + 4 * c4;
+  const int64_t ob = b * out_bs + 4 * c4;
   const int64_t t1 = min(T, ((int64_t)blockIdx.x + 1) * 1024);
   for (int64_t t = (int64_t)blockIdx.x * 1024 + rl; t < t1; t += nrl) {
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -145,13 +159,13 @@ __global__ void __launch_bounds__(256) conv1in_fwd_kernel(const float* __restric
       o = make_float4(a[0] > 0.f ? a[0] : a[0] * slope, a[1] > 0.f ? a[1] : a[1] * slope, a[2] > 0.f ? a[2] : a[2] * slope,
                       a[3] > 0.f ? a[3] : a[3] * slope);
     }
-    *reinterpret_cast<float4*>(ob + t * (4 * C4)) = o;
+    st4_any(out, ob + t * (4 * C4), o, odt);
   }
 }
 
 // dw[c*(k+1) + j] += sum_{b,t} dy[b,t,c] * x[b*x_ld + s*t + j],  dw[c*(k+1) + k] += sum dy[b,t,c]   (weight + bias gradient).
 template <int KMAX>
-__global__ void __launch_bounds__(256) conv1in_wgrad_kernel(const float* __restrict__ dy, int64_t dy_bs, const float* __restrict__ x,
+__global__ void __launch_bounds__(256) conv1in_wgrad_kernel(const void* __restrict__ dy, int ydt, int64_t dy_bs, const float* __restrict__ x,
                                                             int64_t x_ld, float* __restrict__ dw, int k, int s, int C4, int64_t T) {
   __shared__ float red[256];
   const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4, nrl = 256 / C4;
@@ -163,10 +177,10 @@ __global__ void __launch_bounds__(256) conv1in_wgrad_kernel(const float* __restr
     for (int j = 0; j <= KMAX; ++j) acc[e][j] = 0.f;
   if (rl < nrl) {
     const float* xb = x + b * x_ld;
-    const float* yb = dy + b * dy_bs + 4 * c4;
+    const int64_t yb = b * dy_bs + 4 * c4;
     const int64_t t1 = min(T, ((int64_t)blockIdx.x + 1) * 2048);
     for (int64_t t = (int64_t)blockIdx.x * 2048 + rl; t < t1; t += nrl) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(yb + t * (4 * C4)));
+      const float4 g = ldg4_any(dy, yb + t * (4 * C4), ydt);
       const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
       for (int j = 0; j < KMAX; ++j) {
@@ -202,59 +216,64 @@ __global__ void __launch_bounds__(256) conv1in_wgrad_kernel(const float* __restr
 using namespace ag;
 extern "C" {
 
-int ag_conv1in_fwd(const float* x, int64_t x_ld, const float* w, const float* bias, float* out, int64_t out_bs, int32_t k,
-                   int32_t s, int64_t C, int64_t B, int64_t T, const int32_t* len, float slope, void* stream) {
+int ag_conv1in_fwd(const float* x, int64_t x_ld, const float* w, const float* bias, void* out, int32_t out_dtype, int64_t out_bs,
+                   int32_t k, int32_t s, int64_t C, int64_t B, int64_t T, const int32_t* len, float slope, void* stream) {
   AG_CHECK_ARG(x && w && out && B > 0 && B < 65536 && T > 0 && C > 0 && C % 4 == 0 && C <= 1024 && k > 0 && k <= 8 && s > 0 &&
-                   out_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "ag_conv1in_fwd: bad args");
+                   out_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & (out_dtype ? 7 : 15)) == 0, "ag_conv1in_fwd: bad args");
   dim3 grid((unsigned)((T + 1023) / 1024), (unsigned)B);
-  conv1in_fwd_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_ld, w, bias, out, out_bs, k, s, (int)(C / 4), T, len, slope);
+  conv1in_fwd_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_ld, w, bias, out, out_dtype, out_bs, k, s, (int)(C / 4), T, len, slope);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
 
-int ag_conv1in_wgrad(const float* dy, int64_t dy_bs, const float* x, int64_t x_ld, float* dw, int32_t k, int32_t s, int64_t C,
+int ag_conv1in_wgrad(const void* dy, int32_t dy_dtype, int64_t dy_bs, const float* x, int64_t x_ld, float* dw, int32_t k, int32_t s, int64_t C,
                      int64_t B, int64_t T, void* stream) {
   AG_CHECK_ARG(dy && x && dw && B > 0 && B < 65536 && T > 0 && C > 0 && C % 4 == 0 && C <= 1024 && k > 0 && k <= 8 && s > 0 &&
-                   dy_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0, "ag_conv1in_wgrad: bad args");
+                   dy_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(dy) & (dy_dtype ? 7 : 15)) == 0, "ag_conv1in_wgrad: bad args");
   dim3 grid((unsigned)((T + 2047) / 2048), (unsigned)B);
-  conv1in_wgrad_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, dy_bs, x, x_ld, dw, k, s, (int)(C / 4), T);
+  conv1in_wgrad_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, dy_bs, x, x_ld, dw, k, s, (int)(C / 4), T);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
 
-int ag_conv1out_fwd(const float* X, int64_t x_bs, int64_t C, int32_t k, const float* w, const float* bias, float* out,
+int ag_conv1out_fwd(const void* X, int32_t x_dtype, int64_t x_bs, int64_t C, int32_t k, const float* w, const float* bias, float* out,
                     int64_t B, int64_t T, void* stream) {
   AG_CHECK_ARG(X && w && out && B > 0 && T > 0 && C > 0 && C % 4 == 0 && k > 0 && x_bs % 4 == 0, "ag_conv1out_fwd: bad args");
-  AG_CHECK_ARG(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, "ag_conv1out_fwd: unaligned");
+  AG_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                   (!x_dtype || (C % 8 == 0 && x_bs % 8 == 0)), "ag_conv1out_fwd: unaligned");
   const int64_t rows = B * T;
   int64_t grid = (rows + 7) / 8;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (grid > cap) grid = cap;
-  conv1out_fwd_kernel<<<(unsigned)grid, 256, (size_t)k * C * 4, (cudaStream_t)stream>>>(X, x_bs, (int)C, k, w, bias, out, B, T);
+  if (x_dtype) conv1out_fwd_kernel<1><<<(unsigned)grid, 256, (size_t)k * C * 4, (cudaStream_t)stream>>>(X, x_bs, (int)C, k, w, bias, out, B, T);
+  else conv1out_fwd_kernel<0><<<(unsigned)grid, 256, (size_t)k * C * 4, (cudaStream_t)stream>>>(X, x_bs, (int)C, k, w, bias, out, B, T);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
 
-int ag_conv1out_dgrad(const float* g, const float* w, float* dX, int64_t dx_bs, int64_t C, int32_t k, int64_t B, int64_t T,
+int ag_conv1out_dgrad(const float* g, const float* w, void* dX, int32_t dx_dtype, int64_t dx_bs, int64_t C, int32_t k, int64_t B, int64_t T,
                       void* stream) {
   AG_CHECK_ARG(g && w && dX && B > 0 && B < 65536 && T > 0 && C > 0 && C % 4 == 0 && C <= 512 && k > 0 && k <= 4 && dx_bs % 4 == 0,
                "ag_conv1out_dgrad: bad args");
-  AG_CHECK_ARG(((reinterpret_cast<uintptr_t>(dX) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, "ag_conv1out_dgrad: unaligned");
+  AG_CHECK_ARG((reinterpret_cast<uintptr_t>(dX) & (dx_dtype ? 7 : 15)) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+               "ag_conv1out_dgrad: unaligned");
   const int rpb = 64;
   dim3 grid((unsigned)((T + k - 1 + rpb - 1) / rpb), (unsigned)B);
-  conv1out_dgrad_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(g, w, dX, dx_bs, (int)C, k, T, rpb);
+  if (dx_dtype) conv1out_dgrad_kernel<4, 1><<<grid, 128, 0, (cudaStream_t)stream>>>(g, w, dX, dx_bs, (int)C, k, T, rpb);
+  else conv1out_dgrad_kernel<4, 0><<<grid, 128, 0, (cudaStream_t)stream>>>(g, w, dX, dx_bs, (int)C, k, T, rpb);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
 
-int ag_conv1out_wgrad(const float* g, const float* X, int64_t x_bs, int64_t C, int32_t k, float* dw, int64_t B, int64_t T,
+int ag_conv1out_wgrad(const float* g, const void* X, int32_t x_dtype, int64_t x_bs, int64_t C, int32_t k, float* dw, int64_t B, int64_t T,
                       void* stream) {
   AG_CHECK_ARG(g && X && dw && B > 0 && B < 65536 && T > 0 && C > 0 && C % 4 == 0 && C <= 508 && k > 0 && k <= 4 && x_bs % 4 == 0,
                "ag_conv1out_wgrad: bad args");
-  AG_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0, "ag_conv1out_wgrad: unaligned");
+  AG_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & (x_dtype ? 7 : 15)) == 0, "ag_conv1out_wgrad: unaligned");
   const int rpb = 1024;
   dim3 grid((unsigned)((T + k - 1 + rpb - 1) / rpb), (unsigned)B);
-  conv1out_wgrad_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(g, X, x_bs, (int)C, k, dw, T, rpb);
+  if (x_dtype) conv1out_wgrad_kernel<4, 1><<<grid, 128, 0, (cudaStream_t)stream>>>(g, X, x_bs, (int)C, k, dw, T, rpb);
+  else conv1out_wgrad_kernel<4, 0><<<grid, 128, 0, (cudaStream_t)stream>>>(g, X, x_bs, (int)C, k, dw, T, rpb);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

@@ -145,17 +145,21 @@ __global__ void ew_grad_kernel(const ag_ew_desc d) {
     const int64_t t = r - d.pad_l;
     float v = 0.f;
     if (t >= 0 && t < d.T && (!d.len || t < d.len[b])) {
-      if (d.g1) v += d.g1[b * d.g1_bs + t * d.g1_rs + c * d.g1_cs];
-      if (d.g2) v += d.g2[b * d.g2_bs + t * d.g2_rs + c * d.g2_cs];
-      if (d.act) v *= (d.act[b * d.a_bs + t * d.a_rs + c] > 0.f) ? 1.f : d.slope;
-      if (d.acc) d.acc[b * d.acc_bs + t * d.acc_rs + c] += v;
+      if (d.g1) v += ld_any(d.g1, b * d.g1_bs + t * d.g1_rs + c * d.g1_cs, d.g1_dtype);
+      if (d.g2) v += ld_any(d.g2, b * d.g2_bs + t * d.g2_rs + c * d.g2_cs, d.g2_dtype);
+      if (d.act) v *= (ld_any(d.act, b * d.a_bs + t * d.a_rs + c, d.act_dtype) > 0.f) ? 1.f : d.slope;
+      if (d.acc) {
+        const int64_t ai = b * d.acc_bs + t * d.acc_rs + c;
+        st_any(d.acc, ai, ld_any(d.acc, ai, d.acc_dtype) + v, d.acc_dtype);
+      }
     }
-    if (d.out) d.out[i] = v;
+    if (d.out) st_any(d.out, i, v, d.out_dtype);
   }
 }
 
-// 4 channels per thread (float4 everywhere), 32-bit index arithmetic: the scalar kernel above spends its time in three
-// 64-bit divisions per element, not on the memory system.  Requires C % 4 == 0, unit channel strides, strides % 4 == 0.
+// 4 channels per thread (16-byte fp32 / 8-byte bf16 accesses everywhere), 32-bit index arithmetic: the scalar kernel above
+// spends its time in three 64-bit divisions per element, not on the memory system.  Requires C % 4 == 0, unit channel
+// strides, strides % 4 == 0.
 __global__ void __launch_bounds__(256) ew_grad_vec4_kernel(const ag_ew_desc d) {
   const uint32_t C4 = (uint32_t)(d.C >> 2), Tp = (uint32_t)(d.pad_l + d.T + d.pad_r);
   const uint32_t total = (uint32_t)d.B * Tp * C4;
@@ -164,29 +168,29 @@ __global__ void __launch_bounds__(256) ew_grad_vec4_kernel(const ag_ew_desc d) {
     const int64_t t = (int64_t)r - d.pad_l;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (t >= 0 && t < d.T && (!d.len || t < d.len[b])) {
-      if (d.g1) v = __ldg(reinterpret_cast<const float4*>(d.g1 + b * d.g1_bs + t * d.g1_rs + c));
+      if (d.g1) v = ldg4_any(d.g1, b * d.g1_bs + t * d.g1_rs + c, d.g1_dtype);
       if (d.g2) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(d.g2 + b * d.g2_bs + t * d.g2_rs + c));
+        const float4 w = ldg4_any(d.g2, b * d.g2_bs + t * d.g2_rs + c, d.g2_dtype);
         v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
       }
       if (d.act) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(d.act + b * d.a_bs + t * d.a_rs + c));
+        const float4 a = ldg4_any(d.act, b * d.a_bs + t * d.a_rs + c, d.act_dtype);
         v.x *= a.x > 0.f ? 1.f : d.slope; v.y *= a.y > 0.f ? 1.f : d.slope;
         v.z *= a.z > 0.f ? 1.f : d.slope; v.w *= a.w > 0.f ? 1.f : d.slope;
       }
       if (d.acc) {
-        float4* q = reinterpret_cast<float4*>(d.acc + b * d.acc_bs + t * d.acc_rs + c);
-        float4 o = *q;
+        const int64_t ai = b * d.acc_bs + t * d.acc_rs + c;
+        float4 o = ld4_plain_any(d.acc, ai, d.acc_dtype);
         o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
-        *q = o;
+        st4_any(d.acc, ai, o, d.acc_dtype);
       }
     }
-    if (d.out) reinterpret_cast<float4*>(d.out)[i] = v;
+    if (d.out) st4_any(d.out, (int64_t)i << 2, v, d.out_dtype);
   }
 }
 
 // out[c] += sum over rows; block = 32 columns x 8 row lanes, grid.y splits the rows.
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ in, int64_t bs, int64_t rs, int64_t T,
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ in, int dtype, int64_t bs, int64_t rs, int64_t T,
                                                      int64_t M, int64_t C, float* __restrict__ out, int64_t rows_per) {
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ i
   if (c < C)
     for (int64_t m = m0 + ry; m < m1; m += 8) {
       const int64_t b = m / T;
-      acc += in[b * bs + (m - b * T) * rs + c];
+      acc += ld_any(in, b * bs + (m - b * T) * rs + c, dtype);
     }
   red[ry][cx] = acc;
   __syncthreads();
@@ -211,23 +215,23 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ i
 
 // C % 4 == 0, C <= 128, aligned rows: one block per (row chunk, batch) -- no index division; thread = (4 channels, row lane),
 // float4 loads, the row lanes meet in shared memory, one set of atomics per block.
-__global__ void __launch_bounds__(256) colsum_vec4_kernel(const float* __restrict__ in, int64_t bs, int64_t rs, int64_t T, int C4,
+__global__ void __launch_bounds__(256) colsum_vec4_kernel(const void* __restrict__ in, int dtype, int64_t bs, int64_t rs, int64_t T, int C4,
                                                           float* __restrict__ out, int rows_per) {
   __shared__ float4 red[256];
   const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4, nrl = 256 / C4;
   const int64_t t0 = (int64_t)blockIdx.x * rows_per, t1 = min(T, t0 + rows_per);
-  const float* p = in + (int64_t)blockIdx.y * bs + 4 * c4;
+  const int64_t p = (int64_t)blockIdx.y * bs + 4 * c4;      // element index of (batch, row 0, this thread's channels)
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a;
   if (rl < nrl) {
     int64_t t = t0 + rl;
     for (; t + nrl < t1; t += 2 * nrl) {                 // two independent loads in flight per thread
-      const float4 v = __ldg(reinterpret_cast<const float4*>(p + t * rs));
-      const float4 w = __ldg(reinterpret_cast<const float4*>(p + (t + nrl) * rs));
+      const float4 v = ldg4_any(in, p + t * rs, dtype);
+      const float4 w = ldg4_any(in, p + (t + nrl) * rs, dtype);
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
       a2.x += w.x; a2.y += w.y; a2.z += w.z; a2.w += w.w;
     }
     if (t < t1) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(p + t * rs));
+      const float4 v = ldg4_any(in, p + t * rs, dtype);
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
     a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w;
@@ -273,15 +277,15 @@ __global__ void __launch_bounds__(256) outer_dact_kernel(const float* __restrict
 }
 
 // generic strided 3-D copy / accumulate: dst[b,t,c] (+)= src[b,t,c]
-__global__ void copy3d_kernel(float* __restrict__ dst, int64_t d_bs, int64_t d_rs, int64_t d_cs,
-                              const float* __restrict__ src, int64_t s_bs, int64_t s_rs, int64_t s_cs,
-                              int64_t B, int64_t T, int64_t Cn, int accumulate) {
+__global__ void copy3d_kernel(void* __restrict__ dst, int64_t d_bs, int64_t d_rs, int64_t d_cs,
+                              const void* __restrict__ src, int64_t s_bs, int64_t s_rs, int64_t s_cs,
+                              int64_t B, int64_t T, int64_t Cn, int accumulate, int src_dtype, int dst_dtype) {
   const int64_t total = B * T * Cn;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t c = i % Cn, t = (i / Cn) % T, b = i / (Cn * T);
-    const float v = src[b * s_bs + t * s_rs + c * s_cs];
-    float* q = dst + b * d_bs + t * d_rs + c * d_cs;
-    *q = accumulate ? (*q + v) : v;
+    const float v = ld_any(src, b * s_bs + t * s_rs + c * s_cs, src_dtype);
+    const int64_t q = b * d_bs + t * d_rs + c * d_cs;
+    st_any(dst, q, accumulate ? (ld_any(dst, q, dst_dtype) + v) : v, dst_dtype);
   }
 }
 
@@ -390,12 +394,13 @@ int ag_bce_const_fused(const float* x, int64_t ld, const int32_t* len, float tar
 int ag_ew_grad(const ag_ew_desc* d, void* stream) {
   AG_CHECK_ARG(d && d->B > 0 && d->T > 0 && d->C > 0 && (d->out || d->acc), "ag_ew_grad: bad args");
   const int64_t total = d->B * (d->pad_l + d->T + d->pad_r) * d->C;
-  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  auto al = [](const void* p, int dt) { return (reinterpret_cast<uintptr_t>(p) & (dt ? 7 : 15)) == 0; };   // 4 elements
   const bool vec = d->C % 4 == 0 && total / 4 < (1ll << 31) &&
-                   (!d->g1 || (d->g1_cs == 1 && d->g1_bs % 4 == 0 && d->g1_rs % 4 == 0 && al16(d->g1))) &&
-                   (!d->g2 || (d->g2_cs == 1 && d->g2_bs % 4 == 0 && d->g2_rs % 4 == 0 && al16(d->g2))) &&
-                   (!d->act || (d->a_bs % 4 == 0 && d->a_rs % 4 == 0 && al16(d->act))) &&
-                   (!d->acc || (d->acc_bs % 4 == 0 && d->acc_rs % 4 == 0 && al16(d->acc))) && (!d->out || al16(d->out));
+                   (!d->g1 || (d->g1_cs == 1 && d->g1_bs % 4 == 0 && d->g1_rs % 4 == 0 && al(d->g1, d->g1_dtype))) &&
+                   (!d->g2 || (d->g2_cs == 1 && d->g2_bs % 4 == 0 && d->g2_rs % 4 == 0 && al(d->g2, d->g2_dtype))) &&
+                   (!d->act || (d->a_bs % 4 == 0 && d->a_rs % 4 == 0 && al(d->act, d->act_dtype))) &&
+                   (!d->acc || (d->acc_bs % 4 == 0 && d->acc_rs % 4 == 0 && al(d->acc, d->acc_dtype))) &&
+                   (!d->out || al(d->out, d->out_dtype));
   if (vec) {
     ew_grad_vec4_kernel<<<grid_for(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(*d);
     AG_LAUNCH_CHECK();
@@ -405,12 +410,12 @@ int ag_ew_grad(const ag_ew_desc* d, void* stream) {
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
-int ag_colsum(const float* in, int64_t bs, int64_t rs, int64_t B, int64_t T, int64_t C, float* out, void* stream) {
+int ag_colsum(const void* in, int32_t dtype, int64_t bs, int64_t rs, int64_t B, int64_t T, int64_t C, float* out, void* stream) {
   AG_CHECK_ARG(in && out && B > 0 && T > 0 && C > 0, "ag_colsum: bad args");
-  if (C % 4 == 0 && C <= 128 && bs % 4 == 0 && rs % 4 == 0 && B < 65536 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+  if (C % 4 == 0 && C <= 128 && bs % 4 == 0 && rs % 4 == 0 && B < 65536 && (reinterpret_cast<uintptr_t>(in) & (dtype ? 7 : 15)) == 0) {
     const int rows_per = 2048;
     dim3 grid((unsigned)((T + rows_per - 1) / rows_per), (unsigned)B);
-    colsum_vec4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, bs, rs, T, (int)(C / 4), out, rows_per);
+    colsum_vec4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, dtype, bs, rs, T, (int)(C / 4), out, rows_per);
     AG_LAUNCH_CHECK();
     return AG_OK;
   }
@@ -421,15 +426,16 @@ int ag_colsum(const float* in, int64_t bs, int64_t rs, int64_t B, int64_t T, int
   int64_t rows_per = (M + gy - 1) / gy;
   if (rows_per < 64) rows_per = 64;
   gy = (M + rows_per - 1) / rows_per;
-  colsum_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(in, bs, rs, T, M, C, out, rows_per);
+  colsum_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(in, dtype, bs, rs, T, M, C, out, rows_per);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
-int ag_copy3d(float* dst, int64_t d_bs, int64_t d_rs, int64_t d_cs, const float* src, int64_t s_bs, int64_t s_rs,
-              int64_t s_cs, int64_t B, int64_t T, int64_t Cn, int32_t accumulate, void* stream) {
+int ag_copy3d(void* dst, int64_t d_bs, int64_t d_rs, int64_t d_cs, const void* src, int64_t s_bs, int64_t s_rs,
+              int64_t s_cs, int64_t B, int64_t T, int64_t Cn, int32_t accumulate, int32_t src_dtype, int32_t dst_dtype,
+              void* stream) {
   AG_CHECK_ARG(dst && src && B > 0 && T > 0 && Cn > 0, "ag_copy3d: bad args");
   copy3d_kernel<<<grid_for(B * T * Cn, 256), 256, 0, (cudaStream_t)stream>>>(dst, d_bs, d_rs, d_cs, src, s_bs, s_rs, s_cs, B, T,
-                                                                            Cn, accumulate);
+                                                                            Cn, accumulate, src_dtype, dst_dtype);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

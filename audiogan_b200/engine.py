@@ -7,6 +7,8 @@ Three coarse Functions cover the whole hot path (plus plan._PackFn for the weigh
 Every arithmetic step is a call into libaudiogan_b200.so (kernels.py); torch is used for device
 memory, views and autograd bookkeeping only.
 """
+import os
+
 import torch
 from torch.autograd.function import once_differentiable
 
@@ -17,12 +19,22 @@ GPAD = 8        # zero rows either side of the generator's dense channel-last bu
 DPAD = 3        # zero rows either side of the discriminator's channel-last activations
 
 
-def _zeros(*shape, device):
-    return torch.zeros(*shape, device=device, dtype=torch.float32)
+# bf16 mode keeps the conv stacks' activations AND their gradients in HBM as bf16: they only feed tensor-core GEMMs (which
+# round their operands to bf16 anyway) and HBM-bound element-wise kernels, so the storage type sets the step's memory
+# traffic, not its accuracy.  AUDIOGAN_ACT=fp32 keeps fp32 storage (the A/B switch used for profiles/).
+_ACT_BF16 = os.environ.get("AUDIOGAN_ACT", "bf16") != "fp32"
 
 
-def _empty(*shape, device):
-    return torch.empty(*shape, device=device, dtype=torch.float32)
+def _adt(plan):
+    return torch.bfloat16 if (plan.mode == "bf16" and _ACT_BF16) else torch.float32
+
+
+def _zeros(*shape, device, dtype=torch.float32):
+    return torch.zeros(*shape, device=device, dtype=dtype)
+
+
+def _empty(*shape, device, dtype=torch.float32):
+    return torch.empty(*shape, device=device, dtype=dtype)
 
 
 # =========================================================================================
@@ -67,7 +79,8 @@ class _GenFn(torch.autograd.Function):
         L = T * F
         Lp = L + 2 * GPAD
         # frame assembly into channel 0 of the dense buffer (audiogan.py:462-464)
-        Xd = _empty(B, Lp, CT, device=dev)                  # CT = padded channel count (slots of 8, plan.py)
+        adt = _adt(plan)
+        Xd = _empty(B, Lp, CT, device=dev, dtype=adt)       # CT = padded channel count (slots of 8, plan.py)
         Xd[:, :GPAD].zero_()
         Xd[:, GPAD + L:].zero_()
         Xd[:, GPAD:GPAD + L, 1:plan.coff[0]].zero_()        # pad channels of the waveform slot
@@ -77,7 +90,7 @@ class _GenFn(torch.autograd.Function):
         for li, (k, s, hid, out) in enumerate(struct):                       # audiogan.py:278-283, :465-467
             p, pd, Lh = (k - 1) // 2, s // 2, L // s
             cin = plan.cinp[li]                             # padded channel prefix this block reads == slot it writes
-            Hh = _empty(B, Lh + 2, hid, device=dev)
+            Hh = _empty(B, Lh + 2, hid, device=dev, dtype=adt)
             Hh[:, 0].zero_()
             Hh[:, Lh + 1].zero_()
             K.gemm_nt(B * Lh, hid, k * cin, (Xd, (GPAD - p) * CT), (Lh, Lp * CT, s * CT, cin, CT),
@@ -114,7 +127,8 @@ class _GenFn(torch.autograd.Function):
         if gx is not None:
             gx = gx.contiguous()
             # ---- final conv (audiogan.py:403-407): data gradient into all CT channels, weight gradient
-            dXd = _empty(B, Lp, CT, device=dev)
+            adt = Xd.dtype
+            dXd = _empty(B, Lp, CT, device=dev, dtype=adt)
             K.conv1out_dgrad(gx, plan.Poff("f.w"), (dXd, (GPAD - 1) * CT), Lp * CT, CT, 3, B, L)
             if wgrad:
                 K.conv1out_wgrad(gx, (Xd, (GPAD - 1) * CT), Lp * CT, CT, 3, plan.GPoff("f.w"), B, L)
@@ -124,7 +138,7 @@ class _GenFn(torch.autograd.Function):
                 p, pd, Lh, kd = (k - 1) // 2, s // 2, L // s, k - 1
                 Hh = hh[li]
                 # dyl = d(block output) * lrelu'(output); also feeds the dense skip (audiogan.py:281-283)
-                dyl = _empty(B, L + 2 * pd, out, device=dev)
+                dyl = _empty(B, L + 2 * pd, out, device=dev, dtype=adt)
                 slice_off = GPAD * CT + cin
                 K.ew_grad(B, L, out, out=dyl, pad=(pd, pd), g1=(dXd, slice_off), g1_str=(Lp * CT, CT, 1),
                           act=(Xd, slice_off), act_str=(Lp * CT, CT),
@@ -133,7 +147,7 @@ class _GenFn(torch.autograd.Function):
                 if wgrad:
                     K.colsum((dyl, pd * out), (L + 2 * pd) * out, out, B, L, out, plan.GPoff("d%d.b" % li))
                 # transposed-conv data gradient = strided conv over dyl, times lrelu'(hidden)
-                dH = _empty(B, Lh + 2, hid, device=dev)
+                dH = _empty(B, Lh + 2, hid, device=dev, dtype=adt)
                 dH[:, 0].zero_()
                 dH[:, Lh + 1].zero_()
                 K.gemm_nt(B * Lh, hid, kd * out, dyl, (Lh, (L + 2 * pd) * out, s * out), plan.Poff("d%d.wg" % li), kd * out,
@@ -204,7 +218,7 @@ class _DiscCNNFn(torch.autograd.Function):
         cin, Tin = 1, L
         for i, (k, s, cout) in enumerate(struct):
             Tout = (Tin + s - 1) // s
-            a = _empty(B, Tout + 2 * DPAD, cout, device=dev)
+            a = _empty(B, Tout + 2 * DPAD, cout, device=dev, dtype=_adt(plan))
             a[:, :DPAD].zero_()
             a[:, DPAD + Tout:].zero_()
             if cin == 1 and k <= 8 and cout % 4 == 0 and (k - 1) // 2 == DPAD:
@@ -243,7 +257,8 @@ class _DiscCNNFn(torch.autograd.Function):
             PL = ntap - 1                                  # left pad of dy: the data-gradient window reaches ntap-1 rows back
             geo = ((Tout + 2 * DPAD) * cout, cout)         # geometry of the forward activation buffers
             gdy = ((PL + Tout + DPAD) * cout, cout)        # geometry of dy
-            dy = _empty(B, PL + Tout + DPAD, cout, device=dev)
+            adt = a_out.dtype
+            dy = _empty(B, PL + Tout + DPAD, cout, device=dev, dtype=adt)
             kw = {}
             if g is not None:                  # (B, C, T) tensor with arbitrary strides
                 kw.update(g1=g, g1_str=(g.stride(0), g.stride(2), g.stride(1)))
@@ -258,7 +273,8 @@ class _DiscCNNFn(torch.autograd.Function):
                           plan.GPoff("c%d.w" % i), k * cin + 1, ones_col=True)
             if i > 0 or need_dx:
                 Mp = (Tin + DPAD + s - 1) // s
-                dXn = _empty(B, Tin + 2 * DPAD, cin, device=dev)
+                # the gradient of the raw waveform (layer 0) is a caller-visible fp32 tensor
+                dXn = _empty(B, Tin + 2 * DPAD, cin, device=dev, dtype=adt if i > 0 else torch.float32)
                 if s * Mp < Tin + 2 * DPAD:
                     dXn[:, s * Mp:].zero_()
                 K.gemm_nt(B * Mp, s * cin, ntap * cout, dy, (Mp, gdy[0], cout), plan.Poff("c%d.wg" % i), ntap * cout,
@@ -375,7 +391,7 @@ class _DiscTailFn(torch.autograd.Function):
             K.gemm_tn(B, 8 * H, E + 2, dgsum, (B, 0, 8 * H), c1, (B, 0, E + 2), plan.GPoff("wih", Cf), ldi)
         dfeat = None
         if ctx.needs_input_grad[2]:
-            dfeat = _zeros(B, T6, Cf, device=dev) if Tm < T6 else _empty(B, T6, Cf, device=dev)
+            dfeat = _zeros(B, T6, Cf, device=dev, dtype=feat.dtype) if Tm < T6 else _empty(B, T6, Cf, device=dev, dtype=feat.dtype)
             K.gemm_nt(M, Cf, 8 * H, dgo, flat(8 * H), plan.Poff("wiht"), 8 * H, dfeat, (Tm, T6 * Cf, Cf))
             dfeat = dfeat.permute(0, 2, 1)
         dc = None

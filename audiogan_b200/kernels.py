@@ -133,16 +133,18 @@ def ew_grad(B, T, Cn, out=None, pad=(0, 0), g1=None, g1_str=(0, 0, 0), g2=None, 
     d.pad_l, d.pad_r = pad
     d.acc = addr(acc)
     d.acc_bs, d.acc_rs = acc_str
+    d.g1_dtype, d.g2_dtype, d.act_dtype = _dtype_of(g1), _dtype_of(g2), _dtype_of(act)
+    d.acc_dtype, d.out_dtype = _dtype_of(acc), _dtype_of(out)
     A.call("ag_ew_grad", C.byref(d), A.stream())
 
 
 def conv1in_fwd(x, x_ld, w, bias, out, out_bs, k, s, Cn, B, T, length, slope=LRELU_SLOPE):
-    A.call("ag_conv1in_fwd", addr(x), x_ld, addr(w), addr(bias), addr(out), out_bs, k, s, Cn, B, T, addr(length), float(slope),
+    A.call("ag_conv1in_fwd", addr(x), x_ld, addr(w), addr(bias), addr(out), _dtype_of(out), out_bs, k, s, Cn, B, T, addr(length), float(slope),
            A.stream())
 
 
 def conv1in_wgrad(dy, dy_bs, x, x_ld, dw, k, s, Cn, B, T):
-    A.call("ag_conv1in_wgrad", addr(dy), dy_bs, addr(x), x_ld, addr(dw), k, s, Cn, B, T, A.stream())
+    A.call("ag_conv1in_wgrad", addr(dy), _dtype_of(dy), dy_bs, addr(x), x_ld, addr(dw), k, s, Cn, B, T, A.stream())
 
 
 def outer_dact(g, w, act, out, M, N, slope=LRELU_SLOPE):
@@ -151,24 +153,24 @@ def outer_dact(g, w, act, out, M, N, slope=LRELU_SLOPE):
 
 
 def colsum(src, bs, rs, B, T, Cn, out):
-    A.call("ag_colsum", addr(src), bs, rs, B, T, Cn, addr(out), A.stream())
+    A.call("ag_colsum", addr(src), _dtype_of(src), bs, rs, B, T, Cn, addr(out), A.stream())
 
 
 def copy3d(dst, d_str, src, s_str, B, T, Cn, accumulate=False):
     A.call("ag_copy3d", addr(dst), d_str[0], d_str[1], d_str[2], addr(src), s_str[0], s_str[1], s_str[2], B, T, Cn,
-           1 if accumulate else 0, A.stream())
+           1 if accumulate else 0, _dtype_of(src), _dtype_of(dst), A.stream())
 
 
 def conv1out_fwd(X, x_bs, Cn, k, w, bias, out, B, T):
-    A.call("ag_conv1out_fwd", addr(X), x_bs, Cn, k, addr(w), addr(bias), addr(out), B, T, A.stream())
+    A.call("ag_conv1out_fwd", addr(X), _dtype_of(X), x_bs, Cn, k, addr(w), addr(bias), addr(out), B, T, A.stream())
 
 
 def conv1out_dgrad(g, w, dX, dx_bs, Cn, k, B, T):
-    A.call("ag_conv1out_dgrad", addr(g), addr(w), addr(dX), dx_bs, Cn, k, B, T, A.stream())
+    A.call("ag_conv1out_dgrad", addr(g), addr(w), addr(dX), _dtype_of(dX), dx_bs, Cn, k, B, T, A.stream())
 
 
 def conv1out_wgrad(g, X, x_bs, Cn, k, dw, B, T):
-    A.call("ag_conv1out_wgrad", addr(g), addr(X), x_bs, Cn, k, addr(dw), B, T, A.stream())
+    A.call("ag_conv1out_wgrad", addr(g), addr(X), _dtype_of(X), x_bs, Cn, k, addr(dw), B, T, A.stream())
 
 
 def rowgroup_sum(src, out, B, T, N):

@@ -277,6 +277,7 @@ def fourth_moment(v):                                            # audiogan.py:3
 def calc_dists(hidden_states, hidden_state_lengths):             # audiogan.py:341-359 ("next" row)
     means_d, stds_d, fourth_d = [], [], []
     for h, l in zip(hidden_states, hidden_state_lengths):
+        h = h.float()            # bf16 mode hands the conv activations back in their bf16 storage type
         l = l.to(h.device)
         mask = length_mask((h.shape[0], h.shape[2]), l)
         lf = l.unsqueeze(1).float()

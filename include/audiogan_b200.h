@@ -204,17 +204,19 @@ int ag_bce_const_fused(const float* x, int64_t ld, const int32_t* len, float tar
  * ------------------------------------------------------------------------------------------ */
 typedef struct ag_ew_desc {
   int64_t B, T, C;
-  const float* g1; int64_t g1_bs, g1_rs, g1_cs;
-  const float* g2; int64_t g2_bs, g2_rs, g2_cs;
-  const float* act; int64_t a_bs, a_rs;
+  const void* g1; int64_t g1_bs, g1_rs, g1_cs;
+  const void* g2; int64_t g2_bs, g2_rs, g2_cs;
+  const void* act; int64_t a_bs, a_rs;
   float slope; int32_t reserved;
   const int32_t* len;
-  float* out; int64_t pad_l, pad_r;
-  float* acc; int64_t acc_bs, acc_rs;
+  void* out; int64_t pad_l, pad_r;
+  void* acc; int64_t acc_bs, acc_rs;
+  int32_t g1_dtype, g2_dtype, act_dtype, acc_dtype, out_dtype, reserved2;   /* 0 = fp32, 1 = bf16 (bf16 mode stores the conv
+                                                                               stacks' activations and gradients as bf16) */
 } ag_ew_desc;
 int ag_ew_grad(const ag_ew_desc* d, void* stream);
-/* out[c] += sum_{b,t} in[b*bs + t*rs + c]  (bias gradients); out must be initialised. */
-int ag_colsum(const float* in, int64_t bs, int64_t rs, int64_t B, int64_t T, int64_t C, float* out, void* stream);
+/* out[c] += sum_{b,t} in[b*bs + t*rs + c]  (bias gradients); out must be initialised.  in: dtype 0 fp32 / 1 bf16. */
+int ag_colsum(const void* in, int32_t dtype, int64_t bs, int64_t rs, int64_t B, int64_t T, int64_t C, float* out, void* stream);
 /* Rank-1 data gradient with LeakyReLU' (backward of the classifier's 512 -> 1 layer, audiogan.py:508-512):
  * out[m, n] = g[m] * w[n] * (act[m, n] > 0 ? 1 : slope); act / out packed [M, N], dtype 0 fp32 / 1 bf16, N % 4 == 0. */
 int ag_outer_dact(const float* g, const float* w, const void* act, int32_t act_dtype, void* out, int32_t out_dtype, int64_t M,
@@ -225,11 +227,11 @@ int ag_outer_dact(const float* g, const float* w, const void* act, int32_t act_d
  * (audiogan.py:527-536 with C_in = 1), and its weight / bias gradient.  HBM-bound direct kernels (K = k is too small
  * for tensor cores).  x: zero-padded waveform rows (tap j of output t at x[b*x_ld + s*t + j]); out / dy: channel-last
  * [B, rows, C] with batch stride out_bs / dy_bs (pointers at row t = 0); w [C, k]; dw [C, k + 1] (column k = bias
- * gradient), accumulated with atomics (zero it first).  C % 4 == 0.
+ * gradient), accumulated with atomics (zero it first).  C % 4 == 0.  out / dy: dtype 0 fp32 / 1 bf16.
  * ------------------------------------------------------------------------------------------ */
-int ag_conv1in_fwd(const float* x, int64_t x_ld, const float* w, const float* bias, float* out, int64_t out_bs, int32_t k,
-                   int32_t s, int64_t C, int64_t B, int64_t T, const int32_t* len, float slope, void* stream);
-int ag_conv1in_wgrad(const float* dy, int64_t dy_bs, const float* x, int64_t x_ld, float* dw, int32_t k, int32_t s, int64_t C,
+int ag_conv1in_fwd(const float* x, int64_t x_ld, const float* w, const float* bias, void* out, int32_t out_dtype, int64_t out_bs,
+                   int32_t k, int32_t s, int64_t C, int64_t B, int64_t T, const int32_t* len, float slope, void* stream);
+int ag_conv1in_wgrad(const void* dy, int32_t dy_dtype, int64_t dy_bs, const float* x, int64_t x_ld, float* dw, int32_t k, int32_t s, int64_t C,
                      int64_t B, int64_t T, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -239,18 +241,20 @@ int ag_conv1in_wgrad(const float* dy, int64_t dy_bs, const float* x, int64_t x_l
  *   fwd:   out[b,t] = bias + sum_{j<k,c<C} X[b, t+j, c] * w[j*C+c]
  *   dgrad: dX[b, t', c] = sum_j g[b, t'-j] * w[j*C+c]        for t' in [0, T+k-1)   (plain store)
  *   wgrad: dw[j*C+c] += sum_{b,t} g[b,t] * X[b, t+j, c];  dw[k*C] += sum_{b,t} g[b,t]
+ * X / dX: dtype 0 fp32 / 1 bf16 (strides in elements); out, g, w, dw fp32.
  * ------------------------------------------------------------------------------------------ */
-int ag_conv1out_fwd(const float* X, int64_t x_bs, int64_t C, int32_t k, const float* w, const float* bias, float* out,
-                    int64_t B, int64_t T, void* stream);
-int ag_conv1out_dgrad(const float* g, const float* w, float* dX, int64_t dx_bs, int64_t C, int32_t k, int64_t B, int64_t T,
-                      void* stream);
-int ag_conv1out_wgrad(const float* g, const float* X, int64_t x_bs, int64_t C, int32_t k, float* dw, int64_t B, int64_t T,
-                      void* stream);
+int ag_conv1out_fwd(const void* X, int32_t x_dtype, int64_t x_bs, int64_t C, int32_t k, const float* w, const float* bias,
+                    float* out, int64_t B, int64_t T, void* stream);
+int ag_conv1out_dgrad(const float* g, const float* w, void* dX, int32_t dx_dtype, int64_t dx_bs, int64_t C, int32_t k, int64_t B,
+                      int64_t T, void* stream);
+int ag_conv1out_wgrad(const float* g, const void* X, int32_t x_dtype, int64_t x_bs, int64_t C, int32_t k, float* dw, int64_t B,
+                      int64_t T, void* stream);
 
 /* dst[b*d_bs + t*d_rs + c*d_cs] (+)= src[b*s_bs + t*s_rs + c*s_cs]: frame assembly into the dense
  * generator buffer (audiogan.py:462-464) and its gradient read-back. */
-int ag_copy3d(float* dst, int64_t d_bs, int64_t d_rs, int64_t d_cs, const float* src, int64_t s_bs, int64_t s_rs,
-              int64_t s_cs, int64_t B, int64_t T, int64_t C, int32_t accumulate, void* stream);
+int ag_copy3d(void* dst, int64_t d_bs, int64_t d_rs, int64_t d_cs, const void* src, int64_t s_bs, int64_t s_rs,
+              int64_t s_cs, int64_t B, int64_t T, int64_t C, int32_t accumulate, int32_t src_dtype, int32_t dst_dtype,
+              void* stream);
 /* out[b, n] = sum_t in[b, t, n] */
 int ag_rowgroup_sum(const float* in, float* out, int64_t B, int64_t T, int64_t N, void* stream);
 /* dst[b, t, c] (channel-last, row stride dst_rs, batch stride dst_bs) <-> src[b, c, t] */

@@ -440,3 +440,81 @@ def test_lstm_generator_tmem_kernel_tracks_fp32_kernel(B, Tn, stops):
     for nm in ("dgates", "dpx"):
         assert rel(c[nm][:, :te], f[nm][:, :te]) < 3e-2, nm
     assert rel(c["dgates16"][:, :te].float(), c["dgates"][:, :te]) < 1e-2
+
+
+@pytest.mark.parametrize("dt", [T.float32, T.bfloat16])
+def test_streaming_kernels_both_storage_types(dt):
+    """ew_grad / colsum / copy3d / conv1out_* / conv1in_* with fp32 and bf16 activation storage (bf16 mode keeps the
+    conv stacks' activations and gradients in HBM as bf16) against plain torch fp32 on the same (rounded) inputs."""
+    from audiogan_b200 import kernels as K
+    T.manual_seed(3)
+    B, Tn, Cn, pl, pr = 3, 37, 24, 2, 3
+    q = lambda x: x.to(dt).float()          # the values the kernel sees
+    tol = 1e-6 if dt == T.float32 else 8e-3
+    g1, g2, act, acc0 = (q(T.randn(B, Tn, Cn)) for _ in range(4))
+    ln = T.tensor([37, 20, 1], dtype=T.int32)
+    out = T.empty(B, pl + Tn + pr, Cn, device="cuda", dtype=dt)
+    acc = acc0.to(dt).cuda()
+    K.ew_grad(B, Tn, Cn, out=out, pad=(pl, pr), g1=g1.to(dt).cuda(), g1_str=(Tn * Cn, Cn, 1), g2=g2.to(dt).cuda(),
+              g2_str=(Tn * Cn, Cn, 1), act=act.to(dt).cuda(), act_str=(Tn * Cn, Cn), length=ln.cuda(), acc=acc, acc_str=(Tn * Cn, Cn))
+    m = (T.arange(Tn)[None] < ln[:, None]).float()[:, :, None]
+    v = (g1 + g2) * T.where(act > 0, 1.0, 0.01) * m
+    ref = T.zeros(B, pl + Tn + pr, Cn)
+    ref[:, pl:pl + Tn] = v
+    assert rel(out, ref) < tol and rel(acc, acc0 + v) < tol
+    # strided (scalar-path) g1: a (B, C, T) tensor read as [b, t, c]
+    g1t = g1.permute(0, 2, 1).contiguous().to(dt).cuda()
+    out2 = T.empty(B, Tn, Cn, device="cuda", dtype=dt)
+    K.ew_grad(B, Tn, Cn, out=out2, g1=g1t, g1_str=(Cn * Tn, 1, Tn))
+    assert rel(out2, g1) < tol
+    # colsum (vector and generic paths)
+    for Cc in (24, 7):
+        src = q(T.randn(B, Tn, Cc))
+        o = T.zeros(Cc, device="cuda")
+        K.colsum(src.to(dt).cuda(), Tn * Cc, Cc, B, Tn, Cc, o)
+        assert rel(o, src.sum((0, 1))) < 1e-5
+    # copy3d: fp32 frames -> channel 0 of a channel-last buffer of the storage type, and back (accumulating)
+    fr = T.randn(B, Tn)
+    buf = T.zeros(B, Tn, Cn, device="cuda", dtype=dt)
+    K.copy3d(buf, (Tn * Cn, Cn, 0), fr.cuda(), (Tn, 1, 0), B, Tn, 1)
+    assert rel(buf[:, :, 0], q(fr)) < 1e-6 and float(buf[:, :, 1:].abs().max()) == 0
+    back = T.ones(B, Tn, device="cuda")
+    K.copy3d(back, (Tn, 1, 0), buf, (Tn * Cn, Cn, 0), B, Tn, 1, accumulate=True)
+    assert rel(back, q(fr) + 1) < 1e-6
+    # conv1out: Conv1d(C -> 1, k = 3) over a channel-last buffer, its data and weight gradients
+    k = 3
+    X = q(T.randn(B, Tn + k - 1, Cn))
+    w, b = T.randn(k * Cn), T.randn(1)
+    y = T.empty(B, Tn, device="cuda")
+    K.conv1out_fwd(X.to(dt).cuda(), (Tn + k - 1) * Cn, Cn, k, w.cuda(), b.cuda(), y, B, Tn)
+    wt = w.view(k, Cn).t().unsqueeze(0)                      # [1, C, k]
+    yr = F.conv1d(X.permute(0, 2, 1), wt, b)[:, 0]
+    assert rel(y, yr) < 1e-5
+    g = T.randn(B, Tn)
+    dX = T.empty(B, Tn + k - 1, Cn, device="cuda", dtype=dt)
+    K.conv1out_dgrad(g.cuda(), w.cuda(), dX, (Tn + k - 1) * Cn, Cn, k, B, Tn)
+    Xr = X.clone().requires_grad_()
+    wr = wt.clone().requires_grad_()
+    F.conv1d(Xr.permute(0, 2, 1), wr, b)[:, 0].backward(g)
+    assert rel(dX, Xr.grad) < tol
+    dw = T.zeros(k * Cn + 1, device="cuda")
+    K.conv1out_wgrad(g.cuda(), X.to(dt).cuda(), (Tn + k - 1) * Cn, Cn, k, dw, B, Tn)
+    assert rel(dw[:-1].view(k, Cn), wr.grad[0].t()) < 1e-5 and abs(float(dw[-1]) - float(g.sum())) < 1e-4
+    # conv1in: Conv1d(1 -> C, k = 7, s = 2) + bias + LeakyReLU + mask on a zero-padded waveform, weight/bias gradient
+    k, s, Co, L = 7, 2, 16, 60
+    To = (L + s - 1) // s
+    x = T.zeros(B, L + 6)
+    x[:, 3:3 + L] = T.randn(B, L)
+    w1, b1 = T.randn(Co, k), T.randn(Co)
+    ln1 = T.tensor([To, 11, 2], dtype=T.int32)
+    o = T.empty(B, To, Co, device="cuda", dtype=dt)
+    K.conv1in_fwd(x.cuda(), L + 6, w1.cuda(), b1.cuda(), o, To * Co, k, s, Co, B, To, ln1.cuda())
+    m1 = (T.arange(To)[None] < ln1[:, None]).float()[:, None]
+    orf = F.leaky_relu(F.conv1d(x[:, None], w1[:, None], b1, stride=s)[:, :, :To]) * m1
+    assert rel(o, orf.permute(0, 2, 1)) < tol
+    dy = q(T.randn(B, To, Co))
+    dw1 = T.zeros(Co, k + 1, device="cuda")
+    K.conv1in_wgrad(dy.to(dt).cuda(), To * Co, x.cuda(), L + 6, dw1, k, s, Co, B, To)
+    w1r, b1r = w1.clone().requires_grad_(), b1.clone().requires_grad_()
+    F.conv1d(x[:, None], w1r[:, None], b1r, stride=s)[:, :, :To].backward(dy.permute(0, 2, 1))
+    assert rel(dw1[:, :k], w1r.grad) < 1e-5 and rel(dw1[:, k], b1r.grad) < 1e-5
