@@ -501,6 +501,388 @@ static int launch_nt(const ag_gemm_desc* d, cudaStream_t s) {
   return vecc ? launch_nt2<BN, MODE, true>(d, s) : launch_nt2<BN, MODE, false>(d, s);
 }
 
+// ======================================================================================== NT, persistent, TMA-fed A
+// For bf16 activations whose im2col row is ONE contiguous window (every conv / transposed-conv / linear view but the
+// generator's channel-prefix reads), A is a 3-D tensor map {k, t, batch} with strides {a_rs, a_bs} -- overlapping rows
+// are fine for TMA -- and a 128 x 64 box lands in shared memory as the canonical K-major SWIZZLE_128B tile: no producer
+// warps, no register staging.  One persistent CTA per SM walks the tiles; the accumulator is double-buffered in TMEM
+// (2 x BN columns) so the 8 epilogue warps drain tile i while the MMA warp runs tile i+1.  Rows are tiled per batch
+// (row tile = (batch, t0): rows past the batch's end are zero-filled by TMA and skipped by the epilogue).
+//   warps 0-7: epilogue (warp w owns TMEM lanes 32*(w&3).., warps w and w+4 take alternate 32-column chunks)
+//   warp 8: TMA producer (one thread)      warp 9: TMEM allocator + MMA issuer (one thread)
+__host__ __device__ constexpr int tma_stages(int BN) { return BN >= 256 ? 3 : (BN >= 128 ? 5 : (BN >= 64 ? 6 : 8)); }
+constexpr int TM_THREADS = 320, TM_NEPI = 256;
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// Lean vector epilogue of one 32-row x CH-column chunk (the persistent kernel is epilogue-bound: the general code above
+// costs ~30 instructions per element in 64-bit index arithmetic and per-row tables).  Everything per row comes from ONE
+// 16-byte table entry {C row offset | -1, row-bias offset, mask position base, mask length}; offsets are 32-bit element
+// offsets (the host checks the spans); the epilogue operands of all 8 rows of a lane are in flight before the first use.
+template <bool CBF, bool AUXBF, int CH>
+__device__ __forceinline__ void epi_chunk_vec(const ag_gemm_desc& d, const float* __restrict__ tr, const int4* __restrict__ rowtab,
+                                              int wq, int lane, int nc, float alpha) {
+  const int q = lane & 7, rs = lane >> 3;
+  const int n = nc + 4 * q, N = (int)d.N, cnin = (int)d.c_nin;
+  const bool nv = 4 * q < CH && n < N;
+  const int n1 = (nv && n >= cnin) ? (int)((uint32_t)n / (uint32_t)cnin) : 0;
+  const int coff = n1 * (int)d.c_n1s + (n - n1 * cnin);
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (nv && d.bias) {
+    const int bm = (int)d.bias_mod;
+    bv = *reinterpret_cast<const float4*>(d.bias + ((bm > 0 && n >= bm) ? (int)((uint32_t)n % (uint32_t)bm) : n));
+  }
+  const int mposl = n1 * (int)d.mask_n1mul;
+  const bool has_skip = d.skip != nullptr, has_dact = d.dact != nullptr, has_rb = d.rowbias != nullptr, has_mask = d.mask_len != nullptr;
+  const float slope = d.slope;
+  int ci[8];
+  uint32_t keep = 0;
+  float4 rb[8];
+  uint2 sk2[AUXBF ? 8 : 1], da2[AUXBF ? 8 : 1];
+  float4 sk4[AUXBF ? 1 : 8], da4[AUXBF ? 1 : 8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int4 rt = rowtab[wq * 32 + it * 4 + rs];
+    const bool ok = nv && rt.x >= 0;
+    ci[it] = ok ? rt.x + coff : -1;
+    keep |= ((!has_mask || (uint32_t)(rt.z + mposl) < (uint32_t)rt.w) ? 1u : 0u) << it;
+    rb[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_rb && ok) rb[it] = *reinterpret_cast<const float4*>(d.rowbias + (rt.y + n));
+    if (AUXBF) {
+      sk2[it] = make_uint2(0u, 0u);
+      da2[it] = make_uint2(0x3f803f80u, 0x3f803f80u);
+      if (has_skip && ok) sk2[it] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(d.skip) + ci[it]);
+      if (has_dact && ok) da2[it] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(d.dact) + ci[it]);
+    } else {
+      sk4[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      da4[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (has_skip && ok) sk4[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.skip) + ci[it]);
+      if (has_dact && ok) da4[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.dact) + ci[it]);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    if (ci[it] < 0) continue;
+    float4 x = *reinterpret_cast<const float4*>(tr + (it * 4 + rs) * TRLD + 4 * q);
+    float4 sk, da;
+    if (AUXBF) {
+      sk = make_float4(__uint_as_float(sk2[it].x << 16), __uint_as_float(sk2[it].x & 0xffff0000u),
+                       __uint_as_float(sk2[it].y << 16), __uint_as_float(sk2[it].y & 0xffff0000u));
+      da = make_float4(__uint_as_float(da2[it].x << 16), __uint_as_float(da2[it].x & 0xffff0000u),
+                       __uint_as_float(da2[it].y << 16), __uint_as_float(da2[it].y & 0xffff0000u));
+    } else {
+      sk = sk4[it];
+      da = da4[it];
+    }
+    x.x = fmaf(x.x, alpha, bv.x) + (rb[it].x + sk.x); x.y = fmaf(x.y, alpha, bv.y) + (rb[it].y + sk.y);
+    x.z = fmaf(x.z, alpha, bv.z) + (rb[it].z + sk.z); x.w = fmaf(x.w, alpha, bv.w) + (rb[it].w + sk.w);
+    if (d.act == 1) {
+      x.x = x.x > 0.f ? x.x : x.x * slope; x.y = x.y > 0.f ? x.y : x.y * slope;
+      x.z = x.z > 0.f ? x.z : x.z * slope; x.w = x.w > 0.f ? x.w : x.w * slope;
+    }
+    if (has_dact) {
+      x.x *= da.x > 0.f ? 1.f : slope; x.y *= da.y > 0.f ? 1.f : slope;
+      x.z *= da.z > 0.f ? 1.f : slope; x.w *= da.w > 0.f ? 1.f : slope;
+    }
+    if (!((keep >> it) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (CBF) {
+      uint2 o;
+      o.x = pack_bf16(x.x, x.y); o.y = pack_bf16(x.z, x.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.C) + ci[it]) = o;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(d.C) + ci[it]) = x;
+    }
+  }
+}
+
+template <int BN, bool VECC>
+__global__ void __launch_bounds__(TM_THREADS, 1)
+gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   int R, int tpb, int ntn, int total_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int STG = tma_stages(BN);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  float* stage_tr = reinterpret_cast<float*>(smem + STG * STAGE_BYTES);          // 8 warps x 32 x TRLD floats
+  int4* rowtab = reinterpret_cast<int4*>(stage_tr + 8 * 32 * TRLD);              // [BM] the vector epilogue's per-row entry
+  uint64_t* full = reinterpret_cast<uint64_t*>(rowtab + BM);
+  uint64_t* empty = full + STG;
+  uint64_t* tfull = empty + STG;          // [2] accumulator ready
+  uint64_t* tempty = tfull + 2;           // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  int64_t* rowoff = reinterpret_cast<int64_t*>(tmem_slot + 2);   // [BM] C row offsets of the tile in the epilogue
+  int* s_b = reinterpret_cast<int*>(rowoff + BM);
+  int* s_t = s_b + BM;
+  int* s_ml = s_t + BM;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = (int)((d.K + BK - 1) / BK);
+  if (tid == 0) {
+    for (int s = 0; s < STG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TM_NEPI / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ epilogue warps
+    float* tr = stage_tr + warp * (32 * TRLD);
+    const int wq = warp & 3, wh = warp >> 2;
+    const float alpha = d.alpha == 0.f ? 1.f : d.alpha;
+    constexpr int CH = BN < 32 ? BN : 32;
+    int lt = 0;
+    const int dbgf = g_nt_dbg_on;
+    const bool dbg = dbgf != 0 && tid == 0;
+    long long t_wait = 0, t_work = 0, q0 = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int mt = tile / ntn, nt = tile - mt * ntn;
+      const int bt = mt / tpb, t0 = (mt - bt * tpb) * BM;
+      const int n0 = nt * BN;
+      const int acc = lt & 1;
+      if (dbg) q0 = clock64();
+      asm volatile("bar.sync 1, %0;" ::"n"(TM_NEPI) : "memory");       // the previous tile's row table is no longer read
+      if (tid < BM) {
+        const int t = t0 + tid;
+        if (t < R) {
+          const int64_t m = (int64_t)bt * R + t;
+          const int64_t b = m / d.c_rpb, tc_ = m - b * d.c_rpb;
+          const int ml = d.mask_len ? d.mask_len[b] : 0;
+          rowoff[tid] = b * d.c_bs + tc_ * d.c_rs;
+          s_b[tid] = (int)b;
+          s_t[tid] = (int)tc_;
+          s_ml[tid] = ml;
+          if (VECC) rowtab[tid] = make_int4((int)(b * d.c_bs + tc_ * d.c_rs), (int)(b * d.rowbias_ld),
+                                            (int)(tc_ * d.mask_tmul + d.mask_toff), ml);
+        } else {
+          rowoff[tid] = -1;
+          if (VECC) rowtab[tid] = make_int4(-1, 0, 0, 0);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TM_NEPI) : "memory");
+      mbar_wait(&tfull[acc], (lt >> 1) & 1);
+      tc_fence_after();
+      if (dbg) { const long long q1 = clock64(); t_wait += q1 - q0; q0 = q1; }
+      const uint32_t tlane = tmem_base + (uint32_t)(acc * ACC_COLS) + ((uint32_t)(wq * 32) << 16);
+#pragma unroll 1
+      for (int c0 = wh * CH; c0 < BN; c0 += 2 * CH) {
+        if (n0 + c0 >= d.N) break;
+        if (!(dbgf & 2)) {
+          uint32_t v[16];
+          tc_ld16(tlane + (uint32_t)c0, v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(tr + lane * TRLD + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (CH == 32) {
+            tc_ld16(tlane + (uint32_t)(c0 + 16), v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(tr + lane * TRLD + 16 + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+        __syncwarp();
+        if (dbgf & 8) {
+        } else if (VECC) {
+          if (d.c_dtype) {
+            if (d.aux_dtype) epi_chunk_vec<true, true, CH>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
+            else epi_chunk_vec<true, false, CH>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
+          } else {
+            if (d.aux_dtype) epi_chunk_vec<false, true, CH>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
+            else epi_chunk_vec<false, false, CH>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
+          }
+        } else {
+          const int64_t n = n0 + c0 + lane;
+          const bool nv = lane < CH && n < d.N;
+          const int64_t n1 = nv ? n / d.c_nin : 0;
+          const int64_t coff = n1 * d.c_n1s + (n - n1 * d.c_nin);
+          const float bv = (nv && d.bias) ? d.bias[d.bias_mod > 0 ? n % d.bias_mod : n] : 0.f;
+#pragma unroll 2
+          for (int r = 0; r < 32; ++r) {
+            const int row = wq * 32 + r;
+            const int64_t crow = rowoff[row];
+            if (crow < 0 || !nv) continue;
+            const int64_t ci = crow + coff;
+            float x = tr[r * TRLD + lane] * alpha + bv;
+            if (d.rowbias) x += d.rowbias[(int64_t)s_b[row] * d.rowbias_ld + n];
+            if (d.skip) x += ld_any(d.skip, ci, d.aux_dtype);
+            if (d.act == 1) x = x > 0.f ? x : x * d.slope;
+            if (d.dact) x *= (ld_any(d.dact, ci, d.aux_dtype) > 0.f) ? 1.f : d.slope;
+            if (d.mask_len) {
+              const int64_t pos = (int64_t)s_t[row] * d.mask_tmul + n1 * d.mask_n1mul + d.mask_toff;
+              if (pos < 0 || pos >= s_ml[row]) x = 0.f;
+            }
+            st_any(d.C, ci, x, d.c_dtype);
+          }
+        }
+        __syncwarp();
+      }
+      // this warp's share of the accumulator is in registers / memory: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (dbg) t_work += clock64() - q0;
+    }
+    if (dbg) {
+      atomicAdd(&g_nt_dbg[0], (unsigned long long)lt);
+      atomicAdd(&g_nt_dbg[1], (unsigned long long)t_wait);
+      atomicAdd(&g_nt_dbg[2], (unsigned long long)t_work);
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / ntn, nt = tile - mt * ntn;
+        const int bt = mt / tpb, t0 = (mt - bt * tpb) * BM;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STG;
+          mbar_wait(&empty[s], ((it / STG) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          tma_load_3d(smem + s * STAGE_BYTES, &mapA, &full[s], kb * BK, t0, bt);
+          tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &mapB, &full[s], kb * BK, nt * BN);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(BM, BN, 0, 0);
+      int it = 0, lt = 0;
+      const bool dbgm = g_nt_dbg_on != 0;
+      long long t_full = 0, t_tempty = 0;
+      const long long t_begin = clock64();
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const long long q0 = dbgm ? clock64() : 0;
+        mbar_wait(&tempty[acc], ((lt >> 1) & 1) ^ 1);
+        if (dbgm) t_tempty += clock64() - q0;
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * ACC_COLS);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STG;
+          const long long q1 = dbgm ? clock64() : 0;
+          mbar_wait(&full[s], (it / STG) & 1);
+          if (dbgm) t_full += clock64() - q1;
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t da = umma_desc(sa, 16, 1024), db = umma_desc(sa + A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          tc_commit(&empty[s]);
+        }
+        tc_commit(&tfull[acc]);
+      }
+      if (dbgm) {
+        atomicAdd(&g_nt_dbg[3], (unsigned long long)t_full);
+        atomicAdd(&g_nt_dbg[4], (unsigned long long)t_tempty);
+        atomicAdd(&g_nt_dbg[5], (unsigned long long)(clock64() - t_begin));
+        atomicAdd(&g_nt_dbg[6], (unsigned long long)it);
+        atomicAdd(&g_nt_dbg[7], 1ull);
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// 3-D bf16 map {cols (contiguous), rows (stride rs elements), batches (stride bs elements)}; box {box_c, box_r, 1}.
+static int make_map_3d(CUtensorMap* map, const void* ptr, int64_t cols, int64_t rows, int64_t nb, int64_t rs, int64_t bs,
+                       int box_c, int box_r) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return AG_ENOTSUP; }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nb};
+  cuuint64_t strides[2] = {(cuuint64_t)rs * 2, (cuuint64_t)bs * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_r, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed (%d): cols %lld rows %lld nb %lld rs %lld bs %lld", (int)r, (long long)cols,
+              (long long)rows, (long long)nb, (long long)rs, (long long)bs);
+    return AG_ECUDA;
+  }
+  return AG_OK;
+}
+
+// Row-tile height R (rows per batch) when the descriptor can take the TMA-fed kernel, else 0.
+static int64_t tma_rows_per_batch(const ag_gemm_desc* d) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("AUDIOGAN_NT"); off = (e && e[0] == 'o') ? 1 : 0; }     // AUDIOGAN_NT=old: A/B switch
+  if (off) return 0;
+  if (d->a_dtype != 1 || d->b_dtype != 1 || d->a_kin < d->K) return 0;
+  if ((reinterpret_cast<uintptr_t>(d->A) & 15) != 0 || d->a_rs % 8 != 0 || d->a_rs <= 0) return 0;
+  const bool a_flat = d->a_rpb >= d->M, c_flat = d->c_rpb >= d->M;
+  int64_t R = d->M;
+  if (!a_flat) R = d->a_rpb;
+  if (!c_flat) { if (!a_flat && d->c_rpb != d->a_rpb) return 0; R = d->c_rpb; }
+  if (R <= 0 || d->M % R != 0) return 0;
+  if (!a_flat && d->M / R > 1 && (d->a_bs % 8 != 0 || d->a_bs <= 0)) return 0;
+  if (R >= (1ll << 31) || d->M / R >= (1ll << 31)) return 0;
+  // the vector epilogue works with 32-bit element offsets
+  const int64_t cb = c_flat ? 1 : d->M / d->c_rpb, cr = c_flat ? d->M : d->c_rpb;
+  const int64_t span = (cb - 1) * d->c_bs + (cr - 1) * d->c_rs + ((d->N - 1) / d->c_nin) * d->c_n1s + d->c_nin;
+  const int64_t lim = (1ll << 31) - 1;
+  if (span >= lim || d->c_bs < 0 || d->c_rs < 0 || d->c_n1s < 0 || cb * d->rowbias_ld + d->N >= lim || d->rowbias_ld < 0) return 0;
+  if (d->mask_len && (cr * (d->mask_tmul < 0 ? -d->mask_tmul : d->mask_tmul) + ((d->N - 1) / d->c_nin + 1) * (d->mask_n1mul < 0 ? -d->mask_n1mul : d->mask_n1mul) +
+                          (d->mask_toff < 0 ? -d->mask_toff : d->mask_toff) >= lim)) return 0;
+  return R;
+}
+
+template <int BN, bool VECC>
+static int launch_nt_tma2(const ag_gemm_desc* d, int64_t R, cudaStream_t s) {
+  CUtensorMap mapA, mapB;
+  const bool a_flat = d->a_rpb >= d->M;
+  const int64_t nb = d->M / R;
+  int rc = make_map_3d(&mapA, d->A, d->K, R, nb, d->a_rs, (a_flat || nb == 1) ? R * d->a_rs : d->a_bs, BK, BM);
+  if (rc) return rc;
+  rc = make_map_2d(&mapB, d->B, d->N, d->K, d->ldb, BK, BN);
+  if (rc) return rc;
+  constexpr int STG = tma_stages(BN);
+  constexpr int smem = STG * (BM * BK * 2 + BN * BK * 2) + 8 * 32 * TRLD * 4 + 1024 + (2 * STG + 4) * 8 + 16 + BM * 8 + 3 * BM * 4 + BM * 16;
+  static_assert(smem <= 227 * 1024, "shared-memory budget");
+  auto kern = gemm_nt_tma_kernel<BN, VECC>;
+  AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int64_t tpb = (R + BM - 1) / BM, ntn = (d->N + BN - 1) / BN;
+  const int64_t total = nb * tpb * ntn;
+  AG_CHECK_ARG(total < (1ll << 31), "ag_gemm_nt_tc: too many tiles");
+  const int grid = (int)(total < sm_count() ? total : sm_count());
+  kern<<<grid, TM_THREADS, smem, s>>>(*d, mapA, mapB, (int)R, (int)tpb, (int)ntn, (int)total);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+template <int BN>
+static int launch_nt_tma(const ag_gemm_desc* d, int64_t R, cudaStream_t s) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool cal = d->c_dtype == 0 ? al16(d->C) : (reinterpret_cast<uintptr_t>(d->C) & 7) == 0;
+  const bool auxal = d->aux_dtype == 0 ? (al16(d->skip) && al16(d->dact))
+                                       : ((reinterpret_cast<uintptr_t>(d->skip) & 7) == 0 && (reinterpret_cast<uintptr_t>(d->dact) & 7) == 0);
+  const bool vecc = d->N % 4 == 0 && d->c_nin % 4 == 0 && d->c_bs % 4 == 0 && d->c_rs % 4 == 0 && d->c_n1s % 4 == 0 && cal && auxal &&
+                    al16(d->bias) && (d->bias_mod == 0 || d->bias_mod % 4 == 0) && al16(d->rowbias) && d->rowbias_ld % 4 == 0;
+  return vecc ? launch_nt_tma2<BN, true>(d, R, s) : launch_nt_tma2<BN, false>(d, R, s);
+}
+
 // ======================================================================================== TN (weight gradient)
 // D[n, k] (+)= sum_m Y(m, n) * A(m, k): the reduction index m is the row index of both global operands, so both
 // MMA operands are MN-major: a stage holds 64 m-rows; operand "A" = Y^T as two 64-wide n blocks, operand "B" =
@@ -801,7 +1183,10 @@ int ag_gemm_nt_tc(const ag_gemm_desc* d, void* stream) {
   const int al = d->a_dtype == 0 ? 4 : 8;       // elements per 16 bytes
   const bool vec = d->a_kin % 8 == 0 && d->K % 8 == 0 && d->a_bs % al == 0 && d->a_rs % al == 0 && d->a_k1s % al == 0 &&
                    (reinterpret_cast<uintptr_t>(d->A) & 15) == 0;
-#define AG_TC_NT(BN) return !vec ? tc::launch_nt<BN, 2>(d, s) : (d->a_dtype == 0 ? tc::launch_nt<BN, 0>(d, s) : tc::launch_nt<BN, 1>(d, s))
+  const int64_t R = vec ? tc::tma_rows_per_batch(d) : 0;
+#define AG_TC_NT(BN)                                                                                         \
+  return R > 0 ? tc::launch_nt_tma<BN>(d, R, s)                                                              \
+               : (!vec ? tc::launch_nt<BN, 2>(d, s) : (d->a_dtype == 0 ? tc::launch_nt<BN, 0>(d, s) : tc::launch_nt<BN, 1>(d, s)))
   if (d->N > 128) { AG_TC_NT(256); }
   if (d->N > 64) { AG_TC_NT(128); }
   if (d->N > 32) { AG_TC_NT(64); }

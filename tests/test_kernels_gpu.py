@@ -518,3 +518,55 @@ def test_streaming_kernels_both_storage_types(dt):
     w1r, b1r = w1.clone().requires_grad_(), b1.clone().requires_grad_()
     F.conv1d(x[:, None], w1r[:, None], b1r, stride=s)[:, :, :To].backward(dy.permute(0, 2, 1))
     assert rel(dw1[:, :k], w1r.grad) < 1e-5 and rel(dw1[:, k], b1r.grad) < 1e-5
+
+
+@pytest.mark.parametrize("Bn,Cin,Cout,Tin,k,s", [(3, 16, 40, 301, 7, 2), (2, 32, 256, 700, 7, 2), (5, 64, 24, 130, 3, 1),
+                                                 (1, 128, 512, 1000, 7, 2)])
+def test_gemm_nt_tma_conv_window_view(Bn, Cin, Cout, Tin, k, s):
+    """Persistent TMA-fed kernel (bf16 activations, contiguous im2col window, rows tiled per batch): strided conv with
+    bias + skip + LeakyReLU + length mask, fp32 and bf16 outputs, several tiles per CTA and a ragged last row tile."""
+    from audiogan_b200 import kernels as Kn
+    T.manual_seed(18)
+    p = (k - 1) // 2
+    x, w, b = T.randn(Bn, Cin, Tin), T.randn(Cout, Cin, k) / (Cin * k) ** 0.5, T.randn(Cout)
+    Tout = (Tin + 2 * p - k) // s + 1
+    lens = T.randint(1, Tout + 1, (Bn,), dtype=T.int32)
+    lens[0] = Tout
+    skip = T.randn(Bn, Tout, Cout).bfloat16()
+    ref = F.conv1d(x.bfloat16().float(), w.bfloat16().float(), b, stride=s, padding=p).permute(0, 2, 1) + skip.float()
+    ref = F.leaky_relu(ref, 0.01) * (T.arange(Tout)[None, :, None] < lens[:, None, None]).float()
+    xp = T.zeros(Bn, Tin + 2 * p + s, Cin)
+    xp[:, p:p + Tin] = x.permute(0, 2, 1)
+    xp = xp.cuda().bfloat16()
+    wp = w.permute(0, 2, 1).reshape(Cout, k * Cin).contiguous().cuda().bfloat16()
+    for odt, tol in ((T.float32, 3e-5), (T.bfloat16, 8e-3)):
+        out = T.zeros(Bn, Tout, Cout, device="cuda", dtype=odt)
+        Kn.gemm_nt(Bn * Tout, Cout, k * Cin, xp, (Tout, xp.shape[1] * Cin, s * Cin), wp, k * Cin,
+                   out, (Tout, Tout * Cout, Cout), bias=b.cuda(), skip=skip.cuda(), act=1, mask_len=lens.cuda(), mask=(1, 0, 0), tc=True)
+        assert rel(out, ref) < tol
+
+
+@pytest.mark.parametrize("Bn,Tm,N,K", [(4, 250, 1024, 1024), (3, 77, 512, 192), (2, 130, 8, 64)])
+def test_gemm_nt_tma_flat_and_padded_rows(Bn, Tm, N, K):
+    """TMA-fed kernel with a flat A ([B*Tm, K]) written into a padded per-batch C geometry ([B, Tm+2, N], rows 1..Tm),
+    LeakyReLU' of a saved activation and C += skip -- the discriminator tail's data-gradient GEMMs -- and the reverse."""
+    from audiogan_b200 import kernels as Kn
+    T.manual_seed(19)
+    M = Bn * Tm
+    A, W = T.randn(M, K).bfloat16(), (T.randn(N, K) / K ** 0.5).bfloat16()
+    act = T.randn(Bn, Tm + 2, N).bfloat16()
+    sk = T.randn(Bn, Tm + 2, N).bfloat16()
+    geo = (Tm, (Tm + 2) * N, N)
+    out = T.zeros(Bn, Tm + 2, N, device="cuda", dtype=T.bfloat16)
+    Kn.gemm_nt(M, N, K, A.cuda(), (M, 0, K), W.cuda(), K, (out, N), geo, skip=(sk.cuda(), N), dact=(act.cuda(), N), tc=True)
+    ref = (A.float() @ W.float().t()).view(Bn, Tm, N) + sk[:, 1:Tm + 1].float()
+    ref = ref * T.where(act[:, 1:Tm + 1].float() > 0, 1.0, 0.01)
+    assert rel(out[:, 1:Tm + 1], ref) < 8e-3 and float(out[:, 0].abs().max()) == 0 and float(out[:, Tm + 1].abs().max()) == 0
+    # padded per-batch A -> packed fp32 C with a per-batch row bias
+    Ap = T.zeros(Bn, Tm + 2, K).bfloat16()
+    Ap[:, 1:Tm + 1] = A.view(Bn, Tm, K)
+    rb = T.randn(Bn, N)
+    out2 = T.empty(M, N, device="cuda")
+    Kn.gemm_nt(M, N, K, (Ap.cuda(), K), (Tm, (Tm + 2) * K, K), W.cuda(), K, out2, (Tm, Tm * N, N), rowbias=rb.cuda(), rowbias_ld=N, tc=True)
+    ref2 = (A.float() @ W.float().t()).view(Bn, Tm, N) + rb[:, None]
+    assert rel(out2.view(Bn, Tm, N), ref2) < 3e-5
