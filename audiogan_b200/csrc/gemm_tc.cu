@@ -826,12 +826,13 @@ static int make_map_3d(CUtensorMap* map, const void* ptr, int64_t cols, int64_t 
   return AG_OK;
 }
 
+static bool nt_vec_epilogue(const ag_gemm_desc* d);
 // Row-tile height R (rows per batch) when the descriptor can take the TMA-fed kernel, else 0.
 static int64_t tma_rows_per_batch(const ag_gemm_desc* d) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("AUDIOGAN_NT"); off = (e && e[0] == 'o') ? 1 : 0; }     // AUDIOGAN_NT=old: A/B switch
   if (off) return 0;
-  if (d->a_dtype != 1 || d->b_dtype != 1 || d->a_kin < d->K) return 0;
+  if (d->a_dtype != 1 || d->b_dtype != 1 || d->a_kin < d->K || !nt_vec_epilogue(d)) return 0;
   if ((reinterpret_cast<uintptr_t>(d->A) & 15) != 0 || d->a_rs % 8 != 0 || d->a_rs <= 0) return 0;
   const bool a_flat = d->a_rpb >= d->M, c_flat = d->c_rpb >= d->M;
   int64_t R = d->M;
@@ -872,15 +873,17 @@ static int launch_nt_tma2(const ag_gemm_desc* d, int64_t R, cudaStream_t s) {
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
-template <int BN>
-static int launch_nt_tma(const ag_gemm_desc* d, int64_t R, cudaStream_t s) {
+static bool nt_vec_epilogue(const ag_gemm_desc* d) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool cal = d->c_dtype == 0 ? al16(d->C) : (reinterpret_cast<uintptr_t>(d->C) & 7) == 0;
   const bool auxal = d->aux_dtype == 0 ? (al16(d->skip) && al16(d->dact))
                                        : ((reinterpret_cast<uintptr_t>(d->skip) & 7) == 0 && (reinterpret_cast<uintptr_t>(d->dact) & 7) == 0);
-  const bool vecc = d->N % 4 == 0 && d->c_nin % 4 == 0 && d->c_bs % 4 == 0 && d->c_rs % 4 == 0 && d->c_n1s % 4 == 0 && cal && auxal &&
-                    al16(d->bias) && (d->bias_mod == 0 || d->bias_mod % 4 == 0) && al16(d->rowbias) && d->rowbias_ld % 4 == 0;
-  return vecc ? launch_nt_tma2<BN, true>(d, R, s) : launch_nt_tma2<BN, false>(d, R, s);
+  return d->N % 4 == 0 && d->c_nin % 4 == 0 && d->c_bs % 4 == 0 && d->c_rs % 4 == 0 && d->c_n1s % 4 == 0 && cal && auxal &&
+         al16(d->bias) && (d->bias_mod == 0 || d->bias_mod % 4 == 0) && al16(d->rowbias) && d->rowbias_ld % 4 == 0;
+}
+template <int BN>
+static int launch_nt_tma(const ag_gemm_desc* d, int64_t R, cudaStream_t s) {
+  return launch_nt_tma2<BN, true>(d, R, s);       // scalar-epilogue shapes (N < 4, odd strides) stay on the 2-CTA/SM kernel
 }
 
 // ======================================================================================== TN (weight gradient)
@@ -1126,6 +1129,146 @@ __global__ void __launch_bounds__(TN_THREADS, 2) gemm_tn_tc_kernel(const ag_gemm
   }
 }
 
+// ---------------------------------------------------------------------------------------- TN, TMA-fed
+// Both operands bf16 with contiguous columns (Y: plain [.., N] rows; A: one contiguous im2col window per row): a stage is
+// 64 reduction rows of ONE batch, fetched as {64 columns x 64 rows} boxes of two 3-D tensor maps {column, t, batch} --
+// the box IS the MN-major SWIZZLE_128B operand block, rows past the batch's end arrive as zeros and add nothing.  No
+// producer warps: warp 8 issues the TMA loads, warp 9 the MMAs, warps 0-7 only run the epilogue (2 CTAs / SM, so one
+// CTA's epilogue overlaps the other's main loop).  The bias gradient (the "ones" column) is a separate column-sum kernel.
+constexpr int TNT_THREADS = 320;
+template <int BNK>
+__global__ void __launch_bounds__(TNT_THREADS, 2)
+gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA, float* __restrict__ dw, int64_t ldw,
+                   int N, int K, int spb, int total_stages, int stages_per_split) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int RM = 64;
+  constexpr int STAGES = nt_stages(BNK);
+  constexpr int A_BYTES = 2 * RM * 128, B_BYTES = (BNK / 64) * RM * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * BM, k0 = blockIdx.x * BNK;
+  const int sbeg = blockIdx.z * stages_per_split;
+  const int send = min(total_stages, sbeg + stages_per_split);
+  const int nst = send - sbeg;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr uint32_t TMEM_COLS = BNK < 32 ? 32 : BNK;
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp < 8) {
+    // epilogue: TMEM lane = n, column = k; 32x32 transposes through shared memory so that one warp instruction accumulates
+    // 32 consecutive k of one weight row (coalesced red.global.add.f32)
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+    const int wq = warp & 3, wh = warp >> 2;
+#pragma unroll 1
+    for (int c0 = wh * (BNK / 2); c0 < (wh + 1) * (BNK / 2); c0 += 32) {
+      if (k0 + c0 >= K) break;
+      uint32_t v[16];
+      tc_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
+      tc_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(c0 + 16), v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) tr[lane * 33 + 16 + j] = __uint_as_float(v[j]);
+      __syncwarp();
+      const int k = k0 + c0 + lane;
+      if (k < K) {
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const int n = n0 + wq * 32 + r;
+          if (n < N) atomicAdd(&dw[(int64_t)n * ldw + k], tr[r * 33 + lane]);
+        }
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  } else if (warp == 8) {
+    if (lane == 0) {
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % STAGES;
+        const int g = sbeg + it, b = g / spb, t0 = (g - b * spb) * RM;
+        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        tma_load_3d(sa, &mapY, &full[s], n0, t0, b);
+        tma_load_3d(sa + RM * 128, &mapY, &full[s], n0 + 64, t0, b);
+#pragma unroll
+        for (int j = 0; j < BNK / 64; ++j) tma_load_3d(sa + A_BYTES + j * (RM * 128), &mapA, &full[s], k0 + j * 64, t0, b);
+      }
+    }
+    __syncwarp();
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(BM, BNK, 1, 1);
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t da = umma_desc(sa, RM * 128, 1024), db = umma_desc(sa + A_BYTES, RM * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < RM / 16; ++k)
+          tc_mma(tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (it | k) ? 1u : 0u);
+        tc_commit(&empty[s]);
+      }
+      tc_commit(tmem_full);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// dw[n*ldw] += sum_m Y(m, n): the bias gradient beside the TMA-fed weight-gradient kernel.  Thread = 8 columns (16 bytes of
+// bf16), block = 32 column groups x 8 row lanes; grid.y splits the rows.
+__global__ void __launch_bounds__(256) tn_bias_kernel(const __nv_bfloat16* __restrict__ Y, int64_t rpb, int64_t bs, int64_t rs, int64_t M,
+                                                      int N, float* __restrict__ out, int64_t ldw, int64_t rows_per) {
+  __shared__ float red[8][32][9];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int n = (blockIdx.x * 32 + cx) * 8;
+  const int64_t m0 = (int64_t)blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (n < N)
+    for (int64_t m = m0 + ry; m < m1; m += 8) {
+      const int64_t b = m / rpb;
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(Y + b * bs + (m - b * rpb) * rs + n));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { acc[2 * e] += __uint_as_float(w[e] << 16); acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u); }
+    }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[ry][cx][e] = acc[e];
+  __syncthreads();
+  if (ry == 0 && n < N) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v += red[i][cx][e];
+      atomicAdd(&out[(int64_t)(n + e) * ldw], v);
+    }
+  }
+}
+
 static int tn_split_factor() {          // experiment knob: CTAs per SM worth of row splits (AUDIOGAN_TN_SPLIT, default 4)
   static int v = 0;
   if (!v) { const char* e = getenv("AUDIOGAN_TN_SPLIT"); v = e ? atoi(e) : 4; if (v < 1) v = 4; }
@@ -1163,6 +1306,64 @@ static int launch_tn(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones_col
   else AG_TN_LAUNCH(2, 2);
 #undef AG_TN_LAUNCH
   AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+
+// Rows per batch R when the weight-gradient descriptor can take the TMA-fed kernel, else 0.
+static int64_t tn_tma_rows_per_batch(const ag_gemm_desc* d) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("AUDIOGAN_TN"); off = (e && e[0] == 'o') ? 1 : 0; }     // AUDIOGAN_TN=old: A/B switch
+  if (off) return 0;
+  if (d->a_dtype != 1 || d->c_dtype != 1 || d->a_kin < d->K || d->c_nin < d->N) return 0;
+  if (((reinterpret_cast<uintptr_t>(d->A) | reinterpret_cast<uintptr_t>(d->C)) & 15) != 0) return 0;
+  if (d->a_rs % 8 != 0 || d->a_rs <= 0 || d->c_rs % 8 != 0 || d->c_rs <= 0 || d->N % 8 != 0) return 0;
+  const bool a_flat = d->a_rpb >= d->M, y_flat = d->c_rpb >= d->M;
+  int64_t R = d->M;
+  if (!a_flat) R = d->a_rpb;
+  if (!y_flat) { if (!a_flat && d->c_rpb != d->a_rpb) return 0; R = d->c_rpb; }
+  if (R <= 0 || d->M % R != 0) return 0;
+  const int64_t nb = d->M / R;
+  if (nb > 1 && ((!a_flat && (d->a_bs % 8 != 0 || d->a_bs <= 0)) || (!y_flat && (d->c_bs % 8 != 0 || d->c_bs <= 0)))) return 0;
+  if (R >= (1ll << 31) || nb >= (1ll << 31) || d->N >= (1ll << 31) || d->K >= (1ll << 31)) return 0;
+  return R;
+}
+
+template <int BNK>
+static int launch_tn_tma(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones_col, int64_t R, cudaStream_t s) {
+  CUtensorMap mapY, mapA;
+  const bool a_flat = d->a_rpb >= d->M, y_flat = d->c_rpb >= d->M;
+  const int64_t nb = d->M / R;
+  int rc = make_map_3d(&mapY, d->C, d->N, R, nb, d->c_rs, (y_flat || nb == 1) ? R * d->c_rs : d->c_bs, 64, 64);
+  if (rc) return rc;
+  rc = make_map_3d(&mapA, d->A, d->K, R, nb, d->a_rs, (a_flat || nb == 1) ? R * d->a_rs : d->a_bs, 64, 64);
+  if (rc) return rc;
+  constexpr int STAGES = nt_stages(BNK);
+  constexpr int smem = STAGES * (2 * 64 * 128 + (BNK / 64) * 64 * 128) + 1024 + (2 * STAGES + 1) * 8 + 16;
+  static_assert(STAGES * (2 * 64 * 128 + (BNK / 64) * 64 * 128) >= 8 * 32 * 33 * 4, "epilogue transpose tiles must fit in the stages");
+  const int64_t spb = (R + 63) / 64, total = nb * spb;
+  const int64_t gx = (d->K + BNK - 1) / BNK, gy = (d->N + BM - 1) / BM;
+  int64_t want = (int64_t)sm_count() * tn_split_factor() / (gx * gy);
+  if (want < 1) want = 1;
+  int64_t sps = (total + want - 1) / want;
+  if (sps < 8) sps = 8;
+  const int64_t gz = (total + sps - 1) / sps;
+  AG_CHECK_ARG(gy < 65536 && gz < 65536 && total < (1ll << 31), "ag_gemm_tn_tc: grid too large");
+  auto kern = gemm_tn_tma_kernel<BNK>;
+  AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), TNT_THREADS, smem, s>>>(mapY, mapA, dw, ldw, (int)d->N, (int)d->K, (int)spb,
+                                                                                (int)total, (int)sps);
+  AG_LAUNCH_CHECK();
+  if (ones_col) {
+    const int64_t bx = (d->N / 8 + 31) / 32;
+    int64_t by = (int64_t)sm_count() * 8 / bx;
+    if (by < 1) by = 1;
+    int64_t rows_per = (d->M + by - 1) / by;
+    if (rows_per < 64) rows_per = 64;
+    by = (d->M + rows_per - 1) / rows_per;
+    tn_bias_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d->C), d->c_rpb, d->c_bs, d->c_rs,
+                                                                    d->M, (int)d->N, dw + d->K, ldw, rows_per);
+    AG_LAUNCH_CHECK();
+  }
   return AG_OK;
 }
 
@@ -1205,6 +1406,12 @@ int ag_gemm_tn_tc(const ag_gemm_desc* d, float* dw, int64_t ldw, int32_t ones_co
                   (reinterpret_cast<uintptr_t>(d->A) & 15) == 0;
   const bool vy = d->c_nin % 8 == 0 && d->c_bs % aly == 0 && d->c_rs % aly == 0 && d->c_n1s % aly == 0 &&
                   (reinterpret_cast<uintptr_t>(d->C) & 15) == 0;
+  const int64_t Rt = (vy && va) ? tc::tn_tma_rows_per_batch(d) : 0;
+  if (Rt > 0) {
+    if (d->K > 128) return tc::launch_tn_tma<256>(d, dw, ldw, ones_col, Rt, s);
+    if (d->K > 64) return tc::launch_tn_tma<128>(d, dw, ldw, ones_col, Rt, s);
+    return tc::launch_tn_tma<64>(d, dw, ldw, ones_col, Rt, s);
+  }
   const int64_t ktot = d->K + (ones_col ? 1 : 0);
   if (ktot > 128) return tc::launch_tn<256>(d, dw, ldw, ones_col, vy, va, s);
   if (ktot > 64) return tc::launch_tn<128>(d, dw, ldw, ones_col, vy, va, s);

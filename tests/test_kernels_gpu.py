@@ -570,3 +570,47 @@ def test_gemm_nt_tma_flat_and_padded_rows(Bn, Tm, N, K):
     Kn.gemm_nt(M, N, K, (Ap.cuda(), K), (Tm, (Tm + 2) * K, K), W.cuda(), K, out2, (Tm, Tm * N, N), rowbias=rb.cuda(), rowbias_ld=N, tc=True)
     ref2 = (A.float() @ W.float().t()).view(Bn, Tm, N) + rb[:, None]
     assert rel(out2.view(Bn, Tm, N), ref2) < 3e-5
+
+
+@pytest.mark.parametrize("Bn,Cin,Cout,Tin,k,s", [(3, 16, 40, 301, 7, 2), (5, 64, 256, 700, 7, 2), (2, 128, 24, 130, 3, 1)])
+def test_gemm_tn_tma_conv_wgrad_view(Bn, Cin, Cout, Tin, k, s):
+    """TMA-fed weight-gradient kernel (bf16 storage, stages of 64 rows per batch, zero-filled ragged ends): strided-conv
+    weight gradient through the im2col window view + the bias gradient from the column-sum kernel."""
+    from audiogan_b200 import kernels as Kn
+    T.manual_seed(20)
+    p = (k - 1) // 2
+    x = T.randn(Bn, Cin, Tin).bfloat16().float()
+    Tout = (Tin + 2 * p - k) // s + 1
+    dy = T.randn(Bn, Cout, Tout).bfloat16().float()
+    w = T.zeros(Cout, Cin, k, requires_grad=True)
+    bb = T.zeros(Cout, requires_grad=True)
+    (F.conv1d(x, w, bb, stride=s, padding=p) * dy).sum().backward()
+    xp = T.zeros(Bn, Tin + 2 * p + s, Cin)
+    xp[:, p:p + Tin] = x.permute(0, 2, 1)
+    dyc = dy.permute(0, 2, 1).contiguous().cuda().bfloat16()
+    dw = T.zeros(Cout, k * Cin + 1, device="cuda")
+    Kn.gemm_tn(Bn * Tout, Cout, k * Cin, dyc, (Tout, Tout * Cout, Cout), xp.cuda().bfloat16(), (Tout, xp.shape[1] * Cin, s * Cin),
+               dw, k * Cin + 1, ones_col=True, tc=True)
+    assert rel(dw[:, :k * Cin].reshape(Cout, k, Cin).permute(0, 2, 1), w.grad) < 3e-5
+    assert rel(dw[:, k * Cin], bb.grad) < 3e-5
+
+
+@pytest.mark.parametrize("Bn,Tm,N,K", [(4, 250, 1024, 1024), (3, 77, 512, 192), (2, 130, 8, 64), (6, 100, 2048, 512)])
+def test_gemm_tn_tma_flat_and_padded_rows(Bn, Tm, N, K):
+    """TMA-fed weight gradient with a flat Y ([B*Tm, N]) against a padded per-batch activation ([B, Tm+2, K], rows 1..Tm)
+    and the reverse -- the discriminator tail's weight-gradient GEMMs."""
+    from audiogan_b200 import kernels as Kn
+    T.manual_seed(21)
+    M = Bn * Tm
+    Y, A = T.randn(M, N).bfloat16(), T.randn(M, K).bfloat16()
+    ref, refb = Y.float().t() @ A.float(), Y.float().sum(0)
+    Ap = T.randn(Bn, Tm + 2, K).bfloat16()
+    Ap[:, 1:Tm + 1] = A.view(Bn, Tm, K)
+    dw = T.zeros(N, K + 1, device="cuda")
+    Kn.gemm_tn(M, N, K, Y.cuda(), (M, 0, N), (Ap.cuda(), K), (Tm, (Tm + 2) * K, K), dw, K + 1, ones_col=True, tc=True)
+    assert rel(dw[:, :K], ref) < 3e-5 and rel(dw[:, K], refb) < 3e-5
+    Yp = T.randn(Bn, Tm + 2, N).bfloat16()
+    Yp[:, 1:Tm + 1] = Y.view(Bn, Tm, N)
+    dw2 = T.zeros(N, K, device="cuda")
+    Kn.gemm_tn(M, N, K, (Yp.cuda(), N), (Tm, (Tm + 2) * N, N), A.cuda(), (M, 0, K), dw2, K, tc=True)
+    assert rel(dw2, ref) < 3e-5
