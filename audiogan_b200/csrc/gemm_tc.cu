@@ -525,7 +525,10 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 // costs ~30 instructions per element in 64-bit index arithmetic and per-row tables).  Everything per row comes from ONE
 // 16-byte table entry {C row offset | -1, row-bias offset, mask position base, mask length}; offsets are 32-bit element
 // offsets (the host checks the spans); the epilogue operands of all 8 rows of a lane are in flight before the first use.
-template <bool CBF, bool AUXBF, int CH>
+// F: compile-time feature set (bit 0 skip, 1 LeakyReLU' operand, 2 row bias, 3 length mask, 4 LeakyReLU; alpha == 1), so a
+// launch only executes the instructions of the epilogue it asked for; F < 0: every feature decided at run time.
+enum { EPI_SKIP = 1, EPI_DACT = 2, EPI_RB = 4, EPI_MASK = 8, EPI_ACT = 16 };
+template <bool CBF, bool AUXBF, int CH, int F>
 __device__ __forceinline__ void epi_chunk_vec(const ag_gemm_desc& d, const float* __restrict__ tr, const int4* __restrict__ rowtab,
                                               int wq, int lane, int nc, float alpha) {
   const int q = lane & 7, rs = lane >> 3;
@@ -539,7 +542,9 @@ __device__ __forceinline__ void epi_chunk_vec(const ag_gemm_desc& d, const float
     bv = *reinterpret_cast<const float4*>(d.bias + ((bm > 0 && n >= bm) ? (int)((uint32_t)n % (uint32_t)bm) : n));
   }
   const int mposl = n1 * (int)d.mask_n1mul;
-  const bool has_skip = d.skip != nullptr, has_dact = d.dact != nullptr, has_rb = d.rowbias != nullptr, has_mask = d.mask_len != nullptr;
+  const bool has_skip = F < 0 ? d.skip != nullptr : (F & EPI_SKIP) != 0, has_dact = F < 0 ? d.dact != nullptr : (F & EPI_DACT) != 0;
+  const bool has_rb = F < 0 ? d.rowbias != nullptr : (F & EPI_RB) != 0, has_mask = F < 0 ? d.mask_len != nullptr : (F & EPI_MASK) != 0;
+  const bool has_act = F < 0 ? d.act == 1 : (F & EPI_ACT) != 0;
   const float slope = d.slope;
   int ci[8];
   uint32_t keep = 0;
@@ -580,9 +585,11 @@ __device__ __forceinline__ void epi_chunk_vec(const ag_gemm_desc& d, const float
       sk = sk4[it];
       da = da4[it];
     }
-    x.x = fmaf(x.x, alpha, bv.x) + (rb[it].x + sk.x); x.y = fmaf(x.y, alpha, bv.y) + (rb[it].y + sk.y);
-    x.z = fmaf(x.z, alpha, bv.z) + (rb[it].z + sk.z); x.w = fmaf(x.w, alpha, bv.w) + (rb[it].w + sk.w);
-    if (d.act == 1) {
+    if (F < 0) { x.x *= alpha; x.y *= alpha; x.z *= alpha; x.w *= alpha; }
+    x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+    if (has_rb) { x.x += rb[it].x; x.y += rb[it].y; x.z += rb[it].z; x.w += rb[it].w; }
+    if (has_skip) { x.x += sk.x; x.y += sk.y; x.z += sk.z; x.w += sk.w; }
+    if (has_act) {
       x.x = x.x > 0.f ? x.x : x.x * slope; x.y = x.y > 0.f ? x.y : x.y * slope;
       x.z = x.z > 0.f ? x.z : x.z * slope; x.w = x.w > 0.f ? x.w : x.w * slope;
     }
@@ -590,7 +597,7 @@ __device__ __forceinline__ void epi_chunk_vec(const ag_gemm_desc& d, const float
       x.x *= da.x > 0.f ? 1.f : slope; x.y *= da.y > 0.f ? 1.f : slope;
       x.z *= da.z > 0.f ? 1.f : slope; x.w *= da.w > 0.f ? 1.f : slope;
     }
-    if (!((keep >> it) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_mask && !((keep >> it) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
     if (CBF) {
       uint2 o;
       o.x = pack_bf16(x.x, x.y); o.y = pack_bf16(x.z, x.w);
@@ -647,6 +654,12 @@ gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap map
     const float alpha = d.alpha == 0.f ? 1.f : d.alpha;
     constexpr int CH = BN < 32 ? BN : 32;
     int lt = 0;
+    // specialised epilogues: bf16 output, bf16 (or no) epilogue operands, alpha == 1; -1 = the run-time-flag version
+    const bool aux_any = d.skip != nullptr || d.dact != nullptr;
+    const int epi_sel = (d.c_dtype == 1 && (!aux_any || d.aux_dtype == 1) && alpha == 1.f)
+                            ? ((d.skip ? EPI_SKIP : 0) | (d.dact ? EPI_DACT : 0) | (d.rowbias ? EPI_RB : 0) | (d.mask_len ? EPI_MASK : 0) |
+                               (d.act == 1 ? EPI_ACT : 0))
+                            : -1;
     const int dbgf = g_nt_dbg_on;
     const bool dbg = dbgf != 0 && tid == 0;
     long long t_wait = 0, t_work = 0, q0 = 0;
@@ -698,13 +711,20 @@ gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap map
         __syncwarp();
         if (dbgf & 8) {
         } else if (VECC) {
-          if (d.c_dtype) {
-            if (d.aux_dtype) epi_chunk_vec<true, true, CH>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
-            else epi_chunk_vec<true, false, CH>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
+#define AG_EPI(FL) case FL: epi_chunk_vec<true, true, CH, FL>(d, tr, rowtab, wq, lane, n0 + c0, alpha); break;
+          if (epi_sel >= 0) {
+            switch (epi_sel) {       // bf16 output (+ bf16 operands): the feature sets the training step uses, specialised
+              AG_EPI(0) AG_EPI(EPI_ACT) AG_EPI(EPI_SKIP | EPI_ACT) AG_EPI(EPI_SKIP | EPI_MASK | EPI_ACT) AG_EPI(EPI_MASK | EPI_ACT)
+              AG_EPI(EPI_DACT) AG_EPI(EPI_SKIP) AG_EPI(EPI_MASK) AG_EPI(EPI_SKIP | EPI_DACT)
+              default: epi_chunk_vec<true, true, CH, -1>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
+            }
+          } else if (d.c_dtype) {
+            epi_chunk_vec<true, false, CH, -1>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
           } else {
-            if (d.aux_dtype) epi_chunk_vec<false, true, CH>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
-            else epi_chunk_vec<false, false, CH>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
+            if (d.aux_dtype) epi_chunk_vec<false, true, CH, -1>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
+            else epi_chunk_vec<false, false, CH, -1>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
           }
+#undef AG_EPI
         } else {
           const int64_t n = n0 + c0 + lane;
           const bool nv = lane < CH && n < d.N;
