@@ -44,6 +44,65 @@ __global__ void __launch_bounds__(256) conv1out_fwd_kernel(const void* __restric
   }
 }
 
+// Streaming version for C <= 128 (the dense buffer has 120 channels): a warp walks a strip of rows, lane = 4 channels, so
+// every buffer row is loaded ONCE (one coalesced 8/16-byte load per lane, 4 rows in flight), its k tap-partials are
+// reduced over the warp and folded into a rolling window of k outputs; 32 outputs leave as one coalesced store.
+template <int XDT, int KMAX>
+__global__ void __launch_bounds__(256) conv1out_fwd_strip_kernel(const void* __restrict__ X, int64_t x_bs, int C, int k,
+                                                                 const float* __restrict__ w, const float* __restrict__ bias,
+                                                                 float* __restrict__ out, int64_t B, int64_t T, int spb, int S) {
+  const int lane = threadIdx.x & 31;
+  const int64_t strip = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (strip >= B * spb) return;
+  const int64_t b = strip / spb;
+  const int64_t t0 = (strip - b * spb) * S, t1 = min(T, t0 + S);
+  const bool active = 4 * lane < C;
+  float4 wv[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j)
+    wv[j] = (active && j < k) ? *reinterpret_cast<const float4*>(w + j * C + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float bv = bias ? bias[0] : 0.f;
+  float acc[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) acc[j] = 0.f;
+  float keepv = 0.f;
+  const int64_t xb = b * x_bs + 4 * lane;
+  const int64_t rend = t1 + k - 1;                  // input rows [t0, rend)
+  for (int64_t r0 = t0; r0 < rend; r0 += 4) {
+    float4 x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      x[i] = (active && r0 + i < rend) ? ldg4_any(X, xb + (r0 + i) * C, XDT) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = r0 + i;
+      if (r >= rend) break;
+      float pj[KMAX];
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) pj[j] = x[i].x * wv[j].x + x[i].y * wv[j].y + x[i].z * wv[j].z + x[i].w * wv[j].w;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) pj[j] += __shfl_xor_sync(0xffffffffu, pj[j], o);
+      // row r is tap j of output r - j: shift the window, the oldest entry (output r - (k-1)) is complete
+#pragma unroll
+      for (int j = KMAX - 1; j > 0; --j) acc[j] = acc[j - 1] + pj[j];
+      acc[0] = pj[0];
+      const int64_t t = r - (k - 1);
+      if (t >= t0) {
+        float done = acc[0];
+#pragma unroll
+        for (int j = 1; j < KMAX; ++j) done = (j == k - 1) ? acc[j] : done;
+        const int slot = (int)(t - t0) & 31;
+        if (lane == slot) keepv = done + bv;
+        if (slot == 31 || t == t1 - 1) {
+          if (lane <= slot) out[b * T + (t - slot) + lane] = keepv;
+        }
+      }
+    }
+  }
+}
+
 // dX[b, t', c] = sum_j g[b, t'-j] * w[j*C + c], t' in [0, T+k-1).  Thread = 4 channels, block walks rows.
 template <int KMAX, int dxdt>
 __global__ void __launch_bounds__(128) conv1out_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ w,
@@ -241,6 +300,15 @@ int ag_conv1out_fwd(const void* X, int32_t x_dtype, int64_t x_bs, int64_t C, int
   AG_CHECK_ARG(X && w && out && B > 0 && T > 0 && C > 0 && C % 4 == 0 && k > 0 && x_bs % 4 == 0, "ag_conv1out_fwd: bad args");
   AG_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
                    (!x_dtype || (C % 8 == 0 && x_bs % 8 == 0)), "ag_conv1out_fwd: unaligned");
+  if (C <= 128 && k <= 4) {
+    const int S = 128;
+    const int64_t spb = (T + S - 1) / S, strips = B * spb;
+    const unsigned g = (unsigned)((strips + 7) / 8);
+    if (x_dtype) conv1out_fwd_strip_kernel<1, 4><<<g, 256, 0, (cudaStream_t)stream>>>(X, x_bs, (int)C, k, w, bias, out, B, T, (int)spb, S);
+    else conv1out_fwd_strip_kernel<0, 4><<<g, 256, 0, (cudaStream_t)stream>>>(X, x_bs, (int)C, k, w, bias, out, B, T, (int)spb, S);
+    AG_LAUNCH_CHECK();
+    return AG_OK;
+  }
   const int64_t rows = B * T;
   int64_t grid = (rows + 7) / 8;
   const int64_t cap = (int64_t)sm_count() * 8;

@@ -202,7 +202,18 @@ class NetPlan:
         return t
 
     # -- per-step work --------------------------------------------------------------------
+    def pack_key(self):
+        """Changes whenever a parameter may have changed: torch's version counters (in-place torch ops, load_state_dict)
+        plus the epoch the fused optimizers bump (their kernels write through raw pointers, invisible to torch)."""
+        return (self.mode, sum(p._version for p in self.params), sum(getattr(p, "_ag_epoch", 0) for p in self.params))
+
     def pack_forward(self):
+        # The training step touches each net twice per iteration with the same values (G: D-update then G-update; D: G-update
+        # then the next D-update): weight-norm + operand packing run once per parameter change, not once per call.
+        key = self.pack_key()
+        if key == getattr(self, "_packed_key", None):
+            return
+        self._packed_key = key
         K.wn_fwd(self.wn_tab, self.wn_rows, self.wn_n, self.wn_total)
         K.gather(self.pflat, self.wflat, self.idx_pack)
         if self.mode == "bf16":

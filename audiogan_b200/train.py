@@ -134,6 +134,8 @@ class FusedRMSprop:
             A.call("ag_mt_rmsprop", K.addr(tab), K.addr(mt.chunk_tensor), K.addr(mt.chunk_off), mt.nchunks, _CHUNK,
                    K.addr(sq), float(clip), float(grad_scale), float(self.lr), float(self.alpha), float(self.eps),
                    A.stream())
+        for p in self.params:          # the kernels wrote the parameters through raw pointers: tell the packed-operand cache
+            p._ag_epoch = getattr(p, "_ag_epoch", 0) + 1
         return self.last_norm
 
 
