@@ -33,7 +33,7 @@ class GemmDesc(C.Structure):
         ("mask_len", vp),
         ("mask_tmul", i64), ("mask_n1mul", i64), ("mask_toff", i64),
         ("a_dtype", i32), ("b_dtype", i32), ("c_dtype", i32), ("aux_dtype", i32),
-        ("reserved", i32),
+        ("a_layout", i32),
     ]
 
 

@@ -528,6 +528,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 // F: compile-time feature set (bit 0 skip, 1 LeakyReLU' operand, 2 row bias, 3 length mask, 4 LeakyReLU; alpha == 1), so a
 // launch only executes the instructions of the epilogue it asked for; F < 0: every feature decided at run time.
 enum { EPI_SKIP = 1, EPI_DACT = 2, EPI_RB = 4, EPI_MASK = 8, EPI_ACT = 16 };
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 template <bool CBF, bool AUXBF, int CH, int F>
 __device__ __forceinline__ void epi_chunk_vec(const ag_gemm_desc& d, const float* __restrict__ tr, const int4* __restrict__ rowtab,
                                               int wq, int lane, int nc, float alpha) {
@@ -611,7 +619,7 @@ __device__ __forceinline__ void epi_chunk_vec(const ag_gemm_desc& d, const float
 template <int BN, bool VECC>
 __global__ void __launch_bounds__(TM_THREADS, 1)
 gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                   int R, int tpb, int ntn, int total_tiles) {
+                   int R, int tpb, int ntn, int total_tiles, int pfx_G, int pfx_KT) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int STG = tma_stages(BN);
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -629,7 +637,8 @@ gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap map
   int* s_ml = s_t + BM;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nkb = (int)((d.K + BK - 1) / BK);
+  // channel-prefix views (a_layout 1): k-block = (channel group of 8, block of 8 taps), a 4-D box {8 c, 8 taps, 128 rows}
+  const int nkb = pfx_G ? pfx_G * pfx_KT : (int)((d.K + BK - 1) / BK);
   if (tid == 0) {
     for (int s = 0; s < STG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TM_NEPI / 32); }
@@ -773,7 +782,12 @@ gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap map
           const int s = it % STG;
           mbar_wait(&empty[s], ((it / STG) & 1) ^ 1);
           mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-          tma_load_3d(smem + s * STAGE_BYTES, &mapA, &full[s], kb * BK, t0, bt);
+          if (pfx_G) {
+            const int g = kb / pfx_KT;
+            tma_load_4d(smem + s * STAGE_BYTES, &mapA, &full[s], g * 8, t0, (kb - g * pfx_KT) * 8, bt);
+          } else {
+            tma_load_3d(smem + s * STAGE_BYTES, &mapA, &full[s], kb * BK, t0, bt);
+          }
           tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &mapB, &full[s], kb * BK, nt * BN);
         }
       }
@@ -801,10 +815,12 @@ gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap map
           if (dbgm) t_full += clock64() - q1;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const uint64_t da = umma_desc(sa, 16, 1024), db = umma_desc(sa + A_BYTES, 16, 1024);
+          // channel-prefix stage: un-swizzled [tap][row][16 B] (2 taps = 4096 B per UMMA_K); else the SWIZZLE_128B tile
+          const uint64_t da = pfx_G ? umma_desc_ns(sa, BM * 16, 128) : umma_desc(sa, 16, 1024), db = umma_desc(sa + A_BYTES, 16, 1024);
+          const uint64_t astep = pfx_G ? (uint64_t)((2 * BM * 16) >> 4) : 2ull;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            tc_mma(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            tc_mma(tacc, da + (uint64_t)k * astep, db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
           tc_commit(&empty[s]);
         }
         tc_commit(&tfull[acc]);
@@ -847,12 +863,48 @@ static int make_map_3d(CUtensorMap* map, const void* ptr, int64_t cols, int64_t 
 }
 
 static bool nt_vec_epilogue(const ag_gemm_desc* d);
+// 4-D bf16 map of a channel-prefix im2col view {channel (contiguous), row (stride rs), tap (stride ts), batch (stride bs)};
+// box {8 channels, box_r rows, 8 taps, 1}, NO swizzle (measured: SWIZZLE_128B faults unless the box's inner dimension is
+// 128 bytes): shared memory holds [tap][row][16 bytes], i.e. per tap a column of 8-row x 16-byte core matrices -- the
+// canonical un-swizzled UMMA operand (K-major for the NT kernel: LBO = box_r*16 between taps, SBO = 128 between row groups).
+static int make_map_4d(CUtensorMap* map, const void* ptr, int64_t cin, int64_t taps, int64_t rows, int64_t nb, int64_t ts, int64_t rs,
+                       int64_t bs, int box_r) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return AG_ENOTSUP; }
+  cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)rows, (cuuint64_t)taps, (cuuint64_t)nb};
+  cuuint64_t strides[3] = {(cuuint64_t)rs * 2, (cuuint64_t)ts * 2, (cuuint64_t)bs * 2};
+  cuuint32_t box[4] = {8, (cuuint32_t)box_r, 8, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (4-D) failed (%d): cin %lld taps %lld rows %lld nb %lld ts %lld rs %lld bs %lld", (int)r,
+              (long long)cin, (long long)taps, (long long)rows, (long long)nb, (long long)ts, (long long)rs, (long long)bs);
+    return AG_ECUDA;
+  }
+  return AG_OK;
+}
+// a_layout 1 (channel-prefix view, B / dW columns ordered (channel group of 8, tap padded to 8, channel)): taps, groups, blocks
+struct PfxGeom { int64_t taps, G, KT, Kq; };
+static bool pfx_geom(const ag_gemm_desc* d, PfxGeom* g) {
+  if (d->a_layout != 1 || d->a_kin <= 0 || d->a_kin % 8 != 0 || d->K % d->a_kin != 0 || d->a_k1s % 8 != 0 || d->a_k1s <= 0) return false;
+  g->taps = d->K / d->a_kin;
+  g->G = d->a_kin / 8;
+  g->KT = (g->taps + 7) / 8;
+  g->Kq = g->G * g->KT * 64;
+  return true;
+}
+
 // Row-tile height R (rows per batch) when the descriptor can take the TMA-fed kernel, else 0.
 static int64_t tma_rows_per_batch(const ag_gemm_desc* d) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("AUDIOGAN_NT"); off = (e && e[0] == 'o') ? 1 : 0; }     // AUDIOGAN_NT=old: A/B switch
   if (off) return 0;
-  if (d->a_dtype != 1 || d->b_dtype != 1 || d->a_kin < d->K || !nt_vec_epilogue(d)) return 0;
+  PfxGeom pg;
+  const bool pfx = pfx_geom(d, &pg);
+  if (d->a_dtype != 1 || d->b_dtype != 1 || (!pfx && d->a_kin < d->K) || !nt_vec_epilogue(d)) return 0;
+  if (pfx && (d->a_rpb > d->M || d->ldb < pg.Kq)) return 0;
   if ((reinterpret_cast<uintptr_t>(d->A) & 15) != 0 || d->a_rs % 8 != 0 || d->a_rs <= 0) return 0;
   const bool a_flat = d->a_rpb >= d->M, c_flat = d->c_rpb >= d->M;
   int64_t R = d->M;
@@ -876,9 +928,12 @@ static int launch_nt_tma2(const ag_gemm_desc* d, int64_t R, cudaStream_t s) {
   CUtensorMap mapA, mapB;
   const bool a_flat = d->a_rpb >= d->M;
   const int64_t nb = d->M / R;
-  int rc = make_map_3d(&mapA, d->A, d->K, R, nb, d->a_rs, (a_flat || nb == 1) ? R * d->a_rs : d->a_bs, BK, BM);
+  PfxGeom pg = {0, 0, 0, 0};
+  const bool pfx = pfx_geom(d, &pg);
+  int rc = pfx ? make_map_4d(&mapA, d->A, d->a_kin, pg.taps, R, nb, d->a_k1s, d->a_rs, nb == 1 ? R * d->a_rs : d->a_bs, BM)
+               : make_map_3d(&mapA, d->A, d->K, R, nb, d->a_rs, (a_flat || nb == 1) ? R * d->a_rs : d->a_bs, BK, BM);
   if (rc) return rc;
-  rc = make_map_2d(&mapB, d->B, d->N, d->K, d->ldb, BK, BN);
+  rc = make_map_2d(&mapB, d->B, d->N, pfx ? pg.Kq : d->K, d->ldb, BK, BN);
   if (rc) return rc;
   constexpr int STG = tma_stages(BN);
   constexpr int smem = STG * (BM * BK * 2 + BN * BK * 2) + 8 * 32 * TRLD * 4 + 1024 + (2 * STG + 4) * 8 + 16 + BM * 8 + 3 * BM * 4 + BM * 16;
@@ -889,7 +944,7 @@ static int launch_nt_tma2(const ag_gemm_desc* d, int64_t R, cudaStream_t s) {
   const int64_t total = nb * tpb * ntn;
   AG_CHECK_ARG(total < (1ll << 31), "ag_gemm_nt_tc: too many tiles");
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  kern<<<grid, TM_THREADS, smem, s>>>(*d, mapA, mapB, (int)R, (int)tpb, (int)ntn, (int)total);
+  kern<<<grid, TM_THREADS, smem, s>>>(*d, mapA, mapB, (int)R, (int)tpb, (int)ntn, (int)total, (int)pg.G, (int)pg.KT);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
@@ -1159,7 +1214,7 @@ constexpr int TNT_THREADS = 320;
 template <int BNK>
 __global__ void __launch_bounds__(TNT_THREADS, 2)
 gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapA, float* __restrict__ dw, int64_t ldw,
-                   int N, int K, int spb, int total_stages, int stages_per_split) {
+                   int N, int K, int spb, int total_stages, int stages_per_split, int pfx_KT) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int RM = 64;
@@ -1229,7 +1284,14 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
         tma_load_3d(sa, &mapY, &full[s], n0, t0, b);
         tma_load_3d(sa + RM * 128, &mapY, &full[s], n0 + 64, t0, b);
 #pragma unroll
-        for (int j = 0; j < BNK / 64; ++j) tma_load_3d(sa + A_BYTES + j * (RM * 128), &mapA, &full[s], k0 + j * 64, t0, b);
+        for (int j = 0; j < BNK / 64; ++j) {
+          if (pfx_KT) {      // channel-prefix view: 64-column block kb = (channel group, tap block); past the end -> zero fill
+            const int kb = k0 / 64 + j, g = kb / pfx_KT;
+            tma_load_4d(sa + A_BYTES + j * (RM * 128), &mapA, &full[s], g * 8, t0, (kb - g * pfx_KT) * 8, b);
+          } else {
+            tma_load_3d(sa + A_BYTES + j * (RM * 128), &mapA, &full[s], k0 + j * 64, t0, b);
+          }
+        }
       }
     }
     __syncwarp();
@@ -1241,10 +1303,14 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
         mbar_wait(&full[s], (it / STAGES) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t da = umma_desc(sa, RM * 128, 1024), db = umma_desc(sa + A_BYTES, RM * 128, 1024);
+        // channel-prefix stage of the activation operand: un-swizzled [tap][row][16 B] = MN-major core-matrix columns
+        // (LBO = 128 B between 8-row groups along the reduction, SBO = RM*16 B between 8-column groups)
+        const uint64_t da = umma_desc(sa, RM * 128, 1024);
+        const uint64_t db = pfx_KT ? umma_desc_ns(sa + A_BYTES, 128, RM * 16) : umma_desc(sa + A_BYTES, RM * 128, 1024);
+        const uint64_t bstep = pfx_KT ? 16ull : 128ull;           // 16 reduction rows: 2 x 128 B, or 2048 B in the swizzled block
 #pragma unroll
         for (int k = 0; k < RM / 16; ++k)
-          tc_mma(tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (it | k) ? 1u : 0u);
+          tc_mma(tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)k * bstep, idesc, (it | k) ? 1u : 0u);
         tc_commit(&empty[s]);
       }
       tc_commit(tmem_full);
@@ -1334,7 +1400,10 @@ static int64_t tn_tma_rows_per_batch(const ag_gemm_desc* d) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("AUDIOGAN_TN"); off = (e && e[0] == 'o') ? 1 : 0; }     // AUDIOGAN_TN=old: A/B switch
   if (off) return 0;
-  if (d->a_dtype != 1 || d->c_dtype != 1 || d->a_kin < d->K || d->c_nin < d->N) return 0;
+  PfxGeom pg;
+  const bool pfx = pfx_geom(d, &pg);
+  if (d->a_dtype != 1 || d->c_dtype != 1 || (!pfx && d->a_kin < d->K) || d->c_nin < d->N) return 0;
+  if (pfx && d->a_rpb > d->M) return 0;
   if (((reinterpret_cast<uintptr_t>(d->A) | reinterpret_cast<uintptr_t>(d->C)) & 15) != 0) return 0;
   if (d->a_rs % 8 != 0 || d->a_rs <= 0 || d->c_rs % 8 != 0 || d->c_rs <= 0 || d->N % 8 != 0) return 0;
   const bool a_flat = d->a_rpb >= d->M, y_flat = d->c_rpb >= d->M;
@@ -1355,13 +1424,18 @@ static int launch_tn_tma(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones
   const int64_t nb = d->M / R;
   int rc = make_map_3d(&mapY, d->C, d->N, R, nb, d->c_rs, (y_flat || nb == 1) ? R * d->c_rs : d->c_bs, 64, 64);
   if (rc) return rc;
-  rc = make_map_3d(&mapA, d->A, d->K, R, nb, d->a_rs, (a_flat || nb == 1) ? R * d->a_rs : d->a_bs, 64, 64);
+  PfxGeom pg = {0, 0, 0, 0};
+  const bool pfx = pfx_geom(d, &pg);
+  const int64_t Kd = pfx ? pg.Kq : d->K;                  // columns of dw the kernel produces
+  AG_CHECK_ARG(ldw >= Kd + (ones_col ? 1 : 0), "ag_gemm_tn_tc: bad ldw for the channel-prefix layout");
+  rc = pfx ? make_map_4d(&mapA, d->A, d->a_kin, pg.taps, R, nb, d->a_k1s, d->a_rs, nb == 1 ? R * d->a_rs : d->a_bs, 64)
+           : make_map_3d(&mapA, d->A, d->K, R, nb, d->a_rs, (a_flat || nb == 1) ? R * d->a_rs : d->a_bs, 64, 64);
   if (rc) return rc;
   constexpr int STAGES = nt_stages(BNK);
   constexpr int smem = STAGES * (2 * 64 * 128 + (BNK / 64) * 64 * 128) + 1024 + (2 * STAGES + 1) * 8 + 16;
   static_assert(STAGES * (2 * 64 * 128 + (BNK / 64) * 64 * 128) >= 8 * 32 * 33 * 4, "epilogue transpose tiles must fit in the stages");
   const int64_t spb = (R + 63) / 64, total = nb * spb;
-  const int64_t gx = (d->K + BNK - 1) / BNK, gy = (d->N + BM - 1) / BM;
+  const int64_t gx = (Kd + BNK - 1) / BNK, gy = (d->N + BM - 1) / BM;
   int64_t want = (int64_t)sm_count() * tn_split_factor() / (gx * gy);
   if (want < 1) want = 1;
   int64_t sps = (total + want - 1) / want;
@@ -1370,8 +1444,8 @@ static int launch_tn_tma(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones
   AG_CHECK_ARG(gy < 65536 && gz < 65536 && total < (1ll << 31), "ag_gemm_tn_tc: grid too large");
   auto kern = gemm_tn_tma_kernel<BNK>;
   AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), TNT_THREADS, smem, s>>>(mapY, mapA, dw, ldw, (int)d->N, (int)d->K, (int)spb,
-                                                                                (int)total, (int)sps);
+  kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), TNT_THREADS, smem, s>>>(mapY, mapA, dw, ldw, (int)d->N, (int)Kd, (int)spb,
+                                                                                (int)total, (int)sps, (int)pg.KT);
   AG_LAUNCH_CHECK();
   if (ones_col) {
     const int64_t bx = (d->N / 8 + 31) / 32;
@@ -1381,7 +1455,7 @@ static int launch_tn_tma(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones
     if (rows_per < 64) rows_per = 64;
     by = (d->M + rows_per - 1) / rows_per;
     tn_bias_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d->C), d->c_rpb, d->c_bs, d->c_rs,
-                                                                    d->M, (int)d->N, dw + d->K, ldw, rows_per);
+                                                                    d->M, (int)d->N, dw + Kd, ldw, rows_per);
     AG_LAUNCH_CHECK();
   }
   return AG_OK;
@@ -1405,6 +1479,8 @@ int ag_gemm_nt_tc(const ag_gemm_desc* d, void* stream) {
   const bool vec = d->a_kin % 8 == 0 && d->K % 8 == 0 && d->a_bs % al == 0 && d->a_rs % al == 0 && d->a_k1s % al == 0 &&
                    (reinterpret_cast<uintptr_t>(d->A) & 15) == 0;
   const int64_t R = vec ? tc::tma_rows_per_batch(d) : 0;
+  AG_CHECK_ARG(d->a_layout == 0 || (d->a_layout == 1 && R > 0),
+               "ag_gemm_nt_tc: the channel-prefix layout (a_layout 1) needs bf16 operands, 16-byte aligned strides and a vector epilogue");
 #define AG_TC_NT(BN)                                                                                         \
   return R > 0 ? tc::launch_nt_tma<BN>(d, R, s)                                                              \
                : (!vec ? tc::launch_nt<BN, 2>(d, s) : (d->a_dtype == 0 ? tc::launch_nt<BN, 0>(d, s) : tc::launch_nt<BN, 1>(d, s)))
@@ -1428,15 +1504,52 @@ int ag_gemm_tn_tc(const ag_gemm_desc* d, float* dw, int64_t ldw, int32_t ones_co
                   (reinterpret_cast<uintptr_t>(d->C) & 15) == 0;
   const int64_t Rt = (vy && va) ? tc::tn_tma_rows_per_batch(d) : 0;
   if (Rt > 0) {
-    if (d->K > 128) return tc::launch_tn_tma<256>(d, dw, ldw, ones_col, Rt, s);
-    if (d->K > 64) return tc::launch_tn_tma<128>(d, dw, ldw, ones_col, Rt, s);
+    tc::PfxGeom pg;
+    const int64_t Kd = tc::pfx_geom(d, &pg) ? pg.Kq : d->K;
+    if (Kd > 128) return tc::launch_tn_tma<256>(d, dw, ldw, ones_col, Rt, s);
+    if (Kd > 64) return tc::launch_tn_tma<128>(d, dw, ldw, ones_col, Rt, s);
     return tc::launch_tn_tma<64>(d, dw, ldw, ones_col, Rt, s);
   }
+  AG_CHECK_ARG(d->a_layout != 1, "ag_gemm_tn_tc: the channel-prefix layout (a_layout 1) needs bf16 operands with 16-byte aligned strides");
   const int64_t ktot = d->K + (ones_col ? 1 : 0);
   if (ktot > 128) return tc::launch_tn<256>(d, dw, ldw, ones_col, vy, va, s);
   if (ktot > 64) return tc::launch_tn<128>(d, dw, ldw, ones_col, vy, va, s);
   return tc::launch_tn<64>(d, dw, ldw, ones_col, vy, va, s);
 }
+}
+
+// debugging aid: one 4-D TMA box {8, 8, 128, 1} (SWIZZLE_128B) copied verbatim from shared memory to `out` (16 KB)
+namespace ag { namespace tc {
+__global__ void __launch_bounds__(128) dbg_tma4d_kernel(const __grid_constant__ CUtensorMap map, int c0, int c1, int c2, int c3, uint4* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_arrive_expect_tx(bar, 16384);
+    tma_load_4d(smem, &map, bar, c0, c1, c2, c3);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) out[i] = reinterpret_cast<const uint4*>(smem)[i];
+}
+} }
+extern "C" int ag_dbg_tma4d(const void* A, int64_t cin, int64_t taps, int64_t rows, int64_t nb, int64_t ts, int64_t rs, int64_t bs,
+                            int c0, int c1, int c2, int c3, void* out, int b0, int b1, int b2, int swz) {
+  CUtensorMap map;
+  ag::tc::EncodeTiledFn fn = ag::tc::encode_fn();
+  cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)rows, (cuuint64_t)nb};
+  cuuint64_t strides[3] = {(cuuint64_t)ts * 2, (cuuint64_t)rs * 2, (cuuint64_t)bs * 2};
+  cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(A), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  (CUtensorMapSwizzle)swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ag::set_error("encode failed %d", (int)r); return AG_ECUDA; }
+  AG_CUDA(cudaFuncSetAttribute(ag::tc::dbg_tma4d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 1024 + 64));
+  ag::tc::dbg_tma4d_kernel<<<1, 128, 16384 + 1024 + 64>>>(map, c0, c1, c2, c3, reinterpret_cast<uint4*>(out));
+  AG_LAUNCH_CHECK();
+  return AG_OK;
 }
 
 // profiling aid: enable/reset (on != 0) the NT kernel's phase counters, read them back (16 values)

@@ -68,6 +68,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= 2ull << 61;          // SWIZZLE_128B
   return d;
 }
+// Same fields, no swizzle ("interleaved" canonical layout): core matrices of 8 rows x 16 bytes stored as 128 contiguous
+// bytes.  K-major: LBO = stride between core matrices along K, SBO = along M/N.  MN-major: LBO along K, SBO along M/N.
+__device__ __forceinline__ uint64_t umma_desc_ns(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  return d;
+}
 // kind::f16 instruction descriptor: fp32 accumulate, bf16 x bf16, M x N, per-operand major-ness.
 __host__ __device__ inline uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |

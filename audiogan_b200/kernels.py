@@ -32,7 +32,7 @@ def _dtype_of(x):
 
 
 def gemm_desc(M, N, K, A_, a_view, B_, ldb, C_, c_view, alpha=0.0, bias=None, bias_mod=0, rowbias=None,
-              rowbias_ld=0, skip=None, act=0, dact=None, slope=LRELU_SLOPE, mask_len=None, mask=(0, 0, 0)):
+              rowbias_ld=0, skip=None, act=0, dact=None, slope=LRELU_SLOPE, mask_len=None, mask=(0, 0, 0), a_layout=0):
     """a_view = (rows_per_batch, batch_stride, row_stride[, k_inner, k_outer_stride]);
     c_view = (rows_per_batch, batch_stride, row_stride[, n_inner, n_outer_stride])."""
     d = A.GemmDesc()
@@ -58,6 +58,7 @@ def gemm_desc(M, N, K, A_, a_view, B_, ldb, C_, c_view, alpha=0.0, bias=None, bi
     d.mask_tmul, d.mask_n1mul, d.mask_toff = mask
     d.a_dtype, d.b_dtype, d.c_dtype = _dtype_of(A_), _dtype_of(B_), _dtype_of(C_)
     d.aux_dtype = _dtype_of(skip if skip is not None else dact)
+    d.a_layout = a_layout
     return d
 
 
@@ -81,11 +82,11 @@ def gemm_nt(M, N, K, A_, a_view, B_, ldb, C_, c_view, tc=False, **kw):
     A.call("ag_gemm_nt_tc" if tc else "ag_gemm_nt_f32", C.byref(d), A.stream())
 
 
-def gemm_tn(M, N, K, Y, y_view, A_, a_view, dw, ldw, ones_col=False, tc=False):
+def gemm_tn(M, N, K, Y, y_view, A_, a_view, dw, ldw, ones_col=False, tc=False, a_layout=0):
     """dw[n, k] += sum_m Y(m, n) * A(m, k); optional bias column K."""
     if not tc and _plan_mode(dw) == "bf16" and M * N * K >= TC_MIN_MACS:
         tc = True
-    d = gemm_desc(M, N, K, A_, a_view, None, 0, Y, y_view)
+    d = gemm_desc(M, N, K, A_, a_view, None, 0, Y, y_view, a_layout=a_layout)
     A.call("ag_gemm_tn_tc" if tc else "ag_gemm_tn_f32", C.byref(d), addr(dw), ldw, 1 if ones_col else 0, A.stream())
 
 
@@ -109,7 +110,7 @@ def lstm_bwd(**kw):
 
 
 def gather(dst, src, idx):
-    A.call("ag_gather", addr(dst), addr(src), addr(idx), idx.numel(), _DT[dst.dtype], A.stream())
+    A.call("ag_gather", addr(dst), addr(src), addr(idx), idx.numel(), _dtype_of(dst), A.stream())
 
 
 def frame_noise(dst, dst_ld, pad_l, src, src_ld, noise, noise_scale, B, L):

@@ -323,7 +323,7 @@ def build_generator_plan(mod, device):
         return idx.index_select(dim, pos_t[:cin])
 
     cin = 1
-    pl.cinp, pl.coff, pl.skip_off = [], [], []
+    pl.cinp, pl.coff, pl.skip_off, pl.q2c, pl.Kq = [], [], [], [], []
     for li, (k, s, hid, out) in enumerate(mod._struct):
         cw, cb, dw, db = convs[li]
         kd = k - 1
@@ -348,6 +348,16 @@ def build_generator_plan(mod, device):
         # conv data-gradient over 3 taps: [(r', ci_p), (u, h)] = Wc[h, ci, s*(2-u) + r']
         cpad = torch.cat([cwp, neg(hid, cp, 3 * s - k)], 2).view(hid, cp, 3, s).flip(2)   # [h, ci_p, u, r']
         pl.layout("c%d.wg" % li, cpad.permute(3, 1, 2, 0).reshape(s * cp, 3 * hid))
+        # the same filter for the TMA-fed kernels' channel-prefix view (include/audiogan_b200.h: a_layout 1): columns ordered
+        # (channel group of 8, tap padded to a multiple of 8, channel); its gradient region + the map back to "c%d.w"'s
+        G_, KT = cp // 8, (k + 7) // 8
+        Kq = G_ * KT * 64
+        cq = torch.cat([cwp, neg(hid, cp, KT * 8 - k)], 2).view(hid, G_, 8, KT * 8)          # [h, g, c8, tap]
+        pl.layout("c%d.wq" % li, cq.permute(0, 1, 3, 2).reshape(hid, Kq))
+        gq = pl.grad_region("c%d.wq" % li, (hid, Kq + 1))
+        gqv = gq[:, :Kq].view(hid, G_, KT * 8, 8)[:, :, :k].permute(0, 2, 1, 3).reshape(hid, k * cp)      # -> (tap, ci_p)
+        pl.q2c.append((torch.cat([gqv, gq[:, Kq:]], 1) - pl.gpack.off["c%d.wq" % li]).to(torch.int32).contiguous().to(device))
+        pl.Kq.append(Kq)
         gc = pl.grad_region("c%d.w" % li, (hid, k * cp + 1))
         gd = pl.grad_region("d%d.w" % li, (hid, kd * out))
         gb = pl.grad_region("d%d.b" % li, (out,))

@@ -65,7 +65,10 @@ typedef struct ag_gemm_desc {
   const int32_t* mask_len;      /* pos = t*mask_tmul + (n/c_nin)*mask_n1mul + mask_toff; zero unless 0 <= pos < mask_len[batch] */
   int64_t mask_tmul, mask_n1mul, mask_toff;
   int32_t a_dtype, b_dtype, c_dtype, aux_dtype;   /* 0 = fp32, 1 = bf16 (skip/dact use aux_dtype) */
-  int32_t reserved;
+  int32_t a_layout;   /* 0: B / dW columns in A's column order.  1 (tensor-core path, bf16, channel-prefix views with
+                         a_kin % 8 == 0): columns ordered (channel group g of 8, tap j padded to a multiple of 8, channel c),
+                         column = ((g*KT + j/8)*8 + j%8)*8 + c with KT = ceil(taps/8), taps = K/a_kin; ldb / ldw >=
+                         (a_kin/8)*KT*64 (+1 with ones_col, the bias column comes last); padded taps hold zeros. */
 } ag_gemm_desc;
 
 /* C = epilogue(A . B^T).  fp32 FFMA path ("fp32 mode", <=1e-5 parity). */

@@ -614,3 +614,43 @@ def test_gemm_tn_tma_flat_and_padded_rows(Bn, Tm, N, K):
     dw2 = T.zeros(N, K, device="cuda")
     Kn.gemm_tn(M, N, K, (Yp.cuda(), N), (Tm, (Tm + 2) * N, N), A.cuda(), (M, 0, K), dw2, K, tc=True)
     assert rel(dw2, ref) < 3e-5
+
+
+@pytest.mark.parametrize("Bn,cin,CT,hid,L,k,s", [(3, 24, 120, 64, 1000, 9, 4), (2, 8, 120, 128, 1600, 17, 8), (2, 88, 120, 32, 520, 9, 4)])
+def test_gemm_tma_channel_prefix_view(Bn, cin, CT, hid, L, k, s):
+    """a_layout 1: the generator's conv over a channel PREFIX of the dense channel-last buffer through a 4-D tensor map
+    {channel, tap, row, batch}; filter / gradient columns ordered (channel group, tap padded to 8, channel).  Forward
+    (bias + LeakyReLU) and weight + bias gradient against conv1d on the same bf16-rounded data."""
+    from audiogan_b200 import kernels as Kn
+    T.manual_seed(22)
+    p, Lh, PAD = (k - 1) // 2, L // s, 8
+    Lp = L + 2 * PAD
+    Xd = T.zeros(Bn, Lp, CT)
+    Xd[:, PAD:PAD + L] = T.randn(Bn, L, CT)             # channels >= cin hold data the view must not read
+    Xd = Xd.bfloat16()
+    w = (T.randn(hid, cin, k) / (cin * k) ** 0.5).bfloat16()
+    b = T.randn(hid)
+    G_, KT = cin // 8, (k + 7) // 8
+    Kq = G_ * KT * 64
+    wq = T.zeros(hid, G_, KT * 8, 8)
+    wq[:, :, :k] = w.float().view(hid, G_, 8, k).permute(0, 1, 3, 2)
+    wq = wq.reshape(hid, Kq).bfloat16().cuda()
+    x = Xd[:, PAD:PAD + L, :cin].float().permute(0, 2, 1)
+    wr, br = w.float().clone().requires_grad_(), b.clone().requires_grad_()
+    pre = F.conv1d(x, wr, br, stride=s, padding=p)[:, :, :Lh]
+    ref = F.leaky_relu(pre, 0.01)
+    Hh = T.zeros(Bn, Lh + 2, hid, device="cuda", dtype=T.bfloat16)
+    Xg = Xd.cuda()
+    Kn.gemm_nt(Bn * Lh, hid, k * cin, (Xg, (PAD - p) * CT), (Lh, Lp * CT, s * CT, cin, CT), wq, Kq, (Hh, hid),
+               (Lh, (Lh + 2) * hid, hid), bias=b.cuda(), act=1, tc=True, a_layout=1)
+    assert rel(Hh[:, 1:Lh + 1], ref.permute(0, 2, 1)) < 8e-3
+    dH = T.randn(Bn, Lh, hid).bfloat16()
+    pre.backward(dH.float().permute(0, 2, 1))
+    dHp = T.zeros(Bn, Lh + 2, hid, dtype=T.bfloat16)
+    dHp[:, 1:Lh + 1] = dH
+    dw = T.zeros(hid, Kq + 1, device="cuda")
+    Kn.gemm_tn(Bn * Lh, hid, k * cin, (dHp.cuda(), hid), (Lh, (Lh + 2) * hid, hid), (Xg, (PAD - p) * CT),
+               (Lh, Lp * CT, s * CT, cin, CT), dw, Kq + 1, ones_col=True, tc=True, a_layout=1)
+    got = dw[:, :Kq].view(hid, G_, KT * 8, 8)[:, :, :k].permute(0, 1, 3, 2).reshape(hid, cin, k)
+    assert rel(got, wr.grad) < 3e-5 and rel(dw[:, Kq], br.grad) < 3e-5
+    assert float(dw[:, :Kq].view(hid, G_, KT * 8, 8)[:, :, k:].abs().max()) == 0 or KT * 8 == k
