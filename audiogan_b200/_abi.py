@@ -102,6 +102,8 @@ _PROTOS = {
     "ag_outer_dact": [vp, vp, vp, i32, vp, i32, i64, i64, f32, vp],
     "ag_conv1in_fwd": [vp, i64, vp, vp, vp, i32, i64, i32, i32, i64, i64, i64, vp, f32, vp],
     "ag_conv1in_wgrad": [vp, i32, i64, vp, i64, vp, i32, i32, i64, i64, i64, vp],
+    "ag_conv1in_dgrad": [vp, i32, i64, vp, vp, i64, i32, i32, i32, i64, i64, i64, i64, vp],
+    "ag_wcolsum": [vp, vp, i32, i64, i64, vp, vp],
     "ag_conv1out_fwd": [vp, i32, i64, i64, i32, vp, vp, vp, i64, i64, vp],
     "ag_conv1out_dgrad": [vp, vp, vp, i32, i64, i64, i32, i64, i64, vp],
     "ag_conv1out_wgrad": [vp, vp, i32, i64, i64, i32, vp, i64, i64, vp],

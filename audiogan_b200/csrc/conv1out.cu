@@ -144,14 +144,19 @@ __global__ void __launch_bounds__(128) conv1out_wgrad_kernel(const float* __rest
     float4 acc[KMAX];
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-    for (int64_t r = r0 + rl; r < r1; r += 4) {
-      const float4 x = ldg4_any(X, b * x_bs + r * C + cc, xdt);
+    for (int64_t r = r0 + rl; r < r1; r += 16) {        // 4 rows of this lane in flight before the first use
+      float4 x[4];
 #pragma unroll
-      for (int j = 0; j < KMAX; ++j) {
-        const int64_t t = r - j;                       // X row r is tap j of output t = r - j
-        const float gv = (j < k && t >= 0 && t < T) ? __ldg(gb + t) : 0.f;
-        acc[j].x += gv * x.x; acc[j].y += gv * x.y; acc[j].z += gv * x.z; acc[j].w += gv * x.w;
+      for (int i = 0; i < 4; ++i)
+        x[i] = (r + 4 * i < r1) ? ldg4_any(X, b * x_bs + (r + 4 * i) * C + cc, xdt) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          const int64_t t = r + 4 * i - j;             // X row r is tap j of output t = r - j
+          const float gv = (j < k && t >= 0 && t < T && r + 4 * i < r1) ? __ldg(gb + t) : 0.f;
+          acc[j].x += gv * x[i].x; acc[j].y += gv * x[i].y; acc[j].z += gv * x[i].z; acc[j].w += gv * x[i].w;
+        }
       }
     }
     // the 4 row lanes meet in shared memory: same-address L2 atomics serialise, so one set per block, not per warp
@@ -270,6 +275,63 @@ __global__ void __launch_bounds__(256) conv1in_wgrad_kernel(const void* __restri
   }
 }
 
+// Data gradient of that first layer (the gradient of the raw waveform, audiogan.py:769, :145, :131 -- x_grad_norm, FGSM and the
+// generator update need it): dx[b, u] = sum_{t, j : s*t + j == u} sum_c dy[b, t, c] * w[c*k + j] in padded coordinates
+// u in [0, Tin + 2p), zero outside the real samples.  As a GEMM it has N = s = 2 columns; here: one thread per sample.
+__global__ void __launch_bounds__(256) conv1in_dgrad_kernel(const void* __restrict__ dy, int ydt, int64_t dy_bs, const float* __restrict__ w,
+                                                            float* __restrict__ dx, int64_t dx_ld, int k, int s, int p, int C,
+                                                            int64_t T, int64_t Tin) {
+  extern __shared__ float wsm[];                    // [k][C] (transposed: the channel loop reads consecutive floats)
+  for (int i = threadIdx.x; i < k * C; i += blockDim.x) { const int c = i / k, j = i - c * k; wsm[j * C + c] = w[i]; }
+  __syncthreads();
+  const int64_t b = blockIdx.y;
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= dx_ld) return;
+  float acc = 0.f;
+  if (u >= p && u < p + Tin) {
+    for (int j = 0; j < k; ++j) {
+      const int64_t r = u - j;
+      if (r < 0 || r % s != 0) continue;
+      const int64_t t = r / s;
+      if (t >= T) continue;
+      const int64_t row = b * dy_bs + t * C;
+      const float* wj = wsm + j * C;
+      for (int c = 0; c < C; c += 4) {
+        const float4 g = ldg4_any(dy, row + c, ydt);
+        acc += g.x * wj[c] + g.y * wj[c + 1] + g.z * wj[c + 2] + g.w * wj[c + 3];
+      }
+    }
+  }
+  dx[b * dx_ld + u] = acc;
+}
+
+// out[k] += sum_m g[m] * X[m, k], out[K] += sum_m g[m]: weight + bias gradient of a Linear(K -> 1) (the classifier's last layer,
+// audiogan.py:508-512) -- a GEMM with N = 1, here a weighted column sum over the packed [M, K] activation (HBM-bound).
+__global__ void __launch_bounds__(256) wcolsum_kernel(const float* __restrict__ g, const void* __restrict__ X, int xdt, int64_t M, int K4,
+                                                      float* __restrict__ out, int64_t rows_per) {
+  __shared__ float4 red[256];
+  const int c4 = threadIdx.x % K4, rl = threadIdx.x / K4, nrl = 256 / K4;
+  const int64_t m0 = (int64_t)blockIdx.x * rows_per, m1 = min(M, m0 + rows_per);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  float gs = 0.f;
+  if (rl < nrl)
+    for (int64_t m = m0 + rl; m < m1; m += nrl) {
+      const float gv = __ldg(g + m);
+      const float4 x = ldg4_any(X, m * (4 * K4) + 4 * c4, xdt);
+      a.x += gv * x.x; a.y += gv * x.y; a.z += gv * x.z; a.w += gv * x.w;
+      gs += gv;
+    }
+  red[threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.x < K4) {
+    float4 v = red[threadIdx.x];
+    for (int r = 1; r < nrl; ++r) { const float4 q = red[r * K4 + threadIdx.x]; v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+    float* o = out + 4 * threadIdx.x;
+    atomicAdd(o, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
+  }
+  if (c4 == 0 && rl < nrl) atomicAdd(out + 4 * K4, gs);          // every row lane of column group 0 saw a disjoint set of rows
+}
+
 }  // namespace ag
 
 using namespace ag;
@@ -342,6 +404,28 @@ int ag_conv1out_wgrad(const float* g, const void* X, int32_t x_dtype, int64_t x_
   dim3 grid((unsigned)((T + k - 1 + rpb - 1) / rpb), (unsigned)B);
   if (x_dtype) conv1out_wgrad_kernel<4, 1><<<grid, 128, 0, (cudaStream_t)stream>>>(g, X, x_bs, (int)C, k, dw, T, rpb);
   else conv1out_wgrad_kernel<4, 0><<<grid, 128, 0, (cudaStream_t)stream>>>(g, X, x_bs, (int)C, k, dw, T, rpb);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_conv1in_dgrad(const void* dy, int32_t dy_dtype, int64_t dy_bs, const float* w, float* dx, int64_t dx_ld, int32_t k, int32_t s,
+                     int32_t p, int64_t C, int64_t B, int64_t T, int64_t Tin, void* stream) {
+  AG_CHECK_ARG(dy && w && dx && B > 0 && B < 65536 && T > 0 && Tin > 0 && C > 0 && C % 4 == 0 && C <= 1024 && k > 0 && k <= 64 && s > 0 && p >= 0 &&
+                   dy_bs % 4 == 0 && dx_ld >= Tin + p && (reinterpret_cast<uintptr_t>(dy) & (dy_dtype ? 7 : 15)) == 0,
+               "ag_conv1in_dgrad: bad args");
+  dim3 grid((unsigned)((dx_ld + 255) / 256), (unsigned)B);
+  conv1in_dgrad_kernel<<<grid, 256, (size_t)k * C * 4, (cudaStream_t)stream>>>(dy, dy_dtype, dy_bs, w, dx, dx_ld, k, s, p, (int)C, T, Tin);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+
+int ag_wcolsum(const float* g, const void* X, int32_t x_dtype, int64_t M, int64_t K, float* out, void* stream) {
+  AG_CHECK_ARG(g && X && out && M > 0 && K > 0 && K % 4 == 0 && K <= 1024 && (reinterpret_cast<uintptr_t>(X) & (x_dtype ? 7 : 15)) == 0,
+               "ag_wcolsum: bad args");
+  int64_t blocks = (int64_t)sm_count() * 4;
+  int64_t rows_per = (M + blocks - 1) / blocks;
+  if (rows_per < 64) rows_per = 64;
+  blocks = (M + rows_per - 1) / rows_per;
+  wcolsum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, X, x_dtype, M, (int)(K / 4), out, rows_per);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

@@ -1518,40 +1518,6 @@ int ag_gemm_tn_tc(const ag_gemm_desc* d, float* dw, int64_t ldw, int32_t ones_co
 }
 }
 
-// debugging aid: one 4-D TMA box {8, 8, 128, 1} (SWIZZLE_128B) copied verbatim from shared memory to `out` (16 KB)
-namespace ag { namespace tc {
-__global__ void __launch_bounds__(128) dbg_tma4d_kernel(const __grid_constant__ CUtensorMap map, int c0, int c1, int c2, int c3, uint4* out) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384);
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_arrive_expect_tx(bar, 16384);
-    tma_load_4d(smem, &map, bar, c0, c1, c2, c3);
-  }
-  __syncthreads();
-  mbar_wait(bar, 0);
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) out[i] = reinterpret_cast<const uint4*>(smem)[i];
-}
-} }
-extern "C" int ag_dbg_tma4d(const void* A, int64_t cin, int64_t taps, int64_t rows, int64_t nb, int64_t ts, int64_t rs, int64_t bs,
-                            int c0, int c1, int c2, int c3, void* out, int b0, int b1, int b2, int swz) {
-  CUtensorMap map;
-  ag::tc::EncodeTiledFn fn = ag::tc::encode_fn();
-  cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)rows, (cuuint64_t)nb};
-  cuuint64_t strides[3] = {(cuuint64_t)ts * 2, (cuuint64_t)rs * 2, (cuuint64_t)bs * 2};
-  cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(A), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  (CUtensorMapSwizzle)swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { ag::set_error("encode failed %d", (int)r); return AG_ECUDA; }
-  AG_CUDA(cudaFuncSetAttribute(ag::tc::dbg_tma4d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 1024 + 64));
-  ag::tc::dbg_tma4d_kernel<<<1, 128, 16384 + 1024 + 64>>>(map, c0, c1, c2, c3, reinterpret_cast<uint4*>(out));
-  AG_LAUNCH_CHECK();
-  return AG_OK;
-}
-
 // profiling aid: enable/reset (on != 0) the NT kernel's phase counters, read them back (16 values)
 extern "C" int ag_gemm_dbg_enable(int on) {
   unsigned long long z[16] = {0};

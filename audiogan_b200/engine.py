@@ -52,7 +52,15 @@ class _GenFn(torch.autograd.Function):
         save = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         # hoisted input projection: pre = [z|c|1|1] . [W_z | b_ih | b_hh]^T      (audiogan.py:425-426, :439-440)
         pre = _empty(B, Tcap, 4 * H, device=dev)
-        K.gemm_nt(B * Tcap, 4 * H, NZ + 2, zc1, (Tcap, Tcap * (NZ + 2), NZ + 2), plan.Poff("wz"), NZ + 2,
+        if _adt(plan) == torch.bfloat16 and B * Tcap * 4 * H * plan.ZP >= K.TC_MIN_MACS:
+            # bf16 copy with a 16-byte row pitch: the projection and its weight gradient run on the TMA-fed kernels
+            # (K = the padded width: the pad columns are zeros on both sides)
+            zld = plan.ZP
+            zin = torch.zeros(B, Tcap, zld, device=dev, dtype=torch.bfloat16)
+            zin[:, :, :NZ + 2] = zc1
+        else:
+            zld, zin = NZ + 2, zc1
+        K.gemm_nt(B * Tcap, 4 * H, zld, zin, (Tcap, Tcap * zld, zld), plan.Poff("wz"), NZ + 2,
                   pre, (Tcap, Tcap * 4 * H, 4 * H))
         hbuf = _zeros(B, Tcap + 2, H, device=dev)
         xbuf = _zeros(B, Tcap + 1, F, device=dev)
@@ -114,7 +122,7 @@ class _GenFn(torch.autograd.Function):
         s_out = sbuf[:, :T]
         if save:
             ctx.plan, ctx.struct, ctx.dims = plan, struct, (B, T, Tcap, L)
-            ctx.bufs = (zc1, hbuf, xbuf, gates, cbuf, Xd, hh, hbuf16, xbuf16)
+            ctx.bufs = (zin, hbuf, xbuf, gates, cbuf, Xd, hh, hbuf16, xbuf16)
         ctx.mark_non_differentiable(stop, glen)
         ctx.set_materialize_grads(False)
         return xout, s_out, stop[:, :T], glen
@@ -202,7 +210,8 @@ class _GenFn(torch.autograd.Function):
             yv = (T, Tcap * 4 * H, 4 * H)
             K.gemm_tn(B * T, 4 * H, H, dgo, yv, hbo, (T, (Tcap + 2) * H, H), plan.GPoff("w1"), H + F)
             K.gemm_tn(B * T, 4 * H, F, dgo, yv, xbo, (T, (Tcap + 1) * F, F), plan.GPoff("w1", H), H + F)
-            K.gemm_tn(B * T, 4 * H, NZ + 2, dgo, yv, zc1, (T, Tcap * (NZ + 2), NZ + 2), plan.GPoff("wz"), NZ + 2)
+            zld = zc1.shape[2]        # fp32 [.., NZ+2] or the bf16 copy with its padded row pitch
+            K.gemm_tn(B * T, 4 * H, zld, dgo, yv, zc1, (T, Tcap * zld, zld), plan.GPoff("wz"), plan.ZP)
             K.gemm_tn(B * T, FP, H, dpo, (T, Tcap * FP, FP), (hbo, H), (T, (Tcap + 2) * H, H), plan.GPoff("w2"), H + 1,
                       ones_col=True)
         dzc1 = None
@@ -284,7 +293,11 @@ class _DiscCNNFn(torch.autograd.Function):
             elif wgrad:
                 K.gemm_tn(B * Tout, cout, k * cin, (dy, PL * cout), (Tout, gdy[0], cout), acts[i], a_view,
                           plan.GPoff("c%d.w" % i), k * cin + 1, ones_col=True)
-            if i > 0 or need_dx:
+            if i == 0 and need_dx and cin == 1 and cout % 4 == 0 and (k - 1) // 2 == DPAD:
+                # gradient of the raw waveform: a GEMM with N = s columns -> direct kernel (one thread per sample)
+                dX = _empty(B, Tin + 2 * DPAD, 1, device=dev)
+                K.conv1in_dgrad((dy, PL * cout), gdy[0], plan.Poff("c%d.w" % i), dX, Tin + 2 * DPAD, k, s, DPAD, cout, B, Tout, Tin)
+            elif i > 0 or need_dx:
                 Mp = (Tin + DPAD + s - 1) // s
                 # the gradient of the raw waveform (layer 0) is a caller-visible fp32 tensor
                 dXn = _empty(B, Tin + 2 * DPAD, cin, device=dev, dtype=adt if i > 0 else torch.float32)
@@ -365,7 +378,9 @@ class _DiscTailFn(torch.autograd.Function):
         g = g.contiguous()
         geo = (Tm, (Tm + 2) * S, S)
         flat = lambda n: (M, 0, n)
-        if wgrad:
+        if wgrad and (S // 2) % 4 == 0 and S // 2 <= 1024:
+            K.wcolsum(g, h3, M, S // 2, plan.GPoff("k2.w"))             # Linear(S/2 -> 1): weighted column sum, not a GEMM
+        elif wgrad:
             K.gemm_tn(M, 1, S // 2, g, flat(1), h3, flat(S // 2), plan.GPoff("k2.w"), S // 2 + 1, ones_col=True)
         adt = torch.bfloat16 if bf else torch.float32
         hin = hbuf16 if bf else hbuf

@@ -148,6 +148,15 @@ def conv1in_wgrad(dy, dy_bs, x, x_ld, dw, k, s, Cn, B, T):
     A.call("ag_conv1in_wgrad", addr(dy), _dtype_of(dy), dy_bs, addr(x), x_ld, addr(dw), k, s, Cn, B, T, A.stream())
 
 
+def conv1in_dgrad(dy, dy_bs, w, dx, dx_ld, k, s, p, Cn, B, T, Tin):
+    A.call("ag_conv1in_dgrad", addr(dy), _dtype_of(dy), dy_bs, addr(w), addr(dx), dx_ld, k, s, p, Cn, B, T, Tin, A.stream())
+
+
+def wcolsum(g, X, M, Kn, out):
+    """out[k] += sum_m g[m] X[m, k], out[Kn] += sum_m g[m] (X packed [M, Kn], fp32 or bf16)."""
+    A.call("ag_wcolsum", addr(g), addr(X), _dtype_of(X), M, Kn, addr(out), A.stream())
+
+
 def outer_dact(g, w, act, out, M, N, slope=LRELU_SLOPE):
     """out[m, n] = g[m] * w[n] * lrelu'(act[m, n]) (packed [M, N]; act / out fp32 or bf16)."""
     A.call("ag_outer_dact", addr(g), addr(w), addr(act), _dtype_of(act), addr(out), _dtype_of(out), M, N, float(slope), A.stream())

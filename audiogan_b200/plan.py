@@ -289,7 +289,8 @@ def build_generator_plan(mod, device):
     pl.layout("wxt", wih[:, :F].t())                                                   # [F, 4H]
     pl.layout("wzt", wih[:, F:].t())                                                   # [NZ, 4H]
     g1 = pl.grad_region("w1", (4 * H, H + F))
-    gz = pl.grad_region("wz", (4 * H, NZ + 2))
+    pl.ZP = (NZ + 2 + 7) // 8 * 8                  # row pitch of the wz gradient region (and of the bf16 [z|c|1|1] operand)
+    gz = pl.grad_region("wz", (4 * H, pl.ZP))
     g2 = pl.grad_region("w2", (FP, H + 1))
     pl.grad_of("rnn.wih", torch.cat([g1[:, H:], gz[:, :NZ]], 1))
     pl.grad_of("rnn.whh", g1[:, :H])

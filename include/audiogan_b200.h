@@ -236,6 +236,14 @@ int ag_conv1in_fwd(const float* x, int64_t x_ld, const float* w, const float* bi
                    int32_t k, int32_t s, int64_t C, int64_t B, int64_t T, const int32_t* len, float slope, void* stream);
 int ag_conv1in_wgrad(const void* dy, int32_t dy_dtype, int64_t dy_bs, const float* x, int64_t x_ld, float* dw, int32_t k, int32_t s, int64_t C,
                      int64_t B, int64_t T, void* stream);
+/* Data gradient of the same layer = gradient of the raw waveform (audiogan.py:769 x_grad_norm, :145 / :131 FGSM, and the
+ * generator update): dx[b*dx_ld + u] = sum_{t,j: s*t + j == u} sum_c dy[b,t,c] * w[c*k + j] for p <= u < p + Tin (padded
+ * coordinates, p = left zero pad of the forward input), 0 elsewhere; every one of the dx_ld entries is written. */
+int ag_conv1in_dgrad(const void* dy, int32_t dy_dtype, int64_t dy_bs, const float* w, float* dx, int64_t dx_ld, int32_t k, int32_t s,
+                     int32_t p, int64_t C, int64_t B, int64_t T, int64_t Tin, void* stream);
+/* Weight + bias gradient of a Linear(K -> 1) (the classifier's last layer, audiogan.py:508-512 backward):
+ * out[k] += sum_m g[m] * X[m*K + k], out[K] += sum_m g[m]; X packed [M, K], dtype 0 fp32 / 1 bf16, K % 4 == 0, K <= 1024. */
+int ag_wcolsum(const float* g, const void* X, int32_t x_dtype, int64_t M, int64_t K, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Last generator layer, Conv1d(C -> 1, k) over the dense channel-last buffer (audiogan.py:403-407, :467): HBM-bound

@@ -654,3 +654,26 @@ def test_gemm_tma_channel_prefix_view(Bn, cin, CT, hid, L, k, s):
     got = dw[:, :Kq].view(hid, G_, KT * 8, 8)[:, :, :k].permute(0, 1, 3, 2).reshape(hid, cin, k)
     assert rel(got, wr.grad) < 3e-5 and rel(dw[:, Kq], br.grad) < 3e-5
     assert float(dw[:, :Kq].view(hid, G_, KT * 8, 8)[:, :, k:].abs().max()) == 0 or KT * 8 == k
+
+
+@pytest.mark.parametrize("dt", [T.float32, T.bfloat16])
+def test_conv1in_dgrad_and_wcolsum(dt):
+    """Direct kernels for the two GEMMs with 1-2 output columns: gradient of the raw waveform through the discriminator's first
+    conv (k = 7, s = 2, C_in = 1), and the weight / bias gradient of the classifier's Linear(K -> 1)."""
+    from audiogan_b200 import kernels as K
+    T.manual_seed(4)
+    B, L, k, s, Co, p = 3, 61, 7, 2, 16, 3
+    To = (L + s - 1) // s
+    w = T.randn(Co, k)
+    dy = T.randn(B, To, Co).to(dt)
+    x = T.zeros(B, 1, L, requires_grad=True)
+    F.conv1d(x, w[:, None], None, stride=s, padding=p)[:, :, :To].backward(dy.float().permute(0, 2, 1))
+    dx = T.full((B, L + 2 * p), 7.0, device="cuda")
+    K.conv1in_dgrad(dy.cuda(), To * Co, w.cuda(), dx, L + 2 * p, k, s, p, Co, B, To, L)
+    assert rel(dx[:, p:p + L], x.grad[:, 0]) < 1e-5
+    assert float(dx[:, :p].abs().max()) == 0 and float(dx[:, p + L:].abs().max()) == 0
+    M, Kn = 1003, 512
+    g, X = T.randn(M), T.randn(M, Kn).to(dt)
+    out = T.zeros(Kn + 1, device="cuda")
+    K.wcolsum(g.cuda(), X.cuda(), M, Kn, out)
+    assert rel(out[:Kn], g @ X.float()) < 1e-5 and abs(float(out[Kn]) - float(g.sum())) < 1e-3
