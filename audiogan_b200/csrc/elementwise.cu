@@ -332,6 +332,16 @@ __global__ void transpose_bct_kernel(const float* __restrict__ src, float* __res
   }
 }
 
+// zero rows [0, head) and [tail0, rows) of every batch of a packed [B, rows, row_bytes] buffer, 16 bytes per thread
+__global__ void zero_pads_kernel(uint4* __restrict__ p, int64_t B, int64_t rows, int64_t row16, int64_t head, int64_t tail0) {
+  const int64_t per = (head + rows - tail0) * row16, total = B * per;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per, j = i - b * per;
+    const int64_t off = j < head * row16 ? j : tail0 * row16 + (j - head * row16);
+    p[b * rows * row16 + off] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 static inline int grid_for(int64_t n, int threads) {
   int64_t b = (n + threads - 1) / threads;
   int64_t cap = (int64_t)sm_count() * 16;
@@ -436,6 +446,15 @@ int ag_copy3d(void* dst, int64_t d_bs, int64_t d_rs, int64_t d_cs, const void* s
   AG_CHECK_ARG(dst && src && B > 0 && T > 0 && Cn > 0, "ag_copy3d: bad args");
   copy3d_kernel<<<grid_for(B * T * Cn, 256), 256, 0, (cudaStream_t)stream>>>(dst, d_bs, d_rs, d_cs, src, s_bs, s_rs, s_cs, B, T,
                                                                             Cn, accumulate, src_dtype, dst_dtype);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_zero_pads(void* buf, int64_t B, int64_t rows, int64_t row_bytes, int64_t head, int64_t tail0, void* stream) {
+  AG_CHECK_ARG(buf && B > 0 && rows > 0 && row_bytes > 0 && row_bytes % 16 == 0 && head >= 0 && tail0 >= head && tail0 <= rows &&
+                   (reinterpret_cast<uintptr_t>(buf) & 15) == 0, "ag_zero_pads: bad args");
+  const int64_t n = B * (head + rows - tail0) * (row_bytes / 16);
+  if (n == 0) return AG_OK;
+  zero_pads_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4*>(buf), B, rows, row_bytes / 16, head, tail0);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

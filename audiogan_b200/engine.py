@@ -89,8 +89,7 @@ class _GenFn(torch.autograd.Function):
         # frame assembly into channel 0 of the dense buffer (audiogan.py:462-464)
         adt = _adt(plan)
         Xd = _empty(B, Lp, CT, device=dev, dtype=adt)       # CT = padded channel count (slots of 8, plan.py)
-        Xd[:, :GPAD].zero_()
-        Xd[:, GPAD + L:].zero_()
+        K.zero_pads(Xd, GPAD, GPAD + L)
         Xd[:, GPAD:GPAD + L, 1:plan.coff[0]].zero_()        # pad channels of the waveform slot
         K.copy3d((Xd, GPAD * CT), (Lp * CT, CT, 0), (xbuf, F), ((Tcap + 1) * F, 1, 0), B, L, 1)
         hh = []
@@ -99,8 +98,7 @@ class _GenFn(torch.autograd.Function):
             p, pd, Lh = (k - 1) // 2, s // 2, L // s
             cin = plan.cinp[li]                             # padded channel prefix this block reads == slot it writes
             Hh = _empty(B, Lh + 2, hid, device=dev, dtype=adt)
-            Hh[:, 0].zero_()
-            Hh[:, Lh + 1].zero_()
+            K.zero_pads(Hh, 1, Lh + 1)
             # TMA-fed kernel over a 4-D tensor map (channel prefix, row, tap, batch).  Its boxes have 16-byte inner rows, so for
             # wide prefixes the producer-warp kernel is faster (measured: cin 8 / 24 -> 1.9x / 1.5x faster, 56 equal, 88 0.6x)
             if adt == torch.bfloat16 and cin <= 32:
@@ -163,8 +161,7 @@ class _GenFn(torch.autograd.Function):
                     K.colsum((dyl, pd * out), (L + 2 * pd) * out, out, B, L, out, plan.GPoff("d%d.b" % li))
                 # transposed-conv data gradient = strided conv over dyl, times lrelu'(hidden)
                 dH = _empty(B, Lh + 2, hid, device=dev, dtype=adt)
-                dH[:, 0].zero_()
-                dH[:, Lh + 1].zero_()
+                K.zero_pads(dH, 1, Lh + 1)
                 K.gemm_nt(B * Lh, hid, kd * out, dyl, (Lh, (L + 2 * pd) * out, s * out), plan.Poff("d%d.wg" % li), kd * out,
                           (dH, hid), (Lh, (Lh + 2) * hid, hid), dact=(Hh, hid))
                 if wgrad:
@@ -241,8 +238,7 @@ class _DiscCNNFn(torch.autograd.Function):
         for i, (k, s, cout) in enumerate(struct):
             Tout = (Tin + s - 1) // s
             a = _empty(B, Tout + 2 * DPAD, cout, device=dev, dtype=_adt(plan))
-            a[:, :DPAD].zero_()
-            a[:, DPAD + Tout:].zero_()
+            K.zero_pads(a, DPAD, DPAD + Tout)
             if cin == 1 and k <= 8 and cout % 4 == 0 and (k - 1) // 2 == DPAD:
                 # first layer on the raw waveform: K = k, a stream over the output (direct HBM kernel, fp32 arithmetic)
                 K.conv1in_fwd(acts[-1], Tin + 2 * DPAD, plan.Poff("c%d.w" % i), plan.Poff("c%d.b" % i), (a, DPAD * cout),

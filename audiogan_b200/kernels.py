@@ -183,6 +183,17 @@ def conv1out_wgrad(g, X, x_bs, Cn, k, dw, B, T):
     A.call("ag_conv1out_wgrad", addr(g), addr(X), _dtype_of(X), x_bs, Cn, k, addr(dw), B, T, A.stream())
 
 
+def zero_pads(buf, head, tail0):
+    """zero rows [0, head) and [tail0, rows) of every batch of a contiguous [B, rows, C] tensor."""
+    Bn, rows = buf.shape[0], buf.shape[1]
+    rb = buf[0, 0].numel() * buf.element_size()
+    if rb % 16 == 0 and buf.is_contiguous() and buf.data_ptr() % 16 == 0:
+        A.call("ag_zero_pads", addr(buf), Bn, rows, rb, head, tail0, A.stream())
+    else:
+        buf[:, :head].zero_()
+        buf[:, tail0:].zero_()
+
+
 def rowgroup_sum(src, out, B, T, N):
     A.call("ag_rowgroup_sum", addr(src), addr(out), B, T, N, A.stream())
 

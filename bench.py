@@ -224,14 +224,46 @@ def run_ours(args):
     # ---- e2e: host buffers, H2D of the step's inputs and D2H of the losses inside the timed region
     d2h = [0]
 
+    # The input pipeline a training loop would run: step i+1's inputs are copied from pinned host memory on a copy stream
+    # while step i computes (every step's H2D copy happens inside the timed region), and step i's three losses come back
+    # through a pinned buffer that the host reads one step later (an immediate .cpu() would drain the launch queue every step).
+    copy_stream = torch.cuda.Stream()
+    pinned_out = [torch.empty(3, pin_memory=True) for _ in range(2)]
+    out_ev = [None, None]
+    losses_seen = []
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            di = on_dev(host[i % 2], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return di, ev
+
+    pending = [prefetch(0)]
+
     def e2e_step(i):
-        di = on_dev(host[i % 2], non_blocking=True)
+        di, ev = pending.pop()
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for k, v in di.items():
+            if not k.endswith("_len"):
+                v.record_stream(cur)
+        pending.append(prefetch(i + 1))
         m1, m2 = step(di)
-        res = torch.stack([m1["loss_d"], m1["loss_g"], m2["loss"]]).cpu()
+        res = torch.stack([m1["loss_d"], m1["loss_g"], m2["loss"]])
+        pinned_out[i % 2].copy_(res, non_blocking=True)
+        e = torch.cuda.Event()
+        e.record()
+        j = (i + 1) % 2
+        if out_ev[j] is not None:               # the previous step's losses have landed: read them on the host
+            out_ev[j].synchronize()
+            losses_seen.append(float(pinned_out[j][0]))
+        out_ev[i % 2] = e
         d2h[0] = res.numel() * res.element_size()
 
     e2e_step(0)
     ms_e2e = timed(e2e_step, args.steps) / args.steps
+    assert all(v == v for v in losses_seen), "NaN loss in the end-to-end run"
 
     # ---- per-kernel attribution with CUDA events around every launch (same steps, instrumented)
     kt = KernelTimer(torch, shapes=args.shapes)
@@ -244,8 +276,16 @@ def run_ours(args):
     top = max(fam.items(), key=lambda kv: kv[1][0])
     tname, (tms, tflops, tcount) = top
     achieved = (tflops / (tms * 1e-3)) / 1e12 if tms > 0 else 0.0
+    # DRAM bytes per launch of that family, from the committed ncu launch list of this same command
+    # (tools/ncu_summary.py traffic -> profiles/r1_bf16_traffic.json); null when the capture is missing
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_%s_traffic.json" % args.mode)) as f:
+            traffic = round(json.load(f)[tname.split(" ")[0]]["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"kernel": tname, "bound": "tensor", "achieved": round(achieved, 3), "peak": pk["tc"], "unit": "TFLOP/s",
-                "frac": round(achieved / pk["tc"], 5), "traffic": None, "avg_launch_ms": round(tms / tcount, 5),
+                "frac": round(achieved / pk["tc"], 5), "traffic": traffic, "avg_launch_ms": round(tms / tcount, 5),
                 "launches_per_step": tcount / args.steps, "share_of_kernel_time": round(tms / tot_kernel_ms, 4),
                 "peak_source": pk["src"] + " (bf16_tflops_sustained, of measured)"}
     families = {k: {"ms_per_step": round(v[0] / args.steps, 4), "tflops": round((v[1] / (v[0] * 1e-3)) / 1e12, 3) if v[0] > 0 else 0,
@@ -263,7 +303,8 @@ def run_ours(args):
                    "global_batch": world * B, "samples": L, "mode": args.mode, "parallelism": "dp%d" % world,
                    "l2_policy": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; two input batches alternate"},
         "e2e": {"value": round(audio_s / (ms_e2e * 1e-3), 2), "unit": "audio-s/s", "ms_per_step": round(ms_e2e, 4),
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h[0]},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h[0],
+                "pipeline": "inputs double-buffered on a copy stream, losses read back one step late"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

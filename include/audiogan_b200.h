@@ -266,6 +266,10 @@ int ag_conv1out_wgrad(const float* g, const void* X, int32_t x_dtype, int64_t x_
 int ag_copy3d(void* dst, int64_t d_bs, int64_t d_rs, int64_t d_cs, const void* src, int64_t s_bs, int64_t s_rs,
               int64_t s_cs, int64_t B, int64_t T, int64_t C, int32_t accumulate, int32_t src_dtype, int32_t dst_dtype,
               void* stream);
+/* Zero the pad rows [0, head) and [tail0, rows) of every batch of a packed channel-last buffer [B, rows, row_bytes] (the zero
+ * padding every conv view relies on, audiogan.py:272 / :490 `padding=`): one launch instead of two strided fills.
+ * row_bytes % 16 == 0, buf 16-byte aligned. */
+int ag_zero_pads(void* buf, int64_t B, int64_t rows, int64_t row_bytes, int64_t head, int64_t tail0, void* stream);
 /* out[b, n] = sum_t in[b, t, n] */
 int ag_rowgroup_sum(const float* in, float* out, int64_t B, int64_t T, int64_t N, void* stream);
 /* dst[b, t, c] (channel-last, row stride dst_rs, batch stride dst_bs) <-> src[b, c, t] */

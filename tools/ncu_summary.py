@@ -38,6 +38,49 @@ def launches(path, out):
     print(open(out).read())
 
 
+# C-ABI entry point (bench.py's kernel families) <- kernel names
+FAMILY = (("gemm_nt_tma_kernel", "ag_gemm_nt_tc"), ("gemm_nt_tc_kernel", "ag_gemm_nt_tc"), ("gemm_tn_tma_kernel", "ag_gemm_tn_tc"),
+          ("gemm_tn_tc_kernel", "ag_gemm_tn_tc"), ("tn_bias_kernel", "ag_gemm_tn_tc"), ("lstm_cl_fwd", "ag_lstm_fwd"), ("lstm_gen_fwd", "ag_lstm_fwd"),
+          ("lstm_fwd_kernel", "ag_lstm_fwd"), ("lstm_cl_bwd", "ag_lstm_bwd"), ("lstm_gen_bwd", "ag_lstm_bwd"), ("lstm_bwd_kernel", "ag_lstm_bwd"))
+
+
+def traffic(path, out):
+    """launch list with dram__bytes_read.sum / dram__bytes_write.sum beside gpu__time_duration.sum -> per kernel and per C-ABI
+    family: launches, time share, DRAM bytes per launch (what bench.py reports as roofline.traffic)."""
+    import json
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    per = collections.OrderedDict()          # launch id -> [name, ns, bytes]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", "")) * scale.get(row["Metric Unit"], 1.0)
+        e = per.setdefault(row["ID"], [re.sub(r"\(.*", "", row["Kernel Name"]), 0.0, 0.0])
+        if row["Metric Name"] == "gpu__time_duration.sum":
+            e[1] += v
+        elif row["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            e[2] += v
+    kern, fam = collections.OrderedDict(), collections.OrderedDict()
+    for name, ns, by in per.values():
+        k = kern.setdefault(name, [0, 0.0, 0.0])
+        k[0] += 1; k[1] += ns; k[2] += by
+        fn = next((f_ for pat, f_ in FAMILY if pat in name), None)
+        if fn:
+            q = fam.setdefault(fn, [0, 0.0, 0.0])
+            q[0] += 1; q[1] += ns; q[2] += by
+    tot = sum(k[1] for k in kern.values())
+    with open(out, "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none\n")
+        f.write("# (cold-cache, serialised: compare SHARES) source: %s ; total %.3f ms over %d launches\n" % (path, tot / 1e6, len(per)))
+        for k, (n, ns, by) in sorted(kern.items(), key=lambda kv: -kv[1][1]):
+            f.write("%-64s n=%5d %10.3f ms %6.2f%%  DRAM %9.2f MB/launch  %7.0f GB/s\n" % (k[:64], n, ns / 1e6, 100 * ns / tot, by / n / 1e6, by / ns))
+        f.write("# per C-ABI family\n")
+        for k, (n, ns, by) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
+            f.write("%-64s n=%5d %10.3f ms %6.2f%%  DRAM %9.2f MB/launch\n" % (k, n, ns / 1e6, 100 * ns / tot, by / n / 1e6))
+    with open(out.rsplit(".", 1)[0] + ".json", "w") as f:
+        json.dump({k: {"launches": n, "dram_bytes_per_launch": by / n, "ms": ns / 1e6} for k, (n, ns, by) in fam.items()}, f, indent=1)
+    print(open(out).read())
+
+
 def report(path, out):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -54,4 +97,4 @@ def report(path, out):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
