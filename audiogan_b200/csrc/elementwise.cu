@@ -332,6 +332,28 @@ __global__ void transpose_bct_kernel(const float* __restrict__ src, float* __res
   }
 }
 
+// frame assembly (audiogan.py:462-464) into channel 0 of a channel-last buffer whose first slot has `slot` channels: writes
+// (x, 0, ..., 0) per row in one pass (the pad channels of the slot must read as zeros for the conv GEMMs)
+__global__ void frames_to_slot_kernel(void* __restrict__ dst, int ddt, int64_t d_bs, int64_t d_rs, int slot,
+                                      const float* __restrict__ src, int64_t s_bs, int64_t B, int64_t L) {
+  const int64_t total = B * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / L, t = i - b * L;
+    const float v = __ldg(src + b * s_bs + t);
+    const int64_t o = b * d_bs + t * d_rs;
+    if (ddt == 1 && slot == 8) {
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst) + o) = make_uint4((uint32_t)__bfloat16_as_ushort(__float2bfloat16(v)), 0u, 0u, 0u);
+    } else if (ddt == 0 && slot == 8) {
+      float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + o);
+      q[0] = make_float4(v, 0.f, 0.f, 0.f);
+      q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      st_any(dst, o, v, ddt);
+      for (int c = 1; c < slot; ++c) st_any(dst, o + c, 0.f, ddt);
+    }
+  }
+}
+
 // zero rows [0, head) and [tail0, rows) of every batch of a packed [B, rows, row_bytes] buffer, 16 bytes per thread
 __global__ void zero_pads_kernel(uint4* __restrict__ p, int64_t B, int64_t rows, int64_t row16, int64_t head, int64_t tail0) {
   const int64_t per = (head + rows - tail0) * row16, total = B * per;
@@ -446,6 +468,15 @@ int ag_copy3d(void* dst, int64_t d_bs, int64_t d_rs, int64_t d_cs, const void* s
   AG_CHECK_ARG(dst && src && B > 0 && T > 0 && Cn > 0, "ag_copy3d: bad args");
   copy3d_kernel<<<grid_for(B * T * Cn, 256), 256, 0, (cudaStream_t)stream>>>(dst, d_bs, d_rs, d_cs, src, s_bs, s_rs, s_cs, B, T,
                                                                             Cn, accumulate, src_dtype, dst_dtype);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_frames_to_slot(void* dst, int32_t dst_dtype, int64_t d_bs, int64_t d_rs, int32_t slot, const float* src, int64_t s_bs, int64_t B,
+                      int64_t L, void* stream) {
+  AG_CHECK_ARG(dst && src && B > 0 && L > 0 && slot > 0, "ag_frames_to_slot: bad args");
+  if (slot == 8)
+    AG_CHECK_ARG((reinterpret_cast<uintptr_t>(dst) & (dst_dtype ? 15 : 31)) % 16 == 0 && d_bs % 8 == 0 && d_rs % 8 == 0, "ag_frames_to_slot: unaligned");
+  frames_to_slot_kernel<<<grid_for(B * L, 256), 256, 0, (cudaStream_t)stream>>>(dst, dst_dtype, d_bs, d_rs, slot, src, s_bs, B, L);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

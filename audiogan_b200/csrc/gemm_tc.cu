@@ -1325,31 +1325,41 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
 }
 
 // dw[n*ldw] += sum_m Y(m, n): the bias gradient beside the TMA-fed weight-gradient kernel.  Thread = 8 columns (16 bytes of
-// bf16), block = 32 column groups x 8 row lanes; grid.y splits the rows.
+// bf16); a block covers NCG column groups x 256/NCG row lanes (NCG = power of two >= N/8, at most 32: narrow Y matrices -- the
+// generator's 32..128 hidden channels -- keep all 256 threads loading); grid.y splits the rows.
 __global__ void __launch_bounds__(256) tn_bias_kernel(const __nv_bfloat16* __restrict__ Y, int64_t rpb, int64_t bs, int64_t rs, int64_t M,
-                                                      int N, float* __restrict__ out, int64_t ldw, int64_t rows_per) {
-  __shared__ float red[8][32][9];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int n = (blockIdx.x * 32 + cx) * 8;
+                                                      int N, float* __restrict__ out, int64_t ldw, int64_t rows_per, int ncg_log2) {
+  __shared__ float red[256][9];
+  const int ncg = 1 << ncg_log2, nrl = 256 >> ncg_log2;
+  const int cx = threadIdx.x & (ncg - 1), ry = threadIdx.x >> ncg_log2;
+  const int n = (blockIdx.x * ncg + cx) * 8;
   const int64_t m0 = (int64_t)blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (n < N)
-    for (int64_t m = m0 + ry; m < m1; m += 8) {
-      const int64_t b = m / rpb;
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(Y + b * bs + (m - b * rpb) * rs + n));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  if (n < N) {
+    const uint32_t rpb32 = (uint32_t)rpb;
+    for (int64_t m = m0 + ry; m < m1; m += 2 * nrl) {           // two rows in flight per thread
+      const uint32_t b0 = (uint32_t)m / rpb32;
+      const int64_t m2 = m + nrl;
+      const uint32_t b1 = (uint32_t)m2 / rpb32;
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(Y + b0 * bs + (m - (int64_t)b0 * rpb) * rs + n));
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (m2 < m1) v = __ldg(reinterpret_cast<const uint4*>(Y + b1 * bs + (m2 - (int64_t)b1 * rpb) * rs + n));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w}, x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { acc[2 * e] += __uint_as_float(w[e] << 16); acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u); }
+      for (int e = 0; e < 4; ++e) {
+        acc[2 * e] += __uint_as_float(w[e] << 16) + __uint_as_float(x[e] << 16);
+        acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u) + __uint_as_float(x[e] & 0xffff0000u);
+      }
     }
+  }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) red[ry][cx][e] = acc[e];
+  for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = acc[e];
   __syncthreads();
   if (ry == 0 && n < N) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float v = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v += red[i][cx][e];
+      for (int i = 0; i < nrl; ++i) v += red[i * ncg + cx][e];
       atomicAdd(&out[(int64_t)(n + e) * ldw], v);
     }
   }
@@ -1448,14 +1458,16 @@ static int launch_tn_tma(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones
                                                                                 (int)total, (int)sps, (int)pg.KT);
   AG_LAUNCH_CHECK();
   if (ones_col) {
-    const int64_t bx = (d->N / 8 + 31) / 32;
+    int lg = 0;
+    while ((1 << lg) < d->N / 8 && lg < 5) ++lg;
+    const int64_t bx = (d->N / 8 + (1 << lg) - 1) >> lg;
     int64_t by = (int64_t)sm_count() * 8 / bx;
     if (by < 1) by = 1;
     int64_t rows_per = (d->M + by - 1) / by;
-    if (rows_per < 64) rows_per = 64;
+    if (rows_per < 512) rows_per = 512;
     by = (d->M + rows_per - 1) / rows_per;
     tn_bias_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d->C), d->c_rpb, d->c_bs, d->c_rs,
-                                                                    d->M, (int)d->N, dw + Kd, ldw, rows_per);
+                                                                    d->M, (int)d->N, dw + Kd, ldw, rows_per, lg);
     AG_LAUNCH_CHECK();
   }
   return AG_OK;

@@ -90,8 +90,8 @@ class _GenFn(torch.autograd.Function):
         adt = _adt(plan)
         Xd = _empty(B, Lp, CT, device=dev, dtype=adt)       # CT = padded channel count (slots of 8, plan.py)
         K.zero_pads(Xd, GPAD, GPAD + L)
-        Xd[:, GPAD:GPAD + L, 1:plan.coff[0]].zero_()        # pad channels of the waveform slot
-        K.copy3d((Xd, GPAD * CT), (Lp * CT, CT, 0), (xbuf, F), ((Tcap + 1) * F, 1, 0), B, L, 1)
+        # frames -> channel 0 of the waveform slot, its pad channels zeroed in the same pass
+        K.frames_to_slot((Xd, GPAD * CT), Lp * CT, CT, plan.coff[0], (xbuf, F), (Tcap + 1) * F, B, L)
         hh = []
         lenL = plan.const_len(B, L)
         for li, (k, s, hid, out) in enumerate(struct):                       # audiogan.py:278-283, :465-467

@@ -183,6 +183,10 @@ def conv1out_wgrad(g, X, x_bs, Cn, k, dw, B, T):
     A.call("ag_conv1out_wgrad", addr(g), addr(X), _dtype_of(X), x_bs, Cn, k, addr(dw), B, T, A.stream())
 
 
+def frames_to_slot(dst, d_bs, d_rs, slot, src, s_bs, B, L):
+    A.call("ag_frames_to_slot", addr(dst), _dtype_of(dst), d_bs, d_rs, slot, addr(src), s_bs, B, L, A.stream())
+
+
 def zero_pads(buf, head, tail0):
     """zero rows [0, head) and [tail0, rows) of every batch of a contiguous [B, rows, C] tensor."""
     Bn, rows = buf.shape[0], buf.shape[1]

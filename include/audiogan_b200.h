@@ -266,6 +266,10 @@ int ag_conv1out_wgrad(const float* g, const void* X, int32_t x_dtype, int64_t x_
 int ag_copy3d(void* dst, int64_t d_bs, int64_t d_rs, int64_t d_cs, const void* src, int64_t s_bs, int64_t s_rs,
               int64_t s_cs, int64_t B, int64_t T, int64_t C, int32_t accumulate, int32_t src_dtype, int32_t dst_dtype,
               void* stream);
+/* Frame assembly (audiogan.py:462-464) into the first channel slot of the generator's dense channel-last buffer:
+ * dst[b*d_bs + t*d_rs + 0] = src[b*s_bs + t], dst[.. + 1 .. slot-1] = 0 for t < L (dst dtype 0 fp32 / 1 bf16). */
+int ag_frames_to_slot(void* dst, int32_t dst_dtype, int64_t d_bs, int64_t d_rs, int32_t slot, const float* src, int64_t s_bs, int64_t B,
+                      int64_t L, void* stream);
 /* Zero the pad rows [0, head) and [tail0, rows) of every batch of a packed channel-last buffer [B, rows, row_bytes] (the zero
  * padding every conv view relies on, audiogan.py:272 / :490 `padding=`): one launch instead of two strided fills.
  * row_bytes % 16 == 0, buf 16-byte aligned. */
