@@ -724,7 +724,7 @@ gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap map
           if (epi_sel >= 0) {
             switch (epi_sel) {       // bf16 output (+ bf16 operands): the feature sets the training step uses, specialised
               AG_EPI(0) AG_EPI(EPI_ACT) AG_EPI(EPI_SKIP | EPI_ACT) AG_EPI(EPI_SKIP | EPI_MASK | EPI_ACT) AG_EPI(EPI_MASK | EPI_ACT)
-              AG_EPI(EPI_DACT) AG_EPI(EPI_SKIP) AG_EPI(EPI_MASK) AG_EPI(EPI_SKIP | EPI_DACT)
+              AG_EPI(EPI_DACT) AG_EPI(EPI_SKIP) AG_EPI(EPI_MASK) AG_EPI(EPI_SKIP | EPI_DACT) AG_EPI(EPI_DACT | EPI_MASK)
               default: epi_chunk_vec<true, true, CH, -1>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
             }
           } else if (d.c_dtype) {

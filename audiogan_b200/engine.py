@@ -264,6 +264,7 @@ class _DiscCNNFn(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[3]
         chans = [1] + [c for (_, _, c) in struct]
         dX = None                   # internal gradient wrt acts[i+1], padded geometry
+        fused_dy = False            # dX already is dy of the layer below (LeakyReLU' and mask applied by the GEMM above)
         for i in range(len(struct) - 1, -1, -1):
             k, s, cout = struct[i]
             cin, Tin, Tout = chans[i], Ts[i], Ts[i + 1]
@@ -276,13 +277,19 @@ class _DiscCNNFn(torch.autograd.Function):
             geo = ((Tout + 2 * DPAD) * cout, cout)         # geometry of the forward activation buffers
             gdy = ((PL + Tout + DPAD) * cout, cout)        # geometry of dy
             adt = a_out.dtype
-            dy = _empty(B, PL + Tout + DPAD, cout, device=dev, dtype=adt)
-            kw = {}
-            if g is not None:                  # (B, C, T) tensor with arbitrary strides
-                kw.update(g1=g, g1_str=(g.stride(0), g.stride(2), g.stride(1)))
-            if dX is not None:
-                kw.update(g2=(dX, DPAD * cout), g2_str=(geo[0], geo[1], 1))
-            K.ew_grad(B, Tout, cout, out=dy, pad=(PL, DPAD), act=(a_out, DPAD * cout), act_str=geo, length=lens[i], **kw)
+            if g is None and fused_dy:
+                # the data-gradient GEMM of the layer above already applied LeakyReLU'(a_out) and this layer's length mask in
+                # its epilogue and wrote into the dy geometry (PL == DPAD): no activation-gradient pass
+                dy = dX
+            else:
+                dy = _empty(B, PL + Tout + DPAD, cout, device=dev, dtype=adt)
+                kw = {}
+                if g is not None:                  # (B, C, T) tensor with arbitrary strides
+                    kw.update(g1=g, g1_str=(g.stride(0), g.stride(2), g.stride(1)))
+                if dX is not None:
+                    kw.update(g2=(dX, DPAD * cout), g2_str=(geo[0], geo[1], 1))
+                K.ew_grad(B, Tout, cout, out=dy, pad=(PL, DPAD), act=(a_out, DPAD * cout), act_str=geo, length=lens[i], **kw)
+            fused_dy = False
             a_view = (Tout, (Tin + 2 * DPAD) * cin, s * cin)
             if wgrad and cin == 1 and k <= 8 and cout % 4 == 0 and (k - 1) // 2 == DPAD:
                 K.conv1in_wgrad((dy, PL * cout), gdy[0], acts[i], Tin + 2 * DPAD, plan.GPoff("c%d.w" % i), k, s, cout, B, Tout)
@@ -299,9 +306,18 @@ class _DiscCNNFn(torch.autograd.Function):
                 dXn = _empty(B, Tin + 2 * DPAD, cin, device=dev, dtype=adt if i > 0 else torch.float32)
                 if s * Mp < Tin + 2 * DPAD:
                     dXn[:, s * Mp:].zero_()
-                K.gemm_nt(B * Mp, s * cin, ntap * cout, dy, (Mp, gdy[0], cout), plan.Poff("c%d.wg" % i), ntap * cout,
-                          dXn, (Mp, (Tin + 2 * DPAD) * cin, s * cin, cin, cin),
-                          mask_len=plan.const_len(B, Tin), mask=(s, 1, -DPAD))
+                # When nothing else flows into the activation below (no external gradient for cnn_outputs[i-1]) and its dy buffer
+                # has this geometry, fold its LeakyReLU' and length mask into this epilogue.
+                fuse = (i > 0 and gouts[i - 1] is None and plan.d_ntap[i - 1] - 1 == DPAD and adt == torch.bfloat16)
+                if fuse:
+                    K.gemm_nt(B * Mp, s * cin, ntap * cout, dy, (Mp, gdy[0], cout), plan.Poff("c%d.wg" % i), ntap * cout,
+                              dXn, (Mp, (Tin + 2 * DPAD) * cin, s * cin, cin, cin), dact=acts[i],
+                              mask_len=lens[i - 1], mask=(s, 1, -DPAD))
+                else:
+                    K.gemm_nt(B * Mp, s * cin, ntap * cout, dy, (Mp, gdy[0], cout), plan.Poff("c%d.wg" % i), ntap * cout,
+                              dXn, (Mp, (Tin + 2 * DPAD) * cin, s * cin, cin, cin),
+                              mask_len=plan.const_len(B, Tin), mask=(s, 1, -DPAD))
+                fused_dy = fuse
                 dX = dXn
             else:
                 dX = None
