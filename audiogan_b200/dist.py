@@ -54,13 +54,42 @@ class GradSync:
         self.nbuckets, self.group = nbuckets, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bytes_last = 0
+        self._pending = {}           # id(plan) -> ([async works], [(a, b) spans already being reduced])
+
+    # -- overlap with backward: the engine reports finished weight-gradient regions of plan.gpflat (NetPlan.reduce_span),
+    #    each becomes one asynchronous all-reduce bucket that runs while the rest of backward executes -------------------
+    def attach(self, *modules):
+        """Let these Generator / Discriminator modules reduce their packed weight gradients during backward."""
+        for m in modules:
+            m._get_plan().early_sync = self
+        return self
+
+    def reduce_async(self, plan, a, b):
+        works, spans = self._pending.setdefault(id(plan), ([], []))
+        works.append(dist.all_reduce(plan.gpflat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        spans.append((a, b))
+
+    def finish(self, plan):
+        """Reduce whatever part of plan.gpflat has not been started yet, then make the current stream wait for all buckets."""
+        works, spans = self._pending.pop(id(plan), ([], []))
+        pos, n = 0, plan.gpflat.numel()
+        for a, b in sorted(spans) + [(n, n)]:
+            if a > pos:
+                for c in plan.gpflat[pos:a].chunk(max(1, min(self.nbuckets, (a - pos) >> 20))):
+                    works.append(dist.all_reduce(c, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            pos = max(pos, b)
+        self.bytes_last = n * plan.gpflat.element_size()
+        for w in works:
+            w.wait()
 
     def __call__(self, params):
         if self.world == 1:
             return 1.0
-        grads = [p.grad for p in params if p.grad is not None]
+        # gradients that are views of a buffer whose packed form was reduced during backward are already global sums
+        grads = [p.grad for p in params
+                 if p.grad is not None and not getattr(getattr(p.grad, "_base", None), "_ag_reduced", False)]
         if not grads:
-            return 1.0
+            return 1.0 / self.world
         flat = _flat_base(grads)
         copied = flat is None
         if copied:

@@ -185,6 +185,8 @@ class _GenFn(torch.autograd.Function):
         if gs is not None:
             ds_ext = _zeros(B, Tcap, device=dev)
             ds_ext[:, :T] = gs
+        if wgrad and gx is not None:
+            plan.reduce_span("c0.wq", "f.w")          # data-parallel: the conv stack's gradients travel under the BPTT
         # ---- BPTT through the recurrence (audiogan.py:437-444)
         dgates = _empty(B, Tcap, 4 * H, device=dev)
         dpx = _empty(B, Tcap, FP, device=dev)
@@ -408,6 +410,8 @@ class _DiscTailFn(torch.autograd.Function):
         K.gemm_nt(M, S, S, (dz2, S), geo, plan.Poff("r1.wt"), S, (dz1, S), geo, skip=(dz2, S), dact=(r1, S))
         if wgrad:
             K.gemm_tn(M, S, S, (dz1, S), geo, (hin, S), geo, plan.GPoff("r0.w"), S + 1, ones_col=True)
+        if wgrad:
+            plan.reduce_span("r0.w", "k2.w")          # data-parallel: these gradients are final, reduce them under the BPTT
         dh_ext = _empty(B, Tm + 2, S, device=dev)
         K.gemm_nt(M, S, S, (dz1, S), geo, plan.Poff("r0.wt"), S, (dh_ext, S), geo, skip=(dz1, S))
         # BPTT through both directions
@@ -429,6 +433,7 @@ class _DiscTailFn(torch.autograd.Function):
                           plan.GPoff("whh", d * 4 * H * H), H)
             K.gemm_tn(M, 8 * H, Cf, dgo, flat(8 * H), feat, (Tm, feat.stride(0), feat.stride(2)), plan.GPoff("wih"), ldi)
             K.gemm_tn(B, 8 * H, E + 2, dgsum, (B, 0, 8 * H), c1, (B, 0, E + 2), plan.GPoff("wih", Cf), ldi)
+            plan.reduce_span("wih", "whh")            # ... and the recurrent weights' under the conv stack's backward
         dfeat = None
         if ctx.needs_input_grad[2]:
             dfeat = _zeros(B, T6, Cf, device=dev, dtype=feat.dtype) if Tm < T6 else _empty(B, T6, Cf, device=dev, dtype=feat.dtype)

@@ -93,6 +93,8 @@ class NetPlan:
         self.lstm_prec = 2 if os.environ.get("AUDIOGAN_LSTM", "") == "tcgen05" else 1
         # AUDIOGAN_LSTM=grid keeps the grid-barrier kernels (no cluster / TMEM-resident variants): A/B timing aid
         self.lstm_flags = 1 if os.environ.get("AUDIOGAN_LSTM", "") == "grid" else 0
+        # data-parallel: a dist.GradSync that all-reduces packed weight-gradient regions while backward is still running
+        self.early_sync = None
 
     # -- declaration ----------------------------------------------------------------------
     def weight(self, name, v, g=None):
@@ -219,12 +221,29 @@ class NetPlan:
         if self.mode == "bf16":
             K.gather(self.pflat16, self.wflat, self.idx_pack16)
 
+    def reduce_span(self, first, last):
+        """The weight-gradient regions first..last (contiguous in gpflat) are complete: start their all-reduce now, on NCCL's
+        stream, so it overlaps the rest of backward.  Un-packing and weight-norm backward are linear in the packed gradients,
+        so reducing before them gives the same sums as reducing p.grad afterwards."""
+        es = self.early_sync
+        if es is None or es.world == 1:
+            return
+        n = 1
+        for d in self.gpack.shape[last]:
+            n *= d
+        es.reduce_async(self, self.gpack.off[first], self.gpack.off[last] + n)
+
     def pack_backward(self):
         """Consume gpflat -> fresh flat gradient buffer in parameter order (views per parameter)."""
+        reduced = False
+        if self.early_sync is not None and self.early_sync.world > 1:
+            self.early_sync.finish(self)                 # the remaining regions, then wait for every bucket
+            reduced = True
         K.gather(self.dwflat, self.gpflat, self.idx_unpack)
         self.gpflat.zero_()
         K.wn_bwd(self.wn_tab, self.wn_rows, self.wn_n, self.wn_total)
         out = self.gwork.clone()
+        out._ag_reduced = reduced                        # dist.GradSync skips gradients that are views of a reduced buffer
         return [out[self.poff[id(p)]:self.poff[id(p)] + p.numel()].view(p.shape) for p in self.params]
 
 

@@ -55,6 +55,24 @@ def _worker(rank, world, port, q):
     scale = sync(ps)
     for i, p in enumerate(ps):
         assert T.equal(p.grad, T.full_like(p, float(3 + 2 * i)))
+    # overlap path: spans of a plan's packed gradient buffer reduced early (asynchronously), finish() reduces the rest once
+    class _Plan:
+        pass
+    fp = _Plan()
+    n = 2_500_000
+    fp.gpflat = T.arange(n, dtype=T.float32) % 1000 * (rank + 1)
+    sync2 = agd.GradSync(nbuckets=4)
+    sync2.reduce_async(fp, 1_000_000, 1_500_000)
+    sync2.reduce_async(fp, 100, 2000)
+    sync2.finish(fp)
+    assert T.equal(fp.gpflat, T.arange(n, dtype=T.float32) % 1000 * 3) and sync2.bytes_last == 4 * n
+    sync2.finish(fp)                                                     # nothing started early: the whole buffer, in buckets
+    assert T.equal(fp.gpflat, T.arange(n, dtype=T.float32) % 1000 * 6)
+    # gradients that are views of a buffer already reduced in packed form are skipped (still scaled by 1/world)
+    red = T.ones(18)
+    red._ag_reduced = True
+    ps[0].grad, ps[1].grad = red[:15].view(3, 5), red[15:18].view(3)
+    assert sync(ps) == 0.5 and T.equal(red, T.ones(18))
     # mean-of-means == global mean with equal shards
     x = T.arange(8, dtype=T.float32)
     local_mean = x[off:off + per].mean().reshape(1)
