@@ -55,6 +55,7 @@ class GradSync:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bytes_last = 0
         self._pending = {}           # id(plan) -> ([async works], [(a, b) spans already being reduced])
+        self._done = set()           # id(param) whose gradient came out of a packed buffer that was reduced during backward
 
     # -- overlap with backward: the engine reports finished weight-gradient regions of plan.gpflat (NetPlan.reduce_span),
     #    each becomes one asynchronous all-reduce bucket that runs while the rest of backward executes -------------------
@@ -81,13 +82,15 @@ class GradSync:
         self.bytes_last = n * plan.gpflat.element_size()
         for w in works:
             w.wait()
+        self._done.update(id(p) for p in getattr(plan, "params", ()))
 
     def __call__(self, params):
         if self.world == 1:
             return 1.0
-        # gradients that are views of a buffer whose packed form was reduced during backward are already global sums
-        grads = [p.grad for p in params
-                 if p.grad is not None and not getattr(getattr(p.grad, "_base", None), "_ag_reduced", False)]
+        # gradients whose packed form was reduced during backward (finish) are already global sums
+        params = list(params)
+        grads = [p.grad for p in params if p.grad is not None and id(p) not in self._done]
+        self._done.difference_update(id(p) for p in params)
         if not grads:
             return 1.0 / self.world
         flat = _flat_base(grads)

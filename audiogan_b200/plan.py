@@ -235,15 +235,13 @@ class NetPlan:
 
     def pack_backward(self):
         """Consume gpflat -> fresh flat gradient buffer in parameter order (views per parameter)."""
-        reduced = False
         if self.early_sync is not None and self.early_sync.world > 1:
-            self.early_sync.finish(self)                 # the remaining regions, then wait for every bucket
-            reduced = True
+            self.early_sync.finish(self)                 # the remaining regions, then wait for every bucket; GradSync then
+                                                         # skips these parameters (their gradients are already global sums)
         K.gather(self.dwflat, self.gpflat, self.idx_unpack)
         self.gpflat.zero_()
         K.wn_bwd(self.wn_tab, self.wn_rows, self.wn_n, self.wn_total)
         out = self.gwork.clone()
-        out._ag_reduced = reduced                        # dist.GradSync skips gradients that are views of a reduced buffer
         return [out[self.poff[id(p)]:self.poff[id(p)] + p.numel()].view(p.shape) for p in self.params]
 
 

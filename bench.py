@@ -167,7 +167,11 @@ def run_ours(args):
     agd.broadcast_parameters([g, d])
     opt_d = ag.FusedRMSprop(d.parameters(), lr=1e-4)
     opt_g = ag.FusedRMSprop(g.parameters(), lr=1e-4)
-    sync = agd.GradSync(nbuckets=4).attach(g, d) if world > 1 else None
+    sync = agd.GradSync(nbuckets=4) if world > 1 else None
+    # AUDIOGAN_DP_EARLY=1: packed gradient regions are all-reduced while backward is still running.  Off by default: measured
+    # 0.4 ms/step SLOWER at 2 GPUs (15.65-15.72 vs 15.26-15.31 ms) -- the NCCL CTAs take SMs the recurrent kernels' clusters need
+    if sync is not None and os.environ.get("AUDIOGAN_DP_EARLY", "0") == "1":
+        sync.attach(g, d)
 
     host = make_batches(torch, B, L, rank, 2, pinned=True)
     # the per-sample lengths are host metadata (the reference carries them as numpy arrays and reads them on the host inside

@@ -68,11 +68,12 @@ def _worker(rank, world, port, q):
     assert T.equal(fp.gpflat, T.arange(n, dtype=T.float32) % 1000 * 3) and sync2.bytes_last == 4 * n
     sync2.finish(fp)                                                     # nothing started early: the whole buffer, in buckets
     assert T.equal(fp.gpflat, T.arange(n, dtype=T.float32) % 1000 * 6)
-    # gradients that are views of a buffer already reduced in packed form are skipped (still scaled by 1/world)
-    red = T.ones(18)
-    red._ag_reduced = True
-    ps[0].grad, ps[1].grad = red[:15].view(3, 5), red[15:18].view(3)
-    assert sync(ps) == 0.5 and T.equal(red, T.ones(18))
+    # parameters of a plan whose packed gradients were reduced during backward are skipped once (still scaled by 1/world)
+    fp.params = ps
+    sync2.finish(fp)
+    ps[0].grad, ps[1].grad = T.ones(3, 5), T.ones(3)
+    assert sync2(ps) == 0.5 and T.equal(ps[0].grad, T.ones(3, 5))
+    assert sync2(ps) == 0.5 and T.equal(ps[0].grad, T.full((3, 5), 2.0))      # the next call reduces again
     # mean-of-means == global mean with equal shards
     x = T.arange(8, dtype=T.float32)
     local_mean = x[off:off + per].mean().reshape(1)
