@@ -45,10 +45,11 @@ __global__ void __launch_bounds__(256) conv1out_fwd_kernel(const void* __restric
 }
 
 // Streaming version for C <= 128 (the dense buffer has 120 channels): a warp walks a strip of rows, lane = 4 channels, so
-// every buffer row is loaded ONCE (one coalesced 8/16-byte load per lane, 4 rows in flight), its k tap-partials are
-// reduced over the warp and folded into a rolling window of k outputs; 32 outputs leave as one coalesced store.
-template <int XDT, int KMAX>
-__global__ void __launch_bounds__(256) conv1out_fwd_strip_kernel(const void* __restrict__ X, int64_t x_bs, int C, int k,
+// every buffer row is loaded ONCE (one coalesced 8/16-byte load per lane, 4 rows in flight).  The tap partials of a row are
+// folded -- per lane, before any reduction (the window sum is linear) -- into a rolling window of output partials; each batch
+// of 4 rows completes 4 outputs, which are reduced over the warp with a halving butterfly: 6 shuffles per 4 rows.
+template <int XDT, int KK>
+__global__ void __launch_bounds__(256) conv1out_fwd_strip_kernel(const void* __restrict__ X, int64_t x_bs, int C,
                                                                  const float* __restrict__ w, const float* __restrict__ bias,
                                                                  float* __restrict__ out, int64_t B, int64_t T, int spb, int S) {
   const int lane = threadIdx.x & 31;
@@ -57,49 +58,42 @@ __global__ void __launch_bounds__(256) conv1out_fwd_strip_kernel(const void* __r
   const int64_t b = strip / spb;
   const int64_t t0 = (strip - b * spb) * S, t1 = min(T, t0 + S);
   const bool active = 4 * lane < C;
-  float4 wv[KMAX];
+  float4 wv[KK];
 #pragma unroll
-  for (int j = 0; j < KMAX; ++j)
-    wv[j] = (active && j < k) ? *reinterpret_cast<const float4*>(w + j * C + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < KK; ++j)
+    wv[j] = active ? *reinterpret_cast<const float4*>(w + j * C + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float bv = bias ? bias[0] : 0.f;
-  float acc[KMAX];
+  float carry[KK - 1];
 #pragma unroll
-  for (int j = 0; j < KMAX; ++j) acc[j] = 0.f;
-  float keepv = 0.f;
+  for (int j = 0; j < KK - 1; ++j) carry[j] = 0.f;
   const int64_t xb = b * x_bs + 4 * lane;
-  const int64_t rend = t1 + k - 1;                  // input rows [t0, rend)
+  const int64_t rend = t1 + KK - 1;                 // input rows [t0, rend)
+  const bool hi = (lane & 16) != 0, hi2 = (lane & 8) != 0;
+  const int idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
   for (int64_t r0 = t0; r0 < rend; r0 += 4) {
     float4 x[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       x[i] = (active && r0 + i < rend) ? ldg4_any(X, xb + (r0 + i) * C, XDT) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float o[4 + KK - 1];                              // o[m]: this lane's partial of output r0 - (KK-1) + m
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t r = r0 + i;
-      if (r >= rend) break;
-      float pj[KMAX];
+    for (int m = 0; m < 4 + KK - 1; ++m) o[m] = m < KK - 1 ? carry[m] : 0.f;
 #pragma unroll
-      for (int j = 0; j < KMAX; ++j) pj[j] = x[i].x * wv[j].x + x[i].y * wv[j].y + x[i].z * wv[j].z + x[i].w * wv[j].w;
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
+      for (int j = 0; j < KK; ++j)                     // row r0 + i is tap j of output r0 + i - j
+        o[i - j + KK - 1] += x[i].x * wv[j].x + x[i].y * wv[j].y + x[i].z * wv[j].z + x[i].w * wv[j].w;
 #pragma unroll
-        for (int j = 0; j < KMAX; ++j) pj[j] += __shfl_xor_sync(0xffffffffu, pj[j], o);
-      // row r is tap j of output r - j: shift the window, the oldest entry (output r - (k-1)) is complete
-#pragma unroll
-      for (int j = KMAX - 1; j > 0; --j) acc[j] = acc[j - 1] + pj[j];
-      acc[0] = pj[0];
-      const int64_t t = r - (k - 1);
-      if (t >= t0) {
-        float done = acc[0];
-#pragma unroll
-        for (int j = 1; j < KMAX; ++j) done = (j == k - 1) ? acc[j] : done;
-        const int slot = (int)(t - t0) & 31;
-        if (lane == slot) keepv = done + bv;
-        if (slot == 31 || t == t1 - 1) {
-          if (lane <= slot) out[b * T + (t - slot) + lane] = keepv;
-        }
-      }
-    }
+    for (int j = 0; j < KK - 1; ++j) carry[j] = o[4 + j];
+    // outputs o[0..3] are complete: halving butterfly (lanes < 16 keep 0,1; then bit 3 picks one), then 3 plain steps
+    const float s0 = __shfl_xor_sync(0xffffffffu, hi ? o[0] : o[2], 16), s1 = __shfl_xor_sync(0xffffffffu, hi ? o[1] : o[3], 16);
+    const float k0 = (hi ? o[2] : o[0]) + s0, k1 = (hi ? o[3] : o[1]) + s1;
+    float v = (hi2 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, hi2 ? k0 : k1, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    const int64_t t = r0 - (KK - 1) + idx;
+    if ((lane & 7) == 0 && t >= t0 && t < t1) out[b * T + t] = v + bv;
   }
 }
 
@@ -362,12 +356,12 @@ int ag_conv1out_fwd(const void* X, int32_t x_dtype, int64_t x_bs, int64_t C, int
   AG_CHECK_ARG(X && w && out && B > 0 && T > 0 && C > 0 && C % 4 == 0 && k > 0 && x_bs % 4 == 0, "ag_conv1out_fwd: bad args");
   AG_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
                    (!x_dtype || (C % 8 == 0 && x_bs % 8 == 0)), "ag_conv1out_fwd: unaligned");
-  if (C <= 128 && k <= 4) {
+  if (C <= 128 && k == 3) {
     const int S = 128;
     const int64_t spb = (T + S - 1) / S, strips = B * spb;
     const unsigned g = (unsigned)((strips + 7) / 8);
-    if (x_dtype) conv1out_fwd_strip_kernel<1, 4><<<g, 256, 0, (cudaStream_t)stream>>>(X, x_bs, (int)C, k, w, bias, out, B, T, (int)spb, S);
-    else conv1out_fwd_strip_kernel<0, 4><<<g, 256, 0, (cudaStream_t)stream>>>(X, x_bs, (int)C, k, w, bias, out, B, T, (int)spb, S);
+    if (x_dtype) conv1out_fwd_strip_kernel<1, 3><<<g, 256, 0, (cudaStream_t)stream>>>(X, x_bs, (int)C, w, bias, out, B, T, (int)spb, S);
+    else conv1out_fwd_strip_kernel<0, 3><<<g, 256, 0, (cudaStream_t)stream>>>(X, x_bs, (int)C, w, bias, out, B, T, (int)spb, S);
     AG_LAUNCH_CHECK();
     return AG_OK;
   }
