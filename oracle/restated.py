@@ -85,7 +85,7 @@ def generator_forward(P, c, z=None, batch_size=None, length=None, frame_size=200
     """
     if z is None:
         nframes = div_roundup(length, frame_size)
-        z = T.randn(batch_size, nframes, noise_size)
+        z = T.randn(batch_size, nframes, noise_size, device=c.device)
     else:
         batch_size, nframes, _ = z.shape
     pre = "rnn.0.module."
@@ -95,11 +95,12 @@ def generator_forward(P, c, z=None, batch_size=None, length=None, frame_size=200
     w_s, b_s = wn(P, "stopper.module.weight"), wn(P, "stopper.module.bias")
     H = w_hh.shape[1]
     zc = T.cat([z, c.unsqueeze(1).expand(batch_size, nframes, c.shape[1])], 2)   # :425-426
-    h = T.zeros(batch_size, H)
-    cc = T.zeros(batch_size, H)
-    x_t = T.zeros(batch_size, frame_size)
-    generating = T.ones(batch_size, dtype=T.long)
-    nlen = T.zeros(batch_size, dtype=T.long)
+    dev = c.device                  # CPU in every parity use; tests/test_stock_torch_gpu.py times the same code on the GPU
+    h = T.zeros(batch_size, H, device=dev)
+    cc = T.zeros(batch_size, H, device=dev)
+    x_t = T.zeros(batch_size, frame_size, device=dev)
+    generating = T.ones(batch_size, dtype=T.long, device=dev)
+    nlen = T.zeros(batch_size, dtype=T.long, device=dev)
     xs, ss, stops = [], [], []
     for t in range(nframes):                                                    # :437
         inp = T.cat([x_t, zc[:, t]], 1)                                         # :439
@@ -363,7 +364,7 @@ def g_update(Pg, Pd, st_g, batch, lr=1e-4, clip=0.1, g_optim="boundary_seeking",
     fake, fake_s, fake_stop, fake_len = generator_forward(Pg, batch["c_g"], z=z, u_stop=u_stop)   # :841
     fake = fake + batch["noise_fake"]                                            # :842-843
     cls_g, hs_g, hl_g, nframes_g = discriminator_forward(Pd, fake, fake_len, batch["c_d"])       # :845
-    fp = T.zeros(())
+    fp = T.zeros((), device=cls_g.device)
     if feature_matching:                                                         # :847-855
         real = batch["real"] + batch["noise_real"]
         _, hs_d, hl_d, _ = discriminator_forward(Pd, real, batch["real_len"], batch["c_d"])
