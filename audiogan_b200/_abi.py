@@ -110,7 +110,7 @@ _PROTOS = {
     "ag_copy3d": [vp, i64, i64, i64, vp, i64, i64, i64, i64, i64, i64, i32, i32, i32, vp],
     "ag_zero_pads": [vp, i64, i64, i64, i64, i64, vp],
     "ag_frames_to_slot": [vp, i32, i64, i64, i32, vp, i64, i64, i64, vp],
-    "ag_rowgroup_sum": [vp, vp, i64, i64, i64, vp],
+    "ag_rowgroup_sum": [vp, i32, vp, i64, i64, i64, vp],
     "ag_transpose_bct": [vp, vp, i64, i64, i64, i64, i64, i32, vp],
     "ag_mt_sqnorm": [vp, vp, vp, i32, i32, vp, vp, vp],
     "ag_mt_clip": [vp, vp, vp, i32, i32, vp, f32, vp],

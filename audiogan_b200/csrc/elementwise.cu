@@ -299,6 +299,24 @@ __global__ void rowgroup_sum_kernel(const float* __restrict__ in, float* __restr
   for (int64_t t = 0; t < T; ++t) acc += p[t * N];
   out[b * N + n] = acc;
 }
+// bf16 input: two columns per thread (32-bit loads), four rows in flight
+__global__ void rowgroup_sum_bf16_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int64_t T, int64_t N) {
+  const int64_t b = blockIdx.y;
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (n >= N) return;
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(in + b * T * N + n);
+  const int64_t st = N / 2;
+  float a0 = 0.f, a1 = 0.f;
+  int64_t t = 0;
+  for (; t + 4 <= T; t += 4) {
+    const uint32_t u0 = __ldg(p + t * st), u1 = __ldg(p + (t + 1) * st), u2 = __ldg(p + (t + 2) * st), u3 = __ldg(p + (t + 3) * st);
+    a0 += (__uint_as_float(u0 << 16) + __uint_as_float(u1 << 16)) + (__uint_as_float(u2 << 16) + __uint_as_float(u3 << 16));
+    a1 += (__uint_as_float(u0 & 0xffff0000u) + __uint_as_float(u1 & 0xffff0000u)) + (__uint_as_float(u2 & 0xffff0000u) + __uint_as_float(u3 & 0xffff0000u));
+  }
+  for (; t < T; ++t) { const uint32_t u = __ldg(p + t * st); a0 += __uint_as_float(u << 16); a1 += __uint_as_float(u & 0xffff0000u); }
+  out[b * N + n] = a0;
+  out[b * N + n + 1] = a1;
+}
 
 // src [B,C,T] <-> dst channel-last with strides; 32x32 smem tile transpose.
 __global__ void transpose_bct_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t C, int64_t T,
@@ -489,10 +507,17 @@ int ag_zero_pads(void* buf, int64_t B, int64_t rows, int64_t row_bytes, int64_t 
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
-int ag_rowgroup_sum(const float* in, float* out, int64_t B, int64_t T, int64_t N, void* stream) {
-  AG_CHECK_ARG(in && out && B > 0 && T > 0 && N > 0, "ag_rowgroup_sum: bad args");
+int ag_rowgroup_sum(const void* in, int32_t dtype, float* out, int64_t B, int64_t T, int64_t N, void* stream) {
+  AG_CHECK_ARG(in && out && B > 0 && T > 0 && N > 0 && B < 65536, "ag_rowgroup_sum: bad args");
+  if (dtype == 1) {
+    AG_CHECK_ARG(N % 2 == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0, "ag_rowgroup_sum: bf16 input needs an even N");
+    dim3 g2((unsigned)((N / 2 + 127) / 128), (unsigned)B);
+    rowgroup_sum_bf16_kernel<<<g2, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, T, N);
+    AG_LAUNCH_CHECK();
+    return AG_OK;
+  }
   dim3 grid((unsigned)((N + 127) / 128), (unsigned)B);
-  rowgroup_sum_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(in, out, T, N);
+  rowgroup_sum_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(in), out, T, N);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

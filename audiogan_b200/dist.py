@@ -117,3 +117,4 @@ def broadcast_parameters(modules, src=0):
     for m in modules:
         for p in m.parameters():
             dist.broadcast(p.data, src)
+            p._ag_epoch = getattr(p, "_ag_epoch", 0) + 1      # written through .data: invalidate the packed-operand cache

@@ -425,7 +425,7 @@ class _DiscTailFn(torch.autograd.Function):
         dgsum = None
         if wgrad or ctx.needs_input_grad[3]:
             dgsum = _empty(B, 8 * H, device=dev)
-            K.rowgroup_sum(dgates, dgsum, B, Tm, 8 * H)
+            K.rowgroup_sum(dgo, dgsum, B, Tm, 8 * H)          # bf16 mode: from the bf16 shadow (half the bytes)
         if wgrad:
             for d in range(2):
                 K.gemm_tn(M, 4 * H, H, (dgo, d * 4 * H), (Tm, Tm * 8 * H, 8 * H),

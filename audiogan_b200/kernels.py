@@ -199,7 +199,7 @@ def zero_pads(buf, head, tail0):
 
 
 def rowgroup_sum(src, out, B, T, N):
-    A.call("ag_rowgroup_sum", addr(src), addr(out), B, T, N, A.stream())
+    A.call("ag_rowgroup_sum", addr(src), _dtype_of(src), addr(out), B, T, N, A.stream())
 
 
 def bce_fwd(x, tgt, w, loss, B, T):

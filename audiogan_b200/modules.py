@@ -118,6 +118,12 @@ class _PlanOwner(NN.Module):
         st.pop("_plan", None)
         return st
 
+    def invalidate_packed(self):
+        """Call after changing parameters behind torch's back (writes through ``p.data`` do not bump the version counters the
+        packed-operand cache watches; in-place ops on the parameter itself, load_state_dict and the fused optimizers do)."""
+        for p in self.parameters():
+            p._ag_epoch = getattr(p, "_ag_epoch", 0) + 1
+
     def _get_plan(self):
         params = list(self.parameters())
         dev = params[0].device

@@ -274,8 +274,8 @@ int ag_frames_to_slot(void* dst, int32_t dst_dtype, int64_t d_bs, int64_t d_rs, 
  * padding every conv view relies on, audiogan.py:272 / :490 `padding=`): one launch instead of two strided fills.
  * row_bytes % 16 == 0, buf 16-byte aligned. */
 int ag_zero_pads(void* buf, int64_t B, int64_t rows, int64_t row_bytes, int64_t head, int64_t tail0, void* stream);
-/* out[b, n] = sum_t in[b, t, n] */
-int ag_rowgroup_sum(const float* in, float* out, int64_t B, int64_t T, int64_t N, void* stream);
+/* out[b, n] = sum_t in[b, t, n]; in: dtype 0 fp32 / 1 bf16 (N even) */
+int ag_rowgroup_sum(const void* in, int32_t dtype, float* out, int64_t B, int64_t T, int64_t N, void* stream);
 /* dst[b, t, c] (channel-last, row stride dst_rs, batch stride dst_bs) <-> src[b, c, t] */
 int ag_transpose_bct(const float* src, float* dst, int64_t B, int64_t C, int64_t T,
                      int64_t dst_bs, int64_t dst_rs, int32_t to_channel_last, void* stream);
