@@ -167,7 +167,16 @@ def check(rc, who):
         raise AudioganError("%s failed: %s (%s)" % (who, _ERRNAMES.get(rc, rc), msg))
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_get_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream():
+    """torch's current CUDA stream as a raw handle.  Called once per kernel launch (~170 per step): the private fast path
+    costs ~0.3 us, torch.cuda.current_stream().cuda_stream ~15 us (it builds a Stream object); falls back if the private
+    accessors are absent."""
+    if _raw_stream is not None and _get_device is not None:
+        return C.c_void_p(_raw_stream(_get_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

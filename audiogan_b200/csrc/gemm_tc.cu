@@ -484,7 +484,8 @@ static int launch_nt2(const ag_gemm_desc* d, cudaStream_t s) {
   constexpr int smem = STG * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + (2 * STG + 1) * 8 + 16 + BM * 8 + 3 * BM * 4;
   static_assert(STG * (BM * BK * 2 + BN * BK * 2) >= 8 * 32 * TRLD * 4, "epilogue transpose tiles must fit in the stages");
   auto kern = gemm_nt_tc_kernel<BN, MODE, VECC>;
-  AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static bool attr_set = false;      // once per instantiation (a driver call per launch otherwise)
+  if (!attr_set) { AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
   dim3 grid((unsigned)((d->M + BM - 1) / BM), (unsigned)((d->N + BN - 1) / BN));
   kern<<<grid, NT_THREADS, smem, s>>>(*d, mapB);
   AG_LAUNCH_CHECK();
@@ -939,7 +940,8 @@ static int launch_nt_tma2(const ag_gemm_desc* d, int64_t R, cudaStream_t s) {
   constexpr int smem = STG * (BM * BK * 2 + BN * BK * 2) + 8 * 32 * TRLD * 4 + 1024 + (2 * STG + 4) * 8 + 16 + BM * 8 + 3 * BM * 4 + BM * 16;
   static_assert(smem <= 227 * 1024, "shared-memory budget");
   auto kern = gemm_nt_tma_kernel<BN, VECC>;
-  AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static bool attr_set = false;      // once per instantiation (a driver call per launch otherwise)
+  if (!attr_set) { AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
   const int64_t tpb = (R + BM - 1) / BM, ntn = (d->N + BN - 1) / BN;
   const int64_t total = nb * tpb * ntn;
   AG_CHECK_ARG(total < (1ll << 31), "ag_gemm_nt_tc: too many tiles");
@@ -1453,7 +1455,8 @@ static int launch_tn_tma(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones
   const int64_t gz = (total + sps - 1) / sps;
   AG_CHECK_ARG(gy < 65536 && gz < 65536 && total < (1ll << 31), "ag_gemm_tn_tc: grid too large");
   auto kern = gemm_tn_tma_kernel<BNK>;
-  AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static bool attr_set = false;      // once per instantiation (a driver call per launch otherwise)
+  if (!attr_set) { AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
   kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), TNT_THREADS, smem, s>>>(mapY, mapA, dw, ldw, (int)d->N, (int)Kd, (int)spb,
                                                                                 (int)total, (int)sps, (int)pg.KT);
   AG_LAUNCH_CHECK();

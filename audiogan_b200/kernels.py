@@ -34,32 +34,17 @@ def _dtype_of(x):
 def gemm_desc(M, N, K, A_, a_view, B_, ldb, C_, c_view, alpha=0.0, bias=None, bias_mod=0, rowbias=None,
               rowbias_ld=0, skip=None, act=0, dact=None, slope=LRELU_SLOPE, mask_len=None, mask=(0, 0, 0), a_layout=0):
     """a_view = (rows_per_batch, batch_stride, row_stride[, k_inner, k_outer_stride]);
-    c_view = (rows_per_batch, batch_stride, row_stride[, n_inner, n_outer_stride])."""
-    d = A.GemmDesc()
-    d.M, d.N, d.K = M, N, K
-    d.A = addr(A_)
-    a = tuple(a_view) + ((K, 0) if len(a_view) == 3 else ())
-    d.a_rpb, d.a_bs, d.a_rs, d.a_kin, d.a_k1s = a
-    d.B = addr(B_)
-    d.ldb = ldb
-    d.C = addr(C_)
-    c = tuple(c_view) + ((N, 0) if len(c_view) == 3 else ())
-    d.c_rpb, d.c_bs, d.c_rs, d.c_nin, d.c_n1s = c
-    d.alpha = alpha
-    d.bias = addr(bias)
-    d.bias_mod = bias_mod
-    d.rowbias = addr(rowbias)
-    d.rowbias_ld = rowbias_ld
-    d.skip = addr(skip)
-    d.act = act
-    d.dact = addr(dact)
-    d.slope = slope
-    d.mask_len = addr(mask_len)
-    d.mask_tmul, d.mask_n1mul, d.mask_toff = mask
-    d.a_dtype, d.b_dtype, d.c_dtype = _dtype_of(A_), _dtype_of(B_), _dtype_of(C_)
-    d.aux_dtype = _dtype_of(skip if skip is not None else dact)
-    d.a_layout = a_layout
-    return d
+    c_view = (rows_per_batch, batch_stride, row_stride[, n_inner, n_outer_stride]).
+    (One positional constructor call in field order: ~90 descriptors are built per training step.)"""
+    a = a_view if len(a_view) == 5 else (a_view[0], a_view[1], a_view[2], K, 0)
+    c = c_view if len(c_view) == 5 else (c_view[0], c_view[1], c_view[2], N, 0)
+    return A.GemmDesc(M, N, K,
+                      addr(A_), a[0], a[1], a[2], a[3], a[4],
+                      addr(B_), ldb,
+                      addr(C_), c[0], c[1], c[2], c[3], c[4],
+                      alpha, addr(bias), bias_mod, addr(rowbias), rowbias_ld, addr(skip), act, addr(dact), slope,
+                      addr(mask_len), mask[0], mask[1], mask[2],
+                      _dtype_of(A_), _dtype_of(B_), _dtype_of(C_), _dtype_of(skip if skip is not None else dact), a_layout)
 
 
 TC_MIN_MACS = 1 << 20      # below this a GEMM stays on the fp32 FFMA kernel even in bf16 mode (launch-bound anyway)

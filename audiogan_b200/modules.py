@@ -116,6 +116,7 @@ class _PlanOwner(NN.Module):
         # and is rebuilt lazily, so it never travels with the module
         st = dict(self.__dict__)
         st.pop("_plan", None)
+        st.pop("_param_list", None)
         return st
 
     def invalidate_packed(self):
@@ -124,8 +125,16 @@ class _PlanOwner(NN.Module):
         for p in self.parameters():
             p._ag_epoch = getattr(p, "_ag_epoch", 0) + 1
 
+    def _params(self):
+        """Cached parameter list (module.parameters() walks the module tree: ~0.1 ms per call, several calls per step)."""
+        pl = self.__dict__.get("_param_list")
+        if pl is None:
+            pl = list(self.parameters())
+            object.__setattr__(self, "_param_list", pl)
+        return pl
+
     def _get_plan(self):
-        params = list(self.parameters())
+        params = self._params()
         dev = params[0].device
         if dev.type != "cuda":
             raise RuntimeError("audiogan_b200 runs on CUDA (sm_100a) only -- move the module with .cuda(); "
