@@ -670,6 +670,10 @@ gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap map
                             ? ((d.skip ? EPI_SKIP : 0) | (d.dact ? EPI_DACT : 0) | (d.rowbias ? EPI_RB : 0) | (d.mask_len ? EPI_MASK : 0) |
                                (d.act == 1 ? EPI_ACT : 0))
                             : -1;
+    const int epi_sel32 = (d.c_dtype == 0 && (!aux_any || d.aux_dtype == 1) && alpha == 1.f)
+                              ? ((d.skip ? EPI_SKIP : 0) | (d.dact ? EPI_DACT : 0) | (d.rowbias ? EPI_RB : 0) | (d.mask_len ? EPI_MASK : 0) |
+                                 (d.act == 1 ? EPI_ACT : 0))
+                              : -1;
     const int dbgf = g_nt_dbg_on;
     const bool dbg = dbgf != 0 && tid == 0;
     long long t_wait = 0, t_work = 0, q0 = 0;
@@ -727,6 +731,13 @@ gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap map
               AG_EPI(0) AG_EPI(EPI_ACT) AG_EPI(EPI_SKIP | EPI_ACT) AG_EPI(EPI_SKIP | EPI_MASK | EPI_ACT) AG_EPI(EPI_MASK | EPI_ACT)
               AG_EPI(EPI_DACT) AG_EPI(EPI_SKIP) AG_EPI(EPI_MASK) AG_EPI(EPI_SKIP | EPI_DACT) AG_EPI(EPI_DACT | EPI_MASK)
               default: epi_chunk_vec<true, true, CH, -1>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
+            }
+          } else if (epi_sel32 >= 0) {
+            switch (epi_sel32) {     // fp32 output (LSTM input projection: row bias; data gradient into the recurrent state: skip)
+#define AG_EPI32(FL) case FL: epi_chunk_vec<false, true, CH, FL>(d, tr, rowtab, wq, lane, n0 + c0, alpha); break;
+              AG_EPI32(0) AG_EPI32(EPI_RB) AG_EPI32(EPI_SKIP)
+#undef AG_EPI32
+              default: epi_chunk_vec<false, true, CH, -1>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
             }
           } else if (d.c_dtype) {
             epi_chunk_vec<true, false, CH, -1>(d, tr, rowtab, wq, lane, n0 + c0, alpha);
