@@ -333,8 +333,10 @@ class _DiscCNNFn(torch.autograd.Function):
 # =========================================================================================
 class _DiscTailFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan, token, feat, c, nfr, Tm):
-        """feat: (B, Cf, T6) channel-last view; c (B, E); nfr int32 [B] frames per sample; Tm = max(nfr)."""
+    def forward(ctx, plan, token, feat, c, nfr, Tm, Tmin=0):
+        """feat: (B, Cf, T6) channel-last view; c (B, E); nfr int32 [B] frames per sample; Tm = max(nfr), Tmin = min(nfr)
+        (host values: rows 1..Tmin of the recurrent state are written by the kernel for every sample, so only row 0 and
+        rows > Tmin are zeroed -- packed-sequence semantics, audiogan.py:214-229: outputs past a sample's length are zero)."""
         dev = plan.device
         B, Cf, T6 = feat.shape
         if feat.stride(1) != 1:
@@ -348,9 +350,14 @@ class _DiscTailFn(torch.autograd.Function):
         pre = _empty(B, Tm, 8 * H, device=dev)
         K.gemm_nt(B * Tm, 8 * H, Cf, feat, (Tm, feat.stride(0), feat.stride(2)), plan.Poff("wih"), ldi,
                   pre, (Tm, Tm * 8 * H, 8 * H), rowbias=rb, rowbias_ld=8 * H)
-        hbuf = _zeros(B, Tm + 2, 2 * H, device=dev)
         bf = plan.mode == "bf16"
-        hbuf16 = torch.zeros(B, Tm + 2, 2 * H, device=dev, dtype=torch.bfloat16) if bf else None
+        Tmin = max(0, min(int(Tmin), Tm))
+        hbuf = _empty(B, Tm + 2, 2 * H, device=dev)
+        K.zero_pads(hbuf, 1, Tmin + 1)
+        hbuf16 = None
+        if bf:
+            hbuf16 = torch.empty(B, Tm + 2, 2 * H, device=dev, dtype=torch.bfloat16)
+            K.zero_pads(hbuf16, 1, Tmin + 1)
         gates = _empty(B, Tm, 8 * H, device=dev)
         cbuf = _empty(B, Tm, 2 * H, device=dev)
         misc = torch.zeros(16, device=dev, dtype=torch.int32)
@@ -445,7 +452,7 @@ class _DiscTailFn(torch.autograd.Function):
             K.gemm_nt(B, E, 8 * H, dgsum, (B, 0, 8 * H), plan.Poff("wiht", Cf * 8 * H), 8 * H,
                       dc, (B, 0, E))
         gtok = torch.zeros(1, device=dev) if wgrad else None
-        return None, gtok, dfeat, dc, None, None
+        return None, gtok, dfeat, dc, None, None, None
 
 
 # =========================================================================================

@@ -246,7 +246,7 @@ class Discriminator(_PlanOwner):
         Tm = int(lens_h[-1].max())
         token = P.pack(plan)
         outs = E._DiscCNNFn.apply(plan, self._cnn_struct, token, x, lens_d)
-        logits = E._DiscTailFn.apply(plan, token, outs[-1], c, lens_d[-1], Tm)
+        logits = E._DiscTailFn.apply(plan, token, outs[-1], c, lens_d[-1], Tm, int(lens_h[-1].min()))
         lens_out = [l.to(length.device) for l in lens_h]
         return logits, list(outs), lens_out, lens_out[-1]
 
