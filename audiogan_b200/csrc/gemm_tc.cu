@@ -1350,18 +1350,22 @@ __global__ void __launch_bounds__(256) tn_bias_kernel(const __nv_bfloat16* __res
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (n < N) {
     const uint32_t rpb32 = (uint32_t)rpb;
-    for (int64_t m = m0 + ry; m < m1; m += 2 * nrl) {           // two rows in flight per thread
-      const uint32_t b0 = (uint32_t)m / rpb32;
-      const int64_t m2 = m + nrl;
-      const uint32_t b1 = (uint32_t)m2 / rpb32;
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(Y + b0 * bs + (m - (int64_t)b0 * rpb) * rs + n));
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (m2 < m1) v = __ldg(reinterpret_cast<const uint4*>(Y + b1 * bs + (m2 - (int64_t)b1 * rpb) * rs + n));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w}, x[4] = {v.x, v.y, v.z, v.w};
+    for (int64_t m = m0 + ry; m < m1; m += 4 * nrl) {           // four rows in flight per thread
+      uint4 u[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        acc[2 * e] += __uint_as_float(w[e] << 16) + __uint_as_float(x[e] << 16);
-        acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u) + __uint_as_float(x[e] & 0xffff0000u);
+      for (int i = 0; i < 4; ++i) {
+        const int64_t mi = m + (int64_t)i * nrl;
+        const uint32_t bi = (uint32_t)mi / rpb32;
+        u[i] = mi < m1 ? __ldg(reinterpret_cast<const uint4*>(Y + bi * bs + (mi - (int64_t)bi * rpb) * rs + n)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] += __uint_as_float(w[e] << 16);
+          acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+        }
       }
     }
   }
@@ -1478,7 +1482,7 @@ static int launch_tn_tma(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones
     int64_t by = (int64_t)sm_count() * 8 / bx;
     if (by < 1) by = 1;
     int64_t rows_per = (d->M + by - 1) / by;
-    if (rows_per < 512) rows_per = 512;
+    if (rows_per < 128) rows_per = 128;
     by = (d->M + rows_per - 1) / rows_per;
     tn_bias_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d->C), d->c_rpb, d->c_bs, d->c_rs,
                                                                     d->M, (int)d->N, dw + Kd, ldw, rows_per, lg);
