@@ -77,6 +77,7 @@ class EwDesc(C.Structure):
         ("out", vp), ("pad_l", i64), ("pad_r", i64),
         ("acc", vp), ("acc_bs", i64), ("acc_rs", i64),
         ("g1_dtype", i32), ("g2_dtype", i32), ("act_dtype", i32), ("acc_dtype", i32), ("out_dtype", i32), ("reserved2", i32),
+        ("colsum", vp),
     ]
 
 

@@ -163,6 +163,7 @@ __global__ void ew_grad_kernel(const ag_ew_desc d) {
 __global__ void __launch_bounds__(256) ew_grad_vec4_kernel(const ag_ew_desc d) {
   const uint32_t C4 = (uint32_t)(d.C >> 2), Tp = (uint32_t)(d.pad_l + d.T + d.pad_r);
   const uint32_t total = (uint32_t)d.B * Tp * C4;
+  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);     // d.colsum: this thread's column group is fixed (256 % C4 == 0, host-checked)
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint32_t rb = i / C4, c = (i - rb * C4) << 2, b = rb / Tp, r = rb - b * Tp;
     const int64_t t = (int64_t)r - d.pad_l;
@@ -186,6 +187,18 @@ __global__ void __launch_bounds__(256) ew_grad_vec4_kernel(const ag_ew_desc d) {
       }
     }
     if (d.out) st4_any(d.out, (int64_t)i << 2, v, d.out_dtype);
+    csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w;
+  }
+  if (d.colsum) {                                   // fused bias gradient: column sums of v, one set of atomics per block
+    __shared__ float4 red[256];
+    red[threadIdx.x] = csum;
+    __syncthreads();
+    if (threadIdx.x < C4) {
+      float4 a = red[threadIdx.x];
+      for (uint32_t r = threadIdx.x + C4; r < 256; r += C4) { const float4 q = red[r]; a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w; }
+      float* o = d.colsum + 4 * threadIdx.x;
+      atomicAdd(o, a.x); atomicAdd(o + 1, a.y); atomicAdd(o + 2, a.z); atomicAdd(o + 3, a.w);
+    }
   }
 }
 
@@ -451,6 +464,8 @@ int ag_ew_grad(const ag_ew_desc* d, void* stream) {
                    (!d->act || (d->a_bs % 4 == 0 && d->a_rs % 4 == 0 && al(d->act, d->act_dtype))) &&
                    (!d->acc || (d->acc_bs % 4 == 0 && d->acc_rs % 4 == 0 && al(d->acc, d->acc_dtype))) &&
                    (!d->out || al(d->out, d->out_dtype));
+  AG_CHECK_ARG(!d->colsum || (vec && d->C / 4 <= 256 && 256 % (d->C / 4) == 0),
+               "ag_ew_grad: the fused column sum needs the vector path and a channel count of 4 * 2^k <= 1024");
   if (vec) {
     ew_grad_vec4_kernel<<<grid_for(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(*d);
     AG_LAUNCH_CHECK();

@@ -153,11 +153,12 @@ class _GenFn(torch.autograd.Function):
                 # dyl = d(block output) * lrelu'(output); also feeds the dense skip (audiogan.py:281-283)
                 dyl = _empty(B, L + 2 * pd, out, device=dev, dtype=adt)
                 slice_off = GPAD * CT + cin
+                fuse_b = wgrad and out % 4 == 0 and (out // 4) & (out // 4 - 1) == 0 and out <= 1024      # bias gradient in the same pass
                 K.ew_grad(B, L, out, out=dyl, pad=(pd, pd), g1=(dXd, slice_off), g1_str=(Lp * CT, CT, 1),
                           act=(Xd, slice_off), act_str=(Lp * CT, CT),
                           acc=((dXd, GPAD * CT + plan.skip_off[li]) if plan.skip_off[li] >= 0 else None),
-                          acc_str=(Lp * CT, CT))
-                if wgrad:
+                          acc_str=(Lp * CT, CT), colsum=plan.GPoff("d%d.b" % li) if fuse_b else None)
+                if wgrad and not fuse_b:
                     K.colsum((dyl, pd * out), (L + 2 * pd) * out, out, B, L, out, plan.GPoff("d%d.b" % li))
                 # transposed-conv data gradient = strided conv over dyl, times lrelu'(hidden)
                 dH = _empty(B, Lh + 2, hid, device=dev, dtype=adt)

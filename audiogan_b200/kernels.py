@@ -104,7 +104,7 @@ def frame_noise(dst, dst_ld, pad_l, src, src_ld, noise, noise_scale, B, L):
 
 
 def ew_grad(B, T, Cn, out=None, pad=(0, 0), g1=None, g1_str=(0, 0, 0), g2=None, g2_str=(0, 0, 0), act=None,
-            act_str=(0, 0), length=None, acc=None, acc_str=(0, 0), slope=LRELU_SLOPE):
+            act_str=(0, 0), length=None, acc=None, acc_str=(0, 0), slope=LRELU_SLOPE, colsum=None):
     d = A.EwDesc()
     d.B, d.T, d.C = B, T, Cn
     d.g1 = addr(g1)
@@ -121,6 +121,7 @@ def ew_grad(B, T, Cn, out=None, pad=(0, 0), g1=None, g1_str=(0, 0, 0), g2=None, 
     d.acc_bs, d.acc_rs = acc_str
     d.g1_dtype, d.g2_dtype, d.act_dtype = _dtype_of(g1), _dtype_of(g2), _dtype_of(act)
     d.acc_dtype, d.out_dtype = _dtype_of(acc), _dtype_of(out)
+    d.colsum = addr(colsum)
     A.call("ag_ew_grad", C.byref(d), A.stream())
 
 

@@ -202,7 +202,9 @@ int ag_bce_const_fused(const float* x, int64_t ld, const int32_t* len, float tar
  *   v[b,t,c] = (g1[b,t,c] + g2[b,t,c]) * (act[b,t,c] > 0 ? 1 : slope) * (t < len[b])
  *   out[b, pad_l + t, c] = v, the pad_l rows before and pad_r rows after each sequence zeroed
  *   (out is a packed channel-last buffer [B, pad_l + T + pad_r, C] ready to be a GEMM operand);
- *   acc[b,t,c] += v when acc != NULL (the dense-net skip path).
+ *   acc[b,t,c] += v when acc != NULL (the dense-net skip path);
+ *   colsum[c] += sum_{b,t} v[b,t,c] when colsum != NULL (the bias gradient of the layer that produced the activation, fused:
+ *   needs unit channel strides, 16-byte aligned rows and C = 4 * 2^k).
  * g1/g2/act/len may be NULL (0 / 1 / all).
  * ------------------------------------------------------------------------------------------ */
 typedef struct ag_ew_desc {
@@ -216,6 +218,7 @@ typedef struct ag_ew_desc {
   void* acc; int64_t acc_bs, acc_rs;
   int32_t g1_dtype, g2_dtype, act_dtype, acc_dtype, out_dtype, reserved2;   /* 0 = fp32, 1 = bf16 (bf16 mode stores the conv
                                                                                stacks' activations and gradients as bf16) */
+  float* colsum;
 } ag_ew_desc;
 int ag_ew_grad(const ag_ew_desc* d, void* stream);
 /* out[c] += sum_{b,t} in[b*bs + t*rs + c]  (bias gradients); out must be initialised.  in: dtype 0 fp32 / 1 bf16. */

@@ -462,6 +462,15 @@ def test_streaming_kernels_both_storage_types(dt):
     ref = T.zeros(B, pl + Tn + pr, Cn)
     ref[:, pl:pl + Tn] = v
     assert rel(out, ref) < tol and rel(acc, acc0 + v) < tol
+    # fused bias gradient: column sums of the assembled gradient in the same pass (C = 4 * 2^k)
+    Cs = 32
+    gs_, as_ = q(T.randn(B, Tn, Cs)), q(T.randn(B, Tn, Cs))
+    outs = T.empty(B, pl + Tn + pr, Cs, device="cuda", dtype=dt)
+    cs = T.zeros(Cs, device="cuda")
+    K.ew_grad(B, Tn, Cs, out=outs, pad=(pl, pr), g1=gs_.to(dt).cuda(), g1_str=(Tn * Cs, Cs, 1), act=as_.to(dt).cuda(),
+              act_str=(Tn * Cs, Cs), colsum=cs)
+    vs = gs_ * T.where(as_ > 0, 1.0, 0.01)
+    assert rel(outs[:, pl:pl + Tn], vs) < tol and rel(cs, vs.sum((0, 1))) < 1e-5
     # strided (scalar-path) g1: a (B, C, T) tensor read as [b, t, c]
     g1t = g1.permute(0, 2, 1).contiguous().to(dt).cuda()
     out2 = T.empty(B, Tn, Cn, device="cuda", dtype=dt)
