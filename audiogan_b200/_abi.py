@@ -50,7 +50,7 @@ class LstmDesc(C.Structure):
         ("w1t", vp), ("wxt", vp),
         ("barrier", vp),
         ("dh_ext_bs", i64),
-        ("prec", i32), ("reserved2", i32),
+        ("prec", i32), ("flags", i32),
         ("hbuf16", vp), ("xbuf16", vp), ("dgates16", vp), ("dpx16", vp),
         ("dbg", vp),
         ("ll_ws", vp), ("ll_ws_bytes", i64),
@@ -98,6 +98,7 @@ _PROTOS = {
     "ag_bce_fwd": [vp, vp, vp, vp, i64, i64, vp],
     "ag_bce_bwd": [vp, vp, vp, vp, vp, i64, i64, vp],
     "ag_bce_const_fused": [vp, i64, vp, f32, f32, vp, vp, vp, vp, i64, i64, vp],
+    "ag_reinforce_dlogit": [vp, i64, vp, i64, vp, vp, vp, vp, vp, i64, i64, i64, vp],
     "ag_ew_grad": [C.POINTER(EwDesc), vp],
     "ag_colsum": [vp, i32, i64, i64, i64, i64, i64, vp, vp],
     "ag_outer_dact": [vp, vp, vp, i32, vp, i32, i64, i64, f32, vp],
@@ -113,7 +114,7 @@ _PROTOS = {
     "ag_frames_to_slot": [vp, i32, i64, i64, i32, vp, i64, i64, i64, vp],
     "ag_rowgroup_sum": [vp, i32, vp, i64, i64, i64, vp],
     "ag_transpose_bct": [vp, vp, i64, i64, i64, i64, i64, i32, vp],
-    "ag_mt_sqnorm": [vp, vp, vp, i32, i32, vp, vp, vp],
+    "ag_mt_sqnorm": [vp, vp, vp, i32, i32, vp, vp, f32, vp],
     "ag_mt_clip": [vp, vp, vp, i32, i32, vp, f32, vp],
     "ag_mt_rmsprop": [vp, vp, vp, i32, i32, vp, f32, f32, f32, f32, f32, vp],
     "ag_mt_adam": [vp, vp, vp, i32, i32, vp, f32, f32, f32, f32, f32, f32, i32, vp],
@@ -150,12 +151,16 @@ def lib():
             fn.restype = C.c_int
     L.ag_last_error_string.argtypes = []
     L.ag_last_error_string.restype = C.c_char_p
+    L.ag_lstm_last_path.argtypes = []
+    L.ag_lstm_last_path.restype = C.c_char_p
+    L.ag_lstm_workspace_bytes.argtypes = [C.POINTER(LstmDesc), i32]
+    L.ag_lstm_workspace_bytes.restype = C.c_int64
     _lib = L
     return L
 
 
 def exported_symbols():
-    return list(_PROTOS) + ["ag_last_error_string"]
+    return list(_PROTOS) + ["ag_last_error_string", "ag_lstm_last_path", "ag_lstm_workspace_bytes"]
 
 
 class AudioganError(RuntimeError):

@@ -9,6 +9,10 @@
 namespace ag {
 
 void set_error(const char* fmt, ...);
+// diagnostics of the recurrent dispatch (abi.cu): why a fast path declined / which family ran (ag_lstm_last_path)
+void set_decline(const char* fmt, ...);
+void clear_decline();
+void set_path(const char* family);
 
 #define AG_CHECK_ARG(cond, ...)                 \
   do {                                          \

@@ -385,13 +385,15 @@ __global__ void frames_to_slot_kernel(void* __restrict__ dst, int ddt, int64_t d
   }
 }
 
-// zero rows [0, head) and [tail0, rows) of every batch of a packed [B, rows, row_bytes] buffer, 16 bytes per thread
-__global__ void zero_pads_kernel(uint4* __restrict__ p, int64_t B, int64_t rows, int64_t row16, int64_t head, int64_t tail0) {
-  const int64_t per = (head + rows - tail0) * row16, total = B * per;
+// zero rows [0, head) and [tail0, rows) of every batch of a packed [B, rows, row_bytes] buffer; one store of sizeof(U) bytes
+// per thread and iteration (U = uint4 when rows are 16-byte multiples and the buffer is aligned, else uint32_t / uint16_t)
+template <typename U>
+__global__ void zero_pads_kernel(U* __restrict__ p, int64_t B, int64_t rows, int64_t rowu, int64_t head, int64_t tail0) {
+  const int64_t per = (head + rows - tail0) * rowu, total = B * per;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / per, j = i - b * per;
-    const int64_t off = j < head * row16 ? j : tail0 * row16 + (j - head * row16);
-    p[b * rows * row16 + off] = make_uint4(0u, 0u, 0u, 0u);
+    const int64_t off = j < head * rowu ? j : tail0 * rowu + (j - head * rowu);
+    p[b * rows * rowu + off] = U{};
   }
 }
 
@@ -514,11 +516,16 @@ int ag_frames_to_slot(void* dst, int32_t dst_dtype, int64_t d_bs, int64_t d_rs, 
   return AG_OK;
 }
 int ag_zero_pads(void* buf, int64_t B, int64_t rows, int64_t row_bytes, int64_t head, int64_t tail0, void* stream) {
-  AG_CHECK_ARG(buf && B > 0 && rows > 0 && row_bytes > 0 && row_bytes % 16 == 0 && head >= 0 && tail0 >= head && tail0 <= rows &&
-                   (reinterpret_cast<uintptr_t>(buf) & 15) == 0, "ag_zero_pads: bad args");
-  const int64_t n = B * (head + rows - tail0) * (row_bytes / 16);
+  AG_CHECK_ARG(buf && B > 0 && rows > 0 && row_bytes > 0 && row_bytes % 2 == 0 && head >= 0 && tail0 >= head && tail0 <= rows &&
+                   (reinterpret_cast<uintptr_t>(buf) & 1) == 0, "ag_zero_pads: bad args");
+  const uintptr_t a = reinterpret_cast<uintptr_t>(buf);
+  const int unit = (row_bytes % 16 == 0 && (a & 15) == 0) ? 16 : (row_bytes % 4 == 0 && (a & 3) == 0) ? 4 : 2;
+  const int64_t n = B * (head + rows - tail0) * (row_bytes / unit);
   if (n == 0) return AG_OK;
-  zero_pads_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4*>(buf), B, rows, row_bytes / 16, head, tail0);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (unit == 16) zero_pads_kernel<uint4><<<grid_for(n, 256), 256, 0, s>>>(reinterpret_cast<uint4*>(buf), B, rows, row_bytes / 16, head, tail0);
+  else if (unit == 4) zero_pads_kernel<uint32_t><<<grid_for(n, 256), 256, 0, s>>>(reinterpret_cast<uint32_t*>(buf), B, rows, row_bytes / 4, head, tail0);
+  else zero_pads_kernel<uint16_t><<<grid_for(n, 256), 256, 0, s>>>(reinterpret_cast<uint16_t*>(buf), B, rows, row_bytes / 2, head, tail0);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

@@ -1213,14 +1213,26 @@ int cluster_bwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);
 } namespace lg {
 int gen_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);       // lstm_gen.cu
 int gen_bwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);
+int64_t gen_fwd_ws_bytes(const ag_lstm_desc* d);
+int64_t gen_bwd_ws_bytes(const ag_lstm_desc* d);
 } }
 
 using namespace ag;
 extern "C" {
 
+static const char* grid_family(const Plan& p) {
+  return p.bf == 2 ? "grid-tcgen05" : p.bf == 1 ? "grid-bf16" : p.res ? "grid-fp32" : "grid-fp32-streamed";
+}
+
+int64_t ag_lstm_workspace_bytes(const ag_lstm_desc* d, int32_t bwd) {
+  if (!d) return AG_EINVAL;
+  return bwd ? lg::gen_bwd_ws_bytes(d) : lg::gen_fwd_ws_bytes(d);
+}
+
 int ag_lstm_fwd(const ag_lstm_desc* d, void* stream) {
   int rc = check_lstm(d, "ag_lstm_fwd", false);
   if (rc) return rc;
+  clear_decline();
   {
     int launched = 0;
     rc = lc::cluster_fwd(d, (cudaStream_t)stream, &launched);
@@ -1281,12 +1293,14 @@ int ag_lstm_fwd(const ag_lstm_desc* d, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   AG_CUDA(cudaMemsetAsync(d->barrier, 0, 8 * sizeof(unsigned), s));
   if (d->F > 0) AG_CUDA(cudaMemsetAsync(d->t_end, 0, sizeof(int), s));
+  set_path(grid_family(p));
   return run_fwd(d, p, s);
 }
 
 int ag_lstm_bwd(const ag_lstm_desc* d, void* stream) {
   int rc = check_lstm(d, "ag_lstm_bwd", true);
   if (rc) return rc;
+  clear_decline();
   {
     int launched = 0;
     rc = lc::cluster_bwd(d, (cudaStream_t)stream, &launched);
@@ -1343,6 +1357,7 @@ int ag_lstm_bwd(const ag_lstm_desc* d, void* stream) {
   AG_CHECK_ARG(p.smem <= (size_t)smem_optin(), "ag_lstm_bwd: needs %zu B of shared memory", p.smem);
   cudaStream_t s = (cudaStream_t)stream;
   AG_CUDA(cudaMemsetAsync(d->barrier, 0, 8 * sizeof(unsigned), s));
+  set_path(grid_family(p));
   return run_bwd(d, p, s);
 }
 }

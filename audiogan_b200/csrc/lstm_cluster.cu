@@ -608,9 +608,11 @@ static size_t bwd_smem_bytes(int H, int G) {
 }
 
 static bool eligible(const ag_lstm_desc* d) {
-  if (d->F != 0 || d->prec < 1 || (d->reserved2 & 1)) return false;
+  if (d->F != 0 || d->prec < 1 || (d->flags & 1)) return false;
   const int H = d->H;
-  return H == 128 || H == 256 || H == 512;                  // H/32 CTAs per cluster (4, 8, 16), whole 128-unit M-tiles
+  if (H == 128 || H == 256 || H == 512) return true;        // H/32 CTAs per cluster (4, 8, 16), whole 128-unit M-tiles
+  set_decline("cluster declined: H=%d not in {128, 256, 512}", H);
+  return false;
 }
 
 static void cluster_cfg(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int CS, int threads, size_t smem, cudaStream_t s) {
@@ -627,7 +629,7 @@ static int launch_groups(KernT kern, const ag_lstm_desc* d, int maxg, size_t (*s
   *launched = 0;
   const int CS = d->H / UPC;
   size_t smem = smem_of(d->H, maxg);
-  if (smem > (size_t)smem_optin()) return AG_OK;
+  if (smem > (size_t)smem_optin()) { set_decline("cluster declined: %zu B of shared memory", smem); return AG_OK; }
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return AG_OK; }
   if (CS > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return AG_OK; }
   cudaLaunchConfig_t cfg = {};
@@ -635,7 +637,10 @@ static int launch_groups(KernT kern, const ag_lstm_desc* d, int maxg, size_t (*s
   cluster_cfg(&cfg, at, CS, GT * maxg, smem, s);
   int nmax = 0;
   if (cudaOccupancyMaxActiveClusters(&nmax, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return AG_OK; }
-  if (nmax < d->ndir) return AG_OK;                         // cannot host one cluster per direction: caller falls back
+  if (nmax < d->ndir) {                                     // cannot host one cluster per direction: caller falls back
+    set_decline("cluster declined: %d co-resident clusters of %d CTAs < %d directions", nmax, CS, d->ndir);
+    return AG_OK;
+  }
   // sub-slices of 16 samples per direction -> G warp groups on each of cpd clusters (fewest rounds, then fewest groups)
   const int nss = (d->B + NBG - 1) / NBG, cpd_max = nmax / d->ndir;
   const int G = std::min(maxg, (nss + cpd_max - 1) / cpd_max);
@@ -646,11 +651,13 @@ static int launch_groups(KernT kern, const ag_lstm_desc* d, int maxg, size_t (*s
   ag_lstm_desc dd = *d;
   AG_CUDA(cudaLaunchKernelEx(&cfg, kern, dd, nss, cpd, G));
   *launched = 1;
+  set_path("cluster");
   return AG_OK;
 }
 int cluster_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
   *launched = 0;
-  if (!eligible(d) || !d->hbuf16) return AG_OK;
+  if (!eligible(d)) return AG_OK;
+  if (!d->hbuf16) { set_decline("cluster declined: hbuf16 missing"); return AG_OK; }
   return launch_groups(lstm_cl_fwd_kernel, d, MAXG, fwd_smem_bytes, s, launched);
 }
 int cluster_bwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {

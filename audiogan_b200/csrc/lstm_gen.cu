@@ -956,24 +956,41 @@ static size_t fwd_smem(const ag_lstm_desc* d, const FwdGeom& g, int NB) {
          (size_t)4 * NB * UPC * 4 + 2 * NB * 4 + 64;
 }
 
-// *launched = 1 when this kernel took the call, 0 -> the caller falls back to lstm.cu
-int gen_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
-  *launched = 0;
-  if (d->F <= 0 || d->ndir != 1 || d->prec < 1 || !(d->reserved2 & 2) || (d->reserved2 & 1)) return AG_OK;
-  if (!d->hbuf16 || !d->xbuf16 || d->H % 128 != 0 || d->F % 8 != 0 || !d->ll_ws) return AG_OK;
-  FwdGeom g;
+// geometry of the forward launch for (B, H, F); returns a reason string when the shape cannot run here, else NULL
+static const char* fwd_geom(const ag_lstm_desc* d, FwdGeom& g, int& NB, size_t& ll_need, size_t& smem, char* why, size_t nwhy) {
+  if (d->H % 128 != 0 || d->F % 8 != 0) { snprintf(why, nwhy, "H=%d %% 128 or F=%d %% 8 != 0", d->H, d->F); return why; }
   g.nsl = d->H / UPC;
-  const int NB = (d->B + 15) / 16 * g.nsl <= sm_count() ? 16 : 32;
+  NB = (d->B + 15) / 16 * g.nsl <= sm_count() ? 16 : 32;
   g.ngroups = (d->B + NB - 1) / NB;
-  if (g.ngroups * g.nsl > sm_count() || g.ngroups > 16) return AG_OK;
+  if (g.ngroups * g.nsl > sm_count() || g.ngroups > 16) {
+    snprintf(why, nwhy, "B=%d: %d batch groups x %d slices > %d SMs", d->B, g.ngroups, g.nsl, sm_count());
+    return why;
+  }
   g.KP = (d->H + d->F + 15) / 16 * 16;
   g.KT = std::min(d->H / 64 * 64, 896);             // 448 TMEM columns of weights + 64 of accumulators; k < KT <= H
   g.PR = (d->F + 1 + g.nsl - 1) / g.nsl;
-  if (g.PR > 8) return AG_OK;
-  const size_t ll_need = ((size_t)2 * g.ngroups * NB * (d->H / 2) + (size_t)2 * g.ngroups * NB * d->F + 32) * 8;
-  if ((size_t)d->ll_ws_bytes < ll_need) return AG_OK;
-  const size_t smem = fwd_smem(d, g, NB);
-  if (smem > (size_t)smem_optin() || smem < (size_t)116 * 1024) return AG_OK;   // one CTA per SM (all 512 TMEM columns each)
+  if (g.PR > 8) { snprintf(why, nwhy, "F=%d: %d projection rows per CTA > 8", d->F, g.PR); return why; }
+  ll_need = ((size_t)2 * g.ngroups * NB * (d->H / 2) + (size_t)2 * g.ngroups * NB * d->F + 32) * 8;
+  smem = fwd_smem(d, g, NB);
+  if (smem > (size_t)smem_optin()) {
+    snprintf(why, nwhy, "H=%d F=%d: weight slice needs %zu B of shared memory beside tensor memory (> %d)", d->H, d->F, smem, smem_optin());
+    return why;
+  }
+  if (smem < (size_t)116 * 1024) { snprintf(why, nwhy, "H=%d: slice too small to pin one CTA per SM", d->H); return why; }
+  return nullptr;
+}
+
+// *launched = 1 when this kernel took the call, 0 -> the caller falls back to lstm.cu
+int gen_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
+  *launched = 0;
+  if (d->F <= 0 || d->ndir != 1 || d->prec < 1 || !(d->flags & 2) || (d->flags & 1)) return AG_OK;
+  FwdGeom g;
+  int NB = 16;
+  size_t ll_need = 0, smem = 0;
+  char why[160];
+  if (fwd_geom(d, g, NB, ll_need, smem, why, sizeof(why))) { set_decline("tmem declined: %s", why); return AG_OK; }
+  if (!d->hbuf16 || !d->xbuf16 || !d->ll_ws) { set_decline("tmem declined: hbuf16 / xbuf16 / ll_ws missing"); return AG_OK; }
+  if ((size_t)d->ll_ws_bytes < ll_need) { set_decline("tmem declined: ll_ws %lld B < %zu B", (long long)d->ll_ws_bytes, ll_need); return AG_OK; }
   const void* kern = NB == 16 ? (const void*)lstm_gen_fwd_kernel<16> : (const void*)lstm_gen_fwd_kernel<32>;
   AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   AG_CUDA(cudaMemsetAsync(d->ll_ws, 0, ll_need, s));                  // tags: step numbers start at 1
@@ -982,7 +999,17 @@ int gen_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
   void* args[2] = {&dd, &g};
   AG_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)(g.ngroups * g.nsl)), dim3(LT), args, smem, s));
   *launched = 1;
+  set_path("tmem");
   return AG_OK;
+}
+int64_t gen_fwd_ws_bytes(const ag_lstm_desc* d) {
+  if (d->F <= 0 || d->ndir != 1 || d->prec < 1) return 0;
+  FwdGeom g;
+  int NB = 16;
+  size_t ll_need = 0, smem = 0;
+  char why[160];
+  if (fwd_geom(d, g, NB, ll_need, smem, why, sizeof(why))) return 0;
+  return (int64_t)ll_need;
 }
 
 
@@ -991,23 +1018,41 @@ static size_t bwd_smem(const ag_lstm_desc* d, const BwdGeom& g) {
   return 1024 + (size_t)(NMT - BT_TMEM) * 32768 + 16 * BNB * 16 + (size_t)(UPC + BNB) * WLD * 2 + (size_t)(BNB * 33) * 4 + 64;
 }
 
-int gen_bwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
-  *launched = 0;
-  if (d->F <= 0 || d->ndir != 1 || d->prec < 1 || !(d->reserved2 & 2) || (d->reserved2 & 1)) return AG_OK;
-  if (d->H % 128 != 0 || d->F % 8 != 0 || !d->ll_ws || d->len || d->dh_ext) return AG_OK;
-  BwdGeom g;
+static const char* bwd_geom(const ag_lstm_desc* d, BwdGeom& g, size_t& ll_need, size_t& smem, char* why, size_t nwhy) {
+  if (d->H % 128 != 0 || d->F % 8 != 0) { snprintf(why, nwhy, "H=%d %% 128 or F=%d %% 8 != 0", d->H, d->F); return why; }
   g.nsl = d->H / UPC;
   g.ngroups = (d->B + BNB - 1) / BNB;
-  if (g.nsl > 32 || g.ngroups * g.nsl > sm_count()) return AG_OK;
+  if (g.nsl > 32 || g.ngroups * g.nsl > sm_count()) {
+    snprintf(why, nwhy, "B=%d H=%d: %d batch groups x %d slices > %d SMs (or > 32 slices)", d->B, d->H, g.ngroups, g.nsl, sm_count());
+    return why;
+  }
   g.MR = d->H + d->F;
   g.FP = (d->F + 1 + 7) / 8 * 8;
   g.PR = (d->F + g.nsl - 1) / g.nsl;
   const int NMT = (g.MR + 127) / 128;
-  if (g.PR * 8 > LT || NMT <= BT_TMEM || BT_TMEM * 64 + NMT * BNB > 512 || g.FP % 16 != 0) return AG_OK;
-  const size_t ll_need = ((size_t)2 * g.ngroups * g.nsl * g.MR * 8 + (size_t)2 * g.ngroups * BNB * d->F + 32) * 8;
-  if ((size_t)d->ll_ws_bytes < ll_need) return AG_OK;
-  const size_t smem = bwd_smem(d, g);
-  if (smem > (size_t)smem_optin() || smem < (size_t)116 * 1024) return AG_OK;
+  if (g.PR * 8 > LT || NMT <= BT_TMEM || BT_TMEM * 64 + NMT * BNB > 512 || g.FP % 16 != 0) {
+    snprintf(why, nwhy, "H=%d F=%d: %d M-tiles do not fit tensor memory / FP=%d %% 16", d->H, d->F, NMT, g.FP);
+    return why;
+  }
+  ll_need = ((size_t)2 * g.ngroups * g.nsl * g.MR * 8 + (size_t)2 * g.ngroups * BNB * d->F + 32) * 8;
+  smem = bwd_smem(d, g);
+  if (smem > (size_t)smem_optin()) {
+    snprintf(why, nwhy, "H=%d F=%d: needs %zu B of shared memory (> %d)", d->H, d->F, smem, smem_optin());
+    return why;
+  }
+  if (smem < (size_t)116 * 1024) { snprintf(why, nwhy, "H=%d: slice too small to pin one CTA per SM", d->H); return why; }
+  return nullptr;
+}
+
+int gen_bwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
+  *launched = 0;
+  if (d->F <= 0 || d->ndir != 1 || d->prec < 1 || !(d->flags & 2) || (d->flags & 1)) return AG_OK;
+  BwdGeom g;
+  size_t ll_need = 0, smem = 0;
+  char why[160];
+  if (bwd_geom(d, g, ll_need, smem, why, sizeof(why))) { set_decline("tmem declined: %s", why); return AG_OK; }
+  if (!d->ll_ws || d->len || d->dh_ext) { set_decline("tmem declined: ll_ws missing or len / dh_ext given"); return AG_OK; }
+  if ((size_t)d->ll_ws_bytes < ll_need) { set_decline("tmem declined: ll_ws %lld B < %zu B", (long long)d->ll_ws_bytes, ll_need); return AG_OK; }
   const void* kern = (const void*)lstm_gen_bwd_kernel;
   AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   AG_CUDA(cudaMemsetAsync(d->ll_ws, 0, ll_need, s));
@@ -1015,7 +1060,16 @@ int gen_bwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
   void* args[2] = {&dd, &g};
   AG_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)(g.ngroups * g.nsl)), dim3(LT), args, smem, s));
   *launched = 1;
+  set_path("tmem");
   return AG_OK;
+}
+int64_t gen_bwd_ws_bytes(const ag_lstm_desc* d) {
+  if (d->F <= 0 || d->ndir != 1 || d->prec < 1) return 0;
+  BwdGeom g;
+  size_t ll_need = 0, smem = 0;
+  char why[160];
+  if (bwd_geom(d, g, ll_need, smem, why, sizeof(why))) return 0;
+  return (int64_t)ll_need;
 }
 
 }  // namespace lg

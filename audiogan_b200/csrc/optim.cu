@@ -9,7 +9,7 @@ namespace ag {
 __global__ void __launch_bounds__(256) mt_sqnorm_kernel(const ag_mt_entry* __restrict__ table,
                                                         const int32_t* __restrict__ chunk_tensor,
                                                         const int64_t* __restrict__ chunk_off, int chunk,
-                                                        float* __restrict__ sqnorm, int32_t* __restrict__ flags) {
+                                                        float* __restrict__ sqnorm, int32_t* __restrict__ flags, float big) {
   __shared__ float red[32];
   const int ti = chunk_tensor[blockIdx.x];
   const int64_t off = chunk_off[blockIdx.x];
@@ -25,18 +25,18 @@ __global__ void __launch_bounds__(256) mt_sqnorm_kernel(const ag_mt_entry* __res
       const float4 v = g4[i];
       acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
       bad |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
-      bad |= ((fabsf(v.x) > 1e5f) | (fabsf(v.y) > 1e5f) | (fabsf(v.z) > 1e5f) | (fabsf(v.w) > 1e5f)) << 1;
+      bad |= ((fabsf(v.x) > big) | (fabsf(v.y) > big) | (fabsf(v.z) > big) | (fabsf(v.w) > big)) << 1;
     }
     for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
       const float v = g[i];
       acc += v * v;
-      bad |= (v != v) | ((fabsf(v) > 1e5f) << 1);
+      bad |= (v != v) | ((fabsf(v) > big) << 1);
     }
   } else {
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
       const float v = g[i];
       acc += v * v;
-      bad |= (v != v) | ((fabsf(v) > 1e5f) << 1);
+      bad |= (v != v) | ((fabsf(v) > big) << 1);
     }
   }
   acc = block_sum(acc, red);
@@ -122,9 +122,9 @@ __global__ void __launch_bounds__(256) mt_clip_kernel(const ag_mt_entry* __restr
 using namespace ag;
 extern "C" {
 int ag_mt_sqnorm(const ag_mt_entry* table, const int32_t* ct, const int64_t* co, int32_t nchunks, int32_t chunk,
-                 float* sqnorm, int32_t* flags, void* stream) {
+                 float* sqnorm, int32_t* flags, float big, void* stream) {
   AG_CHECK_ARG(table && ct && co && nchunks > 0 && chunk > 0 && sqnorm && flags, "ag_mt_sqnorm: bad args");
-  mt_sqnorm_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(table, ct, co, chunk, sqnorm, flags);
+  mt_sqnorm_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(table, ct, co, chunk, sqnorm, flags, big > 0.f ? big : 1e5f);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

@@ -13,7 +13,7 @@ import torch
 from torch.autograd.function import once_differentiable
 
 from . import kernels as K
-from .plan import pack  # noqa: F401  (re-exported)
+from .plan import pack, wgrad_enabled  # noqa: F401  (pack re-exported)
 
 GPAD = 8        # zero rows either side of the generator's dense channel-last buffer
 DPAD = 3        # zero rows either side of the discriminator's channel-last activations
@@ -75,11 +75,12 @@ class _GenFn(torch.autograd.Function):
         misc = torch.zeros(1024, device=dev, dtype=torch.int32)        # [0:8] barrier, [8] t_end, [16:] per-CTA flags
         u = u_stop.contiguous() if u_stop is not None else None
         # exchange workspace of the TMEM-resident recurrence (include/audiogan_b200.h: ag_lstm_desc.ll_ws)
-        ll_ws = torch.empty(16 * ((B + 31) // 32 * 32) * (H // 2 + F) + 256, device=dev, dtype=torch.uint8)
+        ll_ws = K.lstm_workspace(B, H, F, False, dev) if bf else None
         K.lstm_fwd(B=B, T=Tcap, Tcap=Tcap, H=H, ndir=1, F=F, pre=pre, w1=plan.Poff("w1"), w2=plan.Poff("w2"),
                    b2=plan.Poff("b2"), hbuf=hbuf, gates=gates, cbuf=cbuf, xbuf=xbuf, sbuf=sbuf, u=u, stop=stop,
                    glen=glen, t_end=(misc, 8), barrier=misc, prec=plan.lstm_prec if bf else 0, hbuf16=hbuf16, xbuf16=xbuf16,
-                   reserved2=plan.lstm_flags | 2, ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel())
+                   flags=plan.lstm_flags | 2, ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel() if ll_ws is not None else 0)
+        plan.last_path["g_fwd"] = K.lstm_last_path()
         if u is not None and early_exit_sync:
             T = int(misc[8].item())          # the one host sync per generator pass (audiogan.py:459-460)
         else:
@@ -135,7 +136,7 @@ class _GenFn(torch.autograd.Function):
         dev = plan.device
         H, F, NZ, CT, FP = plan.H, plan.F, plan.NZ, plan.CT, plan.FP
         Lp = L + 2 * GPAD
-        wgrad = ctx.needs_input_grad[2]
+        wgrad = ctx.needs_input_grad[2] and wgrad_enabled()
         dx_ext = None
         if gx is not None:
             gx = gx.contiguous()
@@ -198,12 +199,20 @@ class _GenFn(torch.autograd.Function):
         dgates16 = torch.empty(B, Tcap, 4 * H, device=dev, dtype=torch.bfloat16) if bf else None
         dpx16 = torch.empty(B, Tcap, FP, device=dev, dtype=torch.bfloat16) if bf else None
         # reduce-scatter workspace of the TMEM-resident BPTT kernel (include/audiogan_b200.h: ag_lstm_desc.ll_ws)
-        ngr = (B + 15) // 16
-        ll_ws = torch.empty((2 * ngr * (H // 32) * (H + F) * 8 + 2 * ngr * 16 * F + 32) * 8, device=dev, dtype=torch.uint8) if bf else None
+        ll_ws = K.lstm_workspace(B, H, F, True, dev) if bf else None
         K.lstm_bwd(B=B, T=T, Tcap=Tcap, H=H, ndir=1, F=F, gates=gates, cbuf=cbuf, xbuf=xbuf, dx_ext=dx_ext,
                    ds_ext=ds_ext, dgates=dgates, dpx=dpx, w1t=plan.Poff("w1t"), wxt=plan.Poff("wxt"), barrier=misc,
-                   prec=plan.lstm_prec if bf else 0, dgates16=dgates16, dpx16=dpx16, reserved2=plan.lstm_flags | 2,
-                   ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel() if bf else 0)
+                   prec=plan.lstm_prec if bf else 0, dgates16=dgates16, dpx16=dpx16, flags=plan.lstm_flags | 2,
+                   ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel() if ll_ws is not None else 0)
+        plan.last_path["g_bwd"] = K.lstm_last_path()
+        # REINFORCE (audiogan.py:900-908): the score-function gradient of the stop logits reaches the stop head's weight and
+        # bias ONLY (the reference freezes every other generator parameter for that backward), so it joins column F of dpx
+        # after the BPTT has run -- it feeds row F of the [wp; ws] weight-gradient GEMM below and nothing else.
+        r = plan.__dict__.pop("stopper_ds", None)
+        if r is not None and wgrad:
+            K.copy3d((dpx, F), (Tcap * FP, FP, 0), r, (r.stride(0), r.stride(1), 0), B, T, 1, accumulate=True)
+            if bf:
+                K.copy3d((dpx16, F), (Tcap * FP, FP, 0), r, (r.stride(0), r.stride(1), 0), B, T, 1, accumulate=True)
         # in bf16 mode the batched GEMMs read the kernels' bf16 shadow copies (half the operand traffic)
         dgo, hbo, xbo, dpo = (dgates16, hbuf16, xbuf16, dpx16) if bf else (dgates, hbuf, xbuf, dpx)
         if wgrad:
@@ -263,7 +272,7 @@ class _DiscCNNFn(torch.autograd.Function):
         plan, struct, acts, Ts, lens = ctx.plan, ctx.struct, ctx.acts, ctx.Ts, ctx.lens
         dev = plan.device
         B = acts[0].shape[0]
-        wgrad = ctx.needs_input_grad[2]
+        wgrad = ctx.needs_input_grad[2] and wgrad_enabled()
         need_dx = ctx.needs_input_grad[3]
         chans = [1] + [c for (_, _, c) in struct]
         dX = None                   # internal gradient wrt acts[i+1], padded geometry
@@ -363,7 +372,8 @@ class _DiscTailFn(torch.autograd.Function):
         cbuf = _empty(B, Tm, 2 * H, device=dev)
         misc = torch.zeros(16, device=dev, dtype=torch.int32)
         K.lstm_fwd(B=B, T=Tm, Tcap=Tm, H=H, ndir=2, F=0, pre=pre, w1=plan.Poff("w1"), hbuf=hbuf, gates=gates, cbuf=cbuf,
-                   len=nfr, barrier=misc, prec=plan.lstm_prec if bf else 0, hbuf16=hbuf16, reserved2=plan.lstm_flags)
+                   len=nfr, barrier=misc, prec=plan.lstm_prec if bf else 0, hbuf16=hbuf16, flags=plan.lstm_flags)
+        plan.last_path["d_fwd"] = K.lstm_last_path()
         # residual_net + classifier on the (B*Tm) rows (audiogan.py:547-549); same row geometry as hbuf
         geo = (Tm, (Tm + 2) * S, S)
         # bf16 mode: the tail's activations live in HBM as bf16 (they only feed tensor-core GEMMs, whose throughput is
@@ -395,7 +405,7 @@ class _DiscTailFn(torch.autograd.Function):
         dev = plan.device
         S, H, E = plan.S, plan.H, plan.E
         ldi = Cf + E + 2
-        wgrad = ctx.needs_input_grad[1]
+        wgrad = ctx.needs_input_grad[1] and wgrad_enabled()
         M = B * Tm
         g = g.contiguous()
         geo = (Tm, (Tm + 2) * S, S)
@@ -428,7 +438,8 @@ class _DiscTailFn(torch.autograd.Function):
         dgates16 = torch.empty(B, Tm, 8 * H, device=dev, dtype=torch.bfloat16) if bf else None
         K.lstm_bwd(B=B, T=Tm, Tcap=Tm, H=H, ndir=2, F=0, gates=gates, cbuf=cbuf, len=nfr, dh_ext=(dh_ext, S),
                    dh_ext_bs=(Tm + 2) * S, dgates=dgates, w1t=plan.Poff("w1t"), barrier=misc,
-                   prec=plan.lstm_prec if bf else 0, dgates16=dgates16, reserved2=plan.lstm_flags)
+                   prec=plan.lstm_prec if bf else 0, dgates16=dgates16, flags=plan.lstm_flags)
+        plan.last_path["d_bwd"] = K.lstm_last_path()
         dgo, hbo = (dgates16, hbuf16) if bf else (dgates, hbuf)
         dgsum = None
         if wgrad or ctx.needs_input_grad[3]:

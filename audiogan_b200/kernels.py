@@ -94,6 +94,22 @@ def lstm_bwd(**kw):
     A.call("ag_lstm_bwd", C.byref(d), A.stream())
 
 
+def lstm_workspace(B, H, F, bwd, device):
+    """`ll_ws` for the TMEM-resident generator recurrence, sized by the library (ag_lstm_workspace_bytes); None when the shape
+    does not run there (the call then uses a kernel family that needs no workspace)."""
+    d = A.LstmDesc()
+    d.B, d.H, d.F, d.ndir, d.prec = B, H, F, 1, 1
+    n = A.lib().ag_lstm_workspace_bytes(C.byref(d), 1 if bwd else 0)
+    if n < 0:
+        raise A.AudioganError("ag_lstm_workspace_bytes failed (%d)" % n)
+    return torch.empty(n, device=device, dtype=torch.uint8) if n > 0 else None
+
+
+def lstm_last_path():
+    """Kernel family (and decline reason, if any) of the last lstm_fwd / lstm_bwd call on this thread."""
+    return A.lib().ag_lstm_last_path().decode("utf-8", "replace")
+
+
 def gather(dst, src, idx):
     A.call("ag_gather", addr(dst), addr(src), addr(idx), idx.numel(), _dtype_of(dst), A.stream())
 
@@ -177,11 +193,9 @@ def zero_pads(buf, head, tail0):
     """zero rows [0, head) and [tail0, rows) of every batch of a contiguous [B, rows, C] tensor."""
     Bn, rows = buf.shape[0], buf.shape[1]
     rb = buf[0, 0].numel() * buf.element_size()
-    if rb % 16 == 0 and buf.is_contiguous() and buf.data_ptr() % 16 == 0:
-        A.call("ag_zero_pads", addr(buf), Bn, rows, rb, head, tail0, A.stream())
-    else:
-        buf[:, :head].zero_()
-        buf[:, tail0:].zero_()
+    if not buf.is_contiguous():
+        raise ValueError("zero_pads needs a contiguous [B, rows, ...] buffer")
+    A.call("ag_zero_pads", addr(buf), Bn, rows, rb, head, tail0, A.stream())
 
 
 def rowgroup_sum(src, out, B, T, N):
@@ -199,6 +213,11 @@ def bce_bwd(x, tgt, w, gout, dx, B, T):
 def bce_const_fused(x, ld, length, target, sign, loss_mean, loss_ps, dlogits, stats, B, T):
     A.call("ag_bce_const_fused", addr(x), ld, addr(length), float(target), float(sign), addr(loss_mean), addr(loss_ps),
            addr(dlogits), addr(stats), B, T, A.stream())
+
+
+def reinforce_dlogit(s, s_ld, stop, stop_ld, loss_ps, glen, baseline_in, baseline_out, out, out_ld, B, T):
+    A.call("ag_reinforce_dlogit", addr(s), s_ld, addr(stop), stop_ld, addr(loss_ps), addr(glen), addr(baseline_in),
+           addr(baseline_out), addr(out), out_ld, B, T, A.stream())
 
 
 def wn_table(entries, device):

@@ -196,6 +196,7 @@ class Generator(_PlanOwner):
         token = P.pack(plan)
         x, s, stop, glen = E._GenFn.apply(plan, self._struct, token, zc1, u_stop, self.early_exit_sync)
         stop_list = list(stop.long().unsqueeze(2).unbind(1))
+        s._ag_stop, s._ag_glen = stop, glen          # raw int32 device copies for the REINFORCE kernel (train.g_update)
         out_len = glen.long() * self._frame_size
         if u_stop is None:
             # no stop is ever drawn: every sample runs all frames.  The host copy rides along so that a following

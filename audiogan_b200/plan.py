@@ -21,6 +21,30 @@ from . import kernels as K
 
 _ALIGN = 64     # elements: every region starts 256-byte aligned
 
+# Weight-gradient work is decided at BACKWARD time.  ctx.needs_input_grad is fixed when the forward runs, so a
+# ``torch.autograd.grad(loss, x)`` pass over a graph whose parameters require grad (x_grad_norm audiogan.py:769-770, the FGSM
+# moves :145 and :131) would otherwise accumulate weight gradients into plan.gpflat that no _PackFn.backward consumes -- the
+# reference never lets autograd.grad touch p.grad.  The loop helpers wrap those calls in ``no_weight_grads()``.
+_wgrad_off = 0
+
+
+class no_weight_grads:
+    """Context manager: backward passes run inside it produce data gradients only (no weight gradients, no early all-reduce)."""
+
+    def __enter__(self):
+        global _wgrad_off
+        _wgrad_off += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _wgrad_off
+        _wgrad_off -= 1
+        return False
+
+
+def wgrad_enabled():
+    return _wgrad_off == 0
+
 
 def _round(n, a=_ALIGN):
     return (n + a - 1) // a * a
@@ -95,6 +119,8 @@ class NetPlan:
         self.lstm_flags = 1 if os.environ.get("AUDIOGAN_LSTM", "") == "grid" else 0
         # data-parallel: a dist.GradSync that all-reduces packed weight-gradient regions while backward is still running
         self.early_sync = None
+        # kernel family (+ decline reason) the recurrent calls of the last pass ran on: {"g_fwd" | "g_bwd" | "d_fwd" | "d_bwd": str}
+        self.last_path = {}
 
     # -- declaration ----------------------------------------------------------------------
     def weight(self, name, v, g=None):

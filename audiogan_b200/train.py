@@ -6,11 +6,14 @@ multi-tensor optimizer with the reference's per-tensor clip, and the loop helper
 tests read side by side; they run the reference's call pattern on the drop-in modules
 (``Generator`` / ``Discriminator`` forward, ``loss.backward()``, clip, optimizer step).
 """
+import collections
+
 import torch
 from torch.autograd.function import once_differentiable
 
 from . import kernels as K
 from . import _abi as A
+from .plan import no_weight_grads
 from .modules import (binary_cross_entropy_with_logits_per_sample, calc_dists, length_mask, cat_lengths)  # noqa: F401
 
 _CHUNK = 65536
@@ -57,22 +60,32 @@ class _MT:
         self._tab, self._tab_key = raw.to(self.device, non_blocking=True), key
         return self._tab
 
-    def sqnorms(self, table):
+    def sqnorms(self, table, grad_scale=1.0):
+        """per-tensor sum of squares + NaN / |g * grad_scale| > 1e5 flags (check_grad's test on the gradient the optimizer
+        will see: after a summed all-reduce the stored values are world x the mean gradient)."""
         self.sqnorm.zero_()
         self.flags.zero_()
         A.call("ag_mt_sqnorm", K.addr(table), K.addr(self.chunk_tensor), K.addr(self.chunk_off), self.nchunks, _CHUNK,
-               K.addr(self.sqnorm), K.addr(self.flags), A.stream())
+               K.addr(self.sqnorm), K.addr(self.flags), 1e5 / float(grad_scale), A.stream())
 
 
-_mt_cache = {}
+# chunk tables for check_grad / clip_grad on caller-supplied parameter lists: a small LRU keyed by the parameters' identity
+# (weak references would not do: torch Parameters hash by identity but a list of them is not weak-referenceable)
+_MT_CACHE_MAX = 8
+_mt_cache = collections.OrderedDict()
 
 
 def _mt_for(params):
     params = list(params)
     key = tuple(id(p) for p in params)
     mt = _mt_cache.get(key)
-    if mt is None or mt.device != params[0].device:
+    if mt is not None and (mt.device != params[0].device or any(a is not b for a, b in zip(mt.params, params))):
+        mt = None                               # ids were recycled by other tensors
+    if mt is None:
         mt = _mt_cache[key] = _MT(params)
+    _mt_cache.move_to_end(key)
+    while len(_mt_cache) > _MT_CACHE_MAX:
+        _mt_cache.popitem(last=False)
     return mt
 
 
@@ -126,7 +139,7 @@ class FusedRMSprop:
         tab = mt.table(self.s1, self.s2)
         sq = None
         if clip > 0 or check:
-            mt.sqnorms(tab)
+            mt.sqnorms(tab, grad_scale)
             sq = mt.sqnorm
             self.last_norm = sq.sqrt().sum() * grad_scale
         if check:
@@ -181,7 +194,8 @@ def masked_bce_mean(logits, nframes, target, sign=1.0):
 def adversarial_movement_d(d, data, data_len, embed_d, target, weight, scale=1e-3):     # audiogan.py:139-150
     cls, _, _, nframes = d(data, data_len, embed_d)
     loss = binary_cross_entropy_with_logits_per_sample(cls, target, weight) / nframes.to(cls.device).float()
-    grad = torch.autograd.grad(loss, data, grad_outputs=torch.ones_like(loss))[0]
+    with no_weight_grads():           # autograd.grad never touches p.grad in the reference: data gradient only
+        grad = torch.autograd.grad(loss, data, grad_outputs=torch.ones_like(loss))[0]
     return ((grad > 0).float() - (grad < 0).float()) * scale
 
 
@@ -194,7 +208,8 @@ def adversarially_sample_z(g, d, z, embed_g, embed_d, noise, g_optim="boundary_s
     tgt = torch.full_like(cls_g, 0.5 if g_optim == "boundary_seeking" else 0.0)
     weight = length_mask(cls_g.shape, nframes_g)
     loss = binary_cross_entropy_with_logits_per_sample(cls_g, tgt, weight) / nframes_g.to(cls_g.device).float()
-    grad = torch.autograd.grad(loss, z, grad_outputs=torch.ones_like(loss))[0]
+    with no_weight_grads():
+        grad = torch.autograd.grad(loss, z, grad_outputs=torch.ones_like(loss))[0]
     advers = ((grad > 1e-9).float() - (grad < -1e-9).float()) * scale
     return (z + advers).detach()
 
@@ -274,7 +289,8 @@ def d_update(g, d, opt_d, batch, clip=1.0, fgsm=False, with_x_grad_norm=False, c
     cls_g, _, _, nframes_g = d(fake, fake_len, batch["c_d2"])                    # :761
     loss_g, loss_g_ps, st_g = masked_bce_mean(cls_g, nframes_g, 0.0, -1.0)       # :762-766, :780-782
     if with_x_grad_norm:                                                        # :769-775
-        gx = torch.autograd.grad(loss_g, fake, retain_graph=True)[0] * fake.shape[0]
+        with no_weight_grads():
+            gx = torch.autograd.grad(loss_g, fake, retain_graph=True)[0] * fake.shape[0]
         out["x_grad_norm"] = ((gx.norm(2, 1) ** 2) / nframes_g.to(gx.device).float()).mean()
     loss = loss_d + loss_g                                                      # :783
     opt_d.zero_grad()
@@ -287,9 +303,13 @@ def d_update(g, d, opt_d, batch, clip=1.0, fgsm=False, with_x_grad_norm=False, c
 
 
 def g_update(g, d, opt_g, batch, clip=0.1, g_optim="boundary_seeking", feature_matching=False, adv_z=False,
-             check=False, lambda_fp=1.0, grad_sync=None):
-    """One generator update, audiogan.py:816-921 (core step: feature_matching = adv_z = False).
-    batch keys as oracle.restated.g_update."""
+             check=False, lambda_fp=1.0, grad_sync=None, reinforce=False, baseline=None):
+    """One generator update, audiogan.py:816-921 (core step: feature_matching = adv_z = reinforce = False).
+    batch keys as oracle.restated.g_update.
+
+    ``reinforce=True`` adds the REINFORCE update of the stop head (:873-908): reward = -loss per sample, ``baseline`` the
+    running EMA(0.5) of the mean reward (None on the first call; a 1-element device tensor afterwards -- the returned
+    ``baseline`` is passed back in on the next call, no host read), score-function gradient into ``g.stopper`` only."""
     _set_requires_grad(g, True)                                                 # :816-819
     _set_requires_grad(d, False)
     z = batch["z"]
@@ -309,10 +329,20 @@ def g_update(g, d, opt_g, batch, clip=0.1, g_optim="boundary_seeking", feature_m
     tgt = 0.5 if g_optim == "boundary_seeking" else 0.0                          # :857-860
     _loss, loss_ps, _ = masked_bce_mean(cls_g, nframes_g, tgt, -1.0)             # :864, :897
     loss = _loss if fp is None else _loss + fp * lambda_fp                      # :898
+    new_baseline = baseline
+    if reinforce:                                                               # :873-885, :900-901
+        Bn, Tn = fake_s.shape
+        if baseline is not None and not torch.is_tensor(baseline):
+            baseline = torch.full((1,), float(baseline), device=fake_s.device)
+        new_baseline = torch.empty(1, device=fake_s.device)
+        ds = torch.empty(Bn, Tn, device=fake_s.device)
+        K.reinforce_dlogit(fake_s.detach(), fake_s.stride(0), fake_s._ag_stop, fake_s._ag_stop.stride(0), loss_ps,
+                           fake_s._ag_glen, baseline, new_baseline, ds, Tn, Bn, Tn)
+        g._get_plan().stopper_ds = ds            # consumed by the generator's backward (stop head only, :904-908)
     opt_g.zero_grad()
     loss.backward()                                                             # :902-903
     scale = grad_sync(opt_g.params) if grad_sync is not None else 1.0
     gn = opt_g.step(clip=clip, grad_scale=scale, check=check)                   # :909-921 fused
     _set_requires_grad(d, True)
     return dict(loss=_loss.detach(), feature_penalty=fp, g_grad_norm=gn, cls_g=cls_g.detach(), fake=fake.detach(),
-                loss_ps=loss_ps)
+                loss_ps=loss_ps, baseline=new_baseline, fake_len=fake_len)

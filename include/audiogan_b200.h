@@ -134,8 +134,8 @@ typedef struct ag_lstm_desc {
   /* bf16 mode (prec = 1): the recurrent products run on tensor cores (bf16 operands, fp32 accumulate, fp32 state).
    * The kernels keep bf16 shadow copies of the per-step operands, same shapes as their fp32 twins:
    * hbuf16 / xbuf16 (forward writes, rows 0 / T+1 zero on entry), dgates16 / dpx16 (backward writes). */
-  int32_t prec, reserved2;   /* reserved2 bit 0: use the grid-barrier kernels only (no cluster / TMEM-resident kernels);
-                              * bit 1: allow the TMEM-resident generator kernel (needs ll_ws) */
+  int32_t prec, flags;       /* flags bit 0 (AG_LSTM_GRID_ONLY): use the grid-barrier kernels only (no cluster / TMEM-resident
+                              * kernels); bit 1 (AG_LSTM_ALLOW_TMEM): allow the TMEM-resident generator kernel (needs ll_ws) */
   void* hbuf16; void* xbuf16; void* dgates16; void* dpx16;
   long long* dbg;        /* optional [gridDim][8] cycle counters per CTA: gemm, cell, barrier, phase2/A, total (profiling aid) */
   /* Workspace of the TMEM-resident generator kernel (bf16 mode, F > 0): the per-step h_t / x_t exchange between the CTAs
@@ -144,8 +144,17 @@ typedef struct ag_lstm_desc {
   void* ll_ws; int64_t ll_ws_bytes;
 } ag_lstm_desc;
 
+#define AG_LSTM_GRID_ONLY 1
+#define AG_LSTM_ALLOW_TMEM 2
 int ag_lstm_fwd(const ag_lstm_desc* d, void* stream);
 int ag_lstm_bwd(const ag_lstm_desc* d, void* stream);
+/* Bytes of `ll_ws` the TMEM-resident generator kernels need for this descriptor's (B, H, F) -- forward (bwd == 0) or BPTT
+ * (bwd != 0); 0 when the shape runs on a path that needs no workspace.  Only B, H, F, ndir and prec are read. */
+int64_t ag_lstm_workspace_bytes(const ag_lstm_desc* d, int32_t bwd);
+/* Which kernel family the last ag_lstm_fwd / ag_lstm_bwd call ON THIS THREAD ran on, and -- when a bf16-mode call fell off
+ * the fast (cluster / TMEM-resident) kernels -- why: e.g. "cluster", "tmem", "grid-bf16 (tmem declined: 8 groups x 32
+ * slices > 148 SMs)".  With AUDIOGAN_VERBOSE=1 in the environment every distinct decline is also printed to stderr once. */
+const char* ag_lstm_last_path(void);
 /* Non-feedback sequences in bf16 mode (prec >= 1, F == 0, H in {128, 256, 512}: the discriminator's BiLSTM) run on
  * cluster-resident kernels: one thread-block cluster of H/32 CTAs keeps a full copy of one direction's recurrent
  * weights in distributed shared memory and carries a slice of <= 32 samples through all T steps with tcgen05 MMAs,
@@ -195,6 +204,15 @@ int ag_bce_bwd(const float* x, const float* tgt, const float* w, const float* go
 int ag_bce_const_fused(const float* x, int64_t ld, const int32_t* len, float target, float sign,
                        float* loss_mean, float* loss_ps, float* dlogits, float* stats,
                        int64_t B, int64_t T, void* stream);
+
+/* REINFORCE gradient of the generator's stop head (audiogan.py:873-908: reward = -loss, EMA(0.5) baseline,
+ * fake_stop.reinforce(reward[:, i]), stopper-only backward).  reward_b = -loss_ps[b]; *baseline_out = mean_b(reward) when
+ * baseline_in is NULL, else 0.5 * *baseline_in + 0.5 * mean_b(reward) (device scalars, must not alias);
+ * out[b*out_ld + t] = -(reward_b - *baseline_out) * (stop[b,t] - sigmoid(s[b,t])) for t < glen[b] (frames, stop inclusive),
+ * 0 for glen[b] <= t < T: the gradient of -sum (reward - baseline) * log p(stop_bt) with respect to the stop logits. */
+int ag_reinforce_dlogit(const float* s, int64_t s_ld, const int32_t* stop, int64_t stop_ld, const float* loss_ps,
+                        const int32_t* glen, const float* baseline_in, float* baseline_out, float* out, int64_t out_ld,
+                        int64_t B, int64_t T, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Activation-gradient assembly (backward of LeakyReLU + length mask + dense skip,
@@ -275,7 +293,7 @@ int ag_frames_to_slot(void* dst, int32_t dst_dtype, int64_t d_bs, int64_t d_rs, 
                       int64_t L, void* stream);
 /* Zero the pad rows [0, head) and [tail0, rows) of every batch of a packed channel-last buffer [B, rows, row_bytes] (the zero
  * padding every conv view relies on, audiogan.py:272 / :490 `padding=`): one launch instead of two strided fills.
- * row_bytes % 16 == 0, buf 16-byte aligned. */
+ * 16-byte stores when row_bytes % 16 == 0 and buf is 16-byte aligned, else 4- / 2-byte stores (row_bytes % 2 == 0). */
 int ag_zero_pads(void* buf, int64_t B, int64_t rows, int64_t row_bytes, int64_t head, int64_t tail0, void* stream);
 /* out[b, n] = sum_t in[b, t, n]; in: dtype 0 fp32 / 1 bf16 (N even) */
 int ag_rowgroup_sum(const void* in, int32_t dtype, float* out, int64_t B, int64_t T, int64_t N, void* stream);
@@ -286,7 +304,8 @@ int ag_transpose_bct(const float* src, float* dst, int64_t B, int64_t C, int64_t
 /* ------------------------------------------------------------------------------------------
  * Fused multi-tensor optimizer with the reference's per-tensor clip (audiogan.py:232-253,
  * :693-694, :786-788, :909-921).  Table entries in DEVICE memory.
- *   pass 1 (ag_mt_sqnorm): sqnorm[i] = sum g^2, flags[0] |= any NaN, flags[1] |= any |g| > 1e5
+ *   pass 1 (ag_mt_sqnorm): sqnorm[i] = sum g^2, flags[0] |= any NaN, flags[1] |= any |g| > big (big <= 0: the reference's
+ *     1e5, audiogan.py:240; data-parallel callers holding an un-normalised SUM over ranks pass 1e5 * world)
  *   pass 2 (ag_mt_rmsprop / ag_mt_adam): g' = g * min(1, clip/||g||) (clip <= 0: none), then
  *     RMSprop: sq = alpha*sq + (1-alpha)*g'^2 ; p -= lr * g' / (sqrt(sq) + eps)
  *     Adam   : m,v moments with bias correction from `step`.
@@ -296,7 +315,7 @@ typedef struct ag_mt_entry {
   int64_t n;
 } ag_mt_entry;
 int ag_mt_sqnorm(const ag_mt_entry* table, const int32_t* chunk_tensor, const int64_t* chunk_off,
-                 int32_t nchunks, int32_t chunk, float* sqnorm, int32_t* flags, void* stream);
+                 int32_t nchunks, int32_t chunk, float* sqnorm, int32_t* flags, float big, void* stream);
 /* clip_grad alone (audiogan.py:243-253): g *= clip/||g|| in place where ||g|| > clip. */
 int ag_mt_clip(const ag_mt_entry* table, const int32_t* chunk_tensor, const int64_t* chunk_off,
                int32_t nchunks, int32_t chunk, const float* sqnorm, float clip, void* stream);

@@ -26,6 +26,9 @@ CASES = {
     "default_b3_l1200_mixed": (3, 1200, False, {}, {}),
     "default_b2_l1600_full": (2, 1600, True, {}, {}),
     "small_h64_b4_l1000_mixed": (4, 1000, False, {"state_size": 64}, {"state_size": 64}),
+    # BASELINE configs[1] geometry (2 s waveforms: T_g = 80 generator frames, T_d = 250 discriminator frames), small batch
+    "default_b4_l16000_full": (4, 16000, True, {}, {}),
+    "default_b4_l16000_mixed": (4, 16000, False, {}, {}),
 }
 
 
@@ -82,9 +85,31 @@ def run_case(name, B, L, full, gk, dk):
     print(name, "loss_g", out["G"]["loss"], "loss_d", out["D"]["loss_d"], "loss_f", out["D"]["loss_f"])
 
 
+def run_embedder():
+    """Embedder (audiogan.py:302-334): the reference class's own parameters (53.6 k floats), inputs and output."""
+    ns = R.load()
+    T.manual_seed(7)
+    ref = ns["Embedder"](output_size=100)
+    chars = T.randint(0, 256, (6, 12))
+    lens = T.tensor([12, 3, 7, 1, 5, 12])
+    with R.py2_tensor_semantics():
+        c = ref(chars, lens)
+        up = T.randn(6, 100)
+        (c * up).sum().backward()
+    os.makedirs(os.path.join(OUT, "aux"), exist_ok=True)
+    T.save({"state_dict": {k: v.clone() for k, v in ref.state_dict().items()}, "chars": chars, "lens": lens, "c": c.detach().clone(),
+            "up": up, "grads": {k: p.grad.clone() for k, p in ref.named_parameters()}},
+           os.path.join(OUT, "aux", "embedder.pt"))
+    print("embedder", float(c.norm()))
+
+
 if __name__ == "__main__":
     warnings.filterwarnings("ignore")
     os.makedirs(OUT, exist_ok=True)
     T.manual_seed(0)
+    only = sys.argv[1:]
     for name, args in CASES.items():
-        run_case(name, *args)
+        if not only or name in only:
+            run_case(name, *args)
+    if not only or "embedder" in only:
+        run_embedder()

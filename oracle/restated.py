@@ -266,7 +266,7 @@ def adversarially_sample_z(Pg, Pd, z, embed_g, embed_d, noise, g_optim="boundary
     """z, noise are supplied (the reference draws them at :101, :104)."""
     z = z.detach().clone().requires_grad_(True)
     fake, _, _, fake_len = generator_forward(Pg, embed_g, z=z, u_stop=u_stop)
-    fake = fake + noise
+    fake = fake + noise[:, :fake.shape[1]]
     cls_g, _, _, nframes_g = discriminator_forward(Pd, fake, fake_len, embed_d)
     tgt = T.full_like(cls_g, 0.5 if g_optim == "boundary_seeking" else 0.0)
     weight = length_mask(cls_g.shape, nframes_g)
@@ -277,9 +277,9 @@ def adversarially_sample_z(Pg, Pd, z, embed_g, embed_d, noise, g_optim="boundary
 
 
 # ------------------------------------------------------------------------ the two updates
-def _grads_of(loss, params):
+def _grads_of(loss, params, retain_graph=False):
     keys = [k for k, p in params.items() if p.requires_grad]
-    gs = T.autograd.grad(loss, [params[k] for k in keys], allow_unused=True)
+    gs = T.autograd.grad(loss, [params[k] for k in keys], allow_unused=True, retain_graph=retain_graph)
     return {k: (g if g is not None else None) for k, g in zip(keys, gs)}
 
 
@@ -313,7 +313,7 @@ def d_update(Pg, Pd, st_d, batch, lr=1e-4, clip=1.0, fgsm=False, with_x_grad_nor
         fake, _, _, fake_len = generator_forward(Pg, batch["c_g"], z=batch["z"],
                                                  u_stop=batch.get("u_stop"))     # :748
     if not fgsm:
-        fake = (fake + batch["noise_fake"]).detach()                             # :750-751
+        fake = (fake + batch["noise_fake"][:, :fake.shape[1]]).detach()          # :750-751
     else:
         fake = fake.detach().clone().requires_grad_(True)                        # :753-754
         cls_g, _, _, nframes_g = discriminator_forward(Pd, fake, fake_len, batch["c_d2"])
@@ -362,7 +362,7 @@ def g_update(Pg, Pd, st_g, batch, lr=1e-4, clip=0.1, g_optim="boundary_seeking",
         z = adversarially_sample_z(Pg, Pd, z, batch["c_g"], batch["c_d"], batch["noise_adv"],
                                    g_optim=g_optim, u_stop=u_stop)
     fake, fake_s, fake_stop, fake_len = generator_forward(Pg, batch["c_g"], z=z, u_stop=u_stop)   # :841
-    fake = fake + batch["noise_fake"]                                            # :842-843
+    fake = fake + batch["noise_fake"][:, :fake.shape[1]]                         # :842-843 (noise drawn at fake's size)
     cls_g, hs_g, hl_g, nframes_g = discriminator_forward(Pd, fake, fake_len, batch["c_d"])       # :845
     fp = T.zeros((), device=cls_g.device)
     if feature_matching:                                                         # :847-855
@@ -374,16 +374,23 @@ def g_update(Pg, Pd, st_g, batch, lr=1e-4, clip=0.1, g_optim="boundary_seeking",
     loss_ps = bce_with_logits_per_sample(cls_g, tgt, weight) / nframes_g.float()  # :864
     _loss = loss_ps.mean()                                                       # :897
     loss = _loss + fp * lambda_fp                                                # :898
+    grads = _grads_of(loss, Pg, retain_graph=reinforce)                          # :902-903 (retain_graph=True there too)
     if reinforce:                                                                # :873-908
-        # Variable.reinforce() no longer exists: score-function surrogate on the stopper.
-        reward = -loss_ps.detach()
-        baseline = float(reward.mean()) if baseline is None else baseline * 0.5 + float(reward.mean()) * 0.5
-        nf = fake_len // 200
+        # Variable.reinforce() (:901) no longer exists: the stochastic node's backward is restated as the gradient of the
+        # score-function surrogate -sum (reward - baseline) * w_r * log p(stop_t).  The reference runs that backward with
+        # every generator parameter frozen EXCEPT g.stopper's (:904-907), so only the stop head receives it (on top of what
+        # loss.backward() left in .grad): the hidden states are constants here.
+        reward = -loss_ps.detach()                                               # :873
+        baseline = float(reward.mean()) if baseline is None else baseline * 0.5 + float(reward.mean()) * 0.5   # :874
+        nf = fake_len // 200                                                     # :862-863 fake_len / framesize
         w_r = length_mask((fake.shape[0], int(nf.max())), nf)
-        adv = (reward - baseline).unsqueeze(1) * w_r
+        adv = (reward - baseline).unsqueeze(1) * w_r                             # :885
         logp = T.where(fake_stop.bool(), F.logsigmoid(fake_s), F.logsigmoid(-fake_s))
-        loss = loss - (adv * logp[:, :adv.shape[1]]).sum()
-    grads = _grads_of(loss, Pg)                                                  # :902-903
+        surrogate = -(adv * logp[:, :adv.shape[1]]).sum()
+        sk = [k for k in Pg if k.startswith("stopper.")]
+        for k, gr in zip(sk, T.autograd.grad(surrogate, [Pg[k] for k in sk], allow_unused=True)):
+            if gr is not None:
+                grads[k] = gr if grads.get(k) is None else grads[k] + gr
     check_grad(grads.values())                                                   # :909
     gn = clip_grad([g for g in grads.values() if g is not None], clip)           # :910
     out = dict(loss=float(_loss), feature_penalty=float(fp), g_grad_norm=gn, baseline=baseline,

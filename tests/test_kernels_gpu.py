@@ -336,7 +336,7 @@ def test_lstm_bf16_mode_tracks_fp32_kernels(H, B, Tn, ndir, Fr, prec_tc):
 def test_lstm_cluster_kernels_track_fp32_kernels(H, B, Tn):
     """Cluster-resident BiLSTM (csrc/lstm_cluster.cu: TMEM-resident weights, DSMEM exchange; what the discriminator's
     NN.LSTM, audiogan.py:498-503, runs on in bf16 mode) against the fp32 grid-barrier kernels and against the bf16
-    grid-barrier kernels (reserved2 bit 0) on the same inputs, mixed lengths, ragged last slice, several rounds (B = 200)."""
+    grid-barrier kernels (flags bit 0) on the same inputs, mixed lengths, ragged last slice, several rounds (B = 200)."""
     from audiogan_b200 import kernels as Kn, _abi as A
     assert A.lib().ag_lstm_cluster_max_active(H, 0) >= 2 and A.lib().ag_lstm_cluster_max_active(H, 1) >= 2, "cluster launch unavailable"
     T.manual_seed(5)
@@ -356,12 +356,12 @@ def test_lstm_cluster_kernels_track_fp32_kernels(H, B, Tn):
         dgates = T.full((B, Tn, ndir * 4 * H), float("nan"), device=dev)
         dgates16 = T.zeros(B, Tn, ndir * 4 * H, device=dev, dtype=T.bfloat16) if prec else None
         Kn.lstm_fwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=ndir, F=0, pre=pre, w1=w1, hbuf=hbuf, gates=gates, cbuf=cbuf, len=lens,
-                    barrier=misc, prec=prec, reserved2=flags, hbuf16=hbuf16, dbg=dbg)
+                    barrier=misc, prec=prec, flags=flags, hbuf16=hbuf16, dbg=dbg)
         if dbg is not None:
             assert int((dbg[:, 7] > 0).sum()) > 0, "the cluster forward kernel did not run"
             dbg.zero_()
         Kn.lstm_bwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=ndir, F=0, gates=gates, cbuf=cbuf, len=lens, dh_ext=dh_ext, dgates=dgates,
-                    w1t=w1t, barrier=misc, prec=prec, reserved2=flags, dgates16=dgates16, dbg=dbg)
+                    w1t=w1t, barrier=misc, prec=prec, flags=flags, dgates16=dgates16, dbg=dbg)
         if dbg is not None:
             assert int((dbg[:, 7] > 0).sum()) > 0, "the cluster backward kernel did not run"
         out[name] = (hbuf, gates, cbuf, dgates, hbuf16, dgates16)
@@ -403,7 +403,7 @@ def test_lstm_generator_tmem_kernel_tracks_fp32_kernel(B, Tn, stops):
         xbuf16 = T.zeros(B, Tn + 1, Fr, device=dev, dtype=T.bfloat16) if prec else None
         Kn.lstm_fwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=1, F=Fr, pre=pre, w1=w1, w2=w2, b2=b2, hbuf=hbuf, gates=gates, cbuf=cbuf,
                     xbuf=xbuf, sbuf=sbuf, u=u, stop=stop, glen=glen, t_end=(misc, 8), barrier=misc, prec=prec,
-                    reserved2=flags, hbuf16=hbuf16, xbuf16=xbuf16, dbg=dbg, ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel())
+                    flags=flags, hbuf16=hbuf16, xbuf16=xbuf16, dbg=dbg, ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel())
         T.cuda.synchronize()
         if dbg is not None:
             assert int((dbg[:, 7] > 0).sum()) > 0, "the TMEM-resident kernel did not run"
@@ -422,7 +422,7 @@ def test_lstm_generator_tmem_kernel_tracks_fp32_kernel(B, Tn, stops):
         ll_wb = T.empty((2 * ngr * (H // 32) * (H + Fr) * 8 + 2 * ngr * 16 * Fr + 32) * 8, device=dev, dtype=T.uint8)
         Kn.lstm_bwd(B=B, T=te_, Tcap=Tn, H=H, ndir=1, F=Fr, gates=gates, cbuf=cbuf, xbuf=xbuf, dx_ext=dx_ext, ds_ext=ds_ext,
                     dgates=dgates, dpx=dpx, w1t=w1t, wxt=wxt, barrier=T.zeros(1024, dtype=T.int32, device=dev), prec=prec,
-                    reserved2=flags, dgates16=dgates16, dpx16=dpx16, dbg=dbg, ll_ws=ll_wb, ll_ws_bytes=ll_wb.numel())
+                    flags=flags, dgates16=dgates16, dpx16=dpx16, dbg=dbg, ll_ws=ll_wb, ll_ws_bytes=ll_wb.numel())
         T.cuda.synchronize()
         if dbg is not None and B <= 64:
             assert int((dbg[:, 7] > 0).sum()) > 0, "the TMEM-resident BPTT kernel did not run"

@@ -341,7 +341,77 @@ def test_reference_faithful_extras_match_oracle():
     o4 = O.g_update({k: v.clone() for k, v in Pg4.items()}, {k: v.clone() for k, v in Pd4.items()}, {}, gb_r, adv_z=True)
     m4 = ag.g_update(g4, d4, ag.FusedRMSprop(g4.parameters(), lr=1e-4), gb_d, clip=0.1, adv_z=True, check=True)
     R.check("G loss (adv z)", m4["loss"].reshape(1), T.tensor([o4["loss"]]), 2e-3)
+    # ---- the autograd.grad passes above must not leak weight gradients into the update (the reference never lets
+    # autograd.grad touch p.grad): gradient norms and post-step parameters against the oracle's
+    R.check("d_grad_norm (x_grad_norm)", m1["d_grad_norm"].reshape(1), T.tensor([o1["d_grad_norm"]]), 5e-5)
+    for k, p in d.named_parameters():
+        if not noise_only(k):
+            R.check("D after step (x_grad_norm) " + k, p, Pd_r[k], tol=2e-5)
+    R.check("d_grad_norm (fgsm)", m3["d_grad_norm"].reshape(1), T.tensor([o3["d_grad_norm"]]), 5e-3)
+    R.check("g_grad_norm (adv z)", m4["g_grad_norm"].reshape(1), T.tensor([o4["g_grad_norm"]]), 5e-3)
     R.done("extras")
+
+
+def test_autograd_grad_passes_leave_the_update_unchanged():
+    """x_grad_norm (audiogan.py:769-775) is a logging-only data-gradient pass: with it on, the D-update must be the
+    update without it, bit for bit up to atomics order (weight gradients leaked from autograd.grad passes)."""
+    import audiogan_b200 as ag
+    cs = dict(B=3, L=1200, full=True, gk={"state_size": 64}, dk={"state_size": 64})
+    inp = step_inputs(cs["B"], cs["L"], seed=101, full_length=True)
+    di = to_dev(inp)
+    di["u_stop"] = None
+    res = []
+    for flag in (False, True):
+        _, _, g, d = build(cs)
+        m = ag.d_update(g, d, ag.FusedRMSprop(d.parameters(), lr=1e-4), di, clip=1.0, with_x_grad_norm=flag, batched=False)
+        res.append((float(m["d_grad_norm"]), {k: p.detach().clone() for k, p in d.named_parameters()}))
+    assert abs(res[0][0] - res[1][0]) <= 1e-5 * res[0][0], (res[0][0], res[1][0])
+    for k in res[0][1]:
+        if not noise_only(k):
+            assert rel(res[1][1][k], res[0][1][k]) < 1e-6, k
+
+
+@pytest.mark.parametrize("all_stop", [False, True])
+def test_reinforce_stop_head_update_matches_oracle(all_stop):
+    """REINFORCE for the stop head (audiogan.py:873-908) with live stop sampling on supplied uniforms: stop decisions,
+    lengths, loss, EMA baseline over two calls, gradient norm and the post-step stop-head parameters."""
+    import audiogan_b200 as ag
+    cs = dict(B=4, L=1600, full=True, gk={"state_size": 64}, dk={"state_size": 64})
+    Pg = O.init_generator(11, **cs["gk"])            # stop head NOT pinned: p(stop) ~ 0.5 per frame
+    Pd = O.init_discriminator(12, **cs["dk"])
+    g = ag.Generator(embed_size=100, **cs["gk"]); g.load_state_dict(Pg); g = g.cuda()
+    d = ag.Discriminator(embed_size=100, **cs["dk"]); d.load_state_dict(Pd); d = d.cuda()
+    inp = step_inputs(cs["B"], cs["L"], seed=55, full_length=True)
+    gen = T.Generator().manual_seed(9)
+    u = T.rand(cs["B"], 8, generator=gen) * 0.2 + 0.37          # some samples stop early, at different frames
+    if all_stop:
+        u[:, 4] = 0.0                                           # everyone has stopped after frame 5: early exit, T < Tcap
+    else:
+        u[0] = 1.0                                              # sample 0 never stops: runs all 8 frames
+    gb_r = {"c_g": inp["g_c_g"], "c_d": inp["g_c_d"], "z": inp["g_z"], "noise_fake": inp["g_noise_fake"], "u_stop": u}
+    gb_d = to_dev(gb_r)
+    Pg_r = {k: v.clone() for k, v in Pg.items()}
+    Pd_r = {k: v.clone() for k, v in Pd.items()}
+    st_g = {}
+    opt_g = ag.FusedRMSprop(g.parameters(), lr=1e-4)
+    R = Report()
+    base_r, base = None, None
+    for it in range(2):
+        o = O.g_update(Pg_r, Pd_r, st_g, gb_r, reinforce=True, baseline=base_r)
+        m = ag.g_update(g, d, opt_g, gb_d, clip=0.1, reinforce=True, baseline=base, check=True)
+        base_r, base = o["baseline"], m["baseline"]
+        assert tuple(m["fake"].shape) == tuple(o["fake"].shape)
+        lens_r = O.generator_forward({k: v for k, v in Pg.items()}, inp["g_c_g"], z=inp["g_z"], u_stop=u)[3] if it == 0 else None
+        if lens_r is not None:
+            assert T.equal(m["fake_len"].cpu(), lens_r), (m["fake_len"], lens_r)
+            assert len(set(lens_r.tolist())) > 1, "the case must exercise ragged stop lengths"
+        R.check("loss[%d]" % it, m["loss"].reshape(1), T.tensor([o["loss"]]))
+        R.check("baseline[%d]" % it, m["baseline"].reshape(1), T.tensor([o["baseline"]]))
+        R.check("g_grad_norm[%d]" % it, m["g_grad_norm"].reshape(1), T.tensor([o["g_grad_norm"]]), tol=5e-5)
+        for k, p in g.named_parameters():
+            if not noise_only(k):
+                R.check("G after step %d %s" % (it, k), p, Pg_r[k], tol=2e-5 if it == 0 else 1e-4)
+    R.done("reinforce_all_stop" if all_stop else "reinforce")
 
 
 def test_loss_trajectory_tracks_oracle():

@@ -36,14 +36,14 @@ def run(H, B, Tn, ndir=2, mixed=True, time_it=True):
             e = [T.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record()
             Kn.lstm_fwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=ndir, F=0, pre=pre, w1=w1, hbuf=hbuf, gates=gates, cbuf=cbuf, len=lens,
-                        barrier=misc, prec=prec, reserved2=flags, hbuf16=hbuf16, dbg=dbg if name == "cluster" else None)
+                        barrier=misc, prec=prec, flags=flags, hbuf16=hbuf16, dbg=dbg if name == "cluster" else None)
             e[1].record()
             T.cuda.synchronize()
             dfw = dbg.cpu().float().clone()
             dbg.zero_()
             e[1].record()
             Kn.lstm_bwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=ndir, F=0, gates=gates, cbuf=cbuf, len=lens, dh_ext=dh_ext, dgates=dgates,
-                        w1t=w1t, barrier=misc, prec=prec, reserved2=flags, dgates16=dgates16, dbg=dbg if name == "cluster" else None)
+                        w1t=w1t, barrier=misc, prec=prec, flags=flags, dgates16=dgates16, dbg=dbg if name == "cluster" else None)
             e[2].record()
             T.cuda.synchronize()
             dbw = dbg.cpu().float().clone()

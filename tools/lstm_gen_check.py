@@ -43,7 +43,7 @@ def run(H, B, Tn, Fr=200, stops=False, time_it=True, bwd=True):
             e[0].record()
             Kn.lstm_fwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=1, F=Fr, pre=pre, w1=w1, w2=w2, b2=b2, hbuf=hbuf, gates=gates, cbuf=cbuf,
                         xbuf=xbuf, sbuf=sbuf, u=u, stop=stop, glen=glen, t_end=(misc, 8), barrier=misc, prec=prec,
-                        reserved2=flags, hbuf16=hbuf16, xbuf16=xbuf16, dbg=dbg if name == "tmem" else None,
+                        flags=flags, hbuf16=hbuf16, xbuf16=xbuf16, dbg=dbg if name == "tmem" else None,
                         ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel())
             e[1].record()
             T.cuda.synchronize()
@@ -60,7 +60,7 @@ def run(H, B, Tn, Fr=200, stops=False, time_it=True, bwd=True):
             e[1].record()
             if bwd:
                 Kn.lstm_bwd(B=B, T=t_end, Tcap=Tn, H=H, ndir=1, F=Fr, gates=gates, cbuf=cbuf, xbuf=xbuf, dx_ext=dx_ext, ds_ext=ds_ext,
-                            dgates=dgates, dpx=dpx, w1t=w1t, wxt=wxt, barrier=misc2, prec=prec, reserved2=flags, dgates16=dgates16,
+                            dgates=dgates, dpx=dpx, w1t=w1t, wxt=wxt, barrier=misc2, prec=prec, flags=flags, dgates16=dgates16,
                             dpx16=dpx16, dbg=dbg if name == "tmem" else None, ll_ws=ll_wb, ll_ws_bytes=ll_wb.numel())
             e[2].record()
             T.cuda.synchronize()
