@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libaudiogan_b200.so")
 AG_OK = 0
 _ERRNAMES = {-1: "AG_EINVAL", -2: "AG_ECUDA", -3: "AG_ENOTSUP"}
 
-i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+i32, i64, f32, f64, vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
 
 
 class GemmDesc(C.Structure):
@@ -116,8 +116,8 @@ _PROTOS = {
     "ag_transpose_bct": [vp, vp, i64, i64, i64, i64, i64, i32, vp],
     "ag_mt_sqnorm": [vp, vp, vp, i32, i32, vp, vp, f32, vp],
     "ag_mt_clip": [vp, vp, vp, i32, i32, vp, f32, vp],
-    "ag_mt_rmsprop": [vp, vp, vp, i32, i32, vp, f32, f32, f32, f32, f32, vp],
-    "ag_mt_adam": [vp, vp, vp, i32, i32, vp, f32, f32, f32, f32, f32, f32, i32, vp],
+    "ag_mt_rmsprop": [vp, vp, vp, i32, i32, vp, f32, f32, f64, f64, f64, vp],
+    "ag_mt_adam": [vp, vp, vp, i32, i32, vp, f32, f32, f64, f64, f64, f64, i32, vp],
 }
 _PROTOS.update({
     "ag_gemm_nt_tc": [C.POINTER(GemmDesc), vp],

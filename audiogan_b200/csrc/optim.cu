@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) mt_update_kernel(const ag_mt_entry* __res
                                                         const int32_t* __restrict__ chunk_tensor,
                                                         const int64_t* __restrict__ chunk_off, int chunk,
                                                         const float* __restrict__ sqnorm, float clip, float gscale,
-                                                        float lr, float a1, float a2, float eps, float bc1, float bc2) {
+                                                        float lr, float a1, float a2, float om1, float om2, float eps, float bc1, float bc2) {
   const int ti = chunk_tensor[blockIdx.x];
   const int64_t off = chunk_off[blockIdx.x];
   const ag_mt_entry e = table[ti];
@@ -67,11 +67,11 @@ __global__ void __launch_bounds__(256) mt_update_kernel(const ag_mt_entry* __res
   auto upd = [&](float& pv, float gv, float& s1v, float& s2v) {
     gv *= sc;
     if (ADAM) {
-      s1v = a1 * s1v + (1.f - a1) * gv;
-      s2v = a2 * s2v + (1.f - a2) * gv * gv;
+      s1v = a1 * s1v + om1 * gv;
+      s2v = a2 * s2v + om2 * gv * gv;
       pv -= lr * (s1v / bc1) / (sqrtf(s2v / bc2) + eps);
     } else {
-      s1v = a1 * s1v + (1.f - a1) * gv * gv;
+      s1v = a1 * s1v + om1 * gv * gv;
       pv -= lr * gv / (sqrtf(s1v) + eps);
     }
   };
@@ -136,20 +136,23 @@ int ag_mt_clip(const ag_mt_entry* table, const int32_t* ct, const int64_t* co, i
   return AG_OK;
 }
 int ag_mt_rmsprop(const ag_mt_entry* table, const int32_t* ct, const int64_t* co, int32_t nchunks, int32_t chunk,
-                  const float* sqnorm, float clip, float gscale, float lr, float alpha, float eps, void* stream) {
+                  const float* sqnorm, float clip, float gscale, double lr, double alpha, double eps, void* stream) {
   AG_CHECK_ARG(table && ct && co && nchunks > 0 && chunk > 0 && (clip <= 0.f || sqnorm), "ag_mt_rmsprop: bad args");
   mt_update_kernel<false><<<nchunks, 256, 0, (cudaStream_t)stream>>>(table, ct, co, chunk, sqnorm, clip,
-                                                                      gscale == 0.f ? 1.f : gscale, lr, alpha, 0.f, eps, 1.f, 1.f);
+                                                                      gscale == 0.f ? 1.f : gscale, (float)lr, (float)alpha, 0.f,
+                                                                      (float)(1.0 - alpha), 0.f, (float)eps, 1.f, 1.f);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
 int ag_mt_adam(const ag_mt_entry* table, const int32_t* ct, const int64_t* co, int32_t nchunks, int32_t chunk,
-               const float* sqnorm, float clip, float gscale, float lr, float b1, float b2, float eps, int32_t step,
+               const float* sqnorm, float clip, float gscale, double lr, double b1, double b2, double eps, int32_t step,
                void* stream) {
   AG_CHECK_ARG(table && ct && co && nchunks > 0 && chunk > 0 && step > 0 && (clip <= 0.f || sqnorm), "ag_mt_adam: bad args");
-  const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+  // hyper-parameters arrive as doubles so that 1 - beta and the bias corrections are rounded ONCE, as torch.optim does
+  const float bc1 = (float)(1.0 - pow(b1, (double)step)), bc2 = (float)(1.0 - pow(b2, (double)step));
   mt_update_kernel<true><<<nchunks, 256, 0, (cudaStream_t)stream>>>(table, ct, co, chunk, sqnorm, clip,
-                                                                     gscale == 0.f ? 1.f : gscale, lr, b1, b2, eps, bc1, bc2);
+                                                                     gscale == 0.f ? 1.f : gscale, (float)lr, (float)b1, (float)b2,
+                                                                     (float)(1.0 - b1), (float)(1.0 - b2), (float)eps, bc1, bc2);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

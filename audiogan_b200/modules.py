@@ -325,7 +325,10 @@ class Embedder(NN.Module):
         batch_size = chars.size(0)
         seq = self.embed.module(chars).permute(1, 0, 2)                          # :322-324
         packed = pack_padded_sequence(seq, length.detach().cpu(), enforce_sorted=False)   # dynamic_rnn :214-229
-        _, (h, _) = self.rnn(packed)
+        # cuDNN's RNN would otherwise run its GEMMs in TF32 on sm_100 (4e-4 relative on `c`): the conditioning vector is an
+        # fp32 quantity in the reference
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            _, (h, _) = self.rnn(packed)
         h = h.permute(1, 0, 2)                                                   # :333
         return h[:, -2:].reshape(batch_size, self._output_size)                   # :334
 

@@ -321,10 +321,10 @@ int ag_mt_clip(const ag_mt_entry* table, const int32_t* chunk_tensor, const int6
                int32_t nchunks, int32_t chunk, const float* sqnorm, float clip, void* stream);
 int ag_mt_rmsprop(const ag_mt_entry* table, const int32_t* chunk_tensor, const int64_t* chunk_off,
                   int32_t nchunks, int32_t chunk, const float* sqnorm, float clip, float gscale,
-                  float lr, float alpha, float eps, void* stream);
+                  double lr, double alpha, double eps, void* stream);   /* doubles: 1 - alpha is rounded once, as torch.optim does */
 int ag_mt_adam(const ag_mt_entry* table, const int32_t* chunk_tensor, const int64_t* chunk_off,
                int32_t nchunks, int32_t chunk, const float* sqnorm, float clip, float gscale,
-               float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+               double lr, double beta1, double beta2, double eps, int32_t step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -157,7 +157,9 @@ def test_against_reference_golden(path):
     cls_g, hs, hl, nf = d(x + di["g_noise_fake"], ln, di["g_c_d"])
     R.check("cls_g", cls_g, G["cls_g"])
     for h, n in zip(hs, G["cnn_norms"]):
-        assert abs(float(h.detach().cpu().norm()) - n) <= 2e-5 * n
+        # the golden norm is torch's CPU fp32 reduction over the contiguous (B, C, T) tensor (itself 3-6e-5 away from the fp64
+        # norm at this size): reduce our activation in the same memory order
+        assert abs(float(h.detach().float().cpu().contiguous().norm()) - n) <= 2e-5 * n
     loss, _, _ = ag.masked_bce_mean(cls_g, nf, 0.5, -1.0)
     assert abs(float(loss) - G["loss"]) < 2e-6
     loss.backward()
@@ -173,7 +175,10 @@ def test_against_reference_golden(path):
         if gs is None or noise_only(k):
             continue
         check_summary("dG/", k, p.grad, gs)
-    assert abs(float(z.grad.cpu().norm()) - G["dz"]["norm"]) <= 5e-5 * G["dz"]["norm"]
+    # input gradients through 80 / 250 recurrent steps (the L = 16000 fixtures): the reference's own fp32 result is 1e-4 ... 1e-2
+    # (element-wise) away from an fp64 run of the same code at this geometry (tests/test_config1_gpu.py's control band)
+    tol_in = 5e-5 if cs["L"] <= 2000 else 3e-4
+    assert abs(float(z.grad.cpu().norm()) - G["dz"]["norm"]) <= tol_in * G["dz"]["norm"]
     # D-update style losses on real + detached fake
     D = gold["D"]
     g.zero_grad(); d.zero_grad()
@@ -193,8 +198,8 @@ def test_against_reference_golden(path):
         if noise_only(k):
             continue
         check_summary("dD/", k, p.grad, D["grads"][k])
-    assert abs(float(real.grad.cpu().norm()) - D["dreal"]["norm"]) <= 5e-5 * D["dreal"]["norm"]
-    assert abs(float(fk.grad.cpu().norm()) - D["dfake"]["norm"]) <= 5e-5 * D["dfake"]["norm"]
+    assert abs(float(real.grad.cpu().norm()) - D["dreal"]["norm"]) <= tol_in * D["dreal"]["norm"]
+    assert abs(float(fk.grad.cpu().norm()) - D["dfake"]["norm"]) <= tol_in * D["dfake"]["norm"]
     R.done("golden_" + os.path.basename(path)[:-3])
 
 
@@ -407,10 +412,23 @@ def test_reinforce_stop_head_update_matches_oracle(all_stop):
             assert len(set(lens_r.tolist())) > 1, "the case must exercise ragged stop lengths"
         R.check("loss[%d]" % it, m["loss"].reshape(1), T.tensor([o["loss"]]))
         R.check("baseline[%d]" % it, m["baseline"].reshape(1), T.tensor([o["baseline"]]))
-        R.check("g_grad_norm[%d]" % it, m["g_grad_norm"].reshape(1), T.tensor([o["g_grad_norm"]]), tol=5e-5)
+        # The REINFORCE advantage is reward - baseline = a difference of nearly equal numbers (|adv| ~ 1e-3 |reward| on this
+        # case): the cancellation amplifies fp32 rounding of the per-sample losses ~1000x, so the stop head's gradient carries
+        # ~2-4e-4 relative noise on ANY fp32 implementation (measured: the CPU oracle's own fp32 result is 2.4e-4 away from its
+        # fp64 result on stopper.*, 1.7e-6 on proj.*).  stopper.* and the norm sum that contains it are held to 2e-3.
+        R.check("g_grad_norm[%d]" % it, m["g_grad_norm"].reshape(1), T.tensor([o["g_grad_norm"]]), tol=2e-3)
         for k, p in g.named_parameters():
             if not noise_only(k):
-                R.check("G after step %d %s" % (it, k), p, Pg_r[k], tol=2e-5 if it == 0 else 1e-4)
+                R.check("G after step %d %s" % (it, k), p, Pg_r[k],
+                        tol=(1e-4 if k.startswith("stopper.") else 2e-5) if it == 0 else 2e-4)
+        # every raw gradient of the same update (no clipping on either side; the oracle clips its copies in place)
+        Pg_c = {k: v.detach().clone() for k, v in g.state_dict().items()}
+        o_c = O.g_update({k: v.cpu() for k, v in Pg_c.items()}, Pd_r, {}, gb_r, clip=0, reinforce=True, baseline=base_r)
+        g2 = ag.Generator(embed_size=100, **cs["gk"]); g2.load_state_dict(Pg_c); g2 = g2.cuda()
+        ag.g_update(g2, d, ag.FusedRMSprop(g2.parameters(), lr=1e-4), gb_d, clip=0.0, reinforce=True, baseline=base)
+        for k, p in g2.named_parameters():
+            if not noise_only(k) and o_c["grads"].get(k) is not None:
+                R.check("raw dG[%d]/%s" % (it, k), p.grad, o_c["grads"][k], tol=2e-3 if k.startswith("stopper.") else grad_tol(k))
     R.done("reinforce_all_stop" if all_stop else "reinforce")
 
 
