@@ -7,3 +7,4 @@ from .modules import (Generator, Discriminator, Embedder, binary_cross_entropy_w
                       calc_dists, fourth_moment, div_roundup, pin_stopper, G_STRUCT, D_STRUCT)
 from .train import (FusedRMSprop, check_grad, clip_grad, d_update, g_update, masked_bce_mean,  # noqa: F401
                     adversarial_movement_d, adversarially_sample_z)
+from .graph import GraphedStep  # noqa: F401,E402

@@ -99,6 +99,8 @@ _PROTOS = {
     "ag_bce_bwd": [vp, vp, vp, vp, vp, i64, i64, vp],
     "ag_bce_const_fused": [vp, i64, vp, f32, f32, vp, vp, vp, vp, i64, i64, vp],
     "ag_reinforce_dlogit": [vp, i64, vp, i64, vp, vp, vp, vp, vp, i64, i64, i64, vp],
+    "ag_time_moments_fwd": [vp, i32, i64, i64, vp, i64, i64, i64, vp, vp, vp],
+    "ag_time_moments_bwd": [vp, i32, i64, i64, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, i32, vp],
     "ag_ew_grad": [C.POINTER(EwDesc), vp],
     "ag_colsum": [vp, i32, i64, i64, i64, i64, i64, vp, vp],
     "ag_outer_dact": [vp, vp, vp, i32, vp, i32, i64, i64, f32, vp],

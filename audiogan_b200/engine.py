@@ -468,6 +468,95 @@ class _DiscTailFn(torch.autograd.Function):
 
 
 # =========================================================================================
+# Embedder: dynamic_rnn + BiLSTM over the character sequence, last hidden states (audiogan.py:214-229, :325-334)
+# =========================================================================================
+class _EmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, token, x, nfr, len_long):
+        """x (B, T, E) embedded characters; nfr int32 [B] / len_long int64 [B] lengths on the device.  Returns (B, 2H):
+        [h of the forward direction at its last valid step | h of the reverse direction at step 0] (audiogan.py:333-334)."""
+        dev = plan.device
+        B, Tm, E = x.shape
+        H, HP = plan.H, plan.HP
+        x1 = torch.cat([x, torch.ones(B, Tm, 2, device=dev)], 2).contiguous()          # [x | 1 | 1]: both biases ride along
+        pre = _empty(B, Tm, 8 * HP, device=dev)
+        K.gemm_nt(B * Tm, 8 * HP, E + 2, x1, (Tm, Tm * (E + 2), E + 2), plan.Poff("wih"), E + 2, pre, (Tm, Tm * 8 * HP, 8 * HP))
+        hbuf = _zeros(B, Tm + 2, 2 * HP, device=dev)
+        gates = _empty(B, Tm, 8 * HP, device=dev)
+        cbuf = _empty(B, Tm, 2 * HP, device=dev)
+        misc = torch.zeros(16, device=dev, dtype=torch.int32)
+        K.lstm_fwd(B=B, T=Tm, Tcap=Tm, H=HP, ndir=2, F=0, pre=pre, w1=plan.Poff("w1"), hbuf=hbuf, gates=gates, cbuf=cbuf,
+                   len=nfr, barrier=misc, prec=0, flags=1)
+        ar = torch.arange(B, device=dev)
+        out = torch.cat([hbuf[ar, len_long, :H], hbuf[:, 1, HP:HP + H]], 1)            # row t+1 = h_t
+        ctx.plan, ctx.bufs = plan, (x1, nfr, len_long, hbuf, gates, cbuf)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        plan = ctx.plan
+        x1, nfr, len_long, hbuf, gates, cbuf = ctx.bufs
+        dev = plan.device
+        B, Tm, E2 = x1.shape
+        E, H, HP = E2 - 2, plan.H, plan.HP
+        M = B * Tm
+        wgrad = ctx.needs_input_grad[1] and wgrad_enabled()
+        dh_ext = _zeros(B, Tm + 2, 2 * HP, device=dev)
+        ar = torch.arange(B, device=dev)
+        dh_ext[ar, len_long, :H] = g[:, :H]
+        dh_ext[:, 1, HP:HP + H] = g[:, H:]
+        dgates = _empty(B, Tm, 8 * HP, device=dev)
+        misc = torch.zeros(16, device=dev, dtype=torch.int32)
+        K.lstm_bwd(B=B, T=Tm, Tcap=Tm, H=HP, ndir=2, F=0, gates=gates, cbuf=cbuf, len=nfr, dh_ext=(dh_ext, 2 * HP),
+                   dh_ext_bs=(Tm + 2) * 2 * HP, dgates=dgates, w1t=plan.Poff("w1t"), barrier=misc, prec=0, flags=1)
+        flat = lambda n: (M, 0, n)
+        if wgrad:
+            for d in range(2):
+                K.gemm_tn(M, 4 * HP, HP, (dgates, d * 4 * HP), (Tm, Tm * 8 * HP, 8 * HP),
+                          (hbuf, (2 * d) * 2 * HP + d * HP), (Tm, (Tm + 2) * 2 * HP, 2 * HP),
+                          plan.GPoff("whh", d * 4 * HP * HP), HP)
+            K.gemm_tn(M, 8 * HP, E + 2, dgates, flat(8 * HP), x1, flat(E + 2), plan.GPoff("wih"), E + 2)
+        dx = None
+        if ctx.needs_input_grad[2]:
+            dx = _empty(B, Tm, E, device=dev)
+            K.gemm_nt(M, E, 8 * HP, dgates, flat(8 * HP), plan.Poff("wiht"), 8 * HP, dx, flat(E))
+        gtok = torch.zeros(1, device=dev) if wgrad else None
+        return None, gtok, dx, None, None
+
+
+# =========================================================================================
+# calc_dists: per-(sample, channel) time moments of a conv activation (audiogan.py:341-348)
+# =========================================================================================
+class _TimeMomentsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, nfr):
+        """h (B, C, T): a cnn_outputs entry of Discriminator.forward (a permuted view of the kernels' channel-last buffer; any
+        other layout is re-laid-out once); nfr int32 [B] on the device.  Returns q (3, B, C) = (m, s, f)."""
+        B, Cn, Tn = h.shape
+        if h.stride(1) != 1 or h.dtype not in (torch.float32, torch.bfloat16):
+            h = h.float().permute(0, 2, 1).contiguous().permute(0, 2, 1)
+        dev = h.device
+        S1 = torch.empty(B, Cn, device=dev)
+        Q = torch.empty(3, B, Cn, device=dev)
+        K.time_moments_fwd(h, h.stride(0), h.stride(2), nfr, B, Tn, Cn, S1, Q)
+        lf = nfr.to(torch.float32).unsqueeze(1)
+        q = torch.stack([S1 / lf, Q[0].sqrt() / lf, Q[2].pow(0.25) / lf], 0)
+        ctx.save_for_backward(h, nfr, S1, Q)
+        return q
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gq):
+        h, nfr, S1, Q = ctx.saved_tensors
+        B, Cn, Tn = h.shape
+        gq = gq.contiguous().float()
+        dh = torch.empty(B, Tn, Cn, device=h.device, dtype=h.dtype)
+        K.time_moments_bwd(h, h.stride(0), h.stride(2), nfr, B, Tn, Cn, S1, Q, gq[0], gq[1], gq[2], dh)
+        return dh.permute(0, 2, 1), None
+
+
+# =========================================================================================
 # BCE with logits per sample (audiogan.py:187-197)
 # =========================================================================================
 class _BCEFn(torch.autograd.Function):

@@ -220,6 +220,15 @@ def reinforce_dlogit(s, s_ld, stop, stop_ld, loss_ps, glen, baseline_in, baselin
            addr(baseline_out), addr(out), out_ld, B, T, A.stream())
 
 
+def time_moments_fwd(h, h_bs, h_rs, length, B, T, Cn, S1, Q):
+    A.call("ag_time_moments_fwd", addr(h), _dtype_of(h), h_bs, h_rs, addr(length), B, T, Cn, addr(S1), addr(Q), A.stream())
+
+
+def time_moments_bwd(h, h_bs, h_rs, length, B, T, Cn, S1, Q, gm, gs, gf, dh):
+    A.call("ag_time_moments_bwd", addr(h), _dtype_of(h), h_bs, h_rs, addr(length), B, T, Cn, addr(S1), addr(Q), addr(gm), addr(gs),
+           addr(gf), addr(dh), _dtype_of(dh), A.stream())
+
+
 def wn_table(entries, device):
     """entries: list of dicts(v,g,w,norm,dw,dv,dg,rows,cols,kind) with tensors/None -> device table + row_start."""
     arr = (A.WnEntry * len(entries))()

@@ -7,6 +7,7 @@ are fp32 master copies owned by PyTorch; gradients arrive through autograd as us
 reference training loop (``loss.backward()``, ``T.autograd.grad(loss, x)``, ``requires_grad``
 toggling, ``opt.step()``) works unchanged.  CUDA only: there is no CPU fallback.
 """
+import collections
 import math
 
 import torch
@@ -236,25 +237,57 @@ class Discriminator(_PlanOwner):
         plan = self._get_plan()
         dev = plan.device
         B, L = x.shape
-        length_h = host_lengths(length)                              # host copy of the lengths (reference: tonumpy)
-        lens_h, lens_d = [], []
-        nf = length_h
-        for _, s, _ in self._cnn_struct:                              # audiogan.py:533
-            nf = (nf + s - 1) // s
-            lens_h.append(nf)
-        all_d = torch.stack(lens_h, 0).to(torch.int32).to(dev, non_blocking=True)
-        lens_d = [all_d[i] for i in range(len(lens_h))]
-        Tm = int(lens_h[-1].max())
+        lens_h, lens_d, Tm, Tmin, lens_out = _length_tables(length, tuple(s for _, s, _ in self._cnn_struct), dev)
         token = P.pack(plan)
         outs = E._DiscCNNFn.apply(plan, self._cnn_struct, token, x, lens_d)
-        logits = E._DiscTailFn.apply(plan, token, outs[-1], c, lens_d[-1], Tm, int(lens_h[-1].min()))
-        lens_out = [l.to(length.device) for l in lens_h]
+        logits = E._DiscTailFn.apply(plan, token, outs[-1], c, lens_d[-1], Tm, Tmin)
         return logits, list(outs), lens_out, lens_out[-1]
 
 
 # =========================================================================================
 # helper functions the training loop calls (audiogan.py:172-253, :336-359)
 # =========================================================================================
+# per-layer frame counts of a lengths vector (audiogan.py:533: nframes = (nframes + stride - 1) / stride per conv layer): host
+# values (shapes, Tm) and int32 device copies for the kernels' masks.  Keyed by the lengths' VALUES: a training loop sees the same
+# few vectors over and over (full-length batches; the D-update's [real | fake] concatenation), so in steady state a forward
+# pass issues no host<->device copy for its lengths at all (which also keeps it capturable in a CUDA graph).
+_LENS_CACHE = collections.OrderedDict()
+_LENS_CACHE_MAX = 32
+
+
+def _length_tables(length, strides, dev):
+    length_h = host_lengths(length)
+    key = (dev, strides, length.device, tuple(length_h.tolist()))
+    ent = _LENS_CACHE.get(key)
+    if ent is None:
+        lens_h, nf = [], length_h
+        for s in strides:
+            nf = (nf + s - 1) // s
+            lens_h.append(nf)
+        all_d = torch.stack(lens_h, 0).to(torch.int32).to(dev)
+        lens_d = [all_d[i] for i in range(len(lens_h))]
+        lens_out = []
+        for lh, ld in zip(lens_h, lens_d):
+            lo = lh.to(length.device)                        # what the reference returns: LongTensors beside the input lengths
+            lo._ag_host, lo._ag_dev_i32 = lh, ld
+            lens_out.append(lo)
+        ent = (lens_h, lens_d, int(lens_h[-1].max()), int(lens_h[-1].min()), lens_out)
+        _LENS_CACHE[key] = ent
+        while len(_LENS_CACHE) > _LENS_CACHE_MAX:
+            _LENS_CACHE.popitem(last=False)
+    else:
+        _LENS_CACHE.move_to_end(key)
+    return ent
+
+
+def dev_i32(length, device):
+    """int32 device copy of a lengths tensor; free when it came out of Discriminator.forward (cached beside it)."""
+    d = getattr(length, "_ag_dev_i32", None)
+    if d is not None and d.device == torch.device(device):
+        return d
+    return length.to(device, torch.int32)
+
+
 def host_lengths(length):
     """int64 CPU copy of a lengths tensor.  CPU tensors and tensors that carry a host copy (Generator.forward without stop
     sampling, cat_lengths) cost nothing; a bare CUDA tensor costs the device-to-host read the reference also pays."""
@@ -265,19 +298,22 @@ def host_lengths(length):
 
 
 def cat_lengths(parts, device):
-    """torch.cat of lengths tensors on `device`, keeping a host copy when every part has one."""
+    """torch.cat of lengths tensors.  When every part is known on the host (CPU tensors, Generator.forward without stop
+    sampling) the result is a CPU tensor -- Discriminator.forward needs the host values and caches its device tables by
+    them, so nothing is copied; otherwise the parts are concatenated on `device`."""
     hosts = [p if not p.is_cuda else getattr(p, "_ag_host", None) for p in parts]
-    out = torch.cat([p.to(device, non_blocking=True) for p in parts], 0)
     if all(h is not None for h in hosts):
-        out._ag_host = torch.cat([h.to(torch.int64) for h in hosts], 0)
-    return out
+        out = torch.cat([h.to(torch.int64) for h in hosts], 0)
+        out._ag_host = out
+        return out
+    return torch.cat([p.to(device, non_blocking=True) for p in parts], 0)
 
 
 def length_mask(size, length):                                   # audiogan.py:204-211
     """1 where t < length[b]; built on the device (the reference fills it in a host loop and uploads it)."""
-    dev = length.device if length.is_cuda else torch.device("cuda")
+    dev = length.device if length.is_cuda else torch.device("cuda", torch.cuda.current_device())
     ar = torch.arange(size[1], device=dev).unsqueeze(0)
-    return (ar < length.to(dev).reshape(-1, 1)).float()
+    return (ar < dev_i32(length, dev).reshape(-1, 1)).float()
 
 
 def binary_cross_entropy_with_logits_per_sample(input, target, weight=None):    # audiogan.py:187-197
@@ -290,47 +326,63 @@ def fourth_moment(v):                                            # audiogan.py:3
     return (((v - v.mean(0).unsqueeze(0)) ** 4).sum(0)) ** (1 / 4)
 
 
-def calc_dists(hidden_states, hidden_state_lengths):             # audiogan.py:341-359 ("next" row)
+def calc_dists(hidden_states, hidden_state_lengths, gather=None):            # audiogan.py:341-359
+    """Feature-matching statistics of the discriminator's conv activations.  The scans over the activations (197 MB per
+    discriminator pass at configs[1]: per (sample, channel) mean / centred 2nd / centred 4th moment over time, and their
+    gradient back into every activation) are the library's streaming kernels (engine._TimeMomentsFn -> ag_time_moments_*);
+    what is left here works on (B, C) arrays: the batch statistics and the reference's list layout
+    (means + stds + fourths, three (value, std) pairs per layer each).
+
+    ``gather``: data-parallel hook ``q (3, B_local, C) -> q (3, B_global, C)`` (dist.gather_batch) so that the batch
+    statistics are those of the GLOBAL minibatch, as in the reference's single process."""
     means_d, stds_d, fourth_d = [], [], []
     for h, l in zip(hidden_states, hidden_state_lengths):
-        h = h.float()            # bf16 mode hands the conv activations back in their bf16 storage type
-        l = l.to(h.device)
-        mask = length_mask((h.shape[0], h.shape[2]), l)
-        lf = l.unsqueeze(1).float()
-        m = h.sum(2) / lf
-        dev = h - m.unsqueeze(2) * mask.unsqueeze(1)
-        s = ((dev ** 2).sum(2) ** (1. / 2.)) / lf
-        f = ((dev ** 4).sum(2) ** (1. / 4.)) / lf
-        for q in (m, s, f):
-            means_d.append((q.mean(0), q.std(0)))
-            stds_d.append((q.std(0), q.std(0)))
-            fourth_d.append((fourth_moment(q), q.std(0)))
+        nfr = getattr(l, "_ag_dev_i32", None)
+        if nfr is None or nfr.device != h.device:
+            nfr = l.to(h.device, torch.int32)
+        q = E._TimeMomentsFn.apply(h, nfr)                           # (3, B, C): m, s, f of :345-347
+        if gather is not None:
+            q = gather(q)
+        mean, std = q.mean(1), q.std(1)
+        fourth = ((q - mean.unsqueeze(1)) ** 4).sum(1) ** (1 / 4)
+        for i in range(3):
+            means_d.append((mean[i], std[i]))
+            stds_d.append((std[i], std[i]))
+            fourth_d.append((fourth[i], std[i]))
     return means_d + stds_d + fourth_d
 
 
-class Embedder(NN.Module):
+class Embedder(_PlanOwner):
     """Character embedder producing the conditioning vector `c` (audiogan.py:302-334): Embedding(256, 50) ->
-    BiLSTM(50 -> 2 x output/2) over the packed character sequence -> last hidden states (B, output).  A "next" row of
-    SURVEY 8(f): 53.6 k parameters and <= ~20 character steps, far off the hot path -- it runs on stock torch modules
-    (cuDNN); same constructor, forward signature, state_dict keys (`embed.module.weight`, `rnn.*`) as the reference."""
+    BiLSTM(50 -> 2 x output/2) over the character sequence with per-sample lengths (the reference's dynamic_rnn sorts, packs
+    and unpacks, :214-229) -> last hidden states (B, output).  Same constructor, forward signature and state_dict keys
+    (`embed.module.weight`, `rnn.weight_ih_l0`, ..., `rnn.bias_hh_l0_reverse`) as the reference.  The recurrence, its input
+    projection and every gradient run on the library's fp32 kernels (engine._EmbedFn: hidden size padded 50 -> 64 with
+    structural zeros, per-sample lengths in the kernel -- no sort / pack / unpack); the table lookup is torch indexing."""
 
     def __init__(self, output_size=100, char_embed_size=50, num_layers=1, num_chars=256):
         NN.Module.__init__(self)
+        if num_layers != 1:
+            raise NotImplementedError("num_layers > 1 (the reference default is 1)")
         self._output_size, self._char_embed_size, self._num_layers = output_size, char_embed_size, num_layers
         self.embed = _DP(NN.Embedding(num_chars, char_embed_size))
-        self.rnn = NN.LSTM(char_embed_size, output_size // 2, num_layers, bidirectional=True)
+        self.rnn = _PlainLSTM(char_embed_size, output_size // 2)
+
+    def _build_plan(self, dev):
+        return P.build_embedder_plan(self, dev)
+
+    def set_mode(self, mode):
+        """53.6 k parameters, <= ~20 steps: always the fp32 kernels (the conditioning vector is an fp32 quantity)."""
+        return self
 
     def forward(self, chars, length):
-        from torch.nn.utils.rnn import pack_padded_sequence
-        batch_size = chars.size(0)
-        seq = self.embed.module(chars).permute(1, 0, 2)                          # :322-324
-        packed = pack_padded_sequence(seq, length.detach().cpu(), enforce_sorted=False)   # dynamic_rnn :214-229
-        # cuDNN's RNN would otherwise run its GEMMs in TF32 on sm_100 (4e-4 relative on `c`): the conditioning vector is an
-        # fp32 quantity in the reference
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            _, (h, _) = self.rnn(packed)
-        h = h.permute(1, 0, 2)                                                   # :333
-        return h[:, -2:].reshape(batch_size, self._output_size)                   # :334
+        plan = self._get_plan()
+        dev = plan.device
+        x = self.embed.module(chars.to(dev))                                     # :322 (B, T, E)
+        len_long = length.to(dev, torch.int64)
+        Tm = int(host_lengths(length).max())
+        token = P.pack(plan)
+        return E._EmbedFn.apply(plan, token, x[:, :Tm].contiguous(), len_long.to(torch.int32), len_long)
 
 
 def pin_stopper(g, value=30.0):

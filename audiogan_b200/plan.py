@@ -482,3 +482,48 @@ def build_discriminator_plan(mod, device):
         pl.grad_of(name + ".b", g[:, kk])
     pl.S, pl.H, pl.E, pl.Cf = S, H, E, Cf
     return pl.finalize(mod.parameters())
+
+
+# =========================================================================================
+# Embedder plan (audiogan.py:302-334): BiLSTM(50 -> 2 x 50) over <= ~20 characters
+# =========================================================================================
+def build_embedder_plan(mod, device):
+    """The recurrent kernels want a hidden size that tiles onto CTAs: H = output/2 (50 by default) is padded to HP = 64 with
+    structural zeros.  A padded unit has zero weights and zero bias, so its cell stays c = 0.5 c + 0.5 * 0 = 0 and its output
+    h = 0.5 tanh(0) = 0 at every step: the padded network computes the reference's numbers exactly."""
+    H, E = mod._output_size // 2, mod._char_embed_size
+    HP = (H + 15) // 16 * 16
+    pl = NetPlan(device)
+    neg = lambda *shape: torch.full(shape, -1, dtype=torch.int64)
+    r = mod.rnn
+
+    def pad_rows(idx):                       # [4H, X] -> [4HP, X], gate-major
+        out = neg(4 * HP, idx.shape[1])
+        for g in range(4):
+            out[g * HP:g * HP + H] = idx[g * H:(g + 1) * H]
+        return out
+
+    def pad_cols(idx):                       # [R, H] -> [R, HP]
+        return torch.cat([idx, neg(idx.shape[0], HP - H)], 1)
+
+    wih, whh, bih, bhh = [], [], [], []
+    for d, sfx in enumerate(("", "_reverse")):
+        wih.append(pl.weight("rnn.wih%d" % d, getattr(r, "weight_ih_l0" + sfx)))
+        whh.append(pl.weight("rnn.whh%d" % d, getattr(r, "weight_hh_l0" + sfx)))
+        bih.append(pl.weight("rnn.bih%d" % d, getattr(r, "bias_ih_l0" + sfx)))
+        bhh.append(pl.weight("rnn.bhh%d" % d, getattr(r, "bias_hh_l0" + sfx)))
+    pl.layout("wih", torch.cat([pad_rows(torch.cat([wih[d], bih[d][:, None], bhh[d][:, None]], 1)) for d in range(2)], 0))
+    w1 = [pad_rows(pad_cols(whh[d])) for d in range(2)]
+    pl.layout("w1", torch.stack(w1, 0))                                                # [2, 4HP, HP]
+    pl.layout("w1t", torch.stack([w.t() for w in w1], 0))                              # [2, HP, 4HP]
+    pl.layout("wiht", torch.cat([pad_rows(wih[d]).t() for d in range(2)], 1))          # [E, 8HP]
+    gi = pl.grad_region("wih", (8 * HP, E + 2))
+    gh = pl.grad_region("whh", (2, 4 * HP, HP))
+    for d in range(2):
+        rows = torch.cat([torch.arange(d * 4 * HP + g * HP, d * 4 * HP + g * HP + H) for g in range(4)])
+        pl.grad_of("rnn.wih%d" % d, gi[rows, :E])
+        pl.grad_of("rnn.bih%d" % d, gi[rows, E])
+        pl.grad_of("rnn.bhh%d" % d, gi[rows, E + 1])
+        pl.grad_of("rnn.whh%d" % d, gh[d][rows - d * 4 * HP, :H])
+    pl.H, pl.HP, pl.E = H, HP, E
+    return pl.finalize(list(mod.rnn.parameters()))

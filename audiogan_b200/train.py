@@ -14,7 +14,7 @@ from torch.autograd.function import once_differentiable
 from . import kernels as K
 from . import _abi as A
 from .plan import no_weight_grads
-from .modules import (binary_cross_entropy_with_logits_per_sample, calc_dists, length_mask, cat_lengths)  # noqa: F401
+from .modules import (binary_cross_entropy_with_logits_per_sample, calc_dists, length_mask, cat_lengths, dev_i32)  # noqa: F401
 
 _CHUNK = 65536
 
@@ -37,6 +37,7 @@ class _MT:
         self.sqnorm = torch.zeros(len(self.params), device=dev)
         self.flags = torch.zeros(2, dtype=torch.int32, device=dev)
         self.device = dev
+        self._stage, self._stage_ev = [None, None], [None, None]
 
     def table(self, state1=None, state2=None):
         ents, key = [], [id(state1), id(state2)]
@@ -56,8 +57,25 @@ class _MT:
         for i, (p, g, s1, s2) in enumerate(ents):
             arr[i].p, arr[i].g, arr[i].s1, arr[i].s2 = K.addr(p), K.addr(g), K.addr(s1), K.addr(s2)
             arr[i].n = p.numel() if g is not None else 0
-        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
-        self._tab, self._tab_key = raw.to(self.device, non_blocking=True), key
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        # Pinned staging buffers owned by this object (no allocation here).  A table built while a CUDA graph is being captured
+        # (graph.GraphedStep: the gradients then live at the graph pool's addresses) gets its own buffer: the captured copy
+        # node re-reads it on every replay, so eager steps in between must not overwrite it.
+        cap = torch.cuda.is_current_stream_capturing()
+        stage = self._stage[1 if cap else 0]
+        if stage is None or stage.numel() != raw.numel():
+            if cap:
+                raise RuntimeError("FusedRMSprop: run one eager step before capturing a CUDA graph (staging buffers)")
+            self._stage = [torch.empty(raw.numel(), dtype=torch.uint8).pin_memory() for _ in range(2)]
+            stage = self._stage[0]
+        ev = self._stage_ev[1 if cap else 0]
+        if ev is not None and not cap:
+            ev.synchronize()                    # the previous upload from this buffer has left the host
+        stage.copy_(raw)
+        self._tab, self._tab_key = stage.to(self.device, non_blocking=True), key
+        if not cap:
+            self._stage_ev[0] = torch.cuda.Event()
+            self._stage_ev[0].record()
         return self._tab
 
     def sqnorms(self, table, grad_scale=1.0):
@@ -186,14 +204,13 @@ class _BCEConstFn(torch.autograd.Function):
 
 def masked_bce_mean(logits, nframes, target, sign=1.0):
     """-> (loss scalar, per-sample loss (B,), stats = [sum(mask * (sign*x > 0)), sum(mask)])."""
-    nf = nframes.to(logits.device, torch.int32)
-    return _BCEConstFn.apply(logits, nf, float(target), float(sign))
+    return _BCEConstFn.apply(logits, dev_i32(nframes, logits.device), float(target), float(sign))
 
 
 # ------------------------------------------------------------------------------- FGSM helpers
 def adversarial_movement_d(d, data, data_len, embed_d, target, weight, scale=1e-3):     # audiogan.py:139-150
     cls, _, _, nframes = d(data, data_len, embed_d)
-    loss = binary_cross_entropy_with_logits_per_sample(cls, target, weight) / nframes.to(cls.device).float()
+    loss = binary_cross_entropy_with_logits_per_sample(cls, target, weight) / dev_i32(nframes, cls.device).float()
     with no_weight_grads():           # autograd.grad never touches p.grad in the reference: data gradient only
         grad = torch.autograd.grad(loss, data, grad_outputs=torch.ones_like(loss))[0]
     return ((grad > 0).float() - (grad < 0).float()) * scale
@@ -207,7 +224,7 @@ def adversarially_sample_z(g, d, z, embed_g, embed_d, noise, g_optim="boundary_s
     cls_g, _, _, nframes_g = d(fake, fake_len, embed_d)
     tgt = torch.full_like(cls_g, 0.5 if g_optim == "boundary_seeking" else 0.0)
     weight = length_mask(cls_g.shape, nframes_g)
-    loss = binary_cross_entropy_with_logits_per_sample(cls_g, tgt, weight) / nframes_g.to(cls_g.device).float()
+    loss = binary_cross_entropy_with_logits_per_sample(cls_g, tgt, weight) / dev_i32(nframes_g, cls_g.device).float()
     with no_weight_grads():
         grad = torch.autograd.grad(loss, z, grad_outputs=torch.ones_like(loss))[0]
     advers = ((grad > 1e-9).float() - (grad < -1e-9).float()) * scale
@@ -239,7 +256,7 @@ def _d_update_batched(g, d, opt_d, batch, clip, check, grad_sync):
     lens = cat_lengths([real_len, fake_len], x.device)
     c = torch.cat([batch["c_real"], batch["c_d2"]], 0)
     cls, _, _, nf = d(x, lens, c)
-    cls_d, cls_g, nf = cls[:Bn], cls[Bn:], nf.to(cls.device)
+    cls_d, cls_g, nf = cls[:Bn], cls[Bn:], dev_i32(nf, cls.device)
     loss_d, _, st_d = masked_bce_mean(cls_d, nf[:Bn], 0.9, 1.0)                   # :739-742
     loss_g, _, st_g = masked_bce_mean(cls_g, nf[Bn:], 0.0, -1.0)                  # :762-766, :780-782
     loss = loss_d + loss_g                                                      # :783
@@ -291,7 +308,7 @@ def d_update(g, d, opt_d, batch, clip=1.0, fgsm=False, with_x_grad_norm=False, c
     if with_x_grad_norm:                                                        # :769-775
         with no_weight_grads():
             gx = torch.autograd.grad(loss_g, fake, retain_graph=True)[0] * fake.shape[0]
-        out["x_grad_norm"] = ((gx.norm(2, 1) ** 2) / nframes_g.to(gx.device).float()).mean()
+        out["x_grad_norm"] = ((gx.norm(2, 1) ** 2) / dev_i32(nframes_g, gx.device).float()).mean()
     loss = loss_d + loss_g                                                      # :783
     opt_d.zero_grad()
     loss.backward()                                                             # :784-785

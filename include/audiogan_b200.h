@@ -214,6 +214,18 @@ int ag_reinforce_dlogit(const float* s, int64_t s_ld, const int32_t* stop, int64
                         const int32_t* glen, const float* baseline_in, float* baseline_out, float* out, int64_t out_ld,
                         int64_t B, int64_t T, void* stream);
 
+/* calc_dists time moments (audiogan.py:341-348: the per-(sample, channel) statistics over time of a discriminator conv
+ * activation that the feature-matching penalty :848-855 compares between real and generated batches).
+ * h: channel-last activation, element (b, t, c) at h[b*h_bs + t*h_rs + c] (dtype 0 fp32 / 1 bf16), rows t >= len[b] hold zeros.
+ * fwd writes S1[b*C+c] = sum_t h and Q[q*B*C + b*C + c] = sum_{t<len} (h - S1/len)^(2+q), q = 0..2 (two streaming passes; the
+ *   caller finishes m = S1/l, s = sqrt(Q2)/l, f = Q4^(1/4)/l on the (B, C) arrays).
+ * bwd writes dh[b, t, c] (packed [B, T, C], dh_dtype) from the gradients gm, gs, gf (B, C) of m, s, f. */
+int ag_time_moments_fwd(const void* h, int32_t dtype, int64_t h_bs, int64_t h_rs, const int32_t* len, int64_t B, int64_t T,
+                        int64_t C, float* S1, float* Q, void* stream);
+int ag_time_moments_bwd(const void* h, int32_t dtype, int64_t h_bs, int64_t h_rs, const int32_t* len, int64_t B, int64_t T,
+                        int64_t C, const float* S1, const float* Q, const float* gm, const float* gs, const float* gf,
+                        void* dh, int32_t dh_dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Activation-gradient assembly (backward of LeakyReLU + length mask + dense skip,
  * audiogan.py:261-264, :277-283, :532-534), strided element-wise:

@@ -686,3 +686,35 @@ def test_conv1in_dgrad_and_wcolsum(dt):
     out = T.zeros(Kn + 1, device="cuda")
     K.wcolsum(g.cuda(), X.cuda(), M, Kn, out)
     assert rel(out[:Kn], g @ X.float()) < 1e-5 and abs(float(out[Kn]) - float(g.sum())) < 1e-3
+
+
+@pytest.mark.parametrize("dt", [T.float32, T.bfloat16])
+@pytest.mark.parametrize("Bn,Cn,Tn", [(3, 16, 700), (5, 64, 130), (2, 512, 19), (4, 24, 300)])
+def test_time_moments_kernels_match_reference_formula(dt, Bn, Cn, Tn):
+    """ag_time_moments_fwd / _bwd (calc_dists, audiogan.py:341-348) against the reference formula evaluated by torch in
+    float64 on the same (storage-rounded) activation: values and the gradient into the activation."""
+    from audiogan_b200 import engine as E
+    T.manual_seed(3)
+    lens = T.randint(max(1, Tn // 3), Tn + 1, (Bn,))
+    lens[0] = Tn
+    mask = (T.arange(Tn)[None, :] < lens[:, None]).float()
+    buf = (T.randn(Bn, Tn + 6, Cn) * 0.7 + 0.3).to(dt)                 # channel-last storage with pad rows, as the engine's
+    buf[:, 3:3 + Tn] *= mask[:, :, None].to(dt)
+    bufd = buf.cuda()
+    h = bufd[:, 3:3 + Tn].permute(0, 2, 1).requires_grad_(True)         # (B, C, T) view, channel stride 1
+    q = E._TimeMomentsFn.apply(h, lens.cuda().to(T.int32))
+    w = T.randn(3, Bn, Cn, generator=T.Generator().manual_seed(4))
+    (q * w.cuda()).sum().backward()
+    hr = buf[:, 3:3 + Tn].permute(0, 2, 1).double().requires_grad_(True)
+    lf = lens.double().unsqueeze(1)
+    m = hr.sum(2) / lf
+    dv = hr - m.unsqueeze(2) * mask.unsqueeze(1).double()
+    sr = ((dv ** 2).sum(2) ** 0.5) / lf
+    fr = ((dv ** 4).sum(2) ** 0.25) / lf
+    (T.stack([m, sr, fr]) * w.double()).sum().backward()
+    tol = 2e-5
+    for i, ref in enumerate((m, sr, fr)):
+        assert rel(q[i], ref.detach().float()) < tol, (i, rel(q[i], ref.detach().float()))
+    gref = (hr.grad * mask.unsqueeze(1).double()).float()               # the gradient past a sample's length is masked away
+    got = h.grad.float().cpu() * mask.unsqueeze(1)
+    assert rel(got, gref) < (2e-5 if dt == T.float32 else 8e-3), rel(got, gref)

@@ -163,11 +163,17 @@ def test_against_reference_golden(path):
     loss, _, _ = ag.masked_bce_mean(cls_g, nf, 0.5, -1.0)
     assert abs(float(loss) - G["loss"]) < 2e-6
     loss.backward()
+    # The L = 16000 fixtures (T_g = 80, T_d = 250) hold the reference's fp32 CPU gradients, which at that depth are themselves
+    # 1e-4 ... 1e-3 away from an fp64 run of the same code (the control band measured in tests/test_config1_gpu.py, where the
+    # CUDA gradients are judged against fp64): gradient summaries of those fixtures are held to 5e-4 (norm) / 1e-3 (elements).
+    long_seq = cs["L"] > 2000
+
     def check_summary(tag, k, grad, gs):
         # the golden norm was taken with torch's CPU fp32 reduction: use the same reduction on our gradient
-        R.check(tag + k + " |norm|", grad.cpu().norm().reshape(1), T.tensor([gs["norm"]]), tol=grad_tol(k))
+        tn, th = (max(grad_tol(k), 5e-4), max(grad_tol(k), 1e-3)) if long_seq else (grad_tol(k), grad_tol(k))
+        R.check(tag + k + " |norm|", grad.cpu().norm().reshape(1), T.tensor([gs["norm"]]), tol=tn)
         R.rows.append((tag + k + " head", float((grad.flatten()[:32].cpu() - gs["head"]).abs().max()) / (gs["absmax"] + 1e-30)))
-        if R.rows[-1][1] > grad_tol(k):
+        if R.rows[-1][1] > th:
             R.bad.append("%s head err %.3e" % (tag + k, R.rows[-1][1]))
 
     for k, p in g.named_parameters():
@@ -342,6 +348,15 @@ def test_reference_faithful_extras_match_oracle():
     R.check("G loss", m2["loss"].reshape(1), T.tensor([o2["loss"]]), 1e-5)
     R.check("feature_penalty", m2["feature_penalty"].detach().reshape(1), T.tensor([o2["feature_penalty"]]), 1e-4)
     R.check("g_grad_norm (fm)", m2["g_grad_norm"].reshape(1), T.tensor([o2["g_grad_norm"]]), 1e-4)
+    # every raw generator gradient with the penalty's gradient injected into all six conv activations (calc_dists kernels)
+    Pg5, Pd5, g5, d5 = build(cs)
+    o5 = O.g_update({k: v.clone() for k, v in Pg5.items()}, {k: v.clone() for k, v in Pd5.items()}, {}, gb_r,
+                    feature_matching=True, clip=0, lambda_fp=50.0)
+    m5 = ag.g_update(g5, d5, ag.FusedRMSprop(g5.parameters(), lr=1e-4), gb_d, clip=0.0, feature_matching=True, lambda_fp=50.0)
+    R.check("feature_penalty (lambda 50)", m5["feature_penalty"].detach().reshape(1), T.tensor([o5["feature_penalty"]]), 1e-4)
+    for k, p in g5.named_parameters():
+        if not noise_only(k) and o5["grads"].get(k) is not None:
+            R.check("fm dG/" + k, p.grad, o5["grads"][k], tol=max(grad_tol(k), 1e-4))
     Pg4, Pd4, g4, d4 = build(cs)
     o4 = O.g_update({k: v.clone() for k, v in Pg4.items()}, {k: v.clone() for k, v in Pd4.items()}, {}, gb_r, adv_z=True)
     m4 = ag.g_update(g4, d4, ag.FusedRMSprop(g4.parameters(), lr=1e-4), gb_d, clip=0.1, adv_z=True, check=True)
@@ -542,3 +557,41 @@ def test_double_hidden_generator_streams_weights():
             R.check("dG/" + k, sg[k].grad, gr, tol=5e-5)
     R.check("dz", z.grad, grads_r[-1], tol=5e-5)
     R.done("h2048")
+
+
+def test_cuda_graph_step_equals_eager_step():
+    """graph.GraphedStep (the whole core step captured as one CUDA graph) against the eager launch sequence in fp32 mode:
+    same seeds and batches -> same losses and the same parameters after three steps (atomics order only)."""
+    import audiogan_b200 as ag
+    cs = dict(B=3, L=1200, full=True, gk={"state_size": 64}, dk={"state_size": 64})
+    batches = [to_dev(step_inputs(cs["B"], cs["L"], seed=300 + i, full_length=True)) for i in range(4)]
+    for b in batches:
+        b["real_len"] = b["real_len"].cpu()
+
+    def eager_step(g, d, od, og, di):
+        di = dict(di); di["u_stop"] = None
+        m1 = ag.d_update(g, d, od, di, clip=1.0)
+        gb = {"c_g": di["g_c_g"], "c_d": di["g_c_d"], "z": di["g_z"], "noise_fake": di["g_noise_fake"], "u_stop": None}
+        m2 = ag.g_update(g, d, og, gb, clip=0.1)
+        return T.stack([m1["loss_d"], m1["loss_g"], m2["loss"]]).cpu()
+
+    _, _, g1, d1 = build(cs)
+    od1, og1 = ag.FusedRMSprop(d1.parameters(), lr=1e-4), ag.FusedRMSprop(g1.parameters(), lr=1e-4)
+    eager_step(g1, d1, od1, og1, batches[0])                      # GraphedStep's warm-up step
+    le = [eager_step(g1, d1, od1, og1, batches[i]) for i in (1, 2, 3)]
+    _, _, g2, d2 = build(cs)
+    od2, og2 = ag.FusedRMSprop(d2.parameters(), lr=1e-4), ag.FusedRMSprop(g2.parameters(), lr=1e-4)
+    gs = ag.GraphedStep(g2, d2, od2, og2, batches[0], warmup=1)
+    assert gs.launches > 100
+    lg = [gs.run(batches[i])["losses"].clone().cpu() for i in (1, 2, 3)]
+    for a, b in zip(le, lg):
+        assert float((a - b).abs().max()) < 2e-6, (a, b)
+    for (k, p), (_, q) in zip(list(g1.named_parameters()) + list(d1.named_parameters()),
+                              list(g2.named_parameters()) + list(d2.named_parameters())):
+        if not noise_only(k):
+            # three sign-like RMSprop steps: an element whose gradient is rounding noise may step the other way
+            err = (p - q).abs()
+            assert float((err > 1e-6).float().mean()) < 2e-3 and float(err.max()) < 6.1e-3, (k, float(err.max()))
+    with pytest.raises(ValueError):
+        bad = dict(batches[1]); bad["real_len"] = bad["real_len"] - 200
+        gs.load(bad)
