@@ -42,9 +42,10 @@ def _empty(*shape, device, dtype=torch.float32):
 # =========================================================================================
 class _GenFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan, struct, token, zc1, u_stop, early_exit_sync):
+    def forward(ctx, plan, struct, token, zc1, u_stop, early_exit_sync, grad_from=0):
         """zc1: (B, T, NZ+2) = [noise | conditioning | 1 | 1].  Returns (x (B, t*F), s (B, t), stop (B, t) int32,
-        glen (B,) int32)."""
+        glen (B,) int32).  ``grad_from``: only samples [grad_from, B) take part in the backward pass (train.core_step runs the
+        D-update's detached generator pass and the G-update's pass as ONE forward; the first half is never differentiated)."""
         dev = plan.device
         B, Tcap, _ = zc1.shape
         H, F, NZ, CT, FP = plan.H, plan.F, plan.NZ, plan.CT, plan.FP
@@ -120,8 +121,10 @@ class _GenFn(torch.autograd.Function):
         K.conv1out_fwd((Xd, (GPAD - 1) * CT), Lp * CT, CT, 3, plan.Poff("f.w"), plan.Poff("f.b"), xout, B, L)
         s_out = sbuf[:, :T]
         if save:
-            ctx.plan, ctx.struct, ctx.dims = plan, struct, (B, T, Tcap, L)
-            ctx.bufs = (zin, hbuf, xbuf, gates, cbuf, Xd, hh, hbuf16, xbuf16)
+            gf = int(grad_from)
+            ctx.plan, ctx.struct, ctx.dims, ctx.gf = plan, struct, (B - gf, T, Tcap, L), gf
+            cut = (lambda t: t[gf:] if t is not None else None) if gf else (lambda t: t)   # batch-major buffers: a row slice
+            ctx.bufs = (cut(zin), cut(hbuf), cut(xbuf), cut(gates), cut(cbuf), cut(Xd), [cut(h) for h in hh], cut(hbuf16), cut(xbuf16))
         ctx.mark_non_differentiable(stop, glen)
         ctx.set_materialize_grads(False)
         return xout, s_out, stop[:, :T], glen
@@ -131,6 +134,10 @@ class _GenFn(torch.autograd.Function):
     def backward(ctx, gx, gs, _gstop, _glen):
         plan, struct = ctx.plan, ctx.struct
         B, T, Tcap, L = ctx.dims
+        gf = ctx.gf
+        if gf:
+            gx = gx[gf:] if gx is not None else None
+            gs = gs[gf:] if gs is not None else None
         zc1, hbuf, xbuf, gates, cbuf, Xd, hh, hbuf16, xbuf16 = ctx.bufs
         bf = hbuf16 is not None
         dev = plan.device
@@ -225,11 +232,13 @@ class _GenFn(torch.autograd.Function):
                       ones_col=True)
         dzc1 = None
         if ctx.needs_input_grad[3]:
-            dzc1 = _zeros(B, Tcap, NZ + 2, device=dev)
+            dzc1_all = _zeros(B + gf, Tcap, NZ + 2, device=dev)
+            dzc1 = dzc1_all[gf:]
             K.gemm_nt(B * T, NZ, 4 * H, dgo, (T, Tcap * 4 * H, 4 * H), plan.Poff("wzt"), 4 * H,
                       dzc1, (T, Tcap * (NZ + 2), NZ + 2))
+            dzc1 = dzc1_all
         gtok = torch.zeros(1, device=dev) if wgrad else None
-        return None, None, gtok, dzc1, None, None
+        return None, None, gtok, dzc1, None, None, None
 
 
 # =========================================================================================

@@ -40,6 +40,9 @@ class GraphedStep:
     def _step(self):
         di = dict(self.inputs)
         di["u_stop"] = None
+        if not self.d_kwargs and not self.g_kwargs:
+            return train.core_step(self.g, self.d, self.opt_d, self.opt_g, di, clip_d=self.clip_d, clip_g=self.clip_g,
+                                   grad_sync=self.grad_sync)
         m1 = train.d_update(self.g, self.d, self.opt_d, di, clip=self.clip_d, grad_sync=self.grad_sync, **self.d_kwargs)
         gb = {"c_g": di["g_c_g"], "c_d": di["g_c_d"], "z": di["g_z"], "noise_fake": di["g_noise_fake"], "u_stop": None}
         for k in ("real", "real_len", "noise_real", "noise_adv"):

@@ -178,8 +178,9 @@ class Generator(_PlanOwner):
     def _build_plan(self, dev):
         return P.build_generator_plan(self, dev)
 
-    def forward(self, batch_size=None, length=None, z=None, c=None, u_stop="sample"):
+    def forward(self, batch_size=None, length=None, z=None, c=None, u_stop="sample", grad_from=0):
         """Returns (x (B, t*frame), s (B, t) stop logits, stop_list: t LongTensors (B, 1), length (B,) samples).
+        ``grad_from`` (extension, default 0): samples below this index are forward-only (train.core_step).
 
         ``u_stop``: uniforms (B, T) for the stop draw ``stop = u < sigmoid(logit)`` (audiogan.py:445-450 draws
         the same Bernoulli through ``multinomial``); "sample" draws them with torch.rand, None never stops."""
@@ -195,7 +196,7 @@ class Generator(_PlanOwner):
         if isinstance(u_stop, str):
             u_stop = torch.rand(batch_size, nframes, device=dev)
         token = P.pack(plan)
-        x, s, stop, glen = E._GenFn.apply(plan, self._struct, token, zc1, u_stop, self.early_exit_sync)
+        x, s, stop, glen = E._GenFn.apply(plan, self._struct, token, zc1, u_stop, self.early_exit_sync, grad_from)
         stop_list = list(stop.long().unsqueeze(2).unbind(1))
         s._ag_stop, s._ag_glen = stop, glen          # raw int32 device copies for the REINFORCE kernel (train.g_update)
         out_len = glen.long() * self._frame_size

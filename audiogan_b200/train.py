@@ -17,6 +17,7 @@ from .plan import no_weight_grads
 from .modules import (binary_cross_entropy_with_logits_per_sample, calc_dists, length_mask, cat_lengths, dev_i32)  # noqa: F401
 
 _CHUNK = 65536
+_NSTAGE = 4
 
 
 class _MT:
@@ -37,7 +38,7 @@ class _MT:
         self.sqnorm = torch.zeros(len(self.params), device=dev)
         self.flags = torch.zeros(2, dtype=torch.int32, device=dev)
         self.device = dev
-        self._stage, self._stage_ev = [None, None], [None, None]
+        self._stage, self._stage_ev, self._stage_i = None, None, 0
 
     def table(self, state1=None, state2=None):
         ents, key = [], [id(state1), id(state2)]
@@ -58,24 +59,29 @@ class _MT:
             arr[i].p, arr[i].g, arr[i].s1, arr[i].s2 = K.addr(p), K.addr(g), K.addr(s1), K.addr(s2)
             arr[i].n = p.numel() if g is not None else 0
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-        # Pinned staging buffers owned by this object (no allocation here).  A table built while a CUDA graph is being captured
-        # (graph.GraphedStep: the gradients then live at the graph pool's addresses) gets its own buffer: the captured copy
-        # node re-reads it on every replay, so eager steps in between must not overwrite it.
+        # Pinned staging buffers owned by this object (no allocation on the step path): a ring of _NSTAGE for eager steps (a
+        # buffer is rewritten only after the upload issued _NSTAGE table changes ago has left the host) plus one for a table
+        # built while a CUDA graph is being captured (graph.GraphedStep: the gradients then live at the graph pool's addresses;
+        # the captured copy node re-reads that buffer on every replay, so eager steps in between must not overwrite it).
         cap = torch.cuda.is_current_stream_capturing()
-        stage = self._stage[1 if cap else 0]
-        if stage is None or stage.numel() != raw.numel():
+        if self._stage is None or self._stage[0].numel() != raw.numel():
             if cap:
                 raise RuntimeError("FusedRMSprop: run one eager step before capturing a CUDA graph (staging buffers)")
-            self._stage = [torch.empty(raw.numel(), dtype=torch.uint8).pin_memory() for _ in range(2)]
-            stage = self._stage[0]
-        ev = self._stage_ev[1 if cap else 0]
-        if ev is not None and not cap:
-            ev.synchronize()                    # the previous upload from this buffer has left the host
+            self._stage = [torch.empty(raw.numel(), dtype=torch.uint8).pin_memory() for _ in range(_NSTAGE + 1)]
+            self._stage_ev, self._stage_i = [None] * _NSTAGE, 0
+        if cap:
+            stage = self._stage[_NSTAGE]
+            stage.copy_(raw)
+            self._tab, self._tab_key = stage.to(self.device, non_blocking=True), key
+            return self._tab
+        i = self._stage_i = (self._stage_i + 1) % _NSTAGE
+        if self._stage_ev[i] is not None:
+            self._stage_ev[i].synchronize()
+        stage = self._stage[i]
         stage.copy_(raw)
         self._tab, self._tab_key = stage.to(self.device, non_blocking=True), key
-        if not cap:
-            self._stage_ev[0] = torch.cuda.Event()
-            self._stage_ev[0].record()
+        self._stage_ev[i] = torch.cuda.Event()
+        self._stage_ev[i].record()
         return self._tab
 
     def sqnorms(self, table, grad_scale=1.0):
@@ -238,13 +244,17 @@ def _set_requires_grad(module, flag):
         p.requires_grad = flag
 
 
-def _d_update_batched(g, d, opt_d, batch, clip, check, grad_sync):
+def _d_update_batched(g, d, opt_d, batch, clip, check, grad_sync, fake_pass=None):
     """Even-iteration D-update (audiogan.py:723-728, :748-751, :761-788) with the real and the fake pass of the
     discriminator run as ONE pass over the concatenated 2B minibatch.  D has no cross-sample operation, so logits,
-    losses and gradients are those of the two separate calls; the sequential recurrent kernels run once, not twice."""
+    losses and gradients are those of the two separate calls; the sequential recurrent kernels run once, not twice.
+    ``fake_pass``: (fake, fake_len) of a generator pass already run on batch["z"], batch["c_g"] (core_step)."""
     real_len = batch["real_len"]
-    with torch.no_grad():
-        fake, _, _, fake_len = g(z=batch["z"], c=batch["c_g"], u_stop=batch.get("u_stop"))   # :748
+    if fake_pass is None:
+        with torch.no_grad():
+            fake, _, _, fake_len = g(z=batch["z"], c=batch["c_g"], u_stop=batch.get("u_stop"))   # :748
+    else:
+        fake, fake_len = fake_pass
     fake = fake + batch["noise_fake"][:, :fake.shape[1]]                         # :750-751
     real = batch["real"] + batch["noise_real"]                                   # :724-725
     Bn, Lr, Lf = real.shape[0], real.shape[1], fake.shape[1]
@@ -320,7 +330,7 @@ def d_update(g, d, opt_d, batch, clip=1.0, fgsm=False, with_x_grad_norm=False, c
 
 
 def g_update(g, d, opt_g, batch, clip=0.1, g_optim="boundary_seeking", feature_matching=False, adv_z=False,
-             check=False, lambda_fp=1.0, grad_sync=None, reinforce=False, baseline=None):
+             check=False, lambda_fp=1.0, grad_sync=None, reinforce=False, baseline=None, fake_pass=None):
     """One generator update, audiogan.py:816-921 (core step: feature_matching = adv_z = reinforce = False).
     batch keys as oracle.restated.g_update.
 
@@ -333,7 +343,10 @@ def g_update(g, d, opt_g, batch, clip=0.1, g_optim="boundary_seeking", feature_m
     u_stop = batch.get("u_stop")
     if adv_z:                                                                   # :836
         z = adversarially_sample_z(g, d, z, batch["c_g"], batch["c_d"], batch["noise_adv"], g_optim, u_stop=u_stop)
-    fake, fake_s, fake_stop, fake_len = g(z=z, c=batch["c_g"], u_stop=u_stop)   # :841
+    if fake_pass is None:
+        fake, fake_s, fake_stop, fake_len = g(z=z, c=batch["c_g"], u_stop=u_stop)   # :841
+    else:                                     # core_step: this pass already ran (same parameters) beside the D-update's
+        fake, fake_s, fake_stop, fake_len = fake_pass
     fake = fake + batch["noise_fake"][:, :fake.shape[1]]                        # :842-843
     cls_g, hs_g, hl_g, nframes_g = d(fake, fake_len, batch["c_d"])               # :845
     fp = None
@@ -363,3 +376,36 @@ def g_update(g, d, opt_g, batch, clip=0.1, g_optim="boundary_seeking", feature_m
     _set_requires_grad(d, True)
     return dict(loss=_loss.detach(), feature_penalty=fp, g_grad_norm=gn, cls_g=cls_g.detach(), fake=fake.detach(),
                 loss_ps=loss_ps, baseline=new_baseline, fake_len=fake_len)
+
+
+def core_step(g, d, opt_d, opt_g, batch, clip_d=1.0, clip_g=0.1, g_optim="boundary_seeking", check=False, grad_sync=None):
+    """One core training step (d_update + g_update, even-iteration branch, no extras) with the two generator
+    forward passes of the step run as ONE pass over 2B samples.
+
+    The D-update's detached generator pass (audiogan.py:748, noise batch["z"]) and the G-update's generator pass (:841, noise
+    batch["g_z"]) use the same generator parameters -- the D-update only changes D -- so running them as one batched forward
+    computes exactly what the two calls compute while the sequential recurrent kernel (80 frames, latency-bound) runs once
+    instead of twice.  Only the second half of that pass is differentiated (Generator.forward(grad_from=B)).  Everything else
+    is the literal sequence: D-update on [real | fake_1], D's optimizer step, then the G-update's discriminator pass on fake_2
+    with the UPDATED discriminator, backward through it and the generator, G's optimizer step.
+    Returns (d_update's dict, g_update's dict)."""
+    _set_requires_grad(g, True)
+    Bn = batch["z"].shape[0]
+    z_all = torch.cat([batch["z"], batch["g_z"]], 0)
+    c_all = torch.cat([batch["c_g"], batch["g_c_g"]], 0)
+    fake_all, s_all, _, len_all = g(z=z_all, c=c_all, u_stop=None, grad_from=Bn)
+    host = getattr(len_all, "_ag_host", None)
+
+    def half(a, b):
+        ln = len_all[a:b]
+        if host is not None:
+            ln._ag_host = host[a:b]
+        return ln
+
+    _set_requires_grad(g, False)                                                # audiogan.py:706-709
+    _set_requires_grad(d, True)
+    m1 = _d_update_batched(g, d, opt_d, batch, clip_d, check, grad_sync, fake_pass=(fake_all[:Bn].detach(), half(0, Bn)))
+    gb = {"c_g": batch["g_c_g"], "c_d": batch["g_c_d"], "z": batch["g_z"], "noise_fake": batch["g_noise_fake"], "u_stop": None}
+    m2 = g_update(g, d, opt_g, gb, clip=clip_g, g_optim=g_optim, check=check, grad_sync=grad_sync,
+                  fake_pass=(fake_all[Bn:], s_all[Bn:], None, half(Bn, 2 * Bn)))
+    return m1, m2

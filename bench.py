@@ -181,8 +181,12 @@ def run_ours(args):
     h2d_bytes = sum(v.numel() * v.element_size() for k, v in host[0].items() if not k.endswith("_len"))
 
     def step(di):
+        # train.core_step = d_update + g_update with the step's two generator forward passes run as one batched pass
+        # (AUDIOGAN_SPLIT_G=1: the literal call-by-call sequence)
         di = dict(di)
         di["u_stop"] = None
+        if os.environ.get("AUDIOGAN_SPLIT_G", "0") != "1":
+            return ag.core_step(g, d, opt_d, opt_g, di, clip_d=1.0, clip_g=0.1, grad_sync=sync)
         m1 = ag.d_update(g, d, opt_d, di, clip=1.0, grad_sync=sync)
         gb = {"c_g": di["g_c_g"], "c_d": di["g_c_d"], "z": di["g_z"], "noise_fake": di["g_noise_fake"], "u_stop": None}
         m2 = ag.g_update(g, d, opt_g, gb, clip=0.1, grad_sync=sync)
@@ -261,12 +265,23 @@ def run_ours(args):
     out_ev = [None] * NOUT
     losses_seen = []
 
+    # Two device staging sets, allocated once: step i+1's H2D copies land in set (i+1) % 2 on the copy stream while step i
+    # computes; the step then moves them into the graph's static inputs (a 20 MB device-to-device copy) and replays.  Nothing is
+    # allocated inside the timed region.
+    dkeys = [k for k in host[0] if not k.endswith("_len")]
+    stage = [on_dev(host[0]), on_dev(host[1])]
+    consumed = [None, None]                 # event: the main stream has finished reading staging set k
+
     def prefetch(i):
+        k = i % 2
         with torch.cuda.stream(copy_stream):
-            di = on_dev(host[i % 2], non_blocking=True)
+            if consumed[k] is not None:
+                copy_stream.wait_event(consumed[k])
+            for key in dkeys:
+                stage[k][key].copy_(host[k][key], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return di, ev
+        return k, ev
 
     pending = [prefetch(0)]
 
@@ -275,15 +290,21 @@ def run_ours(args):
     def e2e_step(_):
         i = e2e_count[0]
         e2e_count[0] += 1
-        di, ev = pending.pop()
+        k, ev = pending.pop()
         cur = torch.cuda.current_stream()
         cur.wait_event(ev)
-        for k, v in di.items():
-            if not k.endswith("_len"):
-                v.record_stream(cur)
         pending.append(prefetch(i + 1))
-        m1, m2 = fast_step(di)
-        res = torch.stack([m1["loss_d"], m1["loss_g"], m2["loss"]])
+        if gs is not None:
+            gs.load(stage[k])
+            consumed[k] = torch.cuda.Event()
+            consumed[k].record(cur)
+            out = gs.replay()
+            res = out["losses"]
+        else:
+            m1, m2 = step(stage[k])
+            consumed[k] = torch.cuda.Event()
+            consumed[k].record(cur)
+            res = torch.stack([m1["loss_d"], m1["loss_g"], m2["loss"]])
         j = (i + 1) % NOUT
         if out_ev[j] is not None:               # the losses of step i - (NOUT - 1) have landed: read them on the host
             out_ev[j].synchronize()
@@ -302,6 +323,7 @@ def run_ours(args):
     assert all(v == v for v in losses_seen), "NaN loss in the end-to-end run"
 
     # ---- per-kernel attribution with CUDA events around every launch (same steps, instrumented)
+    step(resident[0])              # untimed: torch.cuda.graph() emptied the allocator's cache, the first eager step re-mallocs
     kt = KernelTimer(torch, shapes=args.shapes)
     _abi.set_hook(kt.hook)
     ms_inst = timed(lambda i: step(resident[i % 2]), args.steps) / args.steps

@@ -595,3 +595,54 @@ def test_cuda_graph_step_equals_eager_step():
     with pytest.raises(ValueError):
         bad = dict(batches[1]); bad["real_len"] = bad["real_len"] - 200
         gs.load(bad)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_core_step_with_batched_generator_pass_equals_the_two_updates(mode):
+    """train.core_step runs the D-update's detached generator pass and the G-update's generator pass as ONE 2B forward
+    (same parameters; only the second half is differentiated).  It must reproduce d_update followed by g_update: to fp32
+    rounding in fp32 mode; in bf16 mode (other tile shapes -> other bf16 roundings) the batched variant must be as close to the
+    fp32-mode result as the call-by-call variant is (control: both bf16 variants are measured against fp32 mode)."""
+    import audiogan_b200 as ag
+    cs = dict(B=5, L=2400, full=True, gk={"state_size": 128}, dk={"state_size": 128}) if mode == "fp32" else dict(B=6, L=3200, full=True)
+    di = to_dev(step_inputs(cs["B"], cs["L"], seed=77, full_length=True))
+    di["real_len"] = di["real_len"].cpu()
+    di["u_stop"] = None
+
+    def run(md, fused):
+        _, _, g, d = build(cs)
+        g.set_mode(md); d.set_mode(md)
+        od, og = ag.FusedRMSprop(d.parameters(), lr=1e-4), ag.FusedRMSprop(g.parameters(), lr=1e-4)
+        if fused:
+            m1, m2 = ag.core_step(g, d, od, og, di, clip_d=0.0, clip_g=0.0)
+        else:
+            m1 = ag.d_update(g, d, od, di, clip=0.0)
+            gb = {"c_g": di["g_c_g"], "c_d": di["g_c_d"], "z": di["g_z"], "noise_fake": di["g_noise_fake"], "u_stop": None}
+            m2 = ag.g_update(g, d, og, gb, clip=0.0)
+        return dict(ld=m1["loss_d"], lg=m1["loss_g"], l=m2["loss"], fake1=m1["fake"], fake2=m2["fake"],
+                    gd={k: p.grad.clone() for k, p in d.named_parameters()}, gg={k: p.grad.clone() for k, p in g.named_parameters()})
+
+    R = Report()
+    if mode == "fp32":
+        a, b = run("fp32", False), run("fp32", True)
+        for k in ("ld", "lg", "l", "fake1", "fake2"):
+            R.check(k, b[k].reshape(-1), a[k].reshape(-1), 2e-6)
+        for tag, key in (("dD/", "gd"), ("dG/", "gg")):
+            for k in a[key]:
+                if not noise_only(k):
+                    R.check(tag + k, b[key][k], a[key][k], 2e-5)
+    else:
+        ref, a, b = run("fp32", False), run("bf16", False), run("bf16", True)
+        for k in ("ld", "lg", "l", "fake1", "fake2"):
+            R.check(k, b[k].reshape(-1), ref[k].reshape(-1), 2e-2)
+        l2 = lambda x, y: float((x.float() - y.float()).norm() / (y.float().norm() + 1e-30))
+        for tag, key in (("dD/", "gd"), ("dG/", "gg")):
+            for k in ref[key]:
+                if noise_only(k) or ref[key][k].numel() < 8:
+                    continue
+                e_split, e_fused = l2(a[key][k], ref[key][k]), l2(b[key][k], ref[key][k])
+                R.rows.append((tag + k + " relL2 vs fp32: call-by-call", e_split))
+                R.rows.append((tag + k + " relL2 vs fp32: batched G pass", e_fused))
+                if e_fused > max(2.0 * e_split, 0.05):
+                    R.bad.append("%s%s: batched %.3f vs call-by-call %.3f (relative L2 error against fp32 mode)" % (tag, k, e_fused, e_split))
+    R.done("core_step_%s" % mode)
