@@ -32,11 +32,30 @@ RATE = 8000
 FRAME = 200
 
 
-def flops_per_sample(L):
-    """Algorithmic FLOPs of one core step per sample: 4 F_G + 8 F_D MACs, 2 FLOP/MAC."""
-    F_G = 60475.64 * L
-    F_D = 140736.0 * L
+def flops_per_sample(L, gstate=1024, dstate=1024, g_struct=None, d_struct=None, frame=200, embed=100, noise=100):
+    """Algorithmic FLOPs of one core step per sample: 4 F_G + 8 F_D forward MACs, 2 FLOP/MAC.  Default nets:
+    F_G = 60 475.64 L, F_D = 140 736 L (the SURVEY's figures, reproduced by the general formulas below)."""
+    g_struct = g_struct or [[17, 8, 128, 16], [9, 4, 64, 32], [9, 4, 64, 32], [9, 4, 32, 32]]
+    d_struct = d_struct or [[7, 2, 16], [7, 2, 32], [7, 2, 64], [7, 2, 128], [7, 2, 256], [7, 2, 512]]
+    Tg = (L + frame - 1) // frame
+    F_G = Tg * ((frame + embed + noise + gstate) * 4 * gstate + gstate * frame + gstate)
+    cin = 1
+    for k, s, hid, out in g_struct:
+        F_G += (L / s) * hid * k * cin + (L / s) * (k - 1) * hid * out
+        cin += out
+    F_G += 3 * cin * L
+    F_D, cin, T = 0.0, 1, L
+    for k, s, cout in d_struct:
+        T = (T + s - 1) // s
+        F_D += T * cout * k * cin
+        cin = cout
+    Hd = dstate // 2
+    F_D += T * (2 * (cin + embed) * 4 * Hd + 2 * Hd * 4 * Hd + 2 * dstate * dstate + dstate * (dstate // 2) + dstate // 2)
     return 2.0 * (4 * F_G + 8 * F_D)
+
+
+D_STRUCT_SCALED = [[7, 2, 32], [7, 1, 32], [7, 2, 64], [7, 1, 64], [7, 2, 128], [7, 1, 128], [7, 2, 256], [7, 1, 256],
+                   [7, 2, 512], [7, 1, 512], [7, 2, 1024], [7, 1, 1024]]     # configs[4]: 2x channels and depth (SURVEY 8(d) cfg 5)
 
 
 def peaks():
@@ -160,8 +179,12 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.manual_seed(1234)
     B, L = args.batch, args.samples
-    g = ag.pin_stopper(ag.Generator(embed_size=100)).to(dev)
-    d = ag.Discriminator(embed_size=100).to(dev)
+    d_struct = D_STRUCT_SCALED if args.d_struct == "scaled" else None
+    g = ag.pin_stopper(ag.Generator(embed_size=100, state_size=args.gstate)).to(dev)
+    d = ag.Discriminator(embed_size=100, state_size=args.dstate, **({"cnn_struct": d_struct} if d_struct else {})).to(dev)
+    fps = flops_per_sample(L, args.gstate, args.dstate, None, d_struct)
+    nets = "default nets" if (args.gstate, args.dstate, args.d_struct) == (1024, 1024, "default") else (
+        "generator state %d, discriminator state %d, %s discriminator conv stack" % (args.gstate, args.dstate, args.d_struct))
     g.set_mode(args.mode)
     d.set_mode(args.mode)
     agd.broadcast_parameters([g, d])
@@ -250,7 +273,9 @@ def run_ours(args):
     if args.quick:
         if rank == 0:
             emit({"quick": True, "ms_per_step": round(ms_step, 4), "value": round(value, 2), "gpu_launches": launches,
-                  "launch_mode": graph_note})
+                  "launch_mode": graph_note, "n_gpus": world, "workload": "%s, per-GPU batch %d, L=%d" % (nets, B, L),
+                  "step_tflops": round(world * B * fps / (ms_step * 1e-3) / 1e12, 3),
+                  "recurrent_paths": dict(g._plan.last_path, **d._plan.last_path)})
         return
     # ---- e2e: host buffers, H2D of the step's inputs and D2H of the losses inside the timed region
     d2h = [0]
@@ -354,10 +379,11 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.mode == "fp32" else "bf16", "data": "synthetic",
         "steps_per_s": round(1e3 / ms_step, 4),
-        "step_tflops": round(world * B * flops_per_sample(L) / (ms_step * 1e-3) / 1e12, 3),
-        "frac_tc_peak_whole_step": round(B * flops_per_sample(L) / (ms_step * 1e-3) / 1e12 / pk["tc"], 5),
-        "config": {"workload": "audiogan core GAN step (1 D-update + 1 G-update), default nets, per-GPU batch %d, "
-                               "%.1f s synthetic 8 kHz waveforms (L=%d)" % (B, L / RATE, L),
+        "step_tflops": round(world * B * fps / (ms_step * 1e-3) / 1e12, 3),
+        "frac_tc_peak_whole_step": round(B * fps / (ms_step * 1e-3) / 1e12 / pk["tc"], 5),
+        "recurrent_paths": dict(g._plan.last_path, **d._plan.last_path),
+        "config": {"workload": "audiogan core GAN step (1 D-update + 1 G-update), %s, per-GPU batch %d, "
+                               "%.1f s synthetic 8 kHz waveforms (L=%d)" % (nets, B, L / RATE, L),
                    "global_batch": world * B, "samples": L, "mode": args.mode, "parallelism": "dp%d" % world,
                    "l2_policy": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; two input batches alternate"},
         "e2e": {"value": round(audio_s / (ms_e2e * 1e-3), 2), "unit": "audio-s/s", "ms_per_step": round(ms_e2e, 4),
@@ -371,7 +397,7 @@ def run_ours(args):
         "kernel_families": families,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_step_throughput(args, steps=2, warmup=1)
+        out["cpu_baseline"] = cpu_step_throughput(args, steps=2, warmup=1, batch=args.cpu_batch)
     if rank == 0:
         emit(out)
     if world > 1:
@@ -379,41 +405,52 @@ def run_ours(args):
 
 
 # ----------------------------------------------------------------------------------- CPU arm
-def cpu_step_throughput(args, steps, warmup):
-    """The oracle port (oracle/restated.py: the reference's step restated for py3 / torch 2.x, pinned to the
-    reference classes by tests/test_oracle.py) on the host cores, on a bounded sample of the workload."""
+def cpu_step_throughput(args, steps, warmup, batch):
+    """The reference's CPU training step on the host cores, on `batch` samples of the workload's minibatch.
+
+    kind "reference": the reference's OWN Generator / Discriminator / helper definitions (audiogan.py:1-552, located by
+    oracle/ref_step.py: /root/reference in the build container, the build-time copy under oracle/_ref/ on the GPU box) driven
+    through the core step's call order on stock torch CPU kernels.  kind "port" (only when neither is present): the oracle's
+    functional restatement oracle/restated.py (pinned to the reference classes by tests/test_oracle.py)."""
     import torch
     from oracle import restated as O
+    from oracle import ref_step as RS
     from audiogan_b200.synthetic import step_inputs
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs, L = args.cpu_batch, args.samples
-    Pg = O.pin_stopper(O.init_generator(11))
-    Pd = O.init_discriminator(12)
-    inp = step_inputs(Bs, L, seed=1234, full_length=True)
-    gb = {"c_g": inp["g_c_g"], "c_d": inp["g_c_d"], "z": inp["g_z"], "noise_fake": inp["g_noise_fake"]}
-    sd, sg = {}, {}
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        O.d_update(Pg, Pd, sd, inp)
-        O.g_update(Pg, Pd, sg, gb)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    t = sum(times) / len(times)
-    return {"value": round(Bs * L / RATE / t, 3), "unit": "audio-s/s", "cores": cores, "kind": "port",
-            "s_per_step": round(t, 4), "steps_per_s_at_sample_batch": round(1.0 / t, 4),
-            "sample": "oracle port of the reference step (torch fp32 CPU, %d threads) on %d of the %d samples of a "
-                      "minibatch, L=%d, %d timed steps after %d warm-up" % (cores, Bs, args.batch, L, steps, warmup)}
+    L = args.samples
+    inp = step_inputs(batch, L, seed=1234, full_length=True)
+    if RS.locate() is not None:
+        t, _ = RS.time_steps(inp, steps, warmup)
+        kind, what = "reference", "the reference's own classes (audiogan.py:1-552) through the core step's call order"
+    else:
+        Pg = O.pin_stopper(O.init_generator(11))
+        Pd = O.init_discriminator(12)
+        gb = {"c_g": inp["g_c_g"], "c_d": inp["g_c_d"], "z": inp["g_z"], "noise_fake": inp["g_noise_fake"]}
+        sd, sg, times = {}, {}, []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.d_update(Pg, Pd, sd, inp)
+            O.g_update(Pg, Pd, sg, gb)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        t = sum(times) / len(times)
+        kind, what = "port", "oracle port of the reference step (oracle/restated.py)"
+    return {"value": round(batch * L / RATE / t, 3), "unit": "audio-s/s", "cores": cores, "kind": kind,
+            "s_per_step": round(t, 4), "steps_per_s_at_sample_batch": round(1.0 / t, 4), "sample_batch": batch,
+            "sample": "%s, torch fp32 CPU, %d threads, on %d of the %d samples of a minibatch, L=%d, %d timed steps after %d "
+                      "warm-up" % (what, cores, batch, args.batch, L, steps, warmup)}
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the step on the SAME config (full per-GPU minibatch, same L);
+    each step is the whole minibatch, a bounded number of steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 2))
     warm = 1 if args.warmup > 0 else 0
-    cb = cpu_step_throughput(args, steps=steps, warmup=warm)
+    cb = cpu_step_throughput(args, steps=steps, warmup=warm, batch=args.batch)
     L = args.samples
     out = {
         "impl": "reference", "metric": "audio_seconds_per_s", "value": cb["value"], "unit": "audio-s/s",
@@ -456,6 +493,10 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("AUDIOGAN_MODE", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (configs[1]: 64)")
     ap.add_argument("--samples", type=int, default=16000, help="waveform length L (2 s at 8 kHz)")
+    ap.add_argument("--gstate", type=int, default=1024, help="generator state size (configs[3]: 2048)")
+    ap.add_argument("--dstate", type=int, default=1024, help="discriminator state size (configs[3]: 2048)")
+    ap.add_argument("--d-struct", default="default", choices=["default", "scaled"],
+                    help="scaled = configs[4]: 2x conv channels and depth (added layers stride 1)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="samples per step of the bounded CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shapes", action="store_true", help="attribute GEMM time per (M,N,K) shape")

@@ -171,3 +171,27 @@ def test_embedder_and_pickling_match_reference_api():
     buf.seek(0)
     g2 = T.load(buf, weights_only=False)
     assert list(g2.state_dict().keys()) == list(g.state_dict().keys()) and g2._plan is None
+
+
+def test_reference_class_step_matches_restated_step():
+    """oracle/ref_step.py (the reference's own modules through the core step's call order: what `bench.py --impl reference`
+    times) against the functional restatement the GPU parity tests use: same losses, same parameters after the step."""
+    from oracle import ref_step as RS
+    if RS.locate() is None:
+        pytest.skip("reference definitions not present (neither /root/reference nor oracle/_ref)")
+    from audiogan_b200.synthetic import step_inputs
+    inp = step_inputs(3, 1600, seed=5)
+    rs = RS.ReferenceStep()
+    got = rs.step(inp)
+    Pg, Pd = O.pin_stopper(O.init_generator(11)), O.init_discriminator(12)
+    o1 = O.d_update(Pg, Pd, {}, inp)
+    o2 = O.g_update(Pg, Pd, {}, {"c_g": inp["g_c_g"], "c_d": inp["g_c_d"], "z": inp["g_z"], "noise_fake": inp["g_noise_fake"]})
+    for a, b in zip(got, (o1["loss_d"], o1["loss_g"], o2["loss"])):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (got, o1["loss_d"], o1["loss_g"], o2["loss"])
+    for sd, P in ((rs.d.state_dict(), Pd), (rs.g.state_dict(), Pg)):
+        for k, v in sd.items():
+            if k.split(".")[-1].startswith("bias") and k.endswith("_v"):
+                continue                   # w = g * sign(v): d/dv is identically 0, both sides step on rounding noise
+            err = (v - P[k]).abs()
+            # the first RMSprop step is sign-like: elements whose gradient is rounding noise may step the other way
+            assert float((err > 5e-6).float().mean()) < 1e-3 and float(err.max()) < 2.1e-3, (k, float(err.max()))
