@@ -91,6 +91,7 @@ _PROTOS = {
     "ag_lstm_fwd": [C.POINTER(LstmDesc), vp],
     "ag_lstm_bwd": [C.POINTER(LstmDesc), vp],
     "ag_lstm_cluster_max_active": [i32, i32],
+    "ag_lstm_batch_cap": [C.POINTER(LstmDesc), i32],
     "ag_wn_fwd_multi": [vp, vp, i32, i32, vp],
     "ag_wn_bwd_multi": [vp, vp, i32, i32, vp],
     "ag_gather": [vp, vp, vp, i64, i32, vp],

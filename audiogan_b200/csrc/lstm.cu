@@ -1215,6 +1215,7 @@ int gen_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);       // lstm
 int gen_bwd(const ag_lstm_desc* d, cudaStream_t s, int* launched);
 int64_t gen_fwd_ws_bytes(const ag_lstm_desc* d);
 int64_t gen_bwd_ws_bytes(const ag_lstm_desc* d);
+int gen_batch_cap(const ag_lstm_desc* d, int bwd);
 } }
 
 using namespace ag;
@@ -1227,6 +1228,11 @@ static const char* grid_family(const Plan& p) {
 int64_t ag_lstm_workspace_bytes(const ag_lstm_desc* d, int32_t bwd) {
   if (!d) return AG_EINVAL;
   return bwd ? lg::gen_bwd_ws_bytes(d) : lg::gen_fwd_ws_bytes(d);
+}
+
+int32_t ag_lstm_batch_cap(const ag_lstm_desc* d, int32_t bwd) {
+  if (!d) return 0;
+  return lg::gen_batch_cap(d, bwd);
 }
 
 int ag_lstm_fwd(const ag_lstm_desc* d, void* stream) {

@@ -1002,6 +1002,27 @@ int gen_fwd(const ag_lstm_desc* d, cudaStream_t s, int* launched) {
   set_path("tmem");
   return AG_OK;
 }
+static const char* bwd_geom(const ag_lstm_desc* d, BwdGeom& g, size_t& ll_need, size_t& smem, char* why, size_t nwhy);
+// largest batch one launch of the TMEM-resident kernels takes for this (H, F): whole batch groups that fit the SMs
+int gen_batch_cap(const ag_lstm_desc* d, int bwd) {
+  if (d->F <= 0 || d->ndir != 1 || d->prec < 1 || d->H % 128 != 0) return 0;
+  const int nsl = d->H / UPC;
+  const int groups = std::min(sm_count() / std::max(nsl, 1), 16);
+  if (groups <= 0) return 0;
+  ag_lstm_desc t = *d;
+  t.B = groups * (bwd ? BNB : 32);
+  char why[160];
+  size_t ll = 0, smem = 0;
+  if (bwd) {
+    BwdGeom g;
+    if (bwd_geom(&t, g, ll, smem, why, sizeof(why))) return 0;
+  } else {
+    FwdGeom g;
+    int NB = 16;
+    if (fwd_geom(&t, g, NB, ll, smem, why, sizeof(why))) return 0;
+  }
+  return t.B;
+}
 int64_t gen_fwd_ws_bytes(const ag_lstm_desc* d) {
   if (d->F <= 0 || d->ndir != 1 || d->prec < 1) return 0;
   FwdGeom g;

@@ -75,12 +75,21 @@ class _GenFn(torch.autograd.Function):
         glen = torch.zeros(B, device=dev, dtype=torch.int32)
         misc = torch.zeros(1024, device=dev, dtype=torch.int32)        # [0:8] barrier, [8] t_end, [16:] per-CTA flags
         u = u_stop.contiguous() if u_stop is not None else None
+        # Samples are independent: a batch larger than one launch of the TMEM-resident kernel takes (whole co-resident batch
+        # groups: 128 samples for the default net) runs as consecutive launches over row slices of the batch-major buffers
+        # instead of dropping to the grid-barrier kernels (with stop sampling the early exit is a cross-batch decision: one launch)
+        cap = K.lstm_batch_cap(H, F, False) if (bf and u is None and not (plan.lstm_flags & 1)) else 0
+        chunk = cap if (cap and B > cap) else B
         # exchange workspace of the TMEM-resident recurrence (include/audiogan_b200.h: ag_lstm_desc.ll_ws)
-        ll_ws = K.lstm_workspace(B, H, F, False, dev) if bf else None
-        K.lstm_fwd(B=B, T=Tcap, Tcap=Tcap, H=H, ndir=1, F=F, pre=pre, w1=plan.Poff("w1"), w2=plan.Poff("w2"),
-                   b2=plan.Poff("b2"), hbuf=hbuf, gates=gates, cbuf=cbuf, xbuf=xbuf, sbuf=sbuf, u=u, stop=stop,
-                   glen=glen, t_end=(misc, 8), barrier=misc, prec=plan.lstm_prec if bf else 0, hbuf16=hbuf16, xbuf16=xbuf16,
-                   flags=plan.lstm_flags | 2, ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel() if ll_ws is not None else 0)
+        ll_ws = K.lstm_workspace(chunk, H, F, False, dev) if bf else None
+        for b0 in range(0, B, chunk):
+            sl = slice(b0, min(B, b0 + chunk))
+            cut = lambda t: t[sl] if t is not None else None
+            K.lstm_fwd(B=sl.stop - sl.start, T=Tcap, Tcap=Tcap, H=H, ndir=1, F=F, pre=pre[sl], w1=plan.Poff("w1"), w2=plan.Poff("w2"),
+                       b2=plan.Poff("b2"), hbuf=hbuf[sl], gates=cut(gates), cbuf=cut(cbuf), xbuf=xbuf[sl], sbuf=sbuf[sl], u=u,
+                       stop=stop[sl], glen=glen[sl], t_end=(misc, 8), barrier=misc, prec=plan.lstm_prec if bf else 0,
+                       hbuf16=cut(hbuf16), xbuf16=cut(xbuf16), flags=plan.lstm_flags | 2, ll_ws=ll_ws,
+                       ll_ws_bytes=ll_ws.numel() if ll_ws is not None else 0)
         plan.last_path["g_fwd"] = K.lstm_last_path()
         if u is not None and early_exit_sync:
             T = int(misc[8].item())          # the one host sync per generator pass (audiogan.py:459-460)
@@ -205,12 +214,20 @@ class _GenFn(torch.autograd.Function):
         misc = torch.zeros(16, device=dev, dtype=torch.int32)
         dgates16 = torch.empty(B, Tcap, 4 * H, device=dev, dtype=torch.bfloat16) if bf else None
         dpx16 = torch.empty(B, Tcap, FP, device=dev, dtype=torch.bfloat16) if bf else None
+        # batch chunks as in the forward pass (64 samples per launch of the TMEM-resident BPTT kernel for the default net)
+        cap = K.lstm_batch_cap(H, F, True) if (bf and not (plan.lstm_flags & 1)) else 0
+        chunk = cap if (cap and B > cap) else B
         # reduce-scatter workspace of the TMEM-resident BPTT kernel (include/audiogan_b200.h: ag_lstm_desc.ll_ws)
-        ll_ws = K.lstm_workspace(B, H, F, True, dev) if bf else None
-        K.lstm_bwd(B=B, T=T, Tcap=Tcap, H=H, ndir=1, F=F, gates=gates, cbuf=cbuf, xbuf=xbuf, dx_ext=dx_ext,
-                   ds_ext=ds_ext, dgates=dgates, dpx=dpx, w1t=plan.Poff("w1t"), wxt=plan.Poff("wxt"), barrier=misc,
-                   prec=plan.lstm_prec if bf else 0, dgates16=dgates16, dpx16=dpx16, flags=plan.lstm_flags | 2,
-                   ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel() if ll_ws is not None else 0)
+        ll_ws = K.lstm_workspace(chunk, H, F, True, dev) if bf else None
+        for b0 in range(0, B, chunk):
+            sl = slice(b0, min(B, b0 + chunk))
+            cut = lambda t: t[sl] if t is not None else None
+            K.lstm_bwd(B=sl.stop - sl.start, T=T, Tcap=Tcap, H=H, ndir=1, F=F, gates=gates[sl], cbuf=cbuf[sl], xbuf=xbuf[sl],
+                       dx_ext=cut(dx_ext), ds_ext=cut(ds_ext), dgates=dgates[sl], dpx=dpx[sl], w1t=plan.Poff("w1t"),
+                       wxt=plan.Poff("wxt"), barrier=misc, prec=plan.lstm_prec if bf else 0, dgates16=cut(dgates16),
+                       dpx16=cut(dpx16), flags=plan.lstm_flags | 2, ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel() if ll_ws is not None else 0)
+            if chunk < B:
+                misc.zero_()
         plan.last_path["g_bwd"] = K.lstm_last_path()
         # REINFORCE (audiogan.py:900-908): the score-function gradient of the stop logits reaches the stop head's weight and
         # bias ONLY (the reference freezes every other generator parameter for that backward), so it joins column F of dpx

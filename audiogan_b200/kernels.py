@@ -105,6 +105,19 @@ def lstm_workspace(B, H, F, bwd, device):
     return torch.empty(n, device=device, dtype=torch.uint8) if n > 0 else None
 
 
+_batch_cap = {}
+
+
+def lstm_batch_cap(H, F, bwd):
+    """samples one launch of the TMEM-resident generator recurrence takes (0: the shape does not run there)"""
+    key = (H, F, bool(bwd), torch.cuda.current_device())
+    if key not in _batch_cap:
+        d = A.LstmDesc()
+        d.B, d.H, d.F, d.ndir, d.prec = 1, H, F, 1, 1
+        _batch_cap[key] = int(A.lib().ag_lstm_batch_cap(C.byref(d), 1 if bwd else 0))
+    return _batch_cap[key]
+
+
 def lstm_last_path():
     """Kernel family (and decline reason, if any) of the last lstm_fwd / lstm_bwd call on this thread."""
     return A.lib().ag_lstm_last_path().decode("utf-8", "replace")

@@ -151,6 +151,11 @@ int ag_lstm_bwd(const ag_lstm_desc* d, void* stream);
 /* Bytes of `ll_ws` the TMEM-resident generator kernels need for this descriptor's (B, H, F) -- forward (bwd == 0) or BPTT
  * (bwd != 0); 0 when the shape runs on a path that needs no workspace.  Only B, H, F, ndir and prec are read. */
 int64_t ag_lstm_workspace_bytes(const ag_lstm_desc* d, int32_t bwd);
+/* Largest batch ONE launch of the TMEM-resident generator kernels takes for this descriptor's (H, F) on this device
+ * (whole batch groups that are co-resident: 128 samples forward / 64 BPTT for the default net on 148 SMs); 0 when the shape
+ * does not run there.  Samples are independent, so a caller with a larger batch runs the recurrence in chunks of this many
+ * samples over row slices of the batch-major buffers instead of dropping to the grid-barrier kernels. */
+int32_t ag_lstm_batch_cap(const ag_lstm_desc* d, int32_t bwd);
 /* Which kernel family the last ag_lstm_fwd / ag_lstm_bwd call ON THIS THREAD ran on, and -- when a bf16-mode call fell off
  * the fast (cluster / TMEM-resident) kernels -- why: e.g. "cluster", "tmem", "grid-bf16 (tmem declined: 8 groups x 32
  * slices > 148 SMs)".  With AUDIOGAN_VERBOSE=1 in the environment every distinct decline is also printed to stderr once. */

@@ -646,3 +646,41 @@ def test_core_step_with_batched_generator_pass_equals_the_two_updates(mode):
                 if e_fused > max(2.0 * e_split, 0.05):
                     R.bad.append("%s%s: batched %.3f vs call-by-call %.3f (relative L2 error against fp32 mode)" % (tag, k, e_fused, e_split))
     R.done("core_step_%s" % mode)
+
+
+def test_generator_batch_beyond_one_launch_runs_in_chunks_on_the_fast_kernels():
+    """B = 136 > the 128 samples (forward) / 64 samples (BPTT) one launch of the TMEM-resident generator recurrence takes:
+    the engine runs consecutive launches over row slices of the batch (samples are independent) instead of dropping to the
+    grid-barrier kernels (per-GPU batch 128 fell off the fast path silently).  Checked against the CPU oracle."""
+    import audiogan_b200 as ag
+    Bn, L = 136, 800
+    Pg = O.pin_stopper(O.init_generator(11))
+    g = ag.Generator(embed_size=100); g.load_state_dict(Pg); g = g.cuda().set_mode("bf16")
+    gen = T.Generator().manual_seed(3)
+    z = T.randn(Bn, L // 200, 100, generator=gen)
+    c = T.randn(Bn, 100, generator=gen)
+    up = T.randn(Bn, L, generator=gen)
+    zr = z.clone().requires_grad_(True)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in Pg.items()}
+    xr, sr, _, _ = O.generator_forward(Pr, c, z=zr)
+    (xr * up).sum().backward()
+    zd = z.cuda().requires_grad_(True)
+    x, s_, _, _ = g(z=zd, c=c.cuda(), u_stop=None)
+    (x * up.cuda()).sum().backward()
+    assert g._plan.last_path.get("g_fwd") == "tmem" and g._plan.last_path.get("g_bwd") == "tmem", g._plan.last_path
+    R = Report()
+    R.check("x (136 samples)", x, xr, 2e-2)
+    R.check("s", s_, sr, 2e-2)
+    for lo, hi in ((0, 64), (64, 128), (128, 136)):                 # every BPTT chunk
+        a, b = zd.grad[lo:hi].flatten().cpu(), zr.grad[lo:hi].flatten()
+        cos = float(T.dot(a, b) / (a.norm() * b.norm()))
+        R.rows.append(("dz cos rows %d:%d" % (lo, hi), cos))
+        if cos < 0.97:
+            R.bad.append("dz rows %d:%d cos %.4f" % (lo, hi, cos))
+    for k in ("rnn.0.module.weight_hh_v", "proj.module.weight_v", "dense_res_gen.1.module.conv.weight_v"):
+        a, b = dict(g.named_parameters())[k].grad.flatten().cpu(), Pr[k].grad.flatten()
+        cos = float(T.dot(a, b) / (a.norm() * b.norm()))
+        R.rows.append(("d%s cos" % k, cos))
+        if cos < 0.97:
+            R.bad.append("%s cos %.4f" % (k, cos))
+    R.done("gen_batch_chunks")
