@@ -117,6 +117,8 @@ _PROTOS = {
     "ag_frames_to_slot": [vp, i32, i64, i64, i32, vp, i64, i64, i64, vp],
     "ag_rowgroup_sum": [vp, i32, vp, i64, i64, i64, vp],
     "ag_transpose_bct": [vp, vp, i64, i64, i64, i64, i64, i32, vp],
+    "ag_peer_barrier": [vp, i32, i32, vp],
+    "ag_peer_allreduce": [vp, vp, i32, i32, i64, i32, vp],
     "ag_mt_sqnorm": [vp, vp, vp, i32, i32, vp, vp, f32, vp],
     "ag_mt_clip": [vp, vp, vp, i32, i32, vp, f32, vp],
     "ag_mt_rmsprop": [vp, vp, vp, i32, i32, vp, f32, f32, f64, f64, f64, vp],

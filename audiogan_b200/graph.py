@@ -2,9 +2,11 @@
 
 The step (train.d_update + train.g_update on fixed shapes, audiogan.py:706-788 + :816-921 with ``--critic_iter 1
 --gencatchup 1``) contains no host synchronisation once the per-layer length tables are cached: every kernel of both
-forward passes, both backward passes (autograd runs inside the capture), the weight-norm / packing kernels, the per-tensor
-clip + RMSprop launches and, data-parallel, the NCCL all-reduces are recorded once and replayed with one
-``cudaGraphLaunch`` per step.  That removes the host's per-launch cost (≈170 C-ABI launches + ≈240 small torch
+forward passes, both backward passes (autograd runs inside the capture), the weight-norm / packing kernels and the per-tensor
+clip + RMSprop launches are recorded once and replayed with one ``cudaGraphLaunch`` per step.  Data-parallel, the capture is
+cut at the two gradient all-reduces (after the discriminator's backward, after the generator's): three graph segments that
+share one memory pool, with the bucketed NCCL all-reduces issued between them in stream order (no host synchronisation; the
+collectives are deliberately NOT captured -- graph-captured NCCL kernels deadlocked against eager collectives on this stack).  That removes the host's per-launch cost (≈170 C-ABI launches + ≈240 small torch
 fills / copies per step, 6 ms of one host core: profiles/r1_host_profile.txt) and the launch gaps between small kernels.
 
 Inputs live in static device buffers (``GraphedStep.inputs``); ``run(batch)`` copies a batch into them (device-to-device
@@ -37,18 +39,18 @@ class GraphedStep:
         self._capture(warmup)
 
     # the step on the static buffers ------------------------------------------------------------------------------
-    def _step(self):
+    def _step(self, grad_sync):
         di = dict(self.inputs)
         di["u_stop"] = None
         if not self.d_kwargs and not self.g_kwargs:
             return train.core_step(self.g, self.d, self.opt_d, self.opt_g, di, clip_d=self.clip_d, clip_g=self.clip_g,
-                                   grad_sync=self.grad_sync)
-        m1 = train.d_update(self.g, self.d, self.opt_d, di, clip=self.clip_d, grad_sync=self.grad_sync, **self.d_kwargs)
+                                   grad_sync=grad_sync)
+        m1 = train.d_update(self.g, self.d, self.opt_d, di, clip=self.clip_d, grad_sync=grad_sync, **self.d_kwargs)
         gb = {"c_g": di["g_c_g"], "c_d": di["g_c_d"], "z": di["g_z"], "noise_fake": di["g_noise_fake"], "u_stop": None}
         for k in ("real", "real_len", "noise_real", "noise_adv"):
             if k in di:
                 gb[k] = di[k]
-        m2 = train.g_update(self.g, self.d, self.opt_g, gb, clip=self.clip_g, grad_sync=self.grad_sync, **self.g_kwargs)
+        m2 = train.g_update(self.g, self.d, self.opt_g, gb, clip=self.clip_g, grad_sync=grad_sync, **self.g_kwargs)
         return m1, m2
 
     def _capture(self, warmup):
@@ -59,19 +61,48 @@ class GraphedStep:
             # eager warm-up on the capture's side stream: one-time kernel attributes, tensor maps' first use, NCCL
             # communicators, the length-table and constant caches are all populated before the capture starts
             for _ in range(max(1, warmup)):
-                self._step()
+                self._step(self.grad_sync)
         cur.wait_stream(side)
         torch.cuda.synchronize(self.device)
-        self.graph = torch.cuda.CUDAGraph()
+        # NCCL all-reduces are issued between graph segments; the peer-memory all-reduce (dist.PeerGradSync) is plain kernels
+        distributed = (self.grad_sync is not None and getattr(self.grad_sync, "world", 1) > 1
+                       and not getattr(self.grad_sync, "capturable", False))
+        if distributed and any(getattr(m, "_plan", None) is not None and m._plan.early_sync is not None for m in (self.g, self.d)):
+            raise RuntimeError("GraphedStep: GradSync.attach (all-reduce inside backward) cannot be combined with graph capture")
+        self.graphs, self.syncs = [], []
+        state = {}
+
+        def begin():
+            gr = torch.cuda.CUDAGraph()
+            # thread_local: the autograd engine's worker thread (and NCCL's watchdog) issue CUDA calls while the capture runs
+            ctx = torch.cuda.graph(gr, pool=(self.graphs[0].pool() if self.graphs else None), stream=side,
+                                   capture_error_mode="thread_local")
+            ctx.__enter__()
+            self.graphs.append(gr)
+            state["ctx"] = ctx
+
+        def cut(params):
+            """the all-reduce point between backward and the optimizer step: end this graph segment, reduce eagerly (on
+            whatever the gradient buffers hold: nothing has executed yet), start the next segment"""
+            state["ctx"].__exit__(None, None, None)
+            params = list(params)
+            scale = self.grad_sync(params)
+            self.syncs.append(params)
+            begin()
+            return scale
+
         l0 = A.launches
-        # thread_local: the autograd engine's worker thread (and NCCL's watchdog) issue CUDA calls while the capture runs
-        with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
-            m1, m2 = self._step()
+        begin()
+        try:
+            m1, m2 = self._step(cut if distributed else self.grad_sync)
             self.out = {"loss_d": m1["loss_d"], "loss_g": m1["loss_g"], "loss": m2["loss"],
                         "losses": torch.stack([m1["loss_d"], m1["loss_g"], m2["loss"]]),
                         "d_grad_norm": m1["d_grad_norm"], "g_grad_norm": m2["g_grad_norm"],
                         "stats_d": m1["stats_d"], "stats_g": m1["stats_g"]}
+        finally:
+            state["ctx"].__exit__(None, None, None)
         self.launches = A.launches - l0
+        self.graph = self.graphs[0]
 
     # ---------------------------------------------------------------------------------------------------------------
     def load(self, batch, non_blocking=True):
@@ -85,7 +116,10 @@ class GraphedStep:
             dst.copy_(batch[k], non_blocking=non_blocking)
 
     def replay(self):
-        self.graph.replay()
+        for i, gr in enumerate(self.graphs):
+            gr.replay()
+            if i < len(self.syncs):
+                self.grad_sync(self.syncs[i])          # bucketed NCCL all-reduce of that net's gradients, in stream order
         return self.out
 
     def run(self, batch=None):

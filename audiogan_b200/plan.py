@@ -185,7 +185,16 @@ class NetPlan:
             self.poff[id(p)] = n
             n = _round(n + p.numel(), 4)
         self.ngrad = n
-        self.gwork = torch.zeros(n, device=dev)
+        self.gpersist = None
+        self._bind_grad_buffer(torch.zeros(n, device=dev))
+        self.signature = tuple(p.data_ptr() for p in self.params)
+        self._const_len = {}
+        return self
+
+    def _bind_grad_buffer(self, buf):
+        """(re)build the weight-norm table so that the backward kernel writes the parameter gradients into `buf`"""
+        dev = self.device
+        self.gwork = buf
         rows = sum(v.shape[0] for _, _, v, _ in self._wn)
         self.norms = torch.zeros(rows, device=dev)
         entries, r0 = [], 0
@@ -201,9 +210,16 @@ class NetPlan:
             r0 += nrow
         self.wn_tab, self.wn_rows, self.wn_total = K.wn_table(entries, dev)
         self.wn_n = len(entries)
-        self.signature = tuple(p.data_ptr() for p in self.params)
-        self._const_len = {}
-        return self
+        self._packed_key = None                                  # the norms buffer is new: re-run weight-norm forward
+
+    def set_grad_buffer(self, buf):
+        """Data-parallel over peer memory (dist.PeerGradSync): the flat gradient buffer lives in symmetric memory that every
+        rank maps, and ``p.grad`` become PERSISTENT views of it (no per-step copy) -- each backward pass overwrites them, which
+        is what a training loop that calls ``zero_grad()`` before ``backward()`` expects."""
+        assert buf.numel() >= self.ngrad and buf.dtype == torch.float32 and buf.is_contiguous()
+        buf.zero_()
+        self._bind_grad_buffer(buf)
+        self.gpersist = buf
 
     def P(self, name):
         return self.pack.view(self.pflat, name)
@@ -267,7 +283,7 @@ class NetPlan:
         K.gather(self.dwflat, self.gpflat, self.idx_unpack)
         self.gpflat.zero_()
         K.wn_bwd(self.wn_tab, self.wn_rows, self.wn_n, self.wn_total)
-        out = self.gwork.clone()
+        out = self.gwork.clone() if self.gpersist is None else self.gwork
         return [out[self.poff[id(p)]:self.poff[id(p)] + p.numel()].view(p.shape) for p in self.params]
 
 

@@ -330,7 +330,7 @@ def d_update(g, d, opt_d, batch, clip=1.0, fgsm=False, with_x_grad_norm=False, c
 
 
 def g_update(g, d, opt_g, batch, clip=0.1, g_optim="boundary_seeking", feature_matching=False, adv_z=False,
-             check=False, lambda_fp=1.0, grad_sync=None, reinforce=False, baseline=None, fake_pass=None):
+             check=False, lambda_fp=1.0, grad_sync=None, reinforce=False, baseline=None, fake_pass=None, gather=None):
     """One generator update, audiogan.py:816-921 (core step: feature_matching = adv_z = reinforce = False).
     batch keys as oracle.restated.g_update.
 
@@ -354,8 +354,10 @@ def g_update(g, d, opt_g, batch, clip=0.1, g_optim="boundary_seeking", feature_m
         real = batch["real"] + batch["noise_real"]
         _, hs_d, hl_d, _ = d(real, batch["real_len"], batch["c_d"])
         fp = 0
-        for r, f in zip(calc_dists(hs_d, hl_d), calc_dists(hs_g, hl_g)):
-            fp = fp + torch.pow(r[0] - f[0], 2).mean() / fake.shape[0]
+        # data-parallel: `gather` (dist.gather_batch) makes the batch moments those of the global minibatch (:350-358)
+        nb = fake.shape[0] * (torch.distributed.get_world_size() if gather is not None and torch.distributed.is_initialized() else 1)
+        for r, f in zip(calc_dists(hs_d, hl_d, gather), calc_dists(hs_g, hl_g, gather)):
+            fp = fp + torch.pow(r[0] - f[0], 2).mean() / nb
     tgt = 0.5 if g_optim == "boundary_seeking" else 0.0                          # :857-860
     _loss, loss_ps, _ = masked_bce_mean(cls_g, nframes_g, tgt, -1.0)             # :864, :897
     loss = _loss if fp is None else _loss + fp * lambda_fp                      # :898

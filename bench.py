@@ -190,7 +190,20 @@ def run_ours(args):
     agd.broadcast_parameters([g, d])
     opt_d = ag.FusedRMSprop(d.parameters(), lr=1e-4)
     opt_g = ag.FusedRMSprop(g.parameters(), lr=1e-4)
-    sync = agd.GradSync(nbuckets=4) if world > 1 else None
+    # data-parallel gradient all-reduce: the library's peer-memory kernels over NVLink (default), or bucketed NCCL
+    # (AUDIOGAN_DP=nccl; AUDIOGAN_DP_BUCKETS buckets per net)
+    sync, dp_note = None, "single GPU"
+    if world > 1 and os.environ.get("AUDIOGAN_DP", "peer") == "peer":
+        try:
+            sync = agd.PeerGradSync([g, d])
+            dp_note = "two-shot all-reduce over NVLink peer memory (csrc/peer.cu), captured in the step's graph"
+        except Exception as e:                                   # noqa: BLE001 -- reported, never silent
+            sys.stderr.write("[bench] peer-memory all-reduce unavailable (%r): using NCCL\n" % (e,))
+            dp_note = "NCCL (peer-memory path unavailable: %s)" % (str(e).splitlines()[0][:120],)
+    if world > 1 and sync is None:
+        nb = int(os.environ.get("AUDIOGAN_DP_BUCKETS", "1"))
+        sync = agd.GradSync(nbuckets=nb)
+        dp_note = dp_note if dp_note.startswith("NCCL (") else "NCCL all-reduce, %d bucket(s) per net, after backward" % nb
     # AUDIOGAN_DP_EARLY=1: packed gradient regions are all-reduced while backward is still running.  Off by default: measured
     # 0.4 ms/step SLOWER at 2 GPUs (15.65-15.72 vs 15.26-15.31 ms) -- the NCCL CTAs take SMs the recurrent kernels' clusters need
     if sync is not None and os.environ.get("AUDIOGAN_DP_EARLY", "0") == "1":
@@ -244,7 +257,7 @@ def run_ours(args):
     if args.graph:
         try:
             gs = ag.GraphedStep(g, d, opt_d, opt_g, resident[0], clip_d=1.0, clip_g=0.1, grad_sync=sync, warmup=1)
-            graph_note = "one CUDA graph per step (%d library launches + torch fills/copies captured)" % gs.launches
+            graph_note = "%s per step (%d library launches + torch fills/copies captured)" % ("one CUDA graph" if len(gs.graphs) == 1 else "%d CUDA graph segments cut at the gradient all-reduces" % len(gs.graphs), gs.launches)
         except Exception as e:                                   # noqa: BLE001 -- reported in the JSON line, never silent
             gs, graph_note = None, "eager launches: graph capture failed: %s" % (str(e).splitlines()[0][:200],)
             sys.stderr.write("[bench] CUDA graph capture failed, timing eager launches: %r\n" % (e,))
@@ -273,7 +286,7 @@ def run_ours(args):
     if args.quick:
         if rank == 0:
             emit({"quick": True, "ms_per_step": round(ms_step, 4), "value": round(value, 2), "gpu_launches": launches,
-                  "launch_mode": graph_note, "n_gpus": world, "workload": "%s, per-GPU batch %d, L=%d" % (nets, B, L),
+                  "launch_mode": graph_note, "dp_allreduce": dp_note, "n_gpus": world, "workload": "%s, per-GPU batch %d, L=%d" % (nets, B, L),
                   "step_tflops": round(world * B * fps / (ms_step * 1e-3) / 1e12, 3),
                   "recurrent_paths": dict(g._plan.last_path, **d._plan.last_path)})
         return
@@ -391,6 +404,7 @@ def run_ours(args):
                 "pipeline": "inputs double-buffered on a copy stream, losses read back three steps late"},
         "gpu_launches": launches,
         "launch_mode": graph_note,
+        "dp_allreduce": dp_note,
         "clocks": clocks,
         "roofline": roofline,
         "ms_per_step_instrumented": round(ms_inst, 4),

@@ -343,6 +343,18 @@ int ag_mt_adam(const ag_mt_entry* table, const int32_t* chunk_tensor, const int6
                int32_t nchunks, int32_t chunk, const float* sqnorm, float clip, float gscale,
                double lr, double beta1, double beta2, double eps, int32_t step, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel gradient all-reduce over NVLink peer memory (replaces NN.DataParallel's gradient gather, audiogan.py:379-410,
+ * and the NCCL all-reduce between backward and the optimizer step).  buf_ptrs_dev / sig_ptrs_dev: DEVICE arrays of `world`
+ * pointers -- rank r's gradient buffer (n floats, n % 4 == 0, 16-byte aligned) and rank r's signal pad (>= 64 int32, zeroed
+ * once) as mapped into THIS process (symmetric memory).  ag_peer_allreduce: barrier, rank `rank` sums its 1/world range of all
+ * ranks' buffers and stores the sums into all ranks' buffers, barrier; on return (in stream order) every buffer holds the
+ * sum.  Every rank must issue the same sequence of calls.  nblocks <= 0: 2 x SM count.  Plain kernel launches: capturable.
+ * ------------------------------------------------------------------------------------------ */
+int ag_peer_barrier(void* const* sig_ptrs_dev, int32_t rank, int32_t world, void* stream);
+int ag_peer_allreduce(void* const* buf_ptrs_dev, void* const* sig_ptrs_dev, int32_t rank, int32_t world, int64_t n,
+                      int32_t nblocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

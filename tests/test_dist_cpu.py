@@ -79,6 +79,18 @@ def _worker(rank, world, port, q):
     local_mean = x[off:off + per].mean().reshape(1)
     dist.all_reduce(local_mean)
     assert abs(float(local_mean) * scale - float(x.mean())) < 1e-6
+    # semantic reductions: accuracy counters, NaN flag, batch statistics over the GLOBAL minibatch
+    st_d, st_g = agd.reduce_stats(T.tensor([3.0 + rank, 10.0]), T.tensor([1.0, 4.0 + rank]))
+    assert T.equal(st_d, T.tensor([7.0, 20.0])) and T.equal(st_g, T.tensor([2.0, 9.0]))
+    assert agd.any_rank(rank == 1) is True and agd.any_rank(False) is False
+    full = T.arange(24, dtype=T.float32).view(3, 4, 2) ** 1.5
+    mine = full[:, rank * 2:(rank + 1) * 2].clone().requires_grad_(True)
+    gq = agd.gather_batch(mine, dim=1)
+    assert T.equal(gq.detach(), full)
+    (gq.std(1) ** 2).sum().backward()                      # a function of the global batch, identical on both ranks
+    ref = full.clone().requires_grad_(True)
+    (ref.std(1) ** 2).sum().backward()
+    assert T.allclose(mine.grad, ref.grad[:, rank * 2:(rank + 1) * 2] * world)     # x world: the optimizer divides by it
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, "ok"))
