@@ -8,3 +8,4 @@ from .modules import (Generator, Discriminator, Embedder, binary_cross_entropy_w
 from .train import (FusedRMSprop, check_grad, clip_grad, d_update, g_update, core_step, masked_bce_mean,  # noqa: F401
                     adversarial_movement_d, adversarially_sample_z)
 from .graph import GraphedStep  # noqa: F401,E402
+from .feed import StepFeed, make_sample, collate, save_checkpoint, load_checkpoint  # noqa: F401,E402

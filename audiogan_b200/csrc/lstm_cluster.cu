@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(GT * MAXG, 1) lstm_cl_fwd_kernel(const ag_lstm
   const uint32_t idesc = umma_idesc(128, NBG, 0, 0);
   const int64_t hstr = (int64_t)(Tcap + 2) * ndir * H, gstr = (int64_t)Tcap * ndir * 4 * H, cstr = (int64_t)Tcap * ndir * H;
   __nv_bfloat16* hb16 = reinterpret_cast<__nv_bfloat16*>(d.hbuf16);
+  const bool want_h32 = !(d.flags & AG_LSTM_BF16_H_ONLY);       // bf16 mode: every consumer of h reads the bf16 copy
   const uint32_t bt_local = smem_u32(Bt), full_local = smem_u32(full), hs_local = smem_u32(hs);
   uint32_t nuse0 = 0, nuse1 = 0, nmma = 0;     // completed phases of full[0], full[1], mma_done
   Clk ck;
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(GT * MAXG, 1) lstm_cl_fwd_kernel(const ag_lstm
         if (s + 1 < T) load_pre(dir ? (T - 2 - s) : (s + 1));
         if (bme < B) {
           const int64_t ho = bme * hstr + (int64_t)(t + 1) * ndir * H + dir * H + j0 + j4;
-          *reinterpret_cast<float4*>(d.hbuf + ho) = hv;
+          if (want_h32) *reinterpret_cast<float4*>(d.hbuf + ho) = hv;
           *reinterpret_cast<uint2*>(hb16 + ho) = h16;
           if (d.cbuf) *reinterpret_cast<float4*>(d.cbuf + bme * cstr + (int64_t)t * ndir * H + dir * H + j0 + j4) = cv;
           if (d.gates) {
@@ -444,6 +445,7 @@ __global__ void __launch_bounds__(GT * MAXG_BWD, 1) lstm_cl_bwd_kernel(const ag_
   const int64_t gstr = (int64_t)Tcap * ndir * 4 * H, cstr = (int64_t)Tcap * ndir * H;
   const int64_t dhbs = d.dh_ext_bs ? d.dh_ext_bs : cstr;
   __nv_bfloat16* dg16 = reinterpret_cast<__nv_bfloat16*>(d.dgates16);
+  const bool want_f32 = !(dg16 && (d.flags & AG_LSTM_BF16_DGATES_ONLY));   // bf16 mode: every consumer reads the bf16 copy
   const uint32_t bop_local = smem_u32(Bop), stage_local = smem_u32(stage), red_local = smem_u32(red), full_local = smem_u32(full);
   uint32_t nuse0 = 0, nuse1 = 0, nmma = 0;
   Clk ck;
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(GT * MAXG_BWD, 1) lstm_cl_bwd_kernel(const ag_
           const int64_t o = bme * gstr + (int64_t)t * ndir * 4 * H + dir * 4 * H + j0 + j4;
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
-            *reinterpret_cast<float4*>(d.dgates + o + qq * H) = dq[qq];
+            if (want_f32) *reinterpret_cast<float4*>(d.dgates + o + qq * H) = dq[qq];
             if (dg16) *reinterpret_cast<uint2*>(dg16 + o + qq * H) = d16[qq];
           }
         }

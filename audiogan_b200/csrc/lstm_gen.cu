@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
   const int64_t hstr = (int64_t)(Tcap + 2) * H, gstr = (int64_t)Tcap * 4 * H, cstr = (int64_t)Tcap * H, xstr = (int64_t)(Tcap + 1) * F;
   __nv_bfloat16* hb16 = reinterpret_cast<__nv_bfloat16*>(d.hbuf16);
   __nv_bfloat16* xb16 = reinterpret_cast<__nv_bfloat16*>(d.xbuf16);
+  const bool want_h32 = !(d.flags & AG_LSTM_BF16_H_ONLY);
   // cell-update items: sample bl, units jv .. jv + JV - 1
   const int bl = tid / TPS, jv = (tid % TPS) * JV, bme = b0 + bl;
   float cst[JV];
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
       const int64_t ho = bme * hstr + (int64_t)(t + 1) * H + j0 + jv;
 #pragma unroll
       for (int e = 0; e < JV; e += 2) {
-        *reinterpret_cast<float2*>(d.hbuf + ho + e) = make_float2(hv[e], hv[e + 1]);
+        if (want_h32) *reinterpret_cast<float2*>(d.hbuf + ho + e) = make_float2(hv[e], hv[e + 1]);
         *reinterpret_cast<uint32_t*>(hb16 + ho + e) = pack_bf16(hv[e], hv[e + 1]);
       }
       if (d.cbuf) {
@@ -680,6 +681,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_bwd_kernel(const ag_lstm_desc 
   const uint32_t as_local = smem_u32(As), bop_local = smem_u32(Bop);
   const int64_t gstr = (int64_t)Tcap * 4 * H, cstr = (int64_t)Tcap * H, xstr = (int64_t)(Tcap + 1) * F;
   __nv_bfloat16* dg16 = reinterpret_cast<__nv_bfloat16*>(d.dgates16);
+  const bool want_f32 = !(dg16 && (d.flags & AG_LSTM_BF16_DGATES_ONLY));
   __nv_bfloat16* dp16 = reinterpret_cast<__nv_bfloat16*>(d.dpx16);
   // cell-backward items: sample bl, units jv, jv + 1;   reduce items: row rr, sample pair sp
   const int bl = tid >> 4, jv = (tid & 15) * 2, bme = b0 + bl;
@@ -928,7 +930,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_bwd_kernel(const ag_lstm_desc 
         *reinterpret_cast<uint32_t*>(Bop + (lr >> 3) * (NB * 16) + bl * 16 + (lr & 7) * 2) = pk;
         if (bme < B) {
           const int64_t off = bme * gstr + (int64_t)t * 4 * H + qq * H + j0 + jv;
-          *reinterpret_cast<float2*>(d.dgates + off) = make_float2(o[qq][0], o[qq][1]);
+          if (want_f32) *reinterpret_cast<float2*>(d.dgates + off) = make_float2(o[qq][0], o[qq][1]);
           if (dg16) *reinterpret_cast<uint32_t*>(dg16 + off) = pk;
         }
       }

@@ -88,7 +88,7 @@ class _GenFn(torch.autograd.Function):
             K.lstm_fwd(B=sl.stop - sl.start, T=Tcap, Tcap=Tcap, H=H, ndir=1, F=F, pre=pre[sl], w1=plan.Poff("w1"), w2=plan.Poff("w2"),
                        b2=plan.Poff("b2"), hbuf=hbuf[sl], gates=cut(gates), cbuf=cut(cbuf), xbuf=xbuf[sl], sbuf=sbuf[sl], u=u,
                        stop=stop[sl], glen=glen[sl], t_end=(misc, 8), barrier=misc, prec=plan.lstm_prec if bf else 0,
-                       hbuf16=cut(hbuf16), xbuf16=cut(xbuf16), flags=plan.lstm_flags | 2, ll_ws=ll_ws,
+                       hbuf16=cut(hbuf16), xbuf16=cut(xbuf16), flags=plan.lstm_flags | 2 | (8 if u is None else 0), ll_ws=ll_ws,
                        ll_ws_bytes=ll_ws.numel() if ll_ws is not None else 0)
         plan.last_path["g_fwd"] = K.lstm_last_path()
         if u is not None and early_exit_sync:
@@ -225,7 +225,8 @@ class _GenFn(torch.autograd.Function):
             K.lstm_bwd(B=sl.stop - sl.start, T=T, Tcap=Tcap, H=H, ndir=1, F=F, gates=gates[sl], cbuf=cbuf[sl], xbuf=xbuf[sl],
                        dx_ext=cut(dx_ext), ds_ext=cut(ds_ext), dgates=dgates[sl], dpx=dpx[sl], w1t=plan.Poff("w1t"),
                        wxt=plan.Poff("wxt"), barrier=misc, prec=plan.lstm_prec if bf else 0, dgates16=cut(dgates16),
-                       dpx16=cut(dpx16), flags=plan.lstm_flags | 2, ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel() if ll_ws is not None else 0)
+                       dpx16=cut(dpx16), flags=plan.lstm_flags | 2 | (4 if T == Tcap else 0), ll_ws=ll_ws,
+                       ll_ws_bytes=ll_ws.numel() if ll_ws is not None else 0)
             if chunk < B:
                 misc.zero_()
         plan.last_path["g_bwd"] = K.lstm_last_path()
@@ -398,7 +399,8 @@ class _DiscTailFn(torch.autograd.Function):
         cbuf = _empty(B, Tm, 2 * H, device=dev)
         misc = torch.zeros(16, device=dev, dtype=torch.int32)
         K.lstm_fwd(B=B, T=Tm, Tcap=Tm, H=H, ndir=2, F=0, pre=pre, w1=plan.Poff("w1"), hbuf=hbuf, gates=gates, cbuf=cbuf,
-                   len=nfr, barrier=misc, prec=plan.lstm_prec if bf else 0, hbuf16=hbuf16, flags=plan.lstm_flags)
+                   len=nfr, barrier=misc, prec=plan.lstm_prec if bf else 0, hbuf16=hbuf16,
+                   flags=plan.lstm_flags | (8 if bf else 0))       # bf16 mode: h is consumed as bf16 only (fallback kernels ignore the bit)
         plan.last_path["d_fwd"] = K.lstm_last_path()
         # residual_net + classifier on the (B*Tm) rows (audiogan.py:547-549); same row geometry as hbuf
         geo = (Tm, (Tm + 2) * S, S)
@@ -464,7 +466,7 @@ class _DiscTailFn(torch.autograd.Function):
         dgates16 = torch.empty(B, Tm, 8 * H, device=dev, dtype=torch.bfloat16) if bf else None
         K.lstm_bwd(B=B, T=Tm, Tcap=Tm, H=H, ndir=2, F=0, gates=gates, cbuf=cbuf, len=nfr, dh_ext=(dh_ext, S),
                    dh_ext_bs=(Tm + 2) * S, dgates=dgates, w1t=plan.Poff("w1t"), barrier=misc,
-                   prec=plan.lstm_prec if bf else 0, dgates16=dgates16, flags=plan.lstm_flags)
+                   prec=plan.lstm_prec if bf else 0, dgates16=dgates16, flags=plan.lstm_flags | 4)
         plan.last_path["d_bwd"] = K.lstm_last_path()
         dgo, hbo = (dgates16, hbuf16) if bf else (dgates, hbuf)
         dgsum = None

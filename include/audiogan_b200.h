@@ -146,6 +146,9 @@ typedef struct ag_lstm_desc {
 
 #define AG_LSTM_GRID_ONLY 1
 #define AG_LSTM_ALLOW_TMEM 2
+#define AG_LSTM_BF16_H_ONLY 8         /* forward on the cluster / TMEM-resident kernels: h_t goes to hbuf16 only (fp32 `hbuf` untouched) */
+#define AG_LSTM_BF16_DGATES_ONLY 4   /* BPTT on the cluster / TMEM-resident kernels: write the gate gradients to dgates16 only (the
+                                        fp32 `dgates` is then left untouched; bf16 mode's GEMMs read the bf16 copy) */
 int ag_lstm_fwd(const ag_lstm_desc* d, void* stream);
 int ag_lstm_bwd(const ag_lstm_desc* d, void* stream);
 /* Bytes of `ll_ws` the TMEM-resident generator kernels need for this descriptor's (B, H, F) -- forward (bwd == 0) or BPTT

@@ -718,3 +718,20 @@ def test_time_moments_kernels_match_reference_formula(dt, Bn, Cn, Tn):
     gref = (hr.grad * mask.unsqueeze(1).double()).float()               # the gradient past a sample's length is masked away
     got = h.grad.float().cpu() * mask.unsqueeze(1)
     assert rel(got, gref) < (2e-5 if dt == T.float32 else 8e-3), rel(got, gref)
+
+
+def test_step_feed_delivers_every_batch_in_order():
+    """feed.StepFeed: pinned staging + copy stream + two device slots; batches arrive intact and in order while the consumer
+    keeps the previous slot busy; host metadata (`*_len`) passes through."""
+    from audiogan_b200.feed import StepFeed
+    gen = T.Generator().manual_seed(0)
+    src = [{"real": T.randn(4, 1000, generator=gen), "z": T.randn(4, 5, 100, generator=gen), "real_len": T.full((4,), 1000)}
+           for _ in range(7)]
+    feed = StepFeed(iter(src), "cuda")
+    seen, acc = 0, T.zeros((), device="cuda")
+    for i, b in enumerate(feed):
+        assert b["real"].is_cuda and not b["real_len"].is_cuda
+        acc = acc + (b["real"].double().sum() + b["z"].double().sum()).float()          # consumer work on the current stream
+        assert T.equal(b["real"].cpu(), src[i]["real"]) and T.equal(b["z"].cpu(), src[i]["z"])
+        seen += 1
+    assert seen == 7 and feed.h2d_bytes == 4 * (4 * 1000 + 4 * 5 * 100)

@@ -195,3 +195,34 @@ def test_reference_class_step_matches_restated_step():
             err = (v - P[k]).abs()
             # the first RMSprop step is sign-like: elements whose gradient is rounding noise may step the other way
             assert float((err > 5e-6).float().mean()) < 1e-3 and float(err.max()) < 2.1e-3, (k, float(err.max()))
+
+
+def test_feed_collation_and_checkpoint_names_match_reference_conventions(tmp_path):
+    """feed.make_sample / collate against dataset.py:48-71 (zero row of maxlen, peak normalisation, length rounded up to the
+    frame, over-long and silent waveforms rejected) and the checkpoint round trip with the reference's file names and keys."""
+    import numpy as np
+    import audiogan_b200 as ag
+    from audiogan_b200 import feed
+    rng = np.random.default_rng(0)
+    w = np.concatenate([rng.standard_normal(1234) * 3.0, np.zeros(50)])
+    row, ln = feed.make_sample(w, 2000, frame_size=200)
+    assert row.shape == (2000,) and row.dtype == np.float32 and ln == 1400 and abs(float(np.abs(row).max()) - 1.0) < 1e-6
+    assert np.all(row[1234:] == 0) and np.allclose(row[:1234], (w[:1234] / np.abs(w).max()).astype(np.float32))
+    assert feed.make_sample(w, 1000) == (None, None) and feed.make_sample(np.zeros(10), 100) == (None, None)
+    assert feed.make_sample(w, 2000)[1] == 1234
+    b = feed.collate([(row, ln), (row, ln)], words=["hello", "hi"])
+    assert b["real"].shape == (2, 2000) and b["real_len"].tolist() == [1400, 1400]
+    assert b["chars"].shape == (2, 5) and b["chars"][1].tolist() == [104, 105, 0, 0, 0] and b["char_len"].tolist() == [5, 2]
+    g = ag.Generator(embed_size=100, state_size=32)
+    d = ag.Discriminator(embed_size=100, state_size=32)
+    paths = feed.save_checkpoint(str(tmp_path / "m"), 500, g=g, d=d)
+    assert paths["g"].endswith("m-gen-00500") and paths["d"].endswith("m-dis-00500")          # audiogan.py:936-937
+    g2 = ag.Generator(embed_size=100, state_size=32)
+    d2 = ag.Discriminator(embed_size=100, state_size=32)
+    feed.load_checkpoint(str(tmp_path / "m"), 500, g=g2, d=d2)
+    for a, b_ in zip(list(g.parameters()) + list(d.parameters()), list(g2.parameters()) + list(d2.parameters())):
+        assert T.equal(a, b_)
+    if R.available():                                  # the reference's own module takes the file as it is
+        ns = R.load()
+        ref = ns["Generator"](embed_size=100, state_size=32)
+        ref.load_state_dict(T.load(paths["g"]))

@@ -591,7 +591,7 @@ def test_cuda_graph_step_equals_eager_step():
         if not noise_only(k):
             # three sign-like RMSprop steps: an element whose gradient is rounding noise may step the other way
             err = (p - q).abs()
-            assert float((err > 1e-6).float().mean()) < 2e-3 and float(err.max()) < 6.1e-3, (k, float(err.max()))
+            assert float((err > 5e-6).float().mean()) < 2e-3 and float(err.max()) < 6.1e-3, (k, float(err.max()))
     with pytest.raises(ValueError):
         bad = dict(batches[1]); bad["real_len"] = bad["real_len"] - 200
         gs.load(bad)
