@@ -1,7 +1,7 @@
 """1000-step loss trajectories with an ORACLE-vs-ORACLE control band (north_star: "loss trajectories must track over 1k steps";
 VERDICT r1: the divergence of the round-1 curves was called chaos without a control run).
 
-    python tests/trajectory_control.py oracle   # CPU, build container: writes tests/golden/trajectory_control.pt
+    python tests/trajectory_control.py oracle   # CPU, build container: writes tests/golden/aux/trajectory_control.pt
     python tests/trajectory_control.py cuda     # GPU box: CUDA fp32 / bf16 curves against the committed control band
 
 Control = the SAME CPU oracle (oracle/restated.py) run four ways that differ only at rounding level: fp32, fp64, and fp32
@@ -18,7 +18,7 @@ from audiogan_b200.synthetic import step_inputs
 
 NSTEPS, W = 1000, 50
 CS = dict(B=16, L=800, gk={"state_size": 32}, dk={"state_size": 32})
-GOLD = os.path.join(ROOT, "tests", "golden", "trajectory_control.pt")
+GOLD = os.path.join(ROOT, "tests", "golden", "aux", "trajectory_control.pt")
 batches = [step_inputs(CS["B"], CS["L"], seed=100 + i, full_length=True) for i in range(8)]
 gb = lambda dd: {"c_g": dd["g_c_g"], "c_d": dd["g_c_d"], "z": dd["g_z"], "noise_fake": dd["g_noise_fake"]}
 
@@ -61,7 +61,7 @@ if sys.argv[1] == "oracle":
         t0 = time.time()
         curves[name] = oracle_curve(*args)
         print(name, "%.0f s" % (time.time() - t0), windows(curves[name])[-1].tolist(), flush=True)
-    T.save({"case": CS, "nsteps": NSTEPS, "curves": curves, "torch": T.__version__}, GOLD)
+    T.save({"case": CS, "nsteps": NSTEPS, "curves": curves, "torch": str(T.__version__)}, GOLD)
 else:
     import audiogan_b200 as ag
     from test_parity_gpu import to_dev
