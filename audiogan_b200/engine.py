@@ -25,6 +25,63 @@ DPAD = 3        # zero rows either side of the discriminator's channel-last acti
 _ACT_BF16 = os.environ.get("AUDIOGAN_ACT", "bf16") != "fp32"
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# "Shadow" work.  The recurrent kernels are latency-bound and occupy 64-128 of the 148 SMs for 0.6-1.1 ms each; throughput-bound
+# work that nothing on the critical path waits for (the tail's weight gradients; the conv stack of the generator samples that
+# only the G-update will read) is queued here and launched on a side stream right AFTER such a kernel has been issued, so it
+# runs on the idle SMs underneath it.  AUDIOGAN_OVERLAP=0 runs everything in line.
+# ---------------------------------------------------------------------------------------------------------------------
+_OVERLAP = os.environ.get("AUDIOGAN_OVERLAP", "1") != "0"
+_side_streams = {}
+_shadow_jobs = {}          # device -> [callable]
+
+
+def _side_stream(dev):
+    s = _side_streams.get(dev)
+    if s is None:
+        s = _side_streams[dev] = torch.cuda.Stream(dev)
+    return s
+
+
+def shadow_submit(dev, fn):
+    """queue `fn` (kernel launches whose operands the caller keeps alive until shadow_join)"""
+    _shadow_jobs.setdefault(dev, []).append(fn)
+
+
+def shadow_ready(dev):
+    """call BEFORE issuing a latency-bound kernel: marks the point queued jobs may start after.  Returns a token or None."""
+    if not _shadow_jobs.get(dev):
+        return None
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    return ev
+
+
+def shadow_launch(dev, token):
+    """call right AFTER the latency-bound kernel has been issued on the current stream"""
+    jobs = _shadow_jobs.get(dev)
+    if token is None or not jobs:
+        return
+    side = _side_stream(dev)
+    side.wait_event(token)
+    with torch.cuda.stream(side):
+        for fn in jobs:
+            fn()
+    jobs.clear()
+    _side_streams[(dev, "busy")] = True
+
+
+def shadow_join(dev):
+    """everything queued so far has been issued and the current stream waits for it"""
+    jobs = _shadow_jobs.get(dev)
+    if jobs:                                                   # no launch point came by: run them now, in line
+        for fn in jobs:
+            fn()
+        jobs.clear()
+    if _side_streams.pop((dev, "busy"), False):
+        torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))
+
+
 def _adt(plan):
     return torch.bfloat16 if (plan.mode == "bf16" and _ACT_BF16) else torch.float32
 
@@ -42,7 +99,7 @@ def _empty(*shape, device, dtype=torch.float32):
 # =========================================================================================
 class _GenFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan, struct, token, zc1, u_stop, early_exit_sync, grad_from=0):
+    def forward(ctx, plan, struct, token, zc1, u_stop, early_exit_sync, grad_from=0, defer_tail=False):
         """zc1: (B, T, NZ+2) = [noise | conditioning | 1 | 1].  Returns (x (B, t*F), s (B, t), stop (B, t) int32,
         glen (B,) int32).  ``grad_from``: only samples [grad_from, B) take part in the backward pass (train.core_step runs the
         D-update's detached generator pass and the G-update's pass as ONE forward; the first half is never differentiated)."""
@@ -100,34 +157,48 @@ class _GenFn(torch.autograd.Function):
         # frame assembly into channel 0 of the dense buffer (audiogan.py:462-464)
         adt = _adt(plan)
         Xd = _empty(B, Lp, CT, device=dev, dtype=adt)       # CT = padded channel count (slots of 8, plan.py)
-        K.zero_pads(Xd, GPAD, GPAD + L)
-        # frames -> channel 0 of the waveform slot, its pad channels zeroed in the same pass
-        K.frames_to_slot((Xd, GPAD * CT), Lp * CT, CT, plan.coff[0], (xbuf, F), (Tcap + 1) * F, B, L)
-        hh = []
-        lenL = plan.const_len(B, L)
-        for li, (k, s, hid, out) in enumerate(struct):                       # audiogan.py:278-283, :465-467
-            p, pd, Lh = (k - 1) // 2, s // 2, L // s
-            cin = plan.cinp[li]                             # padded channel prefix this block reads == slot it writes
-            Hh = _empty(B, Lh + 2, hid, device=dev, dtype=adt)
-            K.zero_pads(Hh, 1, Lh + 1)
-            # TMA-fed kernel over a 4-D tensor map (channel prefix, row, tap, batch).  Its boxes have 16-byte inner rows, so for
-            # wide prefixes the producer-warp kernel is faster (measured: cin 8 / 24 -> 1.9x / 1.5x faster, 56 equal, 88 0.6x)
-            if adt == torch.bfloat16 and cin <= 32:
-                K.gemm_nt(B * Lh, hid, k * cin, (Xd, (GPAD - p) * CT), (Lh, Lp * CT, s * CT, cin, CT),
-                          plan.Poff("c%d.wq" % li), plan.Kq[li], (Hh, hid), (Lh, (Lh + 2) * hid, hid),
-                          bias=plan.Poff("c%d.b" % li), act=1, a_layout=1)
-            else:
-                K.gemm_nt(B * Lh, hid, k * cin, (Xd, (GPAD - p) * CT), (Lh, Lp * CT, s * CT, cin, CT),
-                          plan.Poff("c%d.w" % li), k * cin, (Hh, hid), (Lh, (Lh + 2) * hid, hid),
-                          bias=plan.Poff("c%d.b" % li), act=1)
-            skip = (Xd, (GPAD - pd) * CT + plan.skip_off[li]) if plan.skip_off[li] >= 0 else None
-            K.gemm_nt(B * (Lh + 1), s * out, 2 * hid, Hh, (Lh + 1, (Lh + 2) * hid, hid),
-                      plan.Poff("d%d.w" % li), 2 * hid, (Xd, (GPAD - pd) * CT + cin), (Lh + 1, Lp * CT, s * CT, out, CT),
-                      bias=plan.Poff("d%d.b" % li), bias_mod=out, skip=skip, act=1,
-                      mask_len=lenL, mask=(s, 1, -pd))
-            hh.append(Hh)
+        hh = [_empty(B, L // s + 2, hid, device=dev, dtype=adt) for (k, s, hid, out) in struct]
         xout = _empty(B, L, device=dev)
-        K.conv1out_fwd((Xd, (GPAD - 1) * CT), Lp * CT, CT, 3, plan.Poff("f.w"), plan.Poff("f.b"), xout, B, L)
+
+        def conv_stack(b0, b1):
+            """frames -> dense buffer -> the four bottleneck blocks -> final conv, for samples [b0, b1) (batch-major buffers)"""
+            n = b1 - b0
+            Xs, xb = Xd[b0:b1], xbuf[b0:b1]
+            K.zero_pads(Xs, GPAD, GPAD + L)
+            # frames -> channel 0 of the waveform slot, its pad channels zeroed in the same pass
+            K.frames_to_slot((Xs, GPAD * CT), Lp * CT, CT, plan.coff[0], (xb, F), (Tcap + 1) * F, n, L)
+            lenL = plan.const_len(n, L)
+            for li, (k, s, hid, out) in enumerate(struct):                       # audiogan.py:278-283, :465-467
+                p, pd, Lh = (k - 1) // 2, s // 2, L // s
+                cin = plan.cinp[li]                             # padded channel prefix this block reads == slot it writes
+                Hh = hh[li][b0:b1]
+                K.zero_pads(Hh, 1, Lh + 1)
+                # TMA-fed kernel over a 4-D tensor map (channel prefix, row, tap, batch).  Its boxes have 16-byte inner rows, so
+                # for wide prefixes the producer-warp kernel is faster (measured: cin 8 / 24 -> 1.9x / 1.5x faster, 56 equal, 88 0.6x)
+                if adt == torch.bfloat16 and cin <= 32:
+                    K.gemm_nt(n * Lh, hid, k * cin, (Xs, (GPAD - p) * CT), (Lh, Lp * CT, s * CT, cin, CT),
+                              plan.Poff("c%d.wq" % li), plan.Kq[li], (Hh, hid), (Lh, (Lh + 2) * hid, hid),
+                              bias=plan.Poff("c%d.b" % li), act=1, a_layout=1)
+                else:
+                    K.gemm_nt(n * Lh, hid, k * cin, (Xs, (GPAD - p) * CT), (Lh, Lp * CT, s * CT, cin, CT),
+                              plan.Poff("c%d.w" % li), k * cin, (Hh, hid), (Lh, (Lh + 2) * hid, hid),
+                              bias=plan.Poff("c%d.b" % li), act=1)
+                skip = (Xs, (GPAD - pd) * CT + plan.skip_off[li]) if plan.skip_off[li] >= 0 else None
+                K.gemm_nt(n * (Lh + 1), s * out, 2 * hid, Hh, (Lh + 1, (Lh + 2) * hid, hid),
+                          plan.Poff("d%d.w" % li), 2 * hid, (Xs, (GPAD - pd) * CT + cin), (Lh + 1, Lp * CT, s * CT, out, CT),
+                          bias=plan.Poff("d%d.b" % li), bias_mod=out, skip=skip, act=1,
+                          mask_len=lenL, mask=(s, 1, -pd))
+            K.conv1out_fwd((Xs, (GPAD - 1) * CT), Lp * CT, CT, 3, plan.Poff("f.w"), plan.Poff("f.b"), xout[b0:b1], n, L)
+
+        gf0 = int(grad_from)
+        if defer_tail and _OVERLAP and bf and 0 < gf0 < B:
+            # train.core_step: samples [grad_from, B) are only read by the G-update -- their conv stack runs in the shadow of
+            # the D-update's recurrent kernels (shadow_join in core_step before the G-update touches them)
+            conv_stack(0, gf0)
+            plan.const_len(B - gf0, L)                           # cached on this stream, not inside the side stream's job
+            shadow_submit(dev, lambda: conv_stack(gf0, B))
+        else:
+            conv_stack(0, B)
         s_out = sbuf[:, :T]
         if save:
             gf = int(grad_from)
@@ -154,14 +225,26 @@ class _GenFn(torch.autograd.Function):
         Lp = L + 2 * GPAD
         wgrad = ctx.needs_input_grad[2] and wgrad_enabled()
         dx_ext = None
+        overlap, keep = False, []
         if gx is not None:
             gx = gx.contiguous()
             # ---- final conv (audiogan.py:403-407): data gradient into all CT channels, weight gradient
             adt = Xd.dtype
             dXd = _empty(B, Lp, CT, device=dev, dtype=adt)
             K.conv1out_dgrad(gx, plan.Poff("f.w"), (dXd, (GPAD - 1) * CT), Lp * CT, CT, 3, B, L)
+            # the conv stack's weight gradients are off the critical path: in bf16 mode they are queued and run on the side stream
+            # under the BPTT kernel below (whatever does not fit there finishes after it; joined at the end of this backward)
+            overlap = wgrad and bf and _OVERLAP and plan.early_sync is None
+            keep = []                                       # operands of queued jobs stay alive until the join
+
+            def wjob(fn):
+                if overlap:
+                    shadow_submit(dev, fn)
+                else:
+                    fn()
+
             if wgrad:
-                K.conv1out_wgrad(gx, (Xd, (GPAD - 1) * CT), Lp * CT, CT, 3, plan.GPoff("f.w"), B, L)
+                wjob(lambda: K.conv1out_wgrad(gx, (Xd, (GPAD - 1) * CT), Lp * CT, CT, 3, plan.GPoff("f.w"), B, L))
             for li in range(len(struct) - 1, -1, -1):
                 k, s, hid, out = struct[li]
                 cin = plan.cinp[li]
@@ -183,16 +266,21 @@ class _GenFn(torch.autograd.Function):
                 K.gemm_nt(B * Lh, hid, kd * out, dyl, (Lh, (L + 2 * pd) * out, s * out), plan.Poff("d%d.wg" % li), kd * out,
                           (dH, hid), (Lh, (Lh + 2) * hid, hid), dact=(Hh, hid))
                 if wgrad:
-                    K.gemm_tn(B * Lh, hid, kd * out, (Hh, hid), (Lh, (Lh + 2) * hid, hid), dyl,
-                              (Lh, (L + 2 * pd) * out, s * out), plan.GPoff("d%d.w" % li), kd * out)
-                    if adt == torch.bfloat16:
-                        Kq = plan.Kq[li]
-                        K.gemm_tn(B * Lh, hid, k * cin, (dH, hid), (Lh, (Lh + 2) * hid, hid), (Xd, (GPAD - p) * CT),
-                                  (Lh, Lp * CT, s * CT, cin, CT), plan.GPoff("c%d.wq" % li), Kq + 1, ones_col=True, a_layout=1)
-                        K.gather(plan.GPoff("c%d.w" % li), plan.GPoff("c%d.wq" % li), plan.q2c[li])
-                    else:
-                        K.gemm_tn(B * Lh, hid, k * cin, (dH, hid), (Lh, (Lh + 2) * hid, hid), (Xd, (GPAD - p) * CT),
-                                  (Lh, Lp * CT, s * CT, cin, CT), plan.GPoff("c%d.w" % li), k * cin + 1, ones_col=True)
+                    keep.append((dyl, dH))
+
+                    def block_wgrad(li=li, k=k, s=s, hid=hid, out=out, cin=cin, p=p, pd=pd, Lh=Lh, kd=kd, Hh=Hh, dyl=dyl, dH=dH):
+                        K.gemm_tn(B * Lh, hid, kd * out, (Hh, hid), (Lh, (Lh + 2) * hid, hid), dyl,
+                                  (Lh, (L + 2 * pd) * out, s * out), plan.GPoff("d%d.w" % li), kd * out)
+                        if adt == torch.bfloat16:
+                            Kq = plan.Kq[li]
+                            K.gemm_tn(B * Lh, hid, k * cin, (dH, hid), (Lh, (Lh + 2) * hid, hid), (Xd, (GPAD - p) * CT),
+                                      (Lh, Lp * CT, s * CT, cin, CT), plan.GPoff("c%d.wq" % li), Kq + 1, ones_col=True, a_layout=1)
+                            K.gather(plan.GPoff("c%d.w" % li), plan.GPoff("c%d.wq" % li), plan.q2c[li])
+                        else:
+                            K.gemm_tn(B * Lh, hid, k * cin, (dH, hid), (Lh, (Lh + 2) * hid, hid), (Xd, (GPAD - p) * CT),
+                                      (Lh, Lp * CT, s * CT, cin, CT), plan.GPoff("c%d.w" % li), k * cin + 1, ones_col=True)
+
+                    wjob(block_wgrad)
                 # conv data gradient (3 taps over dH), accumulated into channels [0, cin) of dXd
                 cdst = (dXd, (GPAD + s - p) * CT)
                 K.gemm_nt(B * Lh, s * cin, 3 * hid, dH, (Lh, (Lh + 2) * hid, hid), plan.Poff("c%d.wg" % li), 3 * hid,
@@ -219,6 +307,7 @@ class _GenFn(torch.autograd.Function):
         chunk = cap if (cap and B > cap) else B
         # reduce-scatter workspace of the TMEM-resident BPTT kernel (include/audiogan_b200.h: ag_lstm_desc.ll_ws)
         ll_ws = K.lstm_workspace(chunk, H, F, True, dev) if bf else None
+        ready = shadow_ready(dev) if bf else None
         for b0 in range(0, B, chunk):
             sl = slice(b0, min(B, b0 + chunk))
             cut = lambda t: t[sl] if t is not None else None
@@ -229,6 +318,8 @@ class _GenFn(torch.autograd.Function):
                        ll_ws_bytes=ll_ws.numel() if ll_ws is not None else 0)
             if chunk < B:
                 misc.zero_()
+            if b0 == 0:
+                shadow_launch(dev, ready)                # queued weight gradients run on the SMs the BPTT kernel leaves idle
         plan.last_path["g_bwd"] = K.lstm_last_path()
         # REINFORCE (audiogan.py:900-908): the score-function gradient of the stop logits reaches the stop head's weight and
         # bias ONLY (the reference freezes every other generator parameter for that backward), so it joins column F of dpx
@@ -255,8 +346,11 @@ class _GenFn(torch.autograd.Function):
             K.gemm_nt(B * T, NZ, 4 * H, dgo, (T, Tcap * 4 * H, 4 * H), plan.Poff("wzt"), 4 * H,
                       dzc1, (T, Tcap * (NZ + 2), NZ + 2))
             dzc1 = dzc1_all
+        if overlap:
+            shadow_join(dev)
+            keep.clear()
         gtok = torch.zeros(1, device=dev) if wgrad else None
-        return None, None, gtok, dzc1, None, None, None
+        return None, None, gtok, dzc1, None, None, None, None
 
 
 # =========================================================================================
@@ -398,9 +492,11 @@ class _DiscTailFn(torch.autograd.Function):
         gates = _empty(B, Tm, 8 * H, device=dev)
         cbuf = _empty(B, Tm, 2 * H, device=dev)
         misc = torch.zeros(16, device=dev, dtype=torch.int32)
+        ready = shadow_ready(dev) if bf else None
         K.lstm_fwd(B=B, T=Tm, Tcap=Tm, H=H, ndir=2, F=0, pre=pre, w1=plan.Poff("w1"), hbuf=hbuf, gates=gates, cbuf=cbuf,
                    len=nfr, barrier=misc, prec=plan.lstm_prec if bf else 0, hbuf16=hbuf16,
                    flags=plan.lstm_flags | (8 if bf else 0))       # bf16 mode: h is consumed as bf16 only (fallback kernels ignore the bit)
+        shadow_launch(dev, ready)
         plan.last_path["d_fwd"] = K.lstm_last_path()
         # residual_net + classifier on the (B*Tm) rows (audiogan.py:547-549); same row geometry as hbuf
         geo = (Tm, (Tm + 2) * S, S)
@@ -438,24 +534,36 @@ class _DiscTailFn(torch.autograd.Function):
         g = g.contiguous()
         geo = (Tm, (Tm + 2) * S, S)
         flat = lambda n: (M, 0, n)
+        # The tail's weight gradients are off the critical path (nothing downstream reads them before _PackFn.backward), and the
+        # BPTT kernel that follows is latency-bound on 64-96 of the 148 SMs: in bf16 mode they are issued on a side stream right
+        # AFTER the BPTT launch and run on the idle SMs underneath it (AUDIOGAN_OVERLAP=0: in line).  Not with the early
+        # all-reduce (GradSync.attach), which wants these gradients final before the BPTT starts.
+        overlap = wgrad and bf and _OVERLAP and plan.early_sync is None
+
+        def wjob(fn):
+            if overlap:
+                shadow_submit(dev, fn)
+            else:
+                fn()
+
         if wgrad and (S // 2) % 4 == 0 and S // 2 <= 1024:
-            K.wcolsum(g, h3, M, S // 2, plan.GPoff("k2.w"))             # Linear(S/2 -> 1): weighted column sum, not a GEMM
+            wjob(lambda: K.wcolsum(g, h3, M, S // 2, plan.GPoff("k2.w")))   # Linear(S/2 -> 1): weighted column sum, not a GEMM
         elif wgrad:
-            K.gemm_tn(M, 1, S // 2, g, flat(1), h3, flat(S // 2), plan.GPoff("k2.w"), S // 2 + 1, ones_col=True)
+            wjob(lambda: K.gemm_tn(M, 1, S // 2, g, flat(1), h3, flat(S // 2), plan.GPoff("k2.w"), S // 2 + 1, ones_col=True))
         adt = torch.bfloat16 if bf else torch.float32
         hin = hbuf16 if bf else hbuf
         dh3 = torch.empty(M, S // 2, device=dev, dtype=adt)
         K.outer_dact(g, plan.Poff("k2.w"), h3, dh3, M, S // 2)          # rank-1: dh3 = g (x) k2.w * lrelu'(h3)
         if wgrad:
-            K.gemm_tn(M, S // 2, S, dh3, flat(S // 2), (r2, S), geo, plan.GPoff("k0.w"), S + 1, ones_col=True)
+            wjob(lambda: K.gemm_tn(M, S // 2, S, dh3, flat(S // 2), (r2, S), geo, plan.GPoff("k0.w"), S + 1, ones_col=True))
         dz2 = torch.empty(B, Tm + 2, S, device=dev, dtype=adt)   # grads below keep the padded-row geometry of r1 / r2 / hbuf
         K.gemm_nt(M, S, S // 2, dh3, flat(S // 2), plan.Poff("k0.wt"), S // 2, (dz2, S), geo, dact=(r2, S))
         if wgrad:
-            K.gemm_tn(M, S, S, (dz2, S), geo, (r1, S), geo, plan.GPoff("r1.w"), S + 1, ones_col=True)
+            wjob(lambda: K.gemm_tn(M, S, S, (dz2, S), geo, (r1, S), geo, plan.GPoff("r1.w"), S + 1, ones_col=True))
         dz1 = torch.empty(B, Tm + 2, S, device=dev, dtype=adt)
         K.gemm_nt(M, S, S, (dz2, S), geo, plan.Poff("r1.wt"), S, (dz1, S), geo, skip=(dz2, S), dact=(r1, S))
         if wgrad:
-            K.gemm_tn(M, S, S, (dz1, S), geo, (hin, S), geo, plan.GPoff("r0.w"), S + 1, ones_col=True)
+            wjob(lambda: K.gemm_tn(M, S, S, (dz1, S), geo, (hin, S), geo, plan.GPoff("r0.w"), S + 1, ones_col=True))
         if wgrad:
             plan.reduce_span("r0.w", "k2.w")          # data-parallel: these gradients are final, reduce them under the BPTT
         dh_ext = _empty(B, Tm + 2, S, device=dev)
@@ -464,9 +572,11 @@ class _DiscTailFn(torch.autograd.Function):
         dgates = _empty(B, Tm, 8 * H, device=dev)
         misc = torch.zeros(16, device=dev, dtype=torch.int32)
         dgates16 = torch.empty(B, Tm, 8 * H, device=dev, dtype=torch.bfloat16) if bf else None
+        ready = shadow_ready(dev)                               # the queued jobs' operands are complete here
         K.lstm_bwd(B=B, T=Tm, Tcap=Tm, H=H, ndir=2, F=0, gates=gates, cbuf=cbuf, len=nfr, dh_ext=(dh_ext, S),
                    dh_ext_bs=(Tm + 2) * S, dgates=dgates, w1t=plan.Poff("w1t"), barrier=misc,
                    prec=plan.lstm_prec if bf else 0, dgates16=dgates16, flags=plan.lstm_flags | 4)
+        shadow_launch(dev, ready)
         plan.last_path["d_bwd"] = K.lstm_last_path()
         dgo, hbo = (dgates16, hbuf16) if bf else (dgates, hbuf)
         dgsum = None
@@ -491,6 +601,8 @@ class _DiscTailFn(torch.autograd.Function):
             dc = _empty(B, E, device=dev)
             K.gemm_nt(B, E, 8 * H, dgsum, (B, 0, 8 * H), plan.Poff("wiht", Cf * 8 * H), 8 * H,
                       dc, (B, 0, E))
+        if overlap:
+            shadow_join(dev)                                      # the side stream's weight gradients join before anything reads them
         gtok = torch.zeros(1, device=dev) if wgrad else None
         return None, gtok, dfeat, dc, None, None, None
 

@@ -16,6 +16,7 @@ they are fixed at capture time (a loop with ragged batches keeps one GraphedStep
 import torch
 
 from . import _abi as A
+from . import engine
 from . import train
 
 
@@ -84,6 +85,7 @@ class GraphedStep:
         def cut(params):
             """the all-reduce point between backward and the optimizer step: end this graph segment, reduce eagerly (on
             whatever the gradient buffers hold: nothing has executed yet), start the next segment"""
+            engine.shadow_join(self.device)                      # side-stream work must rejoin before a capture segment ends
             state["ctx"].__exit__(None, None, None)
             params = list(params)
             scale = self.grad_sync(params)

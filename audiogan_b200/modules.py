@@ -178,9 +178,11 @@ class Generator(_PlanOwner):
     def _build_plan(self, dev):
         return P.build_generator_plan(self, dev)
 
-    def forward(self, batch_size=None, length=None, z=None, c=None, u_stop="sample", grad_from=0):
+    def forward(self, batch_size=None, length=None, z=None, c=None, u_stop="sample", grad_from=0, defer_tail=False):
         """Returns (x (B, t*frame), s (B, t) stop logits, stop_list: t LongTensors (B, 1), length (B,) samples).
-        ``grad_from`` (extension, default 0): samples below this index are forward-only (train.core_step).
+        ``grad_from`` (extension, default 0): samples below this index are forward-only (train.core_step); ``defer_tail``: the
+        conv stack of samples [grad_from, B) may still be in flight on the side stream when this returns -- the caller must
+        call ``engine.shadow_join(device)`` before reading them (train.core_step does).
 
         ``u_stop``: uniforms (B, T) for the stop draw ``stop = u < sigmoid(logit)`` (audiogan.py:445-450 draws
         the same Bernoulli through ``multinomial``); "sample" draws them with torch.rand, None never stops."""
@@ -196,7 +198,7 @@ class Generator(_PlanOwner):
         if isinstance(u_stop, str):
             u_stop = torch.rand(batch_size, nframes, device=dev)
         token = P.pack(plan)
-        x, s, stop, glen = E._GenFn.apply(plan, self._struct, token, zc1, u_stop, self.early_exit_sync, grad_from)
+        x, s, stop, glen = E._GenFn.apply(plan, self._struct, token, zc1, u_stop, self.early_exit_sync, grad_from, defer_tail)
         stop_list = list(stop.long().unsqueeze(2).unbind(1))
         s._ag_stop, s._ag_glen = stop, glen          # raw int32 device copies for the REINFORCE kernel (train.g_update)
         out_len = glen.long() * self._frame_size

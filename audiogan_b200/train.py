@@ -13,6 +13,7 @@ from torch.autograd.function import once_differentiable
 
 from . import kernels as K
 from . import _abi as A
+from . import engine as E
 from .plan import no_weight_grads
 from .modules import (binary_cross_entropy_with_logits_per_sample, calc_dists, length_mask, cat_lengths, dev_i32)  # noqa: F401
 
@@ -395,7 +396,7 @@ def core_step(g, d, opt_d, opt_g, batch, clip_d=1.0, clip_g=0.1, g_optim="bounda
     Bn = batch["z"].shape[0]
     z_all = torch.cat([batch["z"], batch["g_z"]], 0)
     c_all = torch.cat([batch["c_g"], batch["g_c_g"]], 0)
-    fake_all, s_all, _, len_all = g(z=z_all, c=c_all, u_stop=None, grad_from=Bn)
+    fake_all, s_all, _, len_all = g(z=z_all, c=c_all, u_stop=None, grad_from=Bn, defer_tail=True)
     host = getattr(len_all, "_ag_host", None)
 
     def half(a, b):
@@ -407,6 +408,7 @@ def core_step(g, d, opt_d, opt_g, batch, clip_d=1.0, clip_g=0.1, g_optim="bounda
     _set_requires_grad(g, False)                                                # audiogan.py:706-709
     _set_requires_grad(d, True)
     m1 = _d_update_batched(g, d, opt_d, batch, clip_d, check, grad_sync, fake_pass=(fake_all[:Bn].detach(), half(0, Bn)))
+    E.shadow_join(fake_all.device)             # the second half's conv stack ran under the D-update's recurrent kernels
     gb = {"c_g": batch["g_c_g"], "c_d": batch["g_c_d"], "z": batch["g_z"], "noise_fake": batch["g_noise_fake"], "u_stop": None}
     m2 = g_update(g, d, opt_g, gb, clip=clip_g, g_optim=g_optim, check=check, grad_sync=grad_sync,
                   fake_pass=(fake_all[Bn:], s_all[Bn:], None, half(Bn, 2 * Bn)))

@@ -373,10 +373,10 @@ def run_ours(args):
     tname, (tms, tflops, tcount) = top
     achieved = (tflops / (tms * 1e-3)) / 1e12 if tms > 0 else 0.0
     # DRAM bytes per launch of that family, from the committed ncu launch list of this same command
-    # (tools/ncu_summary.py traffic -> profiles/r1_bf16_traffic.json); null when the capture is missing
+    # (tools/ncu_summary.py traffic -> profiles/r2_traffic.json, bf16 mode); null when the capture is missing
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_%s_traffic.json" % args.mode)) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json" if args.mode == "bf16" else "r1_fp32_traffic.json")) as f:
             traffic = round(json.load(f)[tname.split(" ")[0]]["dram_bytes_per_launch"])
     except (OSError, KeyError, ValueError):
         pass
