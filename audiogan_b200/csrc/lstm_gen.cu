@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace ag {
 namespace lg {
@@ -76,6 +77,14 @@ __device__ __forceinline__ void flag_publish(unsigned* flag, unsigned v) {
   __syncthreads();
   if (threadIdx.x == 0) st_release_u32(flag, v);
 }
+// the same with ONE fence: bar.sync orders the CTA's stores before thread 0, whose gpu-scope fence + release store is cumulative
+__device__ __forceinline__ void flag_publish_light(unsigned* flag, unsigned v) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    st_release_u32(flag, v);
+  }
+}
 // wait until flags[first + i*stride] >= v for i < n (warp 0 polls, one flag per lane and pass), then block-wide sync
 __device__ __forceinline__ void flags_wait(const unsigned* flags, int first, int stride, int n, unsigned v) {
   if (threadIdx.x < 32) {
@@ -86,6 +95,14 @@ __device__ __forceinline__ void flags_wait(const unsigned* flags, int first, int
   }
   __syncthreads();
 }
+
+// global -> shared bulk copy (TMA, no tensor map) that completes on an mbarrier of this CTA
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar_smem) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+               "r"(bytes), "r"(mbar_smem)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_full() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 struct Clk {
   long long acc[7], t0;
@@ -107,6 +124,7 @@ struct FwdGeom {
   int PR;        // proj / stop rows per CTA in phase 2 (<= 8)
   int nsl;       // CTAs per batch group = H / 32
   int ngroups;   // batch groups
+  int xchg;      // h_t / x_t exchange: 1 = flags + TMA bulk copies of bf16 blocks (default), 0 = tagged "LL" words
 };
 
 // "LL" exchange (the NCCL low-latency protocol): every 8-byte word carries 4 bytes of payload and the 4-byte step tag,
@@ -162,14 +180,34 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
   int* gen = reinterpret_cast<int*>(gs + 4 * NB * UPC);
   int* cnt = gen + NB;
   uint64_t* mma_done = reinterpret_cast<uint64_t*>(cnt + NB);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+  uint64_t* hfull = mma_done + 1;                  // TMA exchange: h_t / x_{t-1} block has landed in Bs
+  uint64_t* xfull = mma_done + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 3);
 
+  const bool tma_x = gm.xchg != 0;
+  // k-chunk stride of the B operand: contiguous chunks when TMA writes it (one bulk copy moves a whole block), padded by
+  // 16 B when threads store chunk-major (bank conflicts)
+  const uint32_t bstr = tma_x ? (uint32_t)NB * 16u : (uint32_t)CSTR;
   uint2* LLh = reinterpret_cast<uint2*>(d.ll_ws);
   uint2* LLx = LLh + (size_t)2 * Bpad * (H / 2);
   uint2* LLa = LLx + (size_t)2 * Bpad * F;
+  // TMA exchange: Hx [2 slots][group][H/8 k-chunks][NB rows][16 B] bf16 -- the image of the B operand's h part, so a consumer
+  // fetches one k-chunk (NB * 16 bytes) per bulk copy; Xx likewise [2][group][F/8][NB][16 B]; one release flag per producer
+  // CTA, slot and exchange (value = step tag)
+  uint8_t* Hx = reinterpret_cast<uint8_t*>(d.ll_ws);
+  uint8_t* Xx = Hx + (size_t)2 * Bpad * H * 2;
+  unsigned* flagH = nullptr;
+  unsigned* flagX = nullptr;
+  if (tma_x) {
+    LLa = reinterpret_cast<uint2*>(Xx + (size_t)2 * Bpad * F * 2);
+    flagH = reinterpret_cast<unsigned*>(LLa + 32);
+    flagX = flagH + 2 * gm.ngroups * 32;
+  }
 
   if (tid == 0) {
     mbar_init(mma_done, NCH);
+    mbar_init(hfull, 1);
+    mbar_init(xfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // TMEM: columns [0, KT/2) = A (weights), then NCH accumulators of NB columns
@@ -235,7 +273,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
     const float4 a = __ldg(reinterpret_cast<const float4*>(d.w2 + (int64_t)(p0 + r) * H) + k4);
     *reinterpret_cast<uint2*>(W2s + r * (H + 8) + 4 * k4) = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
   }
-  for (uint32_t i = tid * 16; i < (uint32_t)nkc * CSTR; i += LT * 16) *reinterpret_cast<uint4*>(Bs + i) = make_uint4(0u, 0u, 0u, 0u);
+  for (uint32_t i = tid * 16; i < (uint32_t)nkc * bstr; i += LT * 16) *reinterpret_cast<uint4*>(Bs + i) = make_uint4(0u, 0u, 0u, 0u);
   for (int b = tid; b < NB; b += LT) { gen[b] = 1; cnt[b] = 0; }
   fence_proxy_async();
   tc_fence_before();
@@ -275,15 +313,15 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
     if (lane == 0 && w < NCH) {
       tc_fence_after();
       uint32_t ta = tmem + (uint32_t)(w * nt * 8);
-      uint64_t db = umma_desc_nosw(bs_local, CSTR, 128) + (uint64_t)(w * nt * (2 * CSTR / 16));
+      uint64_t db = umma_desc_nosw(bs_local, bstr, 128) + (uint64_t)(w * nt * (2 * bstr / 16));
       for (int kk = 0; kk < nt; ++kk) {
         tc_mma_ts(tmem_d + NB * w, ta, db, idesc, kk ? 1u : 0u);
         ta += 8;
-        db += 2 * CSTR / 16;
+        db += 2 * bstr / 16;
       }
       for (int kk = w; kk < nsh; kk += NCH)
         tc_mma(tmem_d + NB * w, umma_desc_nosw(as_local + (uint32_t)kk * 4096, 2048, 128),
-               umma_desc_nosw(bs_local + (uint32_t)(KT / 8 + 2 * kk) * CSTR, CSTR, 128), idesc, 1u);
+               umma_desc_nosw(bs_local + (uint32_t)(KT / 8 + 2 * kk) * bstr, bstr, 128), idesc, 1u);
     }
   };
   auto issue_x_part = [&]() {
@@ -291,7 +329,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
       tc_fence_after();
       for (int kk = nsh + w; kk < nsh + nsx; kk += NCH)
         tc_mma(tmem_d + NB * w, umma_desc_nosw(as_local + (uint32_t)kk * 4096, 2048, 128),
-               umma_desc_nosw(bs_local + (uint32_t)(KT / 8 + 2 * kk) * CSTR, CSTR, 128), idesc, 1u);
+               umma_desc_nosw(bs_local + (uint32_t)(KT / 8 + 2 * kk) * bstr, bstr, 128), idesc, 1u);
       tc_commit(mma_done);
     }
   };
@@ -313,6 +351,24 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
         }
         if (a == 0u) { steps_run = s; break; }
       }
+      if (tma_x) {
+        // x_{t-1}: wait for the flags of the CTAs that own projection rows, then one bulk copy per k-chunk
+        if (w == 0) {
+          for (int pr = lane; pr * PR < F; pr += 32) {
+            const unsigned* fp = flagX + ((size_t)pslot * gm.ngroups + grp) * 32 + pr;
+            while (ld_acquire_u32(fp) < ptag) { }
+          }
+          __syncwarp();
+          __threadfence();
+          fence_proxy_async_full();
+          if (lane == 0) {
+            const uint8_t* xs = Xx + ((size_t)pslot * gm.ngroups + grp) * (F / 8) * NB * 16;
+            mbar_arrive_expect_tx(xfull, (uint32_t)(F / 8) * NB * 16);
+            bulk_g2s(bs_local + (uint32_t)(H / 8) * bstr, xs, (uint32_t)(F / 8) * NB * 16, smem_u32(xfull));
+          }
+        }
+        mbar_wait(xfull, (uint32_t)(s - 1) & 1u);
+      } else {
       // x_{t-1} [NB, F]: 8 consecutive rows p of one sample = one 16-byte k-chunk of the B operand
       const uint2* src = LLx + ((size_t)pslot * Bpad + b0) * F;
       if (w == 0) {                                     // one word per producer CTA first (see the h exchange)
@@ -349,7 +405,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
               for (int e = 0; e < 4; ++e) ok = ok && v[i][e].y == ptag && v[i][e].w == ptag;
               if (ok) {
                 const int idx = base + i * LT + tid, b = idx / (F / 8), c = idx - b * (F / 8);
-                *reinterpret_cast<uint4*>(Bs + (size_t)(H / 8 + c) * CSTR + b * 16) = make_uint4(
+                *reinterpret_cast<uint4*>(Bs + (size_t)(H / 8 + c) * bstr + b * 16) = make_uint4(
                     pack_bf16(__uint_as_float(v[i][0].x), __uint_as_float(v[i][0].z)), pack_bf16(__uint_as_float(v[i][1].x), __uint_as_float(v[i][1].z)),
                     pack_bf16(__uint_as_float(v[i][2].x), __uint_as_float(v[i][2].z)), pack_bf16(__uint_as_float(v[i][3].x), __uint_as_float(v[i][3].z)));
                 pending &= ~(1u << i);
@@ -360,6 +416,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
       }
       fence_proxy_async();
       __syncthreads();
+      }
     }
     ck.lap(0);
     issue_x_part();
@@ -402,7 +459,13 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
       cv[e] = c;
       hv[e] = go * tanh_approx(c);
     }
-    {
+    if (tma_x) {
+      // h_t slice -> Hx in the consumers' operand layout (k-chunk major), then this CTA's release flag
+      uint8_t* dst = Hx + (((size_t)slot * gm.ngroups + grp) * (H / 8) + (size_t)((j0 + jv) >> 3)) * NB * 16 + bl * 16 + ((j0 + jv) & 7) * 2;
+      if (JV == 2) *reinterpret_cast<uint32_t*>(dst) = pack_bf16(hv[0], hv[1]);
+      else *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(hv[0], hv[1]), pack_bf16(hv[JV - 2], hv[JV - 1]));
+      flag_publish_light(flagH + ((size_t)slot * gm.ngroups + grp) * 32 + slice, tag);
+    } else {
       // h_t slice -> LL buffer (what the peers wait for), samples past B included (zeros keep their operand rows clean)
       uint2* dst = LLh + ((size_t)slot * Bpad + bme) * (H / 2) + (j0 + jv) / 2;
       if (JV == 2) ll_store2(dst, pack_bf16(hv[0], hv[1]), tag);
@@ -431,8 +494,27 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
     }
     if (s + 1 < T) load_pre(s + 1);
     ck.lap(3);
-    // h_t [NB, H] of the whole batch group: 8 units = 4 LL words = one 16-byte k-chunk
-    {
+    // h_t [NB, H] of the whole batch group
+    if (tma_x) {
+      if (w == 0) {
+        for (int pr = lane; pr < nsl; pr += 32) {
+          const unsigned* fp = flagH + ((size_t)slot * gm.ngroups + grp) * 32 + pr;
+          while (ld_acquire_u32(fp) < tag) { }
+        }
+        __syncwarp();
+        __threadfence();
+        fence_proxy_async_full();
+        if (lane == 0) mbar_arrive_expect_tx(hfull, (uint32_t)(H / 8) * NB * 16);
+        __syncwarp();
+        if (lane < 4) {                                      // four bulk copies of a quarter of the block each
+          const uint32_t q4 = (uint32_t)(H / 8) * NB * 16 / 4;
+          const uint8_t* hsrc = Hx + ((size_t)slot * gm.ngroups + grp) * (H / 8) * NB * 16;
+          bulk_g2s(bs_local + lane * q4, hsrc + (size_t)lane * q4, q4, smem_u32(hfull));
+        }
+      }
+      mbar_wait(hfull, (uint32_t)s & 1u);
+    } else {
+      // 8 units = 4 LL words = one 16-byte k-chunk
       const uint2* src = LLh + ((size_t)slot * Bpad + b0) * (H / 2);
       // 128 CTAs re-polling 64 KB each saturate the L2 (measured: the exchange took ~8 k cycles that way), so one warp
       // first waits on ONE word per producer CTA; the tagged bulk read below then succeeds on its first pass almost always
@@ -464,15 +546,15 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
           for (int i = 0; i < HC; ++i) {
             if ((pending & (1u << i)) && v[i][0].y == tag && v[i][0].w == tag && v[i][1].y == tag && v[i][1].w == tag) {
               const int idx = base + i * LT + tid, b = idx / (H / 8), c = idx - b * (H / 8);
-              *reinterpret_cast<uint4*>(Bs + (size_t)c * CSTR + b * 16) = make_uint4(v[i][0].x, v[i][0].z, v[i][1].x, v[i][1].z);
+              *reinterpret_cast<uint4*>(Bs + (size_t)c * bstr + b * 16) = make_uint4(v[i][0].x, v[i][0].z, v[i][1].x, v[i][1].z);
               pending &= ~(1u << i);
             }
           }
         }
       }
+      fence_proxy_async();
+      __syncthreads();
     }
-    fence_proxy_async();
-    __syncthreads();
     ck.lap(4);
     if (s + 1 < T) issue_h_part();                  // next step's whh . h_t runs under phase 2 and the x exchange
     // phase 2: rows p0 .. p0 + np of [wp ; ws] against h_t on mma.sync (m16n8k16; warp w takes k in [w H/8, (w+1) H/8))
@@ -491,11 +573,11 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
         a[1] = *reinterpret_cast<const uint32_t*>(wr + 8 * (H + 8) + k0);
         a[2] = *reinterpret_cast<const uint32_t*>(wr + k0 + 8);
         a[3] = *reinterpret_cast<const uint32_t*>(wr + 8 * (H + 8) + k0 + 8);
-        const uint8_t* bp = Bs + (size_t)(k0 / 8) * CSTR + g8 * 16 + tq * 4;
+        const uint8_t* bp = Bs + (size_t)(k0 / 8) * bstr + g8 * 16 + tq * 4;
 #pragma unroll
         for (int n = 0; n < NB / 8; ++n) {
           const uint32_t bb0 = *reinterpret_cast<const uint32_t*>(bp + n * 128);
-          const uint32_t bb1 = *reinterpret_cast<const uint32_t*>(bp + n * 128 + CSTR);
+          const uint32_t bb1 = *reinterpret_cast<const uint32_t*>(bp + n * 128 + bstr);
           if ((k0 >> 4) & 1) mma_bf16_16816(acc3[n], a, bb0, bb1);
           else mma_bf16_16816(acc2[n], a, bb0, bb1);
         }
@@ -515,7 +597,11 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
       for (int ww = 0; ww < 8; ++ww) v += gs[(ww * 8 + r) * NB + b2];
       if (p < F) {
         const float xv = 1.f - __fdividef(2.f, 1.f + __expf(2.f * v));     // tanh, abs error ~1e-7
-        ll_store2(LLx + ((size_t)slot * Bpad + b) * F + p, __float_as_uint(xv), tag);
+        if (tma_x)
+          *reinterpret_cast<__nv_bfloat16*>(Xx + (((size_t)slot * gm.ngroups + grp) * (F / 8) + (size_t)(p >> 3)) * NB * 16 + b2 * 16 + (p & 7) * 2) =
+              __float2bfloat16(xv);
+        else
+          ll_store2(LLx + ((size_t)slot * Bpad + b) * F + p, __float_as_uint(xv), tag);
         if (b < B) {
           d.xbuf[b * xstr + (int64_t)(t + 1) * F + p] = xv;
           xb16[b * xstr + (int64_t)(t + 1) * F + p] = __float2bfloat16(xv);
@@ -528,6 +614,7 @@ __global__ void __launch_bounds__(LT, 1) lstm_gen_fwd_kernel(const ag_lstm_desc 
         if (stop) gen[b2] = 0;
       }
     }
+    if (tma_x && np > 0 && p0 < F) flag_publish_light(flagX + ((size_t)slot * gm.ngroups + grp) * 32 + slice, tag);
     if (owns_logit && d.u) {
       __syncthreads();
       if (tid == 0) {
@@ -972,7 +1059,12 @@ static const char* fwd_geom(const ag_lstm_desc* d, FwdGeom& g, int& NB, size_t& 
   g.KT = std::min(d->H / 64 * 64, 896);             // 448 TMEM columns of weights + 64 of accumulators; k < KT <= H
   g.PR = (d->F + 1 + g.nsl - 1) / g.nsl;
   if (g.PR > 8) { snprintf(why, nwhy, "F=%d: %d projection rows per CTA > 8", d->F, g.PR); return why; }
-  ll_need = ((size_t)2 * g.ngroups * NB * (d->H / 2) + (size_t)2 * g.ngroups * NB * d->F + 32) * 8;
+  ll_need = ((size_t)2 * g.ngroups * NB * (d->H / 2) + (size_t)2 * g.ngroups * NB * d->F + 32) * 8 + 16384;   // + exchange flags
+  {
+    static int mode = -1;                  // AUDIOGAN_GEN_XCHG=ll: the tagged-word exchange (A/B knob); default: flags + TMA bulk copies
+    if (mode < 0) { const char* e = getenv("AUDIOGAN_GEN_XCHG"); mode = (e && e[0] == 'l') ? 0 : 1; }
+    g.xchg = mode;
+  }
   smem = fwd_smem(d, g, NB);
   if (smem > (size_t)smem_optin()) {
     snprintf(why, nwhy, "H=%d F=%d: weight slice needs %zu B of shared memory beside tensor memory (> %d)", d->H, d->F, smem, smem_optin());

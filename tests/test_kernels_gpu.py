@@ -398,12 +398,12 @@ def test_lstm_generator_tmem_kernel_tracks_fp32_kernel(B, Tn, stops):
         stop, glen = T.zeros(B, Tn, dtype=T.int32, device=dev), T.zeros(B, dtype=T.int32, device=dev)
         misc = T.zeros(1024, dtype=T.int32, device=dev)
         dbg = T.zeros(148, 8, dtype=T.int64, device=dev) if prec else None
-        ll_ws = T.empty(16 * ((B + 31) // 32 * 32) * (H // 2 + Fr) + 256, device=dev, dtype=T.uint8)
+        ll_ws = Kn.lstm_workspace(B, H, Fr, False, dev)            # sized by the library (ag_lstm_workspace_bytes)
         hbuf16 = T.zeros(B, Tn + 2, H, device=dev, dtype=T.bfloat16) if prec else None
         xbuf16 = T.zeros(B, Tn + 1, Fr, device=dev, dtype=T.bfloat16) if prec else None
         Kn.lstm_fwd(B=B, T=Tn, Tcap=Tn, H=H, ndir=1, F=Fr, pre=pre, w1=w1, w2=w2, b2=b2, hbuf=hbuf, gates=gates, cbuf=cbuf,
                     xbuf=xbuf, sbuf=sbuf, u=u, stop=stop, glen=glen, t_end=(misc, 8), barrier=misc, prec=prec,
-                    flags=flags, hbuf16=hbuf16, xbuf16=xbuf16, dbg=dbg, ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel())
+                    flags=flags, hbuf16=hbuf16, xbuf16=xbuf16, dbg=dbg, ll_ws=ll_ws, ll_ws_bytes=ll_ws.numel() if ll_ws is not None else 0)
         T.cuda.synchronize()
         if dbg is not None:
             assert int((dbg[:, 7] > 0).sum()) > 0, "the TMEM-resident kernel did not run"
@@ -419,10 +419,10 @@ def test_lstm_generator_tmem_kernel_tracks_fp32_kernel(B, Tn, stops):
         dgates16 = T.zeros(B, Tn, 4 * H, device=dev, dtype=T.bfloat16) if prec else None
         dpx16 = T.zeros(B, Tn, FP, device=dev, dtype=T.bfloat16) if prec else None
         ngr = (B + 15) // 16
-        ll_wb = T.empty((2 * ngr * (H // 32) * (H + Fr) * 8 + 2 * ngr * 16 * Fr + 32) * 8, device=dev, dtype=T.uint8)
+        ll_wb = Kn.lstm_workspace(B, H, Fr, True, dev)
         Kn.lstm_bwd(B=B, T=te_, Tcap=Tn, H=H, ndir=1, F=Fr, gates=gates, cbuf=cbuf, xbuf=xbuf, dx_ext=dx_ext, ds_ext=ds_ext,
                     dgates=dgates, dpx=dpx, w1t=w1t, wxt=wxt, barrier=T.zeros(1024, dtype=T.int32, device=dev), prec=prec,
-                    flags=flags, dgates16=dgates16, dpx16=dpx16, dbg=dbg, ll_ws=ll_wb, ll_ws_bytes=ll_wb.numel())
+                    flags=flags, dgates16=dgates16, dpx16=dpx16, dbg=dbg, ll_ws=ll_wb, ll_ws_bytes=ll_wb.numel() if ll_wb is not None else 0)
         T.cuda.synchronize()
         if dbg is not None and B <= 64:
             assert int((dbg[:, 7] > 0).sum()) > 0, "the TMEM-resident BPTT kernel did not run"

@@ -36,7 +36,7 @@ def run(H, B, Tn, Fr=200, stops=False, time_it=True, bwd=True):
             stop, glen = T.zeros(B, Tn, dtype=T.int32, device=dev), T.zeros(B, dtype=T.int32, device=dev)
             misc = T.zeros(1024, dtype=T.int32, device=dev)
             dbg = T.zeros(148, 8, dtype=T.int64, device=dev)
-            ll_ws = T.empty(16 * ((B + 31) // 32 * 32) * (H // 2 + Fr) + 256, device=dev, dtype=T.uint8)
+            ll_ws = Kn.lstm_workspace(B, H, Fr, False, dev)            # sized by the library (ag_lstm_workspace_bytes)
             hbuf16 = T.zeros(B, Tn + 2, H, device=dev, dtype=T.bfloat16) if prec else None
             xbuf16 = T.zeros(B, Tn + 1, Fr, device=dev, dtype=T.bfloat16) if prec else None
             e = [T.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -56,7 +56,7 @@ def run(H, B, Tn, Fr=200, stops=False, time_it=True, bwd=True):
             dbg.zero_()
             misc2 = T.zeros(1024, dtype=T.int32, device=dev)
             ngr = (B + 15) // 16
-            ll_wb = T.empty((2 * ngr * (H // 32) * (H + Fr) * 8 + 2 * ngr * 16 * Fr + 32) * 8, device=dev, dtype=T.uint8)
+            ll_wb = Kn.lstm_workspace(B, H, Fr, True, dev)
             e[1].record()
             if bwd:
                 Kn.lstm_bwd(B=B, T=t_end, Tcap=Tn, H=H, ndir=1, F=Fr, gates=gates, cbuf=cbuf, xbuf=xbuf, dx_ext=dx_ext, ds_ext=ds_ext,
