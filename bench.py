@@ -361,11 +361,16 @@ def run_ours(args):
     assert all(v == v for v in losses_seen), "NaN loss in the end-to-end run"
 
     # ---- per-kernel attribution with CUDA events around every launch (same steps, instrumented)
+    # (eager launches, every kernel alone on the GPU: the side-stream "shadow" scheduling of engine.py is switched off here so that
+    # an event pair brackets one kernel and not whatever runs beside it)
+    from audiogan_b200 import engine as _engine
+    _ovl, _engine._OVERLAP = _engine._OVERLAP, False
     step(resident[0])              # untimed: torch.cuda.graph() emptied the allocator's cache, the first eager step re-mallocs
     kt = KernelTimer(torch, shapes=args.shapes)
     _abi.set_hook(kt.hook)
     ms_inst = timed(lambda i: step(resident[i % 2]), args.steps) / args.steps
     _abi.set_hook(None)
+    _engine._OVERLAP = _ovl
     fam = kt.summary()
     pk = peaks()
     tot_kernel_ms = sum(v[0] for v in fam.values())
@@ -411,7 +416,7 @@ def run_ours(args):
         "kernel_families": families,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_step_throughput(args, steps=2, warmup=1, batch=args.cpu_batch)
+        out["cpu_baseline"] = cpu_leg_subprocess(args, steps=2, warmup=1, batch=args.cpu_batch)
     if rank == 0:
         emit(out)
     if world > 1:
@@ -419,6 +424,22 @@ def run_ours(args):
 
 
 # ----------------------------------------------------------------------------------- CPU arm
+def cpu_leg_subprocess(args, steps, warmup, batch):
+    """cpu_step_throughput in a child process that cannot see the GPU: the reference wraps its sub-modules in NN.DataParallel
+    (audiogan.py:379-410), which on a box with visible GPUs moves the inputs to cuda:0 -- its CPU path needs CUDA hidden."""
+    import subprocess
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-leg", "--steps", str(steps), "--warmup", str(warmup),
+           "--cpu-batch", str(batch), "--batch", str(args.batch), "--samples", str(args.samples)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1500)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError("CPU baseline leg failed: %s" % (r.stderr.strip().splitlines()[-1:] or ["no output"])[0])
+    return json.loads(lines[-1])
+
+
 def cpu_step_throughput(args, steps, warmup, batch):
     """The reference's CPU training step on the host cores, on `batch` samples of the workload's minibatch.
 
@@ -464,7 +485,7 @@ def run_reference(args):
         return
     steps = max(1, min(args.steps, 2))
     warm = 1 if args.warmup > 0 else 0
-    cb = cpu_step_throughput(args, steps=steps, warmup=warm, batch=args.batch)
+    cb = cpu_leg_subprocess(args, steps=steps, warmup=warm, batch=args.batch)
     L = args.samples
     out = {
         "impl": "reference", "metric": "audio_seconds_per_s", "value": cb["value"], "unit": "audio-s/s",
@@ -517,7 +538,11 @@ def main():
     ap.add_argument("--quick", action="store_true", help="headline timing only (for ncu runs): no e2e / attribution / CPU legs")
     ap.add_argument("--no-graph", dest="graph", action="store_false", default=os.environ.get("AUDIOGAN_GRAPH", "1") != "0",
                     help="time the eager launch sequence instead of the captured CUDA graph")
+    ap.add_argument("--cpu-leg", action="store_true", help=argparse.SUPPRESS)     # child process of cpu_leg_subprocess
     args = ap.parse_args()
+    if args.cpu_leg:
+        emit(cpu_step_throughput(args, steps=args.steps, warmup=args.warmup, batch=args.cpu_batch))
+        return
     if args.impl == "reference":
         run_reference(args)
     else:
