@@ -120,11 +120,25 @@ class _GenFn(torch.autograd.Function):
             zld, zin = NZ + 2, zc1
         K.gemm_nt(B * Tcap, 4 * H, zld, zin, (Tcap, Tcap * zld, zld), plan.Poff("wz"), NZ + 2,
                   pre, (Tcap, Tcap * 4 * H, 4 * H))
-        hbuf = _zeros(B, Tcap + 2, H, device=dev)
-        xbuf = _zeros(B, Tcap + 1, F, device=dev)
         bf = plan.mode == "bf16"
-        hbuf16 = torch.zeros(B, Tcap + 2, H, device=dev, dtype=torch.bfloat16) if bf else None
-        xbuf16 = torch.zeros(B, Tcap + 1, F, device=dev, dtype=torch.bfloat16) if bf else None
+        if u_stop is None:
+            # no stop sampling: every frame of every sample is written by the kernel; only the initial state (row 0 = h_{-1} /
+            # x_{-1}) and the row past the end have to be zero -- not the whole buffers (76 MB of fills at B = 128)
+            hbuf = _empty(B, Tcap + 2, H, device=dev)
+            xbuf = _empty(B, Tcap + 1, F, device=dev)
+            K.zero_pads(hbuf, 1, Tcap + 1)
+            K.zero_pads(xbuf, 1, Tcap + 1)
+            hbuf16 = xbuf16 = None
+            if bf:
+                hbuf16 = torch.empty(B, Tcap + 2, H, device=dev, dtype=torch.bfloat16)
+                xbuf16 = torch.empty(B, Tcap + 1, F, device=dev, dtype=torch.bfloat16)
+                K.zero_pads(hbuf16, 1, Tcap + 1)
+                K.zero_pads(xbuf16, 1, Tcap + 1)
+        else:
+            hbuf = _zeros(B, Tcap + 2, H, device=dev)
+            xbuf = _zeros(B, Tcap + 1, F, device=dev)
+            hbuf16 = torch.zeros(B, Tcap + 2, H, device=dev, dtype=torch.bfloat16) if bf else None
+            xbuf16 = torch.zeros(B, Tcap + 1, F, device=dev, dtype=torch.bfloat16) if bf else None
         gates = _empty(B, Tcap, 4 * H, device=dev) if save else None
         cbuf = _empty(B, Tcap, H, device=dev) if save else None
         sbuf = _zeros(B, Tcap, device=dev)
