@@ -374,6 +374,10 @@ __global__ void frames_to_slot_kernel(void* __restrict__ dst, int ddt, int64_t d
     const int64_t o = b * d_bs + t * d_rs;
     if (ddt == 1 && slot == 8) {
       *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst) + o) = make_uint4((uint32_t)__bfloat16_as_ushort(__float2bfloat16(v)), 0u, 0u, 0u);
+    } else if (ddt == 1 && slot == 16) {                     // one 32-byte sector per row
+      uint4* q = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst) + o);
+      q[0] = make_uint4((uint32_t)__bfloat16_as_ushort(__float2bfloat16(v)), 0u, 0u, 0u);
+      q[1] = make_uint4(0u, 0u, 0u, 0u);
     } else if (ddt == 0 && slot == 8) {
       float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + o);
       q[0] = make_float4(v, 0.f, 0.f, 0.f);
@@ -509,7 +513,7 @@ int ag_copy3d(void* dst, int64_t d_bs, int64_t d_rs, int64_t d_cs, const void* s
 int ag_frames_to_slot(void* dst, int32_t dst_dtype, int64_t d_bs, int64_t d_rs, int32_t slot, const float* src, int64_t s_bs, int64_t B,
                       int64_t L, void* stream) {
   AG_CHECK_ARG(dst && src && B > 0 && L > 0 && slot > 0, "ag_frames_to_slot: bad args");
-  if (slot == 8)
+  if (slot == 8 || slot == 16)
     AG_CHECK_ARG((reinterpret_cast<uintptr_t>(dst) & (dst_dtype ? 15 : 31)) % 16 == 0 && d_bs % 8 == 0 && d_rs % 8 == 0, "ag_frames_to_slot: unaligned");
   frames_to_slot_kernel<<<grid_for(B * L, 256), 256, 0, (cudaStream_t)stream>>>(dst, dst_dtype, d_bs, d_rs, slot, src, s_bs, B, L);
   AG_LAUNCH_CHECK();

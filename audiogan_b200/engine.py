@@ -32,6 +32,7 @@ _ACT_BF16 = os.environ.get("AUDIOGAN_ACT", "bf16") != "fp32"
 # runs on the idle SMs underneath it.  AUDIOGAN_OVERLAP=0 runs everything in line.
 # ---------------------------------------------------------------------------------------------------------------------
 _OVERLAP = os.environ.get("AUDIOGAN_OVERLAP", "1") != "0"
+_TMA_CIN = int(os.environ.get("AUDIOGAN_TMA_CIN", "32"))     # widest channel prefix whose conv runs on the 4-D-map TMA kernel
 _side_streams = {}
 _shadow_jobs = {}          # device -> [callable]
 
@@ -189,7 +190,7 @@ class _GenFn(torch.autograd.Function):
                 K.zero_pads(Hh, 1, Lh + 1)
                 # TMA-fed kernel over a 4-D tensor map (channel prefix, row, tap, batch).  Its boxes have 16-byte inner rows, so
                 # for wide prefixes the producer-warp kernel is faster (measured: cin 8 / 24 -> 1.9x / 1.5x faster, 56 equal, 88 0.6x)
-                if adt == torch.bfloat16 and cin <= 32:
+                if adt == torch.bfloat16 and cin <= _TMA_CIN:
                     K.gemm_nt(n * Lh, hid, k * cin, (Xs, (GPAD - p) * CT), (Lh, Lp * CT, s * CT, cin, CT),
                               plan.Poff("c%d.wq" % li), plan.Kq[li], (Hh, hid), (Lh, (Lh + 2) * hid, hid),
                               bias=plan.Poff("c%d.b" % li), act=1, a_layout=1)

@@ -362,7 +362,13 @@ def build_generator_plan(mod, device):
     # conv stack.  The dense channel-last buffer keeps every channel group in a slot padded to a multiple of 8
     # channels (x: 1 -> 8, then each block's `out`), so channel prefixes, slot offsets and the row pitch are all
     # 16/32-byte aligned: vector loads / stores in the GEMM kernels.  pos[c] = padded position of canonical channel c.
-    r8 = lambda n: (n + 7) // 8 * 8
+    # AUDIOGAN_SLOT (A/B knob, default 16): slot granularity in channels.  16 bf16 channels = 32 bytes = one DRAM sector, and the
+    # default net's slots (16, 16, 32, 32, 32) then add up to 128 channels = a 256-byte row pitch, so every slot of every row is
+    # sector-aligned: a block's output write touches exactly its own sectors and a prefix read exactly the prefix's.  With
+    # 8-channel slots the pitch was 240 bytes (rows alternately misaligned by half a sector) and the transposed-conv launches
+    # moved 2.1x their algorithmic DRAM bytes (profiles/r1_bf16_gemm_nt_tma_metrics.txt).
+    SL = int(os.environ.get("AUDIOGAN_SLOT", "16"))
+    r8 = lambda n: (n + SL - 1) // SL * SL
     pos, slot_off, nxt = [0], [], r8(1)
     for (_, _, _, out) in mod._struct:
         slot_off.append(nxt)
