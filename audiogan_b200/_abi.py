@@ -117,6 +117,10 @@ _PROTOS = {
     "ag_frames_to_slot": [vp, i32, i64, i64, i32, vp, i64, i64, i64, vp],
     "ag_rowgroup_sum": [vp, i32, vp, i64, i64, i64, vp],
     "ag_transpose_bct": [vp, vp, i64, i64, i64, i64, i64, i32, vp],
+    "ag_lstm_step_cell_fwd": [vp, vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, vp, i64, i32, i32, vp],
+    "ag_gen_step_proj_finish": [vp, i32, vp, vp, i64, vp, i64, i32, vp, i64, i32, i32, vp],
+    "ag_gen_step_dpx": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, i32, vp],
+    "ag_lstm_step_cell_bwd": [vp, vp, i64, vp, vp, i64, vp, vp, vp, i64, vp, i64, i32, i32, vp],
     "ag_peer_barrier": [vp, i32, i32, vp],
     "ag_peer_allreduce": [vp, vp, i32, i32, i64, i32, vp],
     "ag_mt_sqnorm": [vp, vp, vp, i32, i32, vp, vp, f32, vp],

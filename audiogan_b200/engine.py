@@ -13,6 +13,7 @@ import torch
 from torch.autograd.function import once_differentiable
 
 from . import kernels as K
+from . import _abi as A
 from .plan import pack, wgrad_enabled  # noqa: F401  (pack re-exported)
 
 GPAD = 8        # zero rows either side of the generator's dense channel-last buffer
@@ -32,6 +33,7 @@ _ACT_BF16 = os.environ.get("AUDIOGAN_ACT", "bf16") != "fp32"
 # runs on the idle SMs underneath it.  AUDIOGAN_OVERLAP=0 runs everything in line.
 # ---------------------------------------------------------------------------------------------------------------------
 _OVERLAP = os.environ.get("AUDIOGAN_OVERLAP", "1") != "0"
+_STEPWISE = os.environ.get("AUDIOGAN_STEPWISE", "1") != "0"   # per-frame GEMM recurrence for hidden sizes that cannot be resident
 _TMA_CIN = int(os.environ.get("AUDIOGAN_TMA_CIN", "32"))     # widest channel prefix whose conv runs on the 4-D-map TMA kernel
 _side_streams = {}
 _shadow_jobs = {}          # device -> [callable]
@@ -81,6 +83,47 @@ def shadow_join(dev):
         jobs.clear()
     if _side_streams.pop((dev, "busy"), False):
         torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Step-wise generator recurrence (csrc/lstm_step.cu): hidden sizes whose recurrent weights cannot stay resident on chip
+# (--gstatesize 2048: 36.8 MB in bf16).  One small-M tensor-core GEMM per frame over the bf16 weights (which stay in the L2
+# between frames) + the point-wise kernels between them; 4 launches per frame, all inside the step's CUDA graph.
+# ---------------------------------------------------------------------------------------------------------------------
+def _gen_stepwise_fwd(plan, B, Tcap, H, F, FP, pre, hbuf16, xbuf, xbuf16, gates, cbuf, sbuf):
+    dev = plan.device
+    KP = (H + F + 7) // 8 * 8
+    hx = torch.zeros(B, KP, device=dev, dtype=torch.bfloat16)          # operand rows [h_{t-1} | x_{t-1}]; zeros = initial state
+    gpre = _empty(B, 4 * H, device=dev)
+    px = _empty(B, FP, device=dev)
+    st = A.stream
+    for t in range(Tcap):
+        K.gemm_nt(B, 4 * H, H + F, hx, (B, 0, KP), plan.Poff("w1"), H + F, gpre, (B, 0, 4 * H))
+        A.call("ag_lstm_step_cell_fwd", K.addr(gpre), K.addr(pre[:, t]), Tcap * 4 * H, K.addr(cbuf[:, t - 1]) if t else None, Tcap * H,
+               K.addr(gates[:, t]) if gates is not None else None, Tcap * 4 * H, K.addr(cbuf[:, t]), None, (Tcap + 2) * H,
+               K.addr(hbuf16[:, t + 1]), K.addr(hx), KP, B, H, st())
+        K.gemm_nt(B, F + 1, H, hx, (B, 0, KP), plan.Poff("w2"), H, px, (B, 0, FP), bias=plan.Poff("b2"))
+        A.call("ag_gen_step_proj_finish", K.addr(px), FP, K.addr(xbuf[:, t + 1]), K.addr(xbuf16[:, t + 1]), (Tcap + 1) * F, K.addr(hx), KP, H,
+               K.addr(sbuf[:, t]), Tcap, B, F, st())
+
+
+def _gen_stepwise_bwd(plan, B, T, Tcap, H, F, FP, gates, cbuf, xbuf, dx_ext, ds_ext, dpx, dpx16, dgates16):
+    dev = plan.device
+    KW = 4 * H + FP
+    dgp = torch.zeros(B, KW, device=dev, dtype=torch.bfloat16)         # operand rows [dgates_{t+1} | dpx_t]
+    dc = torch.zeros(B, H, device=dev)
+    dh = _empty(B, H, device=dev)
+    dxpre = _empty(B, F, device=dev)
+    st = A.stream
+    for t in range(T - 1, -1, -1):
+        last = t == T - 1
+        if not last:
+            K.gemm_nt(B, F, 4 * H, dgp, (B, 0, KW), plan.Poff("wxt"), 4 * H, dxpre, (B, 0, F))
+        A.call("ag_gen_step_dpx", None if last else K.addr(dxpre), F, K.addr(dx_ext[:, t]) if dx_ext is not None else None, Tcap * F,
+               K.addr(ds_ext[:, t]) if ds_ext is not None else None, Tcap, K.addr(xbuf[:, t + 1]), (Tcap + 1) * F, K.addr(dpx[:, t]),
+               K.addr(dpx16[:, t]), Tcap * FP, K.addr(dgp), KW, 4 * H, B, F, FP, st())
+        K.gemm_nt(B, H, KW, dgp, (B, 0, KW), plan.Poff("w1t"), KW, dh, (B, 0, H))
+        A.call("ag_lstm_step_cell_bwd", K.addr(dh), K.addr(gates[:, t]), Tcap * 4 * H, K.addr(cbuf[:, t]), K.addr(cbuf[:, t - 1]) if t else None,
+               Tcap * H, K.addr(dc), None, K.addr(dgates16[:, t]), Tcap * 4 * H, K.addr(dgp), KW, B, H, st())
 
 
 def _adt(plan):
@@ -152,9 +195,16 @@ class _GenFn(torch.autograd.Function):
         # instead of dropping to the grid-barrier kernels (with stop sampling the early exit is a cross-batch decision: one launch)
         cap = K.lstm_batch_cap(H, F, False) if (bf and u is None and not (plan.lstm_flags & 1)) else 0
         chunk = cap if (cap and B > cap) else B
+        # a hidden size the resident kernel cannot hold (H = 2048): per-frame tensor-core GEMMs over the bf16 weights
+        stepwise = (bf and u is None and cap == 0 and not (plan.lstm_flags & 1) and H % 8 == 0 and F % 8 == 0 and H >= 1024 and _STEPWISE)
+        if stepwise:
+            if cbuf is None:
+                cbuf = _empty(B, Tcap, H, device=dev)
+            _gen_stepwise_fwd(plan, B, Tcap, H, F, FP, pre, hbuf16, xbuf, xbuf16, gates, cbuf, sbuf)
+            glen.fill_(Tcap)
         # exchange workspace of the TMEM-resident recurrence (include/audiogan_b200.h: ag_lstm_desc.ll_ws)
         ll_ws = K.lstm_workspace(chunk, H, F, False, dev) if bf else None
-        for b0 in range(0, B, chunk):
+        for b0 in (() if stepwise else range(0, B, chunk)):
             sl = slice(b0, min(B, b0 + chunk))
             cut = lambda t: t[sl] if t is not None else None
             K.lstm_fwd(B=sl.stop - sl.start, T=Tcap, Tcap=Tcap, H=H, ndir=1, F=F, pre=pre[sl], w1=plan.Poff("w1"), w2=plan.Poff("w2"),
@@ -162,7 +212,7 @@ class _GenFn(torch.autograd.Function):
                        stop=stop[sl], glen=glen[sl], t_end=(misc, 8), barrier=misc, prec=plan.lstm_prec if bf else 0,
                        hbuf16=cut(hbuf16), xbuf16=cut(xbuf16), flags=plan.lstm_flags | 2 | (8 if u is None else 0), ll_ws=ll_ws,
                        ll_ws_bytes=ll_ws.numel() if ll_ws is not None else 0)
-        plan.last_path["g_fwd"] = K.lstm_last_path()
+        plan.last_path["g_fwd"] = "stepwise (per-frame tcgen05 GEMMs: H=%d is too large for the resident kernel)" % H if stepwise else K.lstm_last_path()
         if u is not None and early_exit_sync:
             T = int(misc[8].item())          # the one host sync per generator pass (audiogan.py:459-460)
         else:
@@ -320,10 +370,14 @@ class _GenFn(torch.autograd.Function):
         # batch chunks as in the forward pass (64 samples per launch of the TMEM-resident BPTT kernel for the default net)
         cap = K.lstm_batch_cap(H, F, True) if (bf and not (plan.lstm_flags & 1)) else 0
         chunk = cap if (cap and B > cap) else B
+        stepwise = (bf and K.lstm_batch_cap(H, F, False) == 0 and not (plan.lstm_flags & 1) and H % 8 == 0 and F % 8 == 0 and H >= 1024
+                    and _STEPWISE and T == Tcap)
+        if stepwise:
+            _gen_stepwise_bwd(plan, B, T, Tcap, H, F, FP, gates, cbuf, xbuf, dx_ext, ds_ext, dpx, dpx16, dgates16)
         # reduce-scatter workspace of the TMEM-resident BPTT kernel (include/audiogan_b200.h: ag_lstm_desc.ll_ws)
         ll_ws = K.lstm_workspace(chunk, H, F, True, dev) if bf else None
         ready = shadow_ready(dev) if bf else None
-        for b0 in range(0, B, chunk):
+        for b0 in (() if stepwise else range(0, B, chunk)):
             sl = slice(b0, min(B, b0 + chunk))
             cut = lambda t: t[sl] if t is not None else None
             K.lstm_bwd(B=sl.stop - sl.start, T=T, Tcap=Tcap, H=H, ndir=1, F=F, gates=gates[sl], cbuf=cbuf[sl], xbuf=xbuf[sl],
@@ -335,7 +389,7 @@ class _GenFn(torch.autograd.Function):
                 misc.zero_()
             if b0 == 0:
                 shadow_launch(dev, ready)                # queued weight gradients run on the SMs the BPTT kernel leaves idle
-        plan.last_path["g_bwd"] = K.lstm_last_path()
+        plan.last_path["g_bwd"] = "stepwise" if stepwise else K.lstm_last_path()
         # REINFORCE (audiogan.py:900-908): the score-function gradient of the stop logits reaches the stop head's weight and
         # bias ONLY (the reference freezes every other generator parameter for that backward), so it joins column F of dpx
         # after the BPTT has run -- it feeds row F of the [wp; ws] weight-gradient GEMM below and nothing else.

@@ -347,6 +347,27 @@ int ag_mt_adam(const ag_mt_entry* table, const int32_t* chunk_tensor, const int6
                double lr, double beta1, double beta2, double eps, int32_t step, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Step-wise generator recurrence (audiogan.py:428-460 for hidden sizes whose recurrent weights cannot stay resident on chip,
+ * e.g. --gstatesize 2048): the per-frame gate / projection / transposed products are ag_gemm_nt_tc launches issued by the host
+ * side, the entry points below are the point-wise parts between them.  All pointers are already offset to frame t; *_bs are
+ * batch strides in elements; `hx` / `dgp` are the bf16 operand row blocks ([B, hx_ld] = [h_t | x_t], [B, dgp_ld] =
+ * [dgates_t | dpx_{t-1}]) of the NEXT frame's GEMM.
+ *   cell_fwd:     gates = act(gpre + pre_t) (order i, f, g, o), c_t = f c_{t-1} + i g, h_t = o tanh(c_t)
+ *   proj_finish:  x_t = tanh(px[:, :F]) (fp32 + bf16 + hx[:, hx_off:]), stop logit px[:, F] -> sbuf
+ *   dpx:          dpx_t = (dx_ext_t + dxpre)(1 - x_t^2), column F = ds_ext_t, pad columns 0 (fp32 + bf16 + dgp[:, dgp_off:])
+ *   cell_bwd:     dh_t -> dgates_t (fp32 optional, bf16, dgp[:, :4H]); `dc` [B, H] carries dc between frames
+ * ------------------------------------------------------------------------------------------ */
+int ag_lstm_step_cell_fwd(const float* gpre, const float* pre, int64_t pre_bs, const float* cprev, int64_t c_bs, float* gates, int64_t g_bs,
+                          float* cout, float* h32, int64_t h_bs, void* h16, void* hx, int64_t hx_ld, int32_t B, int32_t H, void* stream);
+int ag_gen_step_proj_finish(const float* px, int32_t FP, float* x32, void* x16, int64_t x_bs, void* hx, int64_t hx_ld, int32_t hx_off,
+                            float* sbuf, int64_t s_bs, int32_t B, int32_t F, void* stream);
+int ag_gen_step_dpx(const float* dxpre, int64_t dxpre_ld, const float* dx_ext, int64_t dx_bs, const float* ds_ext, int64_t ds_bs, const float* xt,
+                    int64_t x_bs, float* dpx, void* dpx16, int64_t dpx_bs, void* dgp, int64_t dgp_ld, int32_t dgp_off, int32_t B, int32_t F,
+                    int32_t FP, void* stream);
+int ag_lstm_step_cell_bwd(const float* dh, const float* gates, int64_t g_bs, const float* c, const float* cprev, int64_t c_bs, float* dc,
+                          float* dg32, void* dg16, int64_t dg_bs, void* dgp, int64_t dgp_ld, int32_t B, int32_t H, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Data-parallel gradient all-reduce over NVLink peer memory (replaces NN.DataParallel's gradient gather, audiogan.py:379-410,
  * and the NCCL all-reduce between backward and the optimizer step).  buf_ptrs_dev / sig_ptrs_dev: DEVICE arrays of `world`
  * pointers -- rank r's gradient buffer (n floats, n % 4 == 0, 16-byte aligned) and rank r's signal pad (>= 64 int32, zeroed

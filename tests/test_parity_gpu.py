@@ -684,3 +684,42 @@ def test_generator_batch_beyond_one_launch_runs_in_chunks_on_the_fast_kernels():
         if cos < 0.97:
             R.bad.append("%s cos %.4f" % (k, cos))
     R.done("gen_batch_chunks")
+
+
+def test_double_hidden_generator_runs_stepwise_on_tensor_cores_in_bf16_mode():
+    """configs[3]'s generator (state 2048): its recurrent weights (36.8 MB in bf16) cannot stay resident on chip, so in bf16 mode
+    the recurrence runs frame by frame on tcgen05 GEMMs over the bf16 weights (engine._gen_stepwise_*, csrc/lstm_step.cu)
+    instead of the fp32 grid-barrier kernel that streams fp32 weights.  Against the CPU oracle: forward <= 2e-2, gradients by
+    direction and norm."""
+    import audiogan_b200 as ag
+    gk = {"state_size": 2048}
+    Bn, L = 5, 1000
+    Pg = O.pin_stopper(O.init_generator(11, **gk))
+    g = ag.Generator(embed_size=100, **gk); g.load_state_dict(Pg); g = g.cuda().set_mode("bf16")
+    gen = T.Generator().manual_seed(3)
+    z, c, up = T.randn(Bn, L // 200, 100, generator=gen), T.randn(Bn, 100, generator=gen), T.randn(Bn, L, generator=gen)
+    zr = z.clone().requires_grad_(True)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in Pg.items()}
+    xr, sr, _, _ = O.generator_forward(Pr, c, z=zr)
+    ((xr * up).sum() + 3.0 * sr.sum()).backward()                   # the stop logits take part too (they do under REINFORCE)
+    zd = z.cuda().requires_grad_(True)
+    x, s_, _, ln = g(z=zd, c=c.cuda(), u_stop=None)
+    ((x * up.cuda()).sum() + 3.0 * s_.sum()).backward()
+    assert g._plan.last_path["g_fwd"].startswith("stepwise") and g._plan.last_path["g_bwd"].startswith("stepwise"), g._plan.last_path
+    assert ln.tolist() == [L] * Bn
+    R = Report()
+    R.check("x", x, xr, 2e-2)
+    R.check("s", s_, sr, 2e-2)
+    for tag, a, b in [("dz", zd.grad, zr.grad)] + [("d" + k, dict(g.named_parameters())[k].grad, Pr[k].grad) for k in
+                                                  ("rnn.0.module.weight_hh_v", "rnn.0.module.weight_ih_v", "proj.module.weight_v",
+                                                   "rnn.0.module.bias_hh_g", "dense_res_gen.0.module.conv.weight_v")]:
+        if a is None or b is None:
+            continue
+        a, b = a.flatten().float().cpu(), b.flatten()
+        if float(b.norm()) == 0:
+            continue
+        cos, ratio = float(T.dot(a, b) / (a.norm() * b.norm())), float(a.norm() / b.norm())
+        R.rows.append((tag + " cos", cos))
+        if cos < 0.97 or abs(ratio - 1) > 0.1:
+            R.bad.append("%s: cos %.4f norm ratio %.4f" % (tag, cos, ratio))
+    R.done("gen_stepwise_h2048")
