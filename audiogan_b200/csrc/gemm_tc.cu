@@ -1514,10 +1514,20 @@ int ag_gemm_nt_tc(const ag_gemm_desc* d, void* stream) {
 #define AG_TC_NT(BN)                                                                                         \
   return R > 0 ? tc::launch_nt_tma<BN>(d, R, s)                                                              \
                : (!vec ? tc::launch_nt<BN, 2>(d, s) : (d->a_dtype == 0 ? tc::launch_nt<BN, 0>(d, s) : tc::launch_nt<BN, 1>(d, s)))
-  if (d->N > 128) { AG_TC_NT(256); }
-  if (d->N > 64) { AG_TC_NT(128); }
-  if (d->N > 32) { AG_TC_NT(64); }
-  if (d->N > 16) { AG_TC_NT(32); }
+  // Column-tile width: the widest tile N allows -- unless that leaves most SMs without a tile.  Skinny products (a handful of
+  // 128-row tiles: the per-frame GEMMs of the step-wise recurrence, M = batch) are bound by how fast the weights stream from
+  // L2, i.e. by the number of CTAs pulling: narrow the tile until ~2/3 of the SMs have one.
+  int bn = d->N > 128 ? 256 : d->N > 64 ? 128 : d->N > 32 ? 64 : d->N > 16 ? 32 : 16;
+  {
+    const int64_t rpb = R > 0 ? R : (d->a_rpb < d->M ? d->a_rpb : d->M);
+    const int64_t row_tiles = (d->M / (rpb > 0 ? rpb : 1)) * ((rpb + tc::BM - 1) / tc::BM);
+    const int64_t want = (int64_t)sm_count() * 2 / 3;
+    while (bn > 16 && row_tiles * ((d->N + bn - 1) / bn) < want && row_tiles <= 8) bn >>= 1;
+  }
+  if (bn == 256) { AG_TC_NT(256); }
+  if (bn == 128) { AG_TC_NT(128); }
+  if (bn == 64) { AG_TC_NT(64); }
+  if (bn == 32) { AG_TC_NT(32); }
   AG_TC_NT(16);
 #undef AG_TC_NT
 }
