@@ -109,6 +109,7 @@ _PROTOS = {
     "ag_conv1in_wgrad": [vp, i32, i64, vp, i64, vp, i32, i32, i64, i64, i64, vp],
     "ag_conv1in_dgrad": [vp, i32, i64, vp, vp, i64, i32, i32, i32, i64, i64, i64, i64, vp],
     "ag_wcolsum": [vp, vp, i32, i64, i64, vp, vp],
+    "ag_rowdot": [vp, i32, vp, vp, i64, i64, vp, vp],
     "ag_conv1out_fwd": [vp, i32, i64, i64, i32, vp, vp, vp, i64, i64, vp],
     "ag_conv1out_dgrad": [vp, vp, vp, i32, i64, i64, i32, i64, i64, vp],
     "ag_conv1out_wgrad": [vp, vp, i32, i64, i64, i32, vp, i64, i64, vp],

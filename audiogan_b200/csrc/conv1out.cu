@@ -326,6 +326,29 @@ __global__ void __launch_bounds__(256) wcolsum_kernel(const float* __restrict__ 
   if (c4 == 0 && rl < nrl) atomicAdd(out + 4 * K4, gs);          // every row lane of column group 0 saw a disjoint set of rows
 }
 
+
+// out[m] = sum_k X[m, k] * w[k] + bias[0]: forward of a Linear(K -> 1) (the classifier's last layer, audiogan.py:508-512) -- a GEMM with
+// N = 1 wastes a 128 x 16 tensor-core tile per 128 rows; this is one warp per row streaming the packed [M, K] activation (HBM-bound).
+__global__ void __launch_bounds__(256) rowdot_kernel(const void* __restrict__ X, int xdt, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, int64_t M, int K4, float* __restrict__ out) {
+  __shared__ float4 ws[256];
+  for (int i = threadIdx.x; i < K4; i += 256) ws[i] = make_float4(__ldg(w + 4 * i), __ldg(w + 4 * i + 1), __ldg(w + 4 * i + 2), __ldg(w + 4 * i + 3));
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const float b = bias ? __ldg(bias) : 0.f;
+  for (int64_t m = (int64_t)blockIdx.x * 8 + wid; m < M; m += (int64_t)gridDim.x * 8) {
+    float acc = 0.f;
+    for (int k4 = lane; k4 < K4; k4 += 32) {
+      const float4 x = ldg4_any(X, m * (4 * (int64_t)K4) + 4 * k4, xdt);
+      const float4 q = ws[k4];
+      acc += x.x * q.x + x.y * q.y + x.z * q.z + x.w * q.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[m] = acc + b;
+  }
+}
+
 }  // namespace ag
 
 using namespace ag;
@@ -420,6 +443,17 @@ int ag_wcolsum(const float* g, const void* X, int32_t x_dtype, int64_t M, int64_
   if (rows_per < 64) rows_per = 64;
   blocks = (M + rows_per - 1) / rows_per;
   wcolsum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, X, x_dtype, M, (int)(K / 4), out, rows_per);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+
+int ag_rowdot(const void* X, int32_t x_dtype, const float* w, const float* bias, int64_t M, int64_t K, float* out, void* stream) {
+  AG_CHECK_ARG(X && w && out && M > 0 && K > 0 && K % 4 == 0 && K <= 1024 && (reinterpret_cast<uintptr_t>(X) & (x_dtype ? 7 : 15)) == 0,
+               "ag_rowdot: bad args");
+  int64_t blocks = (M + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  rowdot_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(X, x_dtype, w, bias, M, (int)(K / 4), out);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

@@ -638,8 +638,10 @@ gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap map
   int* s_ml = s_t + BM;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // channel-prefix views (a_layout 1): k-block = (channel group of 8, block of 8 taps), a 4-D box {8 c, 8 taps, 128 rows}
-  const int nkb = pfx_G ? pfx_G * pfx_KT : (int)((d.K + BK - 1) / BK);
+  // channel-prefix views.  a_layout 1 (pfx_G > 0): k-block = (channel group of 8, block of 8 taps), a 4-D box {8 c, 128 rows, 8 taps};
+  // a_layout 2 (pfx_G < 0: -pfx_G groups of 64 channels, pfx_KT taps): k-block = (tap, channel group), a box {64 c, 128 rows, 1 tap}
+  const int pfxG = pfx_G < 0 ? -pfx_G : pfx_G;
+  const int nkb = pfx_G ? pfxG * pfx_KT : (int)((d.K + BK - 1) / BK);
   if (tid == 0) {
     for (int s = 0; s < STG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TM_NEPI / 32); }
@@ -794,9 +796,12 @@ gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap map
           const int s = it % STG;
           mbar_wait(&empty[s], ((it / STG) & 1) ^ 1);
           mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-          if (pfx_G) {
+          if (pfx_G > 0) {
             const int g = kb / pfx_KT;
             tma_load_4d(smem + s * STAGE_BYTES, &mapA, &full[s], g * 8, t0, (kb - g * pfx_KT) * 8, bt);
+          } else if (pfx_G < 0) {
+            const int j = kb / pfxG;
+            tma_load_4d(smem + s * STAGE_BYTES, &mapA, &full[s], (kb - j * pfxG) * 64, t0, j, bt);
           } else {
             tma_load_3d(smem + s * STAGE_BYTES, &mapA, &full[s], kb * BK, t0, bt);
           }
@@ -828,8 +833,8 @@ gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap map
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           // channel-prefix stage: un-swizzled [tap][row][16 B] (2 taps = 4096 B per UMMA_K); else the SWIZZLE_128B tile
-          const uint64_t da = pfx_G ? umma_desc_ns(sa, BM * 16, 128) : umma_desc(sa, 16, 1024), db = umma_desc(sa + A_BYTES, 16, 1024);
-          const uint64_t astep = pfx_G ? (uint64_t)((2 * BM * 16) >> 4) : 2ull;
+          const uint64_t da = pfx_G > 0 ? umma_desc_ns(sa, BM * 16, 128) : umma_desc(sa, 16, 1024), db = umma_desc(sa + A_BYTES, 16, 1024);
+          const uint64_t astep = pfx_G > 0 ? (uint64_t)((2 * BM * 16) >> 4) : 2ull;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             tc_mma(tacc, da + (uint64_t)k * astep, db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
@@ -875,21 +880,25 @@ static int make_map_3d(CUtensorMap* map, const void* ptr, int64_t cols, int64_t 
 }
 
 static bool nt_vec_epilogue(const ag_gemm_desc* d);
-// 4-D bf16 map of a channel-prefix im2col view {channel (contiguous), row (stride rs), tap (stride ts), batch (stride bs)};
-// box {8 channels, box_r rows, 8 taps, 1}, NO swizzle (measured: SWIZZLE_128B faults unless the box's inner dimension is
-// 128 bytes): shared memory holds [tap][row][16 bytes], i.e. per tap a column of 8-row x 16-byte core matrices -- the
-// canonical un-swizzled UMMA operand (K-major for the NT kernel: LBO = box_r*16 between taps, SBO = 128 between row groups).
+// 4-D bf16 map of a channel-prefix im2col view {channel (contiguous), row (stride rs), tap (stride ts), batch (stride bs)}.
+//   a_layout 1: box {8 channels, box_r rows, 8 taps, 1}, NO swizzle (measured: SWIZZLE_128B faults unless the box's inner
+//     dimension is 128 bytes): shared memory holds [tap][row][16 bytes], i.e. per tap a column of 8-row x 16-byte core matrices --
+//     the canonical un-swizzled UMMA operand (K-major for the NT kernel: LBO = box_r*16 between taps, SBO = 128 between row groups).
+//   a_layout 2: box {64 channels, box_r rows, 1 tap, 1}, SWIZZLE_128B: one tap's 64-channel group of box_r rows = the same
+//     [row][128 B] swizzled tile the plain 3-D map delivers (K-major block of the NT kernel, MN-major block of the TN kernel).
+//     Channels past the prefix (the last group of a prefix that is not a multiple of 64) are out of the map's bounds: zero-filled
+//     by the TMA unit, never read from memory.  128-byte requests instead of 16-byte ones: the request rate no longer bounds it.
 static int make_map_4d(CUtensorMap* map, const void* ptr, int64_t cin, int64_t taps, int64_t rows, int64_t nb, int64_t ts, int64_t rs,
-                       int64_t bs, int box_r) {
+                       int64_t bs, int box_r, bool wide) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return AG_ENOTSUP; }
   cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)rows, (cuuint64_t)taps, (cuuint64_t)nb};
   cuuint64_t strides[3] = {(cuuint64_t)rs * 2, (cuuint64_t)ts * 2, (cuuint64_t)bs * 2};
-  cuuint32_t box[4] = {8, (cuuint32_t)box_r, 8, 1};
+  cuuint32_t box[4] = {wide ? 64u : 8u, (cuuint32_t)box_r, wide ? 1u : 8u, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (4-D) failed (%d): cin %lld taps %lld rows %lld nb %lld ts %lld rs %lld bs %lld", (int)r,
               (long long)cin, (long long)taps, (long long)rows, (long long)nb, (long long)ts, (long long)rs, (long long)bs);
@@ -897,13 +906,21 @@ static int make_map_4d(CUtensorMap* map, const void* ptr, int64_t cin, int64_t t
   }
   return AG_OK;
 }
-// a_layout 1 (channel-prefix view, B / dW columns ordered (channel group of 8, tap padded to 8, channel)): taps, groups, blocks
-struct PfxGeom { int64_t taps, G, KT, Kq; };
+// Channel-prefix views.  a_layout 1: B / dW columns ordered (channel group of 8, tap padded to 8, channel): G groups, KT tap blocks.
+// a_layout 2: columns ordered (tap, channel group of 64, channel): G = ceil(prefix / 64) groups per tap, KT = taps.
+struct PfxGeom { int64_t taps, G, KT, Kq; int wide; };
 static bool pfx_geom(const ag_gemm_desc* d, PfxGeom* g) {
-  if (d->a_layout != 1 || d->a_kin <= 0 || d->a_kin % 8 != 0 || d->K % d->a_kin != 0 || d->a_k1s % 8 != 0 || d->a_k1s <= 0) return false;
+  if ((d->a_layout != 1 && d->a_layout != 2) || d->a_kin <= 0 || d->a_kin % 8 != 0 || d->K % d->a_kin != 0 || d->a_k1s % 8 != 0 || d->a_k1s <= 0)
+    return false;
   g->taps = d->K / d->a_kin;
-  g->G = d->a_kin / 8;
-  g->KT = (g->taps + 7) / 8;
+  g->wide = d->a_layout == 2;
+  if (g->wide) {
+    g->G = (d->a_kin + 63) / 64;
+    g->KT = g->taps;
+  } else {
+    g->G = d->a_kin / 8;
+    g->KT = (g->taps + 7) / 8;
+  }
   g->Kq = g->G * g->KT * 64;
   return true;
 }
@@ -940,9 +957,9 @@ static int launch_nt_tma2(const ag_gemm_desc* d, int64_t R, cudaStream_t s) {
   CUtensorMap mapA, mapB;
   const bool a_flat = d->a_rpb >= d->M;
   const int64_t nb = d->M / R;
-  PfxGeom pg = {0, 0, 0, 0};
+  PfxGeom pg = {0, 0, 0, 0, 0};
   const bool pfx = pfx_geom(d, &pg);
-  int rc = pfx ? make_map_4d(&mapA, d->A, d->a_kin, pg.taps, R, nb, d->a_k1s, d->a_rs, nb == 1 ? R * d->a_rs : d->a_bs, BM)
+  int rc = pfx ? make_map_4d(&mapA, d->A, d->a_kin, pg.taps, R, nb, d->a_k1s, d->a_rs, nb == 1 ? R * d->a_rs : d->a_bs, BM, pg.wide != 0)
                : make_map_3d(&mapA, d->A, d->K, R, nb, d->a_rs, (a_flat || nb == 1) ? R * d->a_rs : d->a_bs, BK, BM);
   if (rc) return rc;
   rc = make_map_2d(&mapB, d->B, d->N, pfx ? pg.Kq : d->K, d->ldb, BK, BN);
@@ -957,7 +974,8 @@ static int launch_nt_tma2(const ag_gemm_desc* d, int64_t R, cudaStream_t s) {
   const int64_t total = nb * tpb * ntn;
   AG_CHECK_ARG(total < (1ll << 31), "ag_gemm_nt_tc: too many tiles");
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  kern<<<grid, TM_THREADS, smem, s>>>(*d, mapA, mapB, (int)R, (int)tpb, (int)ntn, (int)total, (int)pg.G, (int)pg.KT);
+  kern<<<grid, TM_THREADS, smem, s>>>(*d, mapA, mapB, (int)R, (int)tpb, (int)ntn, (int)total,
+                                          (int)(pg.wide ? -pg.G : pg.G), (int)pg.KT);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
@@ -1298,9 +1316,12 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
         tma_load_3d(sa + RM * 128, &mapY, &full[s], n0 + 64, t0, b);
 #pragma unroll
         for (int j = 0; j < BNK / 64; ++j) {
-          if (pfx_KT) {      // channel-prefix view: 64-column block kb = (channel group, tap block); past the end -> zero fill
+          if (pfx_KT > 0) {  // channel-prefix view: 64-column block kb = (channel group, tap block); past the end -> zero fill
             const int kb = k0 / 64 + j, g = kb / pfx_KT;
             tma_load_4d(sa + A_BYTES + j * (RM * 128), &mapA, &full[s], g * 8, t0, (kb - g * pfx_KT) * 8, b);
+          } else if (pfx_KT < 0) {   // a_layout 2 (-pfx_KT groups of 64 channels per tap): block kb = (tap, channel group); a tap past
+            const int kb = k0 / 64 + j, tap = kb / (-pfx_KT);                          // the last one is out of bounds -> zero fill
+            tma_load_4d(sa + A_BYTES + j * (RM * 128), &mapA, &full[s], (kb + tap * pfx_KT) * 64, t0, tap, b);
           } else {
             tma_load_3d(sa + A_BYTES + j * (RM * 128), &mapA, &full[s], k0 + j * 64, t0, b);
           }
@@ -1319,8 +1340,8 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
         // channel-prefix stage of the activation operand: un-swizzled [tap][row][16 B] = MN-major core-matrix columns
         // (LBO = 128 B between 8-row groups along the reduction, SBO = RM*16 B between 8-column groups)
         const uint64_t da = umma_desc(sa, RM * 128, 1024);
-        const uint64_t db = pfx_KT ? umma_desc_ns(sa + A_BYTES, 128, RM * 16) : umma_desc(sa + A_BYTES, RM * 128, 1024);
-        const uint64_t bstep = pfx_KT ? 16ull : 128ull;           // 16 reduction rows: 2 x 128 B, or 2048 B in the swizzled block
+        const uint64_t db = pfx_KT > 0 ? umma_desc_ns(sa + A_BYTES, 128, RM * 16) : umma_desc(sa + A_BYTES, RM * 128, 1024);
+        const uint64_t bstep = pfx_KT > 0 ? 16ull : 128ull;           // 16 reduction rows: 2 x 128 B, or 2048 B in the swizzled block
 #pragma unroll
         for (int k = 0; k < RM / 16; ++k)
           tc_mma(tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)k * bstep, idesc, (it | k) ? 1u : 0u);
@@ -1451,11 +1472,11 @@ static int launch_tn_tma(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones
   const int64_t nb = d->M / R;
   int rc = make_map_3d(&mapY, d->C, d->N, R, nb, d->c_rs, (y_flat || nb == 1) ? R * d->c_rs : d->c_bs, 64, 64);
   if (rc) return rc;
-  PfxGeom pg = {0, 0, 0, 0};
+  PfxGeom pg = {0, 0, 0, 0, 0};
   const bool pfx = pfx_geom(d, &pg);
   const int64_t Kd = pfx ? pg.Kq : d->K;                  // columns of dw the kernel produces
   AG_CHECK_ARG(ldw >= Kd + (ones_col ? 1 : 0), "ag_gemm_tn_tc: bad ldw for the channel-prefix layout");
-  rc = pfx ? make_map_4d(&mapA, d->A, d->a_kin, pg.taps, R, nb, d->a_k1s, d->a_rs, nb == 1 ? R * d->a_rs : d->a_bs, 64)
+  rc = pfx ? make_map_4d(&mapA, d->A, d->a_kin, pg.taps, R, nb, d->a_k1s, d->a_rs, nb == 1 ? R * d->a_rs : d->a_bs, 64, pg.wide != 0)
            : make_map_3d(&mapA, d->A, d->K, R, nb, d->a_rs, (a_flat || nb == 1) ? R * d->a_rs : d->a_bs, 64, 64);
   if (rc) return rc;
   constexpr int STAGES = nt_stages(BNK);
@@ -1473,7 +1494,7 @@ static int launch_tn_tma(const ag_gemm_desc* d, float* dw, int64_t ldw, int ones
   static bool attr_set = false;      // once per instantiation (a driver call per launch otherwise)
   if (!attr_set) { AG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
   kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), TNT_THREADS, smem, s>>>(mapY, mapA, dw, ldw, (int)d->N, (int)Kd, (int)spb,
-                                                                                (int)total, (int)sps, (int)pg.KT);
+                                                                                (int)total, (int)sps, (int)(pg.wide ? -pg.G : pg.KT));
   AG_LAUNCH_CHECK();
   if (ones_col) {
     int lg = 0;
@@ -1509,8 +1530,8 @@ int ag_gemm_nt_tc(const ag_gemm_desc* d, void* stream) {
   const bool vec = d->a_kin % 8 == 0 && d->K % 8 == 0 && d->a_bs % al == 0 && d->a_rs % al == 0 && d->a_k1s % al == 0 &&
                    (reinterpret_cast<uintptr_t>(d->A) & 15) == 0;
   const int64_t R = vec ? tc::tma_rows_per_batch(d) : 0;
-  AG_CHECK_ARG(d->a_layout == 0 || (d->a_layout == 1 && R > 0),
-               "ag_gemm_nt_tc: the channel-prefix layout (a_layout 1) needs bf16 operands, 16-byte aligned strides and a vector epilogue");
+  AG_CHECK_ARG(d->a_layout == 0 || ((d->a_layout == 1 || d->a_layout == 2) && R > 0),
+               "ag_gemm_nt_tc: the channel-prefix layouts (a_layout 1, 2) need bf16 operands, 16-byte aligned strides and a vector epilogue");
 #define AG_TC_NT(BN)                                                                                         \
   return R > 0 ? tc::launch_nt_tma<BN>(d, R, s)                                                              \
                : (!vec ? tc::launch_nt<BN, 2>(d, s) : (d->a_dtype == 0 ? tc::launch_nt<BN, 0>(d, s) : tc::launch_nt<BN, 1>(d, s)))
@@ -1550,7 +1571,7 @@ int ag_gemm_tn_tc(const ag_gemm_desc* d, float* dw, int64_t ldw, int32_t ones_co
     if (Kd > 64) return tc::launch_tn_tma<128>(d, dw, ldw, ones_col, Rt, s);
     return tc::launch_tn_tma<64>(d, dw, ldw, ones_col, Rt, s);
   }
-  AG_CHECK_ARG(d->a_layout != 1, "ag_gemm_tn_tc: the channel-prefix layout (a_layout 1) needs bf16 operands with 16-byte aligned strides");
+  AG_CHECK_ARG(d->a_layout == 0, "ag_gemm_tn_tc: the channel-prefix layouts (a_layout 1, 2) need bf16 operands with 16-byte aligned strides");
   const int64_t ktot = d->K + (ones_col ? 1 : 0);
   if (ktot > 128) return tc::launch_tn<256>(d, dw, ldw, ones_col, vy, va, s);
   if (ktot > 64) return tc::launch_tn<128>(d, dw, ldw, ones_col, vy, va, s);

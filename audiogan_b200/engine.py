@@ -240,10 +240,11 @@ class _GenFn(torch.autograd.Function):
                 K.zero_pads(Hh, 1, Lh + 1)
                 # TMA-fed kernel over a 4-D tensor map (channel prefix, row, tap, batch).  Its boxes have 16-byte inner rows, so
                 # for wide prefixes the producer-warp kernel is faster (measured: cin 8 / 24 -> 1.9x / 1.5x faster, 56 equal, 88 0.6x)
-                if adt == torch.bfloat16 and cin <= _TMA_CIN:
+                # (plan.alay 1).  Prefixes of 32 channels and more use 128-byte boxes (plan.alay 2: one tap's 64-channel group per box).
+                if adt == torch.bfloat16 and (cin <= _TMA_CIN or plan.alay[li] == 2):
                     K.gemm_nt(n * Lh, hid, k * cin, (Xs, (GPAD - p) * CT), (Lh, Lp * CT, s * CT, cin, CT),
                               plan.Poff("c%d.wq" % li), plan.Kq[li], (Hh, hid), (Lh, (Lh + 2) * hid, hid),
-                              bias=plan.Poff("c%d.b" % li), act=1, a_layout=1)
+                              bias=plan.Poff("c%d.b" % li), act=1, a_layout=plan.alay[li])
                 else:
                     K.gemm_nt(n * Lh, hid, k * cin, (Xs, (GPAD - p) * CT), (Lh, Lp * CT, s * CT, cin, CT),
                               plan.Poff("c%d.w" % li), k * cin, (Hh, hid), (Lh, (Lh + 2) * hid, hid),
@@ -339,7 +340,7 @@ class _GenFn(torch.autograd.Function):
                         if adt == torch.bfloat16:
                             Kq = plan.Kq[li]
                             K.gemm_tn(B * Lh, hid, k * cin, (dH, hid), (Lh, (Lh + 2) * hid, hid), (Xd, (GPAD - p) * CT),
-                                      (Lh, Lp * CT, s * CT, cin, CT), plan.GPoff("c%d.wq" % li), Kq + 1, ones_col=True, a_layout=1)
+                                      (Lh, Lp * CT, s * CT, cin, CT), plan.GPoff("c%d.wq" % li), Kq + 1, ones_col=True, a_layout=plan.alay[li])
                             K.gather(plan.GPoff("c%d.w" % li), plan.GPoff("c%d.wq" % li), plan.q2c[li])
                         else:
                             K.gemm_tn(B * Lh, hid, k * cin, (dH, hid), (Lh, (Lh + 2) * hid, hid), (Xd, (GPAD - p) * CT),
@@ -582,8 +583,12 @@ class _DiscTailFn(torch.autograd.Function):
         h3 = torch.empty(B * Tm, S // 2, device=dev, dtype=adt)
         K.gemm_nt(B * Tm, S // 2, S, (r2, S), geo, plan.Poff("k0.w"), S, h3, (B * Tm, 0, S // 2), bias=plan.Poff("k0.b"), act=1)
         logits = _empty(B, Tm, device=dev)
-        K.gemm_nt(B * Tm, 1, S // 2, h3, (B * Tm, 0, S // 2), plan.Poff("k2.w"), S // 2, logits, (B * Tm, 0, 1),
-                  bias=plan.Poff("k2.b"))
+        if bf and (S // 2) % 4 == 0 and S // 2 <= 1024:
+            # Linear(S/2 -> 1): one warp per row over the packed activation (a GEMM with one output column wastes the tile)
+            K.rowdot(h3, plan.Poff("k2.w"), plan.Poff("k2.b"), logits, B * Tm, S // 2)
+        else:
+            K.gemm_nt(B * Tm, 1, S // 2, h3, (B * Tm, 0, S // 2), plan.Poff("k2.w"), S // 2, logits, (B * Tm, 0, 1),
+                      bias=plan.Poff("k2.b"))
         ctx.plan, ctx.dims = plan, (B, Cf, T6, Tm)
         ctx.bufs = (feat, c1, nfr, hbuf, gates, cbuf, r1, r2, h3, hbuf16)
         return logits

@@ -172,6 +172,11 @@ def wcolsum(g, X, M, Kn, out):
     A.call("ag_wcolsum", addr(g), addr(X), _dtype_of(X), M, Kn, addr(out), A.stream())
 
 
+def rowdot(X, w, bias, out, M, Kn):
+    """out[m] = sum_k X[m, k] * w[k] + bias[0] (Linear(K -> 1) forward)"""
+    A.call("ag_rowdot", addr(X), _dtype_of(X), addr(w), addr(bias), M, Kn, addr(out), A.stream())
+
+
 def outer_dact(g, w, act, out, M, N, slope=LRELU_SLOPE):
     """out[m, n] = g[m] * w[n] * lrelu'(act[m, n]) (packed [M, N]; act / out fp32 or bf16)."""
     A.call("ag_outer_dact", addr(g), addr(w), addr(act), _dtype_of(act), addr(out), _dtype_of(out), M, N, float(slope), A.stream())

@@ -389,7 +389,8 @@ def build_generator_plan(mod, device):
         return idx.index_select(dim, pos_t[:cin])
 
     cin = 1
-    pl.cinp, pl.coff, pl.skip_off, pl.q2c, pl.Kq = [], [], [], [], []
+    pl.cinp, pl.coff, pl.skip_off, pl.q2c, pl.Kq, pl.alay = [], [], [], [], [], []
+    PFX64 = int(os.environ.get("AUDIOGAN_PFX64", "32"))       # A/B knob: narrowest channel prefix on the 128-byte-box layout
     for li, (k, s, hid, out) in enumerate(mod._struct):
         cw, cb, dw, db = convs[li]
         kd = k - 1
@@ -414,14 +415,26 @@ def build_generator_plan(mod, device):
         # conv data-gradient over 3 taps: [(r', ci_p), (u, h)] = Wc[h, ci, s*(2-u) + r']
         cpad = torch.cat([cwp, neg(hid, cp, 3 * s - k)], 2).view(hid, cp, 3, s).flip(2)   # [h, ci_p, u, r']
         pl.layout("c%d.wg" % li, cpad.permute(3, 1, 2, 0).reshape(s * cp, 3 * hid))
-        # the same filter for the TMA-fed kernels' channel-prefix view (include/audiogan_b200.h: a_layout 1): columns ordered
-        # (channel group of 8, tap padded to a multiple of 8, channel); its gradient region + the map back to "c%d.w"'s
-        G_, KT = cp // 8, (k + 7) // 8
-        Kq = G_ * KT * 64
-        cq = torch.cat([cwp, neg(hid, cp, KT * 8 - k)], 2).view(hid, G_, 8, KT * 8)          # [h, g, c8, tap]
-        pl.layout("c%d.wq" % li, cq.permute(0, 1, 3, 2).reshape(hid, Kq))
-        gq = pl.grad_region("c%d.wq" % li, (hid, Kq + 1))
-        gqv = gq[:, :Kq].view(hid, G_, KT * 8, 8)[:, :, :k].permute(0, 2, 1, 3).reshape(hid, k * cp)      # -> (tap, ci_p)
+        # the same filter for the TMA-fed kernels' channel-prefix view (include/audiogan_b200.h: a_layout 1 / 2); its gradient region +
+        # the map back to "c%d.w"'s.  Narrow prefixes: columns ordered (channel group of 8, tap padded to a multiple of 8, channel),
+        # 16-byte TMA boxes.  Prefixes of PFX64 channels and more: columns ordered (tap, channel group of 64, channel), 128-byte boxes
+        # (the TMA request rate bounds the 16-byte variant: 0.6x the producer-warp kernel at 88 channels).
+        if cp >= PFX64:
+            G_ = (cp + 63) // 64
+            Kq = k * G_ * 64
+            cq = torch.cat([cwp, neg(hid, G_ * 64 - cp, k)], 1)                                  # [h, G*64, tap]
+            pl.layout("c%d.wq" % li, cq.permute(0, 2, 1).reshape(hid, Kq))
+            gq = pl.grad_region("c%d.wq" % li, (hid, Kq + 1))
+            gqv = gq[:, :Kq].view(hid, k, G_ * 64)[:, :, :cp].reshape(hid, k * cp)               # -> (tap, ci_p)
+            pl.alay.append(2)
+        else:
+            G_, KT = cp // 8, (k + 7) // 8
+            Kq = G_ * KT * 64
+            cq = torch.cat([cwp, neg(hid, cp, KT * 8 - k)], 2).view(hid, G_, 8, KT * 8)          # [h, g, c8, tap]
+            pl.layout("c%d.wq" % li, cq.permute(0, 1, 3, 2).reshape(hid, Kq))
+            gq = pl.grad_region("c%d.wq" % li, (hid, Kq + 1))
+            gqv = gq[:, :Kq].view(hid, G_, KT * 8, 8)[:, :, :k].permute(0, 2, 1, 3).reshape(hid, k * cp)      # -> (tap, ci_p)
+            pl.alay.append(1)
         pl.q2c.append((torch.cat([gqv, gq[:, Kq:]], 1) - pl.gpack.off["c%d.wq" % li]).to(torch.int32).contiguous().to(device))
         pl.Kq.append(Kq)
         gc = pl.grad_region("c%d.w" % li, (hid, k * cp + 1))

@@ -68,7 +68,11 @@ typedef struct ag_gemm_desc {
   int32_t a_layout;   /* 0: B / dW columns in A's column order.  1 (tensor-core path, bf16, channel-prefix views with
                          a_kin % 8 == 0): columns ordered (channel group g of 8, tap j padded to a multiple of 8, channel c),
                          column = ((g*KT + j/8)*8 + j%8)*8 + c with KT = ceil(taps/8), taps = K/a_kin; ldb / ldw >=
-                         (a_kin/8)*KT*64 (+1 with ones_col, the bias column comes last); padded taps hold zeros. */
+                         (a_kin/8)*KT*64 (+1 with ones_col, the bias column comes last); padded taps hold zeros.
+                         2 (same conditions): columns ordered (tap j, channel group g of 64, channel c), column =
+                         (j*G + g)*64 + c with G = ceil(a_kin/64); ldb / ldw >= taps*G*64 (+1 with ones_col); the columns of
+                         channels >= a_kin hold zeros (B) / receive zeros (dW).  128-byte TMA requests: the layout for prefixes
+                         of 32 channels and more. */
 } ag_gemm_desc;
 
 /* C = epilogue(A . B^T).  fp32 FFMA path ("fp32 mode", <=1e-5 parity). */
@@ -285,6 +289,9 @@ int ag_conv1in_dgrad(const void* dy, int32_t dy_dtype, int64_t dy_bs, const floa
 /* Weight + bias gradient of a Linear(K -> 1) (the classifier's last layer, audiogan.py:508-512 backward):
  * out[k] += sum_m g[m] * X[m*K + k], out[K] += sum_m g[m]; X packed [M, K], dtype 0 fp32 / 1 bf16, K % 4 == 0, K <= 1024. */
 int ag_wcolsum(const float* g, const void* X, int32_t x_dtype, int64_t M, int64_t K, float* out, void* stream);
+/* Forward of the same Linear(K -> 1) (audiogan.py:508-512, the logits of :549): out[m] = sum_k X[m*K + k] * w[k] + bias[0]
+ * (bias may be null); X packed [M, K], dtype 0 fp32 / 1 bf16, K % 4 == 0, K <= 1024; w / bias fp32.  One warp per row. */
+int ag_rowdot(const void* X, int32_t x_dtype, const float* w, const float* bias, int64_t M, int64_t K, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Last generator layer, Conv1d(C -> 1, k) over the dense channel-last buffer (audiogan.py:403-407, :467): HBM-bound

@@ -666,6 +666,63 @@ def test_gemm_tma_channel_prefix_view(Bn, cin, CT, hid, L, k, s):
 
 
 @pytest.mark.parametrize("dt", [T.float32, T.bfloat16])
+def test_rowdot_linear_to_one(dt):
+    """ag_rowdot: forward of the classifier's Linear(512 -> 1) (audiogan.py:508-512) against torch on the same (rounded) rows"""
+    from audiogan_b200 import kernels as Kn
+    T.manual_seed(31)
+    for M, Kd in ((1037, 512), (5, 8), (300, 1024)):
+        X = T.randn(M, Kd).to(dt)
+        w, b = T.randn(Kd + 3)[3:].contiguous(), T.randn(1)          # w at an odd offset: no alignment assumed
+        wg = T.randn(Kd + 3).cuda()
+        wg[3:] = w.cuda()
+        out = T.empty(M, device="cuda")
+        Kn.rowdot(X.cuda(), (wg, 3), b.cuda(), out, M, Kd)
+        ref = X.double() @ w.double() + b.double()
+        assert float((out.cpu().double() - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("Bn,cin,CT,hid,L,k,s", [(3, 32, 128, 64, 1000, 9, 4), (2, 64, 128, 64, 1600, 9, 4), (2, 96, 128, 32, 520, 9, 4),
+                                                  (2, 88, 120, 32, 520, 9, 4), (2, 16, 128, 128, 1600, 17, 8)])
+def test_gemm_tma_channel_prefix_view_wide(Bn, cin, CT, hid, L, k, s):
+    """a_layout 2: the same conv over a channel prefix, through 128-byte TMA boxes {64 channels, rows, 1 tap}; filter / gradient
+    columns ordered (tap, channel group of 64, channel), the channels past the prefix zero-filled by the TMA unit (the buffer
+    holds data there that must not leak in).  Forward (bias + LeakyReLU), weight + bias gradient against conv1d."""
+    from audiogan_b200 import kernels as Kn
+    T.manual_seed(23)
+    p, Lh, PAD = (k - 1) // 2, L // s, 8
+    Lp = L + 2 * PAD
+    Xd = T.zeros(Bn, Lp, CT)
+    Xd[:, PAD:PAD + L] = T.randn(Bn, L, CT)             # channels >= cin hold data the view must not read
+    Xd = Xd.bfloat16()
+    w = (T.randn(hid, cin, k) / (cin * k) ** 0.5).bfloat16()
+    b = T.randn(hid)
+    G_ = (cin + 63) // 64
+    Kq = k * G_ * 64
+    wq = T.zeros(hid, k, G_ * 64)
+    wq[:, :, :cin] = w.float().permute(0, 2, 1)
+    wq = wq.reshape(hid, Kq).bfloat16().cuda()
+    x = Xd[:, PAD:PAD + L, :cin].float().permute(0, 2, 1)
+    wr, br = w.float().clone().requires_grad_(), b.clone().requires_grad_()
+    pre = F.conv1d(x, wr, br, stride=s, padding=p)[:, :, :Lh]
+    ref = F.leaky_relu(pre, 0.01)
+    Hh = T.zeros(Bn, Lh + 2, hid, device="cuda", dtype=T.bfloat16)
+    Xg = Xd.cuda()
+    Kn.gemm_nt(Bn * Lh, hid, k * cin, (Xg, (PAD - p) * CT), (Lh, Lp * CT, s * CT, cin, CT), wq, Kq, (Hh, hid),
+               (Lh, (Lh + 2) * hid, hid), bias=b.cuda(), act=1, tc=True, a_layout=2)
+    assert rel(Hh[:, 1:Lh + 1], ref.permute(0, 2, 1)) < 8e-3
+    dH = T.randn(Bn, Lh, hid).bfloat16()
+    pre.backward(dH.float().permute(0, 2, 1))
+    dHp = T.zeros(Bn, Lh + 2, hid, dtype=T.bfloat16)
+    dHp[:, 1:Lh + 1] = dH
+    dw = T.zeros(hid, Kq + 1, device="cuda")
+    Kn.gemm_tn(Bn * Lh, hid, k * cin, (dHp.cuda(), hid), (Lh, (Lh + 2) * hid, hid), (Xg, (PAD - p) * CT),
+               (Lh, Lp * CT, s * CT, cin, CT), dw, Kq + 1, ones_col=True, tc=True, a_layout=2)
+    got = dw[:, :Kq].view(hid, k, G_ * 64)[:, :, :cin].permute(0, 2, 1)
+    assert rel(got, wr.grad) < 3e-5 and rel(dw[:, Kq], br.grad) < 3e-5
+    assert G_ * 64 == cin or float(dw[:, :Kq].view(hid, k, G_ * 64)[:, :, cin:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("dt", [T.float32, T.bfloat16])
 def test_conv1in_dgrad_and_wcolsum(dt):
     """Direct kernels for the two GEMMs with 1-2 output columns: gradient of the raw waveform through the discriminator's first
     conv (k = 7, s = 2, C_in = 1), and the weight / bias gradient of the classifier's Linear(K -> 1)."""
