@@ -537,6 +537,11 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 template <bool CBF, bool AUXBF, int CH, int F>
 __device__ __forceinline__ void epi_chunk_vec(const ag_gemm_desc& d, const float* __restrict__ tr, const int4* __restrict__ rowtab,
                                               int wq, int lane, int nc, float alpha) {
@@ -620,7 +625,8 @@ __device__ __forceinline__ void epi_chunk_vec(const ag_gemm_desc& d, const float
 template <int BN, bool VECC>
 __global__ void __launch_bounds__(TM_THREADS, 1)
 gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                   int R, int tpb, int ntn, int total_tiles, int pfx_G, int pfx_KT) {
+                   int R, int tpb, int ntn, int total_tiles, int pfx_G, int pfx_KT, const __grid_constant__ CUtensorMap mapS,
+                   const __grid_constant__ CUtensorMap mapD, int pf_flags, int pf_cn) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int STG = tma_stages(BN);
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -807,6 +813,16 @@ gemm_nt_tma_kernel(const ag_gemm_desc d, const __grid_constant__ CUtensorMap map
           }
           tma_load_2d(smem + s * STAGE_BYTES + A_BYTES, &mapB, &full[s], kb * BK, nt * BN);
         }
+        // The epilogue's skip / LeakyReLU' operands are read once, 8 bytes per lane by 8 warps (~16 KB in flight per SM): their
+        // DRAM latency, not bandwidth, sets the tile time of the thin GEMMs that have them.  The producer runs STG stages ahead of
+        // the MMAs: one TMA prefetch per operand and tile (the whole box of C-addressed runs) puts the lines in the L2 early.
+        if (pf_flags & 3) {
+          const int n0 = nt * BN, run = n0 / pf_cn;
+          const int c0 = (pf_flags & 4) ? n0 - run * pf_cn : 0;
+          const int rowc = (pf_flags & 8) ? bt * R + t0 : t0, batc = (pf_flags & 8) ? 0 : bt;
+          if (pf_flags & 1) tma_prefetch_4d(&mapS, c0, run, rowc, batc);
+          if (pf_flags & 2) tma_prefetch_4d(&mapD, c0, run, rowc, batc);
+        }
       }
     }
     __syncwarp();
@@ -952,6 +968,40 @@ static int64_t tma_rows_per_batch(const ag_gemm_desc* d) {
   return R;
 }
 
+static int epi_prefetch_on() {          // A/B knob: AUDIOGAN_EPI_PF=0 switches the epilogue-operand L2 prefetch off
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AUDIOGAN_EPI_PF"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
+// 4-D bf16 map of an epilogue operand in C addressing {column within a run of c_nin, run (stride c_n1s), row (stride c_rs), batch
+// (stride c_bs)}; box = the runs one BN-column tile touches x 128 rows.  Only used by cp.async.bulk.prefetch.tensor (no shared-memory
+// destination).  Returns false when the geometry does not fit a tensor map (16-byte strides / box rows): no prefetch then.
+template <int BN>
+static bool make_map_epi(CUtensorMap* map, const ag_gemm_desc* d, const void* ptr, int* flags, int* cn_out) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || !ptr || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return false;
+  const bool c_flat = d->c_rpb >= d->M;
+  const int64_t cn = d->c_nin < d->N ? d->c_nin : d->N;
+  const int64_t nruns = (d->N + cn - 1) / cn;
+  const bool wide = cn >= BN;
+  const int64_t box_c = wide ? BN : cn;
+  int64_t box_runs = wide ? 1 : ((BN + cn - 1) / cn + ((BN % cn) ? 1 : 0));
+  if (box_runs > 256) box_runs = 256;
+  const int64_t rows = c_flat ? d->M : d->c_rpb, nbat = c_flat ? 1 : d->M / d->c_rpb;
+  const int64_t rstr = d->c_rs, nstr = nruns > 1 ? d->c_n1s : d->c_rs, bstr = nbat > 1 ? d->c_bs : rows * d->c_rs;
+  if (box_c > 256 || box_c % 8 != 0 || rstr <= 0 || rstr % 8 != 0 || nstr <= 0 || nstr % 8 != 0 || bstr <= 0 || bstr % 8 != 0) return false;
+  if (rows >= (1ll << 31) || nbat >= (1ll << 31)) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)cn, (cuuint64_t)nruns, (cuuint64_t)rows, (cuuint64_t)nbat};
+  cuuint64_t strides[3] = {(cuuint64_t)nstr * 2, (cuuint64_t)rstr * 2, (cuuint64_t)bstr * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_runs, (cuuint32_t)BM, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  if (fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  *flags |= (wide ? 4 : 0) | (c_flat ? 8 : 0);
+  *cn_out = (int)cn;
+  return true;
+}
 template <int BN, bool VECC>
 static int launch_nt_tma2(const ag_gemm_desc* d, int64_t R, cudaStream_t s) {
   CUtensorMap mapA, mapB;
@@ -973,9 +1023,19 @@ static int launch_nt_tma2(const ag_gemm_desc* d, int64_t R, cudaStream_t s) {
   const int64_t tpb = (R + BM - 1) / BM, ntn = (d->N + BN - 1) / BN;
   const int64_t total = nb * tpb * ntn;
   AG_CHECK_ARG(total < (1ll << 31), "ag_gemm_nt_tc: too many tiles");
+  // L2 prefetch of the bf16 epilogue operands (skip, LeakyReLU' operand), one TMA prefetch per tile
+  CUtensorMap mapS = mapA, mapD = mapA;
+  int pf_flags = 0, pf_cn = 1;
+  if (epi_prefetch_on() && d->aux_dtype == 1 && (d->skip || d->dact)) {
+    const bool c_flat = d->c_rpb >= d->M;
+    if (c_flat || d->c_rpb == R) {                     // the row tiles are the C operand's (batch, row) tiles
+      if (d->skip && make_map_epi<BN>(&mapS, d, d->skip, &pf_flags, &pf_cn)) pf_flags |= 1;
+      if (d->dact && make_map_epi<BN>(&mapD, d, d->dact, &pf_flags, &pf_cn)) pf_flags |= 2;
+    }
+  }
   const int grid = (int)(total < sm_count() ? total : sm_count());
   kern<<<grid, TM_THREADS, smem, s>>>(*d, mapA, mapB, (int)R, (int)tpb, (int)ntn, (int)total,
-                                          (int)(pg.wide ? -pg.G : pg.G), (int)pg.KT);
+                                          (int)(pg.wide ? -pg.G : pg.G), (int)pg.KT, mapS, mapD, pf_flags, pf_cn);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }
