@@ -70,11 +70,18 @@ __global__ void __launch_bounds__(256) conv1out_fwd_strip_kernel(const void* __r
   const int64_t rend = t1 + KK - 1;                 // input rows [t0, rend)
   const bool hi = (lane & 16) != 0, hi2 = (lane & 8) != 0;
   const int idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
-  for (int64_t r0 = t0; r0 < rend; r0 += 4) {
+  for (int64_t rr = t0; rr < rend; rr += 8) {
+    float4 x8[8];                                     // 8 rows in flight per lane (the kernel is bound by bytes in flight)
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      x8[i] = (active && rr + i < rend) ? ldg4_any(X, xb + (rr + i) * C, XDT) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+    const int64_t r0 = rr + 4 * h;
+    if (r0 >= rend) break;
     float4 x[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      x[i] = (active && r0 + i < rend) ? ldg4_any(X, xb + (r0 + i) * C, XDT) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 4; ++i) x[i] = x8[4 * h + i];
     float o[4 + KK - 1];                              // o[m]: this lane's partial of output r0 - (KK-1) + m
 #pragma unroll
     for (int m = 0; m < 4 + KK - 1; ++m) o[m] = m < KK - 1 ? carry[m] : 0.f;
@@ -94,6 +101,7 @@ __global__ void __launch_bounds__(256) conv1out_fwd_strip_kernel(const void* __r
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     const int64_t t = r0 - (KK - 1) + idx;
     if ((lane & 7) == 0 && t >= t0 && t < t1) out[b * T + t] = v + bv;
+    }
   }
 }
 
@@ -138,13 +146,13 @@ __global__ void __launch_bounds__(128) conv1out_wgrad_kernel(const float* __rest
     float4 acc[KMAX];
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t r = r0 + rl; r < r1; r += 16) {        // 4 rows of this lane in flight before the first use
-      float4 x[4];
+    for (int64_t r = r0 + rl; r < r1; r += 32) {        // 8 rows of this lane in flight before the first use
+      float4 x[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
         x[i] = (r + 4 * i < r1) ? ldg4_any(X, b * x_bs + (r + 4 * i) * C + cc, xdt) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
 #pragma unroll
         for (int j = 0; j < KMAX; ++j) {
           const int64_t t = r + 4 * i - j;             // X row r is tap j of output t = r - j
@@ -417,7 +425,7 @@ int ag_conv1out_wgrad(const float* g, const void* X, int32_t x_dtype, int64_t x_
   AG_CHECK_ARG(g && X && dw && B > 0 && B < 65536 && T > 0 && C > 0 && C % 4 == 0 && C <= 508 && k > 0 && k <= 4 && x_bs % 4 == 0,
                "ag_conv1out_wgrad: bad args");
   AG_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & (x_dtype ? 7 : 15)) == 0, "ag_conv1out_wgrad: unaligned");
-  const int rpb = 1024;
+  const int rpb = 512;
   dim3 grid((unsigned)((T + k - 1 + rpb - 1) / rpb), (unsigned)B);
   if (x_dtype) conv1out_wgrad_kernel<4, 1><<<grid, 128, 0, (cudaStream_t)stream>>>(g, X, x_bs, (int)C, k, dw, T, rpb);
   else conv1out_wgrad_kernel<4, 0><<<grid, 128, 0, (cudaStream_t)stream>>>(g, X, x_bs, (int)C, k, dw, T, rpb);
