@@ -146,13 +146,13 @@ __global__ void __launch_bounds__(128) conv1out_wgrad_kernel(const float* __rest
     float4 acc[KMAX];
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t r = r0 + rl; r < r1; r += 32) {        // 8 rows of this lane in flight before the first use
-      float4 x[8];
+    for (int64_t r = r0 + rl; r < r1; r += 16) {        // 4 rows of this lane in flight before the first use
+      float4 x[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
         x[i] = (r + 4 * i < r1) ? ldg4_any(X, b * x_bs + (r + 4 * i) * C + cc, xdt) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
 #pragma unroll
         for (int j = 0; j < KMAX; ++j) {
           const int64_t t = r + 4 * i - j;             // X row r is tap j of output t = r - j
@@ -182,10 +182,81 @@ __global__ void __launch_bounds__(128) conv1out_wgrad_kernel(const float* __rest
     }
     __syncthreads();
   }
-  if (threadIdx.x == 127) {                            // the bias gradient over this block's outputs
+  {                                                    // the bias gradient over this block's outputs: one atomic per warp
     float s = 0.f;
-    for (int64_t t = r0; t < min(T, r0 + (int64_t)rows_per_block); ++t) s += gb[t];
-    atomicAdd(dw + k * C, s);
+    for (int64_t t = r0 + threadIdx.x; t < min(T, r0 + (int64_t)rows_per_block); t += 128) s += __ldg(gb + t);
+    s = warp_sum(s);
+    if (c4 == 0) atomicAdd(dw + k * C, s);
+  }
+}
+
+// Streaming version for C <= 128 and a compile-time tap count: a warp owns a strip of S consecutive buffer rows, lane = 4
+// channels, 8 rows in flight; the KK + 7 gradient values a batch of 8 rows needs are loaded once (the kernel above re-derives
+// a bounds-checked g for every (row, tap) pair: ~200 instructions per KB of X, issue-bound at 1.4 TB/s).  X row r is tap j of
+// output t = r - j.  The block's 8 warps meet in shared memory: one set of atomics per block.
+template <int KK, int xdt>
+__global__ void __launch_bounds__(256) conv1out_wgrad_strip_kernel(const float* __restrict__ g, const void* __restrict__ X, int64_t x_bs, int C,
+                                                                   float* __restrict__ dw, int64_t B, int64_t T, int spb, int S) {
+  __shared__ float4 red[7][KK][32];
+  __shared__ float redb[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t strip = (int64_t)blockIdx.x * 8 + w;
+  const bool active = 4 * lane < C;
+  float4 acc[KK];
+#pragma unroll
+  for (int j = 0; j < KK; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float gsum = 0.f;
+  if (strip < B * spb) {
+    const int64_t b = strip / spb;
+    const int64_t r0 = (strip - b * spb) * S, r1 = min(T + KK - 1, r0 + (int64_t)S);     // buffer rows of this strip
+    const float* gb = g + b * T;
+    const int64_t xb = b * x_bs + 4 * lane;
+    for (int64_t r = r0; r < r1; r += 8) {
+      float4 x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        x[i] = (active && r + i < r1) ? ldg4_any(X, xb + (r + i) * C, xdt) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float gv[8 + KK - 1];                            // gv[m] = g[r - (KK-1) + m], zero outside [0, T) and past the strip's rows
+#pragma unroll
+      for (int m = 0; m < 8 + KK - 1; ++m) {
+        const int64_t t = r - (KK - 1) + m;
+        gv[m] = (t >= 0 && t < T) ? __ldg(gb + t) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < KK; ++j) {                 // row r + i, tap j: output t = r + i - j -> gv[i - j + KK - 1]
+          const float gq = gv[i - j + KK - 1];
+          acc[j].x += gq * x[i].x; acc[j].y += gq * x[i].y; acc[j].z += gq * x[i].z; acc[j].w += gq * x[i].w;
+        }
+    }
+    // bias gradient: the outputs t in [r0, min(T, r1)) belong to this strip
+    for (int64_t t = r0 + lane; t < min(T, r1); t += 32) gsum += __ldg(gb + t);
+  }
+  gsum = warp_sum(gsum);
+  if (w > 0) {
+#pragma unroll
+    for (int j = 0; j < KK; ++j) red[w - 1][j][lane] = acc[j];
+  }
+  if (lane == 0) redb[w] = gsum;
+  __syncthreads();
+  if (w == 0) {
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < KK; ++j) {
+        float4 a = acc[j];
+#pragma unroll
+        for (int o = 0; o < 7; ++o) { const float4 v = red[o][j][lane]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+        float* q = dw + j * C + 4 * lane;
+        atomicAdd(q, a.x); atomicAdd(q + 1, a.y); atomicAdd(q + 2, a.z); atomicAdd(q + 3, a.w);
+      }
+    }
+    if (lane == 0) {
+      float sb = 0.f;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) sb += redb[o];
+      atomicAdd(dw + KK * C, sb);
+    }
   }
 }
 
@@ -425,6 +496,15 @@ int ag_conv1out_wgrad(const float* g, const void* X, int32_t x_dtype, int64_t x_
   AG_CHECK_ARG(g && X && dw && B > 0 && B < 65536 && T > 0 && C > 0 && C % 4 == 0 && C <= 508 && k > 0 && k <= 4 && x_bs % 4 == 0,
                "ag_conv1out_wgrad: bad args");
   AG_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & (x_dtype ? 7 : 15)) == 0, "ag_conv1out_wgrad: unaligned");
+  if (C <= 128 && k == 3) {
+    const int S = 128;
+    const int64_t spb = (T + k - 1 + S - 1) / S, strips = B * spb;
+    const unsigned gr = (unsigned)((strips + 7) / 8);
+    if (x_dtype) conv1out_wgrad_strip_kernel<3, 1><<<gr, 256, 0, (cudaStream_t)stream>>>(g, X, x_bs, (int)C, dw, B, T, (int)spb, S);
+    else conv1out_wgrad_strip_kernel<3, 0><<<gr, 256, 0, (cudaStream_t)stream>>>(g, X, x_bs, (int)C, dw, B, T, (int)spb, S);
+    AG_LAUNCH_CHECK();
+    return AG_OK;
+  }
   const int rpb = 512;
   dim3 grid((unsigned)((T + k - 1 + rpb - 1) / rpb), (unsigned)B);
   if (x_dtype) conv1out_wgrad_kernel<4, 1><<<grid, 128, 0, (cudaStream_t)stream>>>(g, X, x_bs, (int)C, k, dw, T, rpb);

@@ -509,6 +509,19 @@ def test_streaming_kernels_both_storage_types(dt):
     dw = T.zeros(k * Cn + 1, device="cuda")
     K.conv1out_wgrad(g.cuda(), X.to(dt).cuda(), (Tn + k - 1) * Cn, Cn, k, dw, B, Tn)
     assert rel(dw[:-1].view(k, Cn), wr.grad[0].t()) < 1e-5 and abs(float(dw[-1]) - float(g.sum())) < 1e-4
+    # the same three kernels at the dense buffer's width (C = 128: strip kernels, several strips per sample) and an odd length
+    B2, T2, C2 = 2, 301, 128
+    X2 = q(T.randn(B2, T2 + k - 1, C2))
+    w2, g2_ = T.randn(k * C2), T.randn(B2, T2)
+    y2 = T.empty(B2, T2, device="cuda")
+    K.conv1out_fwd(X2.to(dt).cuda(), (T2 + k - 1) * C2, C2, k, w2.cuda(), b.cuda(), y2, B2, T2)
+    wt2 = w2.view(k, C2).t().unsqueeze(0).clone().requires_grad_()
+    yr2 = F.conv1d(X2.permute(0, 2, 1), wt2, b)[:, 0]
+    assert rel(y2, yr2) < 1e-5
+    yr2.backward(g2_)
+    dw2 = T.zeros(k * C2 + 1, device="cuda")
+    K.conv1out_wgrad(g2_.cuda(), X2.to(dt).cuda(), (T2 + k - 1) * C2, C2, k, dw2, B2, T2)
+    assert rel(dw2[:-1].view(k, C2), wt2.grad[0].t()) < 1e-5 and abs(float(dw2[-1]) - float(g2_.sum())) < 1e-3
     # conv1in: Conv1d(1 -> C, k = 7, s = 2) + bias + LeakyReLU + mask on a zero-padded waveform, weight/bias gradient
     k, s, Co, L = 7, 2, 16, 60
     To = (L + s - 1) // s
