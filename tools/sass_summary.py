@@ -13,6 +13,7 @@ PAT = collections.OrderedDict([
     ("tcgen05.mma (UTC*MMA)", re.compile(r"\bUTC[A-Z0-9]*MMA")), ("tcgen05.ld (LDTM)", re.compile(r"\bLDTM")),
     ("tcgen05.st (STTM)", re.compile(r"\bSTTM")), ("tcgen05.cp (UTCCP)", re.compile(r"\bUTCCP")),
     ("TMA tensor load (UTMALDG)", re.compile(r"\bUTMALDG")), ("TMA tensor store (UTMASTG)", re.compile(r"\bUTMASTG")),
+    ("TMA L2 prefetch (UTMAPF)", re.compile(r"\bUTMAPF")),
     ("bulk copy (UBLKCP)", re.compile(r"\bUBLKCP")), ("mbarrier (SYNCS)", re.compile(r"\bSYNCS")),
     ("cluster barrier (UCGABAR)", re.compile(r"\bUCGABAR")), ("legacy mma.sync (HMMA)", re.compile(r"\bHMMA")),
     ("FFMA", re.compile(r"\bFFMA")), ("MUFU", re.compile(r"\bMUFU"))])
