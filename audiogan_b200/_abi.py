@@ -37,6 +37,11 @@ class GemmDesc(C.Structure):
     ]
 
 
+class PadEntry(C.Structure):
+    _fields_ = [("buf", C.c_void_p), ("B", C.c_int64), ("rows", C.c_int64), ("row_bytes", C.c_int64), ("head", C.c_int64),
+                ("tail0", C.c_int64)]
+
+
 class LstmDesc(C.Structure):
     _fields_ = [
         ("B", i32), ("T", i32), ("Tcap", i32), ("H", i32), ("ndir", i32), ("F", i32),
@@ -115,6 +120,7 @@ _PROTOS = {
     "ag_conv1out_wgrad": [vp, vp, i32, i64, i64, i32, vp, i64, i64, vp],
     "ag_copy3d": [vp, i64, i64, i64, vp, i64, i64, i64, i64, i64, i64, i32, i32, i32, vp],
     "ag_zero_pads": [vp, i64, i64, i64, i64, i64, vp],
+    "ag_zero_pads_multi": [vp, i32, vp],
     "ag_frames_to_slot": [vp, i32, i64, i64, i32, vp, i64, i64, i64, vp],
     "ag_rowgroup_sum": [vp, i32, vp, i64, i64, i64, vp],
     "ag_transpose_bct": [vp, vp, i64, i64, i64, i64, i64, i32, vp],

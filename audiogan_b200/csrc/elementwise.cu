@@ -401,6 +401,30 @@ __global__ void zero_pads_kernel(U* __restrict__ p, int64_t B, int64_t rows, int
   }
 }
 
+// Up to 8 buffers per launch (blockIdx.y = buffer): the conv stacks allocate 2-5 padded activation buffers per pass, and a 4 us
+// launch per buffer is all latency.  unit[e] = bytes per store (16 / 4 / 2, by alignment).
+struct PadBatch {
+  void* p[8];
+  long long B[8], rows[8], rowb[8], head[8], tail0[8];
+  int unit[8];
+};
+template <typename U>
+__device__ __forceinline__ void zero_pads_one(void* pv, int64_t B, int64_t rows, int64_t rowu, int64_t head, int64_t tail0) {
+  U* p = reinterpret_cast<U*>(pv);
+  const int64_t per = (head + rows - tail0) * rowu, total = B * per;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per, j = i - b * per;
+    const int64_t off = j < head * rowu ? j : tail0 * rowu + (j - head * rowu);
+    p[b * rows * rowu + off] = U{};
+  }
+}
+__global__ void zero_pads_multi_kernel(const PadBatch pb) {
+  const int e = blockIdx.y, u = pb.unit[e];
+  if (u == 16) zero_pads_one<uint4>(pb.p[e], pb.B[e], pb.rows[e], pb.rowb[e] / 16, pb.head[e], pb.tail0[e]);
+  else if (u == 4) zero_pads_one<uint32_t>(pb.p[e], pb.B[e], pb.rows[e], pb.rowb[e] / 4, pb.head[e], pb.tail0[e]);
+  else zero_pads_one<uint16_t>(pb.p[e], pb.B[e], pb.rows[e], pb.rowb[e] / 2, pb.head[e], pb.tail0[e]);
+}
+
 static inline int grid_for(int64_t n, int threads) {
   int64_t b = (n + threads - 1) / threads;
   int64_t cap = (int64_t)sm_count() * 16;
@@ -530,6 +554,26 @@ int ag_zero_pads(void* buf, int64_t B, int64_t rows, int64_t row_bytes, int64_t 
   if (unit == 16) zero_pads_kernel<uint4><<<grid_for(n, 256), 256, 0, s>>>(reinterpret_cast<uint4*>(buf), B, rows, row_bytes / 16, head, tail0);
   else if (unit == 4) zero_pads_kernel<uint32_t><<<grid_for(n, 256), 256, 0, s>>>(reinterpret_cast<uint32_t*>(buf), B, rows, row_bytes / 4, head, tail0);
   else zero_pads_kernel<uint16_t><<<grid_for(n, 256), 256, 0, s>>>(reinterpret_cast<uint16_t*>(buf), B, rows, row_bytes / 2, head, tail0);
+  AG_LAUNCH_CHECK();
+  return AG_OK;
+}
+int ag_zero_pads_multi(const ag_pad_entry* e, int32_t n, void* stream) {
+  AG_CHECK_ARG(e && n > 0 && n <= 8, "ag_zero_pads_multi: 1..8 entries");
+  PadBatch pb;
+  int64_t nmax = 0;
+  for (int i = 0; i < n; ++i) {
+    AG_CHECK_ARG(e[i].buf && e[i].B > 0 && e[i].rows > 0 && e[i].row_bytes > 0 && e[i].row_bytes % 2 == 0 && e[i].head >= 0 &&
+                     e[i].tail0 >= e[i].head && e[i].tail0 <= e[i].rows && (reinterpret_cast<uintptr_t>(e[i].buf) & 1) == 0,
+                 "ag_zero_pads_multi: bad entry %d", i);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(e[i].buf);
+    const int unit = (e[i].row_bytes % 16 == 0 && (a & 15) == 0) ? 16 : (e[i].row_bytes % 4 == 0 && (a & 3) == 0) ? 4 : 2;
+    pb.p[i] = e[i].buf; pb.B[i] = e[i].B; pb.rows[i] = e[i].rows; pb.rowb[i] = e[i].row_bytes; pb.head[i] = e[i].head;
+    pb.tail0[i] = e[i].tail0; pb.unit[i] = unit;
+    const int64_t cnt = e[i].B * (e[i].head + e[i].rows - e[i].tail0) * (e[i].row_bytes / unit);
+    if (cnt > nmax) nmax = cnt;
+  }
+  if (nmax == 0) return AG_OK;
+  zero_pads_multi_kernel<<<dim3((unsigned)grid_for(nmax, 256), (unsigned)n), 256, 0, (cudaStream_t)stream>>>(pb);
   AG_LAUNCH_CHECK();
   return AG_OK;
 }

@@ -1605,6 +1605,13 @@ int ag_gemm_nt_tc(const ag_gemm_desc* d, void* stream) {
     const int64_t want = (int64_t)sm_count() * 2 / 3;
     while (bn > 16 && row_tiles * ((d->N + bn - 1) / bn) < want && row_tiles <= 8) bn >>= 1;
   }
+  // N = 384 (the widest generator data gradient, 4 x 96 prefix channels): two 256-column tiles leave the second half empty and cost
+  // its MMAs and B loads anyway; three 128-column tiles are exact (AUDIOGAN_BN_EXACT=0: A/B knob)
+  {
+    static int exact = -1;
+    if (exact < 0) { const char* e = getenv("AUDIOGAN_BN_EXACT"); exact = (e && e[0] == '0') ? 0 : 1; }
+    if (exact && bn == 256 && d->N > 256 && d->N <= 512 && d->N % 256 != 0 && d->N % 256 <= 128 && d->N % 128 == 0) bn = 128;
+  }
   if (bn == 256) { AG_TC_NT(256); }
   if (bn == 128) { AG_TC_NT(128); }
   if (bn == 64) { AG_TC_NT(64); }

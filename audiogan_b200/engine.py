@@ -170,14 +170,11 @@ class _GenFn(torch.autograd.Function):
             # x_{-1}) and the row past the end have to be zero -- not the whole buffers (76 MB of fills at B = 128)
             hbuf = _empty(B, Tcap + 2, H, device=dev)
             xbuf = _empty(B, Tcap + 1, F, device=dev)
-            K.zero_pads(hbuf, 1, Tcap + 1)
-            K.zero_pads(xbuf, 1, Tcap + 1)
             hbuf16 = xbuf16 = None
             if bf:
                 hbuf16 = torch.empty(B, Tcap + 2, H, device=dev, dtype=torch.bfloat16)
                 xbuf16 = torch.empty(B, Tcap + 1, F, device=dev, dtype=torch.bfloat16)
-                K.zero_pads(hbuf16, 1, Tcap + 1)
-                K.zero_pads(xbuf16, 1, Tcap + 1)
+            K.zero_pads_multi([(t, 1, Tcap + 1) for t in (hbuf, xbuf, hbuf16, xbuf16) if t is not None])    # one launch
         else:
             hbuf = _zeros(B, Tcap + 2, H, device=dev)
             xbuf = _zeros(B, Tcap + 1, F, device=dev)
@@ -229,7 +226,8 @@ class _GenFn(torch.autograd.Function):
             """frames -> dense buffer -> the four bottleneck blocks -> final conv, for samples [b0, b1) (batch-major buffers)"""
             n = b1 - b0
             Xs, xb = Xd[b0:b1], xbuf[b0:b1]
-            K.zero_pads(Xs, GPAD, GPAD + L)
+            # the pad rows of the dense buffer and of the four hidden activations: one launch
+            K.zero_pads_multi([(Xs, GPAD, GPAD + L)] + [(hh[li][b0:b1], 1, L // s_ + 1) for li, (_, s_, _, _) in enumerate(struct)])
             # frames -> channel 0 of the waveform slot, its pad channels zeroed in the same pass
             K.frames_to_slot((Xs, GPAD * CT), Lp * CT, CT, plan.coff[0], (xb, F), (Tcap + 1) * F, n, L)
             lenL = plan.const_len(n, L)
@@ -237,7 +235,6 @@ class _GenFn(torch.autograd.Function):
                 p, pd, Lh = (k - 1) // 2, s // 2, L // s
                 cin = plan.cinp[li]                             # padded channel prefix this block reads == slot it writes
                 Hh = hh[li][b0:b1]
-                K.zero_pads(Hh, 1, Lh + 1)
                 # TMA-fed kernel over a 4-D tensor map (channel prefix, row, tap, batch).  Its boxes have 16-byte inner rows, so
                 # for wide prefixes the producer-warp kernel is faster (measured: cin 8 / 24 -> 1.9x / 1.5x faster, 56 equal, 88 0.6x)
                 # (plan.alay 1).  Prefixes of 32 channels and more use 128-byte boxes (plan.alay 2: one tap's 64-channel group per box).
@@ -311,6 +308,8 @@ class _GenFn(torch.autograd.Function):
 
             if wgrad:
                 wjob(lambda: K.conv1out_wgrad(gx, (Xd, (GPAD - 1) * CT), Lp * CT, CT, 3, plan.GPoff("f.w"), B, L))
+            dHs = [_empty(B, L // s_ + 2, hid_, device=dev, dtype=adt) for (_, s_, hid_, _) in struct]
+            K.zero_pads_multi([(t, 1, t.shape[1] - 1) for t in dHs])            # pad rows of the four hidden gradients: one launch
             for li in range(len(struct) - 1, -1, -1):
                 k, s, hid, out = struct[li]
                 cin = plan.cinp[li]
@@ -327,8 +326,7 @@ class _GenFn(torch.autograd.Function):
                 if wgrad and not fuse_b:
                     K.colsum((dyl, pd * out), (L + 2 * pd) * out, out, B, L, out, plan.GPoff("d%d.b" % li))
                 # transposed-conv data gradient = strided conv over dyl, times lrelu'(hidden)
-                dH = _empty(B, Lh + 2, hid, device=dev, dtype=adt)
-                K.zero_pads(dH, 1, Lh + 1)
+                dH = dHs[li]
                 K.gemm_nt(B * Lh, hid, kd * out, dyl, (Lh, (L + 2 * pd) * out, s * out), plan.Poff("d%d.wg" % li), kd * out,
                           (dH, hid), (Lh, (Lh + 2) * hid, hid), dact=(Hh, hid))
                 if wgrad:
@@ -438,10 +436,14 @@ class _DiscCNNFn(torch.autograd.Function):
         K.frame_noise(a0, L + 2 * DPAD, DPAD, x, L, None, 0.0, B, L)
         acts, Ts = [a0], [L]
         cin, Tin = 1, L
+        outs, Tq = [], L
+        for (k, s, cout) in struct:
+            Tq = (Tq + s - 1) // s
+            outs.append(_empty(B, Tq + 2 * DPAD, cout, device=dev, dtype=_adt(plan)))
+        K.zero_pads_multi([(o, DPAD, o.shape[1] - DPAD) for o in outs])         # every layer's pad rows: one launch per 8 layers
         for i, (k, s, cout) in enumerate(struct):
             Tout = (Tin + s - 1) // s
-            a = _empty(B, Tout + 2 * DPAD, cout, device=dev, dtype=_adt(plan))
-            K.zero_pads(a, DPAD, DPAD + Tout)
+            a = outs[i]
             if cin == 1 and k <= 8 and cout % 4 == 0 and (k - 1) // 2 == DPAD:
                 # first layer on the raw waveform: K = k, a stream over the output (direct HBM kernel, fp32 arithmetic)
                 K.conv1in_fwd(acts[-1], Tin + 2 * DPAD, plan.Poff("c%d.w" % i), plan.Poff("c%d.b" % i), (a, DPAD * cout),
@@ -554,11 +556,8 @@ class _DiscTailFn(torch.autograd.Function):
         bf = plan.mode == "bf16"
         Tmin = max(0, min(int(Tmin), Tm))
         hbuf = _empty(B, Tm + 2, 2 * H, device=dev)
-        K.zero_pads(hbuf, 1, Tmin + 1)
-        hbuf16 = None
-        if bf:
-            hbuf16 = torch.empty(B, Tm + 2, 2 * H, device=dev, dtype=torch.bfloat16)
-            K.zero_pads(hbuf16, 1, Tmin + 1)
+        hbuf16 = torch.empty(B, Tm + 2, 2 * H, device=dev, dtype=torch.bfloat16) if bf else None
+        K.zero_pads_multi([(t, 1, Tmin + 1) for t in (hbuf, hbuf16) if t is not None])
         gates = _empty(B, Tm, 8 * H, device=dev)
         cbuf = _empty(B, Tm, 2 * H, device=dev)
         misc = torch.zeros(16, device=dev, dtype=torch.int32)

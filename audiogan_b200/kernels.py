@@ -216,6 +216,19 @@ def zero_pads(buf, head, tail0):
     A.call("ag_zero_pads", addr(buf), Bn, rows, rb, head, tail0, A.stream())
 
 
+def zero_pads_multi(items):
+    """items: [(buf, head, tail0), ...] as for zero_pads -- one launch per 8 buffers."""
+    for i0 in range(0, len(items), 8):
+        chunk = items[i0:i0 + 8]
+        arr = (A.PadEntry * len(chunk))()
+        for e, (buf, head, tail0) in zip(arr, chunk):
+            if not buf.is_contiguous():
+                raise ValueError("zero_pads needs a contiguous [B, rows, ...] buffer")
+            e.buf, e.B, e.rows = buf.data_ptr(), buf.shape[0], buf.shape[1]
+            e.row_bytes, e.head, e.tail0 = buf[0, 0].numel() * buf.element_size(), head, tail0
+        A.call("ag_zero_pads_multi", C.cast(arr, C.c_void_p), len(chunk), A.stream())
+
+
 def rowgroup_sum(src, out, B, T, N):
     A.call("ag_rowgroup_sum", addr(src), _dtype_of(src), addr(out), B, T, N, A.stream())
 

@@ -322,6 +322,9 @@ int ag_frames_to_slot(void* dst, int32_t dst_dtype, int64_t d_bs, int64_t d_rs, 
  * padding every conv view relies on, audiogan.py:272 / :490 `padding=`): one launch instead of two strided fills.
  * 16-byte stores when row_bytes % 16 == 0 and buf is 16-byte aligned, else 4- / 2-byte stores (row_bytes % 2 == 0). */
 int ag_zero_pads(void* buf, int64_t B, int64_t rows, int64_t row_bytes, int64_t head, int64_t tail0, void* stream);
+/* The same for up to 8 buffers in ONE launch (a conv stack allocates 2-5 padded activation buffers per pass; `e` is a host array). */
+typedef struct { void* buf; int64_t B, rows, row_bytes, head, tail0; } ag_pad_entry;
+int ag_zero_pads_multi(const ag_pad_entry* e, int32_t n, void* stream);
 /* out[b, n] = sum_t in[b, t, n]; in: dtype 0 fp32 / 1 bf16 (N even) */
 int ag_rowgroup_sum(const void* in, int32_t dtype, float* out, int64_t B, int64_t T, int64_t N, void* stream);
 /* dst[b, t, c] (channel-last, row stride dst_rs, batch stride dst_bs) <-> src[b, c, t] */
