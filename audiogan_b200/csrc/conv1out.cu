@@ -329,6 +329,32 @@ __global__ void __launch_bounds__(256) conv1in_wgrad_kernel(const void* __restri
       for (int e = 0; e < 4; ++e) acc[e][KMAX] += gv[e];
     }
   }
+  if ((C4 & (C4 - 1)) == 0 && C4 <= 8) {
+    // C <= 32 channels (the default first layer has 16): lanes with the same channel group meet by shuffles, the 8 warps in shared
+    // memory, one atomic per value and block.  (The generic path below runs 4 (k + 1) block reductions with a serial 256/C4-term
+    // sum each: ~30 us per block at C4 = 4.)
+    __shared__ float sred[8][4 * (KMAX + 1) * 8];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int j = 0; j <= KMAX; ++j) {
+        float v = acc[e][j];
+        for (int o = C4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane < C4) sred[wp][(e * (KMAX + 1) + j) * C4 + lane] = v;
+      }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 4 * (KMAX + 1) * C4; idx += 256) {
+      const int cc = idx % C4, ej = idx / C4, e = ej / (KMAX + 1), j = ej - e * (KMAX + 1);
+      if (j < k || j == KMAX) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += sred[q][idx];
+        atomicAdd(dw + (4 * cc + e) * (k + 1) + (j == KMAX ? k : j), v);
+      }
+    }
+    return;
+  }
   // block reduction over the row lanes, one value at a time (k + 1 values x 4 channels), then one atomic per value
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -388,11 +414,21 @@ __global__ void __launch_bounds__(256) wcolsum_kernel(const float* __restrict__ 
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   float gs = 0.f;
   if (rl < nrl)
-    for (int64_t m = m0 + rl; m < m1; m += nrl) {
-      const float gv = __ldg(g + m);
-      const float4 x = ldg4_any(X, m * (4 * K4) + 4 * c4, xdt);
-      a.x += gv * x.x; a.y += gv * x.y; a.z += gv * x.z; a.w += gv * x.w;
-      gs += gv;
+    for (int64_t m = m0 + rl; m < m1; m += 4 * nrl) {      // 4 rows of this thread in flight (K = 512: only 2 row lanes per block)
+      float4 x[4];
+      float gv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t mm = m + (int64_t)i * nrl;
+        const bool ok = mm < m1;
+        gv[i] = ok ? __ldg(g + mm) : 0.f;
+        x[i] = ok ? ldg4_any(X, mm * (4 * K4) + 4 * c4, xdt) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a.x += gv[i] * x[i].x; a.y += gv[i] * x[i].y; a.z += gv[i] * x[i].z; a.w += gv[i] * x[i].w;
+        gs += gv[i];
+      }
     }
   red[threadIdx.x] = a;
   __syncthreads();

@@ -585,7 +585,9 @@ def test_cuda_graph_step_equals_eager_step():
     assert gs.launches > 100
     lg = [gs.run(batches[i])["losses"].clone().cpu() for i in (1, 2, 3)]
     for a, b in zip(le, lg):
-        assert float((a - b).abs().max()) < 2e-6, (a, b)
+        # the two runs differ in the order of their atomic sums only; an RMSprop step is sign-like, so a parameter whose gradient is
+        # rounding noise may step the other way (bounded below) and the losses of steps 2-3 move by a few 1e-6 (observed <= 2.7e-6)
+        assert float((a - b).abs().max()) < 5e-6, (a, b)
     for (k, p), (_, q) in zip(list(g1.named_parameters()) + list(d1.named_parameters()),
                               list(g2.named_parameters()) + list(d2.named_parameters())):
         if not noise_only(k):
