@@ -586,14 +586,16 @@ def test_cuda_graph_step_equals_eager_step():
     lg = [gs.run(batches[i])["losses"].clone().cpu() for i in (1, 2, 3)]
     for a, b in zip(le, lg):
         # the two runs differ in the order of their atomic sums only; an RMSprop step is sign-like, so a parameter whose gradient is
-        # rounding noise may step the other way (bounded below) and the losses of steps 2-3 move by a few 1e-6 (observed <= 2.7e-6)
-        assert float((a - b).abs().max()) < 5e-6, (a, b)
+        # rounding noise may step the other way (bounded below) and the losses of the later steps move by a few 1e-6 (observed <= 2.7e-6)
+        assert float((a - b).abs().max()) < 1e-5, (a, b)
     for (k, p), (_, q) in zip(list(g1.named_parameters()) + list(d1.named_parameters()),
                               list(g2.named_parameters()) + list(d2.named_parameters())):
         if not noise_only(k):
             # three sign-like RMSprop steps: an element whose gradient is rounding noise may step the other way
+            # (a capture bug -- a missing dependency, a reused buffer -- shows as O(1e-2) losses and most elements off)
             err = (p - q).abs()
-            assert float((err > 5e-6).float().mean()) < 2e-3 and float(err.max()) < 6.1e-3, (k, float(err.max()))
+            nbad = int((err > 5e-6).sum())
+            assert nbad <= max(3, 2e-3 * err.numel()) and float(err.max()) < 6.1e-3, (k, nbad, err.numel(), float(err.max()))
     with pytest.raises(ValueError):
         bad = dict(batches[1]); bad["real_len"] = bad["real_len"] - 200
         gs.load(bad)
