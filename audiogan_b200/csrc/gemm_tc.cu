@@ -1450,15 +1450,23 @@ __global__ void __launch_bounds__(256) tn_bias_kernel(const __nv_bfloat16* __res
       }
     }
   }
+  // row lanes with the same column group: shuffles inside a warp (cx = lane & (ncg - 1)), then the 8 warps through shared memory
+  // (a serial 256/ncg-term sum per value by ncg threads took longer than the loads: 8 us of a 16 us launch at N = 32)
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = acc[e];
+  for (int e = 0; e < 8; ++e) {
+    float v = acc[e];
+    for (int o = ncg; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane < ncg) red[wp * 32 + lane][e] = v;
+  }
   __syncthreads();
-  if (ry == 0 && n < N) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
+  for (int idx = threadIdx.x; idx < 8 * ncg; idx += 256) {
+    const int c = idx >> 3, e = idx & 7, nn = (blockIdx.x * ncg + c) * 8;
+    if (nn < N) {
       float v = 0.f;
-      for (int i = 0; i < nrl; ++i) v += red[i * ncg + cx][e];
-      atomicAdd(&out[(int64_t)(n + e) * ldw], v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v += red[q * 32 + c][e];
+      atomicAdd(&out[(int64_t)(nn + e) * ldw], v);
     }
   }
 }
